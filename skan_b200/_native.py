@@ -1,0 +1,105 @@
+"""ctypes binding of the C-ABI library ``libskan_b200.so`` (declared in include/skan_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a) into
+``skan_b200/lib/``.  There is no CPU implementation behind this module: if the library is
+missing, or no CUDA device is visible, using the package raises.  torch tensors are the
+only array interop -- every pointer argument is ``tensor.data_ptr()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libskan_b200.so')
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); mirrors include/skan_b200.h
+_SIGNATURES = {
+    'skb_abi_version': (_int, []),
+    'skb_last_error': (ctypes.c_char_p, []),
+    'skb_scan_scratch_bytes': (_i64, [_i64]),
+    'skb_tile_voxels': (_i64, []),
+    'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
+    'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp]),
+    'skb_junction_edge_count': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_junction_edge_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int,
+                                      _vp, _vp, _vp, _vp, _vp]),
+    'skb_mst_junctions': (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_mst_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_degrees_indptr': (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    'skb_csr_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp]),
+    'skb_components': (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_rank_arcs': (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    'skb_path_count': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'skb_path_starts': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'skb_path_emit': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'skb_path_stats': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'skb_branch_table': (_int, [_i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _vp, _vp, _vp]),
+    'skb_path_label_image': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_scan_u32': (_int, [_vp, _vp, _i64, _vp, _vp]),
+    'skb_scan_u64': (_int, [_vp, _vp, _i64, _vp, _vp]),
+}
+
+EXPORTS = tuple(sorted(_SIGNATURES))
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Library:
+    """A loaded C-ABI library; every call checks the status code."""
+
+    def __init__(self, path, *, device_type='cuda'):
+        self.path = path
+        self.device_type = device_type
+        self._dll = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(self._dll, name)
+            fn.restype = res
+            fn.argtypes = args
+        if self._dll.skb_abi_version() != 1:
+            raise NativeError(f'{path}: unexpected ABI version')
+        self.tile_voxels = int(self._dll.skb_tile_voxels())
+        self.launches = 0
+
+    def scan_scratch_bytes(self, n):
+        return int(self._dll.skb_scan_scratch_bytes(int(n)))
+
+    def call(self, name, *args):
+        status = getattr(self._dll, name)(*args)
+        self.launches += 1
+        if status < 0:
+            msg = self._dll.skb_last_error().decode('utf-8', 'replace')
+            raise NativeError(f'{name} failed ({status}): {msg}')
+        return status
+
+
+_lib = None
+
+
+def library():
+    """The CUDA library, loaded on first use.  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a). skan_b200 has no CPU fallback.')
+        _lib = Library(LIB_PATH, device_type='cuda')
+    return _lib
+
+
+def _install_library_for_tests(lib):
+    """tests/ only: route the package through another Library (the host emulation harness of
+    tests/emul) so that host-side logic can be unit-tested in a container without a GPU."""
+    global _lib
+    old = _lib
+    _lib = lib
+    return old

@@ -1,0 +1,270 @@
+"""Host-side sequencing of the sm_100a kernels: skeleton image -> pixel graph -> junction MST
+-> CSR -> paths -> per-path statistics -> branch table.
+
+Every array lives in a torch tensor on the image's device; the kernels are reached through
+the C-ABI (skan_b200/_native.py).  The host only allocates (count -> allocate -> fill) and
+reads back the handful of counts that size the next allocation (N, junction edges, E, P, L).
+
+Reference stages replaced (relative to /root/reference/src/skan):
+  csr.py:1070,122-123,131  -> pack_count + scan + emit_nodes     (mask sweep, raster node ids)
+  csr.py:127-157           -> raw_neighbors (+ csr_emit)         (3^d stencil, CSR)
+  csr.py:980-1020          -> junction_edge_* + mst_*            (junction MST)
+  csr.py:347-446           -> components + rank_arcs + path_*    (path tracing)
+  csr.py:962-977, 792-816  -> path_stats                          (distance, mean, stdev)
+  csr.py:909-952           -> branch_table                        (summarize columns)
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _native
+
+# torch dtype -> element code of skb_items.cuh
+_DT = {
+    torch.bool: 0, torch.uint8: 0, torch.int8: 1, torch.int16: 3, torch.int32: 5, torch.int64: 7,
+    torch.float32: 8, torch.float64: 9,
+}
+for _name, _code in (('uint16', 2), ('uint32', 4), ('uint64', 6)):
+    if hasattr(torch, _name):
+        _DT[getattr(torch, _name)] = _code
+
+_NP_DT = {
+    np.dtype(np.bool_): 0, np.dtype(np.uint8): 0, np.dtype(np.int8): 1, np.dtype(np.uint16): 2,
+    np.dtype(np.int16): 3, np.dtype(np.uint32): 4, np.dtype(np.int32): 5, np.dtype(np.uint64): 6,
+    np.dtype(np.int64): 7, np.dtype(np.float32): 8, np.dtype(np.float64): 9,
+}
+_ESIZE = {0: 1, 1: 1, 2: 2, 3: 2, 4: 4, 5: 4, 6: 8, 7: 8, 8: 4, 9: 8}
+
+PACK_VARIANT = {'ldg': 0, 'tma': 1}
+default_pack_variant = 'ldg'
+
+
+def neighbour_weights(ndim, spacing):
+    """fp64 weight of each of the 27 neighbour codes k27 = (dz+1)*9+(dy+1)*3+(dx+1) for an image
+    embedded as (nz, ny, nx).  The arithmetic is nputil.py:278-279 verbatim in NumPy, evaluated
+    on the ndim real axes with spacing = ones(ndim) * spacing (csr.py:1072), so the bits equal
+    the reference's edge weights."""
+    spacing = np.ones(ndim, dtype=float) * spacing
+    grids = np.meshgrid(*([np.arange(-1, 2)] * 3), indexing='ij')
+    offs3 = np.stack([g.ravel() for g in grids], axis=-1)          # (27, 3), k27 order
+    offs = offs3[:, 3 - ndim:]
+    weighted = offs * spacing
+    dist = np.sqrt(np.sum(weighted**2, axis=1))
+    dist[np.any(offs3[:, :3 - ndim] != 0, axis=1)] = 0.0            # codes outside the real axes: unused
+    return np.ascontiguousarray(dist, dtype=np.float64)
+
+
+class _Ctx:
+    """Allocation + call helper bound to one device and stream."""
+
+    def __init__(self, device):
+        self.lib = _native.library()
+        self.device = torch.device(device)
+        if self.lib.device_type == 'cuda':
+            if self.device.type != 'cuda':
+                raise _native.NativeError('skan_b200 runs on CUDA devices only (no CPU fallback); got ' + str(device))
+            self.stream = torch.cuda.current_stream(self.device).cuda_stream
+        else:  # host emulation harness injected by tests/
+            if self.device.type != 'cpu':
+                raise _native.NativeError('emulation library expects CPU tensors')
+            self.stream = 0
+        self._scratch = None
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def scratch(self, n):
+        need = self.lib.scan_scratch_bytes(n)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = self.empty(max(need, 1 << 16), torch.uint8)
+        return self._scratch.data_ptr()
+
+    def call(self, name, *args):
+        conv = [a.data_ptr() if isinstance(a, torch.Tensor) else (0 if a is None else a) for a in args]
+        return self.lib.call(name, *conv, self.stream)
+
+
+def _as_device_image(image, device):
+    """-> (tensor on device viewed through a supported dtype, element code, shape, numpy dtype)."""
+    if isinstance(image, torch.Tensor):
+        t = image
+        if t.dtype not in _DT:
+            raise TypeError(f'unsupported skeleton image dtype {t.dtype}')
+        code = _DT[t.dtype]
+        np_dtype = np.dtype(str(t.dtype).replace('torch.', '')) if t.dtype != torch.bool else np.dtype(bool)
+        shape = tuple(t.shape)
+        t = t.to(device, non_blocking=True).contiguous()
+    else:
+        arr = np.asarray(image)
+        if arr.dtype not in _NP_DT:
+            if arr.dtype == np.float16:
+                arr = arr.astype(np.float32)
+            else:
+                raise TypeError(f'unsupported skeleton image dtype {arr.dtype}')
+        code = _NP_DT[arr.dtype]
+        np_dtype = arr.dtype
+        shape = arr.shape
+        arr = np.ascontiguousarray(arr)
+        t = torch.from_numpy(arr.reshape(-1).view(np.uint8)).to(device, non_blocking=True)
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t, code, shape, np_dtype
+
+
+def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant=None):
+    """skeleton_to_csgraph on the device (csr.py:1028-1089): returns a namespace of device tensors
+    (coords int64 (N,d), values fp64 (N,) | None, indptr/indices int32, data fp64, degrees int32)."""
+    ctx = _Ctx(device)
+    img, code, shape, np_dtype = _as_device_image(image, ctx.device)
+    ndim = len(shape)
+    if ndim < 1 or ndim > 3:
+        raise NotImplementedError('skan_b200 supports 1-D, 2-D and 3-D skeleton images')
+    V = int(np.prod(shape, dtype=np.int64))
+    is_bool = np_dtype == np.dtype(bool)
+    wtab_np = neighbour_weights(ndim, spacing)
+    shape_t = torch.tensor(list(shape), dtype=torch.int64)  # host: read by the C side only
+    tile = ctx.lib.tile_voxels
+    ntiles = max(1, -(-V // tile))
+    variant = PACK_VARIANT[pack_variant or default_pack_variant]
+
+    g = SimpleNamespace(ctx=ctx, shape=tuple(shape), ndim=ndim, np_dtype=np_dtype, dtype_code=code,
+                        spacing=spacing, value_is_height=bool(value_is_height), nvox=V)
+    # --- mask sweep: 1 bit / voxel + per-tile counts, then the tile prefix ------------------
+    store = ctx.empty(ntiles * 256 + 2, torch.int64)
+    store[0] = 0
+    store[-1] = 0
+    bits = store[1:-1]
+    tile_prefix = ctx.empty(ntiles + 1, torch.int32)
+    if V > 0:
+        ctx.call('skb_pack_count', img, code, V, bits, tile_prefix, ntiles, variant)
+    else:
+        bits.zero_()
+        tile_prefix.zero_()
+    ctx.call('skb_scan_u32', tile_prefix, tile_prefix, ntiles, ctx.scratch(ntiles))
+    N = int(tile_prefix[ntiles].item())
+    g.n_nodes = N
+    g.bits = bits
+    g._bits_store = store
+    # --- nodes in raster order ---------------------------------------------------------------
+    lin = ctx.empty(N, torch.int64)
+    coords = ctx.empty((N, ndim), torch.int64)
+    values = None if is_bool else ctx.empty(N, torch.float64)
+    pre256 = ctx.empty(ntiles * 64, torch.int32)
+    ctx.call('skb_emit_nodes', bits, tile_prefix, ntiles, ndim, shape_t.data_ptr(), img, code, lin, coords,
+             values, pre256)
+    g.lin, g.coords, g.values, g.pre256 = lin, coords, values, pre256
+    if value_is_height and values is None:
+        # the reference subtracts booleans here, which NumPy refuses (csr.py:1024)
+        raise TypeError('value_is_height needs a numeric (non-boolean) skeleton image')
+    wtab = torch.from_numpy(wtab_np).to(ctx.device)
+    g.wtab = wtab
+    geom = (ndim, shape_t.data_ptr())
+    # --- raw neighbourhood masks ---------------------------------------------------------------
+    nb = ctx.empty(N, torch.int32)
+    ctx.call('skb_raw_neighbors', bits, *geom, lin, N, nb)
+    # --- junction MST ----------------------------------------------------------------------------
+    jcount = ctx.empty(N + 1, torch.int32)
+    ctx.call('skb_junction_edge_count', bits, pre256, *geom, lin, nb, N, jcount)
+    ctx.call('skb_scan_u32', jcount, jcount, N, ctx.scratch(N))
+    nej = int(jcount[N].item())
+    g.n_junction_edges = nej
+    height = 1 if value_is_height else 0
+    if nej:
+        ea = ctx.empty(nej, torch.int32)
+        eb = ctx.empty(nej, torch.int32)
+        ek = ctx.empty(nej, torch.uint8)
+        ew = ctx.empty(nej, torch.int64)
+        ctx.call('skb_junction_edge_emit', bits, pre256, *geom, lin, nb, jcount, N, wtab, values, height, code,
+                 ea, eb, ek, ew)
+        par = ctx.empty(N, torch.int32)
+        bestw = ctx.empty(N, torch.int64)
+        beste = ctx.empty(N, torch.int32)
+        era = ctx.empty(nej, torch.int32)
+        erb = ctx.empty(nej, torch.int32)
+        tree = ctx.empty(nej, torch.uint8)
+        flag = ctx.empty(1, torch.int32)
+        g.mst_rounds = ctx.call('skb_mst_junctions', ea, eb, ew, nej, N, par, bestw, beste, era, erb, tree, flag)
+        keep = nb.clone()
+        ctx.call('skb_mst_apply', ea, eb, ek, tree, nej, keep)
+        g.raw_nb = nb
+    else:
+        g.mst_rounds = 0
+        keep = nb
+        g.raw_nb = nb
+    # --- final CSR ---------------------------------------------------------------------------------
+    deg = ctx.empty(N, torch.int32)
+    indptr = ctx.empty(N + 1, torch.int32)
+    ctx.call('skb_degrees_indptr', keep, N, deg, indptr, ctx.scratch(N))
+    E = int(indptr[N].item())
+    indices = ctx.empty(E, torch.int32)
+    data = ctx.empty(E, torch.float64)
+    ctx.call('skb_csr_emit', bits, pre256, *geom, lin, keep, indptr, N, wtab, values, height, code, indices, data)
+    g.keep, g.degrees, g.indptr, g.indices, g.data, g.n_edges = keep, deg, indptr, indices, data, E
+    g._keepalive = (img, shape_t)
+    return g
+
+
+def trace_paths(ctx, indptr, indices, values, n_nodes, n_edges):
+    """_build_skeleton_path_graph on the device (csr.py:412-446) plus the component labels that
+    summarize needs (csr.py:909).  Raises ValueError when there is no path, like the reference's
+    csr_matrix constructor does at csr.py:442."""
+    N, E = n_nodes, n_edges
+    p = SimpleNamespace()
+    par = ctx.empty(max(N, 1), torch.int32)
+    hast = ctx.empty(max(N, 1), torch.uint8)
+    label = ctx.empty(max(N, 1), torch.int32)
+    ntype = ctx.empty(max(N, 1), torch.uint8)
+    root_rank = ctx.empty(N + 1, torch.int32)
+    ctx.call('skb_components', indptr, indices, N, par, hast, label, ntype, root_rank, ctx.scratch(N))
+    arcs = ctx.empty((max(E, 1), 2), torch.int32)
+    flag = ctx.empty(1, torch.int32)
+    p.rank_rounds = ctx.call('skb_rank_arcs', indptr, indices, ntype, N, E, arcs, flag)
+    pcount = ctx.empty(N + 1, torch.int64)
+    ctx.call('skb_path_count', indptr, ntype, arcs, N, pcount, ctx.scratch(N))
+    tot = int(pcount[N].item())
+    n_regular, n_cycles = tot & 0xffffffff, tot >> 32
+    P = n_regular + n_cycles
+    p.label, p.ntype, p.root_rank, p.n_paths, p.n_cycles = label, ntype, root_rank, P, n_cycles
+    if P == 0:
+        raise ValueError('index pointer size 0 should be 1')
+    start_node = ctx.empty(P, torch.int32)
+    pindptr = ctx.empty(P + 1, torch.int32)
+    einfo = ctx.empty((max(E, 1), 2), torch.int32)
+    ctx.call('skb_path_starts', indptr, ntype, arcs, pcount, N, E, n_regular, P, start_node, pindptr, einfo,
+             ctx.scratch(P))
+    L = int(pindptr[P].item())
+    pidx = ctx.empty(L, torch.int32)
+    pdata = ctx.empty(L, torch.float64)
+    ctx.call('skb_path_emit', indices, arcs, einfo, pindptr, start_node, values, E, pidx, pdata)
+    p.indptr, p.indices, p.data, p.n_entries = pindptr, pidx, pdata, L
+    return p
+
+
+def path_stats(ctx, gindptr, gindices, gdata, p, *, dist=True, mean=True, stdev=True):
+    P = p.n_paths
+    out = [ctx.empty(P, torch.float64) if want else None for want in (dist, mean, stdev)]
+    ctx.call('skb_path_stats', gindptr, gindices, gdata, p.indptr, p.indices, p.data, P, *out)
+    return out
+
+
+def branch_table(ctx, p, gindptr, coords, values, spacing, ndim, value_is_height):
+    """Device columns of summarize (csr.py:909-952): three SoA buffers (int32, int64, fp64)."""
+    P = p.n_paths
+    height = 1 if value_is_height else 0
+    sp = np.asarray(spacing)
+    if sp.ndim == 0:
+        sp = np.full(ndim, sp)
+    sp_is_int = sp.dtype.kind in 'iub'
+    sp_f = torch.from_numpy(np.ascontiguousarray(sp, dtype=np.float64))
+    sp_i = torch.from_numpy(np.ascontiguousarray(sp.astype(np.int64) if sp_is_int else np.ones(ndim, np.int64)))
+    dh = ndim + height
+    o32 = ctx.empty((3, P), torch.int32)
+    o64 = ctx.empty((1 + 2 * ndim, P), torch.int64)
+    of = ctx.empty((2 * dh + 1, P), torch.float64)
+    ctx.call('skb_branch_table', P, ndim, height, 1 if sp_is_int else 0, sp_f.data_ptr(), sp_i.data_ptr(),
+             p.indptr, p.indices, gindptr, p.label, p.root_rank, coords, values, o32, o64, of)
+    return o32, o64, of, sp_is_int

@@ -1,0 +1,364 @@
+"""Drop-in mirror of ``skan.csr`` for the skeleton-to-graph hot path, computed on a B200.
+
+Same names, signatures, attribute dtypes and error behaviour as the reference
+(/root/reference/src/skan/csr.py): ``Skeleton`` (csr.py:565-858), ``summarize`` (csr.py:861-959),
+``skeleton_to_csgraph`` (csr.py:1028-1089) and ``PathGraph`` (csr.py:449-551).  All numeric
+work runs in the sm_100a kernels behind the C-ABI (see _pipeline.py); this module only wraps
+device results in the SciPy / pandas containers the reference returns.  Host copies are made
+lazily, the first time an attribute is read.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import torch
+from scipy import sparse
+
+from . import _native, _pipeline
+
+
+def _default_device():
+    lib = _native.library()
+    if lib.device_type != 'cuda':
+        return torch.device('cpu')  # host emulation harness installed by tests/
+    if not torch.cuda.is_available():
+        raise _native.NativeError('skan_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _device_of(image):
+    if isinstance(image, torch.Tensor) and image.device.type == 'cuda':
+        return image.device
+    return _default_device()
+
+
+def _to_host(t):
+    return t.cpu().numpy()
+
+
+def skeleton_to_csgraph(skel, *, spacing=1, value_is_height=False):
+    """Convert a skeleton image of thin lines to a graph of neighbor pixels (csr.py:1028-1089).
+
+    Returns ``(graph, pixel_coordinates)``: a ``scipy.sparse.csr_matrix`` of shape (N, N) with
+    fp64 distances (int32 index arrays, sorted columns) and a tuple of ndim int64 coordinate
+    arrays, node ids being 0-based raster ranks of the nonzero pixels.
+    """
+    g = _pipeline.pixel_graph(skel, spacing=spacing, value_is_height=value_is_height, device=_device_of(skel))
+    n = g.n_nodes
+    graph = sparse.csr_matrix((_to_host(g.data), _to_host(g.indices), _to_host(g.indptr)), shape=(n, n))
+    coords = _to_host(g.coords)
+    return graph, tuple(np.ascontiguousarray(coords[:, i]) for i in range(g.ndim))
+
+
+def _pixel_values_host(values_dev, np_dtype):
+    """csr.py:554-562: None for bool images, float64 for integer images, the image dtype for floats."""
+    if values_dev is None:
+        return None
+    v = _to_host(values_dev)
+    if np_dtype.kind == 'f' and np_dtype != np.float64:
+        return v.astype(np_dtype)
+    return v
+
+
+class Skeleton:
+    """Object to group together all the properties of a skeleton (csr.py:565-858).
+
+    Parameters and attributes follow the reference: ``graph`` (csr_matrix (N, N), fp64 data,
+    int32 indices), ``coordinates`` (N, ndim) int64, ``paths`` (csr_matrix (P, L)), ``n_paths``,
+    ``distances``, ``degrees`` (int32, post junction-MST), ``pixel_values``, ``spacing``,
+    ``skeleton_shape``, ``skeleton_dtype``, ``skeleton_image``, ``source_image``.
+    ``skeleton_image`` may be a NumPy array, a (pinned) CPU torch tensor or a CUDA tensor.
+    """
+
+    def __init__(self, skeleton_image, *, spacing=1, source_image=None, keep_images=True,
+                 value_is_height=False):
+        g = _pipeline.pixel_graph(skeleton_image, spacing=spacing, value_is_height=value_is_height,
+                                  device=_device_of(skeleton_image))
+        self._g = g
+        self._ctx = g.ctx
+        self._values_dev = g.values
+        self._coords_dev = g.coords
+        self._graph_dev = (g.indptr, g.indices, g.data)
+        self._n_nodes = g.n_nodes
+        self._p = _pipeline.trace_paths(g.ctx, g.indptr, g.indices, g.values, g.n_nodes, g.n_edges)
+        self.n_paths = self._p.n_paths
+        self._host = {}
+        self._stats = None
+        self._value_is_height = bool(value_is_height)
+        self.skeleton_image = None
+        self.skeleton_shape = tuple(g.shape)
+        self.skeleton_dtype = g.np_dtype
+        self.source_image = None
+        self.spacing = (np.asarray(spacing) if not np.isscalar(spacing) else np.full(g.ndim, spacing))
+        if keep_images:
+            self.keep_images = keep_images
+            self.skeleton_image = skeleton_image
+            self.source_image = source_image
+
+    # ---- lazily materialised host views of the device results ---------------------------
+    def _cached(self, key, make):
+        if key not in self._host:
+            self._host[key] = make()
+        return self._host[key]
+
+    @property
+    def graph(self):
+        def make():
+            indptr, indices, data = self._graph_dev
+            n = self._n_nodes
+            return sparse.csr_matrix((_to_host(data), _to_host(indices), _to_host(indptr)), shape=(n, n))
+        return self._cached('graph', make)
+
+    @graph.setter
+    def graph(self, value):
+        self._host['graph'] = value
+
+    @property
+    def coordinates(self):
+        return self._cached('coordinates', lambda: _to_host(self._coords_dev))
+
+    @coordinates.setter
+    def coordinates(self, value):
+        self._host['coordinates'] = value
+
+    @property
+    def degrees(self):
+        return self._cached('degrees', lambda: np.diff(self.graph.indptr))
+
+    @degrees.setter
+    def degrees(self, value):
+        self._host['degrees'] = value
+
+    @property
+    def pixel_values(self):
+        return self._cached('pixel_values', lambda: _pixel_values_host(self._values_dev, np.dtype(self.skeleton_dtype)))
+
+    @pixel_values.setter
+    def pixel_values(self, value):
+        self._host['pixel_values'] = value
+
+    @property
+    def paths(self):
+        def make():
+            p = self._p
+            return sparse.csr_matrix((_to_host(p.data), _to_host(p.indices), _to_host(p.indptr)),
+                                     shape=(p.n_paths, p.n_entries))
+        return self._cached('paths', make)
+
+    @paths.setter
+    def paths(self, value):
+        self._host['paths'] = value
+
+    @property
+    def nbgraph(self):
+        """numba view of ``graph`` (csr.py:650), built on demand for code that wants it."""
+        def make():
+            from ._nbgraph import csr_to_nbgraph
+            return csr_to_nbgraph(self.graph, self.pixel_values)
+        return self._cached('nbgraph', make)
+
+    def _device_stats(self):
+        if self._stats is None:
+            indptr, indices, data = self._graph_dev
+            self._stats = _pipeline.path_stats(self._ctx, indptr, indices, data, self._p)
+        return self._stats
+
+    @property
+    def distances(self):
+        return self.path_lengths()
+
+    # ---- reference accessors ---------------------------------------------------------------
+    def path(self, index):
+        """Pixel indices of path number `index`, endpoints included (csr.py:690-714)."""
+        start, stop = self.paths.indptr[index:index + 2]
+        return self.paths.indices[start:stop]
+
+    def path_coordinates(self, index):
+        """Image coordinates of the pixels in the path (csr.py:716-730)."""
+        return self.coordinates[self.path(index)]
+
+    def path_with_data(self, index):
+        """Pixel indices and pixel values on a path (csr.py:732-748)."""
+        start, stop = self.paths.indptr[index:index + 2]
+        return self.paths.indices[start:stop], self.paths.data[start:stop]
+
+    def path_lengths(self):
+        """Length of each path (csr.py:750-764; sum of edge weights left to right, csr.py:962-977)."""
+        return self._cached('distances', lambda: _to_host(self._device_stats()[0]))
+
+    def paths_list(self):
+        """All the paths, endpoints included (csr.py:766-774)."""
+        return [list(self.path(i)) for i in range(self.n_paths)]
+
+    def path_means(self):
+        """Mean pixel value along each path (csr.py:792-802)."""
+        return self._cached('means', lambda: _to_host(self._device_stats()[1]))
+
+    def path_stdev(self):
+        """Standard deviation of pixel values along each path (csr.py:804-816)."""
+        return self._cached('stdev', lambda: _to_host(self._device_stats()[2]))
+
+    def path_label_image(self):
+        """Image of the skeleton's shape holding path id + 1 at every path pixel (csr.py:776-790)."""
+        ctx, p = self._ctx, self._p
+        v = int(np.prod(self.skeleton_shape, dtype=np.int64))
+        out = torch.zeros(v, dtype=torch.int64, device=ctx.device)
+        ctx.call('skb_path_label_image', p.indptr, p.indices, self._g.lin, p.n_paths, out)
+        return _to_host(out).reshape(self.skeleton_shape)
+
+    def prune_paths(self, indices):
+        """csr.py:818-854 re-skeletonizes with scikit-image after wiping the paths; thinning is
+        outside this package's scope."""
+        if not np.all(np.array(indices) < self.n_paths):
+            raise ValueError(
+                f'The path index {np.max(indices)} does not exist in this '
+                f'skeleton. (The highest path index is {self.n_paths}.)\n'
+                'If you obtained the index from a summary table, you '
+                'probably need to resummarize the skeleton.')
+        raise NotImplementedError('prune_paths needs skimage.morphology.skeletonize (out of scope)')
+
+    def __array__(self, dtype=None):
+        """Array representation of the skeleton path labels (csr.py:856-858)."""
+        return self.path_label_image()
+
+
+class PathGraph:
+    """Generalization of a skeleton (csr.py:449-551): the same path pipeline from an arbitrary
+    symmetric CSR adjacency (``from_graph``) or from an image (``from_image``)."""
+
+    def __init__(self, adj, node_coordinates, node_values, paths, spacing=1, _dev=None):
+        self.adj = adj
+        self.node_coordinates = node_coordinates
+        self.node_values = node_values
+        self.paths = paths
+        self.spacing = spacing
+        self._dev = _dev
+        self._distances = None
+
+    @classmethod
+    def from_graph(cls, *, adj, node_coordinates, node_values=None, spacing=1):
+        ctx = _pipeline._Ctx(_default_device())
+        adj = sparse.csr_matrix(adj) if not sparse.issparse(adj) or adj.format != 'csr' else adj
+        n = adj.shape[0]
+        indptr = torch.from_numpy(np.ascontiguousarray(adj.indptr, dtype=np.int32)).to(ctx.device)
+        indices = torch.from_numpy(np.ascontiguousarray(adj.indices, dtype=np.int32)).to(ctx.device)
+        data = torch.from_numpy(np.ascontiguousarray(adj.data, dtype=np.float64)).to(ctx.device)
+        values = None
+        if node_values is not None:
+            values = torch.from_numpy(np.ascontiguousarray(node_values, dtype=np.float64)).to(ctx.device)
+        p = _pipeline.trace_paths(ctx, indptr, indices, values, n, int(adj.indices.size))
+        paths = sparse.csr_matrix((_to_host(p.data), _to_host(p.indices), _to_host(p.indptr)),
+                                  shape=(p.n_paths, p.n_entries))
+        dev = dict(ctx=ctx, indptr=indptr, indices=indices, data=data, values=values, p=p)
+        return cls(adj, node_coordinates, node_values, paths, spacing, _dev=dev)
+
+    @classmethod
+    def from_image(cls, skeleton_image, *, spacing=1, value_is_height=False):
+        sk = Skeleton(skeleton_image, spacing=spacing, value_is_height=value_is_height, keep_images=False)
+        dev = dict(ctx=sk._ctx, indptr=sk._graph_dev[0], indices=sk._graph_dev[1], data=sk._graph_dev[2],
+                   values=sk._values_dev, p=sk._p)
+        return cls(sk.graph, sk.coordinates, sk.pixel_values, sk.paths, spacing, _dev=dev)
+
+    @property
+    def distances(self):
+        if self._distances is None:
+            d = self._dev
+            dist, _, _ = _pipeline.path_stats(d['ctx'], d['indptr'], d['indices'], d['data'], d['p'],
+                                              mean=False, stdev=False)
+            self._distances = _to_host(dist)
+        return self._distances
+
+    @property
+    def n_paths(self):
+        return self.paths.shape[0]
+
+    @property
+    def degrees(self):
+        return np.diff(self.adj.indptr)
+
+
+class _PathGraphSkeleton:
+    """What Skeleton.from_path_graph builds (csr.py:670-688), without the dummy image."""
+
+    def __init__(self, pg):
+        d = pg._dev
+        self._ctx = d['ctx']
+        self._graph_dev = (d['indptr'], d['indices'], d['data'])
+        self._values_dev = d['values']
+        self._p = d['p']
+        self.graph = pg.adj
+        self.coordinates = np.asarray(pg.node_coordinates)
+        self._coords_dev = torch.from_numpy(np.ascontiguousarray(self.coordinates, dtype=np.int64)).to(self._ctx.device)
+        self.pixel_values = pg.node_values
+        self.paths = pg.paths
+        self.n_paths = pg.n_paths
+        self.degrees = pg.degrees
+        self.spacing = pg.spacing
+        self.skeleton_shape = np.max(self.coordinates, axis=0) + 1
+        self.skeleton_dtype = bool if pg.node_values is None else np.asarray(pg.node_values).dtype
+
+
+def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=None):
+    """Compute statistics for every skeleton and branch in ``skel`` (csr.py:861-959).
+
+    Returns a pandas.DataFrame with the reference's columns, order and dtypes: skeleton_id,
+    node_id_src/dst (int32), branch_distance, branch_type (int64), mean/stdev_pixel_value,
+    image_coord_src/dst_i (int64), coord_src/dst_i, euclidean_distance.
+    """
+    import pandas as pd
+    if isinstance(skel, PathGraph):
+        skel = _PathGraphSkeleton(skel)
+    if separator is None:
+        warnings.warn(
+            "separator in column name will change to _ in version 0.13; "
+            "to silence this warning, use `separator='-'` to maintain "
+            "current behavior and use `separator='_'` to switch to the "
+            "new default behavior.",
+            np.exceptions.VisibleDeprecationWarning,
+            stacklevel=2,
+        )
+        separator = '-'
+    if find_main_branch:
+        raise NotImplementedError('find_main_branch (summary_utils.py:7-62) is outside the B200 hot path')
+    ctx, p = skel._ctx, skel._p
+    indptr, indices, data = skel._graph_dev
+    ndim = int(skel._coords_dev.shape[1])
+    spacing = skel.spacing
+    if value_is_height and skel._values_dev is None:
+        raise TypeError("'NoneType' object is not subscriptable")  # csr.py:933 on a boolean skeleton
+    dist, mean, stdev = _pipeline.path_stats(ctx, indptr, indices, data, p)
+    o32, o64, of, sp_is_int = _pipeline.branch_table(ctx, p, indptr, skel._coords_dev, skel._values_dev,
+                                                      spacing, ndim, value_is_height)
+    o32, o64, of = _to_host(o32), _to_host(o64), _to_host(of)
+    h = int(bool(value_is_height))
+    dh = ndim + h
+    summary = {}
+    summary['skeleton_id'] = o32[0]
+    summary['node_id_src'] = o32[1]
+    summary['node_id_dst'] = o32[2]
+    summary['branch_distance'] = _to_host(dist)
+    summary['branch_type'] = o64[0]
+    summary['mean_pixel_value'] = _to_host(mean)
+    summary['stdev_pixel_value'] = _to_host(stdev)
+    for i in range(ndim):
+        summary[f'image_coord_src_{i}'] = o64[1 + i]
+    for i in range(ndim):
+        summary[f'image_coord_dst_{i}'] = o64[1 + ndim + i]
+    real = of.view(np.int64) if sp_is_int else of
+    vdtype = None
+    if h:
+        pv = skel.pixel_values
+        vdtype = np.asarray(pv).dtype if pv is not None else np.float64
+    for i in range(ndim):
+        summary[f'coord_src_{i}'] = real[i]
+    if h:
+        summary[f'coord_src_{ndim}'] = of[ndim].astype(vdtype, copy=False)
+    for i in range(ndim):
+        summary[f'coord_dst_{i}'] = real[dh + i]
+    if h:
+        summary[f'coord_dst_{ndim}'] = of[dh + ndim].astype(vdtype, copy=False)
+    summary['euclidean_distance'] = of[2 * dh]
+    df = pd.DataFrame(summary)
+    df.rename(columns=lambda s: s.replace('_', separator), inplace=True)
+    return df

@@ -1,0 +1,535 @@
+// skan_b200 -- sm_100a implementation of the skeleton-to-graph hot path of jni/skan.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared -Xcompiler -fPIC
+//
+// This file holds the block-cooperative kernels (the V-proportional mask sweep, node emission,
+// device-wide scans) and the CUDA side of the platform layer; the per-item kernels of the
+// node/edge/path proportional stages are the functors of skb_items.cuh launched through
+// skb_foreach, sequenced by the C-ABI bodies in skb_api.inl.  There is no CPU fallback here:
+// every entry point launches kernels on the given stream and reports CUDA errors.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "skb_items.cuh"
+
+typedef cudaStream_t skb_stream_t;
+
+// ------------------------------------------------------------------------------- errors
+static thread_local char g_skb_err[512] = "";
+
+static int skb_fail(const char* what) {
+    snprintf(g_skb_err, sizeof(g_skb_err), "%s", what);
+    return -2;
+}
+
+static int skb_cuda_check(cudaError_t e, const char* where) {
+    if (e == cudaSuccess) return 0;
+    snprintf(g_skb_err, sizeof(g_skb_err), "%s: %s", where, cudaGetErrorString(e));
+    return -1;
+}
+
+#define SKB_CUDA(expr) \
+    do { \
+        int _e = skb_cuda_check((expr), #expr); \
+        if (_e) return _e; \
+    } while (0)
+
+static int skb_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// ------------------------------------------------------------------------------- foreach
+template <typename F>
+__global__ void __launch_bounds__(256) skb_foreach_kernel(F f, int64_t n) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+template <typename F>
+static int skb_foreach(int64_t n, skb_stream_t s, F f) {
+    if (n <= 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = (int64_t)skb_sm_count() * 32;  // grid-stride beyond 32 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    skb_foreach_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n);
+    return skb_cuda_check(cudaGetLastError(), "skb_foreach launch");
+}
+
+static int skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t s) {
+    if (!nbytes) return 0;
+    return skb_cuda_check(cudaMemsetAsync(p, byte, nbytes, s), "cudaMemsetAsync");
+}
+
+static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s) {
+    static thread_local int32_t* pinned = nullptr;
+    if (!pinned) SKB_CUDA(cudaMallocHost((void**)&pinned, 64));
+    SKB_CUDA(cudaMemcpyAsync(pinned, p, 4, cudaMemcpyDeviceToHost, s));
+    SKB_CUDA(cudaStreamSynchronize(s));
+    *host_out = *pinned;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- scans
+// Exclusive scan with n+1 outputs (out[n] = total), reduce -> top -> apply.  `in == out` is
+// allowed: every block holds its whole tile in registers before it writes.
+#define SKB_SCAN_THREADS 256
+#define SKB_SCAN_ITEMS 8
+#define SKB_SCAN_TILE (SKB_SCAN_THREADS * SKB_SCAN_ITEMS)
+
+template <typename T>
+__device__ __forceinline__ T skb_block_exclusive(T v, T* total) {
+    // exclusive scan of one value per thread across a 256-thread block
+    __shared__ T warp_sums[SKB_SCAN_THREADS / 32];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        T w = lane < SKB_SCAN_THREADS / 32 ? warp_sums[lane] : (T)0;
+#pragma unroll
+        for (int d = 1; d < SKB_SCAN_THREADS / 32; d <<= 1) {
+            T o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += o;
+        }
+        if (lane < SKB_SCAN_THREADS / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    T base = warp ? warp_sums[warp - 1] : (T)0;
+    *total = warp_sums[SKB_SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_reduce_kernel(const T* __restrict__ in, int64_t n,
+                                                                           T* __restrict__ block_sums) {
+    int64_t base = (int64_t)blockIdx.x * SKB_SCAN_TILE + (int64_t)threadIdx.x * SKB_SCAN_ITEMS;
+    T acc = 0;
+#pragma unroll
+    for (int j = 0; j < SKB_SCAN_ITEMS; ++j)
+        if (base + j < n) acc += in[base + j];
+    T total;
+    skb_block_exclusive<T>(acc, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_top_kernel(T* block_sums, int64_t nb) {
+    // single block: exclusive scan of the block sums in place, total at block_sums[nb]
+    T carry = 0;
+    for (int64_t c = 0; c < nb; c += SKB_SCAN_THREADS) {
+        int64_t i = c + threadIdx.x;
+        T v = i < nb ? block_sums[i] : (T)0;
+        T total;
+        T ex = skb_block_exclusive<T>(v, &total);
+        if (i < nb) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) block_sums[nb] = carry;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_apply_kernel(const T* in, int64_t n, T* out,
+                                                                          const T* __restrict__ block_sums,
+                                                                          int64_t nb) {
+    int64_t base = (int64_t)blockIdx.x * SKB_SCAN_TILE + (int64_t)threadIdx.x * SKB_SCAN_ITEMS;
+    T v[SKB_SCAN_ITEMS];
+    T acc = 0;
+#pragma unroll
+    for (int j = 0; j < SKB_SCAN_ITEMS; ++j) {
+        v[j] = (base + j < n) ? in[base + j] : (T)0;
+        acc += v[j];
+    }
+    T total;
+    T ex = skb_block_exclusive<T>(acc, &total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SKB_SCAN_ITEMS; ++j) {
+        if (base + j < n) out[base + j] = ex;
+        ex += v[j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nb];
+}
+
+template <typename T>
+static int skb_scan_impl(const T* in, T* out, int64_t n, void* scratch, skb_stream_t s) {
+    if (n < 0) return skb_fail("scan: negative length");
+    if (n == 0) return skb_cuda_check(cudaMemsetAsync(out, 0, sizeof(T), s), "scan memset");
+    int64_t nb = (n + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
+    T* sums = (T*)scratch;
+    skb_scan_reduce_kernel<T><<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, sums);
+    skb_scan_top_kernel<T><<<1, SKB_SCAN_THREADS, 0, s>>>(sums, nb);
+    skb_scan_apply_kernel<T><<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, out, sums, nb);
+    return skb_cuda_check(cudaGetLastError(), "scan launch");
+}
+
+static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, skb_stream_t s) {
+    return skb_scan_impl<uint32_t>(in, out, n, scratch, s);
+}
+static int skb_scan_u64_impl(const uint64_t* in, uint64_t* out, int64_t n, void* scratch, skb_stream_t s) {
+    return skb_scan_impl<unsigned long long>((const unsigned long long*)in, (unsigned long long*)out, n, scratch, s);
+}
+
+// ------------------------------------------------------------------------------- mask sweep
+// The only V-proportional pass (replaces image.astype(bool), np.pad and both np.flatnonzero
+// scans, csr.py:1070,122-123,131): read the image once, write 1 bit per voxel and one count
+// per 16384-voxel tile.  A tile is 256 u64 words; each warp owns 2048 voxels of it.
+#define SKB_TILE_VOX 16384
+#define SKB_TILE_WORDS 256
+#define SKB_PACK_THREADS 256
+
+template <int ESIZE>
+__device__ __forceinline__ uint32_t skb_nonzero_bits(uint4 v, bool is_float);
+
+template <>
+__device__ __forceinline__ uint32_t skb_nonzero_bits<1>(uint4 v, bool) {
+    // 16 voxels: byte != 0 -> bit
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t ne = __vcmpne4(w[i], 0u) & 0x01010101u;  // 0x01 per nonzero byte
+        m |= ((ne * 0x10204080u) >> 28) << (4 * i);       // gather bits 0,8,16,24 -> nibble
+    }
+    return m;
+}
+template <>
+__device__ __forceinline__ uint32_t skb_nonzero_bits<2>(uint4 v, bool is_float) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t clr = is_float ? 0x7fff7fffu : 0xffffffffu;  // -0.0 is zero
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t x = w[i] & clr;
+        m |= ((x & 0xffffu) ? 1u : 0u) << (2 * i);
+        m |= ((x >> 16) ? 1u : 0u) << (2 * i + 1);
+    }
+    return m;
+}
+template <>
+__device__ __forceinline__ uint32_t skb_nonzero_bits<4>(uint4 v, bool is_float) {
+    uint32_t clr = is_float ? 0x7fffffffu : 0xffffffffu;
+    return ((v.x & clr) ? 1u : 0u) | ((v.y & clr) ? 2u : 0u) | ((v.z & clr) ? 4u : 0u) | ((v.w & clr) ? 8u : 0u);
+}
+template <>
+__device__ __forceinline__ uint32_t skb_nonzero_bits<8>(uint4 v, bool is_float) {
+    uint32_t clr = is_float ? 0x7fffffffu : 0xffffffffu;
+    return ((v.x | (v.y & clr)) ? 1u : 0u) | ((v.z | (v.w & clr)) ? 2u : 0u);
+}
+
+__device__ __forceinline__ uint4 skb_ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// guarded element-wise load of one 16-byte chunk that crosses the end of the image
+template <int ESIZE>
+__device__ __forceinline__ uint4 skb_load_tail(const uint8_t* img, int64_t byte_off, int64_t nbytes) {
+    union {
+        uint4 v;
+        uint8_t b[16];
+    } u;
+    u.v = make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < 16; ++i)
+        if (byte_off + i < nbytes) u.b[i] = img[byte_off + i];
+    return u.v;
+}
+
+// Variant 0: coalesced 128-bit streaming loads, 4 in flight per thread, bits gathered with
+// xor-shuffles inside groups of 32/EPV lanes.
+template <int ESIZE>
+__global__ void __launch_bounds__(SKB_PACK_THREADS) skb_pack_ldg_kernel(const uint8_t* __restrict__ img,
+                                                                        int64_t nvox, bool is_float,
+                                                                        uint32_t* __restrict__ bits32,
+                                                                        uint32_t* __restrict__ tile_counts,
+                                                                        int64_t ntiles) {
+    constexpr int EPV = 16 / ESIZE;             // voxels per 16-byte chunk
+    constexpr int LANES_PER_WORD = 32 / EPV;    // lanes that share one 32-bit mask word
+    constexpr int CHUNKS_PER_WARP = 2048 / EPV / 32;  // 16-byte chunks per lane per tile
+    constexpr int UNROLL = CHUNKS_PER_WARP < 4 ? CHUNKS_PER_WARP : 4;
+    __shared__ uint32_t warp_counts[SKB_PACK_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nbytes = nvox * ESIZE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t vox0 = tile * SKB_TILE_VOX + (int64_t)warp * 2048;  // first voxel of this warp
+        uint32_t cnt = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CHUNKS_PER_WARP; c0 += UNROLL) {
+            uint4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                int64_t chunk_vox = vox0 + (int64_t)((c0 + u) * 32 + lane) * EPV;
+                int64_t off = chunk_vox * ESIZE;
+                if (off + 16 <= nbytes) v[u] = skb_ldg_stream((const uint4*)(img + off));
+                else if (off < nbytes) v[u] = skb_load_tail<ESIZE>(img, off, nbytes);
+                else v[u] = make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                uint32_t m = skb_nonzero_bits<ESIZE>(v[u], is_float);
+                cnt += __popc(m);
+                uint32_t word = m << ((lane % LANES_PER_WORD) * EPV);
+#pragma unroll
+                for (int d = 1; d < LANES_PER_WORD; d <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, d);
+                if ((lane % LANES_PER_WORD) == 0) {
+                    int64_t chunk_vox = vox0 + (int64_t)((c0 + u) * 32 + lane) * EPV;
+                    bits32[chunk_vox >> 5] = word;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (lane == 0) warp_counts[warp] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < SKB_PACK_THREADS / 32; ++w) t += warp_counts[w];
+            tile_counts[tile] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// Variant 1: the tile is brought into shared memory by the TMA unit (cp.async.bulk, 1-D, one
+// elected thread per CTA arms an mbarrier with the byte count), double-buffered so the next
+// tile streams in while this one is packed.  Threads then read their own 32 voxels with
+// 128-bit shared loads in a lane-rotated order that is bank-conflict free for every dtype.
+__device__ __forceinline__ uint32_t skb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void skb_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(skb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void skb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(skb_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void skb_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(skb_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void skb_tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            skb_smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(skb_smem_u32(bar))
+        : "memory");
+}
+
+// One pipeline stage is 16 KB of image = 16384 / ESIZE voxels; thread t owns bytes [64 t, 64 t + 64).
+#define SKB_STAGE_BYTES 16384
+
+template <int ESIZE, int STAGES>
+__global__ void __launch_bounds__(SKB_PACK_THREADS) skb_pack_tma_kernel(const uint8_t* __restrict__ img,
+                                                                        int64_t nvox, bool is_float,
+                                                                        uint8_t* __restrict__ bits8,
+                                                                        uint32_t* __restrict__ tile_counts,
+                                                                        int64_t ntiles) {
+    constexpr int NBITS = 64 / ESIZE;  // voxels (= mask bits) per thread and stage
+    constexpr int EPV = 16 / ESIZE;    // voxels per 16-byte chunk
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t full_bar[STAGES];
+    __shared__ uint32_t warp_counts[2][SKB_PACK_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nbytes = nvox * ESIZE;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) skb_mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a tile is ESIZE stages
+    int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_stages = my_tiles * ESIZE;
+    auto stage_offset = [&](int64_t q) -> int64_t {
+        int64_t tile = blockIdx.x + (q / ESIZE) * (int64_t)gridDim.x;
+        return (tile * ESIZE + (q % ESIZE)) * (int64_t)SKB_STAGE_BYTES;
+    };
+    auto issue = [&](int64_t q) {  // thread 0 only
+        int s = (int)(q % STAGES);
+        int64_t off = stage_offset(q);
+        int64_t avail = nbytes - off;
+        uint32_t bytes = avail >= SKB_STAGE_BYTES ? (uint32_t)SKB_STAGE_BYTES : (uint32_t)(avail > 0 ? (avail & ~15LL) : 0);
+        skb_mbar_expect_tx(&full_bar[s], bytes);
+        if (bytes) skb_tma_load_1d(smem + (size_t)s * SKB_STAGE_BYTES, img + off, bytes, &full_bar[s]);
+    };
+    if (tid == 0)
+        for (int64_t q = 0; q < STAGES - 1 && q < my_stages; ++q) issue(q);
+    uint32_t tile_acc = 0;  // thread 0
+    for (int64_t q = 0; q < my_stages; ++q) {
+        const int s = (int)(q % STAGES);
+        const uint32_t parity = (uint32_t)((q / STAGES) & 1);
+        // the stage refilled here was read in iteration q-1; every thread has passed that
+        // iteration's __syncthreads before thread 0 gets here
+        if (tid == 0 && q + STAGES - 1 < my_stages) issue(q + STAGES - 1);
+        skb_mbar_wait(&full_bar[s], parity);
+        const uint8_t* st = smem + (size_t)s * SKB_STAGE_BYTES;
+        const int64_t off = stage_offset(q);
+        const int64_t copied = (nbytes - off >= SKB_STAGE_BYTES) ? SKB_STAGE_BYTES : ((nbytes - off) > 0 ? ((nbytes - off) & ~15LL) : 0);
+        uint64_t word = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int jj = (j + (lane >> 1)) & 3;  // rotation: the 8 lanes of a quarter-warp hit 32 distinct banks
+            int boff = tid * 64 + jj * 16;
+            uint4 v;
+            if (boff + 16 <= copied) v = *(const uint4*)(st + boff);
+            else if (off + boff < nbytes) v = skb_load_tail<ESIZE>(img, off + boff, nbytes);
+            else v = make_uint4(0, 0, 0, 0);
+            word |= (uint64_t)skb_nonzero_bits<ESIZE>(v, is_float) << (jj * EPV);
+        }
+        // mask bytes of this thread: voxel index of the stage start is off / ESIZE
+        const int64_t bit0 = off / ESIZE + (int64_t)tid * NBITS;
+        if (NBITS == 64) *(uint64_t*)(bits8 + (bit0 >> 3)) = word;
+        else if (NBITS == 32) *(uint32_t*)(bits8 + (bit0 >> 3)) = (uint32_t)word;
+        else if (NBITS == 16) *(uint16_t*)(bits8 + (bit0 >> 3)) = (uint16_t)word;
+        else bits8[bit0 >> 3] = (uint8_t)word;
+        uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popcll(word));
+        if (lane == 0) warp_counts[q & 1][warp] = cnt;
+        __syncthreads();  // stage s fully read; warp counts visible
+        if (tid == 0) {
+#pragma unroll
+            for (int w = 0; w < SKB_PACK_THREADS / 32; ++w) tile_acc += warp_counts[q & 1][w];
+            if ((q % ESIZE) == ESIZE - 1) {
+                tile_counts[blockIdx.x + (q / ESIZE) * (int64_t)gridDim.x] = tile_acc;
+                tile_acc = 0;
+            }
+        }
+    }
+}
+
+template <int ESIZE>
+static int skb_pack_launch(const void* img, int64_t nvox, bool is_float, uint64_t* bits, uint32_t* tile_counts,
+                           int64_t ntiles, int variant, skb_stream_t s) {
+    int sms = skb_sm_count();
+    if (variant == 1) {
+        constexpr int STAGES = 4;
+        size_t smem = (size_t)STAGES * SKB_STAGE_BYTES;
+        static bool attr_set = false;
+        if (!attr_set) {
+            SKB_CUDA(cudaFuncSetAttribute(skb_pack_tma_kernel<ESIZE, STAGES>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        int64_t grid = (int64_t)sms * 3;
+        if (grid > ntiles) grid = ntiles;
+        skb_pack_tma_kernel<ESIZE, STAGES><<<(unsigned)grid, SKB_PACK_THREADS, smem, s>>>(
+            (const uint8_t*)img, nvox, is_float, (uint8_t*)bits, tile_counts, ntiles);
+    } else {
+        int64_t grid = (int64_t)sms * 8;
+        if (grid > ntiles) grid = ntiles;
+        skb_pack_ldg_kernel<ESIZE><<<(unsigned)grid, SKB_PACK_THREADS, 0, s>>>(
+            (const uint8_t*)img, nvox, is_float, (uint32_t*)bits, tile_counts, ntiles);
+    }
+    return skb_cuda_check(cudaGetLastError(), "pack launch");
+}
+
+// ------------------------------------------------------------------------------- node emission
+// One CTA per 16384-voxel tile of the mask (256 u64 words, one per thread): rank structure
+// (pre256), raveled index, coordinates (csr.py:1088) and fp64 values (csr.py:554-562) of
+// every foreground voxel, in raster order (csr.py:131-132).  Reads V/8 bytes of mask.
+__global__ void __launch_bounds__(SKB_TILE_WORDS) skb_emit_nodes_kernel(
+    const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, SkbGeom g, const void* img,
+    int dtype, int64_t* __restrict__ lin, int64_t* __restrict__ coords, double* __restrict__ values,
+    uint32_t* __restrict__ pre256) {
+    const int64_t tile = blockIdx.x;
+    const int64_t w = tile * SKB_TILE_WORDS + threadIdx.x;
+    const uint32_t t0 = tile_prefix[tile], t1 = tile_prefix[tile + 1];
+    if (t0 == t1) {  // empty tile: only the rank structure
+        if ((threadIdx.x & 3) == 0) pre256[w >> 2] = t0;
+        return;
+    }
+    uint64_t word = bits[w];
+    uint32_t total;
+    uint32_t id = t0 + skb_block_exclusive<uint32_t>((uint32_t)__popcll(word), &total);
+    if ((threadIdx.x & 3) == 0) pre256[w >> 2] = id;
+    while (word) {
+        int b = __ffsll((long long)word) - 1;
+        word &= word - 1;
+        int64_t r = w * 64 + b;
+        lin[id] = r;
+        int32_t z, y, x;
+        skb_coords(g, r, z, y, x);
+        int64_t* c = coords + (int64_t)id * g.ndim;
+        if (g.ndim == 3) {
+            c[0] = z;
+            c[1] = y;
+            c[2] = x;
+        } else if (g.ndim == 2) {
+            c[0] = y;
+            c[1] = x;
+        } else {
+            c[0] = x;
+        }
+        if (values) values[id] = skb_load_value(img, dtype, r);
+        ++id;
+    }
+}
+
+#include "skb_api.inl"
+
+extern "C" {
+
+const char* skb_last_error(void) { return g_skb_err; }
+
+int64_t skb_scan_scratch_bytes(int64_t n) {
+    int64_t nb = (n + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
+    return (nb + 2) * 8;
+}
+
+int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
+
+// mask sweep (replaces csr.py:1070,122-123,131).  bits: ntiles*256 u64 words (the caller owns
+// one zeroed pad word on either side); tile_counts: u32[ntiles].  variant 0 = vector loads,
+// 1 = TMA bulk copies through shared memory.  The image must be 16-byte aligned.
+int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, uint32_t* tile_counts,
+                   int64_t ntiles, int variant, void* stream) {
+    if (dtype < 0 || dtype >= SKB_DT_COUNT) return skb_fail("unsupported image dtype");
+    if (((uintptr_t)image & 15) != 0) return skb_fail("image pointer must be 16-byte aligned");
+    if (ntiles != (nvox + SKB_TILE_VOX - 1) / SKB_TILE_VOX) return skb_fail("ntiles does not match nvox");
+    if (nvox <= 0) return 0;
+    bool is_float = dtype == SKB_DT_F32 || dtype == SKB_DT_F64;
+    skb_stream_t s = (skb_stream_t)stream;
+    switch (skb_dtype_size(dtype)) {
+        case 1: return skb_pack_launch<1>(image, nvox, is_float, bits, tile_counts, ntiles, variant, s);
+        case 2: return skb_pack_launch<2>(image, nvox, is_float, bits, tile_counts, ntiles, variant, s);
+        case 4: return skb_pack_launch<4>(image, nvox, is_float, bits, tile_counts, ntiles, variant, s);
+        default: return skb_pack_launch<8>(image, nvox, is_float, bits, tile_counts, ntiles, variant, s);
+    }
+}
+
+// nodes in raster order (csr.py:131-132,1088,554-562).  tile_prefix: exclusive scan of the
+// tile counts (ntiles+1).  values may be null (bool images).  pre256: u32[ntiles*64].
+int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                   const int64_t* shape, const void* image, int dtype, int64_t* lin, int64_t* coords,
+                   double* values, uint32_t* pre256, void* stream) {
+    SKB_TRY(skb_check_geom(ndim, shape));
+    if (ntiles <= 0) return 0;
+    if (values && !image) return skb_fail("values requested without an image");
+    skb_emit_nodes_kernel<<<(unsigned)ntiles, SKB_TILE_WORDS, 0, (skb_stream_t)stream>>>(
+        bits, tile_prefix, skb_make_geom(ndim, shape), image, dtype, lin, coords, values, pre256);
+    return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// TEST INFRASTRUCTURE -- host emulation of libskan_b200's C-ABI for CPU-only unit tests.
+//
+// Compiles the SAME per-item device functions (skan_b200/csrc/skb_items.cuh) and the SAME
+// C-ABI bodies (skan_b200/csrc/skb_api.inl) with g++, running every "one thread per item"
+// kernel as a serial loop.  This lets `pytest -m "not gpu"` exercise the index arithmetic of
+// the node/edge/path stages and the python host logic in a container without a GPU.  The
+// three block-cooperative CUDA kernels (mask sweep, node emission, scans) are replaced by
+// plain serial restatements below and are therefore NOT covered here -- the `-m gpu` tests
+// cover them.  The skan_b200 package never loads this library: it is built and injected only
+// by tests/ (tests/emul_util.py).
+//
+//   g++ -O2 -ffp-contract=off -shared -fPIC -I skan_b200/csrc -o tests/emul/_build/libskb_emul.so tests/emul/skb_emul.cpp
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "skb_items.cuh"
+
+typedef void* skb_stream_t;
+
+static thread_local char g_skb_err[512] = "";
+
+static int skb_fail(const char* what) {
+    snprintf(g_skb_err, sizeof(g_skb_err), "%s", what);
+    return -2;
+}
+
+template <typename F>
+static int skb_foreach(int64_t n, skb_stream_t, F f) {
+    for (int64_t i = 0; i < n; ++i) f(i);
+    return 0;
+}
+
+static int skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t) {
+    memset(p, byte, nbytes);
+    return 0;
+}
+
+static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t) {
+    *host_out = *p;
+    return 0;
+}
+
+template <typename T>
+static int skb_scan_host(const T* in, T* out, int64_t n) {
+    T acc = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        T v = in[i];
+        out[i] = acc;
+        acc += v;
+    }
+    out[n] = acc;
+    return 0;
+}
+static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*, skb_stream_t) {
+    return skb_scan_host<uint32_t>(in, out, n);
+}
+static int skb_scan_u64_impl(const uint64_t* in, uint64_t* out, int64_t n, void*, skb_stream_t) {
+    return skb_scan_host<uint64_t>(in, out, n);
+}
+
+#define SKB_TILE_VOX 16384
+#define SKB_TILE_WORDS 256
+
+#include "skb_api.inl"
+
+static bool skb_host_nonzero(const void* img, int dt, int64_t r) {
+    switch (dt) {
+        case SKB_DT_U8: case SKB_DT_I8: return ((const uint8_t*)img)[r] != 0;
+        case SKB_DT_U16: case SKB_DT_I16: return ((const uint16_t*)img)[r] != 0;
+        case SKB_DT_U32: case SKB_DT_I32: return ((const uint32_t*)img)[r] != 0;
+        case SKB_DT_U64: case SKB_DT_I64: return ((const uint64_t*)img)[r] != 0;
+        case SKB_DT_F32: return (((const uint32_t*)img)[r] & 0x7fffffffu) != 0;  // -0.0 is zero, NaN is not
+        default: return (((const uint64_t*)img)[r] & 0x7fffffffffffffffull) != 0;
+    }
+}
+
+extern "C" {
+
+const char* skb_last_error(void) { return g_skb_err; }
+int64_t skb_scan_scratch_bytes(int64_t n) { return ((n + 2047) / 2048 + 2) * 8; }
+int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
+
+int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, uint32_t* tile_counts,
+                   int64_t ntiles, int variant, void*) {
+    (void)variant;
+    if (dtype < 0 || dtype >= SKB_DT_COUNT) return skb_fail("unsupported image dtype");
+    if (ntiles != (nvox + SKB_TILE_VOX - 1) / SKB_TILE_VOX) return skb_fail("ntiles does not match nvox");
+    for (int64_t t = 0; t < ntiles; ++t) {
+        uint32_t c = 0;
+        for (int w = 0; w < SKB_TILE_WORDS; ++w) {
+            uint64_t word = 0;
+            for (int b = 0; b < 64; ++b) {
+                int64_t r = (t * SKB_TILE_WORDS + w) * 64 + b;
+                if (r < nvox && skb_host_nonzero(image, dtype, r)) word |= 1ull << b;
+            }
+            bits[t * SKB_TILE_WORDS + w] = word;
+            c += (uint32_t)skb_popcll(word);
+        }
+        tile_counts[t] = c;
+    }
+    return 0;
+}
+
+int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                   const int64_t* shape, const void* image, int dtype, int64_t* lin, int64_t* coords,
+                   double* values, uint32_t* pre256, void*) {
+    SKB_TRY(skb_check_geom(ndim, shape));
+    SkbGeom g = skb_make_geom(ndim, shape);
+    for (int64_t t = 0; t < ntiles; ++t) {
+        uint32_t id = tile_prefix[t];
+        for (int w = 0; w < SKB_TILE_WORDS; ++w) {
+            int64_t wi = t * SKB_TILE_WORDS + w;
+            if ((w & 3) == 0) pre256[wi >> 2] = id;
+            uint64_t word = bits[wi];
+            while (word) {
+                int b = __builtin_ctzll(word);
+                word &= word - 1;
+                int64_t r = wi * 64 + b;
+                lin[id] = r;
+                int32_t z, y, x;
+                skb_coords(g, r, z, y, x);
+                int64_t* c = coords + (int64_t)id * ndim;
+                if (ndim == 3) { c[0] = z; c[1] = y; c[2] = x; }
+                else if (ndim == 2) { c[0] = y; c[1] = x; }
+                else c[0] = x;
+                if (values) values[id] = skb_load_value(image, dtype, r);
+                ++id;
+            }
+        }
+        if (id != tile_prefix[t + 1]) return skb_fail("tile prefix does not match the mask");
+    }
+    return 0;
+}
+
+}  // extern "C"
