@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- skeleton Mvox/s of Skeleton + summarize on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W         # CPU port of the reference path
+    torchrun ... bench.py --gpus N ...                            # one rank per GPU
+
+A "step" is one pass of the whole hot path (mask sweep -> pixel graph -> junction MST -> CSR ->
+paths -> statistics -> branch table) over one synthetic skeleton volume.  `value` is measured
+with the image already resident in HBM (CUDA events, max over ranks); `e2e` is the same job
+through the public API (skan_b200.Skeleton + skan_b200.summarize) from a pinned HOST image,
+H2D and D2H copies inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'skeleton_mvox_per_s'
+UNIT = 'Mvox/s'
+
+# name -> (shape, walkers, steps, seed, isolated, rings, spacing, valued)
+WORKLOADS = {
+    # BASELINE.json configs[4] / north_star target volume (whole volume on one GPU at N=1)
+    'volume_2048': ((2048, 2048, 2048), 16384, 512, 5, 4000, 256, (0.5, 0.1, 0.1), False),
+    # configs[3]
+    'volume_1024': ((1024, 1024, 1024), 2048, 512, 4, 1000, 64, (0.5, 0.1, 0.1), False),
+    # configs[1]: float32-valued 2-D skeleton (path_means over the image's own values)
+    'image_16384': ((16384, 16384), 8192, 512, 2, 1000, 64, 1, True),
+    # small case for quick checks
+    'volume_256': ((256, 256, 256), 256, 256, 6, 100, 16, (0.5, 0.1, 0.1), False),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(',')]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+        return False
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+def cpu_baseline(workload, seconds_hint=15.0):
+    """The oracle (oracle/skan_oracle.py, a NumPy/SciPy/numba port of the reference path) timed on
+    this box's host cores on a bounded sample of the workload: the first Z-planes (rows in 2-D)."""
+    from oracle import skan_oracle as orc
+    from skan_b200.synth import walks
+    shape, nw, steps, seed, iso, rings, spacing, valued = WORKLOADS[workload]
+    # warm numba
+    orc.skeleton_and_summary(walks((32, 32, 32), 8, 24, seed=1), spacing=(0.5, 0.1, 0.1))
+    frac = {'volume_2048': 8, 'volume_1024': 2, 'image_16384': 4, 'volume_256': 1}[workload]
+    sub = (shape[0] // frac,) + tuple(shape[1:])
+    img = walks(sub, max(8, nw // frac), steps, seed, isolated=iso // frac, rings=rings // frac)
+    if valued:
+        rng = np.random.default_rng(seed)
+        img = (img * (rng.random(sub, dtype=np.float32) * 0.9 + 0.1)).astype(np.float32)
+    t0 = time.perf_counter()
+    sk, _ = orc.skeleton_and_summary(img, spacing=spacing)
+    dt = time.perf_counter() - t0
+    return {'value': img.size / dt / 1e6, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': f'first {sub[0]} of {shape[0]} planes of {workload} ({img.size / 1e6:.0f} Mvox, '
+                      f'{sk.graph.shape[0]} nodes, {sk.n_paths} paths), {dt:.2f} s, single thread like the reference',
+            'seconds': dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: the reference is pure Python and
+    cannot travel to the GPU box) on the host cores, bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(args.workload)
+        if i >= args.warmup:
+            vals.append(r)
+        if sum(v['seconds'] for v in vals) > 240:
+            break
+    v = float(np.mean([x['value'] for x in vals]))
+    ms = float(np.mean([x['seconds'] for x in vals])) * 1e3
+    shape = WORKLOADS[args.workload][0]
+    line = {'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(vals), 'warmup': args.warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u8',
+            'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': args.workload, 'shape': list(shape)},
+            'cpu_baseline': {k: vals[-1][k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    line['cpu_baseline']['value'] = v
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='skan_b200')
+    ap.add_argument('--workload', default='volume_2048', choices=sorted(WORKLOADS))
+    ap.add_argument('--pack-variant', default=None, choices=['ldg', 'tma'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--stages', action='store_true', help='also print a per-entry-point timing table to stderr')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import __graft_entry__ as entry
+    entry.build()
+    import skan_b200
+    from skan_b200 import _native, _pipeline
+    from skan_b200.synth import walks_device, walks_points
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}')
+    if world > 1:
+        raise SystemExit('multi-GPU volume mode is not implemented yet')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if args.pack_variant:
+        _pipeline.default_pack_variant = args.pack_variant
+    shape, nw, steps, seed, iso, rings, spacing, valued = WORKLOADS[args.workload]
+    V = int(np.prod(shape, dtype=np.int64))
+
+    # ---- synthetic input, resident in HBM ------------------------------------------------------
+    if valued:
+        mask = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        img = (torch.rand(shape, device=dev, generator=gen) * 0.9 + 0.1) * mask
+        del mask
+        esize, dtype_name = 4, 'f32'
+    else:
+        img = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
+        esize, dtype_name = 1, 'u8'
+    torch.cuda.synchronize()
+    lib = _native.library()
+
+    def step():
+        return _pipeline.skeleton_and_summary_device(img, spacing=spacing, device=dev)
+
+    for _ in range(args.warmup):
+        r = step()
+    torch.cuda.synchronize()
+    g, p = r.graph, r.paths
+    counts = dict(nodes=g.n_nodes, edges=g.n_edges, paths=p.n_paths, path_entries=p.n_entries,
+                  junction_edges=g.n_junction_edges, mst_rounds=g.mst_rounds, rank_rounds=p.rank_rounds)
+    alg = _pipeline.algorithmic_bytes(V, esize, len(shape), g.n_nodes, g.n_edges, p.n_paths, p.n_entries, valued)
+    del r, g, p
+
+    # ---- timed region: K steps, CUDA events, pack kernel timed by its own events --------------
+    hook = {'skb_pack_count': []}
+    _pipeline.EVENT_HOOK = hook
+    launches0 = lib.kernel_launches()
+    start = torch.cuda.Event(enable_timing=True)
+    stop = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(args.steps):
+            r = step()
+            del r
+        stop.record()
+        torch.cuda.synchronize()
+    _pipeline.EVENT_HOOK = None
+    total_ms = start.elapsed_time(stop)
+    launches = lib.kernel_launches() - launches0
+    ms = total_ms / args.steps
+    value = V / (ms * 1e-3) / 1e6
+    pack_ms = float(np.mean([a.elapsed_time(b) for a, b in hook['skb_pack_count']]))
+    peak, peak_src = load_peaks()
+    achieved = V * esize / (pack_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': f'skb_pack_{_pipeline.default_pack_variant}_kernel<{esize}>',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src, 'kernel_ms': pack_ms, 'kernel_share_of_step': pack_ms / ms,
+                'algorithmic_bytes_per_launch': V * esize,
+                'job': {'algorithmic_bytes': alg, 'achieved': alg / (ms * 1e-3) / 1e9,
+                        'frac': alg / (ms * 1e-3) / 1e9 / peak}}
+
+    # ---- optional per-entry-point table (one extra step, not part of any reported number) -----
+    if args.stages:
+        hook = {'*': True}
+        _pipeline.EVENT_HOOK = hook
+        r = step()
+        torch.cuda.synchronize()
+        _pipeline.EVENT_HOOK = None
+        rows = [(k, sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in hook.items() if k != '*']
+        for k, t, n in sorted(rows, key=lambda x: -x[1]):
+            print(f'  {k:28s} {t:9.3f} ms  ({n} calls)', file=sys.stderr)
+        del r
+
+    # ---- end to end through the public API from a pinned host image ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+        host.copy_(img)
+        torch.cuda.synchronize()
+        del img
+        torch.cuda.empty_cache()
+        n_e2e = max(2, min(args.steps, 5))
+        d2h = 0
+        times = []
+        for i in range(1 + n_e2e):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sk = skan_b200.Skeleton(host, spacing=spacing, keep_images=False)
+            df = skan_b200.summarize(sk, separator='_')
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if i:
+                times.append(dt)
+            d2h = int(df.memory_usage(index=False).sum())
+            del sk, df
+        e2e_s = float(np.mean(times))
+        e2e = {'value': V / e2e_s / 1e6, 'unit': UNIT, 'h2d_bytes_per_step': V * esize, 'd2h_bytes_per_step': d2h,
+               'ms_per_step': e2e_s * 1e3, 'steps': n_e2e}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': dtype_name, 'data': 'synthetic',
+            'config': {'workload': args.workload, 'shape': list(shape), 'spacing': list(np.atleast_1d(spacing)),
+                       'l2': 'input larger than L2 (no flush needed)' if V * esize > 256e6 else 'input fits L2',
+                       'pack_variant': _pipeline.default_pack_variant, **counts},
+            'roofline': roofline, 'clocks': clocks.summary(), 'gpu_launches': int(launches),
+            'e2e': e2e}
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline(args.workload)
+        cb.pop('seconds', None)
+        line['cpu_baseline'] = cb
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,145 @@
+/* skan_b200.h -- C-ABI of libskan_b200.so: the skeleton-to-graph hot path of jni/skan on B200.
+ *
+ * The reference (pure Python; /root/reference/src/skan/csr.py) has no FFI for this path: its
+ * "native" side is NumPy / SciPy / numba reached in-process.  Each entry point below replaces
+ * the reference lines cited beside it; the Python mirror of skan.csr (skan_b200/csr.py) calls
+ * them through ctypes with torch.Tensor.data_ptr() as the only array interop.
+ *
+ * Conventions
+ *   - every array pointer is DEVICE memory of the current CUDA device unless marked (host);
+ *   - `stream` is a cudaStream_t; calls are asynchronous unless noted "synchronises";
+ *   - no allocation inside: count -> caller allocates -> fill;
+ *   - return value: >= 0 success (some calls return an iteration count), < 0 failure with the
+ *     message available from skb_last_error() (thread-local);
+ *   - no global state; safe to call from several host threads on different streams;
+ *   - images are embedded as (nz, ny, nx), C order, 1 <= ndim <= 3; `shape` (host) has ndim entries;
+ *   - node ids are 0-based raster ranks of the nonzero voxels (csr.py:131-132), int32;
+ *   - neighbour code k27 = (dz+1)*9 + (dy+1)*3 + (dx+1), 0..26, centre 13 never set.
+ */
+#ifndef SKAN_B200_H
+#define SKAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element codes of the skeleton image (numpy bool is SKB_U8) */
+enum skb_dtype {
+    SKB_U8 = 0, SKB_I8 = 1, SKB_U16 = 2, SKB_I16 = 3, SKB_U32 = 4, SKB_I32 = 5,
+    SKB_U64 = 6, SKB_I64 = 7, SKB_F32 = 8, SKB_F64 = 9
+};
+
+typedef struct skb_i2 { int32_t x, y; } skb_i2;
+
+int skb_abi_version(void);
+const char* skb_last_error(void);
+int64_t skb_scan_scratch_bytes(int64_t n); /* scratch needed by any call taking `scratch` over n items */
+int64_t skb_tile_voxels(void);             /* voxels per mask tile (16384) */
+int64_t skb_kernel_launches(void);         /* kernels launched by the library since it was loaded */
+
+/* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes
+ * (csr.py:1070, 122-123, 131).  Reads the image once; writes 1 bit per voxel (u64 words,
+ * little-endian bit order, ntiles*256 words; the caller keeps one zeroed pad word on either
+ * side) and the foreground count of every 16384-voxel tile.  `image` must be 16-byte aligned.
+ * variant 0: 128-bit streaming loads; variant 1: TMA bulk copies staged in shared memory. */
+int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, uint32_t* tile_counts,
+                   int64_t ntiles, int variant, void* stream);
+
+/* Exclusive scans with n+1 outputs (out[n] = total); in == out allowed. */
+int skb_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, void* stream);
+int skb_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, void* scratch, void* stream);
+
+/* Nodes in raster order -- replaces np.flatnonzero / np.unravel_index / _extract_values
+ * (csr.py:131-132, 1088, 554-562).  tile_prefix = scanned tile counts (ntiles+1).
+ * Out: lin i64[N] raveled index, coords i64[N][ndim], values f64[N] (or NULL for bool images),
+ * pre256 u32[ntiles*64] = popcount prefix of `bits` per 256-bit block (rank structure that
+ * stands in for skimage.util.map_array, csr.py:135,142-144). */
+int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                   const int64_t* shape /*host*/, const void* image, int dtype, int64_t* lin, int64_t* coords,
+                   double* values, uint32_t* pre256, void* stream);
+
+/* Raw 3^d neighbourhood of every node as a 27-bit mask -- replaces the N x (3^d-1) neighbour
+ * table and membership test of pixel_graph (csr.py:122-144). */
+int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape /*host*/, const int64_t* lin, int64_t n,
+                      uint32_t* nb, void* stream);
+
+/* Junction-junction edges (both ends of raw degree >= 3; csr.py:1004-1016): per-node count of
+ * forward edges, then (after an exclusive scan into `offset`) emission in (a, k27) order with
+ * a < b.  ew = fp64 bit pattern of the weight: wtab[k27] (host-computed per nputil.py:278-279) or,
+ * with height != 0, hypot(values[a]-values[b] in the image dtype, wtab[k27]) (csr.py:1023-1025). */
+int skb_junction_edge_count(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape /*host*/,
+                            const int64_t* lin, const uint32_t* nb, int64_t n, uint32_t* count, void* stream);
+int skb_junction_edge_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape /*host*/,
+                           const int64_t* lin, const uint32_t* nb, const uint32_t* offset, int64_t n,
+                           const double* wtab, const double* values, int height, int dtype, int32_t* ea,
+                           int32_t* eb, uint8_t* ek, uint64_t* ew, void* stream);
+
+/* Junction MST -- replaces _mst_junctions (csr.py:980-1020; scipy minimum_spanning_tree):
+ * Boruvka under the strict order (weight, min id, max id).  Scratch: par i32[n], bestw u64[n],
+ * beste u32[n], era/erb i32[nej], flag i32[1].  Out: tree u8[nej].  Returns the number of
+ * rounds; synchronises once per round. */
+int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, int64_t nej, int64_t n,
+                      int32_t* par, uint64_t* bestw, uint32_t* beste, int32_t* era, int32_t* erb, uint8_t* tree,
+                      int32_t* flag, void* stream);
+/* keep[] (a copy of nb[]) loses both directions of every non-tree junction edge (csr.py:1018-1019) */
+int skb_mst_apply(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const uint8_t* tree, int64_t nej,
+                  uint32_t* keep, void* stream);
+
+/* Skeleton.degrees (csr.py:660) and graph.indptr: deg i32[n], indptr i32[n+1] */
+int skb_degrees_indptr(const uint32_t* keep, int64_t n, int32_t* deg, int32_t* indptr, void* scratch, void* stream);
+/* graph.indices i32[E] / graph.data f64[E], canonical CSR (csr.py:153-157) */
+int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape /*host*/,
+                 const int64_t* lin, const uint32_t* keep, const int32_t* indptr, int64_t n, const double* wtab,
+                 const double* values, int height, int dtype, int32_t* indices, double* data, void* stream);
+
+/* Connected components (csr.py:909; label = minimum node id of the component) and node classes
+ * for path tracing: ntype 0 isolated, 1 chain (degree 2), 2 terminal (degree 1 or >= 3),
+ * 3 start of a junction-free cycle (csr.py:369-386).  root_rank u32[n+1]: rank of a component's
+ * minimum among all minima = the reference's skeleton id.  Scratch: par i32[n], has_terminal u8[n]. */
+int skb_components(const int32_t* indptr, const int32_t* indices, int64_t n, int32_t* par, uint8_t* has_terminal,
+                   int32_t* label, uint8_t* ntype, uint32_t* root_rank, void* scratch, void* stream);
+
+/* Path tracing -- replaces _build_paths / _walk_path (csr.py:347-409) by pointer-jumping list
+ * ranking over half-edges.  arcs i2[ne]: x = -1 - (CSR position of the reversed last half-edge
+ * of the list), y = half-edges after this one.  Returns rounds; synchronises once per round. */
+int skb_rank_arcs(const int32_t* indptr, const int32_t* indices, const uint8_t* ntype, int64_t n, int64_t ne,
+                  skb_i2* arcs, int32_t* flag, void* stream);
+/* count u64[n+1]: paths starting at each node, scanned in place; count[n] = cycles<<32 | regular */
+int skb_path_count(const int32_t* indptr, const uint8_t* ntype, const skb_i2* arcs, int64_t n, uint64_t* count,
+                   void* scratch, void* stream);
+/* start_node i32[P], pindptr i32[P+1] (= paths.indptr), einfo i2[ne] */
+int skb_path_starts(const int32_t* indptr, const uint8_t* ntype, const skb_i2* arcs, const uint64_t* prefix,
+                    int64_t n, int64_t ne, int64_t n_regular, int64_t n_paths, int32_t* start_node,
+                    int32_t* pindptr, skb_i2* einfo, void* scratch, void* stream);
+/* paths.indices i32[L], paths.data f64[L] (csr.py:396,402,442-445); values NULL -> 1.0 */
+int skb_path_emit(const int32_t* indices, const skb_i2* arcs, const skb_i2* einfo, const int32_t* pindptr,
+                  const int32_t* start_node, const double* values, int64_t ne, int32_t* pidx, double* pdata,
+                  void* stream);
+
+/* Per-path statistics -- replaces _compute_distances (csr.py:962-977), path_means and
+ * path_stdev (csr.py:792-816; NumPy reduceat summation order).  NULL outputs are skipped. */
+int skb_path_stats(const int32_t* gindptr, const int32_t* gindices, const double* gdata, const int32_t* pindptr,
+                   const int32_t* pidx, const double* pdata, int64_t n_paths, double* dist, double* mean,
+                   double* stdev, void* stream);
+
+/* Branch table -- the remaining columns of summarize (csr.py:909-952) as three SoA buffers:
+ *   out_i32[3][P]            skeleton_id, node_id_src, node_id_dst
+ *   out_i64[1+2d][P]         branch_type, image_coord_src_*, image_coord_dst_*
+ *   out_f64[2(d+h)+1][P]     coord_src_*(+height), coord_dst_*(+height), euclidean_distance
+ * (coord_* carry int64 bit patterns when spacing_is_int).  spacing_f / spacing_i are host arrays. */
+int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, const double* spacing_f /*host*/,
+                     const int64_t* spacing_i /*host*/, const int32_t* pindptr, const int32_t* pidx,
+                     const int32_t* gindptr, const int32_t* label, const uint32_t* root_rank,
+                     const int64_t* coords, const double* values, int32_t* out_i32, int64_t* out_i64,
+                     double* out_f64, void* stream);
+
+/* Skeleton.path_label_image (csr.py:776-790); image i64[V] zeroed by the caller */
+int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int64_t* lin, int64_t n_paths,
+                         int64_t* image, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKAN_B200_H */

@@ -23,6 +23,7 @@ _SIGNATURES = {
     'skb_last_error': (ctypes.c_char_p, []),
     'skb_scan_scratch_bytes': (_i64, [_i64]),
     'skb_tile_voxels': (_i64, []),
+    'skb_kernel_launches': (_i64, []),
     'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
     'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
     'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp]),
@@ -68,6 +69,9 @@ class Library:
             raise NativeError(f'{path}: unexpected ABI version')
         self.tile_voxels = int(self._dll.skb_tile_voxels())
         self.launches = 0
+
+    def kernel_launches(self):
+        return int(self._dll.skb_kernel_launches())
 
     def scan_scratch_bytes(self, n):
         return int(self._dll.skb_scan_scratch_bytes(int(n)))

@@ -39,6 +39,10 @@ _NP_DT = {
 }
 _ESIZE = {0: 1, 1: 1, 2: 2, 3: 2, 4: 4, 5: 4, 6: 8, 7: 8, 8: 4, 9: 8}
 
+# name -> list of (start, stop) CUDA events, filled by _Ctx.call when not None; the key '*' times
+# every entry point, otherwise only the names already present are timed
+EVENT_HOOK = None
+
 PACK_VARIANT = {'ldg': 0, 'tma': 1}
 default_pack_variant = 'ldg'
 
@@ -85,6 +89,16 @@ class _Ctx:
 
     def call(self, name, *args):
         conv = [a.data_ptr() if isinstance(a, torch.Tensor) else (0 if a is None else a) for a in args]
+        hook = EVENT_HOOK
+        if hook is not None and self.device.type == 'cuda' and (hook.get('*') is not None or name in hook):
+            # CUDA events on the launching stream around this entry point (bench.py / profiling only)
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record(torch.cuda.current_stream(self.device))
+            r = self.lib.call(name, *conv, self.stream)
+            b.record(torch.cuda.current_stream(self.device))
+            hook.setdefault(name, []).append((a, b))
+            return r
         return self.lib.call(name, *conv, self.stream)
 
 
@@ -160,6 +174,11 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
     if value_is_height and values is None:
         # the reference subtracts booleans here, which NumPy refuses (csr.py:1024)
         raise TypeError('value_is_height needs a numeric (non-boolean) skeleton image')
+    if value_is_height and np_dtype.kind == 'u':
+        # csr.py:1024 subtracts in the image dtype: unsigned heights wrap around and the reference
+        # ends up with direction-dependent weights (SURVEY.md A.8 ii).  Rejected, not reproduced.
+        raise ValueError('value_is_height with an unsigned integer image wraps the height differences '
+                         '(reference csr.py:1024); cast the image to a signed or floating dtype')
     wtab = torch.from_numpy(wtab_np).to(ctx.device)
     g.wtab = wtab
     geom = (ndim, shape_t.data_ptr())
@@ -268,3 +287,20 @@ def branch_table(ctx, p, gindptr, coords, values, spacing, ndim, value_is_height
     ctx.call('skb_branch_table', P, ndim, height, 1 if sp_is_int else 0, sp_f.data_ptr(), sp_i.data_ptr(),
              p.indptr, p.indices, gindptr, p.label, p.root_rank, coords, values, o32, o64, of)
     return o32, o64, of, sp_is_int
+
+
+def skeleton_and_summary_device(image, *, spacing=1, value_is_height=False, device, pack_variant=None):
+    """The whole hot path with every result left on the device: pixel graph + junction MST + CSR,
+    paths, per-path statistics and the branch table (what Skeleton(...) + summarize(...) compute)."""
+    g = pixel_graph(image, spacing=spacing, value_is_height=value_is_height, device=device,
+                    pack_variant=pack_variant)
+    p = trace_paths(g.ctx, g.indptr, g.indices, g.values, g.n_nodes, g.n_edges)
+    dist, mean, stdev = path_stats(g.ctx, g.indptr, g.indices, g.data, p)
+    o32, o64, of, _ = branch_table(g.ctx, p, g.indptr, g.coords, g.values, spacing, g.ndim, value_is_height)
+    return SimpleNamespace(graph=g, paths=p, dist=dist, mean=mean, stdev=stdev, table=(o32, o64, of))
+
+
+def algorithmic_bytes(nvox, esize, ndim, n, e, p, l, valued):
+    """every input read once, every mandatory output written once."""
+    return (nvox * esize + n * 8 * ndim + (n + 1) * 4 + n * 4 + e * 12 + (n * 8 if valued else 0)
+            + (p + 1) * 4 + l * 12 + p * (52 + 32 * ndim))

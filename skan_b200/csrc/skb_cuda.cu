@@ -35,6 +35,10 @@ static int skb_cuda_check(cudaError_t e, const char* where) {
         if (_e) return _e; \
     } while (0)
 
+// kernels launched by this library since load (bench.py reports it as gpu_launches)
+static unsigned long long g_skb_launches = 0;
+#define SKB_COUNT_LAUNCH(k) __atomic_fetch_add(&g_skb_launches, (unsigned long long)(k), __ATOMIC_RELAXED)
+
 static int skb_sm_count() {
     static int sms = 0;
     if (!sms) {
@@ -59,6 +63,7 @@ static int skb_foreach(int64_t n, skb_stream_t s, F f) {
     int64_t cap = (int64_t)skb_sm_count() * 32;  // grid-stride beyond 32 CTAs per SM
     if (blocks > cap) blocks = cap;
     skb_foreach_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n);
+    SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "skb_foreach launch");
 }
 
@@ -171,6 +176,7 @@ static int skb_scan_impl(const T* in, T* out, int64_t n, void* scratch, skb_stre
     skb_scan_reduce_kernel<T><<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, sums);
     skb_scan_top_kernel<T><<<1, SKB_SCAN_THREADS, 0, s>>>(sums, nb);
     skb_scan_apply_kernel<T><<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, out, sums, nb);
+    SKB_COUNT_LAUNCH(3);
     return skb_cuda_check(cudaGetLastError(), "scan launch");
 }
 
@@ -442,6 +448,7 @@ static int skb_pack_launch(const void* img, int64_t nvox, bool is_float, uint64_
         skb_pack_ldg_kernel<ESIZE><<<(unsigned)grid, SKB_PACK_THREADS, 0, s>>>(
             (const uint8_t*)img, nvox, is_float, (uint32_t*)bits, tile_counts, ntiles);
     }
+    SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "pack launch");
 }
 
@@ -500,6 +507,8 @@ int64_t skb_scan_scratch_bytes(int64_t n) {
 
 int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
 
+int64_t skb_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_skb_launches, __ATOMIC_RELAXED); }
+
 // mask sweep (replaces csr.py:1070,122-123,131).  bits: ntiles*256 u64 words (the caller owns
 // one zeroed pad word on either side); tile_counts: u32[ntiles].  variant 0 = vector loads,
 // 1 = TMA bulk copies through shared memory.  The image must be 16-byte aligned.
@@ -529,6 +538,7 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
     if (values && !image) return skb_fail("values requested without an image");
     skb_emit_nodes_kernel<<<(unsigned)ntiles, SKB_TILE_WORDS, 0, (skb_stream_t)stream>>>(
         bits, tile_prefix, skb_make_geom(ndim, shape), image, dtype, lin, coords, values, pre256);
+    SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
 }
 

@@ -1,0 +1,64 @@
+"""The C-ABI library loads and exports every symbol include/skan_b200.h declares (no compute:
+this runs without a GPU), and the python binding table agrees with the header."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'skan_b200.h')
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(skb_[a-z0-9_]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def built_library():
+    import __graft_entry__ as g
+    g.build()
+    return g.LIB
+
+
+def test_header_and_binding_table_agree():
+    from skan_b200 import _native
+    assert declared_symbols() == sorted(_native.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    dll = ctypes.CDLL(built_library)
+    for sym in declared_symbols():
+        assert hasattr(dll, sym), sym
+    dll.skb_abi_version.restype = ctypes.c_int
+    assert dll.skb_abi_version() == 1
+    dll.skb_tile_voxels.restype = ctypes.c_int64
+    assert dll.skb_tile_voxels() == 16384
+
+
+def test_library_is_sm100a_and_uses_tma(built_library):
+    """The cubin in the library targets sm_100a and the TMA variant of the sweep is a bulk copy."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run([cuobjdump, '-lelf', built_library], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+    sass = subprocess.run([cuobjdump, '-sass', '-fun', '_Z19skb_pack_tma_kernelILi1ELi4EEvPKhlbPhPjl', built_library],
+                          capture_output=True, text=True).stdout
+    assert 'UBLKCP' in sass, 'TMA bulk copy (cp.async.bulk) not found in the sweep kernel'
+
+
+def test_package_has_no_cpu_fallback():
+    """Without a CUDA device the public API must raise instead of computing somewhere else."""
+    import numpy as np
+    import torch
+    import skan_b200
+    from skan_b200 import _native
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present')
+    with pytest.raises(_native.NativeError):
+        skan_b200.Skeleton(np.eye(5, dtype=bool))

@@ -1,0 +1,228 @@
+"""Parity of the CUDA path (through the C-ABI, on a real B200) with the golden vectors of the
+unmodified reference and with the CPU oracle on seeded inputs.  Integer / index results must be
+bit-exact, fp64 sums within 1e-12 relative (BASELINE.json north_star)."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import case, case_names, check_skeleton_against
+from parity_util import compare_with_oracle
+from skan_b200.synth import walks, walks_device
+
+import skan_b200
+from skan_b200 import _pipeline
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=['ldg', 'tma'])
+def pack_variant(request):
+    old = _pipeline.default_pack_variant
+    _pipeline.default_pack_variant = request.param
+    yield request.param
+    _pipeline.default_pack_variant = old
+
+
+def test_cuda_library_is_the_one_loaded():
+    from skan_b200 import _native
+    lib = _native.library()
+    assert lib.device_type == 'cuda' and lib.path.endswith('libskan_b200.so')
+
+
+@pytest.mark.parametrize('name', case_names())
+def test_golden(name, pack_variant):
+    rec = case(name)
+    if 'error' in rec:
+        with pytest.raises(ValueError):
+            skan_b200.Skeleton(rec['image'], spacing=rec['spacing_arg'], value_is_height=rec['height'])
+        return
+    sk = skan_b200.Skeleton(rec['image'], spacing=rec['spacing_arg'], value_is_height=rec['height'])
+    df = skan_b200.summarize(sk, value_is_height=rec['height'], separator='_')
+    summ = {c: df[c].to_numpy() for c in df.columns}
+    check_skeleton_against(rec, sk, summ, exact_weights=True)
+    for c, t in zip(rec['summary_columns'], rec['summary_dtypes']):
+        assert str(df[str(c)].dtype) == str(t), (c, t)
+    assert np.array_equal(sk.path_label_image(), rec['path_label_image'])
+    if 'pixel_values' in rec:
+        assert sk.pixel_values.dtype == rec['pixel_values'].dtype
+        assert np.array_equal(sk.pixel_values, rec['pixel_values'])
+
+
+@pytest.mark.parametrize('shape,nw,steps,spacing', [
+    ((1024, 1024), 256, 256, 1),
+    ((777, 1031), 128, 256, (1.5, 0.7)),          # ragged: nothing divides the tile or word size
+    ((96, 128, 160), 96, 128, (0.5, 0.1, 0.1)),
+    ((61, 67, 71), 64, 96, 1),
+    ((100000,), 0, 0, 2.0),                        # 1-D image
+])
+def test_walks_vs_oracle(shape, nw, steps, spacing, pack_variant):
+    if len(shape) == 1:
+        rng = np.random.default_rng(3)
+        img = rng.random(shape) < 0.6
+    else:
+        img = walks(shape, nw, steps, seed=sum(shape), isolated=20, rings=8)
+    compare_with_oracle(img, spacing)
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_dense_blobs_vs_oracle(seed, pack_variant):
+    # adversarial junction clusters: one giant cluster, many equal-weight ties
+    rng = np.random.default_rng(2000 + seed)
+    shape = [(200, 300), (40, 40, 40), (512, 64), (24, 48, 96)][seed]
+    spacing = [1, (0.5, 0.1, 0.1), (2.0, 1.0), 1][seed]
+    img = rng.random(shape) < [0.5, 0.3, 0.42, 0.2][seed]
+    compare_with_oracle(img, spacing)
+
+
+@pytest.mark.parametrize('dt', [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.uint64, np.int64,
+                                np.float32, np.float64])
+def test_valued_images_vs_oracle(dt, pack_variant):
+    rng = np.random.default_rng(5)
+    w = walks((300, 421), 64, 200, seed=3, isolated=10, rings=5)
+    vals = rng.integers(1, 100, w.shape) if np.issubdtype(dt, np.integer) else rng.random(w.shape) + 0.5
+    compare_with_oracle((w * vals).astype(dt), (1.0, 1.5))
+
+
+def test_height_mode_rejects_unsigned_images():
+    # the reference wraps unsigned height differences; we refuse instead
+    with pytest.raises(ValueError):
+        skan_b200.Skeleton(np.eye(8, dtype=np.uint8) * 7, value_is_height=True)
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64, np.int8, np.int16, np.int32, np.int64])
+def test_height_mode_vs_oracle(dt):
+    rng = np.random.default_rng(6)
+    w = walks((200, 200), 48, 128, seed=4, isolated=5, rings=3)
+    vals = rng.integers(1, 100, w.shape) if np.issubdtype(dt, np.integer) else rng.random(w.shape) * 4 + 1
+    compare_with_oracle((w * vals).astype(dt), (1.0, 2.0), value_is_height=True)
+
+
+def test_float_zero_semantics(pack_variant):
+    img = np.zeros((6, 40), np.float32)
+    img[2, 1:37] = 1.0
+    img[2, 3] = np.nan
+    img[4, 4] = -0.0
+    sk = skan_b200.Skeleton(img)
+    assert sk.graph.shape[0] == 36 and sk.n_paths == 1
+
+
+def test_inputs_cpu_tensor_cuda_tensor_numpy_agree(pack_variant):
+    img = walks((333, 257), 40, 150, seed=8, isolated=5, rings=2)
+    a = skan_b200.Skeleton(img)
+    b = skan_b200.Skeleton(torch.from_numpy(img).pin_memory())
+    c = skan_b200.Skeleton(torch.from_numpy(img).cuda())
+    big = torch.zeros(img.size + 3, dtype=torch.bool, device='cuda')
+    big[3:] = torch.from_numpy(img).cuda().reshape(-1)
+    d = skan_b200.Skeleton(big[3:].reshape(img.shape))      # misaligned device pointer
+    for o in (b, c, d):
+        assert np.array_equal(a.graph.indices, o.graph.indices)
+        assert np.array_equal(a.paths.indices, o.paths.indices)
+        assert np.array_equal(a.coordinates, o.coordinates)
+
+
+def test_zero_path_inputs_raise():
+    for img in (np.zeros((4, 4), bool), np.eye(1, dtype=bool), np.array([[1, 0, 0, 1]], bool)):
+        with pytest.raises(ValueError):
+            skan_b200.Skeleton(img)
+
+
+def test_pathgraph_equivalence():
+    img = walks((256, 256), 64, 128, seed=9, isolated=3, rings=2)
+    sk = skan_b200.Skeleton(img, spacing=2.5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        a = skan_b200.summarize(sk, separator='_')
+        b = skan_b200.summarize(skan_b200.PathGraph.from_image(img, spacing=2.5), separator='_')
+        c = skan_b200.summarize(skan_b200.PathGraph.from_graph(adj=sk.graph, node_coordinates=sk.coordinates,
+                                                               spacing=2.5), separator='_')
+    for col in a.columns:
+        assert np.array_equal(a[col].to_numpy(), b[col].to_numpy()), col
+        assert np.array_equal(a[col].to_numpy(), c[col].to_numpy()), col
+
+
+def _structural_checks(sk, df, n_expected):
+    """Size-independent properties of a correct result (used where the oracle is too slow)."""
+    g = sk.graph
+    n = g.shape[0]
+    assert n == n_expected
+    assert (g != g.T).nnz == 0                                  # symmetric
+    assert g.has_sorted_indices
+    deg = np.diff(g.indptr)
+    assert np.array_equal(deg, sk.degrees)
+    p = sk.paths
+    src = p.indices[p.indptr[:-1]]
+    dst = p.indices[p.indptr[1:] - 1]
+    cyc = src == dst
+    assert np.all((deg[src] != 2) | cyc) and np.all((deg[dst] != 2) | cyc)
+    # interior path nodes have degree 2 and appear on exactly one path
+    interior = np.ones(p.indices.size, bool)
+    interior[p.indptr[:-1]] = False
+    interior[p.indptr[1:] - 1] = False
+    assert np.all(deg[p.indices[interior]] == 2)
+    counts = np.bincount(p.indices[interior], minlength=n)
+    assert counts.max() <= 1
+    # every edge of the graph lies on exactly one path: sum over paths of (len - 1) == E / 2
+    assert int(np.sum(np.diff(p.indptr) - 1)) == g.nnz // 2
+    # consecutive path nodes are adjacent; branch_distance is the sum of those weights
+    a, b = p.indices[:-1], p.indices[1:]
+    inside = np.ones(a.size, bool)
+    inside[p.indptr[1:-1] - 1] = False
+    w = np.asarray(g[a[inside], b[inside]]).ravel()
+    assert np.all(w > 0)
+    seg = np.repeat(np.arange(p.shape[0]), np.diff(p.indptr) - 1)
+    np.testing.assert_allclose(np.bincount(seg, weights=w, minlength=p.shape[0]), df['branch_distance'].to_numpy(),
+                               rtol=1e-12)
+    # skeleton ids agree with SciPy's component labels of the final graph
+    from scipy.sparse import csgraph
+    _, lab = csgraph.connected_components(g, directed=False)
+    assert np.array_equal(lab[src], df['skeleton_id'].to_numpy())
+
+
+@pytest.mark.slow
+def test_config2_size_properties():
+    """BASELINE configs[1]: 16384 x 16384 float32-valued skeleton; structural properties at full size."""
+    shape = (16384, 16384)
+    mask = walks_device(shape, 8192, 512, seed=2, device='cuda', isolated=1000, rings=64)
+    gen = torch.Generator(device='cuda').manual_seed(2)
+    img = (torch.rand(shape, device='cuda', generator=gen) * 0.9 + 0.1) * mask
+    n_expected = int(mask.sum().item())
+    del mask
+    sk = skan_b200.Skeleton(img, keep_images=False)
+    df = skan_b200.summarize(sk, separator='_')
+    _structural_checks(sk, df, n_expected)
+    pv = sk.pixel_values
+    assert pv.dtype == np.float32 and np.all(pv > 0)
+    means = df['mean_pixel_value'].to_numpy()
+    assert np.all((means >= 0.1 - 1e-6) & (means <= 1.0 + 1e-6))
+
+
+@pytest.mark.slow
+def test_config4_size_properties():
+    """BASELINE configs[3]: 1024^3 boolean volume, spacing (0.5, 0.1, 0.1)."""
+    shape = (1024, 1024, 1024)
+    img = walks_device(shape, 2048, 512, seed=4, device='cuda', isolated=1000, rings=64)
+    n_expected = int(img.sum().item())
+    sk = skan_b200.Skeleton(img, spacing=(0.5, 0.1, 0.1), keep_images=False)
+    df = skan_b200.summarize(sk, separator='_')
+    _structural_checks(sk, df, n_expected)
+
+
+@pytest.mark.slow
+def test_more_than_2_pow_32_voxels():
+    """Raveled indices beyond 2^32: a small skeleton stamped at the far corner of a 4.4 Gvox volume
+    must give the graph of the same skeleton in a small volume, translated."""
+    small = walks((40, 48, 56), 16, 64, seed=21, isolated=3, rings=2)
+    shape = (2100, 1500, 1400)
+    off = (shape[0] - 41, shape[1] - 50, shape[2] - 57)
+    big = torch.zeros(shape, dtype=torch.bool, device='cuda')
+    big[off[0]:off[0] + 40, off[1]:off[1] + 48, off[2]:off[2] + 56] = torch.from_numpy(small).cuda()
+    a = skan_b200.Skeleton(small, spacing=(0.5, 0.1, 0.1))
+    b = skan_b200.Skeleton(big, spacing=(0.5, 0.1, 0.1), keep_images=False)
+    assert np.array_equal(a.graph.indptr, b.graph.indptr)
+    assert np.array_equal(a.graph.indices, b.graph.indices)
+    assert np.array_equal(a.graph.data, b.graph.data)
+    assert np.array_equal(a.coordinates + np.array(off), b.coordinates)
+    assert np.array_equal(a.paths.indices, b.paths.indices)
+    assert np.array_equal(a.path_lengths(), b.path_lengths())
