@@ -274,7 +274,7 @@ def main():
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': dtype_name, 'data': 'synthetic',
-            'config': {'workload': args.workload, 'shape': list(shape), 'spacing': list(np.atleast_1d(spacing)),
+            'config': {'workload': args.workload, 'shape': list(shape), 'spacing': [float(x) for x in np.atleast_1d(spacing)],
                        'l2': 'input larger than L2 (no flush needed)' if V * esize > 256e6 else 'input fits L2',
                        'pack_variant': _pipeline.default_pack_variant, **counts},
             'roofline': roofline, 'clocks': clocks.summary(), 'gpu_launches': int(launches),
