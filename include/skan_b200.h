@@ -41,7 +41,7 @@ int64_t skb_kernel_launches(void);         /* kernels launched by the library si
 
 /* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes
  * (csr.py:1070, 122-123, 131).  Reads the image once; writes 1 bit per voxel (u64 words,
- * little-endian bit order, ntiles*256 words; the caller keeps one zeroed pad word on either
+ * little-endian bit order, ntiles*256 words; the caller keeps two zeroed pad words on either
  * side) and the foreground count of every 16384-voxel tile.  `image` must be 16-byte aligned.
  * variant 0: 128-bit streaming loads; variant 1: TMA bulk copies staged in shared memory. */
 int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, uint32_t* tile_counts,
@@ -94,35 +94,53 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
                  const int64_t* lin, const uint32_t* keep, const int32_t* indptr, int64_t n, const double* wtab,
                  const double* values, int height, int dtype, int32_t* indices, double* data, void* stream);
 
-/* Connected components (csr.py:909; label = minimum node id of the component) and node classes
- * for path tracing: ntype 0 isolated, 1 chain (degree 2), 2 terminal (degree 1 or >= 3),
- * 3 start of a junction-free cycle (csr.py:369-386).  root_rank u32[n+1]: rank of a component's
- * minimum among all minima = the reference's skeleton id.  Scratch: par i32[n], has_terminal u8[n]. */
-int skb_components(const int32_t* indptr, const int32_t* indices, int64_t n, int32_t* par, uint8_t* has_terminal,
-                   int32_t* label, uint8_t* ntype, uint32_t* root_rank, void* scratch, void* stream);
+/* ---- Path tracing -- replaces _build_paths / _walk_path (csr.py:347-409) ---------------------
+ * Sampled list ranking: every half-edge leaving a terminal (degree 1 or >= 3) and both half-edges
+ * of every "splitter" (a 1/32 hash sample of the degree-2 nodes) start a bounded local walk to the
+ * next terminal or splitter; the list of starts is ranked by pointer jumping; a second local walk
+ * writes the path entries.  Phase 0 handles paths between terminals, phase 1 junction-free cycles
+ * (csr.py:369-386), whose minimum node is flagged as a "cycle root" and acts as a terminal. */
+typedef struct skb_i4 { int32_t x, y, z, w; } skb_i4; /* 16-byte aligned */
 
-/* Path tracing -- replaces _build_paths / _walk_path (csr.py:347-409) by pointer-jumping list
- * ranking over half-edges.  arcs i2[ne]: x = -1 - (CSR position of the reversed last half-edge
- * of the list), y = half-edges after this one.  Returns rounds; synchronises once per round. */
-int skb_rank_arcs(const int32_t* indptr, const int32_t* indices, const uint8_t* ntype, int64_t n, int64_t ne,
-                  skb_i2* arcs, int32_t* flag, void* stream);
-/* count u64[n+1]: paths starting at each node, scanned in place; count[n] = cycles<<32 | regular */
-int skb_path_count(const int32_t* indptr, const uint8_t* ntype, const skb_i2* arcs, int64_t n, uint64_t* count,
-                   void* scratch, void* stream);
-/* start_node i32[P], pindptr i32[P+1] (= paths.indptr), einfo i2[ne] */
-int skb_path_starts(const int32_t* indptr, const uint8_t* ntype, const skb_i2* arcs, const uint64_t* prefix,
-                    int64_t n, int64_t ne, int64_t n_regular, int64_t n_paths, int32_t* start_node,
-                    int32_t* pindptr, skb_i2* einfo, void* scratch, void* stream);
-/* paths.indices i32[L], paths.data f64[L] (csr.py:396,402,442-445); values NULL -> 1.0 */
-int skb_path_emit(const int32_t* indices, const skb_i2* arcs, const skb_i2* einfo, const int32_t* pindptr,
-                  const int32_t* start_node, const double* values, int64_t ne, int32_t* pidx, double* pdata,
-                  void* stream);
+/* rec i4[n] = (n0, n1, indptr[v], degree | flags); n_chain u32[1] = number of degree-2 nodes */
+int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,
+                     void* stream);
+/* startoff u32[n+1]: exclusive scan of the walk starts per node (phase 1 needs covered u8[n]) */
+int skb_path_start_count(const int32_t* indptr, const skb_i4* rec, const uint8_t* covered, int64_t n, int phase,
+                         uint32_t* startoff, void* scratch, void* stream);
+/* su/se i32[S]: node and half-edge of each start; ranked i4[S]: result of the first local walk */
+int skb_path_walk(const int32_t* indptr, const int32_t* indices, const skb_i4* rec, const uint32_t* startoff,
+                  int64_t n, int64_t n_starts, int32_t* su, int32_t* se, skb_i4* ranked, void* stream);
+/* pointer jumping over the starts, ping-pong buf0 <-> buf1 (i4[S] each); returns 2*rounds + index of
+ * the buffer holding the result; synchronises every round after the third */
+int skb_path_rank(skb_i4* buf0, skb_i4* buf1, int64_t n_starts, int32_t* flag, void* stream);
+/* sel u32[S+1]: exclusive scan of "this start is the head of an emitted path"  */
+int skb_path_select(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, int64_t n_starts, int phase,
+                    uint32_t* sel, void* scratch, void* stream);
+/* per path pid_base + k: start_node i32, plen u32 (entries), pmin i32 (minimum node id); einfo i2[S] */
+int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const uint32_t* sel,
+                   int64_t n_starts, int phase, int64_t pid_base, int32_t* start_node, uint32_t* plen,
+                   int32_t* pmin, skb_i2* einfo, void* stream);
+/* paths.indices i32[L], paths.data f64[L] (csr.py:396,402,442-445; values NULL -> 1.0) and
+ * pw f64[L] = weight of the edge arriving at each entry; covered u8[n] (optional) marks chain nodes */
+int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec, const int32_t* su,
+                  const int32_t* se, const skb_i4* ranked, const skb_i2* einfo, const int32_t* pindptr,
+                  const double* values, uint8_t* covered, int64_t n_starts, int32_t* pidx, double* pdata,
+                  double* pw, void* stream);
+/* flags the minimum node of every component of uncovered degree-2 nodes in rec; scratch par i32[n] */
+int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, void* stream);
 
-/* Per-path statistics -- replaces _compute_distances (csr.py:962-977), path_means and
- * path_stdev (csr.py:792-816; NumPy reduceat summation order).  NULL outputs are skipped. */
-int skb_path_stats(const int32_t* gindptr, const int32_t* gindices, const double* gdata, const int32_t* pindptr,
-                   const int32_t* pidx, const double* pdata, int64_t n_paths, double* dist, double* mean,
-                   double* stdev, void* stream);
+/* Skeleton ids -- replaces csgraph.connected_components (csr.py:909) on the graph contracted to
+ * terminals and paths; skel_id i32[P] = rank of the component's minimum node id.
+ * Scratch: par i32[n], cmin i32[n], rank u32[n+1]. */
+int skb_skeleton_ids(const skb_i4* rec, const int32_t* pindptr, const int32_t* pidx, const int32_t* pmin,
+                     int64_t n, int64_t n_regular, int64_t n_paths, int32_t* par, int32_t* cmin, uint32_t* rank,
+                     int32_t* skel_id, void* scratch, void* stream);
+
+/* Per-path statistics -- replaces _compute_distances (csr.py:962-977, left-to-right sum of pw),
+ * path_means and path_stdev (csr.py:792-816; NumPy reduceat summation order).  NULL outputs are skipped. */
+int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
+                   double* mean, double* stdev, void* stream);
 
 /* Branch table -- the remaining columns of summarize (csr.py:909-952) as three SoA buffers:
  *   out_i32[3][P]            skeleton_id, node_id_src, node_id_dst
@@ -131,9 +149,8 @@ int skb_path_stats(const int32_t* gindptr, const int32_t* gindices, const double
  * (coord_* carry int64 bit patterns when spacing_is_int).  spacing_f / spacing_i are host arrays. */
 int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, const double* spacing_f /*host*/,
                      const int64_t* spacing_i /*host*/, const int32_t* pindptr, const int32_t* pidx,
-                     const int32_t* gindptr, const int32_t* label, const uint32_t* root_rank,
-                     const int64_t* coords, const double* values, int32_t* out_i32, int64_t* out_i64,
-                     double* out_f64, void* stream);
+                     const int32_t* gindptr, const int32_t* skel_id, const int64_t* coords, const double* values,
+                     int32_t* out_i32, int64_t* out_i64, double* out_f64, void* stream);
 
 /* Skeleton.path_label_image (csr.py:776-790); image i64[V] zeroed by the caller */
 int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int64_t* lin, int64_t n_paths,

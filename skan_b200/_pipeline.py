@@ -148,10 +148,10 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
     g = SimpleNamespace(ctx=ctx, shape=tuple(shape), ndim=ndim, np_dtype=np_dtype, dtype_code=code,
                         spacing=spacing, value_is_height=bool(value_is_height), nvox=V)
     # --- mask sweep: 1 bit / voxel + per-tile counts, then the tile prefix ------------------
-    store = ctx.empty(ntiles * 256 + 2, torch.int64)
-    store[0] = 0
-    store[-1] = 0
-    bits = store[1:-1]
+    store = ctx.empty(ntiles * 256 + 4, torch.int64)   # two zero pad words on either side (16-byte aligned mask)
+    store[:2] = 0
+    store[-2:] = 0
+    bits = store[2:-2]
     tile_prefix = ctx.empty(ntiles + 1, torch.int32)
     if V > 0:
         ctx.call('skb_pack_count', img, code, V, bits, tile_prefix, ntiles, variant)
@@ -227,46 +227,105 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
     return g
 
 
-def trace_paths(ctx, indptr, indices, values, n_nodes, n_edges):
-    """_build_skeleton_path_graph on the device (csr.py:412-446) plus the component labels that
-    summarize needs (csr.py:909).  Raises ValueError when there is no path, like the reference's
-    csr_matrix constructor does at csr.py:442."""
+def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
+    """_build_skeleton_path_graph on the device (csr.py:412-446) by sampled list ranking, plus the
+    skeleton ids summarize needs (csr.py:909).  Raises ValueError when there is no path, like the
+    reference's csr_matrix constructor does at csr.py:442."""
     N, E = n_nodes, n_edges
-    p = SimpleNamespace()
-    par = ctx.empty(max(N, 1), torch.int32)
-    hast = ctx.empty(max(N, 1), torch.uint8)
-    label = ctx.empty(max(N, 1), torch.int32)
-    ntype = ctx.empty(max(N, 1), torch.uint8)
-    root_rank = ctx.empty(N + 1, torch.int32)
-    ctx.call('skb_components', indptr, indices, N, par, hast, label, ntype, root_rank, ctx.scratch(N))
-    arcs = ctx.empty((max(E, 1), 2), torch.int32)
-    flag = ctx.empty(1, torch.int32)
-    p.rank_rounds = ctx.call('skb_rank_arcs', indptr, indices, ntype, N, E, arcs, flag)
-    pcount = ctx.empty(N + 1, torch.int64)
-    ctx.call('skb_path_count', indptr, ntype, arcs, N, pcount, ctx.scratch(N))
-    tot = int(pcount[N].item())
-    n_regular, n_cycles = tot & 0xffffffff, tot >> 32
+    p = SimpleNamespace(n_nodes=N)
+    if N == 0 or E == 0:
+        raise ValueError('index pointer size 0 should be 1')
+    rec = ctx.empty((N, 4), torch.int32)
+    n_chain_t = ctx.empty(1, torch.int32)
+    ctx.call('skb_path_records', indptr, indices, N, rec, n_chain_t)
+    p.rec = rec
+
+    def phase(ph, covered, pid_base):
+        startoff = ctx.empty(N + 1, torch.int32)
+        ctx.call('skb_path_start_count', indptr, rec, covered, N, ph, startoff, ctx.scratch(N))
+        S = int(startoff[N].item())
+        if S == 0:
+            return None
+        su = ctx.empty(S, torch.int32)
+        se = ctx.empty(S, torch.int32)
+        buf = [ctx.empty((S, 4), torch.int32), ctx.empty((S, 4), torch.int32)]
+        flag = ctx.empty(1, torch.int32)
+        ctx.call('skb_path_walk', indptr, indices, rec, startoff, N, S, su, se, buf[0])
+        r = ctx.call('skb_path_rank', buf[0], buf[1], S, flag)
+        ranked = buf[r & 1]
+        sel = ctx.empty(S + 1, torch.int32)
+        ctx.call('skb_path_select', su, rec, ranked, S, ph, sel, ctx.scratch(S))
+        return SimpleNamespace(S=S, su=su, se=se, ranked=ranked, sel=sel, rounds=r >> 1, phase=ph, pid_base=pid_base)
+
+    def heads(ph, start_node, plen, pmin):
+        ph.einfo = ctx.empty((ph.S, 2), torch.int32)
+        ctx.call('skb_path_heads', ph.su, rec, ph.ranked, ph.sel, ph.S, ph.phase, ph.pid_base, start_node, plen, pmin,
+                 ph.einfo)
+
+    def emit(ph, pindptr, covered, pidx, pdata, pw):
+        ctx.call('skb_path_emit', indices, gdata, rec, ph.su, ph.se, ph.ranked, ph.einfo, pindptr, values, covered,
+                 ph.S, pidx, pdata, pw)
+
+    # ---- phase 0: paths between terminals -----------------------------------------------------
+    a = phase(0, None, 0)
+    n_regular = int(a.sel[a.S].item()) if a is not None else 0
+    n_chain = int(n_chain_t.item())
+    p.rank_rounds = a.rounds if a is not None else 0
+    # every path entry that is not a path end is a degree-2 node, and each is on exactly one path:
+    # what the regular paths do not cover lies on junction-free cycles (csr.py:369-386)
+    cap_cycles_hint = n_chain  # refined below once the regular path lengths are known
+    P_cap = n_regular + n_chain // 3 + 1
+    start_node = ctx.empty(P_cap, torch.int32)
+    plen = ctx.empty(P_cap + 1, torch.int32)
+    pmin = ctx.empty(P_cap, torch.int32)
+    pindptr = ctx.empty(P_cap + 1, torch.int32)
+    L_reg = 0
+    if n_regular:
+        heads(a, start_node, plen, pmin)
+        ctx.call('skb_scan_u32', plen, pindptr, n_regular, ctx.scratch(n_regular))
+        L_reg = int(pindptr[n_regular].item())
+    n_uncovered = n_chain - (L_reg - 2 * n_regular)
+    L_cap = L_reg + n_uncovered + n_uncovered // 3 + 1
+    pidx = ctx.empty(L_cap, torch.int32)
+    pdata = ctx.empty(L_cap, torch.float64)
+    pw = ctx.empty(L_cap, torch.float64)
+    covered = None
+    if n_uncovered > 0:
+        covered = torch.zeros(N, dtype=torch.uint8, device=ctx.device)
+    if n_regular:
+        emit(a, pindptr, covered, pidx, pdata, pw)
+    # ---- phase 1: junction-free cycles ----------------------------------------------------------
+    n_cycles = 0
+    if n_uncovered > 0:
+        par = ctx.empty(N, torch.int32)
+        ctx.call('skb_cycle_roots', rec, covered, N, par)
+        b = phase(1, covered, n_regular)
+        n_cycles = int(b.sel[b.S].item())
+        heads(b, start_node, plen, pmin)
+        P = n_regular + n_cycles
+        ctx.call('skb_scan_u32', plen, pindptr, P, ctx.scratch(P))
+        emit(b, pindptr, None, pidx, pdata, pw)
     P = n_regular + n_cycles
-    p.label, p.ntype, p.root_rank, p.n_paths, p.n_cycles = label, ntype, root_rank, P, n_cycles
     if P == 0:
         raise ValueError('index pointer size 0 should be 1')
-    start_node = ctx.empty(P, torch.int32)
-    pindptr = ctx.empty(P + 1, torch.int32)
-    einfo = ctx.empty((max(E, 1), 2), torch.int32)
-    ctx.call('skb_path_starts', indptr, ntype, arcs, pcount, N, E, n_regular, P, start_node, pindptr, einfo,
-             ctx.scratch(P))
-    L = int(pindptr[P].item())
-    pidx = ctx.empty(L, torch.int32)
-    pdata = ctx.empty(L, torch.float64)
-    ctx.call('skb_path_emit', indices, arcs, einfo, pindptr, start_node, values, E, pidx, pdata)
-    p.indptr, p.indices, p.data, p.n_entries = pindptr, pidx, pdata, L
+    L = L_reg + n_uncovered + n_cycles
+    p.n_paths, p.n_cycles, p.n_regular, p.n_entries = P, n_cycles, n_regular, L
+    p.indptr, p.indices, p.data, p.weights = pindptr[:P + 1], pidx[:L], pdata[:L], pw[:L]
+    # ---- skeleton ids ---------------------------------------------------------------------------
+    par = ctx.empty(N, torch.int32)
+    cmin = ctx.empty(N, torch.int32)
+    rank = ctx.empty(N + 1, torch.int32)
+    skel_id = ctx.empty(P, torch.int32)
+    ctx.call('skb_skeleton_ids', rec, p.indptr, p.indices, pmin, N, n_regular, P, par, cmin, rank, skel_id,
+             ctx.scratch(N))
+    p.skeleton_id = skel_id
     return p
 
 
-def path_stats(ctx, gindptr, gindices, gdata, p, *, dist=True, mean=True, stdev=True):
+def path_stats(ctx, p, *, dist=True, mean=True, stdev=True):
     P = p.n_paths
     out = [ctx.empty(P, torch.float64) if want else None for want in (dist, mean, stdev)]
-    ctx.call('skb_path_stats', gindptr, gindices, gdata, p.indptr, p.indices, p.data, P, *out)
+    ctx.call('skb_path_stats', p.indptr, p.data, p.weights, P, *out)
     return out
 
 
@@ -285,7 +344,7 @@ def branch_table(ctx, p, gindptr, coords, values, spacing, ndim, value_is_height
     o64 = ctx.empty((1 + 2 * ndim, P), torch.int64)
     of = ctx.empty((2 * dh + 1, P), torch.float64)
     ctx.call('skb_branch_table', P, ndim, height, 1 if sp_is_int else 0, sp_f.data_ptr(), sp_i.data_ptr(),
-             p.indptr, p.indices, gindptr, p.label, p.root_rank, coords, values, o32, o64, of)
+             p.indptr, p.indices, gindptr, p.skeleton_id, coords, values, o32, o64, of)
     return o32, o64, of, sp_is_int
 
 
@@ -294,8 +353,8 @@ def skeleton_and_summary_device(image, *, spacing=1, value_is_height=False, devi
     paths, per-path statistics and the branch table (what Skeleton(...) + summarize(...) compute)."""
     g = pixel_graph(image, spacing=spacing, value_is_height=value_is_height, device=device,
                     pack_variant=pack_variant)
-    p = trace_paths(g.ctx, g.indptr, g.indices, g.values, g.n_nodes, g.n_edges)
-    dist, mean, stdev = path_stats(g.ctx, g.indptr, g.indices, g.data, p)
+    p = trace_paths(g.ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges)
+    dist, mean, stdev = path_stats(g.ctx, p)
     o32, o64, of, _ = branch_table(g.ctx, p, g.indptr, g.coords, g.values, spacing, g.ndim, value_is_height)
     return SimpleNamespace(graph=g, paths=p, dist=dist, mean=mean, stdev=stdev, table=(o32, o64, of))
 

@@ -81,7 +81,7 @@ class Skeleton:
         self._coords_dev = g.coords
         self._graph_dev = (g.indptr, g.indices, g.data)
         self._n_nodes = g.n_nodes
-        self._p = _pipeline.trace_paths(g.ctx, g.indptr, g.indices, g.values, g.n_nodes, g.n_edges)
+        self._p = _pipeline.trace_paths(g.ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges)
         self.n_paths = self._p.n_paths
         self._host = {}
         self._stats = None
@@ -160,8 +160,7 @@ class Skeleton:
 
     def _device_stats(self):
         if self._stats is None:
-            indptr, indices, data = self._graph_dev
-            self._stats = _pipeline.path_stats(self._ctx, indptr, indices, data, self._p)
+            self._stats = _pipeline.path_stats(self._ctx, self._p)
         return self._stats
 
     @property
@@ -247,7 +246,7 @@ class PathGraph:
         values = None
         if node_values is not None:
             values = torch.from_numpy(np.ascontiguousarray(node_values, dtype=np.float64)).to(ctx.device)
-        p = _pipeline.trace_paths(ctx, indptr, indices, values, n, int(adj.indices.size))
+        p = _pipeline.trace_paths(ctx, indptr, indices, data, values, n, int(adj.indices.size))
         paths = sparse.csr_matrix((_to_host(p.data), _to_host(p.indices), _to_host(p.indptr)),
                                   shape=(p.n_paths, p.n_entries))
         dev = dict(ctx=ctx, indptr=indptr, indices=indices, data=data, values=values, p=p)
@@ -264,8 +263,7 @@ class PathGraph:
     def distances(self):
         if self._distances is None:
             d = self._dev
-            dist, _, _ = _pipeline.path_stats(d['ctx'], d['indptr'], d['indices'], d['data'], d['p'],
-                                              mean=False, stdev=False)
+            dist, _, _ = _pipeline.path_stats(d['ctx'], d['p'], mean=False, stdev=False)
             self._distances = _to_host(dist)
         return self._distances
 
@@ -327,7 +325,7 @@ def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=
     spacing = skel.spacing
     if value_is_height and skel._values_dev is None:
         raise TypeError("'NoneType' object is not subscriptable")  # csr.py:933 on a boolean skeleton
-    dist, mean, stdev = _pipeline.path_stats(ctx, indptr, indices, data, p)
+    dist, mean, stdev = _pipeline.path_stats(ctx, p)
     o32, o64, of, sp_is_int = _pipeline.branch_table(ctx, p, indptr, skel._coords_dev, skel._values_dev,
                                                       spacing, ndim, value_is_height)
     o32, o64, of = _to_host(o32), _to_host(o64), _to_host(of)

@@ -117,86 +117,122 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
     return skb_foreach(n, (skb_stream_t)stream, it);
 }
 
-// connected components + node classes (csr.py:909; cycle detection for csr.py:369-386).
-// Scratch: par i32[n], has_terminal u8[n].  Out: label i32[n] (= minimum node id of the
-// component), ntype u8[n], root_rank u32[n+1] (rank of a component's minimum among all minima).
-int skb_components(const int32_t* indptr, const int32_t* indices, int64_t n, int32_t* par, uint8_t* has_terminal,
-                   int32_t* label, uint8_t* ntype, uint32_t* root_rank, void* scratch, void* stream) {
+// ---- path tracing (csr.py:347-446): sampled list ranking, see skb_items.cuh ------------------
+// rec i4[n] (n0, n1, indptr, degree|flags) and the number of degree-2 nodes (n_chain u32[1])
+int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,
+                     void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_fill_bytes(n_chain, 0, 4, s));
+    return skb_foreach(n, s, SkbPathRecItem{indptr, indices, rec, n_chain});
+}
+
+// walk starts per node, scanned in place: startoff u32[n+1].  phase 0: terminals + splitters;
+// phase 1: cycle roots + uncovered splitters (covered u8[n] must be given).
+int skb_path_start_count(const int32_t* indptr, const skb_i4* rec, const uint8_t* covered, int64_t n, int phase,
+                         uint32_t* startoff, void* scratch, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    if (phase != 0 && !covered) return skb_fail("phase 1 needs the covered marks");
+    SKB_TRY(skb_foreach(n, s, SkbStartCountItem{indptr, rec, covered, phase, startoff}));
+    return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
+}
+
+// su/se i32[S] (node and half-edge of every start) and the first local walk: ranked i4[S]
+int skb_path_walk(const int32_t* indptr, const int32_t* indices, const skb_i4* rec, const uint32_t* startoff,
+                  int64_t n, int64_t n_starts, int32_t* su, int32_t* se, skb_i4* ranked, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_foreach(n, s, SkbStartFillItem{indptr, startoff, su, se}));
+    return skb_foreach(n_starts, s, SkbWalkItem{indices, rec, startoff, su, se, ranked});
+}
+
+// pointer jumping over the starts (synchronous rounds, ping-pong between buf0 and buf1).
+// Stops after the first round in which no start reaches its list end: every list that ends at
+// a terminal is then finished, what is left cycles.  Returns 2*rounds + (index of the result buffer).
+int skb_path_rank(skb_i4* buf0, skb_i4* buf1, int64_t n_starts, int32_t* flag, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    if (n_starts <= 0) return 0;
+    skb_i4* b[2] = {buf0, buf1};
+    int cur = 0, rounds = 0;
+    const int blind = 3;  // rounds run before the first host check (lists of up to 8 starts)
+    for (;; ++rounds) {
+        if (rounds > 40) return skb_fail("list ranking did not converge");
+        if (rounds >= blind || rounds == 0) SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
+        SKB_TRY(skb_foreach(n_starts, s, SkbJumpItem{b[cur], b[cur ^ 1], flag}));
+        cur ^= 1;
+        if (rounds + 1 >= blind) {
+            int32_t any = 0;
+            SKB_TRY(skb_fetch_i32(flag, &any, s));
+            if (!any) {
+                ++rounds;
+                break;
+            }
+        }
+    }
+    return 2 * rounds + cur;
+}
+
+// heads of emitted paths among the starts: sel u32[S+1] = exclusive scan of the head flags
+int skb_path_select(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, int64_t n_starts, int phase,
+                    uint32_t* sel, void* scratch, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_foreach(n_starts, s, SkbSelectItem{su, rec, ranked, phase, sel}));
+    return skb_scan_u32_impl(sel, sel, n_starts, scratch, s);
+}
+
+// per path (ids pid_base + ...): start_node i32, plen u32 (entries), pmin i32; einfo i2[S]
+int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const uint32_t* sel,
+                   int64_t n_starts, int phase, int64_t pid_base, int32_t* start_node, uint32_t* plen,
+                   int32_t* pmin, skb_i2* einfo, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_fill_bytes(einfo, 0xff, (size_t)n_starts * 8, s));
+    return skb_foreach(n_starts, s,
+                       SkbHeadsItem{su, rec, ranked, sel, phase, (int32_t)pid_base, start_node, plen, pmin, einfo});
+}
+
+// second local walk: paths.indices i32[L], paths.data f64[L] (csr.py:396,402; values NULL -> 1.0),
+// pw f64[L] = weight of the edge arriving at each entry; chain nodes written are marked in
+// covered u8[n] when it is given
+int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec, const int32_t* su,
+                  const int32_t* se, const skb_i4* ranked, const skb_i2* einfo, const int32_t* pindptr,
+                  const double* values, uint8_t* covered, int64_t n_starts, int32_t* pidx, double* pdata,
+                  double* pw, void* stream) {
+    return skb_foreach(n_starts, (skb_stream_t)stream,
+                       SkbEmitItem{indices, gdata, rec, su, se, ranked, einfo, pindptr, values, covered, pidx, pdata, pw});
+}
+
+// junction-free cycles (csr.py:369-386): the minimum node of every component of uncovered
+// degree-2 nodes is flagged in rec as a cycle root.  Scratch: par i32[n].
+int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     SKB_TRY(skb_foreach(n, s, SkbIotaItem{par}));
-    SKB_TRY(skb_fill_bytes(has_terminal, 0, (size_t)n, s));
-    SKB_TRY(skb_foreach(n, s, SkbCcHookItem{indptr, indices, par}));
-    SKB_TRY(skb_foreach(n, s, SkbCcFlattenItem{indptr, par, label, has_terminal}));
-    SKB_TRY(skb_foreach(n, s, SkbNodeTypeItem{indptr, label, has_terminal, ntype, root_rank}));
-    return skb_scan_u32_impl(root_rank, root_rank, n, scratch, s);
+    SKB_TRY(skb_foreach(n, s, SkbCycleHookItem{rec, covered, par}));
+    return skb_foreach(n, s, SkbCycleRootItem{rec, covered, par});
 }
 
-// list ranking of the half-edge lists (csr.py:347-409).  arcs i2[ne], flag i32[1]. Returns rounds.
-int skb_rank_arcs(const int32_t* indptr, const int32_t* indices, const uint8_t* ntype, int64_t n, int64_t ne,
-                  skb_i2* arcs, int32_t* flag, void* stream) {
+// skeleton ids (csr.py:909): connected components of the contracted graph, labelled by the rank
+// of each component's minimum node id.  Scratch: par i32[n], cmin i32[n], rank u32[n+1].
+int skb_skeleton_ids(const skb_i4* rec, const int32_t* pindptr, const int32_t* pidx, const int32_t* pmin,
+                     int64_t n, int64_t n_regular, int64_t n_paths, int32_t* par, int32_t* cmin, uint32_t* rank,
+                     int32_t* skel_id, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    if (ne <= 0) return 0;
-    SKB_TRY(skb_foreach(n, s, SkbArcInitItem{indptr, indices, ntype, arcs}));
-    int rounds = 0;
-    for (;; ++rounds) {
-        if (rounds > 48) return skb_fail("list ranking did not converge");
-        SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
-        // three launches of two jumps each between host checks: 2^6 arcs per check at least
-        SKB_TRY(skb_foreach(ne, s, SkbArcJumpItem{arcs, flag, 2}));
-        SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
-        SKB_TRY(skb_foreach(ne, s, SkbArcJumpItem{arcs, flag, 2}));
-        SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
-        SKB_TRY(skb_foreach(ne, s, SkbArcJumpItem{arcs, flag, 2}));
-        int32_t any = 0;
-        SKB_TRY(skb_fetch_i32(flag, &any, s));
-        if (!any) break;
-    }
-    return rounds;
-}
-
-// number of paths starting at every node: count u64[n+1] -> exclusive scan in place;
-// count[n] = (cycle paths << 32) | regular paths
-int skb_path_count(const int32_t* indptr, const uint8_t* ntype, const skb_i2* arcs, int64_t n, uint64_t* count,
-                   void* scratch, void* stream) {
-    skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_foreach(n, s, SkbPathCountItem{indptr, ntype, arcs, count}));
-    return skb_scan_u64_impl(count, count, n, scratch, s);
-}
-
-// path ids: start_node i32[P], plen u32[P+1] -> scanned into paths.indptr i32[P+1];
-// einfo i2[ne] tags every emitted list by its (reversed) last half-edge
-int skb_path_starts(const int32_t* indptr, const uint8_t* ntype, const skb_i2* arcs, const uint64_t* prefix,
-                    int64_t n, int64_t ne, int64_t n_regular, int64_t n_paths, int32_t* start_node,
-                    int32_t* pindptr, skb_i2* einfo, void* scratch, void* stream) {
-    skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_fill_bytes(einfo, 0xff, (size_t)ne * 8, s));
-    SKB_TRY(skb_foreach(
-        n, s, SkbPathStartItem{indptr, ntype, arcs, prefix, (uint32_t)n_regular, start_node, (uint32_t*)pindptr, einfo}));
-    return skb_scan_u32_impl((const uint32_t*)pindptr, (uint32_t*)pindptr, n_paths, scratch, s);
-}
-
-// paths.indices i32[L], paths.data f64[L] (csr.py:396,402: node values, 1.0 without values)
-int skb_path_emit(const int32_t* indices, const skb_i2* arcs, const skb_i2* einfo, const int32_t* pindptr,
-                  const int32_t* start_node, const double* values, int64_t ne, int32_t* pidx, double* pdata,
-                  void* stream) {
-    return skb_foreach(ne, (skb_stream_t)stream,
-                       SkbPathEmitItem{indices, arcs, einfo, pindptr, start_node, values, pidx, pdata});
+    SKB_TRY(skb_foreach(n, s, SkbCcInitItem{par, cmin, rank}));
+    SKB_TRY(skb_foreach(n_regular, s, SkbCcPathUnionItem{pindptr, pidx, par}));
+    SKB_TRY(skb_foreach(n_regular, s, SkbCcPathMinItem{pindptr, pidx, pmin, par, cmin}));
+    SKB_TRY(skb_foreach(n, s, SkbCcMarkItem{rec, par, cmin, rank}));
+    SKB_TRY(skb_scan_u32_impl(rank, rank, n, scratch, s));
+    return skb_foreach(n_paths, s, SkbCcPathIdItem{pindptr, pidx, (int32_t)n_regular, par, cmin, rank, skel_id});
 }
 
 // branch_distance / mean / stdev per path (csr.py:962-977, 792-816); null outputs are skipped
-int skb_path_stats(const int32_t* gindptr, const int32_t* gindices, const double* gdata, const int32_t* pindptr,
-                   const int32_t* pidx, const double* pdata, int64_t n_paths, double* dist, double* mean,
-                   double* stdev, void* stream) {
-    return skb_foreach(n_paths, (skb_stream_t)stream,
-                       SkbPathStatsItem{gindptr, gindices, gdata, pindptr, pidx, pdata, dist, mean, stdev});
+int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
+                   double* mean, double* stdev, void* stream) {
+    return skb_foreach(n_paths, (skb_stream_t)stream, SkbPathStatsItem{pindptr, pdata, pw, dist, mean, stdev});
 }
 
 // the remaining columns of summarize() (csr.py:909-952)
 int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, const double* spacing_f,
                      const int64_t* spacing_i, const int32_t* pindptr, const int32_t* pidx,
-                     const int32_t* gindptr, const int32_t* label, const uint32_t* root_rank,
-                     const int64_t* coords, const double* values, int32_t* out_i32, int64_t* out_i64,
-                     double* out_f64, void* stream) {
+                     const int32_t* gindptr, const int32_t* skel_id, const int64_t* coords, const double* values,
+                     int32_t* out_i32, int64_t* out_i64, double* out_f64, void* stream) {
     if (ndim < 1 || ndim > 3) return skb_fail("ndim must be 1, 2 or 3");
     if (height && !values) return skb_fail("height mode needs node values");
     SkbBranchItem it;
@@ -207,8 +243,7 @@ int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, 
     it.pindptr = pindptr;
     it.pidx = pidx;
     it.gindptr = gindptr;
-    it.label = label;
-    it.root_rank = root_rank;
+    it.skel_id = skel_id;
     it.coords = coords;
     it.values = values;
     for (int i = 0; i < 3; ++i) {

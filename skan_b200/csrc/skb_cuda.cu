@@ -453,28 +453,19 @@ static int skb_pack_launch(const void* img, int64_t nvox, bool is_float, uint64_
 }
 
 // ------------------------------------------------------------------------------- node emission
-// One CTA per 16384-voxel tile of the mask (256 u64 words, one per thread): rank structure
-// (pre256), raveled index, coordinates (csr.py:1088) and fp64 values (csr.py:554-562) of
-// every foreground voxel, in raster order (csr.py:131-132).  Reads V/8 bytes of mask.
-__global__ void __launch_bounds__(SKB_TILE_WORDS) skb_emit_nodes_kernel(
-    const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, SkbGeom g, const void* img,
-    int dtype, int64_t* __restrict__ lin, int64_t* __restrict__ coords, double* __restrict__ values,
-    uint32_t* __restrict__ pre256) {
-    const int64_t tile = blockIdx.x;
-    const int64_t w = tile * SKB_TILE_WORDS + threadIdx.x;
-    const uint32_t t0 = tile_prefix[tile], t1 = tile_prefix[tile + 1];
-    if (t0 == t1) {  // empty tile: only the rank structure
-        if ((threadIdx.x & 3) == 0) pre256[w >> 2] = t0;
-        return;
-    }
-    uint64_t word = bits[w];
-    uint32_t total;
-    uint32_t id = t0 + skb_block_exclusive<uint32_t>((uint32_t)__popcll(word), &total);
-    if ((threadIdx.x & 3) == 0) pre256[w >> 2] = id;
+// One WARP per 16384-voxel tile of the mask (256 u64 words = 128 uint4, four per lane, loaded
+// with coalesced 128-bit loads): rank structure (pre256), raveled index, coordinates
+// (csr.py:1088) and fp64 values (csr.py:554-562) of every foreground voxel, in raster order
+// (csr.py:131-132).  Reads V/8 bytes of mask; no block-wide barrier anywhere.
+#define SKB_EMIT_THREADS 256
+
+__device__ __forceinline__ void skb_emit_word(uint64_t word, int64_t wi, uint32_t id, const SkbGeom& g,
+                                              const void* img, int dtype, int64_t* __restrict__ lin,
+                                              int64_t* __restrict__ coords, double* __restrict__ values) {
     while (word) {
         int b = __ffsll((long long)word) - 1;
         word &= word - 1;
-        int64_t r = w * 64 + b;
+        int64_t r = wi * 64 + b;
         lin[id] = r;
         int32_t z, y, x;
         skb_coords(g, r, z, y, x);
@@ -494,6 +485,49 @@ __global__ void __launch_bounds__(SKB_TILE_WORDS) skb_emit_nodes_kernel(
     }
 }
 
+__global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
+    const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, int64_t ntiles, SkbGeom g,
+    const void* img, int dtype, int64_t* __restrict__ lin, int64_t* __restrict__ coords,
+    double* __restrict__ values, uint32_t* __restrict__ pre256) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (SKB_EMIT_THREADS / 32);
+    for (int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + (threadIdx.x >> 5); tile < ntiles;
+         tile += warps) {
+        const uint32_t t0 = tile_prefix[tile], t1 = tile_prefix[tile + 1];
+        uint2* pre = (uint2*)(pre256 + tile * 64);  // 64 blocks of 256 bits per tile
+        if (t0 == t1) {  // empty tile: only the rank structure
+            pre[lane] = make_uint2(t0, t0);
+            continue;
+        }
+        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS);
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = src[j * 32 + lane];
+        uint32_t running = t0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint64_t w0 = (uint64_t)v[j].x | ((uint64_t)v[j].y << 32);
+            uint64_t w1 = (uint64_t)v[j].z | ((uint64_t)v[j].w << 32);
+            uint32_t c0 = (uint32_t)__popcll(w0), c = c0 + (uint32_t)__popcll(w1);
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            uint32_t id = running + inc - c;
+            running += __shfl_sync(0xffffffffu, inc, 31);
+            // words 2*(32 j + lane), +1: the even lane of each pair starts a 256-bit block
+            if ((lane & 1) == 0) pre256[tile * 64 + j * 16 + (lane >> 1)] = id;
+            if (c) {
+                int64_t wi = tile * SKB_TILE_WORDS + 2 * (j * 32 + lane);
+                skb_emit_word(w0, wi, id, g, img, dtype, lin, coords, values);
+                skb_emit_word(w1, wi + 1, id + c0, g, img, dtype, lin, coords, values);
+            }
+        }
+    }
+}
+
 #include "skb_api.inl"
 
 extern "C" {
@@ -510,7 +544,7 @@ int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
 int64_t skb_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_skb_launches, __ATOMIC_RELAXED); }
 
 // mask sweep (replaces csr.py:1070,122-123,131).  bits: ntiles*256 u64 words (the caller owns
-// one zeroed pad word on either side); tile_counts: u32[ntiles].  variant 0 = vector loads,
+// two zeroed pad words on either side); tile_counts: u32[ntiles].  variant 0 = vector loads,
 // 1 = TMA bulk copies through shared memory.  The image must be 16-byte aligned.
 int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, uint32_t* tile_counts,
                    int64_t ntiles, int variant, void* stream) {
@@ -536,8 +570,12 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
     SKB_TRY(skb_check_geom(ndim, shape));
     if (ntiles <= 0) return 0;
     if (values && !image) return skb_fail("values requested without an image");
-    skb_emit_nodes_kernel<<<(unsigned)ntiles, SKB_TILE_WORDS, 0, (skb_stream_t)stream>>>(
-        bits, tile_prefix, skb_make_geom(ndim, shape), image, dtype, lin, coords, values, pre256);
+    if (((uintptr_t)bits & 15) != 0) return skb_fail("mask pointer must be 16-byte aligned");
+    int64_t grid = (ntiles + SKB_EMIT_THREADS / 32 - 1) / (SKB_EMIT_THREADS / 32);
+    int64_t cap = (int64_t)skb_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    skb_emit_nodes_kernel<<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
+        bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, lin, coords, values, pre256);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
 }

@@ -6,7 +6,7 @@
 //
 // Data model (everything addressed by raster-order node id, never by a V-sized id image):
 //   bits    packed foreground mask, 1 bit / voxel in C raster order, little-endian inside u64
-//           words, one zero pad word before word 0 and after the last word
+//           words, zero pad words before word 0 and after the last word
 //   pre256  exclusive popcount prefix of `bits` at every 256-bit block  -> rank(r) = node id
 //   lin     raveled voxel index of node i (int64, ascending)                       csr.py:131
 //   nb      27-bit raw neighbourhood mask of node i; bit k27 = (dz+1)*9+(dy+1)*3+(dx+1),
@@ -433,192 +433,371 @@ struct SkbCsrEmitItem {
     }
 };
 
-// ---- stage: connected components (csr.py:909), lock-free union-find, root = minimum id ------
+// ---- stage: path tracing (csr.py:347-446) as sampled list ranking ----------------------------
+// The serial walk of the reference follows degree-2 chains between terminals (degree 1 or >= 3).
+// Here every half-edge leaving a terminal, and both half-edges leaving every "splitter" chain
+// node (a 1/32 hash sample of the degree-2 nodes), starts a bounded local walk to the next
+// terminal or splitter; the much shorter list of walk starts is then ranked by pointer jumping,
+// which gives every start its path, its distance to the path's end and the minimum node id
+// seen; a second local walk writes the path entries.  Junction-free cycles (csr.py:369-386)
+// are the degree-2 nodes no terminal-started list covers; their minimum node becomes a
+// terminal ("cycle root") and the same machinery runs again on them (phase 1).
+struct alignas(16) skb_i4 {
+    int32_t x, y, z, w;
+};
+#define SKB_REC_DEG_MASK 0xff
+#define SKB_REC_CYCLE_ROOT 0x100
+
+SKB_HD skb_i4 skb_ld_i4(const skb_i4* p) {
+#if defined(__CUDA_ARCH__)
+    int4 v = *reinterpret_cast<const int4*>(p);
+    skb_i4 r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+SKB_HD void skb_st_i4(skb_i4* p, skb_i4 v) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<int4*>(p) = make_int4(v.x, v.y, v.z, v.w);
+#else
+    *p = v;
+#endif
+}
+
+SKB_HD bool skb_is_splitter(int32_t v) { return (((uint32_t)v * 2654435761u) >> 27) == 0u; }
+
+// rec[v] = (n0, n1, indptr[v], degree | flags): the two neighbours of a degree-2 node
+struct SkbPathRecItem {  // over nodes
+    const int32_t* indptr;
+    const int32_t* indices;
+    skb_i4* rec;
+    uint32_t* n_chain;  // number of degree-2 nodes (pre-zeroed)
+    SKB_HD void operator()(int64_t v) const {
+        int32_t o = indptr[v], d = indptr[v + 1] - o;
+        skb_i4 r;
+        r.x = -1;
+        r.y = -1;
+        r.z = o;
+        r.w = d > SKB_REC_DEG_MASK ? SKB_REC_DEG_MASK : d;  // only "== 2" and row scans (bounded below) use it
+        if (d == 2) {
+            r.x = indices[o];
+            r.y = indices[o + 1];
+#if defined(__CUDA_ARCH__)
+            atomicAdd(n_chain, 1u);
+#else
+            *n_chain += 1u;
+#endif
+        }
+        skb_st_i4(rec + v, r);
+    }
+};
+
+// number of walk starts leaving node v.  phase 0: every half-edge of a terminal, both half-edges
+// of a splitter.  phase 1 (cycles): both half-edges of a cycle root and of an uncovered splitter.
+SKB_HD int32_t skb_start_count(const skb_i4& r, int32_t v, int phase, const uint8_t* covered, int32_t true_deg) {
+    int32_t d = r.w & SKB_REC_DEG_MASK;
+    if (phase == 0) {
+        if (d != 2) return true_deg;
+        return skb_is_splitter(v) ? 2 : 0;
+    }
+    if (r.w & SKB_REC_CYCLE_ROOT) return 2;
+    if (d == 2 && !covered[v] && skb_is_splitter(v)) return 2;
+    return 0;
+}
+
+struct SkbStartCountItem {  // over nodes
+    const int32_t* indptr;
+    const skb_i4* rec;
+    const uint8_t* covered;
+    int32_t phase;
+    uint32_t* count;
+    SKB_HD void operator()(int64_t v) const {
+        count[v] = (uint32_t)skb_start_count(skb_ld_i4(rec + v), (int32_t)v, phase, covered, indptr[v + 1] - indptr[v]);
+    }
+};
+
+struct SkbStartFillItem {  // over nodes: start s = startoff[v] + j  <->  half-edge (v -> indices[indptr[v]+j])
+    const int32_t* indptr;
+    const uint32_t* startoff;
+    int32_t* su;
+    int32_t* se;
+    SKB_HD void operator()(int64_t v) const {
+        uint32_t s0 = startoff[v], c = startoff[v + 1] - s0;
+        int32_t o = indptr[v];
+        for (uint32_t j = 0; j < c; ++j) {
+            su[s0 + j] = (int32_t)v;
+            se[s0 + j] = o + (int32_t)j;
+        }
+    }
+};
+
+// ranked[s] = (x, y, z, -):  x >= 0: index of the start that continues this list; x < 0: finished,
+// -1-x = index of the start that is the REVERSED last half-edge (B -> m) of the list;
+// y = half-edges from this start's node to (x >= 0: the next start's node | x < 0: the list end);
+// z = minimum node id seen so far on the list from this start on.
+struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle root / splitter
+    const int32_t* indices;
+    const skb_i4* rec;
+    const uint32_t* startoff;
+    const int32_t* su;
+    const int32_t* se;
+    skb_i4* ranked;
+    SKB_HD void operator()(int64_t s) const {
+        int32_t u = su[s];
+        int32_t prev = u, cur = indices[se[s]];
+        int32_t cnt = 1, mn = u;
+        skb_i4 out;
+        for (;;) {
+            skb_i4 r = skb_ld_i4(rec + cur);
+            if (cur < mn) mn = cur;
+            if (r.w != 2) {  // terminal or cycle root: find the reverse half-edge (cur -> prev)
+                int32_t d = r.w & SKB_REC_DEG_MASK;
+                int32_t j = 0;
+                if (d == SKB_REC_DEG_MASK) {  // saturated degree field: unbounded row, rely on symmetry
+                    while (indices[r.z + j] != prev) ++j;
+                } else {
+                    while (j + 1 < d && indices[r.z + j] != prev) ++j;
+                }
+                out.x = -1 - (int32_t)(startoff[cur] + (uint32_t)j);
+                break;
+            }
+            if (skb_is_splitter(cur)) {  // the list continues with the splitter's other half-edge
+                out.x = (int32_t)(startoff[cur] + (r.x == prev ? 1u : 0u));
+                break;
+            }
+            int32_t nxt = (r.x == prev) ? r.y : r.x;
+            prev = cur;
+            cur = nxt;
+            ++cnt;
+        }
+        out.y = cnt;
+        out.z = mn;
+        out.w = 0;
+        skb_st_i4(ranked + s, out);
+    }
+};
+
+struct SkbJumpItem {  // over starts: one synchronous pointer-jumping round, src -> dst
+    const skb_i4* src;
+    skb_i4* dst;
+    int32_t* flag;  // raised when some start reaches its list end in this round
+    SKB_HD void operator()(int64_t s) const {
+        skb_i4 a = skb_ld_i4(src + s);
+        if (a.x >= 0) {
+            skb_i4 b = skb_ld_i4(src + a.x);
+            a.y += b.y;
+            if (b.z < a.z) a.z = b.z;
+            a.x = b.x;
+            if (a.x < 0) skb_raise(flag);
+        }
+        skb_st_i4(dst + s, a);
+    }
+};
+
+// a half-edge (A,n) starts an emitted path iff it precedes the reversed last half-edge (B,m)
+// in CSR order == in start order (the serial walk of csr.py:347-409 visits start
+// nodes and their neighbours ascending and marks both directions visited)
+SKB_HD bool skb_start_is_head(const skb_i4& r_u, const skb_i4& a, int64_t s, int phase) {
+    bool end_type = phase == 0 ? ((r_u.w & SKB_REC_DEG_MASK) != 2) : ((r_u.w & SKB_REC_CYCLE_ROOT) != 0);
+    return end_type && a.x < 0 && s < (int64_t)(-1 - a.x);
+}
+
+struct SkbSelectItem {  // over starts
+    const int32_t* su;
+    const skb_i4* rec;
+    const skb_i4* ranked;
+    int32_t phase;
+    uint32_t* sel;
+    SKB_HD void operator()(int64_t s) const {
+        sel[s] = skb_start_is_head(skb_ld_i4(rec + su[s]), skb_ld_i4(ranked + s), s, phase) ? 1u : 0u;
+    }
+};
+
+struct SkbHeadsItem {  // over starts: path id, start node, length, minimum node; tag the list end
+    const int32_t* su;
+    const skb_i4* rec;
+    const skb_i4* ranked;
+    const uint32_t* sel;  // exclusive scan of SkbSelectItem flags
+    int32_t phase;
+    int32_t pid_base;
+    int32_t* start_node;
+    uint32_t* plen;
+    int32_t* pmin;
+    skb_i2* einfo;  // pre-set to -1; einfo[reversed last start] = (path id, half-edges on the path)
+    SKB_HD void operator()(int64_t s) const {
+        skb_i4 a = skb_ld_i4(ranked + s);
+        if (!skb_start_is_head(skb_ld_i4(rec + su[s]), a, s, phase)) return;
+        int32_t pid = pid_base + (int32_t)sel[s];
+        start_node[pid] = su[s];
+        plen[pid] = (uint32_t)a.y + 1u;
+        pmin[pid] = a.z;
+        skb_i2 info;
+        info.x = pid;
+        info.y = a.y;
+        einfo[-1 - a.x] = info;
+    }
+};
+
+struct SkbEmitItem {  // over starts: second local walk, writes path entries (csr.py:394-409)
+    const int32_t* indices;
+    const double* gdata;
+    const skb_i4* rec;
+    const int32_t* su;
+    const int32_t* se;
+    const skb_i4* ranked;
+    const skb_i2* einfo;
+    const int32_t* pindptr;
+    const double* values;  // null -> 1.0 (csr.py:207-215)
+    uint8_t* covered;      // may be null; chain nodes written are marked
+    int32_t* pidx;
+    double* pdata;
+    double* pw;  // weight of the edge arriving at each entry (0 for the first)
+    SKB_HD void operator()(int64_t s) const {
+        skb_i4 a = skb_ld_i4(ranked + s);
+        if (a.x >= 0) return;  // list never reaches a terminal: a cycle that phase 1 handles
+        skb_i2 info = einfo[-1 - a.x];
+        if (info.x < 0) return;  // the emitted direction is the other one
+        int64_t base = pindptr[info.x];
+        int32_t pos = info.y - a.y;  // position of this start's node on the path
+        int32_t u = su[s];
+        int32_t arc = se[s];
+        if (pos == 0) {
+            pidx[base] = u;
+            pdata[base] = values ? values[u] : 1.0;
+            pw[base] = 0.0;
+        }
+        int32_t prev = u, cur = indices[arc];
+        for (;;) {
+            ++pos;
+            skb_i4 r = skb_ld_i4(rec + cur);
+            pidx[base + pos] = cur;
+            pdata[base + pos] = values ? values[cur] : 1.0;
+            pw[base + pos] = gdata[arc];
+            if (r.w != 2) break;
+            if (covered) covered[cur] = 1;
+            if (skb_is_splitter(cur)) break;
+            int32_t nxt;
+            if (r.x == prev) {
+                nxt = r.y;
+                arc = r.z + 1;
+            } else {
+                nxt = r.x;
+                arc = r.z;
+            }
+            prev = cur;
+            cur = nxt;
+        }
+    }
+};
+
+// ---- junction-free cycles: minimum node of every uncovered degree-2 component ---------------
+SKB_HD void skb_union_min(int32_t* par, int32_t a, int32_t b) {
+    for (;;) {
+        a = skb_find(par, a);
+        b = skb_find(par, b);
+        if (a == b) return;
+        if (a < b) {
+            int32_t t = a;
+            a = b;
+            b = t;
+        }
+        // larger root goes under the smaller one: the root stays the component minimum
+        if (skb_atomic_cas_i32(par + a, a, b) == a) return;
+    }
+}
+
 struct SkbIotaItem {
     int32_t* par;
     SKB_HD void operator()(int64_t v) const { par[v] = (int32_t)v; }
 };
 
-struct SkbCcHookItem {  // over nodes: union with every smaller neighbour
-    const int32_t* indptr;
-    const int32_t* indices;
+struct SkbCycleHookItem {  // over nodes: uncovered degree-2 nodes join their smaller neighbours
+    const skb_i4* rec;
+    const uint8_t* covered;
     int32_t* par;
     SKB_HD void operator()(int64_t v) const {
-        for (int32_t e = indptr[v]; e < indptr[v + 1]; ++e) {
-            int32_t u = indices[e];
-            if (u >= (int32_t)v) break;  // sorted row
-            int32_t a = (int32_t)v, b = u;
-            for (;;) {
-                a = skb_find(par, a);
-                b = skb_find(par, b);
-                if (a == b) break;
-                if (a < b) {
-                    int32_t t = a;
-                    a = b;
-                    b = t;
-                }
-                // larger root goes under the smaller one: the root stays the component minimum
-                if (skb_atomic_cas_i32(par + a, a, b) == a) break;
-            }
-        }
+        skb_i4 r = skb_ld_i4(rec + v);
+        if (r.w != 2 || covered[v]) return;
+        if (r.x < (int32_t)v) skb_union_min(par, (int32_t)v, r.x);
+        if (r.y < (int32_t)v) skb_union_min(par, (int32_t)v, r.y);
     }
 };
 
-// node classes used by the path stages
-enum { SKB_NT_ISOLATED = 0, SKB_NT_CHAIN = 1, SKB_NT_TERMINAL = 2, SKB_NT_CYCLE_START = 3 };
-
-struct SkbCcFlattenItem {  // label = root; roots that own a node of degree != 2 are marked
-    const int32_t* indptr;
+struct SkbCycleRootItem {  // over nodes: the minimum of every cycle becomes its terminal
+    skb_i4* rec;
+    const uint8_t* covered;
     int32_t* par;
-    int32_t* label;
-    uint8_t* has_terminal;  // per root, pre-zeroed
     SKB_HD void operator()(int64_t v) const {
-        int32_t r = skb_find(par, (int32_t)v);
-        label[v] = r;
-        if (indptr[v + 1] - indptr[v] != 2) has_terminal[r] = 1;
+        skb_i4 r = skb_ld_i4(rec + v);
+        if (r.w != 2 || covered[v]) return;
+        if (skb_find(par, (int32_t)v) == (int32_t)v) rec[v].w = 2 | SKB_REC_CYCLE_ROOT;
     }
 };
 
-struct SkbNodeTypeItem {
-    const int32_t* indptr;
-    const int32_t* label;
-    const uint8_t* has_terminal;
-    uint8_t* ntype;
-    uint32_t* is_root;
+// ---- stage: skeleton ids (csr.py:909 connected_components) on the contracted graph ----------
+// Components of the pixel graph == components of the graph whose nodes are terminals and whose
+// edges are paths; the reference labels components by the rank of their minimum node id, which
+// may be an interior path node, hence the per-path minimum carried through the ranking above.
+struct SkbCcInitItem {  // over nodes
+    int32_t* par;
+    int32_t* cmin;
+    uint32_t* is_min;
     SKB_HD void operator()(int64_t v) const {
-        int32_t d = indptr[v + 1] - indptr[v];
-        int32_t r = label[v];
-        uint8_t t;
-        if (d == 0) t = SKB_NT_ISOLATED;
-        else if (d != 2) t = SKB_NT_TERMINAL;
-        else t = (r == (int32_t)v && !has_terminal[r]) ? SKB_NT_CYCLE_START : SKB_NT_CHAIN;
-        ntype[v] = t;
-        is_root[v] = (r == (int32_t)v) ? 1u : 0u;
+        par[v] = (int32_t)v;
+        cmin[v] = (int32_t)v;
+        is_min[v] = 0u;
     }
 };
 
-// ---- stage: path tracing (csr.py:347-446) as list ranking over half-edges --------------------
-// arcs[e] for CSR entry e = (u -> v):
-//   x >= 0 : successor arc still to be jumped over, y = arcs between e and arcs[e].x
-//   x <  0 : finished; -1-x = CSR position of the REVERSED last arc (B -> m) of the list that
-//            e lies on, y = number of arcs after e on that list
-// A list starts at a terminal (degree 1 or >= 3) or at the minimum node of a junction-free
-// cycle (csr.py:369-386) and runs through degree-2 nodes to the next such node.
-struct SkbArcInitItem {  // over nodes u
-    const int32_t* indptr;
-    const int32_t* indices;
-    const uint8_t* ntype;
-    skb_i2* arcs;
-    SKB_HD void operator()(int64_t u) const {
-        for (int32_t e = indptr[u]; e < indptr[u + 1]; ++e) {
-            int32_t v = indices[e];
-            skb_i2 a;
-            if (ntype[v] == SKB_NT_CHAIN) {
-                int32_t o = indptr[v];
-                a.x = (indices[o] == (int32_t)u) ? o + 1 : o;
-                a.y = 1;
-            } else {
-                int32_t j = indptr[v];
-                while (indices[j] != (int32_t)u) ++j;  // reverse arc (v -> u)
-                a.x = -1 - j;
-                a.y = 0;
-            }
-            arcs[e] = a;
-        }
-    }
-};
-
-struct SkbArcJumpItem {  // over arcs; in-place asynchronous pointer jumping
-    skb_i2* arcs;
-    int32_t* flag;
-    int32_t jumps;
-    SKB_HD void operator()(int64_t e) const {
-        skb_i2 a = skb_ld_cg(arcs + e);
-        if (a.x < 0) return;
-        for (int j = 0; j < jumps && a.x >= 0; ++j) {
-            skb_i2 s = skb_ld_cg(arcs + a.x);  // 8-byte atomic read: always a consistent pair
-            a.x = s.x;
-            a.y += s.y;
-        }
-        skb_st_cg(arcs + e, a);
-        if (a.x >= 0) skb_raise(flag);
-    }
-};
-
-// a half-edge (A,n) starts an emitted path iff it precedes the reversed last half-edge (B,m)
-// in CSR order (the serial walk of csr.py:347-409 visits start nodes and their
-// neighbours ascending and marks both directions visited)
-struct SkbPathCountItem {  // over nodes: lo32 = regular paths starting here, hi32 = cycle paths
-    const int32_t* indptr;
-    const uint8_t* ntype;
-    const skb_i2* arcs;
-    uint64_t* count;
-    SKB_HD void operator()(int64_t u) const {
-        uint8_t t = ntype[u];
-        uint64_t c = 0;
-        if (t >= SKB_NT_TERMINAL) {
-            for (int32_t e = indptr[u]; e < indptr[u + 1]; ++e) {
-                int32_t y = -1 - arcs[e].x;
-                if (e < y) c += (t == SKB_NT_TERMINAL) ? 1ull : (1ull << 32);
-            }
-        }
-        count[u] = c;
-    }
-};
-
-struct SkbPathStartItem {  // over nodes: path id, start node, length; tag the list by its end arc
-    const int32_t* indptr;
-    const uint8_t* ntype;
-    const skb_i2* arcs;
-    const uint64_t* prefix;  // exclusive scan of SkbPathCountItem counts
-    uint32_t n_regular;
-    int32_t* start_node;
-    uint32_t* plen;
-    skb_i2* einfo;  // pre-set to -1; einfo[y] = (path id, arcs on the path)
-    SKB_HD void operator()(int64_t u) const {
-        uint8_t t = ntype[u];
-        if (t < SKB_NT_TERMINAL) return;
-        uint64_t p = prefix[u];
-        uint32_t pid = (t == SKB_NT_TERMINAL) ? (uint32_t)(p & 0xffffffffull) : n_regular + (uint32_t)(p >> 32);
-        for (int32_t e = indptr[u]; e < indptr[u + 1]; ++e) {
-            skb_i2 a = arcs[e];
-            int32_t y = -1 - a.x;
-            if (e < y) {
-                start_node[pid] = (int32_t)u;
-                plen[pid] = (uint32_t)a.y + 2u;
-                skb_i2 info;
-                info.x = (int32_t)pid;
-                info.y = a.y + 1;
-                einfo[y] = info;
-                ++pid;
-            }
-        }
-    }
-};
-
-struct SkbPathEmitItem {  // over arcs: every arc of an emitted list writes its head node
-    const int32_t* indices;
-    const skb_i2* arcs;
-    const skb_i2* einfo;
+struct SkbCcPathUnionItem {  // over regular paths
     const int32_t* pindptr;
-    const int32_t* start_node;
-    const double* values;  // null -> 1.0 (csr.py:207-215)
-    int32_t* pidx;
-    double* pdata;
-    SKB_HD void operator()(int64_t e) const {
-        skb_i2 a = arcs[e];
-        skb_i2 info = einfo[-1 - a.x];
-        if (info.x < 0) return;
-        int32_t base = pindptr[info.x];
-        int32_t pos = info.y - a.y;
-        int32_t v = indices[e];
-        pidx[base + pos] = v;
-        pdata[base + pos] = values ? values[v] : 1.0;
-        if (pos == 1) {
-            int32_t s = start_node[info.x];
-            pidx[base] = s;
-            pdata[base] = values ? values[s] : 1.0;
-        }
+    const int32_t* pidx;
+    int32_t* par;
+    SKB_HD void operator()(int64_t p) const {
+        skb_union_min(par, pidx[pindptr[p]], pidx[pindptr[p + 1] - 1]);
+    }
+};
+
+struct SkbCcPathMinItem {  // over regular paths, after all unions
+    const int32_t* pindptr;
+    const int32_t* pidx;
+    const int32_t* pmin;
+    int32_t* par;
+    int32_t* cmin;
+    SKB_HD void operator()(int64_t p) const {
+        int32_t r = skb_find(par, pidx[pindptr[p]]);
+        skb_atomic_min_u32((uint32_t*)cmin + r, (uint32_t)pmin[p]);
+    }
+};
+
+struct SkbCcMarkItem {  // over nodes: flag the minimum node of every component
+    const skb_i4* rec;
+    int32_t* par;
+    const int32_t* cmin;
+    uint32_t* is_min;
+    SKB_HD void operator()(int64_t v) const {
+        skb_i4 r = skb_ld_i4(rec + v);
+        int32_t d = r.w & SKB_REC_DEG_MASK;
+        if (r.w & SKB_REC_CYCLE_ROOT) is_min[v] = 1u;          // a junction-free cycle
+        else if (d == 0) is_min[v] = 1u;                        // an isolated pixel
+        else if (d != 2 && skb_find(par, (int32_t)v) == (int32_t)v) is_min[cmin[v]] = 1u;
+    }
+};
+
+struct SkbCcPathIdItem {  // over all paths
+    const int32_t* pindptr;
+    const int32_t* pidx;
+    int32_t n_regular;
+    int32_t* par;
+    const int32_t* cmin;
+    const uint32_t* rank;  // exclusive scan of is_min
+    int32_t* skel_id;
+    SKB_HD void operator()(int64_t p) const {
+        int32_t src = pidx[pindptr[p]];
+        int32_t m = p < n_regular ? cmin[skb_find(par, src)] : src;
+        skel_id[p] = (int32_t)rank[m];
     }
 };
 
@@ -711,29 +890,17 @@ SKB_HD double skb_np_reduceat(const Load& ld, int64_t s, int64_t n) {
 }
 
 struct SkbPathStatsItem {  // over paths
-    const int32_t* gindptr;
-    const int32_t* gindices;
-    const double* gdata;
     const int32_t* pindptr;
-    const int32_t* pidx;
     const double* pdata;
+    const double* pw;
     double* dist;   // may be null
     double* mean;   // may be null
     double* stdev;  // may be null
     SKB_HD void operator()(int64_t p) const {
         int32_t s = pindptr[p], e = pindptr[p + 1];
         if (dist) {
-            double acc = 0.0;  // left-to-right, csr.py:971-977
-            for (int32_t j = s; j + 1 < e; ++j) {
-                int32_t u = pidx[j], v = pidx[j + 1];
-                double w = 0.0;
-                for (int32_t r = gindptr[u]; r < gindptr[u + 1]; ++r)
-                    if (gindices[r] == v) {
-                        w = gdata[r];
-                        break;
-                    }
-                acc += w;
-            }
+            double acc = 0.0;  // left to right over the path's edges, csr.py:971-977
+            for (int32_t j = s + 1; j < e; ++j) acc += pw[j];
             dist[p] = acc;
         }
         if (mean || stdev) {
@@ -763,8 +930,7 @@ struct SkbBranchItem {
     const int32_t* pindptr;
     const int32_t* pidx;
     const int32_t* gindptr;
-    const int32_t* label;
-    const uint32_t* root_rank;  // exclusive scan of is_root
+    const int32_t* skel_id;     // per path (SkbCcPathIdItem)
     const int64_t* coords;      // (N, d)
     const double* values;       // node values or null
     double sp_f[3];
@@ -775,7 +941,7 @@ struct SkbBranchItem {
     SKB_HD void operator()(int64_t p) const {
         int32_t src = pidx[pindptr[p]];
         int32_t dst = pidx[pindptr[p + 1] - 1];
-        out_i32[p] = (int32_t)root_rank[label[src]];
+        out_i32[p] = skel_id[p];
         out_i32[P + p] = src;
         out_i32[2 * P + p] = dst;
         int32_t ds = gindptr[src + 1] - gindptr[src];

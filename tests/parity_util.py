@@ -37,3 +37,40 @@ def compare_with_oracle(img, spacing=1, value_is_height=False, image_for_device=
         else:
             assert_close(got, want, c)
     return sk, df, ref
+
+
+def long_chain_image(kind, n=257):
+    """Images whose chains are much longer than the 1/32 splitter spacing of the sampled list
+    ranking: a serpentine line, a big ring (junction-free cycle with many splitters), nested
+    rings, a ring with a tail (one junction), and a comb."""
+    img = np.zeros((n, n), bool)
+    if kind == 'serpentine':
+        for r in range(1, n - 1, 2):
+            img[r, 1:n - 1] = True
+            col = n - 2 if (r // 2) % 2 == 0 else 1
+            if r + 1 < n - 1:
+                img[r + 1, col] = True
+    elif kind in ('ring', 'nested_rings'):
+        # diamond rings |y-c| + |x-c| == R: every pixel has exactly two (diagonal) neighbours
+        c = n // 2
+        yy, xx = np.mgrid[0:n, 0:n]
+        dist = np.abs(yy - c) + np.abs(xx - c)
+        radii = [c - 2] if kind == 'ring' else list(range(3, c - 1, 3))
+        for R in radii:
+            img |= dist == R
+    elif kind == 'ring_with_tail':
+        img[10, 10:n - 10] = True
+        img[n - 11, 10:n - 10] = True
+        img[10:n - 10, 10] = True
+        img[10:n - 10, n - 11] = True
+        img[n // 2, 0:10] = True
+    elif kind == 'comb':
+        img[n // 2, :] = True
+        for c in range(3, n - 3, 4):
+            img[5:n // 2, c] = True
+    else:
+        raise ValueError(kind)
+    return img
+
+
+LONG_CHAIN_KINDS = ['serpentine', 'ring', 'nested_rings', 'ring_with_tail', 'comb']

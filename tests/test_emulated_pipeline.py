@@ -10,7 +10,7 @@ import pytest
 from emul_util import emulated_device
 from golden_util import case, case_names, check_skeleton_against
 from oracle import skan_oracle as orc
-from parity_util import compare_with_oracle
+from parity_util import LONG_CHAIN_KINDS, compare_with_oracle, long_chain_image
 from skan_b200.synth import walks
 
 import skan_b200
@@ -51,6 +51,17 @@ def test_random_dense_blobs_vs_oracle(seed):
     spacing = [1, (0.5, 0.1, 0.1), (2.0, 1.0), 1, (1, 1), (1.5, 1.5, 0.7)][seed]
     img = rng.random(shape) < [0.5, 0.3, 0.45, 0.35, 0.4, 0.25][seed]
     compare_with_oracle(img, spacing)
+
+
+@pytest.mark.parametrize('kind', LONG_CHAIN_KINDS)
+def test_long_chains_and_big_cycles_vs_oracle(kind):
+    # chains and junction-free cycles far longer than the splitter spacing of the list ranking
+    img = long_chain_image(kind, 129)
+    sk, df, ref = compare_with_oracle(img, (1.0, 0.5))
+    if kind in ('ring', 'nested_rings'):
+        assert np.all(df['branch_type'].to_numpy() == 3)
+    rng = np.random.default_rng(1)
+    compare_with_oracle((img * (rng.random(img.shape) + 0.5)).astype(np.float64), 1)
 
 
 def test_values_and_dtypes_vs_oracle():

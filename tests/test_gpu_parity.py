@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from golden_util import case, case_names, check_skeleton_against
-from parity_util import compare_with_oracle
+from parity_util import LONG_CHAIN_KINDS, compare_with_oracle, long_chain_image
 from skan_b200.synth import walks, walks_device
 
 import skan_b200
@@ -64,6 +64,15 @@ def test_walks_vs_oracle(shape, nw, steps, spacing, pack_variant):
     else:
         img = walks(shape, nw, steps, seed=sum(shape), isolated=20, rings=8)
     compare_with_oracle(img, spacing)
+
+
+@pytest.mark.parametrize('kind', LONG_CHAIN_KINDS)
+def test_long_chains_and_big_cycles_vs_oracle(kind):
+    # chains and junction-free cycles far longer than the splitter spacing of the list ranking
+    img = long_chain_image(kind, 513)
+    compare_with_oracle(img, (1.0, 0.5))
+    rng = np.random.default_rng(1)
+    compare_with_oracle((img * (rng.random(img.shape) + 0.5)).astype(np.float32), 1)
 
 
 @pytest.mark.parametrize('seed', range(4))
