@@ -102,10 +102,13 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
  * (csr.py:369-386), whose minimum node is flagged as a "cycle root" and acts as a terminal. */
 typedef struct skb_i4 { int32_t x, y, z, w; } skb_i4; /* 16-byte aligned */
 
-/* rec i4[n] = (n0, n1, indptr[v], degree | flags); n_chain u32[1] = number of degree-2 nodes */
+/* rec i4[n] = (n0, n1, indptr[v], degree | flags); n_chain u32[1] = number of degree-2 nodes;
+ * startoff u32[n+1] = scanned phase-0 walk starts per node; par, cmin i32[n] and is_min u32[n+1] =
+ * initial state of skb_skeleton_ids (isolated pixels already flagged as components) */
 int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,
+                     uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
                      void* stream);
-/* startoff u32[n+1]: exclusive scan of the walk starts per node (phase 1 needs covered u8[n]) */
+/* startoff u32[n+1] for phase 1 (cycle roots + uncovered splitters; needs covered u8[n]) */
 int skb_path_start_count(const int32_t* indptr, const skb_i4* rec, const uint8_t* covered, int64_t n, int phase,
                          uint32_t* startoff, void* scratch, void* stream);
 /* su/se i32[S]: node and half-edge of each start; ranked i4[S]: result of the first local walk */
@@ -127,14 +130,15 @@ int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec
                   const int32_t* se, const skb_i4* ranked, const skb_i2* einfo, const int32_t* pindptr,
                   const double* values, uint8_t* covered, int64_t n_starts, int32_t* pidx, double* pdata,
                   double* pw, void* stream);
-/* flags the minimum node of every component of uncovered degree-2 nodes in rec; scratch par i32[n] */
-int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, void* stream);
+/* flags the minimum node of every component of uncovered degree-2 nodes in rec and in is_min;
+ * scratch par i32[n] */
+int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, uint32_t* is_min, void* stream);
 
 /* Skeleton ids -- replaces csgraph.connected_components (csr.py:909) on the graph contracted to
  * terminals and paths; skel_id i32[P] = rank of the component's minimum node id.
- * Scratch: par i32[n], cmin i32[n], rank u32[n+1]. */
-int skb_skeleton_ids(const skb_i4* rec, const int32_t* pindptr, const int32_t* pidx, const int32_t* pmin,
-                     int64_t n, int64_t n_regular, int64_t n_paths, int32_t* par, int32_t* cmin, uint32_t* rank,
+ * par, cmin, is_min as initialised by skb_path_records / skb_cycle_roots (is_min becomes the rank table). */
+int skb_skeleton_ids(const int32_t* pindptr, const int32_t* pidx, const int32_t* pmin, int64_t n,
+                     int64_t n_regular, int64_t n_paths, int32_t* par, int32_t* cmin, uint32_t* is_min,
                      int32_t* skel_id, void* scratch, void* stream);
 
 /* Per-path statistics -- replaces _compute_distances (csr.py:962-977, left-to-right sum of pw),

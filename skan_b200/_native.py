@@ -34,15 +34,15 @@ _SIGNATURES = {
     'skb_mst_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'skb_degrees_indptr': (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     'skb_csr_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp]),
-    'skb_path_records': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    'skb_path_records': (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_path_start_count': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     'skb_path_walk': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     'skb_path_rank': (_int, [_vp, _vp, _i64, _vp, _vp]),
     'skb_path_select': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
     'skb_path_heads': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
     'skb_path_emit': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
-    'skb_cycle_roots': (_int, [_vp, _vp, _i64, _vp, _vp]),
-    'skb_skeleton_ids': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_cycle_roots': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    'skb_skeleton_ids': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_path_stats': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'skb_branch_table': (_int, [_i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp, _vp]),

@@ -237,12 +237,20 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
         raise ValueError('index pointer size 0 should be 1')
     rec = ctx.empty((N, 4), torch.int32)
     n_chain_t = ctx.empty(1, torch.int32)
-    ctx.call('skb_path_records', indptr, indices, N, rec, n_chain_t)
+    startoff0 = ctx.empty(N + 1, torch.int32)
+    cc_par = ctx.empty(N, torch.int32)
+    cc_min = ctx.empty(N, torch.int32)
+    is_min = ctx.empty(N + 1, torch.int32)
+    ctx.call('skb_path_records', indptr, indices, N, rec, n_chain_t, startoff0, cc_par, cc_min, is_min,
+             ctx.scratch(N))
     p.rec = rec
 
     def phase(ph, covered, pid_base):
-        startoff = ctx.empty(N + 1, torch.int32)
-        ctx.call('skb_path_start_count', indptr, rec, covered, N, ph, startoff, ctx.scratch(N))
+        if ph == 0:
+            startoff = startoff0
+        else:
+            startoff = ctx.empty(N + 1, torch.int32)
+            ctx.call('skb_path_start_count', indptr, rec, covered, N, ph, startoff, ctx.scratch(N))
         S = int(startoff[N].item())
         if S == 0:
             return None
@@ -298,7 +306,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
     n_cycles = 0
     if n_uncovered > 0:
         par = ctx.empty(N, torch.int32)
-        ctx.call('skb_cycle_roots', rec, covered, N, par)
+        ctx.call('skb_cycle_roots', rec, covered, N, par, is_min)
         b = phase(1, covered, n_regular)
         n_cycles = int(b.sel[b.S].item())
         heads(b, start_node, plen, pmin)
@@ -312,11 +320,8 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
     p.n_paths, p.n_cycles, p.n_regular, p.n_entries = P, n_cycles, n_regular, L
     p.indptr, p.indices, p.data, p.weights = pindptr[:P + 1], pidx[:L], pdata[:L], pw[:L]
     # ---- skeleton ids ---------------------------------------------------------------------------
-    par = ctx.empty(N, torch.int32)
-    cmin = ctx.empty(N, torch.int32)
-    rank = ctx.empty(N + 1, torch.int32)
     skel_id = ctx.empty(P, torch.int32)
-    ctx.call('skb_skeleton_ids', rec, p.indptr, p.indices, pmin, N, n_regular, P, par, cmin, rank, skel_id,
+    ctx.call('skb_skeleton_ids', p.indptr, p.indices, pmin, N, n_regular, P, cc_par, cc_min, is_min, skel_id,
              ctx.scratch(N))
     p.skeleton_id = skel_id
     return p

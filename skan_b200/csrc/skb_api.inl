@@ -118,12 +118,16 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
 }
 
 // ---- path tracing (csr.py:347-446): sampled list ranking, see skb_items.cuh ------------------
-// rec i4[n] (n0, n1, indptr, degree|flags) and the number of degree-2 nodes (n_chain u32[1])
+// rec i4[n] (n0, n1, indptr, degree|flags), the number of degree-2 nodes (n_chain u32[1]), the
+// phase-0 start offsets (startoff u32[n+1], scanned) and the initial state of the skeleton-id
+// stage (par, cmin i32[n]; is_min u32[n+1])
 int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,
+                     uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
                      void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     SKB_TRY(skb_fill_bytes(n_chain, 0, 4, s));
-    return skb_foreach(n, s, SkbPathRecItem{indptr, indices, rec, n_chain});
+    SKB_TRY(skb_foreach(n, s, SkbPathRecItem{indptr, indices, rec, n_chain, startoff, par, cmin, is_min}));
+    return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }
 
 // walk starts per node, scanned in place: startoff u32[n+1].  phase 0: terminals + splitters;
@@ -200,26 +204,26 @@ int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec
 }
 
 // junction-free cycles (csr.py:369-386): the minimum node of every component of uncovered
-// degree-2 nodes is flagged in rec as a cycle root.  Scratch: par i32[n].
-int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, void* stream) {
+// degree-2 nodes is flagged in rec as a cycle root and in is_min.  Scratch: par i32[n].
+int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, uint32_t* is_min, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     SKB_TRY(skb_foreach(n, s, SkbIotaItem{par}));
     SKB_TRY(skb_foreach(n, s, SkbCycleHookItem{rec, covered, par}));
-    return skb_foreach(n, s, SkbCycleRootItem{rec, covered, par});
+    return skb_foreach(n, s, SkbCycleRootItem{rec, covered, par, is_min});
 }
 
 // skeleton ids (csr.py:909): connected components of the contracted graph, labelled by the rank
-// of each component's minimum node id.  Scratch: par i32[n], cmin i32[n], rank u32[n+1].
-int skb_skeleton_ids(const skb_i4* rec, const int32_t* pindptr, const int32_t* pidx, const int32_t* pmin,
-                     int64_t n, int64_t n_regular, int64_t n_paths, int32_t* par, int32_t* cmin, uint32_t* rank,
+// of each component's minimum node id.  par, cmin i32[n] and is_min u32[n+1] come initialised from
+// skb_path_records / skb_cycle_roots; is_min is scanned in place into the rank table.
+int skb_skeleton_ids(const int32_t* pindptr, const int32_t* pidx, const int32_t* pmin, int64_t n,
+                     int64_t n_regular, int64_t n_paths, int32_t* par, int32_t* cmin, uint32_t* is_min,
                      int32_t* skel_id, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_foreach(n, s, SkbCcInitItem{par, cmin, rank}));
     SKB_TRY(skb_foreach(n_regular, s, SkbCcPathUnionItem{pindptr, pidx, par}));
     SKB_TRY(skb_foreach(n_regular, s, SkbCcPathMinItem{pindptr, pidx, pmin, par, cmin}));
-    SKB_TRY(skb_foreach(n, s, SkbCcMarkItem{rec, par, cmin, rank}));
-    SKB_TRY(skb_scan_u32_impl(rank, rank, n, scratch, s));
-    return skb_foreach(n_paths, s, SkbCcPathIdItem{pindptr, pidx, (int32_t)n_regular, par, cmin, rank, skel_id});
+    SKB_TRY(skb_foreach(n_regular, s, SkbCcPathMarkItem{pindptr, pidx, par, cmin, is_min}));
+    SKB_TRY(skb_scan_u32_impl(is_min, is_min, n, scratch, s));
+    return skb_foreach(n_paths, s, SkbCcPathIdItem{pindptr, pidx, (int32_t)n_regular, par, cmin, is_min, skel_id});
 }
 
 // branch_distance / mean / stdev per path (csr.py:962-977, 792-816); null outputs are skipped

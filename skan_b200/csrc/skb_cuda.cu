@@ -458,51 +458,56 @@ static int skb_pack_launch(const void* img, int64_t nvox, bool is_float, uint64_
 // (csr.py:1088) and fp64 values (csr.py:554-562) of every foreground voxel, in raster order
 // (csr.py:131-132).  Reads V/8 bytes of mask; no block-wide barrier anywhere.
 #define SKB_EMIT_THREADS 256
+#define SKB_EMIT_CAP 512  // set bits of one 4096-voxel group staged in shared memory per warp
 
-__device__ __forceinline__ void skb_emit_word(uint64_t word, int64_t wi, uint32_t id, const SkbGeom& g,
-                                              const void* img, int dtype, int64_t* __restrict__ lin,
-                                              int64_t* __restrict__ coords, double* __restrict__ values) {
-    while (word) {
-        int b = __ffsll((long long)word) - 1;
-        word &= word - 1;
-        int64_t r = wi * 64 + b;
-        lin[id] = r;
-        int32_t z, y, x;
-        skb_coords(g, r, z, y, x);
-        int64_t* c = coords + (int64_t)id * g.ndim;
-        if (g.ndim == 3) {
-            c[0] = z;
-            c[1] = y;
-            c[2] = x;
-        } else if (g.ndim == 2) {
-            c[0] = y;
-            c[1] = x;
-        } else {
-            c[0] = x;
-        }
-        if (values) values[id] = skb_load_value(img, dtype, r);
-        ++id;
+// coordinates of voxel (tile origin + off) from the tile origin's coordinates: 32-bit arithmetic only
+__device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int32_t z0, int32_t y0, int32_t x0,
+                                             uint32_t id, const SkbGeom& g, const void* img, int dtype,
+                                             int64_t* __restrict__ lin, int64_t* __restrict__ coords,
+                                             double* __restrict__ values) {
+    int64_t r = r0 + off;
+    lin[id] = r;
+    uint32_t t = (uint32_t)x0 + off;
+    uint32_t q = t / (uint32_t)g.nx;
+    uint32_t x = t - q * (uint32_t)g.nx;
+    uint32_t t2 = (uint32_t)y0 + q;
+    uint32_t q2 = t2 / (uint32_t)g.ny;
+    uint32_t y = t2 - q2 * (uint32_t)g.ny;
+    uint32_t z = (uint32_t)z0 + q2;
+    int64_t* c = coords + (int64_t)id * g.ndim;
+    if (g.ndim == 3) {
+        c[0] = z;
+        c[1] = y;
+        c[2] = x;
+    } else if (g.ndim == 2) {
+        c[0] = y;
+        c[1] = x;
+    } else {
+        c[0] = x;
     }
+    if (values) values[id] = skb_load_value(img, dtype, r);
 }
 
 __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, int64_t ntiles, SkbGeom g,
     const void* img, int dtype, int64_t* __restrict__ lin, int64_t* __restrict__ coords,
     double* __restrict__ values, uint32_t* __restrict__ pre256) {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint16_t stage[SKB_EMIT_THREADS / 32][SKB_EMIT_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warps = (int64_t)gridDim.x * (SKB_EMIT_THREADS / 32);
-    for (int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + (threadIdx.x >> 5); tile < ntiles;
-         tile += warps) {
+    for (int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + warp; tile < ntiles; tile += warps) {
         const uint32_t t0 = tile_prefix[tile], t1 = tile_prefix[tile + 1];
-        uint2* pre = (uint2*)(pre256 + tile * 64);  // 64 blocks of 256 bits per tile
-        if (t0 == t1) {  // empty tile: only the rank structure
-            pre[lane] = make_uint2(t0, t0);
+        if (t0 == t1) {  // empty tile: only the rank structure (64 blocks of 256 bits)
+            ((uint2*)(pre256 + tile * 64))[lane] = make_uint2(t0, t0);
             continue;
         }
         const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS);
         uint4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = src[j * 32 + lane];
+        const int64_t r0 = tile * SKB_TILE_VOX;
+        int32_t z0, y0, x0;
+        skb_coords(g, r0, z0, y0, x0);  // warp-uniform; the only 64-bit division of the tile
         uint32_t running = t0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -515,15 +520,46 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
                 uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += o;
             }
-            uint32_t id = running + inc - c;
-            running += __shfl_sync(0xffffffffu, inc, 31);
+            const uint32_t ex = inc - c;
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
             // words 2*(32 j + lane), +1: the even lane of each pair starts a 256-bit block
-            if ((lane & 1) == 0) pre256[tile * 64 + j * 16 + (lane >> 1)] = id;
-            if (c) {
-                int64_t wi = tile * SKB_TILE_WORDS + 2 * (j * 32 + lane);
-                skb_emit_word(w0, wi, id, g, img, dtype, lin, coords, values);
-                skb_emit_word(w1, wi + 1, id + c0, g, img, dtype, lin, coords, values);
+            if ((lane & 1) == 0) pre256[tile * 64 + j * 16 + (lane >> 1)] = running + ex;
+            if (total) {
+                const uint32_t off0 = (uint32_t)(2 * (j * 32 + lane)) * 64u;  // tile-local bit offset of w0
+                if (total <= SKB_EMIT_CAP) {
+                    // compact the set bits of the group into shared memory, then one node per lane
+                    uint32_t k = ex;
+                    uint64_t w = w0;
+                    while (w) {
+                        stage[warp][k++] = (uint16_t)(off0 + (uint32_t)(__ffsll((long long)w) - 1));
+                        w &= w - 1;
+                    }
+                    w = w1;
+                    while (w) {
+                        stage[warp][k++] = (uint16_t)(off0 + 64u + (uint32_t)(__ffsll((long long)w) - 1));
+                        w &= w - 1;
+                    }
+                    __syncwarp();
+                    for (uint32_t i = lane; i < total; i += 32)
+                        skb_emit_one(stage[warp][i], r0, z0, y0, x0, running + i, g, img, dtype, lin, coords, values);
+                    __syncwarp();
+                } else {  // dense group: every lane walks its own two words
+                    uint32_t id = running + ex;
+                    uint64_t w = w0;
+                    while (w) {
+                        skb_emit_one(off0 + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id++, g, img, dtype,
+                                     lin, coords, values);
+                        w &= w - 1;
+                    }
+                    w = w1;
+                    while (w) {
+                        skb_emit_one(off0 + 64u + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id++, g, img,
+                                     dtype, lin, coords, values);
+                        w &= w - 1;
+                    }
+                }
             }
+            running += total;
         }
     }
 }

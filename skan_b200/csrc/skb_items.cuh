@@ -473,7 +473,11 @@ struct SkbPathRecItem {  // over nodes
     const int32_t* indptr;
     const int32_t* indices;
     skb_i4* rec;
-    uint32_t* n_chain;  // number of degree-2 nodes (pre-zeroed)
+    uint32_t* n_chain;   // number of degree-2 nodes (pre-zeroed)
+    uint32_t* count;     // phase-0 walk starts leaving v (scanned by the caller)
+    int32_t* par;        // union-find parent / component minimum / "is a component minimum" flag of
+    int32_t* cmin;       // the skeleton-id stage, initialised here while every node is visited anyway
+    uint32_t* is_min;    // (isolated pixels are their own component, csr.py:909)
     SKB_HD void operator()(int64_t v) const {
         int32_t o = indptr[v], d = indptr[v + 1] - o;
         skb_i4 r;
@@ -491,6 +495,10 @@ struct SkbPathRecItem {  // over nodes
 #endif
         }
         skb_st_i4(rec + v, r);
+        count[v] = (uint32_t)(d != 2 ? d : (skb_is_splitter((int32_t)v) ? 2 : 0));
+        par[v] = (int32_t)v;
+        cmin[v] = (int32_t)v;
+        is_min[v] = d == 0 ? 1u : 0u;
     }
 };
 
@@ -729,10 +737,14 @@ struct SkbCycleRootItem {  // over nodes: the minimum of every cycle becomes its
     skb_i4* rec;
     const uint8_t* covered;
     int32_t* par;
+    uint32_t* is_min;  // a junction-free cycle is a component of its own (csr.py:909)
     SKB_HD void operator()(int64_t v) const {
         skb_i4 r = skb_ld_i4(rec + v);
         if (r.w != 2 || covered[v]) return;
-        if (skb_find(par, (int32_t)v) == (int32_t)v) rec[v].w = 2 | SKB_REC_CYCLE_ROOT;
+        if (skb_find(par, (int32_t)v) == (int32_t)v) {
+            rec[v].w = 2 | SKB_REC_CYCLE_ROOT;
+            is_min[v] = 1u;
+        }
     }
 };
 
@@ -740,17 +752,6 @@ struct SkbCycleRootItem {  // over nodes: the minimum of every cycle becomes its
 // Components of the pixel graph == components of the graph whose nodes are terminals and whose
 // edges are paths; the reference labels components by the rank of their minimum node id, which
 // may be an interior path node, hence the per-path minimum carried through the ranking above.
-struct SkbCcInitItem {  // over nodes
-    int32_t* par;
-    int32_t* cmin;
-    uint32_t* is_min;
-    SKB_HD void operator()(int64_t v) const {
-        par[v] = (int32_t)v;
-        cmin[v] = (int32_t)v;
-        is_min[v] = 0u;
-    }
-};
-
 struct SkbCcPathUnionItem {  // over regular paths
     const int32_t* pindptr;
     const int32_t* pidx;
@@ -772,18 +773,13 @@ struct SkbCcPathMinItem {  // over regular paths, after all unions
     }
 };
 
-struct SkbCcMarkItem {  // over nodes: flag the minimum node of every component
-    const skb_i4* rec;
+struct SkbCcPathMarkItem {  // over regular paths: flag the minimum node of the path's component
+    const int32_t* pindptr;
+    const int32_t* pidx;
     int32_t* par;
     const int32_t* cmin;
     uint32_t* is_min;
-    SKB_HD void operator()(int64_t v) const {
-        skb_i4 r = skb_ld_i4(rec + v);
-        int32_t d = r.w & SKB_REC_DEG_MASK;
-        if (r.w & SKB_REC_CYCLE_ROOT) is_min[v] = 1u;          // a junction-free cycle
-        else if (d == 0) is_min[v] = 1u;                        // an isolated pixel
-        else if (d != 2 && skb_find(par, (int32_t)v) == (int32_t)v) is_min[cmin[v]] = 1u;
-    }
+    SKB_HD void operator()(int64_t p) const { is_min[cmin[skb_find(par, pidx[pindptr[p]])]] = 1u; }
 };
 
 struct SkbCcPathIdItem {  // over all paths
