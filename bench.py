@@ -195,7 +195,7 @@ def main():
     def step():
         return _pipeline.skeleton_and_summary_device(img, spacing=spacing, device=dev)
 
-    for _ in range(args.warmup):
+    for _ in range(max(1, args.warmup)):
         r = step()
     torch.cuda.synchronize()
     g, p = r.graph, r.paths

@@ -488,6 +488,14 @@ __device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int32_t z
     if (values) values[id] = skb_load_value(img, dtype, r);
 }
 
+__device__ __forceinline__ uint32_t skb_stage_bits(uint64_t w, uint32_t off, uint16_t* __restrict__ st, uint32_t k) {
+    while (w) {
+        st[k++] = (uint16_t)(off + (uint32_t)(__ffsll((long long)w) - 1));
+        w &= w - 1;
+    }
+    return k;
+}
+
 __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, int64_t ntiles, SkbGeom g,
     const void* img, int dtype, int64_t* __restrict__ lin, int64_t* __restrict__ coords,
@@ -495,71 +503,64 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     __shared__ uint16_t stage[SKB_EMIT_THREADS / 32][SKB_EMIT_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warps = (int64_t)gridDim.x * (SKB_EMIT_THREADS / 32);
+    uint16_t* st = stage[warp];
     for (int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + warp; tile < ntiles; tile += warps) {
-        const uint32_t t0 = tile_prefix[tile], t1 = tile_prefix[tile + 1];
-        if (t0 == t1) {  // empty tile: only the rank structure (64 blocks of 256 bits)
-            ((uint2*)(pre256 + tile * 64))[lane] = make_uint2(t0, t0);
+        const uint32_t t0 = tile_prefix[tile], total = tile_prefix[tile + 1] - t0;
+        uint2* pre = (uint2*)(pre256 + tile * 64) + lane;  // lane owns blocks 2*lane, 2*lane+1 (words 8*lane..+7)
+        if (total == 0) {  // empty tile: only the rank structure
+            *pre = make_uint2(t0, t0);
             continue;
         }
-        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS);
-        uint4 v[4];
+        // lane-contiguous words: four 128-bit loads per lane cover the lane's 64 bytes
+        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS) + lane * 4;
+        const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+        const uint64_t w0 = (uint64_t)a.x | ((uint64_t)a.y << 32), w1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+        const uint64_t w2 = (uint64_t)b.x | ((uint64_t)b.y << 32), w3 = (uint64_t)b.z | ((uint64_t)b.w << 32);
+        const uint64_t w4 = (uint64_t)c.x | ((uint64_t)c.y << 32), w5 = (uint64_t)c.z | ((uint64_t)c.w << 32);
+        const uint64_t w6 = (uint64_t)d.x | ((uint64_t)d.y << 32), w7 = (uint64_t)d.z | ((uint64_t)d.w << 32);
+        const uint32_t clo = (uint32_t)(__popcll(w0) + __popcll(w1) + __popcll(w2) + __popcll(w3));
+        const uint32_t cnt = clo + (uint32_t)(__popcll(w4) + __popcll(w5) + __popcll(w6) + __popcll(w7));
+        uint32_t inc = cnt;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = src[j * 32 + lane];
+        for (int s = 1; s < 32; s <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
+            if (lane >= s) inc += o;
+        }
+        const uint32_t ex = inc - cnt;  // nodes of this tile before this lane's words
+        *pre = make_uint2(t0 + ex, t0 + ex + clo);
         const int64_t r0 = tile * SKB_TILE_VOX;
         int32_t z0, y0, x0;
         skb_coords(g, r0, z0, y0, x0);  // warp-uniform; the only 64-bit division of the tile
-        uint32_t running = t0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint64_t w0 = (uint64_t)v[j].x | ((uint64_t)v[j].y << 32);
-            uint64_t w1 = (uint64_t)v[j].z | ((uint64_t)v[j].w << 32);
-            uint32_t c0 = (uint32_t)__popcll(w0), c = c0 + (uint32_t)__popcll(w1);
-            uint32_t inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
+        const uint32_t off0 = (uint32_t)lane * 512u;  // tile-local bit offset of w0
+        if (total <= SKB_EMIT_CAP) {
+            // compact the set bits of the tile into shared memory, then one node per lane
+            if (cnt) {
+                uint32_t k = ex;
+                k = skb_stage_bits(w0, off0, st, k);
+                k = skb_stage_bits(w1, off0 + 64u, st, k);
+                k = skb_stage_bits(w2, off0 + 128u, st, k);
+                k = skb_stage_bits(w3, off0 + 192u, st, k);
+                k = skb_stage_bits(w4, off0 + 256u, st, k);
+                k = skb_stage_bits(w5, off0 + 320u, st, k);
+                k = skb_stage_bits(w6, off0 + 384u, st, k);
+                k = skb_stage_bits(w7, off0 + 448u, st, k);
             }
-            const uint32_t ex = inc - c;
-            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-            // words 2*(32 j + lane), +1: the even lane of each pair starts a 256-bit block
-            if ((lane & 1) == 0) pre256[tile * 64 + j * 16 + (lane >> 1)] = running + ex;
-            if (total) {
-                const uint32_t off0 = (uint32_t)(2 * (j * 32 + lane)) * 64u;  // tile-local bit offset of w0
-                if (total <= SKB_EMIT_CAP) {
-                    // compact the set bits of the group into shared memory, then one node per lane
-                    uint32_t k = ex;
-                    uint64_t w = w0;
-                    while (w) {
-                        stage[warp][k++] = (uint16_t)(off0 + (uint32_t)(__ffsll((long long)w) - 1));
-                        w &= w - 1;
-                    }
-                    w = w1;
-                    while (w) {
-                        stage[warp][k++] = (uint16_t)(off0 + 64u + (uint32_t)(__ffsll((long long)w) - 1));
-                        w &= w - 1;
-                    }
-                    __syncwarp();
-                    for (uint32_t i = lane; i < total; i += 32)
-                        skb_emit_one(stage[warp][i], r0, z0, y0, x0, running + i, g, img, dtype, lin, coords, values);
-                    __syncwarp();
-                } else {  // dense group: every lane walks its own two words
-                    uint32_t id = running + ex;
-                    uint64_t w = w0;
-                    while (w) {
-                        skb_emit_one(off0 + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id++, g, img, dtype,
-                                     lin, coords, values);
-                        w &= w - 1;
-                    }
-                    w = w1;
-                    while (w) {
-                        skb_emit_one(off0 + 64u + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id++, g, img,
-                                     dtype, lin, coords, values);
-                        w &= w - 1;
-                    }
+            __syncwarp();
+            for (uint32_t i = lane; i < total; i += 32)
+                skb_emit_one(st[i], r0, z0, y0, x0, t0 + i, g, img, dtype, lin, coords, values);
+            __syncwarp();
+        } else if (cnt) {  // dense tile: every lane walks its own words
+            uint32_t id = t0 + ex;
+            const uint64_t ws[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                uint64_t w = ws[q];
+                while (w) {
+                    skb_emit_one(off0 + 64u * q + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id++, g, img,
+                                 dtype, lin, coords, values);
+                    w &= w - 1;
                 }
             }
-            running += total;
         }
     }
 }
