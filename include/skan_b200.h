@@ -102,7 +102,7 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
  * (csr.py:369-386), whose minimum node is flagged as a "cycle root" and acts as a terminal. */
 typedef struct skb_i4 { int32_t x, y, z, w; } skb_i4; /* 16-byte aligned */
 
-/* rec i4[n] = (n0, n1, indptr[v], degree | flags); n_chain u32[1] = number of degree-2 nodes;
+/* rec i4[n] = (n0, n1, indptr[v], degree | flags); sum of n_chain u32[64] = number of degree-2 nodes;
  * startoff u32[n+1] = scanned phase-0 walk starts per node; par, cmin i32[n] and is_min u32[n+1] =
  * initial state of skb_skeleton_ids (isolated pixels already flagged as components) */
 int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,

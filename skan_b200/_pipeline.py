@@ -236,7 +236,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
     if N == 0 or E == 0:
         raise ValueError('index pointer size 0 should be 1')
     rec = ctx.empty((N, 4), torch.int32)
-    n_chain_t = ctx.empty(1, torch.int32)
+    n_chain_t = ctx.empty(64, torch.int32)
     startoff0 = ctx.empty(N + 1, torch.int32)
     cc_par = ctx.empty(N, torch.int32)
     cc_min = ctx.empty(N, torch.int32)
@@ -277,7 +277,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
     # ---- phase 0: paths between terminals -----------------------------------------------------
     a = phase(0, None, 0)
     n_regular = int(a.sel[a.S].item()) if a is not None else 0
-    n_chain = int(n_chain_t.item())
+    n_chain = int(n_chain_t.sum().item())
     p.rank_rounds = a.rounds if a is not None else 0
     # every path entry that is not a path end is a degree-2 node, and each is on exactly one path:
     # what the regular paths do not cover lies on junction-free cycles (csr.py:369-386)

@@ -118,14 +118,14 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
 }
 
 // ---- path tracing (csr.py:347-446): sampled list ranking, see skb_items.cuh ------------------
-// rec i4[n] (n0, n1, indptr, degree|flags), the number of degree-2 nodes (n_chain u32[1]), the
+// rec i4[n] (n0, n1, indptr, degree|flags), the number of degree-2 nodes (sum of n_chain u32[64]), the
 // phase-0 start offsets (startoff u32[n+1], scanned) and the initial state of the skeleton-id
 // stage (par, cmin i32[n]; is_min u32[n+1])
 int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,
                      uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
                      void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_fill_bytes(n_chain, 0, 4, s));
+    SKB_TRY(skb_fill_bytes(n_chain, 0, 64 * 4, s));
     SKB_TRY(skb_foreach(n, s, SkbPathRecItem{indptr, indices, rec, n_chain, startoff, par, cmin, is_min}));
     return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }

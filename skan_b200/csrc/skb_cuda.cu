@@ -506,59 +506,71 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     uint16_t* st = stage[warp];
     for (int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + warp; tile < ntiles; tile += warps) {
         const uint32_t t0 = tile_prefix[tile], total = tile_prefix[tile + 1] - t0;
-        uint2* pre = (uint2*)(pre256 + tile * 64) + lane;  // lane owns blocks 2*lane, 2*lane+1 (words 8*lane..+7)
-        if (total == 0) {  // empty tile: only the rank structure
-            *pre = make_uint2(t0, t0);
+        if (total == 0) {  // empty tile: only the rank structure (64 blocks of 256 bits)
+            ((uint2*)(pre256 + tile * 64))[lane] = make_uint2(t0, t0);
             continue;
         }
-        // lane-contiguous words: four 128-bit loads per lane cover the lane's 64 bytes
-        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS) + lane * 4;
-        const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
-        const uint64_t w0 = (uint64_t)a.x | ((uint64_t)a.y << 32), w1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
-        const uint64_t w2 = (uint64_t)b.x | ((uint64_t)b.y << 32), w3 = (uint64_t)b.z | ((uint64_t)b.w << 32);
-        const uint64_t w4 = (uint64_t)c.x | ((uint64_t)c.y << 32), w5 = (uint64_t)c.z | ((uint64_t)c.w << 32);
-        const uint64_t w6 = (uint64_t)d.x | ((uint64_t)d.y << 32), w7 = (uint64_t)d.z | ((uint64_t)d.w << 32);
-        const uint32_t clo = (uint32_t)(__popcll(w0) + __popcll(w1) + __popcll(w2) + __popcll(w3));
-        const uint32_t cnt = clo + (uint32_t)(__popcll(w4) + __popcll(w5) + __popcll(w6) + __popcll(w7));
-        uint32_t inc = cnt;
+        // coalesced 128-bit loads: lane holds words 2*(32 j + lane) and +1 for j = 0..3
+        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS) + lane;
+        const uint4 q0 = src[0], q1 = src[32], q2 = src[64], q3 = src[96];
+        uint64_t w[8];
+        w[0] = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
+        w[1] = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
+        w[2] = (uint64_t)q1.x | ((uint64_t)q1.y << 32);
+        w[3] = (uint64_t)q1.z | ((uint64_t)q1.w << 32);
+        w[4] = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
+        w[5] = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
+        w[6] = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
+        w[7] = (uint64_t)q3.z | ((uint64_t)q3.w << 32);
+        // one warp scan for the four groups: 16-bit fields (a group holds at most 4096 set bits)
+        unsigned long long packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            packed |= (unsigned long long)(__popcll(w[2 * j]) + __popcll(w[2 * j + 1])) << (16 * j);
+        unsigned long long inc = packed;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, inc, s);
+            unsigned long long o = __shfl_up_sync(0xffffffffu, inc, s);
             if (lane >= s) inc += o;
         }
-        const uint32_t ex = inc - cnt;  // nodes of this tile before this lane's words
-        *pre = make_uint2(t0 + ex, t0 + ex + clo);
+        const unsigned long long ex = inc - packed;
+        const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
         const int64_t r0 = tile * SKB_TILE_VOX;
         int32_t z0, y0, x0;
         skb_coords(g, r0, z0, y0, x0);  // warp-uniform; the only 64-bit division of the tile
-        const uint32_t off0 = (uint32_t)lane * 512u;  // tile-local bit offset of w0
+        uint32_t base = 0;              // nodes of the tile in groups before j
+        uint32_t idj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            idj[j] = base + (uint32_t)((ex >> (16 * j)) & 0xffffu);
+            base += (uint32_t)((tot >> (16 * j)) & 0xffffu);
+            // words 2*(32 j + lane), +1: the even lane of each pair starts a 256-bit block
+            if ((lane & 1) == 0) pre256[tile * 64 + j * 16 + (lane >> 1)] = t0 + idj[j];
+        }
         if (total <= SKB_EMIT_CAP) {
             // compact the set bits of the tile into shared memory, then one node per lane
-            if (cnt) {
-                uint32_t k = ex;
-                k = skb_stage_bits(w0, off0, st, k);
-                k = skb_stage_bits(w1, off0 + 64u, st, k);
-                k = skb_stage_bits(w2, off0 + 128u, st, k);
-                k = skb_stage_bits(w3, off0 + 192u, st, k);
-                k = skb_stage_bits(w4, off0 + 256u, st, k);
-                k = skb_stage_bits(w5, off0 + 320u, st, k);
-                k = skb_stage_bits(w6, off0 + 384u, st, k);
-                k = skb_stage_bits(w7, off0 + 448u, st, k);
+            if (packed) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t off = (uint32_t)(2 * (j * 32 + lane)) * 64u;
+                    uint32_t k = skb_stage_bits(w[2 * j], off, st, idj[j]);
+                    skb_stage_bits(w[2 * j + 1], off + 64u, st, k);
+                }
             }
             __syncwarp();
             for (uint32_t i = lane; i < total; i += 32)
                 skb_emit_one(st[i], r0, z0, y0, x0, t0 + i, g, img, dtype, lin, coords, values);
             __syncwarp();
-        } else if (cnt) {  // dense tile: every lane walks its own words
-            uint32_t id = t0 + ex;
-            const uint64_t ws[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+        } else if (packed) {  // dense tile: every lane walks its own words
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                uint64_t w = ws[q];
-                while (w) {
-                    skb_emit_one(off0 + 64u * q + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id++, g, img,
-                                 dtype, lin, coords, values);
-                    w &= w - 1;
+                uint64_t x = w[q];
+                uint32_t id = t0 + idj[q >> 1] + ((q & 1) ? (uint32_t)__popcll(w[q - 1]) : 0u);
+                const uint32_t off = (uint32_t)(2 * ((q >> 1) * 32 + lane) + (q & 1)) * 64u;
+                while (x) {
+                    skb_emit_one(off + (uint32_t)(__ffsll((long long)x) - 1), r0, z0, y0, x0, id++, g, img, dtype, lin,
+                                 coords, values);
+                    x &= x - 1;
                 }
             }
         }

@@ -142,27 +142,24 @@ SKB_HD int32_t skb_rank(const uint64_t* bits, const uint32_t* pre256, int64_t r)
     return (int32_t)(acc + (uint32_t)skb_popcll(low));
 }
 
-// calls fn(k27, neighbour_id) for every set bit of mask m of node i, ascending k27
+// calls fn(k27, neighbour_id) for every set bit of mask m of node i, ascending k27.
+// One iteration per set bit (typically two) keeps the lanes of a warp in step; a neighbour in
+// another row costs one rank query, neighbours in the node's own row are i-1 / i+1.
 template <typename Fn>
 SKB_HD void skb_for_neighbors(const SkbGeom& g, const uint64_t* bits, const uint32_t* pre256, int64_t r, int32_t i,
                               uint32_t m, Fn& fn) {
-    for (int row = 0; row < 9; ++row) {
-        uint32_t s = (m >> (row * 3)) & 7u;
-        if (!s) continue;
-        if (row == 4) {
-            if (s & 1u) fn(12, i - 1);
-            if (s & 4u) fn(14, i + 1);
-        } else {
-            int dz = row / 3 - 1, dy = row % 3 - 1;
-            int64_t rr = r + dz * g.sz + dy * (int64_t)g.nx;
-            // m may be a subset of the foreground voxels of this row (edges dropped by the MST):
-            // ids advance with the voxels actually set in the mask, not with the bits of m
-            int b = skb_ffs(s) - 1;
-            int32_t id0 = skb_rank(bits, pre256, rr - 1 + b);
-            uint32_t win = skb_win3(bits, rr - 1) >> b;
-            for (int t = b; t < 3; ++t)
-                if ((s >> t) & 1u) fn(row * 3 + t, id0 + skb_popc(win & ((1u << (t - b)) - 1u)));
+    while (m) {
+        int k = skb_ffs(m) - 1;
+        m &= m - 1u;
+        int32_t id;
+        if (k == 12) id = i - 1;
+        else if (k == 14) id = i + 1;
+        else {
+            int row = k / 3;
+            int dz = row / 3 - 1, dy = row % 3 - 1, dx = k - row * 3 - 1;
+            id = skb_rank(bits, pre256, r + dz * g.sz + dy * (int64_t)g.nx + dx);
         }
+        fn(k, id);
     }
 }
 
@@ -473,7 +470,7 @@ struct SkbPathRecItem {  // over nodes
     const int32_t* indptr;
     const int32_t* indices;
     skb_i4* rec;
-    uint32_t* n_chain;   // number of degree-2 nodes (pre-zeroed)
+    uint32_t* n_chain;   // number of degree-2 nodes, summed over 64 slots (pre-zeroed)
     uint32_t* count;     // phase-0 walk starts leaving v (scanned by the caller)
     int32_t* par;        // union-find parent / component minimum / "is a component minimum" flag of
     int32_t* cmin;       // the skeleton-id stage, initialised here while every node is visited anyway
@@ -489,7 +486,7 @@ struct SkbPathRecItem {  // over nodes
             r.x = indices[o];
             r.y = indices[o + 1];
 #if defined(__CUDA_ARCH__)
-            atomicAdd(n_chain, 1u);
+            atomicAdd(n_chain + (blockIdx.x & 63), 1u);  // 64 slots: no single hot address
 #else
             *n_chain += 1u;
 #endif
