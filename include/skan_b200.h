@@ -55,10 +55,11 @@ int skb_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, void* scratch, vo
  * (csr.py:131-132, 1088, 554-562).  tile_prefix = scanned tile counts (ntiles+1).
  * Out: lin i64[N] raveled index, coords i64[N][ndim], values f64[N] (or NULL for bool images),
  * pre256 u32[ntiles*64] = popcount prefix of `bits` per 256-bit block (rank structure that
- * stands in for skimage.util.map_array, csr.py:135,142-144). */
+ * stands in for skimage.util.map_array, csr.py:135,142-144).  z_origin is added to the first
+ * coordinate of 3-D images (the image may be one Z-slab of a larger volume). */
 int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
-                   const int64_t* shape /*host*/, const void* image, int dtype, int64_t* lin, int64_t* coords,
-                   double* values, uint32_t* pre256, void* stream);
+                   const int64_t* shape /*host*/, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                   int64_t* coords, double* values, uint32_t* pre256, void* stream);
 
 /* Raw 3^d neighbourhood of every node as a 27-bit mask -- replaces the N x (3^d-1) neighbour
  * table and membership test of pixel_graph (csr.py:122-144). */
@@ -102,34 +103,47 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
  * (csr.py:369-386), whose minimum node is flagged as a "cycle root" and acts as a terminal. */
 typedef struct skb_i4 { int32_t x, y, z, w; } skb_i4; /* 16-byte aligned */
 
-/* rec i4[n] = (n0, n1, indptr[v], degree | flags); sum of n_chain u32[64] = number of degree-2 nodes;
- * startoff u32[n+1] = scanned phase-0 walk starts per node; par, cmin i32[n] and is_min u32[n+1] =
- * initial state of skb_skeleton_ids (isolated pixels already flagged as components) */
-int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,
-                     uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
-                     void* stream);
-/* startoff u32[n+1] for phase 1 (cycle roots + uncovered splitters; needs covered u8[n]) */
-int skb_path_start_count(const int32_t* indptr, const skb_i4* rec, const uint8_t* covered, int64_t n, int phase,
+/* `slab` (host, 13 x i64, or NULL on a single GPU): own0, own1 (owned nodes), cnt0, cnt1 (nodes whose
+ * starts are numbered), ga0, ga1, gb0, gb1 (forced-splitter ranges: slab boundary planes), id_shift
+ * (global node id = local + id_shift), start_shift, start_lo, start_hi (global start ids),
+ * lin_offset (global raveled index = lin + lin_offset).  See the Z-slab section below. */
+
+/* rec i4[n] = (n0, n1, indptr[v], degree | flags); sum of n_chain u32[64] = owned degree-2 nodes;
+ * startoff u32[n+1] = scanned phase-0 walk starts per node; par, cmin i32[n] (may be NULL) and
+ * is_min u32[n+1] = initial state of skb_skeleton_ids (isolated pixels already flagged).  With
+ * lin != NULL splitters are sampled by voxel position instead of node id. */
+int skb_path_records(const int32_t* indptr, const int32_t* indices, const int64_t* lin, const int64_t* slab /*host*/,
+                     int64_t n, skb_i4* rec, uint32_t* n_chain, uint32_t* startoff, int32_t* par, int32_t* cmin,
+                     uint32_t* is_min, void* scratch, void* stream);
+/* startoff u32[n+1] for phase 1 (cycle roots + uncovered splitters; covered u8[n]) */
+int skb_path_start_count(const skb_i4* rec, const uint8_t* covered, const int64_t* slab /*host*/, int64_t n,
                          uint32_t* startoff, void* scratch, void* stream);
-/* su/se i32[S]: node and half-edge of each start; ranked i4[S]: result of the first local walk */
-int skb_path_walk(const int32_t* indptr, const int32_t* indices, const skb_i4* rec, const uint32_t* startoff,
-                  int64_t n, int64_t n_starts, int32_t* su, int32_t* se, skb_i4* ranked, void* stream);
-/* pointer jumping over the starts, ping-pong buf0 <-> buf1 (i4[S] each); returns 2*rounds + index of
- * the buffer holding the result; synchronises every round after the third */
-int skb_path_rank(skb_i4* buf0, skb_i4* buf1, int64_t n_starts, int32_t* flag, void* stream);
+/* su/se i32[S]: node and half-edge of each start; ranked i4[S]: result of the first local walk;
+ * aux (48 B per start, NULL on a single GPU): running sums and end node; stamp i32[n] (may be NULL) */
+int skb_path_walk(const int32_t* indptr, const int32_t* indices, const double* gdata, const double* values,
+                  const int64_t* lin, const skb_i4* rec, const uint32_t* startoff, const int64_t* slab /*host*/,
+                  int64_t n, int64_t n_starts, int32_t* su, int32_t* se, skb_i4* ranked, void* aux, int32_t* stamp,
+                  void* stream);
+/* pointer jumping over the starts with global ids [lo, hi), ping-pong buf0/aux0 <-> buf1/aux1;
+ * returns 2*rounds + index of the buffer holding the result; synchronises every round after the third */
+int skb_path_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_starts, int64_t lo, int64_t hi,
+                  int32_t* flag, void* stream);
 /* sel u32[S+1]: exclusive scan of "this start is the head of an emitted path"  */
 int skb_path_select(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, int64_t n_starts, int phase,
-                    uint32_t* sel, void* scratch, void* stream);
-/* per path pid_base + k: start_node i32, plen u32 (entries), pmin i32 (minimum node id); einfo i2[S] */
-int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const uint32_t* sel,
-                   int64_t n_starts, int phase, int64_t pid_base, int32_t* start_node, uint32_t* plen,
-                   int32_t* pmin, skb_i2* einfo, void* stream);
+                    int64_t start_lo, uint32_t* sel, void* scratch, void* stream);
+/* per path pid_base + k: start_node i32 (global id), plen u32 (entries), pmin i32 (minimum node id);
+ * einfo i4[S] (single GPU) or head_end i32[P] + head_aux (48 B each) (slabs) */
+int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const void* aux,
+                   const uint32_t* sel, int64_t n_starts, int phase, int64_t pid_base, int64_t start_lo,
+                   int64_t id_shift, int32_t* start_node, uint32_t* plen, int32_t* pmin, skb_i4* einfo,
+                   int32_t* head_end, void* head_aux, void* stream);
 /* paths.indices i32[L], paths.data f64[L] (csr.py:396,402,442-445; values NULL -> 1.0) and
- * pw f64[L] = weight of the edge arriving at each entry; covered u8[n] (optional) marks chain nodes */
+ * pw f64[L] = weight of the edge arriving at each entry; covered u8[n] (optional) marks chain nodes;
+ * pindptr NULL: the entry offset of a path is einfo.z */
 int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec, const int32_t* su,
-                  const int32_t* se, const skb_i4* ranked, const skb_i2* einfo, const int32_t* pindptr,
-                  const double* values, uint8_t* covered, int64_t n_starts, int32_t* pidx, double* pdata,
-                  double* pw, void* stream);
+                  const int32_t* se, const skb_i4* ranked, const skb_i4* einfo, const int32_t* pindptr,
+                  const double* values, uint8_t* covered, int64_t id_shift, int64_t n_starts, int32_t* pidx,
+                  double* pdata, double* pw, void* stream);
 /* flags the minimum node of every component of uncovered degree-2 nodes in rec and in is_min;
  * scratch par i32[n] */
 int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, uint32_t* is_min, void* stream);
@@ -150,11 +164,48 @@ int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw
  *   out_i32[3][P]            skeleton_id, node_id_src, node_id_dst
  *   out_i64[1+2d][P]         branch_type, image_coord_src_*, image_coord_dst_*
  *   out_f64[2(d+h)+1][P]     coord_src_*(+height), coord_dst_*(+height), euclidean_distance
- * (coord_* carry int64 bit patterns when spacing_is_int).  spacing_f / spacing_i are host arrays. */
+ * (coord_* carry int64 bit patterns when spacing_is_int).  spacing_f / spacing_i are host arrays.
+ * Slabs: head_aux / start_node / id_shift / global_shape describe paths whose last node lives on
+ * another rank (NULL / 0 on a single GPU). */
 int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, const double* spacing_f /*host*/,
                      const int64_t* spacing_i /*host*/, const int32_t* pindptr, const int32_t* pidx,
                      const int32_t* gindptr, const int32_t* skel_id, const int64_t* coords, const double* values,
-                     int32_t* out_i32, int64_t* out_i64, double* out_f64, void* stream);
+                     const void* head_aux, const int32_t* start_node, int64_t id_shift,
+                     const int64_t* global_shape /*host*/, int32_t* out_i32, int64_t* out_i64, double* out_f64,
+                     void* stream);
+
+/* ---- Z-slab mode: one volume split over several GPUs -----------------
+ * Every rank runs the graph stages on its owned planes plus `halo` planes on either side, numbers
+ * walk starts for its owned nodes and the adjacent halo plane exactly as the neighbour rank does,
+ * ranks its own lists, and exchanges only (a) counts, (b) the ranked starts of its two boundary
+ * planes ("inter-slab table"), (c) one head + one link record per path. */
+int skb_rank_query(const uint64_t* bits, const uint32_t* pre256, const int64_t* pos, int64_t n, int32_t* out,
+                   void* stream);
+/* flag i32[1] = 1 when a junction cluster spans owned nodes and the outer two halo planes */
+int skb_mst_halo_check(const uint32_t* nb, int32_t* par, int64_t n, int64_t own0, int64_t own1, int64_t lo1,
+                       int64_t hi0, uint8_t* outer, int32_t* flag, void* stream);
+int skb_slab_covered(const skb_i4* rec, const uint32_t* startoff, const int32_t* stamp, const skb_i4* ranked,
+                     int64_t n, int64_t own0, int64_t own1, uint8_t* covered, uint32_t* n_uncovered, void* stream);
+int skb_slab_export(const skb_i4* ranked, const void* aux, int64_t n_first, int64_t last0, int64_t n_block,
+                    int64_t lo, int64_t hi, skb_i4* out, void* out_aux, void* stream);
+/* table_desc (host i64): n_ranks, start_off[n_ranks+1], n_first[n_ranks], last0[n_ranks], t_off[n_ranks] */
+int skb_slab_table_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_table,
+                        const int64_t* table_desc /*host*/, int32_t* flag, void* stream);
+int skb_slab_apply(skb_i4* ranked, void* aux, const skb_i4* table, const void* table_aux, int64_t n_starts,
+                   const int64_t* table_desc /*host*/, int64_t lo, int64_t hi, void* stream);
+int skb_slab_head_records(const int32_t* head_end, const uint32_t* plen, const int32_t* pindptr,
+                          const int32_t* pmin, const int32_t* start_node, const uint32_t* startoff,
+                          const void* head_aux, const int64_t* slab /*host*/, int64_t n, int64_t n_paths,
+                          int64_t pid_off, int64_t entry_off, skb_i4* head, skb_i4* link, void* stream);
+int skb_slab_einfo(const skb_i4* head, int64_t n_records, int64_t n_total_starts, skb_i4* einfo, void* stream);
+int skb_slab_components(const skb_i4* link, int64_t n_records, int64_t n_keys, int32_t* par, int32_t* cmin,
+                        int64_t node_lo, int64_t node_hi, int64_t id_shift, uint32_t* is_min, int64_t n,
+                        void* scratch, void* stream);
+int skb_slab_skeleton_ids(const skb_i4* link, int64_t n_records, int32_t* par, const int32_t* cmin,
+                          const uint32_t* rank, int64_t node_lo, int64_t node_hi, int64_t id_shift,
+                          int64_t comp_off, int64_t own0, int32_t* skel, void* stream);
+int skb_slab_path_stats(const uint32_t* plen, const void* head_aux, int64_t n_paths, double* dist, double* mean,
+                        double* stdev, void* stream);
 
 /* Skeleton.path_label_image (csr.py:776-790); image i64[V] zeroed by the caller */
 int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int64_t* lin, int64_t n_paths,

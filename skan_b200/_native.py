@@ -25,7 +25,7 @@ _SIGNATURES = {
     'skb_tile_voxels': (_i64, []),
     'skb_kernel_launches': (_i64, []),
     'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
-    'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
     'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp]),
     'skb_junction_edge_count': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp]),
     'skb_junction_edge_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int,
@@ -34,18 +34,31 @@ _SIGNATURES = {
     'skb_mst_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'skb_degrees_indptr': (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     'skb_csr_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp]),
-    'skb_path_records': (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'skb_path_start_count': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
-    'skb_path_walk': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
-    'skb_path_rank': (_int, [_vp, _vp, _i64, _vp, _vp]),
-    'skb_path_select': (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp]),
-    'skb_path_heads': (_int, [_vp, _vp, _vp, _vp, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
-    'skb_path_emit': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    'skb_path_records': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_path_start_count': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'skb_path_walk': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_path_rank': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    'skb_path_select': (_int, [_vp, _vp, _vp, _i64, _int, _i64, _vp, _vp, _vp]),
+    'skb_path_heads': (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp]),
+    'skb_path_emit': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     'skb_cycle_roots': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     'skb_skeleton_ids': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_path_stats': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
-    'skb_branch_table': (_int, [_i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                _vp, _vp, _vp]),
+    'skb_branch_table': (_int, [_i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                _vp, _vp, _vp, _vp, _vp]),
+    'skb_rank_query': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_mst_halo_check': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    'skb_slab_covered': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    'skb_slab_export': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    'skb_slab_table_rank': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    'skb_slab_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp]),
+    'skb_slab_head_records': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp,
+                                     _vp]),
+    'skb_slab_einfo': (_int, [_vp, _i64, _i64, _vp, _vp]),
+    'skb_slab_components': (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
+    'skb_slab_skeleton_ids': (_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),
+    'skb_slab_path_stats': (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'skb_path_label_image': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     'skb_scan_u32': (_int, [_vp, _vp, _i64, _vp, _vp]),
     'skb_scan_u64': (_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -129,7 +129,7 @@ def _as_device_image(image, device):
     return t, code, shape, np_dtype
 
 
-def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant=None):
+def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant=None, z_origin=0):
     """skeleton_to_csgraph on the device (csr.py:1028-1089): returns a namespace of device tensors
     (coords int64 (N,d), values fp64 (N,) | None, indptr/indices int32, data fp64, degrees int32)."""
     ctx = _Ctx(device)
@@ -168,8 +168,8 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
     coords = ctx.empty((N, ndim), torch.int64)
     values = None if is_bool else ctx.empty(N, torch.float64)
     pre256 = ctx.empty(ntiles * 64, torch.int32)
-    ctx.call('skb_emit_nodes', bits, tile_prefix, ntiles, ndim, shape_t.data_ptr(), img, code, lin, coords,
-             values, pre256)
+    ctx.call('skb_emit_nodes', bits, tile_prefix, ntiles, ndim, shape_t.data_ptr(), img, code, int(z_origin), lin,
+             coords, values, pre256)
     g.lin, g.coords, g.values, g.pre256 = lin, coords, values, pre256
     if value_is_height and values is None:
         # the reference subtracts booleans here, which NumPy refuses (csr.py:1024)
@@ -227,7 +227,7 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
     return g
 
 
-def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
+def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None):
     """_build_skeleton_path_graph on the device (csr.py:412-446) by sampled list ranking, plus the
     skeleton ids summarize needs (csr.py:909).  Raises ValueError when there is no path, like the
     reference's csr_matrix constructor does at csr.py:442."""
@@ -241,7 +241,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
     cc_par = ctx.empty(N, torch.int32)
     cc_min = ctx.empty(N, torch.int32)
     is_min = ctx.empty(N + 1, torch.int32)
-    ctx.call('skb_path_records', indptr, indices, N, rec, n_chain_t, startoff0, cc_par, cc_min, is_min,
+    ctx.call('skb_path_records', indptr, indices, lin, None, N, rec, n_chain_t, startoff0, cc_par, cc_min, is_min,
              ctx.scratch(N))
     p.rec = rec
 
@@ -250,7 +250,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
             startoff = startoff0
         else:
             startoff = ctx.empty(N + 1, torch.int32)
-            ctx.call('skb_path_start_count', indptr, rec, covered, N, ph, startoff, ctx.scratch(N))
+            ctx.call('skb_path_start_count', rec, covered, None, N, startoff, ctx.scratch(N))
         S = int(startoff[N].item())
         if S == 0:
             return None
@@ -258,21 +258,22 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges):
         se = ctx.empty(S, torch.int32)
         buf = [ctx.empty((S, 4), torch.int32), ctx.empty((S, 4), torch.int32)]
         flag = ctx.empty(1, torch.int32)
-        ctx.call('skb_path_walk', indptr, indices, rec, startoff, N, S, su, se, buf[0])
-        r = ctx.call('skb_path_rank', buf[0], buf[1], S, flag)
+        ctx.call('skb_path_walk', indptr, indices, gdata, values, lin, rec, startoff, None, N, S, su, se, buf[0],
+                 None, None)
+        r = ctx.call('skb_path_rank', buf[0], buf[1], None, None, S, 0, S, flag)
         ranked = buf[r & 1]
         sel = ctx.empty(S + 1, torch.int32)
-        ctx.call('skb_path_select', su, rec, ranked, S, ph, sel, ctx.scratch(S))
+        ctx.call('skb_path_select', su, rec, ranked, S, ph, 0, sel, ctx.scratch(S))
         return SimpleNamespace(S=S, su=su, se=se, ranked=ranked, sel=sel, rounds=r >> 1, phase=ph, pid_base=pid_base)
 
     def heads(ph, start_node, plen, pmin):
-        ph.einfo = ctx.empty((ph.S, 2), torch.int32)
-        ctx.call('skb_path_heads', ph.su, rec, ph.ranked, ph.sel, ph.S, ph.phase, ph.pid_base, start_node, plen, pmin,
-                 ph.einfo)
+        ph.einfo = ctx.empty((ph.S, 4), torch.int32)
+        ctx.call('skb_path_heads', ph.su, rec, ph.ranked, None, ph.sel, ph.S, ph.phase, ph.pid_base, 0, 0, start_node,
+                 plen, pmin, ph.einfo, None, None)
 
     def emit(ph, pindptr, covered, pidx, pdata, pw):
         ctx.call('skb_path_emit', indices, gdata, rec, ph.su, ph.se, ph.ranked, ph.einfo, pindptr, values, covered,
-                 ph.S, pidx, pdata, pw)
+                 0, ph.S, pidx, pdata, pw)
 
     # ---- phase 0: paths between terminals -----------------------------------------------------
     a = phase(0, None, 0)
@@ -349,7 +350,7 @@ def branch_table(ctx, p, gindptr, coords, values, spacing, ndim, value_is_height
     o64 = ctx.empty((1 + 2 * ndim, P), torch.int64)
     of = ctx.empty((2 * dh + 1, P), torch.float64)
     ctx.call('skb_branch_table', P, ndim, height, 1 if sp_is_int else 0, sp_f.data_ptr(), sp_i.data_ptr(),
-             p.indptr, p.indices, gindptr, p.skeleton_id, coords, values, o32, o64, of)
+             p.indptr, p.indices, gindptr, p.skeleton_id, coords, values, None, None, 0, None, o32, o64, of)
     return o32, o64, of, sp_is_int
 
 

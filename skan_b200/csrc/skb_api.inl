@@ -118,49 +118,79 @@ int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const i
 }
 
 // ---- path tracing (csr.py:347-446): sampled list ranking, see skb_items.cuh ------------------
-// rec i4[n] (n0, n1, indptr, degree|flags), the number of degree-2 nodes (sum of n_chain u32[64]), the
-// phase-0 start offsets (startoff u32[n+1], scanned) and the initial state of the skeleton-id
-// stage (par, cmin i32[n]; is_min u32[n+1])
-int skb_path_records(const int32_t* indptr, const int32_t* indices, int64_t n, skb_i4* rec, uint32_t* n_chain,
-                     uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
-                     void* stream) {
+// `slab` (host, 13 x i64, or NULL on a single GPU) = own0, own1, cnt0, cnt1, ga0, ga1, gb0, gb1,
+// id_shift, start_shift, start_lo, start_hi, lin_offset -- see struct SkbSlab.
+static SkbSlab skb_make_slab(const int64_t* v, int64_t n) {
+    SkbSlab sl;
+    if (!v) {
+        sl.own0 = 0; sl.own1 = (int32_t)n; sl.cnt0 = 0; sl.cnt1 = (int32_t)n;
+        sl.ga0 = sl.ga1 = sl.gb0 = sl.gb1 = 0;
+        sl.id_shift = 0; sl.start_shift = 0; sl.start_lo = 0; sl.start_hi = 0x7fffffff; sl.lin_offset = 0;
+        return sl;
+    }
+    sl.own0 = (int32_t)v[0]; sl.own1 = (int32_t)v[1]; sl.cnt0 = (int32_t)v[2]; sl.cnt1 = (int32_t)v[3];
+    sl.ga0 = (int32_t)v[4]; sl.ga1 = (int32_t)v[5]; sl.gb0 = (int32_t)v[6]; sl.gb1 = (int32_t)v[7];
+    sl.id_shift = (int32_t)v[8]; sl.start_shift = (int32_t)v[9];
+    sl.start_lo = (int32_t)v[10]; sl.start_hi = (int32_t)v[11]; sl.lin_offset = v[12];
+    return sl;
+}
+
+// rec i4[n] (n0, n1, indptr, degree|flags), the number of owned degree-2 nodes (sum of n_chain
+// u32[64]), the phase-0 start offsets (startoff u32[n+1], scanned) and the initial state of the
+// skeleton-id stage (par, cmin i32[n], may be NULL; is_min u32[n+1]).  lin (may be NULL) makes the
+// splitter sample a function of the voxel position instead of the node id.
+int skb_path_records(const int32_t* indptr, const int32_t* indices, const int64_t* lin, const int64_t* slab,
+                     int64_t n, skb_i4* rec, uint32_t* n_chain, uint32_t* startoff, int32_t* par, int32_t* cmin,
+                     uint32_t* is_min, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     SKB_TRY(skb_fill_bytes(n_chain, 0, 64 * 4, s));
-    SKB_TRY(skb_foreach(n, s, SkbPathRecItem{indptr, indices, rec, n_chain, startoff, par, cmin, is_min}));
+    SKB_TRY(skb_foreach(
+        n, s, SkbPathRecItem{indptr, indices, lin, skb_make_slab(slab, n), rec, n_chain, startoff, par, cmin, is_min}));
     return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }
 
-// walk starts per node, scanned in place: startoff u32[n+1].  phase 0: terminals + splitters;
-// phase 1: cycle roots + uncovered splitters (covered u8[n] must be given).
-int skb_path_start_count(const int32_t* indptr, const skb_i4* rec, const uint8_t* covered, int64_t n, int phase,
+// walk starts of phase 1 (cycle roots + uncovered splitters), scanned in place: startoff u32[n+1]
+int skb_path_start_count(const skb_i4* rec, const uint8_t* covered, const int64_t* slab, int64_t n,
                          uint32_t* startoff, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    if (phase != 0 && !covered) return skb_fail("phase 1 needs the covered marks");
-    SKB_TRY(skb_foreach(n, s, SkbStartCountItem{indptr, rec, covered, phase, startoff}));
+    if (!covered) return skb_fail("phase 1 needs the covered marks");
+    SKB_TRY(skb_foreach(n, s, SkbStartCountItem{rec, covered, skb_make_slab(slab, n), startoff}));
     return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }
 
-// su/se i32[S] (node and half-edge of every start) and the first local walk: ranked i4[S]
-int skb_path_walk(const int32_t* indptr, const int32_t* indices, const skb_i4* rec, const uint32_t* startoff,
-                  int64_t n, int64_t n_starts, int32_t* su, int32_t* se, skb_i4* ranked, void* stream) {
+// su/se i32[S] (node and half-edge of every start leaving an owned node) and the first local walk:
+// ranked i4[S]; aux (48 B per start; NULL on a single GPU) carries sums and the end node; stamp
+// i32[n] (may be NULL, pre-set to -1) remembers a start per chain node passed.
+int skb_path_walk(const int32_t* indptr, const int32_t* indices, const double* gdata, const double* values,
+                  const int64_t* lin, const skb_i4* rec, const uint32_t* startoff, const int64_t* slab, int64_t n,
+                  int64_t n_starts, int32_t* su, int32_t* se, skb_i4* ranked, void* aux, int32_t* stamp,
+                  void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_foreach(n, s, SkbStartFillItem{indptr, startoff, su, se}));
-    return skb_foreach(n_starts, s, SkbWalkItem{indices, rec, startoff, su, se, ranked});
+    SkbSlab sl = skb_make_slab(slab, n);
+    SKB_TRY(skb_foreach((int64_t)sl.own1 - sl.own0, s, SkbStartFillItem{indptr, startoff, sl.own0, su, se}));
+    return skb_foreach(
+        n_starts, s,
+        SkbWalkItem{indices, gdata, values, lin, rec, startoff, su, se, sl, ranked, (SkbAux*)aux, stamp});
 }
 
-// pointer jumping over the starts (synchronous rounds, ping-pong between buf0 and buf1).
-// Stops after the first round in which no start reaches its list end: every list that ends at
-// a terminal is then finished, what is left cycles.  Returns 2*rounds + (index of the result buffer).
-int skb_path_rank(skb_i4* buf0, skb_i4* buf1, int64_t n_starts, int32_t* flag, void* stream) {
+// pointer jumping over the starts of this rank (synchronous rounds, ping-pong between buf0/aux0
+// and buf1/aux1; aux may be NULL).  Starts with global ids [lo, hi) are this rank's.  Stops after
+// the first round in which no start stops pointing into [lo, hi): every list that ends at a
+// terminal or leaves the slab is then resolved, what is left cycles.
+// Returns 2*rounds + (index of the result buffer).
+int skb_path_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_starts, int64_t lo, int64_t hi,
+                  int32_t* flag, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     if (n_starts <= 0) return 0;
     skb_i4* b[2] = {buf0, buf1};
+    SkbAux* a[2] = {(SkbAux*)aux0, (SkbAux*)aux1};
     int cur = 0, rounds = 0;
     const int blind = 3;  // rounds run before the first host check (lists of up to 8 starts)
     for (;; ++rounds) {
         if (rounds > 40) return skb_fail("list ranking did not converge");
         if (rounds >= blind || rounds == 0) SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
-        SKB_TRY(skb_foreach(n_starts, s, SkbJumpItem{b[cur], b[cur ^ 1], flag}));
+        SKB_TRY(skb_foreach(n_starts, s,
+                            SkbJumpItem{b[cur], b[cur ^ 1], a[cur], a[cur ^ 1], (int32_t)lo, (int32_t)hi, flag}));
         cur ^= 1;
         if (rounds + 1 >= blind) {
             int32_t any = 0;
@@ -176,31 +206,38 @@ int skb_path_rank(skb_i4* buf0, skb_i4* buf1, int64_t n_starts, int32_t* flag, v
 
 // heads of emitted paths among the starts: sel u32[S+1] = exclusive scan of the head flags
 int skb_path_select(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, int64_t n_starts, int phase,
-                    uint32_t* sel, void* scratch, void* stream) {
+                    int64_t start_lo, uint32_t* sel, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_foreach(n_starts, s, SkbSelectItem{su, rec, ranked, phase, sel}));
+    SKB_TRY(skb_foreach(n_starts, s, SkbSelectItem{su, rec, ranked, phase, (int32_t)start_lo, sel}));
     return skb_scan_u32_impl(sel, sel, n_starts, scratch, s);
 }
 
-// per path (ids pid_base + ...): start_node i32, plen u32 (entries), pmin i32; einfo i2[S]
-int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const uint32_t* sel,
-                   int64_t n_starts, int phase, int64_t pid_base, int32_t* start_node, uint32_t* plen,
-                   int32_t* pmin, skb_i2* einfo, void* stream) {
+// per path (ids pid_base + ...): start_node i32 (global id), plen u32 (entries), pmin i32.
+// Single GPU: einfo i4[S] is filled (and cleared first).  Slabs: einfo NULL; head_end i32 and
+// head_aux (48 B each) receive the reversed last start and the sums / end node of every path.
+int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const void* aux,
+                   const uint32_t* sel, int64_t n_starts, int phase, int64_t pid_base, int64_t start_lo,
+                   int64_t id_shift, int32_t* start_node, uint32_t* plen, int32_t* pmin, skb_i4* einfo,
+                   int32_t* head_end, void* head_aux, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_fill_bytes(einfo, 0xff, (size_t)n_starts * 8, s));
+    if (einfo) SKB_TRY(skb_fill_bytes(einfo, 0xff, (size_t)n_starts * 16, s));
     return skb_foreach(n_starts, s,
-                       SkbHeadsItem{su, rec, ranked, sel, phase, (int32_t)pid_base, start_node, plen, pmin, einfo});
+                       SkbHeadsItem{su, rec, ranked, (const SkbAux*)aux, sel, phase, (int32_t)pid_base,
+                                    (int32_t)start_lo, (int32_t)id_shift, start_node, plen, pmin, einfo, head_end,
+                                    (SkbAux*)head_aux});
 }
 
 // second local walk: paths.indices i32[L], paths.data f64[L] (csr.py:396,402; values NULL -> 1.0),
 // pw f64[L] = weight of the edge arriving at each entry; chain nodes written are marked in
-// covered u8[n] when it is given
+// covered u8[n] when it is given.  einfo is indexed by the id of a list's reversed last start;
+// pindptr NULL means the entry offset of a path is einfo.z (slabs).
 int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec, const int32_t* su,
-                  const int32_t* se, const skb_i4* ranked, const skb_i2* einfo, const int32_t* pindptr,
-                  const double* values, uint8_t* covered, int64_t n_starts, int32_t* pidx, double* pdata,
-                  double* pw, void* stream) {
+                  const int32_t* se, const skb_i4* ranked, const skb_i4* einfo, const int32_t* pindptr,
+                  const double* values, uint8_t* covered, int64_t id_shift, int64_t n_starts, int32_t* pidx,
+                  double* pdata, double* pw, void* stream) {
     return skb_foreach(n_starts, (skb_stream_t)stream,
-                       SkbEmitItem{indices, gdata, rec, su, se, ranked, einfo, pindptr, values, covered, pidx, pdata, pw});
+                       SkbEmitItem{indices, gdata, rec, su, se, ranked, einfo, pindptr, values, covered,
+                                   (int32_t)id_shift, pidx, pdata, pw});
 }
 
 // junction-free cycles (csr.py:369-386): the minimum node of every component of uncovered
@@ -236,9 +273,11 @@ int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw
 int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, const double* spacing_f,
                      const int64_t* spacing_i, const int32_t* pindptr, const int32_t* pidx,
                      const int32_t* gindptr, const int32_t* skel_id, const int64_t* coords, const double* values,
+                     const void* head_aux, const int32_t* start_node, int64_t id_shift, const int64_t* global_shape,
                      int32_t* out_i32, int64_t* out_i64, double* out_f64, void* stream) {
     if (ndim < 1 || ndim > 3) return skb_fail("ndim must be 1, 2 or 3");
     if (height && !values) return skb_fail("height mode needs node values");
+    if (head_aux && (height || !start_node || !global_shape)) return skb_fail("bad slab-mode branch table call");
     SkbBranchItem it;
     it.P = n_paths;
     it.d = ndim;
@@ -248,6 +287,15 @@ int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, 
     it.pidx = pidx;
     it.gindptr = gindptr;
     it.skel_id = skel_id;
+    it.head_aux = (const SkbAux*)head_aux;
+    it.start_node = start_node;
+    it.id_shift = (int32_t)id_shift;
+    it.gny = 1;
+    it.gnx = 1;
+    if (global_shape) {
+        it.gnx = global_shape[ndim - 1];
+        it.gny = ndim >= 2 ? global_shape[ndim - 2] : 1;
+    }
     it.coords = coords;
     it.values = values;
     for (int i = 0; i < 3; ++i) {
@@ -258,6 +306,145 @@ int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, 
     it.out_i64 = out_i64;
     it.out_f64 = out_f64;
     return skb_foreach(n_paths, (skb_stream_t)stream, it);
+}
+
+// ---- Z-slab mode (one volume over several GPUs) ----------------------------------------------
+// out[i] = number of foreground voxels before raveled position pos[i] (pos, out on the device)
+int skb_rank_query(const uint64_t* bits, const uint32_t* pre256, const int64_t* pos, int64_t n, int32_t* out,
+                   void* stream) {
+    return skb_foreach(n, (skb_stream_t)stream, SkbRankQueryItem{bits, pre256, pos, out});
+}
+
+// flag = 1 when a junction cluster reaches both an owned node and the outer two halo planes
+// (nodes < lo1 or >= hi0): the per-slab junction MST could then differ from the global one.
+// par = union-find state left by skb_mst_junctions; outer u8[n] scratch.
+int skb_mst_halo_check(const uint32_t* nb, int32_t* par, int64_t n, int64_t own0, int64_t own1, int64_t lo1,
+                       int64_t hi0, uint8_t* outer, int32_t* flag, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_fill_bytes(outer, 0, (size_t)n, s));
+    SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
+    SKB_TRY(skb_foreach(n, s, SkbMstOuterItem{nb, par, outer, (int32_t)lo1, (int32_t)hi0}));
+    return skb_foreach(own1 - own0, s, SkbMstUnsafeItem{nb, par, outer, (int32_t)own0, flag});
+}
+
+// covered u8[n] from the stamps of the first walk; n_uncovered u32[64] (summed = owned chain nodes
+// that no terminal-started list passes: they lie on junction-free cycles)
+int skb_slab_covered(const skb_i4* rec, const uint32_t* startoff, const int32_t* stamp, const skb_i4* ranked,
+                     int64_t n, int64_t own0, int64_t own1, uint8_t* covered, uint32_t* n_uncovered,
+                     void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_fill_bytes(n_uncovered, 0, 64 * 4, s));
+    return skb_foreach(
+        n, s, SkbCoveredItem{rec, startoff, stamp, ranked, (int32_t)own0, (int32_t)own1, covered, n_uncovered});
+}
+
+static SkbSlabTable skb_make_table(const int64_t* v) {
+    // host array: n_ranks, then start_off[n_ranks+1], n_first[n_ranks], last0[n_ranks], t_off[n_ranks]
+    SkbSlabTable t;
+    int g = (int)v[0];
+    t.n_ranks = g;
+    const int64_t* p = v + 1;
+    for (int k = 0; k <= g; ++k) t.start_off[k] = (int32_t)p[k];
+    p += g + 1;
+    for (int k = 0; k < g; ++k) t.n_first[k] = (int32_t)p[k];
+    p += g;
+    for (int k = 0; k < g; ++k) t.last0[k] = (int32_t)p[k];
+    p += g;
+    for (int k = 0; k < g; ++k) t.t_off[k] = (int32_t)p[k];
+    return t;
+}
+
+// this rank's block of the inter-slab table: the ranked starts of its two boundary planes
+int skb_slab_export(const skb_i4* ranked, const void* aux, int64_t n_first, int64_t last0, int64_t n_block,
+                    int64_t lo, int64_t hi, skb_i4* out, void* out_aux, void* stream) {
+    return skb_foreach(n_block, (skb_stream_t)stream,
+                       SkbTableExportItem{ranked, (const SkbAux*)aux, (int32_t)n_first, (int32_t)last0, (int32_t)lo,
+                                          (int32_t)hi, out, (SkbAux*)out_aux});
+}
+
+// pointer jumping over the gathered table (same on every rank); returns 2*rounds + result buffer
+int skb_slab_table_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_table,
+                        const int64_t* table_desc, int32_t* flag, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    if (n_table <= 0) return 0;
+    if (table_desc[0] > SKB_MAX_RANKS) return skb_fail("too many ranks");
+    SkbSlabTable t = skb_make_table(table_desc);
+    skb_i4* b[2] = {buf0, buf1};
+    SkbAux* a[2] = {(SkbAux*)aux0, (SkbAux*)aux1};
+    int cur = 0, rounds = 0;
+    for (;; ++rounds) {
+        if (rounds > 40) return skb_fail("inter-slab list ranking did not converge");
+        SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
+        SKB_TRY(skb_foreach(n_table, s, SkbTableJumpItem{b[cur], b[cur ^ 1], a[cur], a[cur ^ 1], t, flag}));
+        cur ^= 1;
+        int32_t any = 0;
+        SKB_TRY(skb_fetch_i32(flag, &any, s));
+        if (!any) {
+            ++rounds;
+            break;
+        }
+    }
+    return 2 * rounds + cur;
+}
+
+// finish the lists of this rank that left the slab with the ranked table
+int skb_slab_apply(skb_i4* ranked, void* aux, const skb_i4* table, const void* table_aux, int64_t n_starts,
+                   const int64_t* table_desc, int64_t lo, int64_t hi, void* stream) {
+    if (table_desc[0] > SKB_MAX_RANKS) return skb_fail("too many ranks");
+    return skb_foreach(n_starts, (skb_stream_t)stream,
+                       SkbTableApplyItem{ranked, (SkbAux*)aux, table, (const SkbAux*)table_aux,
+                                         skb_make_table(table_desc), (int32_t)lo, (int32_t)hi});
+}
+
+// head / link records (i4 each) of the paths headed on this rank, for the all-gather
+int skb_slab_head_records(const int32_t* head_end, const uint32_t* plen, const int32_t* pindptr,
+                          const int32_t* pmin, const int32_t* start_node, const uint32_t* startoff,
+                          const void* head_aux, const int64_t* slab, int64_t n, int64_t n_paths, int64_t pid_off,
+                          int64_t entry_off, skb_i4* head, skb_i4* link, void* stream) {
+    return skb_foreach(n_paths, (skb_stream_t)stream,
+                       SkbHeadRecordItem{head_end, plen, pindptr, pmin, start_node, startoff,
+                                         (const SkbAux*)head_aux, skb_make_slab(slab, n), (int32_t)pid_off,
+                                         (int32_t)entry_off, head, link});
+}
+
+// einfo i4[total starts] (cleared here) from all gathered head records (x < 0 = padding)
+int skb_slab_einfo(const skb_i4* head, int64_t n_records, int64_t n_total_starts, skb_i4* einfo, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_fill_bytes(einfo, 0xff, (size_t)n_total_starts * 16, s));
+    return skb_foreach(n_records, s, SkbEinfoScatterItem{head, einfo});
+}
+
+// skeleton ids across slabs, step 1: components of the contracted graph over start keys; marks
+// the component minima that are owned nodes in is_min (local ids) and scans it in place.
+// Scratch: par, cmin i32[n_keys].  link = all gathered link records (x < 0 = padding).
+int skb_slab_components(const skb_i4* link, int64_t n_records, int64_t n_keys, int32_t* par, int32_t* cmin,
+                        int64_t node_lo, int64_t node_hi, int64_t id_shift, uint32_t* is_min, int64_t n,
+                        void* scratch, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_foreach(n_keys, s, SkbKeyInitItem{par, cmin}));
+    SKB_TRY(skb_foreach(n_records, s, SkbKeyUnionItem{link, par}));
+    SKB_TRY(skb_foreach(n_records, s, SkbKeyMinItem{link, par, cmin}));
+    SKB_TRY(skb_foreach(n_records, s,
+                        SkbKeyMarkItem{link, par, cmin, (int32_t)node_lo, (int32_t)node_hi, (int32_t)id_shift, is_min}));
+    return skb_scan_u32_impl(is_min, is_min, n, scratch, s);
+}
+
+// step 2: this rank's contribution to the skeleton id of every gathered path (summed over ranks
+// by the caller): comp_off + rank of the component minimum among the owned component minima
+int skb_slab_skeleton_ids(const skb_i4* link, int64_t n_records, int32_t* par, const int32_t* cmin,
+                          const uint32_t* rank, int64_t node_lo, int64_t node_hi, int64_t id_shift,
+                          int64_t comp_off, int64_t own0, int32_t* skel, void* stream) {
+    return skb_foreach(n_records, (skb_stream_t)stream,
+                       SkbKeySkelItem{link, par, cmin, rank, (int32_t)node_lo, (int32_t)node_hi, (int32_t)id_shift,
+                                      (int32_t)comp_off, (int32_t)own0, skel});
+}
+
+// branch_distance / mean / stdev of the paths headed on this rank from the sums carried through
+// the ranking (tree-order fp64 sums: within 1e-12 of the reference's left-to-right sums)
+int skb_slab_path_stats(const uint32_t* plen, const void* head_aux, int64_t n_paths, double* dist, double* mean,
+                        double* stdev, void* stream) {
+    return skb_foreach(n_paths, (skb_stream_t)stream,
+                       SkbSlabStatsItem{plen, (const SkbAux*)head_aux, dist, mean, stdev});
 }
 
 // Skeleton.path_label_image (csr.py:776-790): image i64[V] must be zeroed by the caller

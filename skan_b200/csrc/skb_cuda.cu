@@ -461,7 +461,7 @@ static int skb_pack_launch(const void* img, int64_t nvox, bool is_float, uint64_
 #define SKB_EMIT_CAP 512  // set bits of one 4096-voxel group staged in shared memory per warp
 
 // coordinates of voxel (tile origin + off) from the tile origin's coordinates: 32-bit arithmetic only
-__device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int32_t z0, int32_t y0, int32_t x0,
+__device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int64_t z0, int32_t y0, int32_t x0,
                                              uint32_t id, const SkbGeom& g, const void* img, int dtype,
                                              int64_t* __restrict__ lin, int64_t* __restrict__ coords,
                                              double* __restrict__ values) {
@@ -473,7 +473,7 @@ __device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int32_t z
     uint32_t t2 = (uint32_t)y0 + q;
     uint32_t q2 = t2 / (uint32_t)g.ny;
     uint32_t y = t2 - q2 * (uint32_t)g.ny;
-    uint32_t z = (uint32_t)z0 + q2;
+    int64_t z = z0 + q2;
     int64_t* c = coords + (int64_t)id * g.ndim;
     if (g.ndim == 3) {
         c[0] = z;
@@ -498,7 +498,7 @@ __device__ __forceinline__ uint32_t skb_stage_bits(uint64_t w, uint32_t off, uin
 
 __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, int64_t ntiles, SkbGeom g,
-    const void* img, int dtype, int64_t* __restrict__ lin, int64_t* __restrict__ coords,
+    const void* img, int dtype, int64_t z_origin, int64_t* __restrict__ lin, int64_t* __restrict__ coords,
     double* __restrict__ values, uint32_t* __restrict__ pre256) {
     __shared__ uint16_t stage[SKB_EMIT_THREADS / 32][SKB_EMIT_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -536,8 +536,9 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
         const unsigned long long ex = inc - packed;
         const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
         const int64_t r0 = tile * SKB_TILE_VOX;
-        int32_t z0, y0, x0;
-        skb_coords(g, r0, z0, y0, x0);  // warp-uniform; the only 64-bit division of the tile
+        int32_t zt, y0, x0;
+        skb_coords(g, r0, zt, y0, x0);  // warp-uniform; the only 64-bit division of the tile
+        const int64_t z0 = (g.ndim == 3 ? z_origin : 0) + zt;
         uint32_t base = 0;              // nodes of the tile in groups before j
         uint32_t idj[4];
 #pragma unroll
@@ -612,10 +613,11 @@ int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, u
 }
 
 // nodes in raster order (csr.py:131-132,1088,554-562).  tile_prefix: exclusive scan of the
-// tile counts (ntiles+1).  values may be null (bool images).  pre256: u32[ntiles*64].
+// tile counts (ntiles+1).  values may be null (bool images).  pre256: u32[ntiles*64].  z_origin is
+// added to the first coordinate of 3-D images (the volume may be one Z-slab of a larger one).
 int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
-                   const int64_t* shape, const void* image, int dtype, int64_t* lin, int64_t* coords,
-                   double* values, uint32_t* pre256, void* stream) {
+                   const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                   int64_t* coords, double* values, uint32_t* pre256, void* stream) {
     SKB_TRY(skb_check_geom(ndim, shape));
     if (ntiles <= 0) return 0;
     if (values && !image) return skb_fail("values requested without an image");
@@ -624,7 +626,7 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
     int64_t cap = (int64_t)skb_sm_count() * 8;
     if (grid > cap) grid = cap;
     skb_emit_nodes_kernel<<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
-        bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, lin, coords, values, pre256);
+        bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
 }

@@ -444,6 +444,8 @@ struct alignas(16) skb_i4 {
 };
 #define SKB_REC_DEG_MASK 0xff
 #define SKB_REC_CYCLE_ROOT 0x100
+#define SKB_REC_SPLITTER 0x200
+#define SKB_DEAD ((int32_t)0x80000000)  // a list that never reaches a terminal (cycle through splitters)
 
 SKB_HD skb_i4 skb_ld_i4(const skb_i4* p) {
 #if defined(__CUDA_ARCH__)
@@ -463,73 +465,112 @@ SKB_HD void skb_st_i4(skb_i4* p, skb_i4 v) {
 #endif
 }
 
-SKB_HD bool skb_is_splitter(int32_t v) { return (((uint32_t)v * 2654435761u) >> 27) == 0u; }
+// 1/32 hash sample; the key is the node id, or the global raveled voxel index when a volume is
+// split into Z-slabs (every rank must take the same decision for the same voxel)
+SKB_HD bool skb_hash_splitter(int64_t key) {
+    uint32_t h = (uint32_t)key ^ (uint32_t)(key >> 32);
+    return ((h * 2654435761u) >> 27) == 0u;
+}
+
+// Z-slab decomposition of one volume over several GPUs (all-zero / full range on a single GPU).
+// Local node ids index this rank's extended slab (owned planes + halo planes).
+struct SkbSlab {
+    int32_t own0, own1;          // owned nodes [own0, own1)
+    int32_t cnt0, cnt1;          // nodes whose walk starts are numbered: owned + one halo plane on either side
+    int32_t ga0, ga1, gb0, gb1;  // degree-2 nodes in these ranges are forced splitters (slab boundary planes)
+    int32_t id_shift;            // global node id = local id + id_shift
+    int32_t start_shift;         // global start id = startoff[v] + j + start_shift
+    int32_t start_lo, start_hi;  // global ids of the starts leaving owned nodes
+    int64_t lin_offset;          // global raveled index = lin[v] + lin_offset
+};
+
+// per-start payload carried through the ranking when results must be combined across slabs:
+// running sums along the list and a description of the node the list ends at
+struct alignas(16) SkbAux {
+    double sw, sx, sxx;  // sum of edge weights, of node values, of squared node values
+    int64_t end_lin;     // global raveled index of the end node
+    int32_t end_node;    // its global node id
+    int32_t end_deg;     // its degree
+    int32_t end_key;     // global id of its first start (a dense key for the end node)
+    int32_t pad;
+};
 
 // rec[v] = (n0, n1, indptr[v], degree | flags): the two neighbours of a degree-2 node
 struct SkbPathRecItem {  // over nodes
     const int32_t* indptr;
     const int32_t* indices;
+    const int64_t* lin;  // null: splitters are sampled by node id
+    SkbSlab sl;
     skb_i4* rec;
-    uint32_t* n_chain;   // number of degree-2 nodes, summed over 64 slots (pre-zeroed)
+    uint32_t* n_chain;   // number of owned degree-2 nodes, summed over 64 slots (pre-zeroed)
     uint32_t* count;     // phase-0 walk starts leaving v (scanned by the caller)
-    int32_t* par;        // union-find parent / component minimum / "is a component minimum" flag of
-    int32_t* cmin;       // the skeleton-id stage, initialised here while every node is visited anyway
-    uint32_t* is_min;    // (isolated pixels are their own component, csr.py:909)
+    int32_t* par;        // union-find parent / component minimum of the skeleton-id stage (may be null)
+    int32_t* cmin;
+    uint32_t* is_min;    // "is the minimum node of a component": isolated pixels are flagged here (csr.py:909)
     SKB_HD void operator()(int64_t v) const {
         int32_t o = indptr[v], d = indptr[v + 1] - o;
+        int32_t iv = (int32_t)v;
         skb_i4 r;
         r.x = -1;
         r.y = -1;
         r.z = o;
         r.w = d > SKB_REC_DEG_MASK ? SKB_REC_DEG_MASK : d;  // only "== 2" and row scans (bounded below) use it
+        bool split = false;
         if (d == 2) {
             r.x = indices[o];
             r.y = indices[o + 1];
+            split = (iv >= sl.ga0 && iv < sl.ga1) || (iv >= sl.gb0 && iv < sl.gb1) ||
+                    skb_hash_splitter(lin ? lin[v] + sl.lin_offset : (int64_t)v);
+            if (split) r.w |= SKB_REC_SPLITTER;
+            if (iv >= sl.own0 && iv < sl.own1) {
 #if defined(__CUDA_ARCH__)
-            atomicAdd(n_chain + (blockIdx.x & 63), 1u);  // 64 slots: no single hot address
+                atomicAdd(n_chain + (blockIdx.x & 63), 1u);  // 64 slots: no single hot address
 #else
-            *n_chain += 1u;
+                *n_chain += 1u;
 #endif
+            }
         }
         skb_st_i4(rec + v, r);
-        count[v] = (uint32_t)(d != 2 ? d : (skb_is_splitter((int32_t)v) ? 2 : 0));
-        par[v] = (int32_t)v;
-        cmin[v] = (int32_t)v;
+        uint32_t c = 0;
+        if (iv >= sl.cnt0 && iv < sl.cnt1) c = (uint32_t)(d != 2 ? d : (split ? 2 : 0));
+        count[v] = c;
+        if (par) {
+            par[v] = iv;
+            cmin[v] = iv;
+        }
         is_min[v] = d == 0 ? 1u : 0u;
     }
 };
 
-// number of walk starts leaving node v.  phase 0: every half-edge of a terminal, both half-edges
-// of a splitter.  phase 1 (cycles): both half-edges of a cycle root and of an uncovered splitter.
-SKB_HD int32_t skb_start_count(const skb_i4& r, int32_t v, int phase, const uint8_t* covered, int32_t true_deg) {
-    int32_t d = r.w & SKB_REC_DEG_MASK;
-    if (phase == 0) {
-        if (d != 2) return true_deg;
-        return skb_is_splitter(v) ? 2 : 0;
-    }
-    if (r.w & SKB_REC_CYCLE_ROOT) return 2;
-    if (d == 2 && !covered[v] && skb_is_splitter(v)) return 2;
-    return 0;
-}
-
+// walk starts of phase 1 (junction-free cycles): both half-edges of a cycle root and of an
+// uncovered splitter
 struct SkbStartCountItem {  // over nodes
-    const int32_t* indptr;
     const skb_i4* rec;
     const uint8_t* covered;
-    int32_t phase;
+    SkbSlab sl;
     uint32_t* count;
     SKB_HD void operator()(int64_t v) const {
-        count[v] = (uint32_t)skb_start_count(skb_ld_i4(rec + v), (int32_t)v, phase, covered, indptr[v + 1] - indptr[v]);
+        skb_i4 r = skb_ld_i4(rec + v);
+        uint32_t c = 0;
+        if ((int32_t)v >= sl.own0 && (int32_t)v < sl.own1) {
+            if (r.w & SKB_REC_CYCLE_ROOT) c = 2;
+            else if ((r.w & SKB_REC_SPLITTER) && !covered[v]) c = 2;
+        }
+        count[v] = c;
     }
 };
 
-struct SkbStartFillItem {  // over nodes: start s = startoff[v] + j  <->  half-edge (v -> indices[indptr[v]+j])
+// start s (local index) = startoff[v] - startoff[own0] + j  <->  half-edge (v -> indices[indptr[v]+j])
+struct SkbStartFillItem {  // over owned nodes (item index is relative to own0)
     const int32_t* indptr;
     const uint32_t* startoff;
+    int32_t own0;
     int32_t* su;
     int32_t* se;
-    SKB_HD void operator()(int64_t v) const {
-        uint32_t s0 = startoff[v], c = startoff[v + 1] - s0;
+    SKB_HD void operator()(int64_t i) const {
+        int64_t v = i + own0;
+        uint32_t base = startoff[own0];
+        uint32_t s0 = startoff[v] - base, c = startoff[v + 1] - startoff[v];
         int32_t o = indptr[v];
         for (uint32_t j = 0; j < c; ++j) {
             su[s0 + j] = (int32_t)v;
@@ -538,26 +579,52 @@ struct SkbStartFillItem {  // over nodes: start s = startoff[v] + j  <->  half-e
     }
 };
 
-// ranked[s] = (x, y, z, -):  x >= 0: index of the start that continues this list; x < 0: finished,
-// -1-x = index of the start that is the REVERSED last half-edge (B -> m) of the list;
+// ranked[s] = (x, y, z, -):  x >= 0: (global) id of the start that continues this list; x < 0:
+// finished, -1-x = id of the start that is the REVERSED last half-edge (B -> m) of the list;
 // y = half-edges from this start's node to (x >= 0: the next start's node | x < 0: the list end);
-// z = minimum node id seen so far on the list from this start on.
+// z = minimum (global) node id seen so far on the list from this start on.
 struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle root / splitter
     const int32_t* indices;
+    const double* gdata;   // only read when aux is given
+    const double* values;  // null -> 1.0
+    const int64_t* lin;    // only read when aux is given; may be null
     const skb_i4* rec;
     const uint32_t* startoff;
     const int32_t* su;
     const int32_t* se;
+    SkbSlab sl;
     skb_i4* ranked;
+    SkbAux* aux;     // null on a single GPU
+    int32_t* stamp;  // null, or: stamp[v] = a start whose list passes through chain node v
     SKB_HD void operator()(int64_t s) const {
         int32_t u = su[s];
-        int32_t prev = u, cur = indices[se[s]];
+        int32_t arc = se[s];
+        int32_t prev = u, cur = indices[arc];
         int32_t cnt = 1, mn = u;
+        double sw = 0.0, sx = 0.0, sxx = 0.0;
+        if (aux) {
+            double x = values ? values[u] : 1.0;
+            sx = x;
+            sxx = x * x;
+        }
         skb_i4 out;
+        SkbAux ax;
+        ax.end_lin = 0;
+        ax.end_node = -1;
+        ax.end_deg = 0;
+        ax.end_key = -1;
+        ax.pad = 0;
         for (;;) {
             skb_i4 r = skb_ld_i4(rec + cur);
             if (cur < mn) mn = cur;
-            if (r.w != 2) {  // terminal or cycle root: find the reverse half-edge (cur -> prev)
+            if (aux) sw += gdata[arc];
+            if (r.w != 2) {
+                if ((r.w & SKB_REC_SPLITTER) && !(r.w & SKB_REC_CYCLE_ROOT)) {
+                    // the list continues with the splitter's other half-edge
+                    out.x = (int32_t)(startoff[cur] + (r.x == prev ? 1u : 0u)) + sl.start_shift;
+                    break;
+                }
+                // terminal or cycle root: find the reverse half-edge (cur -> prev)
                 int32_t d = r.w & SKB_REC_DEG_MASK;
                 int32_t j = 0;
                 if (d == SKB_REC_DEG_MASK) {  // saturated degree field: unbounded row, rely on symmetry
@@ -565,48 +632,197 @@ struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle ro
                 } else {
                     while (j + 1 < d && indices[r.z + j] != prev) ++j;
                 }
-                out.x = -1 - (int32_t)(startoff[cur] + (uint32_t)j);
+                int32_t key = (int32_t)startoff[cur] + sl.start_shift;
+                out.x = -1 - (key + j);
+                if (aux) {
+                    double x = values ? values[cur] : 1.0;
+                    sx += x;
+                    sxx += x * x;
+                    ax.end_lin = lin ? lin[cur] + sl.lin_offset : (int64_t)cur;
+                    ax.end_node = cur + sl.id_shift;
+                    ax.end_deg = d;
+                    ax.end_key = key;
+                }
                 break;
             }
-            if (skb_is_splitter(cur)) {  // the list continues with the splitter's other half-edge
-                out.x = (int32_t)(startoff[cur] + (r.x == prev ? 1u : 0u));
-                break;
+            if (stamp) stamp[cur] = (int32_t)s;
+            if (aux) {
+                double x = values ? values[cur] : 1.0;
+                sx += x;
+                sxx += x * x;
             }
-            int32_t nxt = (r.x == prev) ? r.y : r.x;
+            int32_t nxt;
+            if (r.x == prev) {
+                nxt = r.y;
+                arc = r.z + 1;
+            } else {
+                nxt = r.x;
+                arc = r.z;
+            }
             prev = cur;
             cur = nxt;
             ++cnt;
         }
         out.y = cnt;
-        out.z = mn;
+        out.z = mn + sl.id_shift;
         out.w = 0;
         skb_st_i4(ranked + s, out);
+        if (aux) {
+            ax.sw = sw;
+            ax.sx = sx;
+            ax.sxx = sxx;
+            aux[s] = ax;
+        }
     }
 };
 
-struct SkbJumpItem {  // over starts: one synchronous pointer-jumping round, src -> dst
+SKB_HD void skb_aux_append(SkbAux& a, const SkbAux& b) {  // list of a followed by list of b
+    a.sw += b.sw;
+    a.sx += b.sx;
+    a.sxx += b.sxx;
+    a.end_lin = b.end_lin;
+    a.end_node = b.end_node;
+    a.end_deg = b.end_deg;
+    a.end_key = b.end_key;
+}
+
+// one synchronous pointer-jumping round, src -> dst, over the starts of this rank; pointers
+// outside [lo, hi) belong to other ranks and are left for the inter-slab round
+struct SkbJumpItem {
     const skb_i4* src;
     skb_i4* dst;
-    int32_t* flag;  // raised when some start reaches its list end in this round
+    const SkbAux* aux_src;  // may be null
+    SkbAux* aux_dst;
+    int32_t lo, hi;
+    int32_t* flag;  // raised when some start stops pointing into [lo, hi) in this round
     SKB_HD void operator()(int64_t s) const {
         skb_i4 a = skb_ld_i4(src + s);
-        if (a.x >= 0) {
-            skb_i4 b = skb_ld_i4(src + a.x);
+        bool local = a.x >= lo && a.x < hi;
+        if (local) {
+            int32_t i = a.x - lo;
+            skb_i4 b = skb_ld_i4(src + i);
             a.y += b.y;
             if (b.z < a.z) a.z = b.z;
             a.x = b.x;
+            if (!(a.x >= lo && a.x < hi)) skb_raise(flag);
+            if (aux_src) {
+                SkbAux A = aux_src[s];
+                skb_aux_append(A, aux_src[i]);
+                aux_dst[s] = A;
+            }
+        } else if (aux_src) {
+            aux_dst[s] = aux_src[s];
+        }
+        skb_st_i4(dst + s, a);
+    }
+};
+
+// ---- inter-slab level: the starts leaving slab-boundary planes, gathered from every rank -----
+// table T = for rank 0, 1, ...: [starts of its first owned plane | starts of its last owned plane]
+#define SKB_MAX_RANKS 16
+struct SkbSlabTable {
+    int32_t n_ranks;
+    int32_t start_off[SKB_MAX_RANKS + 1];  // global id of every rank's first start
+    int32_t n_first[SKB_MAX_RANKS];        // starts leaving the first owned plane
+    int32_t last0[SKB_MAX_RANKS];          // local index of the first start leaving the last owned plane
+    int32_t t_off[SKB_MAX_RANKS];          // position of the rank's block in T
+};
+
+SKB_HD int32_t skb_table_index(const SkbSlabTable& t, int32_t g) {  // global start id -> index in T, or -1
+    for (int k = 0; k < t.n_ranks; ++k) {
+        if (g >= t.start_off[k] && g < t.start_off[k + 1]) {
+            int32_t l = g - t.start_off[k];
+            if (l < t.n_first[k]) return t.t_off[k] + l;
+            if (l >= t.last0[k]) return t.t_off[k] + t.n_first[k] + (l - t.last0[k]);
+            return -1;
+        }
+    }
+    return -1;
+}
+
+struct SkbTableJumpItem {  // over T: pointer jumping on the inter-slab list (every rank does the same)
+    const skb_i4* src;
+    skb_i4* dst;
+    const SkbAux* aux_src;
+    SkbAux* aux_dst;
+    SkbSlabTable t;
+    int32_t* flag;
+    SKB_HD void operator()(int64_t s) const {
+        skb_i4 a = skb_ld_i4(src + s);
+        SkbAux A = aux_src[s];
+        if (a.x >= 0) {
+            int32_t i = skb_table_index(t, a.x);
+            if (i < 0) {
+                a.x = SKB_DEAD;
+            } else {
+                skb_i4 b = skb_ld_i4(src + i);
+                a.y += b.y;
+                if (b.z < a.z) a.z = b.z;
+                a.x = b.x;
+                skb_aux_append(A, aux_src[i]);
+            }
             if (a.x < 0) skb_raise(flag);
         }
         skb_st_i4(dst + s, a);
+        aux_dst[s] = A;
+    }
+};
+
+struct SkbTableExportItem {  // over the rank's block of T: copy the ranked boundary-plane starts
+    const skb_i4* ranked;
+    const SkbAux* aux;
+    int32_t n_first, last0, lo, hi;  // hi - lo = starts of this rank; pointers still inside are cycles
+    skb_i4* out;
+    SkbAux* out_aux;
+    SKB_HD void operator()(int64_t i) const {
+        int64_t s = i < n_first ? i : last0 + (i - n_first);
+        skb_i4 a = skb_ld_i4(ranked + s);
+        if (a.x >= lo && a.x < hi) a.x = SKB_DEAD;
+        skb_st_i4(out + i, a);
+        out_aux[i] = aux[s];
+    }
+};
+
+struct SkbTableApplyItem {  // over the starts of this rank: finish the lists that left the slab
+    skb_i4* ranked;
+    SkbAux* aux;
+    const skb_i4* table;
+    const SkbAux* table_aux;
+    SkbSlabTable t;
+    int32_t lo, hi;
+    SKB_HD void operator()(int64_t s) const {
+        skb_i4 a = skb_ld_i4(ranked + s);
+        if (a.x < 0) return;
+        if (a.x >= lo && a.x < hi) {  // still pointing at a start of this rank: a cycle through splitters
+            a.x = SKB_DEAD;
+        } else {
+            int32_t i = skb_table_index(t, a.x);
+            skb_i4 b;
+            b.x = SKB_DEAD;
+            b.y = 0;
+            b.z = a.z;
+            if (i >= 0) b = skb_ld_i4(table + i);
+            if (b.x >= 0 || b.x == SKB_DEAD) {
+                a.x = SKB_DEAD;
+            } else {
+                a.y += b.y;
+                if (b.z < a.z) a.z = b.z;
+                a.x = b.x;
+                SkbAux A = aux[s];
+                skb_aux_append(A, table_aux[i]);
+                aux[s] = A;
+            }
+        }
+        skb_st_i4(ranked + s, a);
     }
 };
 
 // a half-edge (A,n) starts an emitted path iff it precedes the reversed last half-edge (B,m)
 // in CSR order == in start order (the serial walk of csr.py:347-409 visits start
 // nodes and their neighbours ascending and marks both directions visited)
-SKB_HD bool skb_start_is_head(const skb_i4& r_u, const skb_i4& a, int64_t s, int phase) {
+SKB_HD bool skb_start_is_head(const skb_i4& r_u, const skb_i4& a, int64_t s_global, int phase) {
     bool end_type = phase == 0 ? ((r_u.w & SKB_REC_DEG_MASK) != 2) : ((r_u.w & SKB_REC_CYCLE_ROOT) != 0);
-    return end_type && a.x < 0 && s < (int64_t)(-1 - a.x);
+    return end_type && a.x < 0 && a.x != SKB_DEAD && s_global < (int64_t)(-1 - a.x);
 }
 
 struct SkbSelectItem {  // over starts
@@ -614,9 +830,10 @@ struct SkbSelectItem {  // over starts
     const skb_i4* rec;
     const skb_i4* ranked;
     int32_t phase;
+    int32_t start_lo;
     uint32_t* sel;
     SKB_HD void operator()(int64_t s) const {
-        sel[s] = skb_start_is_head(skb_ld_i4(rec + su[s]), skb_ld_i4(ranked + s), s, phase) ? 1u : 0u;
+        sel[s] = skb_start_is_head(skb_ld_i4(rec + su[s]), skb_ld_i4(ranked + s), s + start_lo, phase) ? 1u : 0u;
     }
 };
 
@@ -624,24 +841,37 @@ struct SkbHeadsItem {  // over starts: path id, start node, length, minimum node
     const int32_t* su;
     const skb_i4* rec;
     const skb_i4* ranked;
+    const SkbAux* aux;    // may be null
     const uint32_t* sel;  // exclusive scan of SkbSelectItem flags
     int32_t phase;
     int32_t pid_base;
+    int32_t start_lo;
+    int32_t id_shift;
     int32_t* start_node;
     uint32_t* plen;
     int32_t* pmin;
-    skb_i2* einfo;  // pre-set to -1; einfo[reversed last start] = (path id, half-edges on the path)
+    skb_i4* einfo;      // single GPU: pre-set to -1; einfo[reversed last start] = (path id, half-edges, -, -)
+    int32_t* head_end;  // slabs: id of the reversed last start of every path
+    SkbAux* head_aux;   // slabs: sums and end node of every path
     SKB_HD void operator()(int64_t s) const {
         skb_i4 a = skb_ld_i4(ranked + s);
-        if (!skb_start_is_head(skb_ld_i4(rec + su[s]), a, s, phase)) return;
+        if (!skb_start_is_head(skb_ld_i4(rec + su[s]), a, s + start_lo, phase)) return;
         int32_t pid = pid_base + (int32_t)sel[s];
-        start_node[pid] = su[s];
+        start_node[pid] = su[s] + id_shift;
         plen[pid] = (uint32_t)a.y + 1u;
         pmin[pid] = a.z;
-        skb_i2 info;
-        info.x = pid;
-        info.y = a.y;
-        einfo[-1 - a.x] = info;
+        if (einfo) {
+            skb_i4 info;
+            info.x = pid;
+            info.y = a.y;
+            info.z = 0;
+            info.w = 0;
+            skb_st_i4(einfo + (-1 - a.x), info);
+        }
+        if (head_end) {
+            head_end[pid] = -1 - a.x;
+            head_aux[pid] = aux[s];
+        }
     }
 };
 
@@ -652,24 +882,25 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
     const int32_t* su;
     const int32_t* se;
     const skb_i4* ranked;
-    const skb_i2* einfo;
-    const int32_t* pindptr;
-    const double* values;  // null -> 1.0 (csr.py:207-215)
-    uint8_t* covered;      // may be null; chain nodes written are marked
+    const skb_i4* einfo;     // indexed by the id of the reversed last start: (path id, half-edges, base, -)
+    const int32_t* pindptr;  // null: the entry offset of the path is einfo.z
+    const double* values;    // null -> 1.0 (csr.py:207-215)
+    uint8_t* covered;        // may be null; chain nodes written are marked
+    int32_t id_shift;
     int32_t* pidx;
     double* pdata;
     double* pw;  // weight of the edge arriving at each entry (0 for the first)
     SKB_HD void operator()(int64_t s) const {
         skb_i4 a = skb_ld_i4(ranked + s);
-        if (a.x >= 0) return;  // list never reaches a terminal: a cycle that phase 1 handles
-        skb_i2 info = einfo[-1 - a.x];
+        if (a.x >= 0 || a.x == SKB_DEAD) return;  // never reaches a terminal: a cycle that phase 1 handles
+        skb_i4 info = skb_ld_i4(einfo + (-1 - a.x));
         if (info.x < 0) return;  // the emitted direction is the other one
-        int64_t base = pindptr[info.x];
+        int64_t base = pindptr ? pindptr[info.x] : info.z;
         int32_t pos = info.y - a.y;  // position of this start's node on the path
         int32_t u = su[s];
         int32_t arc = se[s];
         if (pos == 0) {
-            pidx[base] = u;
+            pidx[base] = u + id_shift;
             pdata[base] = values ? values[u] : 1.0;
             pw[base] = 0.0;
         }
@@ -677,12 +908,14 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
         for (;;) {
             ++pos;
             skb_i4 r = skb_ld_i4(rec + cur);
-            pidx[base + pos] = cur;
+            pidx[base + pos] = cur + id_shift;
             pdata[base + pos] = values ? values[cur] : 1.0;
             pw[base + pos] = gdata[arc];
-            if (r.w != 2) break;
+            if (r.w != 2) {
+                if (covered && (r.w & SKB_REC_DEG_MASK) == 2) covered[cur] = 1;
+                break;
+            }
             if (covered) covered[cur] = 1;
-            if (skb_is_splitter(cur)) break;
             int32_t nxt;
             if (r.x == prev) {
                 nxt = r.y;
@@ -724,7 +957,7 @@ struct SkbCycleHookItem {  // over nodes: uncovered degree-2 nodes join their sm
     int32_t* par;
     SKB_HD void operator()(int64_t v) const {
         skb_i4 r = skb_ld_i4(rec + v);
-        if (r.w != 2 || covered[v]) return;
+        if ((r.w & SKB_REC_DEG_MASK) != 2 || covered[v]) return;
         if (r.x < (int32_t)v) skb_union_min(par, (int32_t)v, r.x);
         if (r.y < (int32_t)v) skb_union_min(par, (int32_t)v, r.y);
     }
@@ -737,9 +970,9 @@ struct SkbCycleRootItem {  // over nodes: the minimum of every cycle becomes its
     uint32_t* is_min;  // a junction-free cycle is a component of its own (csr.py:909)
     SKB_HD void operator()(int64_t v) const {
         skb_i4 r = skb_ld_i4(rec + v);
-        if (r.w != 2 || covered[v]) return;
+        if ((r.w & SKB_REC_DEG_MASK) != 2 || covered[v]) return;
         if (skb_find(par, (int32_t)v) == (int32_t)v) {
-            rec[v].w = 2 | SKB_REC_CYCLE_ROOT;
+            rec[v].w |= SKB_REC_CYCLE_ROOT;
             is_min[v] = 1u;
         }
     }
@@ -791,6 +1024,193 @@ struct SkbCcPathIdItem {  // over all paths
         int32_t src = pidx[pindptr[p]];
         int32_t m = p < n_regular ? cmin[skb_find(par, src)] : src;
         skel_id[p] = (int32_t)rank[m];
+    }
+};
+
+// ---- Z-slab mode: pieces that only exist when a volume is split over several GPUs -------------
+struct SkbRankQueryItem {  // out[i] = number of foreground voxels before raveled position pos[i]
+    const uint64_t* bits;
+    const uint32_t* pre256;
+    const int64_t* pos;
+    int32_t* out;
+    SKB_HD void operator()(int64_t i) const { out[i] = skb_rank(bits, pre256, pos[i]); }
+};
+
+// The junction MST is computed per slab on owned + halo planes; that equals the global result for
+// every cluster of junction voxels that lies inside the slab's trusted planes.  A cluster that
+// reaches both an owned voxel and the outer two halo planes is flagged (the halo is too thin).
+struct SkbMstOuterItem {  // over nodes of the outer halo planes
+    const uint32_t* nb;
+    int32_t* par;
+    uint8_t* outer;  // per root, pre-zeroed
+    int32_t lo1, hi0;  // nodes < lo1 or >= hi0 lie in the outer planes
+    SKB_HD void operator()(int64_t v) const {
+        if (!((int32_t)v < lo1 || (int32_t)v >= hi0)) return;
+        if (skb_popc(nb[v]) >= 3) outer[skb_find(par, (int32_t)v)] = 1;
+    }
+};
+struct SkbMstUnsafeItem {  // over owned nodes
+    const uint32_t* nb;
+    int32_t* par;
+    const uint8_t* outer;
+    int32_t own0;
+    int32_t* flag;
+    SKB_HD void operator()(int64_t i) const {
+        int32_t v = (int32_t)i + own0;
+        if (skb_popc(nb[v]) >= 3 && outer[skb_find(par, v)]) skb_raise(flag);
+    }
+};
+
+struct SkbCoveredItem {  // over nodes: a chain node is covered when a list through it reached a terminal
+    const skb_i4* rec;
+    const uint32_t* startoff;
+    const int32_t* stamp;  // pre-set to -1
+    const skb_i4* ranked;
+    int32_t own0, own1;
+    uint8_t* covered;
+    uint32_t* n_uncovered;  // 64 slots, pre-zeroed: owned chain nodes not covered
+    SKB_HD void operator()(int64_t v) const {
+        skb_i4 r = skb_ld_i4(rec + v);
+        uint8_t c = 0;
+        bool owned = (int32_t)v >= own0 && (int32_t)v < own1;
+        if ((r.w & SKB_REC_DEG_MASK) == 2 && owned) {
+            int32_t s = (r.w & SKB_REC_SPLITTER) ? (int32_t)(startoff[v] - startoff[own0]) : stamp[v];
+            if (s >= 0) {
+                skb_i4 a = skb_ld_i4(ranked + s);
+                c = (a.x < 0 && a.x != SKB_DEAD) ? 1 : 0;
+            }
+            if (!c) {
+#if defined(__CUDA_ARCH__)
+                atomicAdd(n_uncovered + (blockIdx.x & 63), 1u);
+#else
+                *n_uncovered += 1u;
+#endif
+            }
+        }
+        covered[v] = c;
+    }
+};
+
+// per path headed on this rank: what every rank needs to place the path's entries
+// (head = (reversed last start, global path id, half-edges, global entry offset)) and to label
+// components (link = (key of the first node, key of the last node, minimum node id, -))
+struct SkbHeadRecordItem {
+    const int32_t* head_end;
+    const uint32_t* plen;
+    const int32_t* pindptr;  // local exclusive scan of plen
+    const int32_t* pmin;
+    const int32_t* start_node;  // global node ids
+    const uint32_t* startoff;
+    const SkbAux* head_aux;
+    SkbSlab sl;
+    int32_t pid_off, entry_off;
+    skb_i4* head;
+    skb_i4* link;
+    SKB_HD void operator()(int64_t p) const {
+        skb_i4 h;
+        h.x = head_end[p];
+        h.y = pid_off + (int32_t)p;
+        h.z = (int32_t)plen[p] - 1;
+        h.w = entry_off + pindptr[p];
+        skb_st_i4(head + p, h);
+        skb_i4 l;
+        l.x = (int32_t)startoff[start_node[p] - sl.id_shift] + sl.start_shift;
+        l.y = head_aux[p].end_key;
+        l.z = pmin[p];
+        l.w = 0;
+        skb_st_i4(link + p, l);
+    }
+};
+
+struct SkbEinfoScatterItem {  // over the gathered head records: einfo[reversed last start] = (id, half-edges, offset)
+    const skb_i4* head;
+    skb_i4* einfo;  // one slot per start of the whole volume, pre-set to -1
+    SKB_HD void operator()(int64_t p) const {
+        skb_i4 h = skb_ld_i4(head + p);
+        if (h.x < 0) return;  // padding
+        skb_i4 info;
+        info.x = h.y;
+        info.y = h.z;
+        info.z = h.w;
+        info.w = 0;
+        skb_st_i4(einfo + h.x, info);
+    }
+};
+
+// skeleton ids across slabs: union-find over start keys (a dense key space for terminals)
+struct SkbKeyInitItem {
+    int32_t* par;
+    int32_t* cmin;
+    SKB_HD void operator()(int64_t k) const {
+        par[k] = (int32_t)k;
+        cmin[k] = 0x7fffffff;
+    }
+};
+struct SkbKeyUnionItem {  // over the gathered links
+    const skb_i4* link;
+    int32_t* par;
+    SKB_HD void operator()(int64_t p) const {
+        skb_i4 l = skb_ld_i4(link + p);
+        if (l.x < 0) return;  // padding
+        skb_union_min(par, l.x, l.y);
+    }
+};
+struct SkbKeyMinItem {
+    const skb_i4* link;
+    int32_t* par;
+    int32_t* cmin;
+    SKB_HD void operator()(int64_t p) const {
+        skb_i4 l = skb_ld_i4(link + p);
+        if (l.x < 0) return;
+        skb_atomic_min_u32((uint32_t*)cmin + skb_find(par, l.x), (uint32_t)l.z);
+    }
+};
+struct SkbKeyMarkItem {  // component minima that are nodes of this rank
+    const skb_i4* link;
+    int32_t* par;
+    const int32_t* cmin;
+    int32_t node_lo, node_hi, id_shift;  // owned global node ids [node_lo, node_hi)
+    uint32_t* is_min;                    // indexed by local node id
+    SKB_HD void operator()(int64_t p) const {
+        skb_i4 l = skb_ld_i4(link + p);
+        if (l.x < 0) return;
+        int32_t m = cmin[skb_find(par, l.x)];
+        if (m >= node_lo && m < node_hi) is_min[m - id_shift] = 1u;
+    }
+};
+struct SkbKeySkelItem {  // contribution of this rank to the skeleton id of every gathered path
+    const skb_i4* link;
+    int32_t* par;
+    const int32_t* cmin;
+    const uint32_t* rank;  // local exclusive scan of is_min
+    int32_t node_lo, node_hi, id_shift, comp_off, own0;
+    int32_t* skel;  // summed over ranks afterwards
+    SKB_HD void operator()(int64_t p) const {
+        skb_i4 l = skb_ld_i4(link + p);
+        int32_t out = 0;
+        if (l.x >= 0) {
+            int32_t m = cmin[skb_find(par, l.x)];
+            if (m >= node_lo && m < node_hi) out = comp_off + (int32_t)(rank[m - id_shift] - rank[own0]);
+        }
+        skel[p] = out;
+    }
+};
+
+struct SkbSlabStatsItem {  // over the paths headed on this rank
+    const uint32_t* plen;
+    const SkbAux* head_aux;
+    double* dist;
+    double* mean;
+    double* stdev;
+    SKB_HD void operator()(int64_t p) const {
+        double n = (double)plen[p];
+        SkbAux a = head_aux[p];
+        dist[p] = a.sw;
+        double m = a.sx / n;
+        mean[p] = m;
+        double var = a.sxx / n - m * m;
+        if (!(var > 0.0)) var = (var == var) ? 0.0 : var;
+        stdev[p] = skb_sqrt(var);
     }
 };
 
@@ -924,6 +1344,10 @@ struct SkbBranchItem {
     const int32_t* pidx;
     const int32_t* gindptr;
     const int32_t* skel_id;     // per path (SkbCcPathIdItem)
+    const SkbAux* head_aux;     // slabs: the last node of a path may live on another rank
+    const int32_t* start_node;  // slabs: global id of the first node
+    int32_t id_shift;           // slabs: local node id = global id - id_shift
+    int64_t gny, gnx;           // slabs: extents of the whole volume (for the last node's coordinates)
     const int64_t* coords;      // (N, d)
     const double* values;       // node values or null
     double sp_f[3];
@@ -932,23 +1356,44 @@ struct SkbBranchItem {
     int64_t* out_i64;
     double* out_f64;
     SKB_HD void operator()(int64_t p) const {
-        int32_t src = pidx[pindptr[p]];
-        int32_t dst = pidx[pindptr[p + 1] - 1];
+        int32_t src, dst, ds, dd;
+        int64_t cdst[3] = {0, 0, 0};
+        double vdst = 0.0;
+        if (head_aux) {
+            SkbAux a = head_aux[p];
+            src = start_node[p] - id_shift;
+            dst = a.end_node;
+            dd = a.end_deg;
+            int64_t q = a.end_lin / gnx;
+            cdst[2] = a.end_lin - q * gnx;
+            int64_t q2 = q / gny;
+            cdst[1] = q - q2 * gny;
+            cdst[0] = q2;
+            if (d < 3) {  // (y, x) or (x)
+                cdst[0] = cdst[3 - d];
+                if (d == 2) cdst[1] = cdst[2];
+            }
+        } else {
+            src = pidx[pindptr[p]];
+            dst = pidx[pindptr[p + 1] - 1];
+            dd = gindptr[dst + 1] - gindptr[dst];
+            for (int i = 0; i < d; ++i) cdst[i] = coords[(int64_t)dst * d + i];
+            if (height) vdst = values[dst];
+        }
+        ds = gindptr[src + 1] - gindptr[src];
         out_i32[p] = skel_id[p];
-        out_i32[P + p] = src;
+        out_i32[P + p] = src + id_shift;
         out_i32[2 * P + p] = dst;
-        int32_t ds = gindptr[src + 1] - gindptr[src];
-        int32_t dd = gindptr[dst + 1] - gindptr[dst];
         int64_t kind = 2;  // csr.py:916-922, applied in this order
         if (ds == 1 || dd == 1) kind = 1;
         if (ds == 1 && dd == 1) kind = 0;
-        if (src == dst) kind = 3;
+        if (src + id_shift == dst) kind = 3;
         out_i64[p] = kind;
         int dh = d + (height ? 1 : 0);
         double acc = 0.0;
         for (int i = 0; i < d; ++i) {
             int64_t cs = coords[(int64_t)src * d + i];
-            int64_t cd = coords[(int64_t)dst * d + i];
+            int64_t cd = cdst[i];
             out_i64[(1 + i) * P + p] = cs;
             out_i64[(1 + d + i) * P + p] = cd;
             double diff;
@@ -966,7 +1411,7 @@ struct SkbBranchItem {
             acc += diff * diff;
         }
         if (height) {
-            double vs = values[src], vd = values[dst];
+            double vs = values[src], vd = vdst;
             out_f64[d * P + p] = vs;
             out_f64[(dh + d) * P + p] = vd;
             double diff = vd - vs;

@@ -104,8 +104,8 @@ int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, u
 }
 
 int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
-                   const int64_t* shape, const void* image, int dtype, int64_t* lin, int64_t* coords,
-                   double* values, uint32_t* pre256, void*) {
+                   const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                   int64_t* coords, double* values, uint32_t* pre256, void*) {
     SKB_TRY(skb_check_geom(ndim, shape));
     SkbGeom g = skb_make_geom(ndim, shape);
     for (int64_t t = 0; t < ntiles; ++t) {
@@ -122,7 +122,7 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
                 int32_t z, y, x;
                 skb_coords(g, r, z, y, x);
                 int64_t* c = coords + (int64_t)id * ndim;
-                if (ndim == 3) { c[0] = z; c[1] = y; c[2] = x; }
+                if (ndim == 3) { c[0] = z + z_origin; c[1] = y; c[2] = x; }
                 else if (ndim == 2) { c[0] = y; c[1] = x; }
                 else c[0] = x;
                 if (values) values[id] = skb_load_value(image, dtype, r);
