@@ -153,96 +153,147 @@ def main():
     ap.add_argument('--pack-variant', default=None, choices=['ldg', 'tma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--halo', type=int, default=8, help='halo planes of the Z-slab decomposition (N > 1)')
     ap.add_argument('--stages', action='store_true', help='also print a per-entry-point timing table to stderr')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
 
     import torch
+    import torch.distributed as dist
     import __graft_entry__ as entry
-    entry.build()
-    import skan_b200
-    from skan_b200 import _native, _pipeline
-    from skan_b200.synth import walks_device, walks_points
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world != args.gpus:
         raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}')
-    if world > 1:
-        raise SystemExit('multi-GPU volume mode is not implemented yet')
+    if rank == 0:
+        entry.build()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        dist.barrier()
+    import skan_b200
+    from skan_b200 import _native, _pipeline, slab
+    from skan_b200.synth import walks_device, walks_points
+
     if args.pack_variant:
         _pipeline.default_pack_variant = args.pack_variant
     shape, nw, steps, seed, iso, rings, spacing, valued = WORKLOADS[args.workload]
     V = int(np.prod(shape, dtype=np.int64))
+    if world > 1 and (len(shape) != 3 or valued):
+        raise SystemExit('multi-GPU runs use the Z-slab decomposition of a 3-D volume (volume_* workloads)')
 
     # ---- synthetic input, resident in HBM ------------------------------------------------------
-    if valued:
-        mask = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
-        gen = torch.Generator(device=dev).manual_seed(seed)
-        img = (torch.rand(shape, device=dev, generator=gen) * 0.9 + 0.1) * mask
-        del mask
-        esize, dtype_name = 4, 'f32'
+    esize, dtype_name = (4, 'f32') if valued else (1, 'u8')
+    if world == 1:
+        if valued:
+            mask = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
+            gen = torch.Generator(device=dev).manual_seed(seed)
+            img = (torch.rand(shape, device=dev, generator=gen) * 0.9 + 0.1) * mask
+            del mask
+        else:
+            img = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
+        V_local = V
     else:
-        img = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
-        esize, dtype_name = 1, 'u8'
+        # this rank's Z-slab: owned planes [z0, z1) plus `halo` planes on either side; the same
+        # seeded point set on every rank, scattered into the slab only
+        z0, z1, ze0, ze1 = slab.slab_bounds(shape[0], world, rank, args.halo)
+        pts = walks_points(shape, nw, steps, seed, isolated=iso, rings=rings)
+        plane = shape[1] * shape[2]
+        pts = pts[(pts >= ze0 * plane) & (pts < ze1 * plane)] - ze0 * plane
+        img = torch.zeros((ze1 - ze0) * plane, dtype=torch.bool, device=dev)
+        img[torch.from_numpy(pts).to(dev)] = True
+        img = img.reshape(ze1 - ze0, shape[1], shape[2])
+        V_local = int(img.numel())
+        del pts
     torch.cuda.synchronize()
     lib = _native.library()
 
-    def step():
-        return _pipeline.skeleton_and_summary_device(img, spacing=spacing, device=dev)
+    def step(image=None):
+        image = img if image is None else image
+        if world == 1:
+            return _pipeline.skeleton_and_summary_device(image, spacing=spacing, device=dev)
+        return slab.skeleton_and_summary_slab(image, global_shape=shape, z0=z0, z1=z1, ze0=ze0, spacing=spacing,
+                                              device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     for _ in range(max(1, args.warmup)):
         r = step()
-    torch.cuda.synchronize()
-    g, p = r.graph, r.paths
-    counts = dict(nodes=g.n_nodes, edges=g.n_edges, paths=p.n_paths, path_entries=p.n_entries,
-                  junction_edges=g.n_junction_edges, mst_rounds=g.mst_rounds, rank_rounds=p.rank_rounds)
-    alg = _pipeline.algorithmic_bytes(V, esize, len(shape), g.n_nodes, g.n_edges, p.n_paths, p.n_entries, valued)
-    del r, g, p
+    sync_all()
+    if world == 1:
+        g, p = r.graph, r.paths
+        counts = dict(nodes=g.n_nodes, edges=g.n_edges, paths=p.n_paths, path_entries=p.n_entries,
+                      junction_edges=g.n_junction_edges, mst_rounds=g.mst_rounds, rank_rounds=p.rank_rounds)
+        del g, p
+    else:
+        counts = dict(nodes=r.n_nodes_total, edges=r.n_edges_total, paths=r.n_paths_total,
+                      path_entries=r.n_entries_total, halo=args.halo, rank_rounds=r.rank_rounds,
+                      table_records=r.n_table, table_rounds=r.table_rounds, collectives_per_step=6)
+    alg = _pipeline.algorithmic_bytes(V, esize, len(shape), counts['nodes'], counts['edges'], counts['paths'],
+                                      counts['path_entries'], valued)
+    del r
 
-    # ---- timed region: K steps, CUDA events, pack kernel timed by its own events --------------
+    # ---- timed region: K steps, CUDA events, max over ranks; pack kernel timed by its own events ----
     hook = {'skb_pack_count': []}
     _pipeline.EVENT_HOOK = hook
     launches0 = lib.kernel_launches()
     start = torch.cuda.Event(enable_timing=True)
     stop = torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        torch.cuda.synchronize()
+        sync_all()
         start.record()
         for _ in range(args.steps):
             r = step()
             del r
         stop.record()
-        torch.cuda.synchronize()
+        sync_all()
     _pipeline.EVENT_HOOK = None
-    total_ms = start.elapsed_time(stop)
-    launches = lib.kernel_launches() - launches0
+    total_ms = max_over_ranks(start.elapsed_time(stop))
+    launches = int(sum_over_ranks(lib.kernel_launches() - launches0))
     ms = total_ms / args.steps
     value = V / (ms * 1e-3) / 1e6
-    pack_ms = float(np.mean([a.elapsed_time(b) for a, b in hook['skb_pack_count']]))
+    pack_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in hook['skb_pack_count']])))
     peak, peak_src = load_peaks()
-    achieved = V * esize / (pack_ms * 1e-3) / 1e9
+    achieved = V_local * esize / (pack_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': f'skb_pack_{_pipeline.default_pack_variant}_kernel<{esize}>',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peak_src, 'kernel_ms': pack_ms, 'kernel_share_of_step': pack_ms / ms,
-                'algorithmic_bytes_per_launch': V * esize,
+                'algorithmic_bytes_per_launch': V_local * esize,
                 'job': {'algorithmic_bytes': alg, 'achieved': alg / (ms * 1e-3) / 1e9,
-                        'frac': alg / (ms * 1e-3) / 1e9 / peak}}
+                        'frac_of_n_gpus': alg / (ms * 1e-3) / 1e9 / (peak * world)}}
 
     # ---- optional per-entry-point table (one extra step, not part of any reported number) -----
     if args.stages:
         hook = {'*': True}
         _pipeline.EVENT_HOOK = hook
         r = step()
-        torch.cuda.synchronize()
+        sync_all()
         _pipeline.EVENT_HOOK = None
         rows = [(k, sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in hook.items() if k != '*']
-        for k, t, n in sorted(rows, key=lambda x: -x[1]):
-            print(f'  {k:28s} {t:9.3f} ms  ({n} calls)', file=sys.stderr)
+        if rank == 0:
+            for k, t, n in sorted(rows, key=lambda x: -x[1]):
+                print(f'  {k:28s} {t:9.3f} ms  ({n} calls)', file=sys.stderr)
         del r
 
     # ---- end to end through the public API from a pinned host image ---------------------------
@@ -257,33 +308,44 @@ def main():
         d2h = 0
         times = []
         for i in range(1 + n_e2e):
-            torch.cuda.synchronize()
+            sync_all()
             t0 = time.perf_counter()
-            sk = skan_b200.Skeleton(host, spacing=spacing, keep_images=False)
-            df = skan_b200.summarize(sk, separator='_')
-            torch.cuda.synchronize()
+            if world == 1:
+                sk = skan_b200.Skeleton(host, spacing=spacing, keep_images=False)
+                df = skan_b200.summarize(sk, separator='_')
+                d2h = int(df.memory_usage(index=False).sum())
+                del sk, df
+            else:
+                r = step(host.to(dev, non_blocking=True))
+                tabs = [t.cpu() for t in r.table] + [r.dist.cpu(), r.mean.cpu(), r.stdev.cpu()]
+                d2h = int(sum(t.numel() * t.element_size() for t in tabs))
+                del r, tabs
+            sync_all()
             dt = time.perf_counter() - t0
             if i:
                 times.append(dt)
-            d2h = int(df.memory_usage(index=False).sum())
-            del sk, df
-        e2e_s = float(np.mean(times))
-        e2e = {'value': V / e2e_s / 1e6, 'unit': UNIT, 'h2d_bytes_per_step': V * esize, 'd2h_bytes_per_step': d2h,
-               'ms_per_step': e2e_s * 1e3, 'steps': n_e2e}
+        e2e_s = max_over_ranks(float(np.mean(times)))
+        e2e = {'value': V / e2e_s / 1e6, 'unit': UNIT, 'h2d_bytes_per_step': int(sum_over_ranks(V_local * esize)),
+               'd2h_bytes_per_step': int(sum_over_ranks(d2h)), 'ms_per_step': e2e_s * 1e3, 'steps': n_e2e}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': dtype_name, 'data': 'synthetic',
             'config': {'workload': args.workload, 'shape': list(shape), 'spacing': [float(x) for x in np.atleast_1d(spacing)],
-                       'l2': 'input larger than L2 (no flush needed)' if V * esize > 256e6 else 'input fits L2',
+                       'parallelism': 'single GPU' if world == 1 else f'{world} Z-slabs, halo {args.halo}',
+                       'l2': 'input larger than L2 (no flush needed)' if V_local * esize > 256e6 else 'input fits L2',
                        'pack_variant': _pipeline.default_pack_variant, **counts},
             'roofline': roofline, 'clocks': clocks.summary(), 'gpu_launches': int(launches),
             'e2e': e2e}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
         cb = cpu_baseline(args.workload)
         cb.pop('seconds', None)
         line['cpu_baseline'] = cb
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

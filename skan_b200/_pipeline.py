@@ -207,11 +207,13 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
         tree = ctx.empty(nej, torch.uint8)
         flag = ctx.empty(1, torch.int32)
         g.mst_rounds = ctx.call('skb_mst_junctions', ea, eb, ew, nej, N, par, bestw, beste, era, erb, tree, flag)
+        g.mst_par = par
         keep = nb.clone()
         ctx.call('skb_mst_apply', ea, eb, ek, tree, nej, keep)
         g.raw_nb = nb
     else:
         g.mst_rounds = 0
+        g.mst_par = None
         keep = nb
         g.raw_nb = nb
     # --- final CSR ---------------------------------------------------------------------------------

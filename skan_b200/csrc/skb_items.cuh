@@ -1071,8 +1071,8 @@ struct SkbCoveredItem {  // over nodes: a chain node is covered when a list thro
     uint32_t* n_uncovered;  // 64 slots, pre-zeroed: owned chain nodes not covered
     SKB_HD void operator()(int64_t v) const {
         skb_i4 r = skb_ld_i4(rec + v);
-        uint8_t c = 0;
         bool owned = (int32_t)v >= own0 && (int32_t)v < own1;
+        uint8_t c = owned ? 0 : 1;  // halo nodes are another rank's business
         if ((r.w & SKB_REC_DEG_MASK) == 2 && owned) {
             int32_t s = (r.w & SKB_REC_SPLITTER) ? (int32_t)(startoff[v] - startoff[own0]) : stamp[v];
             if (s >= 0) {

@@ -1,0 +1,342 @@
+"""One volume over several GPUs: Z-slab decomposition with a halo and path stitching.
+
+The reference has no distributed layer; this module is the B200-native
+answer to "a volume larger than one device" for the skeleton-to-graph hot path
+(BASELINE.json configs[4]).  One process per GPU, ``torch.distributed``
+for the plumbing (NCCL on GPUs; gloo + the host emulation harness in the CPU unit tests).
+
+Decomposition
+  * rank k owns planes [z0, z1) of the volume and receives them together with ``halo`` planes on
+    either side (clipped at the volume ends): the *extended slab*;
+  * mask sweep, raw neighbourhood masks, junction MST and CSR run on the extended slab exactly as
+    on a single GPU.  Raster-order node ids of consecutive slabs are consecutive, so a global node
+    id is the local id plus a per-rank constant.  The per-slab junction MST equals the global one
+    for every junction cluster that stays inside the trusted planes; a cluster that reaches both
+    an owned voxel and the outer two halo planes is detected and reported (halo too thin);
+  * path tracing: walk starts are numbered for the owned nodes and for the adjacent plane of each
+    neighbour exactly as the neighbour numbers them (all chain voxels of slab-boundary planes are
+    forced splitters), so a list that leaves the slab points at a *global* start id.  Every rank
+    ranks its own lists, then the ranked starts of the boundary planes of all ranks (a few
+    thousand records each) are all-gathered, ranked again (same computation on every rank) and
+    substituted back;
+  * every path is owned by the rank that holds its first node; per-path sums (length, sum and sum
+    of squares of the values) travel with the ranking, so the branch table of a path is computed
+    where it is owned, whatever ranks its voxels live on;
+  * skeleton ids: one (first key, last key, minimum node) record per path is all-gathered, the
+    contracted graph is labelled identically on every rank, each rank ranks the component minima
+    that are its own nodes, and one small all-reduce combines the ids.
+
+Collectives per volume: 3 all-gathers of a handful of integers, 1 all-gather of the boundary
+table, 1 all-gather of the path records, 1 all-reduce of one int32 per path.  No voxel data
+crosses NVLink (the halo planes are part of the input partition).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _pipeline
+
+AUX_BYTES = 48
+
+
+def slab_bounds(nz, world, rank, halo):
+    """Owned planes [z0, z1) and extended planes [ze0, ze1) of `rank` for a volume of nz planes."""
+    base, rem = divmod(nz, world)
+    z0 = rank * base + min(rank, rem)
+    z1 = z0 + base + (1 if rank < rem else 0)
+    return z0, z1, max(0, z0 - halo), min(nz, z1 + halo)
+
+
+def _allgather_ints(vals, device, group):
+    t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=device)
+    world = dist.get_world_size(group)
+    out = torch.empty((world, t.numel()), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out.view(-1), t, group=group)
+    return out.cpu().numpy()
+
+
+def _allgather_padded(t, count, max_count, group):
+    """t: (count, ...) tensor -> (world, max_count, ...) tensor (rows beyond each rank's count are -1)."""
+    world = dist.get_world_size(group)
+    pad = torch.full((max_count,) + tuple(t.shape[1:]), -1, dtype=t.dtype, device=t.device)
+    if count:
+        pad[:count] = t[:count]
+    out = torch.empty((world,) + tuple(pad.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out.view(-1), pad.view(-1), group=group)
+    return out
+
+
+def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=1, device=None, group=None,
+                              pack_variant=None):
+    """Skeleton + summarize of one Z-slab of a 3-D volume, collectively over the process group.
+
+    slab_image: planes [ze0, ze0 + slab_image.shape[0]) of the volume (owned planes [z0, z1) plus
+    the halo).  Returns a namespace with this rank's share of the results (device tensors):
+    graph rows of the owned nodes with global column ids, global path arrays holding the entries
+    of this rank's voxels, and the branch table of the paths whose first node is owned here.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    NZ, NY, NX = (int(x) for x in global_shape)
+    if len(slab_image.shape) != 3:
+        raise ValueError('slab mode is for 3-D volumes')
+    ze1 = ze0 + int(slab_image.shape[0])
+    if not (0 <= ze0 <= z0 < z1 <= ze1 <= NZ) or z1 - z0 < 2:
+        raise ValueError('bad slab bounds (each rank needs at least two owned planes)')
+    has_lo, has_hi = z0 > 0, z1 < NZ
+    if (has_lo and z0 - ze0 < 3) or (has_hi and ze1 - z1 < 3):
+        raise ValueError('slab mode needs a halo of at least 3 planes')
+    sz = NY * NX
+    if device is None:
+        device = slab_image.device if isinstance(slab_image, torch.Tensor) and slab_image.device.type == 'cuda' else None
+    if device is None:
+        from .csr import _default_device
+        device = _default_device()
+    # ---- graph stages on the extended slab -----------------------------------------------------
+    g = _pipeline.pixel_graph(slab_image, spacing=spacing, device=device, pack_variant=pack_variant, z_origin=ze0)
+    ctx = g.ctx
+    Ne = g.n_nodes
+    Vloc = (ze1 - ze0) * sz
+
+    def ranks_at(positions):
+        pos = [min(int(p), Vloc) for p in positions]
+        inside = [p for p in pos if p < Vloc]
+        out = {}
+        if inside and Ne:
+            pt = torch.tensor(inside, dtype=torch.int64, device=ctx.device)
+            ot = ctx.empty(len(inside), torch.int32)
+            ctx.call('skb_rank_query', g.bits, g.pre256, pt, len(inside), ot)
+            out = dict(zip(inside, ot.tolist()))
+        return [Ne if p >= Vloc else (out[p] if Ne else 0) for p in pos]
+
+    p_own0, p_own1 = (z0 - ze0) * sz, (z1 - ze0) * sz
+    own0, own1, f1, l0, hl0, hu1, lo1, hi0 = ranks_at([
+        p_own0, p_own1, p_own0 + sz, p_own1 - sz,
+        p_own0 - sz if has_lo else p_own0, p_own1 + sz if has_hi else p_own1,
+        2 * sz if has_lo else 0, Vloc - 2 * sz if has_hi else Vloc])
+    N_k = own1 - own0
+    # junction clusters must not span owned voxels and the outer halo planes
+    unsafe = 0
+    if g.mst_par is not None and (has_lo or has_hi):
+        outer = ctx.empty(max(Ne, 1), torch.uint8)
+        uflag = ctx.empty(1, torch.int32)
+        ctx.call('skb_mst_halo_check', g.raw_nb, g.mst_par, Ne, own0, own1, lo1 if has_lo else 0,
+                 hi0 if has_hi else Ne, outer, uflag)
+    else:
+        uflag = None
+    indptr, indices, gdata, values, lin = g.indptr, g.indices, g.data, g.values, g.lin
+    # ---- records and start numbering -------------------------------------------------------------
+    slab = torch.zeros(13, dtype=torch.int64)
+    slab[0], slab[1], slab[2], slab[3] = own0, own1, hl0, hu1
+    slab[4], slab[5] = (hl0, f1) if has_lo else (0, 0)
+    slab[6], slab[7] = (l0, hu1) if has_hi else (0, 0)
+    slab[12] = ze0 * sz
+    rec = ctx.empty((max(Ne, 1), 4), torch.int32)
+    n_chain_t = ctx.empty(64, torch.int32)
+    startoff = ctx.empty(Ne + 1, torch.int32)
+    is_min = ctx.empty(Ne + 1, torch.int32)
+    ctx.call('skb_path_records', indptr, indices, lin, slab.data_ptr(), Ne, rec, n_chain_t, startoff, None, None,
+             is_min, ctx.scratch(Ne))
+    sel_idx = torch.tensor([own0, own1, f1, l0], dtype=torch.int64, device=ctx.device)
+    so = startoff.index_select(0, sel_idx).tolist()
+    ei = indptr.index_select(0, sel_idx[:2]).tolist()
+    S_k, SF, SL0 = so[1] - so[0], so[2] - so[0], so[3] - so[0]
+    E_k = ei[1] - ei[0]
+    n_chain = int(n_chain_t.sum().item())
+    counts = _allgather_ints([N_k, E_k, S_k, SF, SL0], ctx.device, group)        # collective 1
+    Noff = np.concatenate([[0], np.cumsum(counts[:, 0])])
+    Eoff = np.concatenate([[0], np.cumsum(counts[:, 1])])
+    Soff = np.concatenate([[0], np.cumsum(counts[:, 2])])
+    S_total, N_total = int(Soff[-1]), int(Noff[-1])
+    if N_total >= 2**31 or S_total >= 2**31:
+        raise ValueError('more than 2^31 nodes: node ids no longer fit the reference\'s int32 index arrays')
+    id_shift = int(Noff[rank]) - own0
+    start_lo, start_hi = int(Soff[rank]), int(Soff[rank + 1])
+    slab[8], slab[9], slab[10], slab[11] = id_shift, start_lo - so[0], start_lo, start_hi
+    # ---- phase 0: lists between terminals, first inside the slab ---------------------------------
+    S = S_k
+    su = ctx.empty(max(S, 1), torch.int32)
+    se = ctx.empty(max(S, 1), torch.int32)
+    buf = [ctx.empty((max(S, 1), 4), torch.int32), ctx.empty((max(S, 1), 4), torch.int32)]
+    aux = [ctx.empty((max(S, 1), AUX_BYTES), torch.uint8), ctx.empty((max(S, 1), AUX_BYTES), torch.uint8)]
+    stamp = torch.full((max(Ne, 1),), -1, dtype=torch.int32, device=ctx.device)
+    flag = ctx.empty(1, torch.int32)
+    ctx.call('skb_path_walk', indptr, indices, gdata, values, lin, rec, startoff, slab.data_ptr(), Ne, S, su, se,
+             buf[0], aux[0], stamp)
+    r = ctx.call('skb_path_rank', buf[0], buf[1], aux[0], aux[1], S, start_lo, start_hi, flag)
+    ranked, raux = buf[r & 1], aux[r & 1]
+    rank_rounds = r >> 1
+    # ---- inter-slab table --------------------------------------------------------------------------
+    nblk = counts[:, 3] + (counts[:, 2] - counts[:, 4])
+    max_blk = int(nblk.max())
+    table_rounds = 0
+    cross_cycle = None
+    if world > 1 and max_blk > 0:
+        my_blk = int(nblk[rank])
+        blk = ctx.empty((max(my_blk, 1), 4), torch.int32)
+        blk_aux = ctx.empty((max(my_blk, 1), AUX_BYTES), torch.uint8)
+        ctx.call('skb_slab_export', ranked, raux, SF, SL0, my_blk, start_lo, start_hi, blk, blk_aux)
+        T = _allgather_padded(blk, my_blk, max_blk, group)                       # collective 2
+        TA = _allgather_padded(blk_aux, my_blk, max_blk, group)
+        t_off = np.concatenate([[0], np.cumsum(nblk)])
+        keep_rows = torch.cat([torch.arange(int(nblk[k]), device=ctx.device) + k * max_blk for k in range(world)])
+        T = T.view(-1, 4).index_select(0, keep_rows).contiguous()
+        TA = TA.view(-1, AUX_BYTES).index_select(0, keep_rows).contiguous()
+        n_table = int(t_off[-1])
+        desc = torch.tensor([world] + [int(x) for x in Soff] + [int(x) for x in counts[:, 3]] +
+                            [int(x) for x in counts[:, 4]] + [int(x) for x in t_off[:-1]], dtype=torch.int64)
+        T2, TA2 = torch.empty_like(T), torch.empty_like(TA)
+        r2 = ctx.call('skb_slab_table_rank', T, T2, TA, TA2, n_table, desc.data_ptr(), flag)
+        Tf, TAf = (T, TA) if (r2 & 1) == 0 else (T2, TA2)
+        table_rounds = r2 >> 1
+        ctx.call('skb_slab_apply', ranked, raux, Tf, TAf, S, desc.data_ptr(), start_lo, start_hi)
+        cross_cycle = (Tf[:, 0] >= 0).any()
+    # ---- covered chain voxels, heads of the regular paths ------------------------------------------
+    covered = ctx.empty(max(Ne, 1), torch.uint8)
+    n_unc_t = ctx.empty(64, torch.int32)
+    ctx.call('skb_slab_covered', rec, startoff, stamp, ranked, Ne, own0, own1, covered, n_unc_t)
+    sel = ctx.empty(S + 1, torch.int32)
+    ctx.call('skb_path_select', su, rec, ranked, S, 0, start_lo, sel, ctx.scratch(S))
+    P0 = int(sel[S].item())
+    n_uncovered = int(n_unc_t.sum().item())
+    # ---- phase 1: junction-free cycles inside the slab -----------------------------------------------
+    cyc = None
+    Pc = 0
+    if n_uncovered > 0:
+        par = ctx.empty(max(Ne, 1), torch.int32)
+        ctx.call('skb_cycle_roots', rec, covered, Ne, par, is_min)
+        startoff_b = ctx.empty(Ne + 1, torch.int32)
+        ctx.call('skb_path_start_count', rec, covered, slab.data_ptr(), Ne, startoff_b, ctx.scratch(Ne))
+        sob = startoff_b.index_select(0, sel_idx[:2]).tolist()
+        Sb = sob[1] - sob[0]
+        if Sb:
+            slab_b = slab.clone()
+            slab_b[9], slab_b[10], slab_b[11] = -sob[0], 0, Sb
+            sub, seb = ctx.empty(Sb, torch.int32), ctx.empty(Sb, torch.int32)
+            bufb = [ctx.empty((Sb, 4), torch.int32), ctx.empty((Sb, 4), torch.int32)]
+            auxb = [ctx.empty((Sb, AUX_BYTES), torch.uint8), ctx.empty((Sb, AUX_BYTES), torch.uint8)]
+            ctx.call('skb_path_walk', indptr, indices, gdata, values, lin, rec, startoff_b, slab_b.data_ptr(), Ne, Sb,
+                     sub, seb, bufb[0], auxb[0], None)
+            rb = ctx.call('skb_path_rank', bufb[0], bufb[1], auxb[0], auxb[1], Sb, 0, Sb, flag)
+            selb = ctx.empty(Sb + 1, torch.int32)
+            ctx.call('skb_path_select', sub, rec, bufb[rb & 1], Sb, 1, 0, selb, ctx.scratch(Sb))
+            Pc = int(selb[Sb].item())
+            cyc = SimpleNamespace(S=Sb, su=sub, se=seb, ranked=bufb[rb & 1], aux=auxb[rb & 1], sel=selb)
+    Pk = P0 + Pc
+    start_node = ctx.empty(max(Pk, 1), torch.int32)
+    plen = ctx.empty(Pk + 1, torch.int32)
+    pmin = ctx.empty(max(Pk, 1), torch.int32)
+    head_end = ctx.empty(max(Pk, 1), torch.int32)
+    head_aux = ctx.empty((max(Pk, 1), AUX_BYTES), torch.uint8)
+    ctx.call('skb_path_heads', su, rec, ranked, raux, sel, S, 0, 0, start_lo, id_shift, start_node, plen, pmin, None,
+             head_end, head_aux)
+    einfo_b = None
+    if Pc:
+        einfo_b = ctx.empty((cyc.S, 4), torch.int32)
+        ctx.call('skb_path_heads', cyc.su, rec, cyc.ranked, cyc.aux, cyc.sel, cyc.S, 1, P0, 0, id_shift, start_node,
+                 plen, pmin, einfo_b, head_end, head_aux)
+    pindptr = ctx.empty(Pk + 1, torch.int32)   # local exclusive scan of the entries: regular paths, then cycles
+    ctx.call('skb_scan_u32', plen, pindptr, Pk, ctx.scratch(Pk))
+    ends = pindptr.index_select(0, torch.tensor([P0, Pk], dtype=torch.int64, device=ctx.device)).tolist()
+    L0, Lc = ends[0], ends[1] - ends[0]
+    uns = int(uflag.item()) if uflag is not None else 0
+    cc = int(cross_cycle.item()) if cross_cycle is not None else 0
+    counts2 = _allgather_ints([P0, L0, Pc, Lc, uns, cc], ctx.device, group)       # collective 3
+    if counts2[:, 4].any():
+        raise RuntimeError('a cluster of junction voxels spans owned planes and the outer halo planes: '
+                           'increase the halo of the Z-slab decomposition')
+    if counts2[:, 5].any():
+        raise NotImplementedError('a junction-free cycle crosses a slab boundary')
+    P0off = np.concatenate([[0], np.cumsum(counts2[:, 0])])
+    L0off = np.concatenate([[0], np.cumsum(counts2[:, 1])])
+    Pcoff = np.concatenate([[0], np.cumsum(counts2[:, 2])])
+    Lcoff = np.concatenate([[0], np.cumsum(counts2[:, 3])])
+    P0_total, L0_total, Pc_total, Lc_total = int(P0off[-1]), int(L0off[-1]), int(Pcoff[-1]), int(Lcoff[-1])
+    P_total, L_total = P0_total + Pc_total, L0_total + Lc_total
+    if P_total == 0:
+        raise ValueError('index pointer size 0 should be 1')
+    # ---- path records to every rank -----------------------------------------------------------------
+    head = ctx.empty((max(P0, 1), 4), torch.int32)
+    link = ctx.empty((max(P0, 1), 4), torch.int32)
+    ctx.call('skb_slab_head_records', head_end, plen, pindptr, pmin, start_node, startoff, head_aux, slab.data_ptr(),
+             Ne, P0, int(P0off[rank]), int(L0off[rank]), head, link)
+    maxP = int(counts2[:, 0].max())
+    nrec = world * maxP
+    heads_all = _allgather_padded(head, P0, max(maxP, 1), group).view(-1, 4)        # collective 4
+    links_all = _allgather_padded(link, P0, max(maxP, 1), group).view(-1, 4)
+    einfo = ctx.empty((max(S_total, 1), 4), torch.int32)
+    ctx.call('skb_slab_einfo', heads_all, nrec, S_total, einfo)
+    # ---- path entries: every rank writes the entries of its own voxels at their global positions ----
+    pidx = torch.zeros(L_total, dtype=torch.int32, device=ctx.device)
+    pdata = torch.zeros(L_total, dtype=torch.float64, device=ctx.device)
+    pw = torch.zeros(L_total, dtype=torch.float64, device=ctx.device)
+    ctx.call('skb_path_emit', indices, gdata, rec, su, se, ranked, einfo, None, values, None, id_shift, S, pidx,
+             pdata, pw)
+    if Pc:
+        gptr = pindptr.clone()
+        gptr[P0:] += (L0_total + int(Lcoff[rank])) - L0
+        ctx.call('skb_path_emit', indices, gdata, rec, cyc.su, cyc.se, cyc.ranked, einfo_b, gptr, values, None,
+                 id_shift, cyc.S, pidx, pdata, pw)
+    # ---- skeleton ids ------------------------------------------------------------------------------------
+    kpar = ctx.empty(max(S_total, 1), torch.int32)
+    kmin = ctx.empty(max(S_total, 1), torch.int32)
+    node_lo, node_hi = int(Noff[rank]), int(Noff[rank + 1])
+    ctx.call('skb_slab_components', links_all, nrec, S_total, kpar, kmin, node_lo, node_hi, id_shift, is_min, Ne,
+             ctx.scratch(Ne))
+    cr = is_min.index_select(0, sel_idx[:2]).tolist()
+    C_k = cr[1] - cr[0]
+    counts3 = _allgather_ints([C_k], ctx.device, group)                             # collective 5
+    Coff = np.concatenate([[0], np.cumsum(counts3[:, 0])])
+    skel_all = ctx.empty(max(nrec, 1), torch.int32)
+    ctx.call('skb_slab_skeleton_ids', links_all, nrec, kpar, kmin, is_min, node_lo, node_hi, id_shift,
+             int(Coff[rank]), own0, skel_all)
+    if world > 1:
+        dist.all_reduce(skel_all, op=dist.ReduceOp.SUM, group=group)               # collective 6
+    skel = ctx.empty(max(Pk, 1), torch.int32)
+    if P0:
+        skel[:P0] = skel_all[rank * maxP: rank * maxP + P0]
+    if Pc:
+        roots_local = (start_node[P0:Pk] - id_shift).long()
+        skel[P0:Pk] = int(Coff[rank]) + is_min.index_select(0, roots_local) - cr[0]
+    # ---- statistics and branch table of the paths owned here ------------------------------------------
+    dist_, mean_, stdev_ = (ctx.empty(max(Pk, 1), torch.float64) for _ in range(3))
+    ctx.call('skb_slab_path_stats', plen, head_aux, Pk, dist_, mean_, stdev_)
+    ndim = 3
+    sp = np.asarray(spacing)
+    if sp.ndim == 0:
+        sp = np.full(ndim, sp)
+    sp_is_int = sp.dtype.kind in 'iub'
+    sp_f = torch.from_numpy(np.ascontiguousarray(sp, dtype=np.float64))
+    sp_i = torch.from_numpy(np.ascontiguousarray(sp.astype(np.int64) if sp_is_int else np.ones(ndim, np.int64)))
+    gshape = torch.tensor([NZ, NY, NX], dtype=torch.int64)
+    o32 = ctx.empty((3, max(Pk, 1)), torch.int32)
+    o64 = ctx.empty((1 + 2 * ndim, max(Pk, 1)), torch.int64)
+    of = ctx.empty((2 * ndim + 1, max(Pk, 1)), torch.float64)
+    if Pk:
+        ctx.call('skb_branch_table', Pk, ndim, 0, 1 if sp_is_int else 0, sp_f.data_ptr(), sp_i.data_ptr(), None, None,
+                 indptr, skel, g.coords, values, head_aux, start_node, id_shift, gshape.data_ptr(), o32, o64, of)
+    return SimpleNamespace(
+        rank=rank, world=world, graph=g, own=(own0, own1), id_shift=id_shift,
+        n_nodes=N_k, n_edges=E_k, node_offset=int(Noff[rank]), edge_offset=int(Eoff[rank]),
+        n_nodes_total=N_total, n_edges_total=int(Eoff[-1]),
+        n_regular=P0, n_cycles=Pc, n_paths_total=P_total, n_entries_total=L_total,
+        n_regular_total=P0_total, regular_offset=int(P0off[rank]), cycle_offset=P0_total + int(Pcoff[rank]),
+        path_len=plen[:Pk], paths_indices=pidx, paths_data=pdata, paths_weights=pw,
+        entry_offset_regular=int(L0off[rank]), entry_offset_cycles=L0_total + int(Lcoff[rank]),
+        dist=dist_[:Pk], mean=mean_[:Pk], stdev=stdev_[:Pk], table=(o32[:, :Pk], o64[:, :Pk], of[:, :Pk]),
+        spacing_is_int=sp_is_int, rank_rounds=rank_rounds, table_rounds=table_rounds, n_starts=S_k,
+        n_table=int(nblk.sum()))
+
+
+def owned_graph(res):
+    """This rank's rows of the global graph: (indptr with global offsets, global indices, data, coordinates)."""
+    g = res.graph
+    a, b = res.own
+    indptr = g.indptr[a:b + 1]
+    e0, e1 = int(indptr[0].item()), int(indptr[-1].item())
+    return (indptr - e0 + res.edge_offset, g.indices[e0:e1] + res.id_shift, g.data[e0:e1], g.coords[a:b],
+            g.degrees[a:b])
