@@ -153,7 +153,7 @@ def main():
     ap.add_argument('--pack-variant', default=None, choices=['ldg', 'tma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--halo', type=int, default=8, help='halo planes of the Z-slab decomposition (N > 1)')
+    ap.add_argument('--halo', type=int, default=2, help='halo planes of the Z-slab decomposition (N > 1)')
     ap.add_argument('--stages', action='store_true', help='also print a per-entry-point timing table to stderr')
     args = ap.parse_args()
     if args.impl == 'reference':

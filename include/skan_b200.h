@@ -67,26 +67,29 @@ int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape /*hos
                       uint32_t* nb, void* stream);
 
 /* Junction-junction edges (both ends of raw degree >= 3; csr.py:1004-1016): per-node count of
- * forward edges, then (after an exclusive scan into `offset`) emission in (a, k27) order with
- * a < b.  ew = fp64 bit pattern of the weight: wtab[k27] (host-computed per nputil.py:278-279) or,
+ * forward edges (only nodes a in [a0, a1): the nodes a Z-slab owns), then (after an exclusive scan
+ * into `offset`) emission in (a, k27) order with a < b.  ew = fp64 bit pattern of the weight: wtab[k27] (host-computed per nputil.py:278-279) or,
  * with height != 0, hypot(values[a]-values[b] in the image dtype, wtab[k27]) (csr.py:1023-1025). */
 int skb_junction_edge_count(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape /*host*/,
-                            const int64_t* lin, const uint32_t* nb, int64_t n, uint32_t* count, void* stream);
+                            const int64_t* lin, const uint32_t* nb, int64_t n, int64_t a0, int64_t a1,
+                            uint32_t* count, void* stream);
 int skb_junction_edge_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape /*host*/,
                            const int64_t* lin, const uint32_t* nb, const uint32_t* offset, int64_t n,
                            const double* wtab, const double* values, int height, int dtype, int32_t* ea,
                            int32_t* eb, uint8_t* ek, uint64_t* ew, void* stream);
 
 /* Junction MST -- replaces _mst_junctions (csr.py:980-1020; scipy minimum_spanning_tree):
- * Boruvka under the strict order (weight, min id, max id).  Scratch: par i32[n], bestw u64[n],
- * beste u32[n], era/erb i32[nej], flag i32[1].  Out: tree u8[nej].  Returns the number of
- * rounds; synchronises once per round. */
+ * Boruvka under the strict order (weight, min id, max id).  Endpoints are node ids < n (global ids
+ * when the edges of several Z-slabs were gathered).  Scratch: par i32[n], bestw u64[n], beste u32[n]
+ * (only entries of edge endpoints are touched), era/erb i32[nej], flag i32[1].  Out: tree u8[nej].
+ * Returns the number of rounds; synchronises once per round. */
 int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, int64_t nej, int64_t n,
                       int32_t* par, uint64_t* bestw, uint32_t* beste, int32_t* era, int32_t* erb, uint8_t* tree,
                       int32_t* flag, void* stream);
-/* keep[] (a copy of nb[]) loses both directions of every non-tree junction edge (csr.py:1018-1019) */
+/* keep[] (a copy of nb[]; n_local entries for node ids id_shift ..) loses both directions of every
+ * non-tree junction edge (csr.py:1018-1019); endpoints outside the local range are skipped */
 int skb_mst_apply(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const uint8_t* tree, int64_t nej,
-                  uint32_t* keep, void* stream);
+                  int64_t id_shift, int64_t n_local, uint32_t* keep, void* stream);
 
 /* Skeleton.degrees (csr.py:660) and graph.indptr: deg i32[n], indptr i32[n+1] */
 int skb_degrees_indptr(const uint32_t* keep, int64_t n, int32_t* deg, int32_t* indptr, void* scratch, void* stream);
@@ -175,15 +178,13 @@ int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, 
                      void* stream);
 
 /* ---- Z-slab mode: one volume split over several GPUs -----------------
- * Every rank runs the graph stages on its owned planes plus `halo` planes on either side, numbers
- * walk starts for its owned nodes and the adjacent halo plane exactly as the neighbour rank does,
- * ranks its own lists, and exchanges only (a) counts, (b) the ranked starts of its two boundary
- * planes ("inter-slab table"), (c) one head + one link record per path. */
+ * Every rank runs the voxel and node stages on its owned planes plus 2 halo planes on either side,
+ * the junction MST on the gathered junction edges of all ranks, numbers walk starts for its owned
+ * nodes and the adjacent halo plane exactly as the neighbour rank does, ranks its own lists, and
+ * exchanges only (a) counts, (b) junction edges, (c) the ranked starts of its two boundary planes
+ * ("inter-slab table"), (d) one head + one link record per path. */
 int skb_rank_query(const uint64_t* bits, const uint32_t* pre256, const int64_t* pos, int64_t n, int32_t* out,
                    void* stream);
-/* flag i32[1] = 1 when a junction cluster spans owned nodes and the outer two halo planes */
-int skb_mst_halo_check(const uint32_t* nb, int32_t* par, int64_t n, int64_t own0, int64_t own1, int64_t lo1,
-                       int64_t hi0, uint8_t* outer, int32_t* flag, void* stream);
 int skb_slab_covered(const skb_i4* rec, const uint32_t* startoff, const int32_t* stamp, const skb_i4* ranked,
                      int64_t n, int64_t own0, int64_t own1, uint8_t* covered, uint32_t* n_uncovered, void* stream);
 int skb_slab_export(const skb_i4* ranked, const void* aux, int64_t n_first, int64_t last0, int64_t n_block,

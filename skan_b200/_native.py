@@ -27,11 +27,11 @@ _SIGNATURES = {
     'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
     'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
     'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp]),
-    'skb_junction_edge_count': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_junction_edge_count': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'skb_junction_edge_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int,
                                       _vp, _vp, _vp, _vp, _vp]),
     'skb_mst_junctions': (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'skb_mst_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_mst_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'skb_degrees_indptr': (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     'skb_csr_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     'skb_path_records': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -48,7 +48,6 @@ _SIGNATURES = {
     'skb_branch_table': (_int, [_i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                 _vp, _vp, _vp, _vp, _vp]),
     'skb_rank_query': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
-    'skb_mst_halo_check': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     'skb_slab_covered': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     'skb_slab_export': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     'skb_slab_table_rank': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -129,9 +129,9 @@ def _as_device_image(image, device):
     return t, code, shape, np_dtype
 
 
-def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant=None, z_origin=0):
-    """skeleton_to_csgraph on the device (csr.py:1028-1089): returns a namespace of device tensors
-    (coords int64 (N,d), values fp64 (N,) | None, indptr/indices int32, data fp64, degrees int32)."""
+def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant=None, z_origin=0):
+    """Voxel and node stages of skeleton_to_csgraph (csr.py:1070,122-144,1088): mask sweep, nodes in
+    raster order (ids, raveled indices, coordinates, values) and raw 3^d neighbourhood masks."""
     ctx = _Ctx(device)
     img, code, shape, np_dtype = _as_device_image(image, ctx.device)
     ndim = len(shape)
@@ -179,54 +179,83 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
         # ends up with direction-dependent weights (SURVEY.md A.8 ii).  Rejected, not reproduced.
         raise ValueError('value_is_height with an unsigned integer image wraps the height differences '
                          '(reference csr.py:1024); cast the image to a signed or floating dtype')
-    wtab = torch.from_numpy(wtab_np).to(ctx.device)
-    g.wtab = wtab
-    geom = (ndim, shape_t.data_ptr())
+    g.wtab = torch.from_numpy(wtab_np).to(ctx.device)
+    g.geom = (ndim, shape_t.data_ptr())
+    g.height = 1 if value_is_height else 0
     # --- raw neighbourhood masks ---------------------------------------------------------------
     nb = ctx.empty(N, torch.int32)
-    ctx.call('skb_raw_neighbors', bits, *geom, lin, N, nb)
-    # --- junction MST ----------------------------------------------------------------------------
+    ctx.call('skb_raw_neighbors', bits, *g.geom, lin, N, nb)
+    g.raw_nb = nb
+    g._keepalive = (img, shape_t)
+    return g
+
+
+def junction_edges(g, a0=0, a1=None):
+    """Junction-junction edges (csr.py:1004-1016) whose smaller endpoint is a node in [a0, a1):
+    (ea, eb int32, ek uint8, ew int64 weight bits), in (a, k27) order."""
+    ctx, N = g.ctx, g.n_nodes
+    a1 = N if a1 is None else a1
     jcount = ctx.empty(N + 1, torch.int32)
-    ctx.call('skb_junction_edge_count', bits, pre256, *geom, lin, nb, N, jcount)
+    ctx.call('skb_junction_edge_count', g.bits, g.pre256, *g.geom, g.lin, g.raw_nb, N, a0, a1, jcount)
     ctx.call('skb_scan_u32', jcount, jcount, N, ctx.scratch(N))
     nej = int(jcount[N].item())
-    g.n_junction_edges = nej
-    height = 1 if value_is_height else 0
+    ea = ctx.empty(nej, torch.int32)
+    eb = ctx.empty(nej, torch.int32)
+    ek = ctx.empty(nej, torch.uint8)
+    ew = ctx.empty(nej, torch.int64)
     if nej:
-        ea = ctx.empty(nej, torch.int32)
-        eb = ctx.empty(nej, torch.int32)
-        ek = ctx.empty(nej, torch.uint8)
-        ew = ctx.empty(nej, torch.int64)
-        ctx.call('skb_junction_edge_emit', bits, pre256, *geom, lin, nb, jcount, N, wtab, values, height, code,
-                 ea, eb, ek, ew)
-        par = ctx.empty(N, torch.int32)
-        bestw = ctx.empty(N, torch.int64)
-        beste = ctx.empty(N, torch.int32)
-        era = ctx.empty(nej, torch.int32)
-        erb = ctx.empty(nej, torch.int32)
-        tree = ctx.empty(nej, torch.uint8)
-        flag = ctx.empty(1, torch.int32)
-        g.mst_rounds = ctx.call('skb_mst_junctions', ea, eb, ew, nej, N, par, bestw, beste, era, erb, tree, flag)
-        g.mst_par = par
-        keep = nb.clone()
-        ctx.call('skb_mst_apply', ea, eb, ek, tree, nej, keep)
-        g.raw_nb = nb
+        ctx.call('skb_junction_edge_emit', g.bits, g.pre256, *g.geom, g.lin, g.raw_nb, jcount, N, g.wtab, g.values,
+                 g.height, g.dtype_code, ea, eb, ek, ew)
+    return ea, eb, ek, ew
+
+
+def junction_mst(ctx, ea, eb, ew, n_ids):
+    """Junction MST (csr.py:980-1020) over edges whose endpoints are ids < n_ids: tree flags uint8[nej]."""
+    nej = int(ea.numel())
+    tree = ctx.empty(nej, torch.uint8)
+    if not nej:
+        return tree, 0
+    par = ctx.empty(n_ids, torch.int32)
+    bestw = ctx.empty(n_ids, torch.int64)
+    beste = ctx.empty(n_ids, torch.int32)
+    era = ctx.empty(nej, torch.int32)
+    erb = ctx.empty(nej, torch.int32)
+    flag = ctx.empty(1, torch.int32)
+    rounds = ctx.call('skb_mst_junctions', ea, eb, ew, nej, n_ids, par, bestw, beste, era, erb, tree, flag)
+    return tree, rounds
+
+
+def graph_csr(g, ea, eb, ek, tree, id_shift=0):
+    """Final CSR (csr.py:153-157 after 1018-1019): drop the non-tree junction edges from the raw
+    masks, degrees, indptr, indices, data."""
+    ctx, N = g.ctx, g.n_nodes
+    nej = int(ea.numel())
+    if nej:
+        keep = g.raw_nb.clone()
+        ctx.call('skb_mst_apply', ea, eb, ek, tree, nej, id_shift, N, keep)
     else:
-        g.mst_rounds = 0
-        g.mst_par = None
-        keep = nb
-        g.raw_nb = nb
-    # --- final CSR ---------------------------------------------------------------------------------
+        keep = g.raw_nb
     deg = ctx.empty(N, torch.int32)
     indptr = ctx.empty(N + 1, torch.int32)
     ctx.call('skb_degrees_indptr', keep, N, deg, indptr, ctx.scratch(N))
     E = int(indptr[N].item())
     indices = ctx.empty(E, torch.int32)
     data = ctx.empty(E, torch.float64)
-    ctx.call('skb_csr_emit', bits, pre256, *geom, lin, keep, indptr, N, wtab, values, height, code, indices, data)
+    ctx.call('skb_csr_emit', g.bits, g.pre256, *g.geom, g.lin, keep, indptr, N, g.wtab, g.values, g.height,
+             g.dtype_code, indices, data)
     g.keep, g.degrees, g.indptr, g.indices, g.data, g.n_edges = keep, deg, indptr, indices, data, E
-    g._keepalive = (img, shape_t)
     return g
+
+
+def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant=None):
+    """skeleton_to_csgraph on the device (csr.py:1028-1089): returns a namespace of device tensors
+    (coords int64 (N,d), values fp64 (N,) | None, indptr/indices int32, data fp64, degrees int32)."""
+    g = graph_nodes(image, spacing=spacing, value_is_height=value_is_height, device=device,
+                    pack_variant=pack_variant)
+    ea, eb, ek, ew = junction_edges(g)
+    g.n_junction_edges = int(ea.numel())
+    tree, g.mst_rounds = junction_mst(g.ctx, ea, eb, ew, g.n_nodes)
+    return graph_csr(g, ea, eb, ek, tree)
 
 
 def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None):

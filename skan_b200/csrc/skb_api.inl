@@ -50,9 +50,10 @@ int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape, cons
 
 // junction-junction edges: per-node forward counts, then emission       (csr.py:1004-1016)
 int skb_junction_edge_count(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape,
-                            const int64_t* lin, const uint32_t* nb, int64_t n, uint32_t* count, void* stream) {
+                            const int64_t* lin, const uint32_t* nb, int64_t n, int64_t a0, int64_t a1,
+                            uint32_t* count, void* stream) {
     SKB_TRY(skb_check_geom(ndim, shape));
-    SkbJuncCountItem it{skb_make_geom(ndim, shape), bits, pre256, lin, nb, count};
+    SkbJuncCountItem it{skb_make_geom(ndim, shape), bits, pre256, lin, nb, (int32_t)a0, (int32_t)a1, count};
     return skb_foreach(n, (skb_stream_t)stream, it);
 }
 
@@ -67,14 +68,17 @@ int skb_junction_edge_emit(const uint64_t* bits, const uint32_t* pre256, int ndi
     return skb_foreach(n, (skb_stream_t)stream, it);
 }
 
-// junction MST (csr.py:980-1020).  Scratch: par i32[n], bestw u64[n], beste u32[n],
-// era/erb i32[nej], flag i32[1].  Out: tree u8[nej] (1 = edge stays).  Returns rounds >= 0.
+// junction MST (csr.py:980-1020).  Edge endpoints are node ids < n (global ids when the edges of
+// several Z-slabs were gathered).  Scratch: par i32[n], bestw u64[n], beste u32[n] (only the
+// entries of edge endpoints are touched), era/erb i32[nej], flag i32[1].
+// Out: tree u8[nej] (1 = edge stays).  Returns rounds >= 0.
 int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, int64_t nej, int64_t n,
                       int32_t* par, uint64_t* bestw, uint32_t* beste, int32_t* era, int32_t* erb, uint8_t* tree,
                       int32_t* flag, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     if (nej <= 0) return 0;
-    SKB_TRY(skb_foreach(n, s, SkbMstInitItem{par, bestw, beste}));
+    (void)n;
+    SKB_TRY(skb_foreach(nej, s, SkbMstInitItem{ea, eb, par, bestw, beste}));
     SKB_TRY(skb_fill_bytes(era, 0, (size_t)nej * 4, s));
     SKB_TRY(skb_fill_bytes(tree, 0, (size_t)nej, s));
     int rounds = 0;
@@ -92,10 +96,12 @@ int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, 
     return rounds;
 }
 
-// keep[] starts as a copy of nb[]; clear both directions of every non-tree junction edge
+// keep[] starts as a copy of nb[]; clear both directions of every non-tree junction edge.
+// keep has n_local entries for the nodes with (global) ids id_shift .. id_shift + n_local - 1.
 int skb_mst_apply(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const uint8_t* tree, int64_t nej,
-                  uint32_t* keep, void* stream) {
-    return skb_foreach(nej, (skb_stream_t)stream, SkbMstApplyItem{ea, eb, ek, tree, keep});
+                  int64_t id_shift, int64_t n_local, uint32_t* keep, void* stream) {
+    return skb_foreach(nej, (skb_stream_t)stream,
+                       SkbMstApplyItem{ea, eb, ek, tree, (int32_t)id_shift, (int32_t)n_local, keep});
 }
 
 // degrees (post-MST, csr.py:660) and graph.indptr: deg i32[n], indptr i32[n+1]
@@ -313,18 +319,6 @@ int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, 
 int skb_rank_query(const uint64_t* bits, const uint32_t* pre256, const int64_t* pos, int64_t n, int32_t* out,
                    void* stream) {
     return skb_foreach(n, (skb_stream_t)stream, SkbRankQueryItem{bits, pre256, pos, out});
-}
-
-// flag = 1 when a junction cluster reaches both an owned node and the outer two halo planes
-// (nodes < lo1 or >= hi0): the per-slab junction MST could then differ from the global one.
-// par = union-find state left by skb_mst_junctions; outer u8[n] scratch.
-int skb_mst_halo_check(const uint32_t* nb, int32_t* par, int64_t n, int64_t own0, int64_t own1, int64_t lo1,
-                       int64_t hi0, uint8_t* outer, int32_t* flag, void* stream) {
-    skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_fill_bytes(outer, 0, (size_t)n, s));
-    SKB_TRY(skb_fill_bytes(flag, 0, 4, s));
-    SKB_TRY(skb_foreach(n, s, SkbMstOuterItem{nb, par, outer, (int32_t)lo1, (int32_t)hi0}));
-    return skb_foreach(own1 - own0, s, SkbMstUnsafeItem{nb, par, outer, (int32_t)own0, flag});
 }
 
 // covered u8[n] from the stamps of the first walk; n_uncovered u32[64] (summed = owned chain nodes

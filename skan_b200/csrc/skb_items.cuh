@@ -219,11 +219,12 @@ struct SkbJuncCountItem {
     const uint32_t* pre256;
     const int64_t* lin;
     const uint32_t* nb;
+    int32_t a0, a1;  // only nodes in [a0, a1) emit their forward edges (the nodes a Z-slab owns)
     uint32_t* count;
     SKB_HD void operator()(int64_t i) const {
         uint32_t m = nb[i];
         uint32_t c = 0;
-        if (skb_popc(m) >= 3 && (m >> 14)) {
+        if ((int32_t)i >= a0 && (int32_t)i < a1 && skb_popc(m) >= 3 && (m >> 14)) {
             SkbJuncCountFn fn{nb, 0u};
             skb_for_neighbors(g, bits, pre256, lin[i], (int32_t)i, m & ~((1u << 14) - 1u), fn);
             c = fn.count;
@@ -289,14 +290,20 @@ SKB_HD int32_t skb_find(int32_t* par, int32_t v) {
     return v;
 }
 
-struct SkbMstInitItem {  // over nodes
+struct SkbMstInitItem {  // over junction edges: only the entries of edge endpoints are ever read
+    const int32_t* ea;
+    const int32_t* eb;
     int32_t* par;
     uint64_t* bestw;
     uint32_t* beste;
-    SKB_HD void operator()(int64_t v) const {
-        par[v] = (int32_t)v;
-        bestw[v] = ~0ull;
-        beste[v] = ~0u;
+    SKB_HD void operator()(int64_t e) const {
+        int32_t a = ea[e], b = eb[e];
+        par[a] = a;
+        par[b] = b;
+        bestw[a] = ~0ull;
+        bestw[b] = ~0ull;
+        beste[a] = ~0u;
+        beste[b] = ~0u;
     }
 };
 
@@ -383,12 +390,15 @@ struct SkbMstApplyItem {  // drop non-tree junction-junction edges in both direc
     const int32_t* eb;
     const uint8_t* ek;
     const uint8_t* tree;
+    int32_t id_shift;  // edge endpoints are global ids; keep[] is indexed by local id = global - id_shift
+    int32_t n_local;   // endpoints that are not nodes of this slab are skipped
     uint32_t* keep;
     SKB_HD void operator()(int64_t e) const {
         if (tree[e]) return;
         int k = ek[e];
-        skb_atomic_and_u32(keep + ea[e], ~(1u << k));
-        skb_atomic_and_u32(keep + eb[e], ~(1u << (26 - k)));
+        int32_t a = ea[e] - id_shift, b = eb[e] - id_shift;
+        if (a >= 0 && a < n_local) skb_atomic_and_u32(keep + a, ~(1u << k));
+        if (b >= 0 && b < n_local) skb_atomic_and_u32(keep + b, ~(1u << (26 - k)));
     }
 };
 
@@ -1034,31 +1044,6 @@ struct SkbRankQueryItem {  // out[i] = number of foreground voxels before ravele
     const int64_t* pos;
     int32_t* out;
     SKB_HD void operator()(int64_t i) const { out[i] = skb_rank(bits, pre256, pos[i]); }
-};
-
-// The junction MST is computed per slab on owned + halo planes; that equals the global result for
-// every cluster of junction voxels that lies inside the slab's trusted planes.  A cluster that
-// reaches both an owned voxel and the outer two halo planes is flagged (the halo is too thin).
-struct SkbMstOuterItem {  // over nodes of the outer halo planes
-    const uint32_t* nb;
-    int32_t* par;
-    uint8_t* outer;  // per root, pre-zeroed
-    int32_t lo1, hi0;  // nodes < lo1 or >= hi0 lie in the outer planes
-    SKB_HD void operator()(int64_t v) const {
-        if (!((int32_t)v < lo1 || (int32_t)v >= hi0)) return;
-        if (skb_popc(nb[v]) >= 3) outer[skb_find(par, (int32_t)v)] = 1;
-    }
-};
-struct SkbMstUnsafeItem {  // over owned nodes
-    const uint32_t* nb;
-    int32_t* par;
-    const uint8_t* outer;
-    int32_t own0;
-    int32_t* flag;
-    SKB_HD void operator()(int64_t i) const {
-        int32_t v = (int32_t)i + own0;
-        if (skb_popc(nb[v]) >= 3 && outer[skb_find(par, v)]) skb_raise(flag);
-    }
 };
 
 struct SkbCoveredItem {  // over nodes: a chain node is covered when a list through it reached a terminal

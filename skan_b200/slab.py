@@ -8,11 +8,15 @@ for the plumbing (NCCL on GPUs; gloo + the host emulation harness in the CPU uni
 Decomposition
   * rank k owns planes [z0, z1) of the volume and receives them together with ``halo`` planes on
     either side (clipped at the volume ends): the *extended slab*;
-  * mask sweep, raw neighbourhood masks, junction MST and CSR run on the extended slab exactly as
-    on a single GPU.  Raster-order node ids of consecutive slabs are consecutive, so a global node
-    id is the local id plus a per-rank constant.  The per-slab junction MST equals the global one
-    for every junction cluster that stays inside the trusted planes; a cluster that reaches both
-    an owned voxel and the outer two halo planes is detected and reported (halo too thin);
+  * mask sweep, node emission, raw neighbourhood masks and CSR emission run on the extended slab
+    exactly as on a single GPU.  Raster-order node ids of consecutive slabs are consecutive, so a
+    global node id is the local id plus a per-rank constant.  Two halo planes make the raw masks
+    (and so the "junction" test, raw degree >= 3) exact for the owned voxels and for the adjacent
+    plane of each neighbour;
+  * junction MST: clusters of junction voxels cross slab boundaries freely, so every rank emits the
+    junction-junction edges whose smaller endpoint it owns (with global ids), the edge lists are
+    all-gathered in rank order (which is the global (a, b) order the tie-break needs) and every
+    rank runs the same Boruvka on them; the edge set is ~3 % of the nodes, so this costs little;
   * path tracing: walk starts are numbered for the owned nodes and for the adjacent plane of each
     neighbour exactly as the neighbour numbers them (all chain voxels of slab-boundary planes are
     forced splitters), so a list that leaves the slab points at a *global* start id.  Every rank
@@ -26,9 +30,9 @@ Decomposition
     contracted graph is labelled identically on every rank, each rank ranks the component minima
     that are its own nodes, and one small all-reduce combines the ids.
 
-Collectives per volume: 3 all-gathers of a handful of integers, 1 all-gather of the boundary
-table, 1 all-gather of the path records, 1 all-reduce of one int32 per path.  No voxel data
-crosses NVLink (the halo planes are part of the input partition).
+Collectives per volume: 4 all-gathers of a handful of integers, 1 all-gather of the junction edges,
+1 of the boundary table, 1 of the path records, 1 all-reduce of one int32 per path.  No voxel
+data crosses NVLink (the halo planes are part of the input partition).
 """
 from __future__ import annotations
 
@@ -88,16 +92,16 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     if not (0 <= ze0 <= z0 < z1 <= ze1 <= NZ) or z1 - z0 < 2:
         raise ValueError('bad slab bounds (each rank needs at least two owned planes)')
     has_lo, has_hi = z0 > 0, z1 < NZ
-    if (has_lo and z0 - ze0 < 3) or (has_hi and ze1 - z1 < 3):
-        raise ValueError('slab mode needs a halo of at least 3 planes')
+    if (has_lo and z0 - ze0 < 2) or (has_hi and ze1 - z1 < 2):
+        raise ValueError('slab mode needs a halo of at least 2 planes')
     sz = NY * NX
     if device is None:
         device = slab_image.device if isinstance(slab_image, torch.Tensor) and slab_image.device.type == 'cuda' else None
     if device is None:
         from .csr import _default_device
         device = _default_device()
-    # ---- graph stages on the extended slab -----------------------------------------------------
-    g = _pipeline.pixel_graph(slab_image, spacing=spacing, device=device, pack_variant=pack_variant, z_origin=ze0)
+    # ---- voxel and node stages on the extended slab ---------------------------------------------
+    g = _pipeline.graph_nodes(slab_image, spacing=spacing, device=device, pack_variant=pack_variant, z_origin=ze0)
     ctx = g.ctx
     Ne = g.n_nodes
     Vloc = (ze1 - ze0) * sz
@@ -114,20 +118,39 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
         return [Ne if p >= Vloc else (out[p] if Ne else 0) for p in pos]
 
     p_own0, p_own1 = (z0 - ze0) * sz, (z1 - ze0) * sz
-    own0, own1, f1, l0, hl0, hu1, lo1, hi0 = ranks_at([
+    own0, own1, f1, l0, hl0, hu1 = ranks_at([
         p_own0, p_own1, p_own0 + sz, p_own1 - sz,
-        p_own0 - sz if has_lo else p_own0, p_own1 + sz if has_hi else p_own1,
-        2 * sz if has_lo else 0, Vloc - 2 * sz if has_hi else Vloc])
+        p_own0 - sz if has_lo else p_own0, p_own1 + sz if has_hi else p_own1])
     N_k = own1 - own0
-    # junction clusters must not span owned voxels and the outer halo planes
-    unsafe = 0
-    if g.mst_par is not None and (has_lo or has_hi):
-        outer = ctx.empty(max(Ne, 1), torch.uint8)
-        uflag = ctx.empty(1, torch.int32)
-        ctx.call('skb_mst_halo_check', g.raw_nb, g.mst_par, Ne, own0, own1, lo1 if has_lo else 0,
-                 hi0 if has_hi else Ne, outer, uflag)
+    # ---- junction MST on the junction edges of the whole volume -------------------------------------
+    # every rank emits the edges whose smaller endpoint it owns (global ids), all ranks gather them
+    # in rank order (= global (a, b) order, the MST's tie-break) and solve the same problem
+    ea, eb, ek, ew = _pipeline.junction_edges(g, own0, own1)
+    nej_k = int(ea.numel())
+    counts0 = _allgather_ints([N_k, nej_k], ctx.device, group)                     # collective 1
+    Noff = np.concatenate([[0], np.cumsum(counts0[:, 0])])
+    N_total = int(Noff[-1])
+    if N_total >= 2**31:
+        raise ValueError("more than 2^31 nodes: node ids no longer fit the reference's int32 index arrays")
+    id_shift = int(Noff[rank]) - own0
+    if world > 1:
+        max_e = int(counts0[:, 1].max())
+        if max_e:
+            packed = torch.stack([(ea.long() + id_shift) | ((eb.long() + id_shift) << 32), ew, ek.long()], dim=1) \
+                if nej_k else torch.zeros((1, 3), dtype=torch.int64, device=ctx.device)
+            allp = _allgather_padded(packed, nej_k, max_e, group)                  # collective 2
+            rows = torch.cat([torch.arange(int(counts0[k, 1]), device=ctx.device) + k * max_e for k in range(world)])
+            allp = allp.view(-1, 3).index_select(0, rows)
+            gea = (allp[:, 0] & 0xffffffff).int()
+            geb = (allp[:, 0] >> 32).int()
+            gew = allp[:, 1].contiguous()
+            gek = allp[:, 2].to(torch.uint8)
+        else:
+            gea, geb, gek, gew = ea, eb, ek, ew
     else:
-        uflag = None
+        gea, geb, gek, gew = ea + id_shift, eb + id_shift, ek, ew
+    tree, mst_rounds = _pipeline.junction_mst(ctx, gea, geb, gew, N_total)
+    _pipeline.graph_csr(g, gea, geb, gek, tree, id_shift)
     indptr, indices, gdata, values, lin = g.indptr, g.indices, g.data, g.values, g.lin
     # ---- records and start numbering -------------------------------------------------------------
     slab = torch.zeros(13, dtype=torch.int64)
@@ -147,14 +170,10 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     S_k, SF, SL0 = so[1] - so[0], so[2] - so[0], so[3] - so[0]
     E_k = ei[1] - ei[0]
     n_chain = int(n_chain_t.sum().item())
-    counts = _allgather_ints([N_k, E_k, S_k, SF, SL0], ctx.device, group)        # collective 1
-    Noff = np.concatenate([[0], np.cumsum(counts[:, 0])])
+    counts = _allgather_ints([N_k, E_k, S_k, SF, SL0], ctx.device, group)        # collective 3
     Eoff = np.concatenate([[0], np.cumsum(counts[:, 1])])
     Soff = np.concatenate([[0], np.cumsum(counts[:, 2])])
-    S_total, N_total = int(Soff[-1]), int(Noff[-1])
-    if N_total >= 2**31 or S_total >= 2**31:
-        raise ValueError('more than 2^31 nodes: node ids no longer fit the reference\'s int32 index arrays')
-    id_shift = int(Noff[rank]) - own0
+    S_total = int(Soff[-1])
     start_lo, start_hi = int(Soff[rank]), int(Soff[rank + 1])
     slab[8], slab[9], slab[10], slab[11] = id_shift, start_lo - so[0], start_lo, start_hi
     # ---- phase 0: lists between terminals, first inside the slab ---------------------------------
@@ -180,7 +199,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
         blk = ctx.empty((max(my_blk, 1), 4), torch.int32)
         blk_aux = ctx.empty((max(my_blk, 1), AUX_BYTES), torch.uint8)
         ctx.call('skb_slab_export', ranked, raux, SF, SL0, my_blk, start_lo, start_hi, blk, blk_aux)
-        T = _allgather_padded(blk, my_blk, max_blk, group)                       # collective 2
+        T = _allgather_padded(blk, my_blk, max_blk, group)                       # collective 4
         TA = _allgather_padded(blk_aux, my_blk, max_blk, group)
         t_off = np.concatenate([[0], np.cumsum(nblk)])
         keep_rows = torch.cat([torch.arange(int(nblk[k]), device=ctx.device) + k * max_blk for k in range(world)])
@@ -243,13 +262,9 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     ctx.call('skb_scan_u32', plen, pindptr, Pk, ctx.scratch(Pk))
     ends = pindptr.index_select(0, torch.tensor([P0, Pk], dtype=torch.int64, device=ctx.device)).tolist()
     L0, Lc = ends[0], ends[1] - ends[0]
-    uns = int(uflag.item()) if uflag is not None else 0
     cc = int(cross_cycle.item()) if cross_cycle is not None else 0
-    counts2 = _allgather_ints([P0, L0, Pc, Lc, uns, cc], ctx.device, group)       # collective 3
+    counts2 = _allgather_ints([P0, L0, Pc, Lc, cc], ctx.device, group)            # collective 5
     if counts2[:, 4].any():
-        raise RuntimeError('a cluster of junction voxels spans owned planes and the outer halo planes: '
-                           'increase the halo of the Z-slab decomposition')
-    if counts2[:, 5].any():
         raise NotImplementedError('a junction-free cycle crosses a slab boundary')
     P0off = np.concatenate([[0], np.cumsum(counts2[:, 0])])
     L0off = np.concatenate([[0], np.cumsum(counts2[:, 1])])
@@ -266,7 +281,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
              Ne, P0, int(P0off[rank]), int(L0off[rank]), head, link)
     maxP = int(counts2[:, 0].max())
     nrec = world * maxP
-    heads_all = _allgather_padded(head, P0, max(maxP, 1), group).view(-1, 4)        # collective 4
+    heads_all = _allgather_padded(head, P0, max(maxP, 1), group).view(-1, 4)        # collective 6
     links_all = _allgather_padded(link, P0, max(maxP, 1), group).view(-1, 4)
     einfo = ctx.empty((max(S_total, 1), 4), torch.int32)
     ctx.call('skb_slab_einfo', heads_all, nrec, S_total, einfo)
@@ -289,13 +304,13 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
              ctx.scratch(Ne))
     cr = is_min.index_select(0, sel_idx[:2]).tolist()
     C_k = cr[1] - cr[0]
-    counts3 = _allgather_ints([C_k], ctx.device, group)                             # collective 5
+    counts3 = _allgather_ints([C_k], ctx.device, group)                             # collective 7
     Coff = np.concatenate([[0], np.cumsum(counts3[:, 0])])
     skel_all = ctx.empty(max(nrec, 1), torch.int32)
     ctx.call('skb_slab_skeleton_ids', links_all, nrec, kpar, kmin, is_min, node_lo, node_hi, id_shift,
              int(Coff[rank]), own0, skel_all)
     if world > 1:
-        dist.all_reduce(skel_all, op=dist.ReduceOp.SUM, group=group)               # collective 6
+        dist.all_reduce(skel_all, op=dist.ReduceOp.SUM, group=group)               # collective 8
     skel = ctx.empty(max(Pk, 1), torch.int32)
     if P0:
         skel[:P0] = skel_all[rank * maxP: rank * maxP + P0]

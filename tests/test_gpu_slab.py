@@ -9,8 +9,9 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('args', [
-    ['--kind', 'walks', '--shape', '96,64,64', '--halo', '6', '--seed', '11'],
-    ['--kind', 'lines_z', '--shape', '64,33,40', '--halo', '3'],
+    ['--kind', 'walks', '--shape', '96,64,64', '--halo', '2', '--seed', '11'],
+    ['--kind', 'dense12', '--shape', '64,32,32', '--halo', '2', '--seed', '5'],
+    ['--kind', 'lines_z', '--shape', '64,33,40', '--halo', '2'],
     ['--kind', 'walks', '--shape', '128,96,80', '--halo', '8', '--seed', '12', '--valued', '1'],
 ])
 def test_slab_mode_nccl(args):

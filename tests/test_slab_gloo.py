@@ -32,10 +32,10 @@ def launch(world, *args, backend='gloo', emulate=1, timeout=420):
 
 
 @pytest.mark.parametrize('world,args', [
-    (2, ['--kind', 'walks', '--shape', '24,20,28', '--halo', '4']),
+    (2, ['--kind', 'walks', '--shape', '24,20,28', '--halo', '2']),
     (3, ['--kind', 'walks', '--shape', '48,32,32', '--halo', '5', '--seed', '7', '--valued', '1']),
     (2, ['--kind', 'lines_z', '--shape', '40,21,30', '--halo', '3']),
-    (3, ['--kind', 'dense', '--shape', '60,20,20', '--halo', '9', '--seed', '6']),
+    (3, ['--kind', 'dense', '--shape', '60,20,20', '--halo', '2', '--seed', '6']),
 ])
 def test_slab_mode_matches_oracle(world, args):
     codes, outs = launch(world, *args)
@@ -43,10 +43,9 @@ def test_slab_mode_matches_oracle(world, args):
     assert 'SLAB-OK' in outs[0]
 
 
-def test_thin_halo_is_detected():
-    # a dense volume has junction clusters that span the halo: every rank must refuse, not guess
-    codes, outs = launch(2, '--kind', 'dense12', '--shape', '40,16,16', '--halo', '8', '--seed', '5')
-    if all(c == 0 for c in codes):
-        pytest.skip('no junction cluster crossed the halo for this seed')
-    assert all(c != 0 for c in codes)
-    assert any('increase the halo' in o for o in outs)
+def test_junction_clusters_across_slab_boundaries():
+    # a dense volume: junction clusters percolate through every slab boundary; the junction MST is
+    # solved on the gathered junction edges, so the result must still equal the oracle's
+    codes, outs = launch(2, '--kind', 'dense12', '--shape', '40,16,16', '--halo', '2', '--seed', '5')
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0]
