@@ -172,6 +172,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ['NCCL_DEBUG'] = 'WARN'  # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
         dist.barrier()
     import skan_b200
@@ -249,7 +250,7 @@ def main():
     else:
         counts = dict(nodes=r.n_nodes_total, edges=r.n_edges_total, paths=r.n_paths_total,
                       path_entries=r.n_entries_total, halo=args.halo, rank_rounds=r.rank_rounds,
-                      table_records=r.n_table, table_rounds=r.table_rounds, collectives_per_step=6)
+                      table_records=r.n_table, table_rounds=r.table_rounds, collectives_per_step=8)
     alg = _pipeline.algorithmic_bytes(V, esize, len(shape), counts['nodes'], counts['edges'], counts['paths'],
                                       counts['path_entries'], valued)
     del r
