@@ -47,9 +47,10 @@ int64_t skb_kernel_launches(void);         /* kernels launched by the library si
 int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, uint32_t* tile_counts,
                    int64_t ntiles, int variant, void* stream);
 
-/* Exclusive scans with n+1 outputs (out[n] = total); in == out allowed. */
+/* Exclusive scan with n+1 outputs (out[n] = total); in == out allowed.  Single pass (decoupled
+ * look-back).  `scratch` (here and in every call that takes one): skb_scan_scratch_bytes(n) bytes,
+ * zeroed ONCE by the caller and then reusable by later calls on the same stream. */
 int skb_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, void* stream);
-int skb_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, void* scratch, void* stream);
 
 /* Nodes in raster order -- replaces np.flatnonzero / np.unravel_index / _extract_values
  * (csr.py:131-132, 1088, 554-562).  tile_prefix = scanned tile counts (ntiles+1).
@@ -81,7 +82,7 @@ int skb_junction_edge_emit(const uint64_t* bits, const uint32_t* pre256, int ndi
 /* Junction MST -- replaces _mst_junctions (csr.py:980-1020; scipy minimum_spanning_tree):
  * Boruvka under the strict order (weight, min id, max id).  Endpoints are node ids < n (global ids
  * when the edges of several Z-slabs were gathered).  Scratch: par i32[n], bestw u64[n], beste u32[n]
- * (only entries of edge endpoints are touched), era/erb i32[nej], flag i32[1].  Out: tree u8[nej].
+ * (only entries of edge endpoints are touched), era/erb i32[nej], flag i32[4].  Out: tree u8[nej].
  * Returns the number of rounds; synchronises once per round. */
 int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, int64_t nej, int64_t n,
                       int32_t* par, uint64_t* bestw, uint32_t* beste, int32_t* era, int32_t* erb, uint8_t* tree,

@@ -60,7 +60,6 @@ _SIGNATURES = {
     'skb_slab_path_stats': (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'skb_path_label_image': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     'skb_scan_u32': (_int, [_vp, _vp, _i64, _vp, _vp]),
-    'skb_scan_u64': (_int, [_vp, _vp, _i64, _vp, _vp]),
 }
 
 EXPORTS = tuple(sorted(_SIGNATURES))

@@ -84,7 +84,8 @@ class _Ctx:
     def scratch(self, n):
         need = self.lib.scan_scratch_bytes(n)
         if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = self.empty(max(need, 1 << 16), torch.uint8)
+            # zeroed once: the single-pass scan tags its tile statuses with an epoch
+            self._scratch = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
         return self._scratch.data_ptr()
 
     def call(self, name, *args):
@@ -220,7 +221,7 @@ def junction_mst(ctx, ea, eb, ew, n_ids):
     beste = ctx.empty(n_ids, torch.int32)
     era = ctx.empty(nej, torch.int32)
     erb = ctx.empty(nej, torch.int32)
-    flag = ctx.empty(1, torch.int32)
+    flag = ctx.empty(4, torch.int32)
     rounds = ctx.call('skb_mst_junctions', ea, eb, ew, nej, n_ids, par, bestw, beste, era, erb, tree, flag)
     return tree, rounds
 
@@ -288,7 +289,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None)
         su = ctx.empty(S, torch.int32)
         se = ctx.empty(S, torch.int32)
         buf = [ctx.empty((S, 4), torch.int32), ctx.empty((S, 4), torch.int32)]
-        flag = ctx.empty(1, torch.int32)
+        flag = ctx.empty(4, torch.int32)
         ctx.call('skb_path_walk', indptr, indices, gdata, values, lin, rec, startoff, None, N, S, su, se, buf[0],
                  None, None)
         r = ctx.call('skb_path_rank', buf[0], buf[1], None, None, S, 0, S, flag)

@@ -6,7 +6,7 @@
 //   int  skb_foreach(int64_t n, skb_stream_t s, Functor f)
 //   int  skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t s)
 //   int  skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s)      (synchronises)
-//   int  skb_scan_u32_impl / skb_scan_u64_impl (exclusive scans, n+1 outputs)
+//   int  skb_scan_u32_impl (exclusive scan, n+1 outputs; scratch zeroed once by the caller)
 //   int  skb_fail(const char* what)                                               (records the message)
 // and the three block-cooperative stages (pack, node emit, scans) itself.
 
@@ -78,6 +78,9 @@ int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, 
     skb_stream_t s = (skb_stream_t)stream;
     if (nej <= 0) return 0;
     (void)n;
+#ifdef SKB_HAVE_FUSED_LOOPS
+    return skb_mst_run(ea, eb, ew, nej, par, bestw, beste, era, erb, tree, flag, s);
+#else
     SKB_TRY(skb_foreach(nej, s, SkbMstInitItem{ea, eb, par, bestw, beste}));
     SKB_TRY(skb_fill_bytes(era, 0, (size_t)nej * 4, s));
     SKB_TRY(skb_fill_bytes(tree, 0, (size_t)nej, s));
@@ -94,6 +97,7 @@ int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, 
         SKB_TRY(skb_foreach(nej, s, SkbMstResetItem{era, erb, bestw, beste}));
     }
     return rounds;
+#endif
 }
 
 // keep[] starts as a copy of nb[]; clear both directions of every non-tree junction edge.
@@ -188,6 +192,9 @@ int skb_path_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_
                   int32_t* flag, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     if (n_starts <= 0) return 0;
+#ifdef SKB_HAVE_FUSED_LOOPS
+    return skb_rank_run(buf0, buf1, (SkbAux*)aux0, (SkbAux*)aux1, n_starts, (int32_t)lo, (int32_t)hi, flag, s);
+#else
     skb_i4* b[2] = {buf0, buf1};
     SkbAux* a[2] = {(SkbAux*)aux0, (SkbAux*)aux1};
     int cur = 0, rounds = 0;
@@ -208,6 +215,7 @@ int skb_path_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_
         }
     }
     return 2 * rounds + cur;
+#endif
 }
 
 // heads of emitted paths among the starts: sel u32[S+1] = exclusive scan of the head flags
@@ -363,6 +371,9 @@ int skb_slab_table_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int6
     if (n_table <= 0) return 0;
     if (table_desc[0] > SKB_MAX_RANKS) return skb_fail("too many ranks");
     SkbSlabTable t = skb_make_table(table_desc);
+#ifdef SKB_HAVE_FUSED_LOOPS
+    return skb_table_rank_run(buf0, buf1, (SkbAux*)aux0, (SkbAux*)aux1, n_table, t, flag, s);
+#else
     skb_i4* b[2] = {buf0, buf1};
     SkbAux* a[2] = {(SkbAux*)aux0, (SkbAux*)aux1};
     int cur = 0, rounds = 0;
@@ -379,6 +390,7 @@ int skb_slab_table_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int6
         }
     }
     return 2 * rounds + cur;
+#endif
 }
 
 // finish the lists of this rank that left the slab with the ranked table
@@ -451,8 +463,5 @@ int skb_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, vo
     return skb_scan_u32_impl(in, out, n, scratch, (skb_stream_t)stream);
 }
 
-int skb_scan_u64(const uint64_t* in, uint64_t* out, int64_t n, void* scratch, void* stream) {
-    return skb_scan_u64_impl(in, out, n, scratch, (skb_stream_t)stream);
-}
 
 }  // extern "C"

@@ -82,8 +82,8 @@ static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s) {
 }
 
 // ------------------------------------------------------------------------------- scans
-// Exclusive scan with n+1 outputs (out[n] = total), reduce -> top -> apply.  `in == out` is
-// allowed: every block holds its whole tile in registers before it writes.
+// Exclusive scan with n+1 outputs (out[n] = total).  `in == out` is allowed: every block holds
+// its whole tile in registers before it writes.
 #define SKB_SCAN_THREADS 256
 #define SKB_SCAN_ITEMS 8
 #define SKB_SCAN_TILE (SKB_SCAN_THREADS * SKB_SCAN_ITEMS)
@@ -117,76 +117,90 @@ __device__ __forceinline__ T skb_block_exclusive(T v, T* total) {
     return base + inc - v;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_reduce_kernel(const T* __restrict__ in, int64_t n,
-                                                                           T* __restrict__ block_sums) {
-    int64_t base = (int64_t)blockIdx.x * SKB_SCAN_TILE + (int64_t)threadIdx.x * SKB_SCAN_ITEMS;
-    T acc = 0;
-#pragma unroll
-    for (int j = 0; j < SKB_SCAN_ITEMS; ++j)
-        if (base + j < n) acc += in[base + j];
-    T total;
-    skb_block_exclusive<T>(acc, &total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
+// Single-pass u32 scan (decoupled look-back): every value is read once and written once.
+// scratch (zeroed once by the caller, reused by later scans on the same stream): word 0 = dynamic
+// tile counter (self-resetting), word 1 = unused, then one 64-bit status per tile =
+// (epoch << 34) | (state << 32) | value; the epoch makes stale statuses of earlier scans invalid.
+#define SKB_ST_AGGREGATE 1ull
+#define SKB_ST_INCLUSIVE 2ull
+static unsigned int g_skb_scan_epoch = 0;
 
-template <typename T>
-__global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_top_kernel(T* block_sums, int64_t nb) {
-    // single block: exclusive scan of the block sums in place, total at block_sums[nb]
-    T carry = 0;
-    for (int64_t c = 0; c < nb; c += SKB_SCAN_THREADS) {
-        int64_t i = c + threadIdx.x;
-        T v = i < nb ? block_sums[i] : (T)0;
-        T total;
-        T ex = skb_block_exclusive<T>(v, &total);
-        if (i < nb) block_sums[i] = carry + ex;
-        carry += total;
+__global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(const uint32_t* in, int64_t n,
+                                                                             uint32_t* out,
+                                                                             unsigned long long* scratch,
+                                                                             unsigned long long epoch, int64_t nb) {
+    __shared__ int64_t s_tile;
+    __shared__ uint32_t s_excl;
+    unsigned int* counter = (unsigned int*)scratch;
+    unsigned long long* status = scratch + 1;
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        if (t == (unsigned int)(nb - 1)) *counter = 0u;  // every tile has been handed out: reset for the next scan
+        s_tile = t;
     }
-    if (threadIdx.x == 0) block_sums[nb] = carry;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_apply_kernel(const T* in, int64_t n, T* out,
-                                                                          const T* __restrict__ block_sums,
-                                                                          int64_t nb) {
-    int64_t base = (int64_t)blockIdx.x * SKB_SCAN_TILE + (int64_t)threadIdx.x * SKB_SCAN_ITEMS;
-    T v[SKB_SCAN_ITEMS];
-    T acc = 0;
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t base = tile * SKB_SCAN_TILE + (int64_t)threadIdx.x * SKB_SCAN_ITEMS;
+    uint32_t v[SKB_SCAN_ITEMS];
+    uint32_t acc = 0;
 #pragma unroll
     for (int j = 0; j < SKB_SCAN_ITEMS; ++j) {
-        v[j] = (base + j < n) ? in[base + j] : (T)0;
+        v[j] = (base + j < n) ? in[base + j] : 0u;
         acc += v[j];
     }
-    T total;
-    T ex = skb_block_exclusive<T>(acc, &total) + block_sums[blockIdx.x];
+    uint32_t total;
+    uint32_t ex = skb_block_exclusive<uint32_t>(acc, &total);
+    const unsigned long long tag = epoch << 34;
+    if (threadIdx.x == 0) {
+        unsigned long long st = tag | ((tile == 0 ? SKB_ST_INCLUSIVE : SKB_ST_AGGREGATE) << 32) | total;
+        __stcg(status + tile, st);
+        if (tile == 0) s_excl = 0;
+    }
+    if (tile > 0 && threadIdx.x < 32) {
+        // warp 0 looks back over the 32 nearest predecessors at a time
+        const int lane = threadIdx.x;
+        uint32_t excl = 0;
+        int64_t look = tile - 1;
+        for (;;) {
+            int64_t idx = look - lane;
+            unsigned long long st;
+            do {
+                st = idx >= 0 ? __ldcg(status + idx) : (tag | (SKB_ST_INCLUSIVE << 32));
+            } while (__any_sync(0xffffffffu, (st >> 34) != epoch || ((st >> 32) & 3ull) == 0ull));
+            unsigned incl = __ballot_sync(0xffffffffu, ((st >> 32) & 3ull) == SKB_ST_INCLUSIVE);
+            int stop = incl ? (__ffs((int)incl) - 1) : 31;
+            uint32_t val = lane <= stop ? (uint32_t)(st & 0xffffffffull) : 0u;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+            excl += val;
+            if (incl) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            __stcg(status + tile, tag | (SKB_ST_INCLUSIVE << 32) | (unsigned long long)(excl + total));
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    ex += s_excl;
 #pragma unroll
     for (int j = 0; j < SKB_SCAN_ITEMS; ++j) {
         if (base + j < n) out[base + j] = ex;
         ex += v[j];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nb];
-}
-
-template <typename T>
-static int skb_scan_impl(const T* in, T* out, int64_t n, void* scratch, skb_stream_t s) {
-    if (n < 0) return skb_fail("scan: negative length");
-    if (n == 0) return skb_cuda_check(cudaMemsetAsync(out, 0, sizeof(T), s), "scan memset");
-    int64_t nb = (n + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
-    T* sums = (T*)scratch;
-    skb_scan_reduce_kernel<T><<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, sums);
-    skb_scan_top_kernel<T><<<1, SKB_SCAN_THREADS, 0, s>>>(sums, nb);
-    skb_scan_apply_kernel<T><<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, out, sums, nb);
-    SKB_COUNT_LAUNCH(3);
-    return skb_cuda_check(cudaGetLastError(), "scan launch");
+    if (tile == nb - 1 && threadIdx.x == SKB_SCAN_THREADS - 1) out[n] = ex;
 }
 
 static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, skb_stream_t s) {
-    return skb_scan_impl<uint32_t>(in, out, n, scratch, s);
+    if (n < 0) return skb_fail("scan: negative length");
+    if (n == 0) return skb_cuda_check(cudaMemsetAsync(out, 0, sizeof(uint32_t), s), "scan memset");
+    int64_t nb = (n + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
+    unsigned long long epoch = (unsigned long long)(__atomic_add_fetch(&g_skb_scan_epoch, 1u, __ATOMIC_RELAXED) & 0x3fffffffu);
+    if (epoch == 0) epoch = (unsigned long long)(__atomic_add_fetch(&g_skb_scan_epoch, 1u, __ATOMIC_RELAXED) & 0x3fffffffu);
+    skb_scan_lookback_kernel<<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, out, (unsigned long long*)scratch, epoch, nb);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "scan launch");
 }
-static int skb_scan_u64_impl(const uint64_t* in, uint64_t* out, int64_t n, void* scratch, skb_stream_t s) {
-    return skb_scan_impl<unsigned long long>((const unsigned long long*)in, (unsigned long long*)out, n, scratch, s);
-}
-
 // ------------------------------------------------------------------------------- mask sweep
 // The only V-proportional pass (replaces image.astype(bool), np.pad and both np.flatnonzero
 // scans, csr.py:1070,122-123,131): read the image once, write 1 bit per voxel and one count
@@ -576,6 +590,133 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------- fused round loops
+// The junction MST and the two list rankings are loops of small kernels whose trip count depends on
+// the data; launched one kernel per phase they cost a host synchronisation per round.  Here each
+// loop is ONE cooperative launch (grid = what is co-resident) with grid-wide barriers between the
+// phases and the convergence test done on the device.  The phase bodies are the same functors.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define SKB_HAVE_FUSED_LOOPS 1
+#define SKB_COOP_THREADS 256
+
+#define SKB_GRID_FOR(i, n) \
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+__global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_coop_kernel(
+    const int32_t* ea, const int32_t* eb, const uint64_t* ew, int64_t nej, int32_t* par, uint64_t* bestw,
+    uint32_t* beste, int32_t* era, int32_t* erb, uint8_t* tree, int32_t* flags /* [3]: two flags + rounds */) {
+    cg::grid_group grid = cg::this_grid();
+    const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+    SkbMstInitItem init{ea, eb, par, bestw, beste};
+    SKB_GRID_FOR(e, nej) {
+        init(e);
+        era[e] = 0;
+        tree[e] = 0;
+    }
+    if (first) flags[0] = flags[1] = 0;
+    grid.sync();
+    int round = 0;
+    for (; round < 64; ++round) {
+        int32_t* f = flags + (round & 1);
+        SkbMstMinWItem p1{ea, eb, ew, par, era, erb, bestw, f};
+        SKB_GRID_FOR(e, nej) p1(e);
+        grid.sync();
+        if (*(volatile int32_t*)f == 0) break;  // same value for every thread of the grid
+        SkbMstMinEItem p2{ew, era, erb, bestw, beste};
+        SKB_GRID_FOR(e, nej) p2(e);
+        grid.sync();
+        SkbMstHookItem p3{era, erb, beste, par, tree};
+        SKB_GRID_FOR(e, nej) p3(e);
+        grid.sync();
+        SkbMstResetItem p4{era, erb, bestw, beste};
+        SKB_GRID_FOR(e, nej) p4(e);
+        if (first) flags[(round + 1) & 1] = 0;
+        grid.sync();
+    }
+    if (first) flags[2] = round;
+}
+
+template <typename Jump>
+__device__ __forceinline__ void skb_rank_rounds(cg::grid_group& grid, Jump jump, skb_i4* b0, skb_i4* b1, SkbAux* a0,
+                                                SkbAux* a1, int64_t n, int32_t* flags) {
+    const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+    if (first) flags[0] = flags[1] = 0;
+    grid.sync();
+    int cur = 0, round = 0;
+    for (; round < 64; ++round) {
+        int32_t* f = flags + (round & 1);
+        jump.src = cur ? b1 : b0;
+        jump.dst = cur ? b0 : b1;
+        jump.aux_src = cur ? a1 : a0;
+        jump.aux_dst = cur ? a0 : a1;
+        jump.flag = f;
+        SKB_GRID_FOR(s, n) jump(s);
+        if (first) flags[(round + 1) & 1] = 0;
+        grid.sync();
+        cur ^= 1;
+        if (*(volatile int32_t*)f == 0) break;  // a round without progress: everything that can end has ended
+    }
+    if (cur == 1) {  // leave the result in buffer 0
+        SKB_GRID_FOR(s, n) {
+            skb_st_i4(b0 + s, skb_ld_i4(b1 + s));
+            if (a0) a0[s] = a1[s];
+        }
+    }
+    if (first) flags[2] = round + 1;
+}
+
+__global__ void __launch_bounds__(SKB_COOP_THREADS) skb_rank_coop_kernel(skb_i4* b0, skb_i4* b1, SkbAux* a0,
+                                                                         SkbAux* a1, int64_t n, int32_t lo,
+                                                                         int32_t hi, int32_t* flags) {
+    cg::grid_group grid = cg::this_grid();
+    SkbJumpItem jump{b0, b1, a0, a1, lo, hi, flags};
+    skb_rank_rounds(grid, jump, b0, b1, a0, a1, n, flags);
+}
+
+__global__ void __launch_bounds__(SKB_COOP_THREADS) skb_table_rank_coop_kernel(skb_i4* b0, skb_i4* b1, SkbAux* a0,
+                                                                               SkbAux* a1, int64_t n,
+                                                                               SkbSlabTable t, int32_t* flags) {
+    cg::grid_group grid = cg::this_grid();
+    SkbTableJumpItem jump{b0, b1, a0, a1, t, flags};
+    skb_rank_rounds(grid, jump, b0, b1, a0, a1, n, flags);
+}
+
+template <typename K>
+static int skb_coop_launch(K kernel, int64_t n_items, void** args, skb_stream_t s) {
+    int per_sm = 0;
+    SKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SKB_COOP_THREADS, 0));
+    if (per_sm < 1) return skb_fail("cooperative kernel does not fit");
+    int64_t cap = (int64_t)per_sm * skb_sm_count();
+    int64_t blocks = (n_items + SKB_COOP_THREADS - 1) / SKB_COOP_THREADS;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    SKB_CUDA(cudaLaunchCooperativeKernel((void*)kernel, dim3((unsigned)blocks), dim3(SKB_COOP_THREADS), args, 0, s));
+    SKB_COUNT_LAUNCH(1);
+    return 0;
+}
+
+// flag must hold 3 ints.  All three return 0: no host round trip, the result is in buffer 0 and
+// the round count in flag[2].
+static int skb_mst_run(const int32_t* ea, const int32_t* eb, const uint64_t* ew, int64_t nej, int32_t* par,
+                       uint64_t* bestw, uint32_t* beste, int32_t* era, int32_t* erb, uint8_t* tree, int32_t* flag,
+                       skb_stream_t s) {
+    void* args[] = {&ea, &eb, &ew, &nej, &par, &bestw, &beste, &era, &erb, &tree, &flag};
+    return skb_coop_launch(skb_mst_coop_kernel, nej, args, s);
+}
+
+static int skb_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, int32_t lo, int32_t hi,
+                        int32_t* flag, skb_stream_t s) {
+    void* args[] = {&b0, &b1, &a0, &a1, &n, &lo, &hi, &flag};
+    return skb_coop_launch(skb_rank_coop_kernel, n, args, s);
+}
+
+static int skb_table_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, SkbSlabTable t,
+                              int32_t* flag, skb_stream_t s) {
+    void* args[] = {&b0, &b1, &a0, &a1, &n, &t, &flag};
+    return skb_coop_launch(skb_table_rank_coop_kernel, n, args, s);
 }
 
 #include "skb_api.inl"

@@ -183,7 +183,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     buf = [ctx.empty((max(S, 1), 4), torch.int32), ctx.empty((max(S, 1), 4), torch.int32)]
     aux = [ctx.empty((max(S, 1), AUX_BYTES), torch.uint8), ctx.empty((max(S, 1), AUX_BYTES), torch.uint8)]
     stamp = torch.full((max(Ne, 1),), -1, dtype=torch.int32, device=ctx.device)
-    flag = ctx.empty(1, torch.int32)
+    flag = ctx.empty(4, torch.int32)
     ctx.call('skb_path_walk', indptr, indices, gdata, values, lin, rec, startoff, slab.data_ptr(), Ne, S, su, se,
              buf[0], aux[0], stamp)
     r = ctx.call('skb_path_rank', buf[0], buf[1], aux[0], aux[1], S, start_lo, start_hi, flag)

@@ -55,9 +55,6 @@ static int skb_scan_host(const T* in, T* out, int64_t n) {
 static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*, skb_stream_t) {
     return skb_scan_host<uint32_t>(in, out, n);
 }
-static int skb_scan_u64_impl(const uint64_t* in, uint64_t* out, int64_t n, void*, skb_stream_t) {
-    return skb_scan_host<uint64_t>(in, out, n);
-}
 
 #define SKB_TILE_VOX 16384
 #define SKB_TILE_WORDS 256
