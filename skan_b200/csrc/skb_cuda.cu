@@ -641,20 +641,22 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_coop_kernel(
 
 template <typename Jump>
 __device__ __forceinline__ void skb_rank_rounds(cg::grid_group& grid, Jump jump, skb_i4* b0, skb_i4* b1, SkbAux* a0,
-                                                SkbAux* a1, int64_t n, int32_t* flags) {
+                                                SkbAux* a1, int64_t n, int32_t* flags /* [4]: 3 flags + rounds */) {
     const bool first = blockIdx.x == 0 && threadIdx.x == 0;
-    if (first) flags[0] = flags[1] = 0;
+    if (first) flags[0] = flags[1] = flags[2] = 0;
     grid.sync();
     int cur = 0, round = 0;
     for (; round < 64; ++round) {
-        int32_t* f = flags + (round & 1);
+        // three rotating flags: the one cleared during round r was last READ after the barrier of
+        // round r-2, and every thread has passed that read before it can arrive at the barrier of r-1
+        int32_t* f = flags + (round % 3);
         jump.src = cur ? b1 : b0;
         jump.dst = cur ? b0 : b1;
         jump.aux_src = cur ? a1 : a0;
         jump.aux_dst = cur ? a0 : a1;
         jump.flag = f;
         SKB_GRID_FOR(s, n) jump(s);
-        if (first) flags[(round + 1) & 1] = 0;
+        if (first) flags[(round + 1) % 3] = 0;
         grid.sync();
         cur ^= 1;
         if (*(volatile int32_t*)f == 0) break;  // a round without progress: everything that can end has ended
@@ -665,7 +667,7 @@ __device__ __forceinline__ void skb_rank_rounds(cg::grid_group& grid, Jump jump,
             if (a0) a0[s] = a1[s];
         }
     }
-    if (first) flags[2] = round + 1;
+    if (first) flags[3] = round + 1;
 }
 
 __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_rank_coop_kernel(skb_i4* b0, skb_i4* b1, SkbAux* a0,
@@ -698,8 +700,8 @@ static int skb_coop_launch(K kernel, int64_t n_items, void** args, skb_stream_t 
     return 0;
 }
 
-// flag must hold 3 ints.  All three return 0: no host round trip, the result is in buffer 0 and
-// the round count in flag[2].
+// flag must hold 4 ints.  All three return 0: no host round trip, the result is in buffer 0 and
+// the round count in flag[3] (flag[2] for the MST).
 static int skb_mst_run(const int32_t* ea, const int32_t* eb, const uint64_t* ew, int64_t nej, int32_t* par,
                        uint64_t* bestw, uint32_t* beste, int32_t* era, int32_t* erb, uint8_t* tree, int32_t* flag,
                        skb_stream_t s) {
