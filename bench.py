@@ -154,6 +154,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--halo', type=int, default=2, help='halo planes of the Z-slab decomposition (N > 1)')
+    ap.add_argument('--timeline', action='store_true', help='N > 1: print the host timeline of one step to stderr')
     ap.add_argument('--stages', action='store_true', help='also print a per-entry-point timing table to stderr')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -283,6 +284,22 @@ def main():
                 'algorithmic_bytes_per_launch': V_local * esize,
                 'job': {'algorithmic_bytes': alg, 'achieved': alg / (ms * 1e-3) / 1e9,
                         'frac_of_n_gpus': alg / (ms * 1e-3) / 1e9 / (peak * world)}}
+
+    if args.timeline and world > 1:
+        sync_all()
+        slab.TIMELINE = []
+        t0 = time.perf_counter()
+        r = step()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        tl, slab.TIMELINE = slab.TIMELINE, None
+        if rank == 0:
+            prev = t0
+            for label, t in tl:
+                print(f'  [timeline] {label:24s} +{(t - prev) * 1e3:7.3f} ms', file=sys.stderr)
+                prev = t
+            print(f'  [timeline] {"final sync":24s} +{(t1 - prev) * 1e3:7.3f} ms   total {(t1 - t0) * 1e3:.3f} ms', file=sys.stderr)
+        del r
 
     # ---- optional per-entry-point table (one extra step, not part of any reported number) -----
     if args.stages:

@@ -130,7 +130,8 @@ def _as_device_image(image, device):
     return t, code, shape, np_dtype
 
 
-def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant=None, z_origin=0):
+def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant=None, z_origin=0,
+                rank_positions=None):
     """Voxel and node stages of skeleton_to_csgraph (csr.py:1070,122-144,1088): mask sweep, nodes in
     raster order (ids, raveled indices, coordinates, values) and raw 3^d neighbourhood masks."""
     ctx = _Ctx(device)
@@ -160,7 +161,14 @@ def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant
         bits.zero_()
         tile_prefix.zero_()
     ctx.call('skb_scan_u32', tile_prefix, tile_prefix, ntiles, ctx.scratch(ntiles))
-    N = int(tile_prefix[ntiles].item())
+    g.position_ranks = None
+    if rank_positions is not None and all(p % tile == 0 and p // tile <= ntiles for p in rank_positions):
+        # ranks at tile-aligned voxel positions (Z-slab plane boundaries) come with the same read-back as N
+        idx = torch.tensor([ntiles] + [p // tile for p in rank_positions], dtype=torch.int64, device=ctx.device)
+        vals = tile_prefix.index_select(0, idx).tolist()
+        N, g.position_ranks = vals[0], vals[1:]
+    else:
+        N = int(tile_prefix[ntiles].item())
     g.n_nodes = N
     g.bits = bits
     g._bits_store = store

@@ -82,7 +82,7 @@ int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, 
     return skb_mst_run(ea, eb, ew, nej, par, bestw, beste, era, erb, tree, flag, s);
 #else
     SKB_TRY(skb_foreach(nej, s, SkbMstInitItem{ea, eb, par, bestw, beste}));
-    SKB_TRY(skb_fill_bytes(era, 0, (size_t)nej * 4, s));
+    SKB_TRY(skb_foreach(nej, s, SkbMstDeadItem{ea, era}));
     SKB_TRY(skb_fill_bytes(tree, 0, (size_t)nej, s));
     int rounds = 0;
     for (;; ++rounds) {

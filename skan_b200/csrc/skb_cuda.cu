@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_coop_kernel(
     SkbMstInitItem init{ea, eb, par, bestw, beste};
     SKB_GRID_FOR(e, nej) {
         init(e);
-        era[e] = 0;
+        era[e] = ea[e] < 0 ? -2 : 0;  // padding rows of a gathered edge list are dead from the start
         tree[e] = 0;
     }
     if (first) flags[0] = flags[1] = 0;

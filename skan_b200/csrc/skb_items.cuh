@@ -298,6 +298,7 @@ struct SkbMstInitItem {  // over junction edges: only the entries of edge endpoi
     uint32_t* beste;
     SKB_HD void operator()(int64_t e) const {
         int32_t a = ea[e], b = eb[e];
+        if (a < 0) return;  // padding row of a gathered edge list (the caller marks it dead)
         par[a] = a;
         par[b] = b;
         bestw[a] = ~0ull;
@@ -305,6 +306,12 @@ struct SkbMstInitItem {  // over junction edges: only the entries of edge endpoi
         beste[a] = ~0u;
         beste[b] = ~0u;
     }
+};
+
+struct SkbMstDeadItem {  // over junction edges: padding rows (a < 0) never take part
+    const int32_t* ea;
+    int32_t* era;
+    SKB_HD void operator()(int64_t e) const { era[e] = ea[e] < 0 ? -2 : 0; }
 };
 
 struct SkbMstMinWItem {  // over junction edges: phase 1, lightest weight leaving each component
@@ -394,7 +401,7 @@ struct SkbMstApplyItem {  // drop non-tree junction-junction edges in both direc
     int32_t n_local;   // endpoints that are not nodes of this slab are skipped
     uint32_t* keep;
     SKB_HD void operator()(int64_t e) const {
-        if (tree[e]) return;
+        if (tree[e] || ea[e] < 0) return;
         int k = ek[e];
         int32_t a = ea[e] - id_shift, b = eb[e] - id_shift;
         if (a >= 0 && a < n_local) skb_atomic_and_u32(keep + a, ~(1u << k));

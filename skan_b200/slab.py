@@ -36,6 +36,7 @@ data crosses NVLink (the halo planes are part of the input partition).
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -46,6 +47,16 @@ from . import _pipeline
 
 AUX_BYTES = 48
 
+# optional host timeline (bench.py --timeline): list of (label, perf_counter) appended at the points
+# where the host has just waited for the device or for a collective
+TIMELINE = None
+
+
+def _mark(label):
+    if TIMELINE is not None:
+        import time
+        TIMELINE.append((label, time.perf_counter()))
+
 
 def slab_bounds(nz, world, rank, halo):
     """Owned planes [z0, z1) and extended planes [ze0, ze1) of `rank` for a volume of nz planes."""
@@ -55,8 +66,80 @@ def slab_bounds(nz, world, rank, halo):
     return z0, z1, max(0, z0 - halo), min(nz, z1 + halo)
 
 
+class _CountChannel:
+    """All-gather of a few host integers between the ranks of ONE node through POSIX shared memory.
+
+    The sizes that drive the next allocation are already on the host when they have to be
+    exchanged; sending them through NCCL costs a host->device copy, a collective launch and a
+    device->host synchronisation (~100-150 us) for a few bytes.  A sequence-numbered, double
+    buffered shared-memory table does it in a few microseconds.  Used only when every rank of the
+    group runs on this node; otherwise _allgather_ints falls back to the process group."""
+    MAXV = 15
+
+    def __init__(self, group):
+        from multiprocessing import shared_memory
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        nbytes = 2 * self.world * (1 + self.MAXV) * 8
+        name = [None]
+        if self.rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            self.shm.buf[:nbytes] = bytes(nbytes)
+            name[0] = self.shm.name
+        dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:  # only the creating rank owns the segment (python < 3.13 registers attachers too)
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, 'shared_memory')
+            except Exception:
+                pass
+        self.arr = np.ndarray((2, self.world, 1 + self.MAXV), dtype=np.int64, buffer=self.shm.buf)
+        self.seq = 0
+        dist.barrier(group=group)
+        import atexit
+        atexit.register(self.close)
+
+    def close(self):
+        try:
+            self.arr = None
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+    def allgather(self, vals):
+        self.seq += 1
+        b = self.seq & 1
+        row = self.arr[b, self.rank]
+        row[1:1 + len(vals)] = vals
+        row[0] = self.seq           # published after the values (x86 keeps store order)
+        flags = self.arr[b, :, 0]
+        spins = 0
+        while not (flags == self.seq).all():
+            spins += 1
+            if spins > 50_000_000:
+                raise RuntimeError('count exchange timed out: a rank of the slab decomposition died')
+        return self.arr[b, :, 1:1 + len(vals)].copy()
+
+
+_channels = {}
+
+
+def _single_node(group):
+    lw = os.environ.get('LOCAL_WORLD_SIZE')
+    return lw is None or int(lw) == dist.get_world_size(group)
+
+
 def _allgather_ints(vals, device, group):
-    t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=device)
+    vals = [int(v) for v in vals]
+    if os.environ.get('SKAN_B200_COUNT_CHANNEL', 'shm') == 'shm' and _single_node(group) and len(vals) <= _CountChannel.MAXV:
+        key = id(group) if group is not None else 0
+        if key not in _channels:
+            _channels[key] = _CountChannel(group)
+        return _channels[key].allgather(vals)
+    t = torch.tensor(vals, dtype=torch.int64, device=device)
     world = dist.get_world_size(group)
     out = torch.empty((world, t.numel()), dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(out.view(-1), t, group=group)
@@ -101,10 +184,15 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
         from .csr import _default_device
         device = _default_device()
     # ---- voxel and node stages on the extended slab ---------------------------------------------
-    g = _pipeline.graph_nodes(slab_image, spacing=spacing, device=device, pack_variant=pack_variant, z_origin=ze0)
+    Vloc = (ze1 - ze0) * sz
+    p_own0, p_own1 = (z0 - ze0) * sz, (z1 - ze0) * sz
+    positions = [p_own0, p_own1, p_own0 + sz, p_own1 - sz,
+                 p_own0 - sz if has_lo else p_own0, p_own1 + sz if has_hi else p_own1]
+    g = _pipeline.graph_nodes(slab_image, spacing=spacing, device=device, pack_variant=pack_variant, z_origin=ze0,
+                              rank_positions=positions)
     ctx = g.ctx
     Ne = g.n_nodes
-    Vloc = (ze1 - ze0) * sz
+    _mark('graph_nodes')
 
     def ranks_at(positions):
         pos = [min(int(p), Vloc) for p in positions]
@@ -117,31 +205,31 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
             out = dict(zip(inside, ot.tolist()))
         return [Ne if p >= Vloc else (out[p] if Ne else 0) for p in pos]
 
-    p_own0, p_own1 = (z0 - ze0) * sz, (z1 - ze0) * sz
-    own0, own1, f1, l0, hl0, hu1 = ranks_at([
-        p_own0, p_own1, p_own0 + sz, p_own1 - sz,
-        p_own0 - sz if has_lo else p_own0, p_own1 + sz if has_hi else p_own1])
+    own0, own1, f1, l0, hl0, hu1 = g.position_ranks if g.position_ranks is not None else ranks_at(positions)
     N_k = own1 - own0
+    _mark('rank_queries')
     # ---- junction MST on the junction edges of the whole volume -------------------------------------
     # every rank emits the edges whose smaller endpoint it owns (global ids), all ranks gather them
     # in rank order (= global (a, b) order, the MST's tie-break) and solve the same problem
     ea, eb, ek, ew = _pipeline.junction_edges(g, own0, own1)
     nej_k = int(ea.numel())
+    _mark('junction_edges')
     counts0 = _allgather_ints([N_k, nej_k], ctx.device, group)                     # collective 1
     Noff = np.concatenate([[0], np.cumsum(counts0[:, 0])])
     N_total = int(Noff[-1])
     if N_total >= 2**31:
         raise ValueError("more than 2^31 nodes: node ids no longer fit the reference's int32 index arrays")
     id_shift = int(Noff[rank]) - own0
+    _mark('allgather_counts0')
     if world > 1:
         max_e = int(counts0[:, 1].max())
         if max_e:
             packed = torch.stack([(ea.long() + id_shift) | ((eb.long() + id_shift) << 32), ew, ek.long()], dim=1) \
                 if nej_k else torch.zeros((1, 3), dtype=torch.int64, device=ctx.device)
-            allp = _allgather_padded(packed, nej_k, max_e, group)                  # collective 2
-            rows = torch.cat([torch.arange(int(counts0[k, 1]), device=ctx.device) + k * max_e for k in range(world)])
-            allp = allp.view(-1, 3).index_select(0, rows)
-            gea = (allp[:, 0] & 0xffffffff).int()
+            allp = _allgather_padded(packed, nej_k, max_e, group).view(-1, 3)    # collective 2
+            # padding rows are -1: a = b = -1, skipped by the MST kernels; the row order is the
+            # global (a, b) order the tie-break needs
+            gea = allp[:, 0].int()
             geb = (allp[:, 0] >> 32).int()
             gew = allp[:, 1].contiguous()
             gek = allp[:, 2].to(torch.uint8)
@@ -149,8 +237,10 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
             gea, geb, gek, gew = ea, eb, ek, ew
     else:
         gea, geb, gek, gew = ea + id_shift, eb + id_shift, ek, ew
+    _mark('allgather_edges')
     tree, mst_rounds = _pipeline.junction_mst(ctx, gea, geb, gew, N_total)
     _pipeline.graph_csr(g, gea, geb, gek, tree, id_shift)
+    _mark('mst_csr')
     indptr, indices, gdata, values, lin = g.indptr, g.indices, g.data, g.values, g.lin
     # ---- records and start numbering -------------------------------------------------------------
     slab = torch.zeros(13, dtype=torch.int64)
@@ -165,16 +255,18 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     ctx.call('skb_path_records', indptr, indices, lin, slab.data_ptr(), Ne, rec, n_chain_t, startoff, None, None,
              is_min, ctx.scratch(Ne))
     sel_idx = torch.tensor([own0, own1, f1, l0], dtype=torch.int64, device=ctx.device)
-    so = startoff.index_select(0, sel_idx).tolist()
-    ei = indptr.index_select(0, sel_idx[:2]).tolist()
+    rb = torch.cat([startoff.index_select(0, sel_idx), indptr.index_select(0, sel_idx[:2]),
+                    n_chain_t.sum(dtype=torch.int32).view(1)]).tolist()
+    so, ei, n_chain = rb[:4], rb[4:6], rb[6]
     S_k, SF, SL0 = so[1] - so[0], so[2] - so[0], so[3] - so[0]
     E_k = ei[1] - ei[0]
-    n_chain = int(n_chain_t.sum().item())
+    _mark('records')
     counts = _allgather_ints([N_k, E_k, S_k, SF, SL0], ctx.device, group)        # collective 3
     Eoff = np.concatenate([[0], np.cumsum(counts[:, 1])])
     Soff = np.concatenate([[0], np.cumsum(counts[:, 2])])
     S_total = int(Soff[-1])
     start_lo, start_hi = int(Soff[rank]), int(Soff[rank + 1])
+    _mark('allgather_counts1')
     slab[8], slab[9], slab[10], slab[11] = id_shift, start_lo - so[0], start_lo, start_hi
     # ---- phase 0: lists between terminals, first inside the slab ---------------------------------
     S = S_k
@@ -189,6 +281,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     r = ctx.call('skb_path_rank', buf[0], buf[1], aux[0], aux[1], S, start_lo, start_hi, flag)
     ranked, raux = buf[r & 1], aux[r & 1]
     rank_rounds = r >> 1
+    _mark('walk_rank(launch)')
     # ---- inter-slab table --------------------------------------------------------------------------
     nblk = counts[:, 3] + (counts[:, 2] - counts[:, 4])
     max_blk = int(nblk.max())
@@ -199,29 +292,26 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
         blk = ctx.empty((max(my_blk, 1), 4), torch.int32)
         blk_aux = ctx.empty((max(my_blk, 1), AUX_BYTES), torch.uint8)
         ctx.call('skb_slab_export', ranked, raux, SF, SL0, my_blk, start_lo, start_hi, blk, blk_aux)
-        T = _allgather_padded(blk, my_blk, max_blk, group)                       # collective 4
-        TA = _allgather_padded(blk_aux, my_blk, max_blk, group)
-        t_off = np.concatenate([[0], np.cumsum(nblk)])
-        keep_rows = torch.cat([torch.arange(int(nblk[k]), device=ctx.device) + k * max_blk for k in range(world)])
-        T = T.view(-1, 4).index_select(0, keep_rows).contiguous()
-        TA = TA.view(-1, AUX_BYTES).index_select(0, keep_rows).contiguous()
-        n_table = int(t_off[-1])
+        T = _allgather_padded(blk, my_blk, max_blk, group).view(-1, 4)           # collective 4
+        TA = _allgather_padded(blk_aux, my_blk, max_blk, group).view(-1, AUX_BYTES)
+        n_table = world * max_blk                                                # padded layout: rank k at k * max_blk
         desc = torch.tensor([world] + [int(x) for x in Soff] + [int(x) for x in counts[:, 3]] +
-                            [int(x) for x in counts[:, 4]] + [int(x) for x in t_off[:-1]], dtype=torch.int64)
+                            [int(x) for x in counts[:, 4]] + [k * max_blk for k in range(world)], dtype=torch.int64)
         T2, TA2 = torch.empty_like(T), torch.empty_like(TA)
         r2 = ctx.call('skb_slab_table_rank', T, T2, TA, TA2, n_table, desc.data_ptr(), flag)
         Tf, TAf = (T, TA) if (r2 & 1) == 0 else (T2, TA2)
         table_rounds = r2 >> 1
         ctx.call('skb_slab_apply', ranked, raux, Tf, TAf, S, desc.data_ptr(), start_lo, start_hi)
         cross_cycle = (Tf[:, 0] >= 0).any()
+    _mark('table')
     # ---- covered chain voxels, heads of the regular paths ------------------------------------------
     covered = ctx.empty(max(Ne, 1), torch.uint8)
     n_unc_t = ctx.empty(64, torch.int32)
     ctx.call('skb_slab_covered', rec, startoff, stamp, ranked, Ne, own0, own1, covered, n_unc_t)
     sel = ctx.empty(S + 1, torch.int32)
     ctx.call('skb_path_select', su, rec, ranked, S, 0, start_lo, sel, ctx.scratch(S))
-    P0 = int(sel[S].item())
-    n_uncovered = int(n_unc_t.sum().item())
+    P0, n_uncovered = torch.stack([sel[S], n_unc_t.sum(dtype=torch.int32)]).tolist()
+    _mark('covered_select')
     # ---- phase 1: junction-free cycles inside the slab -----------------------------------------------
     cyc = None
     Pc = 0
@@ -246,6 +336,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
             Pc = int(selb[Sb].item())
             cyc = SimpleNamespace(S=Sb, su=sub, se=seb, ranked=bufb[rb & 1], aux=auxb[rb & 1], sel=selb)
     Pk = P0 + Pc
+    _mark('cycles')
     start_node = ctx.empty(max(Pk, 1), torch.int32)
     plen = ctx.empty(Pk + 1, torch.int32)
     pmin = ctx.empty(max(Pk, 1), torch.int32)
@@ -260,12 +351,14 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
                  plen, pmin, einfo_b, head_end, head_aux)
     pindptr = ctx.empty(Pk + 1, torch.int32)   # local exclusive scan of the entries: regular paths, then cycles
     ctx.call('skb_scan_u32', plen, pindptr, Pk, ctx.scratch(Pk))
-    ends = pindptr.index_select(0, torch.tensor([P0, Pk], dtype=torch.int64, device=ctx.device)).tolist()
-    L0, Lc = ends[0], ends[1] - ends[0]
-    cc = int(cross_cycle.item()) if cross_cycle is not None else 0
+    ends = torch.stack([pindptr[P0], pindptr[Pk],
+                        cross_cycle.int() if cross_cycle is not None else pindptr[0]]).tolist()
+    L0, Lc, cc = ends[0], ends[1] - ends[0], ends[2]
+    _mark('heads')
     counts2 = _allgather_ints([P0, L0, Pc, Lc, cc], ctx.device, group)            # collective 5
     if counts2[:, 4].any():
         raise NotImplementedError('a junction-free cycle crosses a slab boundary')
+    _mark('allgather_counts2')
     P0off = np.concatenate([[0], np.cumsum(counts2[:, 0])])
     L0off = np.concatenate([[0], np.cumsum(counts2[:, 1])])
     Pcoff = np.concatenate([[0], np.cumsum(counts2[:, 2])])
@@ -283,6 +376,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     nrec = world * maxP
     heads_all = _allgather_padded(head, P0, max(maxP, 1), group).view(-1, 4)        # collective 6
     links_all = _allgather_padded(link, P0, max(maxP, 1), group).view(-1, 4)
+    _mark('allgather_heads')
     einfo = ctx.empty((max(S_total, 1), 4), torch.int32)
     ctx.call('skb_slab_einfo', heads_all, nrec, S_total, einfo)
     # ---- path entries: every rank writes the entries of its own voxels at their global positions ----
@@ -303,9 +397,11 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     ctx.call('skb_slab_components', links_all, nrec, S_total, kpar, kmin, node_lo, node_hi, id_shift, is_min, Ne,
              ctx.scratch(Ne))
     cr = is_min.index_select(0, sel_idx[:2]).tolist()
+    _mark('emit_components')
     C_k = cr[1] - cr[0]
     counts3 = _allgather_ints([C_k], ctx.device, group)                             # collective 7
     Coff = np.concatenate([[0], np.cumsum(counts3[:, 0])])
+    _mark('allgather_counts3')
     skel_all = ctx.empty(max(nrec, 1), torch.int32)
     ctx.call('skb_slab_skeleton_ids', links_all, nrec, kpar, kmin, is_min, node_lo, node_hi, id_shift,
              int(Coff[rank]), own0, skel_all)
@@ -317,6 +413,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     if Pc:
         roots_local = (start_node[P0:Pk] - id_shift).long()
         skel[P0:Pk] = int(Coff[rank]) + is_min.index_select(0, roots_local) - cr[0]
+    _mark('skel_allreduce(launch)')
     # ---- statistics and branch table of the paths owned here ------------------------------------------
     dist_, mean_, stdev_ = (ctx.empty(max(Pk, 1), torch.float64) for _ in range(3))
     ctx.call('skb_slab_path_stats', plen, head_aux, Pk, dist_, mean_, stdev_)
@@ -334,6 +431,7 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     if Pk:
         ctx.call('skb_branch_table', Pk, ndim, 0, 1 if sp_is_int else 0, sp_f.data_ptr(), sp_i.data_ptr(), None, None,
                  indptr, skel, g.coords, values, head_aux, start_node, id_shift, gshape.data_ptr(), o32, o64, of)
+    _mark('table_launch')
     return SimpleNamespace(
         rank=rank, world=world, graph=g, own=(own0, own1), id_shift=id_shift,
         n_nodes=N_k, n_edges=E_k, node_offset=int(Noff[rank]), edge_offset=int(Eoff[rank]),
