@@ -188,8 +188,9 @@ int skb_rank_query(const uint64_t* bits, const uint32_t* pre256, const int64_t* 
                    void* stream);
 int skb_slab_covered(const skb_i4* rec, const uint32_t* startoff, const int32_t* stamp, const skb_i4* ranked,
                      int64_t n, int64_t own0, int64_t own1, uint8_t* covered, uint32_t* n_uncovered, void* stream);
+/* n_rows >= n_block rows are written; the extra ones are padding (-1) */
 int skb_slab_export(const skb_i4* ranked, const void* aux, int64_t n_first, int64_t last0, int64_t n_block,
-                    int64_t lo, int64_t hi, skb_i4* out, void* out_aux, void* stream);
+                    int64_t n_rows, int64_t lo, int64_t hi, skb_i4* out, void* out_aux, void* stream);
 /* table_desc (host i64): n_ranks, start_off[n_ranks+1], n_first[n_ranks], last0[n_ranks], t_off[n_ranks] */
 int skb_slab_table_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_table,
                         const int64_t* table_desc /*host*/, int32_t* flag, void* stream);
@@ -198,7 +199,13 @@ int skb_slab_apply(skb_i4* ranked, void* aux, const skb_i4* table, const void* t
 int skb_slab_head_records(const int32_t* head_end, const uint32_t* plen, const int32_t* pindptr,
                           const int32_t* pmin, const int32_t* start_node, const uint32_t* startoff,
                           const void* head_aux, const int64_t* slab /*host*/, int64_t n, int64_t n_paths,
-                          int64_t pid_off, int64_t entry_off, skb_i4* head, skb_i4* link, void* stream);
+                          int64_t n_rows, int64_t pid_off, int64_t entry_off, skb_i4* head, skb_i4* link,
+                          void* stream);
+/* regroup gathered buffers: desc (host i64) = n_seg, then n_seg x (src address, dst address, bytes), 16-byte units */
+int skb_copy_segments(const int64_t* desc /*host*/, void* stream);
+/* gathered junction edges (cap rows per rank, a < 0 = padding): local ids of rank k += shifts[k] */
+int skb_slab_edge_shift(int32_t* ea, int32_t* eb, int64_t n_rows, int64_t cap, const int64_t* shifts /*host*/,
+                        int64_t n_ranks, void* stream);
 int skb_slab_einfo(const skb_i4* head, int64_t n_records, int64_t n_total_starts, skb_i4* einfo, void* stream);
 int skb_slab_components(const skb_i4* link, int64_t n_records, int64_t n_keys, int32_t* par, int32_t* cmin,
                         int64_t node_lo, int64_t node_hi, int64_t id_shift, uint32_t* is_min, int64_t n,

@@ -49,11 +49,13 @@ _SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp]),
     'skb_rank_query': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     'skb_slab_covered': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
-    'skb_slab_export': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    'skb_slab_export': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     'skb_slab_table_rank': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'skb_slab_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp]),
-    'skb_slab_head_records': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp,
-                                     _vp]),
+    'skb_slab_head_records': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp,
+                                     _vp, _vp]),
+    'skb_copy_segments': (_int, [_vp, _vp]),
+    'skb_slab_edge_shift': (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     'skb_slab_einfo': (_int, [_vp, _i64, _i64, _vp, _vp]),
     'skb_slab_components': (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     'skb_slab_skeleton_ids': (_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp]),

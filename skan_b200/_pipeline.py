@@ -199,22 +199,33 @@ def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant
     return g
 
 
-def junction_edges(g, a0=0, a1=None):
-    """Junction-junction edges (csr.py:1004-1016) whose smaller endpoint is a node in [a0, a1):
-    (ea, eb int32, ek uint8, ew int64 weight bits), in (a, k27) order."""
+def junction_edge_counts(g, a0=0, a1=None):
+    """Per-node offsets (scanned, N+1) and the number of junction-junction edges (csr.py:1004-1016)
+    whose smaller endpoint is a node in [a0, a1)."""
     ctx, N = g.ctx, g.n_nodes
     a1 = N if a1 is None else a1
     jcount = ctx.empty(N + 1, torch.int32)
     ctx.call('skb_junction_edge_count', g.bits, g.pre256, *g.geom, g.lin, g.raw_nb, N, a0, a1, jcount)
     ctx.call('skb_scan_u32', jcount, jcount, N, ctx.scratch(N))
-    nej = int(jcount[N].item())
+    return jcount, int(jcount[N].item())
+
+
+def junction_edge_emit(g, jcount, ea, eb, ek, ew):
+    """Write the edges counted by junction_edge_counts, in (a, k27) order: ea, eb int32 node ids,
+    ek uint8 neighbour code, ew int64 weight bits (tensors or raw device addresses)."""
+    g.ctx.call('skb_junction_edge_emit', g.bits, g.pre256, *g.geom, g.lin, g.raw_nb, jcount, g.n_nodes, g.wtab,
+               g.values, g.height, g.dtype_code, ea, eb, ek, ew)
+
+
+def junction_edges(g, a0=0, a1=None):
+    ctx = g.ctx
+    jcount, nej = junction_edge_counts(g, a0, a1)
     ea = ctx.empty(nej, torch.int32)
     eb = ctx.empty(nej, torch.int32)
     ek = ctx.empty(nej, torch.uint8)
     ew = ctx.empty(nej, torch.int64)
     if nej:
-        ctx.call('skb_junction_edge_emit', g.bits, g.pre256, *g.geom, g.lin, g.raw_nb, jcount, N, g.wtab, g.values,
-                 g.height, g.dtype_code, ea, eb, ek, ew)
+        junction_edge_emit(g, jcount, ea, eb, ek, ew)
     return ea, eb, ek, ew
 
 

@@ -358,10 +358,10 @@ static SkbSlabTable skb_make_table(const int64_t* v) {
 
 // this rank's block of the inter-slab table: the ranked starts of its two boundary planes
 int skb_slab_export(const skb_i4* ranked, const void* aux, int64_t n_first, int64_t last0, int64_t n_block,
-                    int64_t lo, int64_t hi, skb_i4* out, void* out_aux, void* stream) {
-    return skb_foreach(n_block, (skb_stream_t)stream,
+                    int64_t n_rows, int64_t lo, int64_t hi, skb_i4* out, void* out_aux, void* stream) {
+    return skb_foreach(n_rows, (skb_stream_t)stream,
                        SkbTableExportItem{ranked, (const SkbAux*)aux, (int32_t)n_first, (int32_t)last0, (int32_t)lo,
-                                          (int32_t)hi, out, (SkbAux*)out_aux});
+                                          (int32_t)hi, (int32_t)n_block, out, (SkbAux*)out_aux});
 }
 
 // pointer jumping over the gathered table (same on every rank); returns 2*rounds + result buffer
@@ -405,12 +405,44 @@ int skb_slab_apply(skb_i4* ranked, void* aux, const skb_i4* table, const void* t
 // head / link records (i4 each) of the paths headed on this rank, for the all-gather
 int skb_slab_head_records(const int32_t* head_end, const uint32_t* plen, const int32_t* pindptr,
                           const int32_t* pmin, const int32_t* start_node, const uint32_t* startoff,
-                          const void* head_aux, const int64_t* slab, int64_t n, int64_t n_paths, int64_t pid_off,
-                          int64_t entry_off, skb_i4* head, skb_i4* link, void* stream) {
-    return skb_foreach(n_paths, (skb_stream_t)stream,
+                          const void* head_aux, const int64_t* slab, int64_t n, int64_t n_paths, int64_t n_rows,
+                          int64_t pid_off, int64_t entry_off, skb_i4* head, skb_i4* link, void* stream) {
+    return skb_foreach(n_rows, (skb_stream_t)stream,
                        SkbHeadRecordItem{head_end, plen, pindptr, pmin, start_node, startoff,
                                          (const SkbAux*)head_aux, skb_make_slab(slab, n), (int32_t)pid_off,
-                                         (int32_t)entry_off, head, link});
+                                         (int32_t)entry_off, (int32_t)n_paths, head, link});
+}
+
+// regroup gathered data: desc (host i64) = n_seg, then n_seg x (src address, dst address, bytes);
+// every address and size a multiple of 16
+int skb_copy_segments(const int64_t* desc, void* stream) {
+    int n = (int)desc[0];
+    if (n < 0 || n > SKB_MAX_SEGMENTS) return skb_fail("too many segments");
+    SkbSegCopyItem it;
+    it.n_seg = n;
+    int64_t total = 0;
+    for (int k = 0; k < n; ++k) {
+        it.src[k] = (const uint8_t*)(uintptr_t)desc[1 + 3 * k];
+        it.dst[k] = (uint8_t*)(uintptr_t)desc[2 + 3 * k];
+        int64_t bytes = desc[3 + 3 * k];
+        if ((desc[1 + 3 * k] | desc[2 + 3 * k] | bytes) & 15) return skb_fail("segments must be 16-byte aligned");
+        it.first[k] = total;
+        total += bytes / 16;
+    }
+    it.first[n] = total;
+    return skb_foreach(total, (skb_stream_t)stream, it);
+}
+
+// gathered junction edges (cap rows per rank, a < 0 = padding): add every rank's id shift
+int skb_slab_edge_shift(int32_t* ea, int32_t* eb, int64_t n_rows, int64_t cap, const int64_t* shifts, int64_t n_ranks,
+                        void* stream) {
+    if (n_ranks > SKB_MAX_RANKS) return skb_fail("too many ranks");
+    SkbEdgeShiftItem it;
+    it.ea = ea;
+    it.eb = eb;
+    it.cap = (int32_t)cap;
+    for (int k = 0; k < SKB_MAX_RANKS; ++k) it.shift[k] = k < n_ranks ? (int32_t)shifts[k] : 0;
+    return skb_foreach(n_rows, (skb_stream_t)stream, it);
 }
 
 // einfo i4[total starts] (cleared here) from all gathered head records (x < 0 = padding)

@@ -785,13 +785,20 @@ struct SkbTableJumpItem {  // over T: pointer jumping on the inter-slab list (ev
     }
 };
 
-struct SkbTableExportItem {  // over the rank's block of T: copy the ranked boundary-plane starts
+struct SkbTableExportItem {  // over the rank's (padded) block of T: copy the ranked boundary-plane starts
     const skb_i4* ranked;
     const SkbAux* aux;
     int32_t n_first, last0, lo, hi;  // hi - lo = starts of this rank; pointers still inside are cycles
+    int32_t n_block;                 // rows beyond the block are padding: finished, never referenced
     skb_i4* out;
     SkbAux* out_aux;
     SKB_HD void operator()(int64_t i) const {
+        if (i >= n_block) {
+            skb_i4 pad;
+            pad.x = pad.y = pad.z = pad.w = -1;
+            skb_st_i4(out + i, pad);
+            return;
+        }
         int64_t s = i < n_first ? i : last0 + (i - n_first);
         skb_i4 a = skb_ld_i4(ranked + s);
         if (a.x >= lo && a.x < hi) a.x = SKB_DEAD;
@@ -1045,6 +1052,35 @@ struct SkbCcPathIdItem {  // over all paths
 };
 
 // ---- Z-slab mode: pieces that only exist when a volume is split over several GPUs -------------
+// copy up to SKB_MAX_SEGMENTS byte ranges (16-byte granules): regroups what an all-gather
+// delivered rank by rank into one array per field
+#define SKB_MAX_SEGMENTS 64
+struct SkbSegCopyItem {  // over 16-byte granules of all segments
+    int32_t n_seg;
+    const uint8_t* src[SKB_MAX_SEGMENTS];
+    uint8_t* dst[SKB_MAX_SEGMENTS];
+    int64_t first[SKB_MAX_SEGMENTS + 1];  // first granule of each segment (exclusive scan of sizes)
+    SKB_HD void operator()(int64_t i) const {
+        int k = 0;
+        while (k + 1 < n_seg && i >= first[k + 1]) ++k;
+        int64_t o = (i - first[k]) * 16;
+        skb_st_i4((skb_i4*)(dst[k] + o), skb_ld_i4((const skb_i4*)(src[k] + o)));
+    }
+};
+
+struct SkbEdgeShiftItem {  // gathered junction edges: local ids of rank k -> global ids
+    int32_t* ea;
+    int32_t* eb;
+    int32_t cap;  // rows per rank
+    int32_t shift[SKB_MAX_RANKS];
+    SKB_HD void operator()(int64_t e) const {
+        if (ea[e] < 0) return;
+        int32_t sh = shift[e / cap];
+        ea[e] += sh;
+        eb[e] += sh;
+    }
+};
+
 struct SkbRankQueryItem {  // out[i] = number of foreground voxels before raveled position pos[i]
     const uint64_t* bits;
     const uint32_t* pre256;
@@ -1096,10 +1132,17 @@ struct SkbHeadRecordItem {
     const SkbAux* head_aux;
     SkbSlab sl;
     int32_t pid_off, entry_off;
+    int32_t n_paths;  // rows beyond are padding (x = -1)
     skb_i4* head;
     skb_i4* link;
     SKB_HD void operator()(int64_t p) const {
         skb_i4 h;
+        if (p >= n_paths) {
+            h.x = h.y = h.z = h.w = -1;
+            skb_st_i4(head + p, h);
+            skb_st_i4(link + p, h);
+            return;
+        }
         h.x = head_end[p];
         h.y = pid_off + (int32_t)p;
         h.z = (int32_t)plen[p] - 1;

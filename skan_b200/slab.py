@@ -157,6 +157,43 @@ def _allgather_padded(t, count, max_count, group):
     return out
 
 
+class _Exchange:
+    """One all-gather of several per-rank arrays of `cap` rows each.  The producing kernels write
+    straight into the send buffer (padding rows included); after the gather one small kernel
+    regroups the rank-major chunks into one contiguous array per field."""
+
+    def __init__(self, ctx, world, cap, row_bytes, dtypes):
+        self.ctx, self.world = ctx, world
+        self.cap = cap = max(16, -(-int(cap) // 16) * 16)     # every field segment is a multiple of 16 bytes
+        self.row_bytes, self.dtypes = row_bytes, dtypes
+        self.offs, o = [], 0
+        for rb in row_bytes:
+            self.offs.append(o)
+            o += cap * rb
+        self.chunk = o
+        self.send = ctx.empty(self.chunk, torch.uint8)
+        self.recv = ctx.empty(world * self.chunk, torch.uint8)
+
+    def field(self, f):
+        """This rank's rows of field f, as a typed view of the send buffer."""
+        rb = self.row_bytes[f]
+        return self.send[self.offs[f]: self.offs[f] + self.cap * rb].view(self.dtypes[f])
+
+    def gather(self, group):
+        dist.all_gather_into_tensor(self.recv, self.send, group=group)
+        outs, desc = [], [self.world * len(self.row_bytes)]
+        base = self.recv.data_ptr()
+        for f, rb in enumerate(self.row_bytes):
+            seg = self.cap * rb
+            out = self.ctx.empty(self.world * seg, torch.uint8)
+            for k in range(self.world):
+                desc += [base + k * self.chunk + self.offs[f], out.data_ptr() + k * seg, seg]
+            outs.append(out.view(self.dtypes[f]))
+        d = torch.tensor(desc, dtype=torch.int64)
+        self.ctx.call('skb_copy_segments', d.data_ptr())
+        return outs
+
+
 def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=1, device=None, group=None,
                               pack_variant=None):
     """Skeleton + summarize of one Z-slab of a 3-D volume, collectively over the process group.
@@ -211,33 +248,28 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     # ---- junction MST on the junction edges of the whole volume -------------------------------------
     # every rank emits the edges whose smaller endpoint it owns (global ids), all ranks gather them
     # in rank order (= global (a, b) order, the MST's tie-break) and solve the same problem
-    ea, eb, ek, ew = _pipeline.junction_edges(g, own0, own1)
-    nej_k = int(ea.numel())
+    jcount, nej_k = _pipeline.junction_edge_counts(g, own0, own1)
     _mark('junction_edges')
-    counts0 = _allgather_ints([N_k, nej_k], ctx.device, group)                     # collective 1
+    counts0 = _allgather_ints([N_k, nej_k, own0], ctx.device, group)               # count exchange 1
     Noff = np.concatenate([[0], np.cumsum(counts0[:, 0])])
     N_total = int(Noff[-1])
     if N_total >= 2**31:
         raise ValueError("more than 2^31 nodes: node ids no longer fit the reference's int32 index arrays")
     id_shift = int(Noff[rank]) - own0
     _mark('allgather_counts0')
-    if world > 1:
-        max_e = int(counts0[:, 1].max())
-        if max_e:
-            packed = torch.stack([(ea.long() + id_shift) | ((eb.long() + id_shift) << 32), ew, ek.long()], dim=1) \
-                if nej_k else torch.zeros((1, 3), dtype=torch.int64, device=ctx.device)
-            allp = _allgather_padded(packed, nej_k, max_e, group).view(-1, 3)    # collective 2
-            # padding rows are -1: a = b = -1, skipped by the MST kernels; the row order is the
-            # global (a, b) order the tie-break needs
-            gea = allp[:, 0].int()
-            geb = (allp[:, 0] >> 32).int()
-            gew = allp[:, 1].contiguous()
-            gek = allp[:, 2].to(torch.uint8)
-        else:
-            gea, geb, gek, gew = ea, eb, ek, ew
+    max_e = int(counts0[:, 1].max())
+    if max_e:
+        ex = _Exchange(ctx, world, max_e, [4, 4, 8, 1], [torch.int32, torch.int32, torch.int64, torch.uint8])
+        ex.field(0).fill_(-1)                      # a < 0 marks the padding rows
+        if nej_k:
+            _pipeline.junction_edge_emit(g, jcount, ex.field(0), ex.field(1), ex.field(3), ex.field(2))
+        gea, geb, gew, gek = ex.gather(group)                                     # collective 1
+        # local ids of rank k -> global ids; the row order is the global (a, b) order the tie-break needs
+        shifts = torch.tensor([int(Noff[k]) - int(counts0[k, 2]) for k in range(world)], dtype=torch.int64)
+        ctx.call('skb_slab_edge_shift', gea, geb, world * ex.cap, ex.cap, shifts.data_ptr(), world)
     else:
-        gea, geb, gek, gew = ea + id_shift, eb + id_shift, ek, ew
-    _mark('allgather_edges')
+        gea = geb = ctx.empty(0, torch.int32)
+        gew, gek = ctx.empty(0, torch.int64), ctx.empty(0, torch.uint8)
     tree, mst_rounds = _pipeline.junction_mst(ctx, gea, geb, gew, N_total)
     _pipeline.graph_csr(g, gea, geb, gek, tree, id_shift)
     _mark('mst_csr')
@@ -289,20 +321,18 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     cross_cycle = None
     if world > 1 and max_blk > 0:
         my_blk = int(nblk[rank])
-        blk = ctx.empty((max(my_blk, 1), 4), torch.int32)
-        blk_aux = ctx.empty((max(my_blk, 1), AUX_BYTES), torch.uint8)
-        ctx.call('skb_slab_export', ranked, raux, SF, SL0, my_blk, start_lo, start_hi, blk, blk_aux)
-        T = _allgather_padded(blk, my_blk, max_blk, group).view(-1, 4)           # collective 4
-        TA = _allgather_padded(blk_aux, my_blk, max_blk, group).view(-1, AUX_BYTES)
-        n_table = world * max_blk                                                # padded layout: rank k at k * max_blk
+        ex = _Exchange(ctx, world, max_blk, [16, AUX_BYTES], [torch.int32, torch.uint8])
+        ctx.call('skb_slab_export', ranked, raux, SF, SL0, my_blk, ex.cap, start_lo, start_hi, ex.field(0), ex.field(1))
+        T, TA = ex.gather(group)                                                  # collective 2
+        n_table = world * ex.cap                                                  # padded layout: rank k at k * cap
         desc = torch.tensor([world] + [int(x) for x in Soff] + [int(x) for x in counts[:, 3]] +
-                            [int(x) for x in counts[:, 4]] + [k * max_blk for k in range(world)], dtype=torch.int64)
+                            [int(x) for x in counts[:, 4]] + [k * ex.cap for k in range(world)], dtype=torch.int64)
         T2, TA2 = torch.empty_like(T), torch.empty_like(TA)
         r2 = ctx.call('skb_slab_table_rank', T, T2, TA, TA2, n_table, desc.data_ptr(), flag)
         Tf, TAf = (T, TA) if (r2 & 1) == 0 else (T2, TA2)
         table_rounds = r2 >> 1
         ctx.call('skb_slab_apply', ranked, raux, Tf, TAf, S, desc.data_ptr(), start_lo, start_hi)
-        cross_cycle = (Tf[:, 0] >= 0).any()
+        cross_cycle = (Tf.view(-1, 4)[:, 0] >= 0).any()
     _mark('table')
     # ---- covered chain voxels, heads of the regular paths ------------------------------------------
     covered = ctx.empty(max(Ne, 1), torch.uint8)
@@ -368,15 +398,13 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     if P_total == 0:
         raise ValueError('index pointer size 0 should be 1')
     # ---- path records to every rank -----------------------------------------------------------------
-    head = ctx.empty((max(P0, 1), 4), torch.int32)
-    link = ctx.empty((max(P0, 1), 4), torch.int32)
-    ctx.call('skb_slab_head_records', head_end, plen, pindptr, pmin, start_node, startoff, head_aux, slab.data_ptr(),
-             Ne, P0, int(P0off[rank]), int(L0off[rank]), head, link)
     maxP = int(counts2[:, 0].max())
+    ex = _Exchange(ctx, world, maxP, [16, 16], [torch.int32, torch.int32])
+    ctx.call('skb_slab_head_records', head_end, plen, pindptr, pmin, start_node, startoff, head_aux, slab.data_ptr(),
+             Ne, P0, ex.cap, int(P0off[rank]), int(L0off[rank]), ex.field(0), ex.field(1))
+    heads_all, links_all = ex.gather(group)                                       # collective 3
+    maxP = ex.cap
     nrec = world * maxP
-    heads_all = _allgather_padded(head, P0, max(maxP, 1), group).view(-1, 4)        # collective 6
-    links_all = _allgather_padded(link, P0, max(maxP, 1), group).view(-1, 4)
-    _mark('allgather_heads')
     einfo = ctx.empty((max(S_total, 1), 4), torch.int32)
     ctx.call('skb_slab_einfo', heads_all, nrec, S_total, einfo)
     # ---- path entries: every rank writes the entries of its own voxels at their global positions ----
