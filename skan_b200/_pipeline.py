@@ -44,7 +44,7 @@ _ESIZE = {0: 1, 1: 1, 2: 2, 3: 2, 4: 4, 5: 4, 6: 8, 7: 8, 8: 4, 9: 8}
 EVENT_HOOK = None
 
 PACK_VARIANT = {'ldg': 0, 'tma': 1}
-default_pack_variant = 'ldg'
+default_pack_variant = 'tma'
 
 
 def neighbour_weights(ndim, spacing):
