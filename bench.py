@@ -36,6 +36,9 @@ WORKLOADS = {
     'volume_1024': ((1024, 1024, 1024), 2048, 512, 4, 1000, 64, (0.5, 0.1, 0.1), False),
     # configs[1]: float32-valued 2-D skeleton (path_means over the image's own values)
     'image_16384': ((16384, 16384), 8192, 512, 2, 1000, 64, 1, True),
+    # configs[2]: 8192 independent 512 x 512 images pushed through the kernels as one stack; ranks take
+    # contiguous shares of the stack, no collective
+    'batch_512': ((8192, 512, 512), 24, 192, 1000, 4, 0, 1, False),
     # small case for quick checks
     'volume_256': ((256, 256, 256), 256, 256, 6, 100, 16, (0.5, 0.1, 0.1), False),
 }
@@ -102,8 +105,25 @@ def cpu_baseline(workload, seconds_hint=15.0):
     shape, nw, steps, seed, iso, rings, spacing, valued = WORKLOADS[workload]
     # warm numba
     orc.skeleton_and_summary(walks((32, 32, 32), 8, 24, seed=1), spacing=(0.5, 0.1, 0.1))
-    frac = {'volume_2048': 2, 'volume_1024': 1, 'image_16384': 1, 'volume_256': 1}[workload]
+    frac = {'volume_2048': 2, 'volume_1024': 1, 'image_16384': 1, 'volume_256': 1, 'batch_512': 64}[workload]
     sub = (shape[0] // frac,) + tuple(shape[1:])
+    if workload.startswith('batch'):
+        from skan_b200.synth import stack_walks_points
+        img = np.zeros(int(np.prod(sub)), bool)
+        img[stack_walks_points(sub[0], sub[1], sub[2], nw, steps, seed, isolated=iso)] = True
+        img = img.reshape(sub)
+        t0 = time.perf_counter()
+        n_paths = 0
+        for i in range(sub[0]):
+            try:
+                sk, _ = orc.skeleton_and_summary(img[i], spacing=spacing)
+                n_paths += sk.n_paths
+            except ValueError:
+                pass
+        dt = time.perf_counter() - t0
+        return {'value': img.size / dt / 1e6, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                'sample': f'first {sub[0]} of {shape[0]} images of {workload}, one by one ({n_paths} paths), {dt:.2f} s, '
+                          'single thread like the reference', 'seconds': dt}
     img = walks(sub, max(8, nw // frac), steps, seed, isolated=iso // frac, rings=rings // frac)
     if valued:
         rng = np.random.default_rng(seed)
@@ -184,12 +204,25 @@ def main():
         _pipeline.default_pack_variant = args.pack_variant
     shape, nw, steps, seed, iso, rings, spacing, valued = WORKLOADS[args.workload]
     V = int(np.prod(shape, dtype=np.int64))
-    if world > 1 and (len(shape) != 3 or valued):
-        raise SystemExit('multi-GPU runs use the Z-slab decomposition of a 3-D volume (volume_* workloads)')
+    is_stack = args.workload.startswith('batch')
+    if world > 1 and not is_stack and (len(shape) != 3 or valued):
+        raise SystemExit('multi-GPU runs use the Z-slab decomposition of a 3-D volume (volume_* workloads) '
+                         'or a stack of independent images (batch_512)')
 
     # ---- synthetic input, resident in HBM ------------------------------------------------------
     esize, dtype_name = (4, 'f32') if valued else (1, 'u8')
-    if world == 1:
+    if is_stack:
+        # this rank's contiguous share of the stack of independent images
+        from skan_b200 import batch
+        from skan_b200.synth import stack_walks_points
+        b0, b1 = rank * shape[0] // world, (rank + 1) * shape[0] // world
+        pts = stack_walks_points(b1 - b0, shape[1], shape[2], nw, steps, seed + rank, isolated=iso)
+        img = torch.zeros((b1 - b0) * shape[1] * shape[2], dtype=torch.bool, device=dev)
+        img[torch.from_numpy(pts).to(dev)] = True
+        img = img.reshape(b1 - b0, shape[1], shape[2])
+        V_local = int(img.numel())
+        del pts
+    elif world == 1:
         if valued:
             mask = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
             gen = torch.Generator(device=dev).manual_seed(seed)
@@ -215,6 +248,8 @@ def main():
 
     def step(image=None):
         image = img if image is None else image
+        if is_stack:
+            return batch.stack_device(image, spacing=spacing, device=dev)
         if world == 1:
             return _pipeline.skeleton_and_summary_device(image, spacing=spacing, device=dev)
         return slab.skeleton_and_summary_slab(image, global_shape=shape, z0=z0, z1=z1, ze0=ze0, spacing=spacing,
@@ -245,10 +280,12 @@ def main():
     for _ in range(max(1, args.warmup)):
         r = step()
     sync_all()
-    if world == 1:
+    if world == 1 or is_stack:
         g, p = r.graph, r.paths
         counts = dict(nodes=g.n_nodes, edges=g.n_edges, paths=p.n_paths, path_entries=p.n_entries,
                       junction_edges=g.n_junction_edges, mst_rounds=g.mst_rounds, rank_rounds=p.rank_rounds)
+        if is_stack and world > 1:
+            counts = {k: int(sum_over_ranks(v)) for k, v in counts.items() if k in ('nodes', 'edges', 'paths', 'path_entries')}
         del g, p
     else:
         counts = dict(nodes=r.n_nodes_total, edges=r.n_edges_total, paths=r.n_paths_total,
@@ -330,7 +367,11 @@ def main():
         for i in range(1 + n_e2e):
             sync_all()
             t0 = time.perf_counter()
-            if world == 1:
+            if is_stack:
+                df = batch.summarize_images(host, spacing=spacing, device=dev)
+                d2h = int(df.memory_usage(index=False).sum())
+                del df
+            elif world == 1:
                 sk = skan_b200.Skeleton(host, spacing=spacing, keep_images=False)
                 df = skan_b200.summarize(sk, separator='_')
                 d2h = int(df.memory_usage(index=False).sum())
@@ -352,7 +393,8 @@ def main():
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': dtype_name, 'data': 'synthetic',
             'config': {'workload': args.workload, 'shape': list(shape), 'spacing': [float(x) for x in np.atleast_1d(spacing)],
-                       'parallelism': 'single GPU' if world == 1 else f'{world} Z-slabs, halo {args.halo}',
+                       'parallelism': 'single GPU' if world == 1 else
+                       (f'{world} shares of the stack, no collective' if is_stack else f'{world} Z-slabs, halo {args.halo}'),
                        'l2': 'input larger than L2 (no flush needed)' if V_local * esize > 256e6 else 'input fits L2',
                        'pack_variant': _pipeline.default_pack_variant, **counts},
             'roofline': roofline, 'clocks': clocks.summary(), 'gpu_launches': int(launches),

@@ -63,9 +63,11 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
                    int64_t* coords, double* values, uint32_t* pre256, void* stream);
 
 /* Raw 3^d neighbourhood of every node as a 27-bit mask -- replaces the N x (3^d-1) neighbour
- * table and membership test of pixel_graph (csr.py:122-144). */
+ * table and membership test of pixel_graph (csr.py:122-144).  planes_independent != 0: the image
+ * is a stack of independent 2-D images (pipe.py:140-148 processes them one by one), no neighbours
+ * across the leading axis. */
 int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape /*host*/, const int64_t* lin, int64_t n,
-                      uint32_t* nb, void* stream);
+                      int planes_independent, uint32_t* nb, void* stream);
 
 /* Junction-junction edges (both ends of raw degree >= 3; csr.py:1004-1016): per-node count of
  * forward edges (only nodes a in [a0, a1): the nodes a Z-slab owns), then (after an exclusive scan

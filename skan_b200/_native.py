@@ -26,7 +26,7 @@ _SIGNATURES = {
     'skb_kernel_launches': (_i64, []),
     'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
     'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
-    'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _vp, _vp]),
+    'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _int, _vp, _vp]),
     'skb_junction_edge_count': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'skb_junction_edge_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int,
                                       _vp, _vp, _vp, _vp, _vp]),

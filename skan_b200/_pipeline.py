@@ -131,7 +131,7 @@ def _as_device_image(image, device):
 
 
 def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant=None, z_origin=0,
-                rank_positions=None):
+                rank_positions=None, image_stack=False):
     """Voxel and node stages of skeleton_to_csgraph (csr.py:1070,122-144,1088): mask sweep, nodes in
     raster order (ids, raveled indices, coordinates, values) and raw 3^d neighbourhood masks."""
     ctx = _Ctx(device)
@@ -141,7 +141,10 @@ def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant
         raise NotImplementedError('skan_b200 supports 1-D, 2-D and 3-D skeleton images')
     V = int(np.prod(shape, dtype=np.int64))
     is_bool = np_dtype == np.dtype(bool)
-    wtab_np = neighbour_weights(ndim, spacing)
+    if image_stack and ndim != 3:
+        raise ValueError('a stack of 2-D images is a 3-D array (image, row, column)')
+    # a stack of 2-D images: 2-D weights on the last two axes, no neighbours across the first
+    wtab_np = neighbour_weights(2 if image_stack else ndim, spacing)
     shape_t = torch.tensor(list(shape), dtype=torch.int64)  # host: read by the C side only
     tile = ctx.lib.tile_voxels
     ntiles = max(1, -(-V // tile))
@@ -193,7 +196,7 @@ def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant
     g.height = 1 if value_is_height else 0
     # --- raw neighbourhood masks ---------------------------------------------------------------
     nb = ctx.empty(N, torch.int32)
-    ctx.call('skb_raw_neighbors', bits, *g.geom, lin, N, nb)
+    ctx.call('skb_raw_neighbors', bits, *g.geom, lin, N, 1 if image_stack else 0, nb)
     g.raw_nb = nb
     g._keepalive = (img, shape_t)
     return g
@@ -376,6 +379,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None)
     ctx.call('skb_skeleton_ids', p.indptr, p.indices, pmin, N, n_regular, P, cc_par, cc_min, is_min, skel_id,
              ctx.scratch(N))
     p.skeleton_id = skel_id
+    p.component_rank = is_min   # exclusive scan of "node is the minimum of its component" (N + 1 entries)
     return p
 
 

@@ -42,9 +42,9 @@ int skb_abi_version(void) { return 1; }
 
 // raw 3^d neighbourhood masks of the N foreground voxels            (replaces csr.py:122-144)
 int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape, const int64_t* lin, int64_t n,
-                      uint32_t* nb, void* stream) {
+                      int planes_independent, uint32_t* nb, void* stream) {
     SKB_TRY(skb_check_geom(ndim, shape));
-    SkbRawNbItem it{skb_make_geom(ndim, shape), bits, lin, nb};
+    SkbRawNbItem it{skb_make_geom(ndim, shape), bits, lin, nb, planes_independent};
     return skb_foreach(n, (skb_stream_t)stream, it);
 }
 

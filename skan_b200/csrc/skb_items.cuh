@@ -169,6 +169,7 @@ struct SkbRawNbItem {
     const uint64_t* bits;
     const int64_t* lin;
     uint32_t* nb;
+    int32_t planes_independent;  // 1: the leading axis indexes independent 2-D images (no dz neighbours)
     SKB_HD void operator()(int64_t i) const {
         int64_t r = lin[i];
         int32_t z, y, x;
@@ -178,7 +179,7 @@ struct SkbRawNbItem {
         if (x == g.nx - 1) xm &= ~4u;
         uint32_t m = 0;
         for (int dz = -1; dz <= 1; ++dz) {
-            if ((uint32_t)(z + dz) >= (uint32_t)g.nz) continue;
+            if ((uint32_t)(z + dz) >= (uint32_t)g.nz || (planes_independent && dz != 0)) continue;
             for (int dy = -1; dy <= 1; ++dy) {
                 if ((uint32_t)(y + dy) >= (uint32_t)g.ny) continue;
                 int64_t rr = r + dz * g.sz + dy * (int64_t)g.nx;

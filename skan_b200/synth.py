@@ -72,3 +72,37 @@ def walks_device(shape, n_walkers, steps, seed, device, sigma=0.15, isolated=0, 
     idx = torch.from_numpy(pts).to(device)
     img[idx] = True if (dtype is None or dtype == torch.bool) else 1
     return img.reshape(tuple(int(s) for s in shape))
+
+
+def stack_walks_points(n_images, height, width, walkers_per_image, steps, seed, sigma=0.15, isolated=0):
+    """Raveled int64 indices into a (n_images, height, width) stack of independent 2-D skeletons:
+    the walks of `walks_points`, vectorised over all images at once (walkers never leave their image,
+    branching re-seeds a walker onto another walker of the same image)."""
+    rng = np.random.default_rng(seed)
+    B, H, W, k = int(n_images), int(height), int(width), int(walkers_per_image)
+    n = B * k
+    img_of = np.repeat(np.arange(B, dtype=np.int64), k)
+    hi = np.array([H - 1, W - 1], dtype=float)
+    pos = rng.random((n, 2)) * hi
+    direc = rng.normal(size=(n, 2))
+    direc /= np.linalg.norm(direc, axis=1, keepdims=True) + 1e-300
+    plane = H * W
+    chunks = []
+    for t in range(steps):
+        p = np.rint(pos).astype(np.int64)
+        ok = (p[:, 0] >= 0) & (p[:, 0] < H) & (p[:, 1] >= 0) & (p[:, 1] < W)
+        chunks.append(img_of[ok] * plane + p[ok, 0] * W + p[ok, 1])
+        direc += sigma * rng.normal(size=direc.shape)
+        direc /= np.linalg.norm(direc, axis=1, keepdims=True) + 1e-300
+        pos += direc / np.abs(direc).max(axis=1, keepdims=True)
+        if t % 64 == 63 and k >= 8:
+            m = n // 8
+            who = rng.choice(n, size=m, replace=False)
+            onto = img_of[who] * k + rng.integers(0, k, size=m)
+            pos[who] = pos[onto]
+            nd = rng.normal(size=(m, 2))
+            direc[who] = nd / (np.linalg.norm(nd, axis=1, keepdims=True) + 1e-300)
+    if isolated:
+        q = rng.integers(0, plane, size=B * isolated) + np.repeat(np.arange(B, dtype=np.int64), isolated) * plane
+        chunks.append(q)
+    return np.concatenate(chunks) if chunks else np.zeros(0, np.int64)
