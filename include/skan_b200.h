@@ -96,10 +96,13 @@ int skb_mst_apply(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const
 
 /* Skeleton.degrees (csr.py:660) and graph.indptr: deg i32[n], indptr i32[n+1] */
 int skb_degrees_indptr(const uint32_t* keep, int64_t n, int32_t* deg, int32_t* indptr, void* scratch, void* stream);
-/* graph.indices i32[E] / graph.data f64[E], canonical CSR (csr.py:153-157) */
+/* graph.indices i32[E] / graph.data f64[E], canonical CSR (csr.py:153-157).  With rec != NULL the
+ * same pass writes the outputs of skb_path_records (lin_splitters: sample splitters by voxel position). */
 int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape /*host*/,
                  const int64_t* lin, const uint32_t* keep, const int32_t* indptr, int64_t n, const double* wtab,
-                 const double* values, int height, int dtype, int32_t* indices, double* data, void* stream);
+                 const double* values, int height, int dtype, int32_t* indices, double* data, skb_i4* rec,
+                 const int64_t* slab /*host*/, int lin_splitters, uint32_t* startoff, int32_t* par, int32_t* cmin,
+                 uint32_t* is_min, void* scratch, void* stream);
 
 /* ---- Path tracing -- replaces _build_paths / _walk_path (csr.py:347-409) ---------------------
  * Sampled list ranking: every half-edge leaving a terminal (degree 1 or >= 3) and both half-edges
@@ -114,13 +117,14 @@ typedef struct skb_i4 { int32_t x, y, z, w; } skb_i4; /* 16-byte aligned */
  * (global node id = local + id_shift), start_shift, start_lo, start_hi (global start ids),
  * lin_offset (global raveled index = lin + lin_offset).  See the Z-slab section below. */
 
-/* rec i4[n] = (n0, n1, indptr[v], degree | flags); sum of n_chain u32[64] = owned degree-2 nodes;
- * startoff u32[n+1] = scanned phase-0 walk starts per node; par, cmin i32[n] (may be NULL) and
- * is_min u32[n+1] = initial state of skb_skeleton_ids (isolated pixels already flagged).  With
- * lin != NULL splitters are sampled by voxel position instead of node id. */
-int skb_path_records(const int32_t* indptr, const int32_t* indices, const int64_t* lin, const int64_t* slab /*host*/,
-                     int64_t n, skb_i4* rec, uint32_t* n_chain, uint32_t* startoff, int32_t* par, int32_t* cmin,
-                     uint32_t* is_min, void* scratch, void* stream);
+/* Node records from an existing CSR: rec = 2 x i4 per node (32 B): (n0, n1, indptr[v], degree | flags)
+ * and the two edge weights of a degree-2 node as (f64, f64); startoff u32[n+1] = scanned phase-0 walk
+ * starts per node; par, cmin i32[n] (may be NULL) and is_min u32[n+1] = initial state of
+ * skb_skeleton_ids (isolated pixels already flagged).  With lin != NULL splitters are sampled by voxel
+ * position instead of node id. */
+int skb_path_records(const int32_t* indptr, const int32_t* indices, const double* gdata, const int64_t* lin,
+                     const int64_t* slab /*host*/, int64_t n, skb_i4* rec, uint32_t* startoff, int32_t* par,
+                     int32_t* cmin, uint32_t* is_min, void* scratch, void* stream);
 /* startoff u32[n+1] for phase 1 (cycle roots + uncovered splitters; covered u8[n]) */
 int skb_path_start_count(const skb_i4* rec, const uint8_t* covered, const int64_t* slab /*host*/, int64_t n,
                          uint32_t* startoff, void* scratch, void* stream);

@@ -33,8 +33,9 @@ _SIGNATURES = {
     'skb_mst_junctions': (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_mst_apply': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'skb_degrees_indptr': (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
-    'skb_csr_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp]),
-    'skb_path_records': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_csr_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _int,
+                            _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_path_records': (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_path_start_count': (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'skb_path_walk': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_path_rank': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),

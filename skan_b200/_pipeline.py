@@ -248,9 +248,10 @@ def junction_mst(ctx, ea, eb, ew, n_ids):
     return tree, rounds
 
 
-def graph_csr(g, ea, eb, ek, tree, id_shift=0):
+def graph_csr(g, ea, eb, ek, tree, id_shift=0, records=True, slab=None, cc_init=True):
     """Final CSR (csr.py:153-157 after 1018-1019): drop the non-tree junction edges from the raw
-    masks, degrees, indptr, indices, data."""
+    masks, degrees, indptr, indices, data.  With records=True the emission pass also writes what the
+    path stage walks on (g.path_state: node records, start offsets, union-find init)."""
     ctx, N = g.ctx, g.n_nodes
     nej = int(ea.numel())
     if nej:
@@ -264,8 +265,18 @@ def graph_csr(g, ea, eb, ek, tree, id_shift=0):
     E = int(indptr[N].item())
     indices = ctx.empty(E, torch.int32)
     data = ctx.empty(E, torch.float64)
+    rec = startoff = par = cmin = is_min = None
+    if records:
+        rec = ctx.empty((max(N, 1), 8), torch.int32)
+        startoff = ctx.empty(N + 1, torch.int32)
+        is_min = ctx.empty(N + 1, torch.int32)
+        if cc_init:
+            par = ctx.empty(max(N, 1), torch.int32)
+            cmin = ctx.empty(max(N, 1), torch.int32)
     ctx.call('skb_csr_emit', g.bits, g.pre256, *g.geom, g.lin, keep, indptr, N, g.wtab, g.values, g.height,
-             g.dtype_code, indices, data)
+             g.dtype_code, indices, data, rec, slab, 1 if slab is not None else 0, startoff, par, cmin, is_min,
+             ctx.scratch(N))
+    g.path_state = (rec, startoff, par, cmin, is_min) if records else None
     g.keep, g.degrees, g.indptr, g.indices, g.data, g.n_edges = keep, deg, indptr, indices, data, E
     return g
 
@@ -281,7 +292,7 @@ def pixel_graph(image, *, spacing=1, value_is_height=False, device, pack_variant
     return graph_csr(g, ea, eb, ek, tree)
 
 
-def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None):
+def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None, state=None):
     """_build_skeleton_path_graph on the device (csr.py:412-446) by sampled list ranking, plus the
     skeleton ids summarize needs (csr.py:909).  Raises ValueError when there is no path, like the
     reference's csr_matrix constructor does at csr.py:442."""
@@ -289,14 +300,16 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None)
     p = SimpleNamespace(n_nodes=N)
     if N == 0 or E == 0:
         raise ValueError('index pointer size 0 should be 1')
-    rec = ctx.empty((N, 4), torch.int32)
-    n_chain_t = ctx.empty(64, torch.int32)
-    startoff0 = ctx.empty(N + 1, torch.int32)
-    cc_par = ctx.empty(N, torch.int32)
-    cc_min = ctx.empty(N, torch.int32)
-    is_min = ctx.empty(N + 1, torch.int32)
-    ctx.call('skb_path_records', indptr, indices, lin, None, N, rec, n_chain_t, startoff0, cc_par, cc_min, is_min,
-             ctx.scratch(N))
+    if state is not None:
+        rec, startoff0, cc_par, cc_min, is_min = state
+    else:
+        rec = ctx.empty((N, 8), torch.int32)
+        startoff0 = ctx.empty(N + 1, torch.int32)
+        cc_par = ctx.empty(N, torch.int32)
+        cc_min = ctx.empty(N, torch.int32)
+        is_min = ctx.empty(N + 1, torch.int32)
+        ctx.call('skb_path_records', indptr, indices, gdata, lin, None, N, rec, startoff0, cc_par, cc_min, is_min,
+                 ctx.scratch(N))
     p.rec = rec
 
     def phase(ph, covered, pid_base):
@@ -332,12 +345,11 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None)
     # ---- phase 0: paths between terminals -----------------------------------------------------
     a = phase(0, None, 0)
     n_regular = int(a.sel[a.S].item()) if a is not None else 0
-    n_chain = int(n_chain_t.sum().item())
     p.rank_rounds = a.rounds if a is not None else 0
-    # every path entry that is not a path end is a degree-2 node, and each is on exactly one path:
-    # what the regular paths do not cover lies on junction-free cycles (csr.py:369-386)
-    cap_cycles_hint = n_chain  # refined below once the regular path lengths are known
-    P_cap = n_regular + n_chain // 3 + 1
+    # every edge lies on exactly one path, so the regular paths account for L - P of the E/2 edges; what
+    # is left are the edges (= nodes) of junction-free cycles (csr.py:369-386).  Their number is only
+    # known after the lengths of the regular paths; until then size by the worst case.
+    P_cap = n_regular + E // 6 + 1
     start_node = ctx.empty(P_cap, torch.int32)
     plen = ctx.empty(P_cap + 1, torch.int32)
     pmin = ctx.empty(P_cap, torch.int32)
@@ -347,7 +359,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None)
         heads(a, start_node, plen, pmin)
         ctx.call('skb_scan_u32', plen, pindptr, n_regular, ctx.scratch(n_regular))
         L_reg = int(pindptr[n_regular].item())
-    n_uncovered = n_chain - (L_reg - 2 * n_regular)
+    n_uncovered = max(0, E // 2 - (L_reg - n_regular))
     L_cap = L_reg + n_uncovered + n_uncovered // 3 + 1
     pidx = ctx.empty(L_cap, torch.int32)
     pdata = ctx.empty(L_cap, torch.float64)
@@ -414,7 +426,7 @@ def skeleton_and_summary_device(image, *, spacing=1, value_is_height=False, devi
     paths, per-path statistics and the branch table (what Skeleton(...) + summarize(...) compute)."""
     g = pixel_graph(image, spacing=spacing, value_is_height=value_is_height, device=device,
                     pack_variant=pack_variant)
-    p = trace_paths(g.ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges)
+    p = trace_paths(g.ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges, state=g.path_state)
     dist, mean, stdev = path_stats(g.ctx, p)
     o32, o64, of, _ = branch_table(g.ctx, p, g.indptr, g.coords, g.values, spacing, g.ndim, value_is_height)
     return SimpleNamespace(graph=g, paths=p, dist=dist, mean=mean, stdev=stdev, table=(o32, o64, of))

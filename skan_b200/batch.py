@@ -43,7 +43,7 @@ def stack_device(images, *, spacing=1, device=None, pack_variant=None):
     g.n_junction_edges = int(ea.numel())
     tree, g.mst_rounds = _pipeline.junction_mst(ctx, ea, eb, ew, g.n_nodes)
     _pipeline.graph_csr(g, ea, eb, ek, tree)
-    p = _pipeline.trace_paths(ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges)
+    p = _pipeline.trace_paths(ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges, state=g.path_state)
     dist, mean, stdev = _pipeline.path_stats(ctx, p)
     sp = np.asarray(spacing)
     sp3 = np.concatenate([[1 if sp.dtype.kind in 'iub' else 1.0], np.full(2, sp) if sp.ndim == 0 else sp])

@@ -81,7 +81,8 @@ class Skeleton:
         self._coords_dev = g.coords
         self._graph_dev = (g.indptr, g.indices, g.data)
         self._n_nodes = g.n_nodes
-        self._p = _pipeline.trace_paths(g.ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges)
+        self._p = _pipeline.trace_paths(g.ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges,
+                                        state=g.path_state)
         self.n_paths = self._p.n_paths
         self._host = {}
         self._stats = None

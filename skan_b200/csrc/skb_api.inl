@@ -36,6 +36,23 @@ static int skb_check_geom(int ndim, const int64_t* shape) {
     return 0;
 }
 
+// `slab` (host, 13 x i64, or NULL on a single GPU) = own0, own1, cnt0, cnt1, ga0, ga1, gb0, gb1,
+// id_shift, start_shift, start_lo, start_hi, lin_offset -- see struct SkbSlab.
+static SkbSlab skb_make_slab(const int64_t* v, int64_t n) {
+    SkbSlab sl;
+    if (!v) {
+        sl.own0 = 0; sl.own1 = (int32_t)n; sl.cnt0 = 0; sl.cnt1 = (int32_t)n;
+        sl.ga0 = sl.ga1 = sl.gb0 = sl.gb1 = 0;
+        sl.id_shift = 0; sl.start_shift = 0; sl.start_lo = 0; sl.start_hi = 0x7fffffff; sl.lin_offset = 0;
+        return sl;
+    }
+    sl.own0 = (int32_t)v[0]; sl.own1 = (int32_t)v[1]; sl.cnt0 = (int32_t)v[2]; sl.cnt1 = (int32_t)v[3];
+    sl.ga0 = (int32_t)v[4]; sl.ga1 = (int32_t)v[5]; sl.gb0 = (int32_t)v[6]; sl.gb1 = (int32_t)v[7];
+    sl.id_shift = (int32_t)v[8]; sl.start_shift = (int32_t)v[9];
+    sl.start_lo = (int32_t)v[10]; sl.start_hi = (int32_t)v[11]; sl.lin_offset = v[12];
+    return sl;
+}
+
 extern "C" {
 
 int skb_abi_version(void) { return 1; }
@@ -116,46 +133,36 @@ int skb_degrees_indptr(const uint32_t* keep, int64_t n, int32_t* deg, int32_t* i
     return skb_scan_u32_impl((const uint32_t*)deg, (uint32_t*)indptr, n, scratch, s);
 }
 
-// graph.indices / graph.data in canonical CSR order (csr.py:153-157)
+// graph.indices / graph.data in canonical CSR order (csr.py:153-157).  With rec != NULL the same
+// pass also writes what skb_path_records would: node records rec (32 B per node), scanned phase-0
+// start offsets startoff u32[n+1] and the initial state of the skeleton-id stage.
 int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
                  const uint32_t* keep, const int32_t* indptr, int64_t n, const double* wtab, const double* values,
-                 int height, int dtype, int32_t* indices, double* data, void* stream) {
+                 int height, int dtype, int32_t* indices, double* data, skb_i4* rec, const int64_t* slab,
+                 int lin_splitters, uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
+                 void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
     SKB_TRY(skb_check_geom(ndim, shape));
     if (height && !values) return skb_fail("height mode needs node values");
     SkbWeight wf{wtab, values, height, dtype};
-    SkbCsrEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, keep, indptr, wf, indices, data};
-    return skb_foreach(n, (skb_stream_t)stream, it);
+    SkbRecOut out{lin_splitters ? lin : nullptr, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min};
+    SkbCsrEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, keep, indptr, wf, indices, data, rec ? 1 : 0, out};
+    SKB_TRY(skb_foreach(n, s, it));
+    if (rec) return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
+    return 0;
 }
 
 // ---- path tracing (csr.py:347-446): sampled list ranking, see skb_items.cuh ------------------
-// `slab` (host, 13 x i64, or NULL on a single GPU) = own0, own1, cnt0, cnt1, ga0, ga1, gb0, gb1,
-// id_shift, start_shift, start_lo, start_hi, lin_offset -- see struct SkbSlab.
-static SkbSlab skb_make_slab(const int64_t* v, int64_t n) {
-    SkbSlab sl;
-    if (!v) {
-        sl.own0 = 0; sl.own1 = (int32_t)n; sl.cnt0 = 0; sl.cnt1 = (int32_t)n;
-        sl.ga0 = sl.ga1 = sl.gb0 = sl.gb1 = 0;
-        sl.id_shift = 0; sl.start_shift = 0; sl.start_lo = 0; sl.start_hi = 0x7fffffff; sl.lin_offset = 0;
-        return sl;
-    }
-    sl.own0 = (int32_t)v[0]; sl.own1 = (int32_t)v[1]; sl.cnt0 = (int32_t)v[2]; sl.cnt1 = (int32_t)v[3];
-    sl.ga0 = (int32_t)v[4]; sl.ga1 = (int32_t)v[5]; sl.gb0 = (int32_t)v[6]; sl.gb1 = (int32_t)v[7];
-    sl.id_shift = (int32_t)v[8]; sl.start_shift = (int32_t)v[9];
-    sl.start_lo = (int32_t)v[10]; sl.start_hi = (int32_t)v[11]; sl.lin_offset = v[12];
-    return sl;
-}
-
-// rec i4[n] (n0, n1, indptr, degree|flags), the number of owned degree-2 nodes (sum of n_chain
-// u32[64]), the phase-0 start offsets (startoff u32[n+1], scanned) and the initial state of the
-// skeleton-id stage (par, cmin i32[n], may be NULL; is_min u32[n+1]).  lin (may be NULL) makes the
-// splitter sample a function of the voxel position instead of the node id.
-int skb_path_records(const int32_t* indptr, const int32_t* indices, const int64_t* lin, const int64_t* slab,
-                     int64_t n, skb_i4* rec, uint32_t* n_chain, uint32_t* startoff, int32_t* par, int32_t* cmin,
+// node records from an existing CSR: rec (32 B per node: (n0, n1, indptr, degree|flags), (w0, w1)),
+// the phase-0 start offsets (startoff u32[n+1], scanned) and the initial state of the skeleton-id
+// stage (par, cmin i32[n], may be NULL; is_min u32[n+1]).  lin (may be NULL) makes the splitter
+// sample a function of the voxel position instead of the node id.
+int skb_path_records(const int32_t* indptr, const int32_t* indices, const double* gdata, const int64_t* lin,
+                     const int64_t* slab, int64_t n, skb_i4* rec, uint32_t* startoff, int32_t* par, int32_t* cmin,
                      uint32_t* is_min, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    SKB_TRY(skb_fill_bytes(n_chain, 0, 64 * 4, s));
-    SKB_TRY(skb_foreach(
-        n, s, SkbPathRecItem{indptr, indices, lin, skb_make_slab(slab, n), rec, n_chain, startoff, par, cmin, is_min}));
+    SkbRecOut out{lin, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min};
+    SKB_TRY(skb_foreach(n, s, SkbPathRecItem{indptr, indices, gdata, out}));
     return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }
 

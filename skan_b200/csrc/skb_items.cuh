@@ -410,44 +410,6 @@ struct SkbMstApplyItem {  // drop non-tree junction-junction edges in both direc
     }
 };
 
-// ---- stage: final CSR (csr.py:153-157 after 1018-1019): count -> scan -> emit ---------------
-struct SkbPopcItem {
-    const uint32_t* keep;
-    uint32_t* deg;
-    SKB_HD void operator()(int64_t i) const { deg[i] = (uint32_t)skb_popc(keep[i]); }
-};
-
-struct SkbCsrEmitFn {
-    SkbWeight wf;
-    int32_t a;
-    int32_t o;
-    int32_t* indices;
-    double* data;
-    SKB_HD void operator()(int k, int32_t u) {
-        indices[o] = u;
-        data[o] = wf(a, u, k);
-        ++o;
-    }
-};
-
-struct SkbCsrEmitItem {
-    SkbGeom g;
-    const uint64_t* bits;
-    const uint32_t* pre256;
-    const int64_t* lin;
-    const uint32_t* keep;
-    const int32_t* indptr;
-    SkbWeight wf;
-    int32_t* indices;
-    double* data;
-    SKB_HD void operator()(int64_t i) const {
-        uint32_t m = keep[i];
-        if (!m) return;
-        SkbCsrEmitFn fn{wf, (int32_t)i, indptr[i], indices, data};
-        skb_for_neighbors(g, bits, pre256, lin[i], (int32_t)i, m, fn);
-    }
-};
-
 // ---- stage: path tracing (csr.py:347-446) as sampled list ranking ----------------------------
 // The serial walk of the reference follows degree-2 chains between terminals (degree 1 or >= 3).
 // Here every half-edge leaving a terminal, and both half-edges leaving every "splitter" chain
@@ -475,6 +437,31 @@ SKB_HD skb_i4 skb_ld_i4(const skb_i4* p) {
     return *p;
 #endif
 }
+struct alignas(16) skb_d2 {
+    double x, y;
+};
+SKB_HD skb_d2 skb_ld_d2(const skb_i4* p) {  // the second half of a 32-byte node record: two edge weights
+#if defined(__CUDA_ARCH__)
+    double2 v = *reinterpret_cast<const double2*>(p);
+    skb_d2 r;
+    r.x = v.x; r.y = v.y;
+    return r;
+#else
+    skb_d2 r;
+    memcpy(&r, p, 16);
+    return r;
+#endif
+}
+SKB_HD void skb_st_d2(skb_i4* p, double x, double y) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<double2*>(p) = make_double2(x, y);
+#else
+    skb_d2 r;
+    r.x = x; r.y = y;
+    memcpy(p, &r, 16);
+#endif
+}
+
 SKB_HD void skb_st_i4(skb_i4* p, skb_i4 v) {
 #if defined(__CUDA_ARCH__)
     *reinterpret_cast<int4*>(p) = make_int4(v.x, v.y, v.z, v.w);
@@ -513,20 +500,18 @@ struct alignas(16) SkbAux {
     int32_t pad;
 };
 
-// rec[v] = (n0, n1, indptr[v], degree | flags): the two neighbours of a degree-2 node
-struct SkbPathRecItem {  // over nodes
-    const int32_t* indptr;
-    const int32_t* indices;
+// Node record, 32 bytes = two 16-byte halves of rec[2v], rec[2v+1]:
+//   (n0, n1, indptr[v], degree | flags)  and  (w0, w1) = weights of the edges to n0 and n1
+// (n0, n1, w0, w1 only meaningful for degree-2 nodes).  One sector per walk step.
+struct SkbRecOut {
     const int64_t* lin;  // null: splitters are sampled by node id
     SkbSlab sl;
     skb_i4* rec;
-    uint32_t* n_chain;   // number of owned degree-2 nodes, summed over 64 slots (pre-zeroed)
-    uint32_t* count;     // phase-0 walk starts leaving v (scanned by the caller)
-    int32_t* par;        // union-find parent / component minimum of the skeleton-id stage (may be null)
+    uint32_t* count;   // phase-0 walk starts leaving v (scanned by the caller)
+    int32_t* par;      // union-find parent / component minimum of the skeleton-id stage (may be null)
     int32_t* cmin;
-    uint32_t* is_min;    // "is the minimum node of a component": isolated pixels are flagged here (csr.py:909)
-    SKB_HD void operator()(int64_t v) const {
-        int32_t o = indptr[v], d = indptr[v + 1] - o;
+    uint32_t* is_min;  // "is the minimum node of a component": isolated pixels are flagged here (csr.py:909)
+    SKB_HD void write(int64_t v, int32_t o, int32_t d, int32_t n0, int32_t n1, double w0, double w1) const {
         int32_t iv = (int32_t)v;
         skb_i4 r;
         r.x = -1;
@@ -535,20 +520,14 @@ struct SkbPathRecItem {  // over nodes
         r.w = d > SKB_REC_DEG_MASK ? SKB_REC_DEG_MASK : d;  // only "== 2" and row scans (bounded below) use it
         bool split = false;
         if (d == 2) {
-            r.x = indices[o];
-            r.y = indices[o + 1];
+            r.x = n0;
+            r.y = n1;
             split = (iv >= sl.ga0 && iv < sl.ga1) || (iv >= sl.gb0 && iv < sl.gb1) ||
                     skb_hash_splitter(lin ? lin[v] + sl.lin_offset : (int64_t)v);
             if (split) r.w |= SKB_REC_SPLITTER;
-            if (iv >= sl.own0 && iv < sl.own1) {
-#if defined(__CUDA_ARCH__)
-                atomicAdd(n_chain + (blockIdx.x & 63), 1u);  // 64 slots: no single hot address
-#else
-                *n_chain += 1u;
-#endif
-            }
         }
-        skb_st_i4(rec + v, r);
+        skb_st_i4(rec + 2 * v, r);
+        skb_st_d2(rec + 2 * v + 1, w0, w1);
         uint32_t c = 0;
         if (iv >= sl.cnt0 && iv < sl.cnt1) c = (uint32_t)(d != 2 ? d : (split ? 2 : 0));
         count[v] = c;
@@ -560,6 +539,70 @@ struct SkbPathRecItem {  // over nodes
     }
 };
 
+struct SkbPathRecItem {  // over nodes: records from an existing CSR (PathGraph.from_graph, csr.py:477-499)
+    const int32_t* indptr;
+    const int32_t* indices;
+    const double* gdata;
+    SkbRecOut out;
+    SKB_HD void operator()(int64_t v) const {
+        int32_t o = indptr[v], d = indptr[v + 1] - o;
+        if (d == 2) out.write(v, o, d, indices[o], indices[o + 1], gdata[o], gdata[o + 1]);
+        else out.write(v, o, d, -1, -1, 0.0, 0.0);
+    }
+};
+
+// ---- stage: final CSR (csr.py:153-157 after 1018-1019): count -> scan -> emit ---------------
+struct SkbPopcItem {
+    const uint32_t* keep;
+    uint32_t* deg;
+    SKB_HD void operator()(int64_t i) const { deg[i] = (uint32_t)skb_popc(keep[i]); }
+};
+
+struct SkbCsrEmitFn {
+    SkbWeight wf;
+    int32_t a;
+    int32_t o;
+    int32_t* indices;
+    double* data;
+    int32_t first;      // position of the row's first entry
+    int32_t n0, n1;     // the first two neighbours and their weights (the record of a degree-2 node)
+    double w0, w1;
+    SKB_HD void operator()(int k, int32_t u) {
+        double w = wf(a, u, k);
+        indices[o] = u;
+        data[o] = w;
+        if (o == first) {
+            n0 = u;
+            w0 = w;
+        } else if (o == first + 1) {
+            n1 = u;
+            w1 = w;
+        }
+        ++o;
+    }
+};
+
+struct SkbCsrEmitItem {
+    SkbGeom g;
+    const uint64_t* bits;
+    const uint32_t* pre256;
+    const int64_t* lin;
+    const uint32_t* keep;
+    const int32_t* indptr;
+    SkbWeight wf;
+    int32_t* indices;
+    double* data;
+    int32_t with_records;  // also write the node record the path stage walks on
+    SkbRecOut out;
+    SKB_HD void operator()(int64_t i) const {
+        uint32_t m = keep[i];
+        int32_t o = indptr[i];
+        SkbCsrEmitFn fn{wf, (int32_t)i, o, indices, data, o, -1, -1, 0.0, 0.0};
+        if (m) skb_for_neighbors(g, bits, pre256, lin[i], (int32_t)i, m, fn);
+        if (with_records) out.write(i, o, fn.o - o, fn.n0, fn.n1, fn.w0, fn.w1);
+    }
+};
+
 // walk starts of phase 1 (junction-free cycles): both half-edges of a cycle root and of an
 // uncovered splitter
 struct SkbStartCountItem {  // over nodes
@@ -568,7 +611,7 @@ struct SkbStartCountItem {  // over nodes
     SkbSlab sl;
     uint32_t* count;
     SKB_HD void operator()(int64_t v) const {
-        skb_i4 r = skb_ld_i4(rec + v);
+        skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
         uint32_t c = 0;
         if ((int32_t)v >= sl.own0 && (int32_t)v < sl.own1) {
             if (r.w & SKB_REC_CYCLE_ROOT) c = 2;
@@ -618,6 +661,7 @@ struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle ro
         int32_t u = su[s];
         int32_t arc = se[s];
         int32_t prev = u, cur = indices[arc];
+        double w_in = aux ? gdata[arc] : 0.0;  // weight of the edge arriving at `cur`
         int32_t cnt = 1, mn = u;
         double sw = 0.0, sx = 0.0, sxx = 0.0;
         if (aux) {
@@ -633,9 +677,10 @@ struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle ro
         ax.end_key = -1;
         ax.pad = 0;
         for (;;) {
-            skb_i4 r = skb_ld_i4(rec + cur);
+            const skb_i4* rp = rec + 2 * (int64_t)cur;
+            skb_i4 r = skb_ld_i4(rp);
             if (cur < mn) mn = cur;
-            if (aux) sw += gdata[arc];
+            if (aux) sw += w_in;
             if (r.w != 2) {
                 if ((r.w & SKB_REC_SPLITTER) && !(r.w & SKB_REC_CYCLE_ROOT)) {
                     // the list continues with the splitter's other half-edge
@@ -669,13 +714,10 @@ struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle ro
                 sx += x;
                 sxx += x * x;
             }
-            int32_t nxt;
-            if (r.x == prev) {
-                nxt = r.y;
-                arc = r.z + 1;
-            } else {
-                nxt = r.x;
-                arc = r.z;
+            int32_t nxt = (r.x == prev) ? r.y : r.x;
+            if (aux) {
+                skb_d2 wn = skb_ld_d2(rp + 1);
+                w_in = (r.x == prev) ? wn.y : wn.x;
             }
             prev = cur;
             cur = nxt;
@@ -858,7 +900,7 @@ struct SkbSelectItem {  // over starts
     int32_t start_lo;
     uint32_t* sel;
     SKB_HD void operator()(int64_t s) const {
-        sel[s] = skb_start_is_head(skb_ld_i4(rec + su[s]), skb_ld_i4(ranked + s), s + start_lo, phase) ? 1u : 0u;
+        sel[s] = skb_start_is_head(skb_ld_i4(rec + 2 * (int64_t)su[s]), skb_ld_i4(ranked + s), s + start_lo, phase) ? 1u : 0u;
     }
 };
 
@@ -880,7 +922,7 @@ struct SkbHeadsItem {  // over starts: path id, start node, length, minimum node
     SkbAux* head_aux;   // slabs: sums and end node of every path
     SKB_HD void operator()(int64_t s) const {
         skb_i4 a = skb_ld_i4(ranked + s);
-        if (!skb_start_is_head(skb_ld_i4(rec + su[s]), a, s + start_lo, phase)) return;
+        if (!skb_start_is_head(skb_ld_i4(rec + 2 * (int64_t)su[s]), a, s + start_lo, phase)) return;
         int32_t pid = pid_base + (int32_t)sel[s];
         start_node[pid] = su[s] + id_shift;
         plen[pid] = (uint32_t)a.y + 1u;
@@ -930,24 +972,27 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
             pw[base] = 0.0;
         }
         int32_t prev = u, cur = indices[arc];
+        double w_in = gdata[arc];  // weight of the edge arriving at `cur`; later ones come with the records
         for (;;) {
             ++pos;
-            skb_i4 r = skb_ld_i4(rec + cur);
+            const skb_i4* rp = rec + 2 * (int64_t)cur;
+            skb_i4 r = skb_ld_i4(rp);
             pidx[base + pos] = cur + id_shift;
             pdata[base + pos] = values ? values[cur] : 1.0;
-            pw[base + pos] = gdata[arc];
+            pw[base + pos] = w_in;
             if (r.w != 2) {
                 if (covered && (r.w & SKB_REC_DEG_MASK) == 2) covered[cur] = 1;
                 break;
             }
             if (covered) covered[cur] = 1;
+            skb_d2 w = skb_ld_d2(rp + 1);
             int32_t nxt;
             if (r.x == prev) {
                 nxt = r.y;
-                arc = r.z + 1;
+                w_in = w.y;
             } else {
                 nxt = r.x;
-                arc = r.z;
+                w_in = w.x;
             }
             prev = cur;
             cur = nxt;
@@ -981,7 +1026,7 @@ struct SkbCycleHookItem {  // over nodes: uncovered degree-2 nodes join their sm
     const uint8_t* covered;
     int32_t* par;
     SKB_HD void operator()(int64_t v) const {
-        skb_i4 r = skb_ld_i4(rec + v);
+        skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
         if ((r.w & SKB_REC_DEG_MASK) != 2 || covered[v]) return;
         if (r.x < (int32_t)v) skb_union_min(par, (int32_t)v, r.x);
         if (r.y < (int32_t)v) skb_union_min(par, (int32_t)v, r.y);
@@ -994,10 +1039,10 @@ struct SkbCycleRootItem {  // over nodes: the minimum of every cycle becomes its
     int32_t* par;
     uint32_t* is_min;  // a junction-free cycle is a component of its own (csr.py:909)
     SKB_HD void operator()(int64_t v) const {
-        skb_i4 r = skb_ld_i4(rec + v);
+        skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
         if ((r.w & SKB_REC_DEG_MASK) != 2 || covered[v]) return;
         if (skb_find(par, (int32_t)v) == (int32_t)v) {
-            rec[v].w |= SKB_REC_CYCLE_ROOT;
+            rec[2 * (int64_t)v].w |= SKB_REC_CYCLE_ROOT;
             is_min[v] = 1u;
         }
     }
@@ -1099,7 +1144,7 @@ struct SkbCoveredItem {  // over nodes: a chain node is covered when a list thro
     uint8_t* covered;
     uint32_t* n_uncovered;  // 64 slots, pre-zeroed: owned chain nodes not covered
     SKB_HD void operator()(int64_t v) const {
-        skb_i4 r = skb_ld_i4(rec + v);
+        skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
         bool owned = (int32_t)v >= own0 && (int32_t)v < own1;
         uint8_t c = owned ? 0 : 1;  // halo nodes are another rank's business
         if ((r.w & SKB_REC_DEG_MASK) == 2 && owned) {

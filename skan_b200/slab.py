@@ -271,25 +271,19 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
         gea = geb = ctx.empty(0, torch.int32)
         gew, gek = ctx.empty(0, torch.int64), ctx.empty(0, torch.uint8)
     tree, mst_rounds = _pipeline.junction_mst(ctx, gea, geb, gew, N_total)
-    _pipeline.graph_csr(g, gea, geb, gek, tree, id_shift)
-    _mark('mst_csr')
-    indptr, indices, gdata, values, lin = g.indptr, g.indices, g.data, g.values, g.lin
-    # ---- records and start numbering -------------------------------------------------------------
+    # ---- CSR + node records + start numbering (one pass) ------------------------------------------
     slab = torch.zeros(13, dtype=torch.int64)
     slab[0], slab[1], slab[2], slab[3] = own0, own1, hl0, hu1
     slab[4], slab[5] = (hl0, f1) if has_lo else (0, 0)
     slab[6], slab[7] = (l0, hu1) if has_hi else (0, 0)
     slab[12] = ze0 * sz
-    rec = ctx.empty((max(Ne, 1), 4), torch.int32)
-    n_chain_t = ctx.empty(64, torch.int32)
-    startoff = ctx.empty(Ne + 1, torch.int32)
-    is_min = ctx.empty(Ne + 1, torch.int32)
-    ctx.call('skb_path_records', indptr, indices, lin, slab.data_ptr(), Ne, rec, n_chain_t, startoff, None, None,
-             is_min, ctx.scratch(Ne))
+    _pipeline.graph_csr(g, gea, geb, gek, tree, id_shift, records=True, slab=slab.data_ptr(), cc_init=False)
+    _mark('mst_csr')
+    indptr, indices, gdata, values, lin = g.indptr, g.indices, g.data, g.values, g.lin
+    rec, startoff, _, _, is_min = g.path_state
     sel_idx = torch.tensor([own0, own1, f1, l0], dtype=torch.int64, device=ctx.device)
-    rb = torch.cat([startoff.index_select(0, sel_idx), indptr.index_select(0, sel_idx[:2]),
-                    n_chain_t.sum(dtype=torch.int32).view(1)]).tolist()
-    so, ei, n_chain = rb[:4], rb[4:6], rb[6]
+    rb = torch.cat([startoff.index_select(0, sel_idx), indptr.index_select(0, sel_idx[:2])]).tolist()
+    so, ei = rb[:4], rb[4:6]
     S_k, SF, SL0 = so[1] - so[0], so[2] - so[0], so[3] - so[0]
     E_k = ei[1] - ei[0]
     _mark('records')
