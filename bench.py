@@ -251,7 +251,7 @@ def main():
         if is_stack:
             return batch.stack_device(image, spacing=spacing, device=dev)
         if world == 1:
-            return _pipeline.skeleton_and_summary_device(image, spacing=spacing, device=dev)
+            return _pipeline.run_native(image, spacing=spacing, device=dev)
         return slab.skeleton_and_summary_slab(image, global_shape=shape, z0=z0, z1=z1, ze0=ze0, spacing=spacing,
                                               device=dev)
 

@@ -226,6 +226,23 @@ int skb_slab_path_stats(const uint32_t* plen, const void* head_aux, int64_t n_pa
 int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int64_t* lin, int64_t n_paths,
                          int64_t* image, void* stream);
 
+/* ---- The whole hot path for one image (or one stack of 2-D images) in one call ---------------------
+ * Native twin of the per-stage sequencing: same kernels in the same order; allocation is a bump
+ * pointer into two caller-provided device arenas (`work`: scratch, `out`: results), the counts that
+ * size allocations are read back inside (~8 stream synchronisations).  Returns 0, or 1 when an arena is
+ * too small (result->work_need / out_need tell how much to provide on the retry), or < 0 on error.
+ * result->off[SKB_O_*] are byte offsets of the result arrays inside `out` (-1 = absent),
+ * result->counts[SKB_C_*] the sizes (see skan_b200/csrc/skb_run.inl for the two enums). */
+typedef struct skb_run_params {
+    const void* image; int32_t dtype, ndim; int64_t shape[3]; int64_t z_origin;
+    int32_t image_stack, height, pack_variant, stop_after_graph, want_values, reserved;
+    const double* wtab;                 /* device: 27 neighbour weights (nputil.py:278-279, host-computed) */
+    double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, table_ndim;
+    void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;
+} skb_run_params;
+typedef struct skb_run_result { int64_t counts[16]; int64_t off[32]; int64_t work_need, out_need; } skb_run_result;
+int skb_run_image(const skb_run_params* params /*host*/, skb_run_result* result /*host*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,33 @@ _SIGNATURES = {
     'skb_scan_u32': (_int, [_vp, _vp, _i64, _vp, _vp]),
 }
 
+
+
+class RunParams(ctypes.Structure):
+    """struct skb_run_params (include/skan_b200.h)"""
+    _fields_ = [('image', _vp), ('dtype', ctypes.c_int32), ('ndim', ctypes.c_int32), ('shape', _i64 * 3),
+                ('z_origin', _i64), ('image_stack', ctypes.c_int32), ('height', ctypes.c_int32),
+                ('pack_variant', ctypes.c_int32), ('stop_after_graph', ctypes.c_int32),
+                ('want_values', ctypes.c_int32), ('reserved', ctypes.c_int32), ('wtab', _vp),
+                ('spacing_f', ctypes.c_double * 3), ('spacing_i', _i64 * 3), ('spacing_is_int', ctypes.c_int32),
+                ('table_ndim', ctypes.c_int32), ('work', _vp), ('work_bytes', _i64), ('out', _vp),
+                ('out_bytes', _i64), ('stream', _vp)]
+
+
+class RunResult(ctypes.Structure):
+    """struct skb_run_result (include/skan_b200.h)"""
+    _fields_ = [('counts', _i64 * 16), ('off', _i64 * 32), ('work_need', _i64), ('out_need', _i64)]
+
+
+_SIGNATURES['skb_run_image'] = (_int, [ctypes.POINTER(RunParams), ctypes.POINTER(RunResult)])
+
+# indices into RunResult.off / .counts (the enums of skan_b200/csrc/skb_run.inl)
+RUN_OFF = {n: i for i, n in enumerate(
+    ['lin', 'coords', 'values', 'degrees', 'indptr', 'indices', 'data', 'pindptr', 'pidx', 'pdata', 'pw', 'skel',
+     'dist', 'mean', 'stdev', 't32', 't64', 'tf', 'comp_rank'])}
+RUN_COUNT = {n: i for i, n in enumerate(
+    ['nodes', 'edges', 'paths', 'regular', 'cycles', 'entries', 'junction_edges', 'starts', 'syncs'])}
+
 EXPORTS = tuple(sorted(_SIGNATURES))
 
 

@@ -436,3 +436,166 @@ def algorithmic_bytes(nvox, esize, ndim, n, e, p, l, valued):
     """every input read once, every mandatory output written once."""
     return (nvox * esize + n * 8 * ndim + (n + 1) * 4 + n * 4 + e * 12 + (n * 8 if valued else 0)
             + (p + 1) * 4 + l * 12 + p * (52 + 32 * ndim))
+
+
+# ---- the same path through the native runner (skb_run_image): one C call per image ---------------
+_arena_cache = {}   # (device, stream) -> dict(work=tensor, out_bytes=int)
+_wtab_cache = {}
+
+
+class _ArenaViews:
+    """Typed views into the output arena, created on first access."""
+
+    def __init__(self, arena, spec):
+        self._arena, self._spec = arena, spec
+
+    def __getattr__(self, name):
+        spec = self.__dict__['_spec']
+        if name not in spec:
+            raise AttributeError(name)
+        off, count, dtype, shape = spec[name]
+        if off < 0:
+            t = None
+        else:
+            nbytes = count * torch.empty(0, dtype=dtype).element_size()
+            t = self._arena[off: off + nbytes].view(dtype)
+            if shape is not None:
+                t = t.view(shape)
+        self.__dict__[name] = t
+        return t
+
+
+def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=None, image_stack=False,
+               graph_only=False, z_origin=0):
+    """Skeleton + summarize (or only skeleton_to_csgraph) of one image through ONE native call.
+    Returns the same namespace as skeleton_and_summary_device, as lazily created views of an arena."""
+    ctx = _Ctx(device)
+    img, code, shape, np_dtype = _as_device_image(image, ctx.device)
+    ndim = len(shape)
+    if ndim < 1 or ndim > 3:
+        raise NotImplementedError('skan_b200 supports 1-D, 2-D and 3-D skeleton images')
+    is_bool = np_dtype == np.dtype(bool)
+    if value_is_height and is_bool:
+        raise TypeError('value_is_height needs a numeric (non-boolean) skeleton image')
+    if value_is_height and np_dtype.kind == 'u':
+        raise ValueError('value_is_height with an unsigned integer image wraps the height differences '
+                         '(reference csr.py:1024); cast the image to a signed or floating dtype')
+    wdim = 2 if image_stack else ndim
+    sp_arr = np.asarray(spacing)
+    wkey = (str(ctx.device), wdim, sp_arr.dtype.str, tuple(np.atleast_1d(sp_arr).tolist()))
+    if wkey not in _wtab_cache:
+        _wtab_cache[wkey] = torch.from_numpy(neighbour_weights(wdim, spacing)).to(ctx.device)
+    wtab = _wtab_cache[wkey]
+    tdim = 3 if image_stack else ndim
+    sp = sp_arr if sp_arr.ndim else np.full(wdim, sp_arr)
+    sp_is_int = sp.dtype.kind in 'iub'
+    if image_stack:
+        sp = np.concatenate([[1 if sp_is_int else 1.0], sp])
+    prm = _native.RunParams()
+    prm.image, prm.dtype, prm.ndim = img.data_ptr(), code, ndim
+    for i, x in enumerate(shape):
+        prm.shape[i] = int(x)
+    prm.z_origin, prm.image_stack = int(z_origin), int(bool(image_stack))
+    prm.height = int(bool(value_is_height))
+    prm.pack_variant = PACK_VARIANT[pack_variant or default_pack_variant]
+    prm.stop_after_graph, prm.want_values = int(bool(graph_only)), int(not is_bool)
+    prm.wtab = wtab.data_ptr()
+    for i in range(tdim):
+        prm.spacing_f[i] = float(sp[i])
+        prm.spacing_i[i] = int(sp[i]) if sp_is_int else 1
+    prm.spacing_is_int, prm.table_ndim = int(sp_is_int), tdim
+    prm.stream = ctx.stream
+    key = (str(ctx.device), ctx.stream)
+    cache = _arena_cache.setdefault(key, dict(work=None, out_bytes=1 << 22))
+    V = int(np.prod(shape, dtype=np.int64))
+    if cache['work'] is None:
+        cache['work'] = ctx.empty(max(1 << 22, V // 4 + (1 << 22)), torch.uint8)
+    res = _native.RunResult()
+    for _ in range(8):
+        work = cache['work']
+        out = ctx.empty(cache['out_bytes'], torch.uint8)
+        prm.work, prm.work_bytes = work.data_ptr(), work.numel()
+        prm.out, prm.out_bytes = out.data_ptr(), out.numel()
+        rc = ctx.lib.call('skb_run_image', ctypes_byref(prm), ctypes_byref(res))
+        if rc == 0:
+            break
+        if res.work_need > work.numel():
+            cache['work'] = ctx.empty(int(res.work_need), torch.uint8)
+        if res.out_need > out.numel():
+            cache['out_bytes'] = int(res.out_need)
+    else:
+        raise _native.NativeError('skb_run_image kept asking for larger arenas')
+    cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
+    C = {k: int(res.counts[i]) for k, i in _native.RUN_COUNT.items()}
+    O = {k: int(res.off[i]) for k, i in _native.RUN_OFF.items()}
+    N, E, P, L = C['nodes'], C['edges'], C['paths'], C['entries']
+    h = int(bool(value_is_height))
+    dh = tdim + h
+    i32, i64, f64 = torch.int32, torch.int64, torch.float64
+    spec = {
+        'lin': (O['lin'], N, i64, None), 'coords': (O['coords'], N * ndim, i64, (N, ndim)),
+        'values': (O['values'], N, f64, None), 'degrees': (O['degrees'], N, i32, None),
+        'indptr': (O['indptr'], N + 1, i32, None), 'indices': (O['indices'], E, i32, None),
+        'data': (O['data'], E, f64, None), 'comp_rank': (O['comp_rank'], N + 1, i32, None),
+        'pindptr': (O['pindptr'], P + 1, i32, None), 'pidx': (O['pidx'], L, i32, None),
+        'pdata': (O['pdata'], L, f64, None), 'pw': (O['pw'], L, f64, None), 'skel': (O['skel'], P, i32, None),
+        'dist': (O['dist'], P, f64, None), 'mean': (O['mean'], P, f64, None), 'stdev': (O['stdev'], P, f64, None),
+        't32': (O['t32'], 3 * P, i32, (3, P)), 't64': (O['t64'], (1 + 2 * tdim) * P, i64, (1 + 2 * tdim, P)),
+        'tf': (O['tf'], (2 * dh + 1) * P, f64, (2 * dh + 1, P)),
+    }
+    v = _ArenaViews(out, spec)
+    g = _GraphView(v, ctx, tuple(shape), ndim, np_dtype, code, spacing, bool(value_is_height), V, N, E,
+                   C['junction_edges'], img)
+    if graph_only:
+        return SimpleNamespace(graph=g, paths=None, counts=C)
+    if P == 0:
+        raise ValueError('index pointer size 0 should be 1')
+    p = _PathView(v, N, P, C['regular'], C['cycles'], L)
+    return _RunView(v, g, p, sp_is_int, C)
+
+
+def ctypes_byref(x):
+    import ctypes
+    return ctypes.byref(x)
+
+
+class _GraphView:
+    """Graph part of a native run; attribute names of the namespace graph_csr() returns."""
+
+    def __init__(self, v, ctx, shape, ndim, np_dtype, code, spacing, height, nvox, n, e, nej, keepalive):
+        self._v, self.ctx, self.shape, self.ndim, self.np_dtype = v, ctx, shape, ndim, np_dtype
+        self.dtype_code, self.spacing, self.value_is_height, self.nvox = code, spacing, height, nvox
+        self.n_nodes, self.n_edges, self.n_junction_edges, self.mst_rounds = n, e, nej, 0
+        self._keepalive = keepalive
+        self.path_state = None
+
+    lin = property(lambda self: self._v.lin)
+    coords = property(lambda self: self._v.coords)
+    values = property(lambda self: self._v.values)
+    degrees = property(lambda self: self._v.degrees)
+    indptr = property(lambda self: self._v.indptr)
+    indices = property(lambda self: self._v.indices)
+    data = property(lambda self: self._v.data)
+
+
+class _PathView:
+    def __init__(self, v, n, p, n_regular, n_cycles, l):
+        self._v, self.n_nodes, self.n_paths, self.n_regular, self.n_cycles, self.n_entries = v, n, p, n_regular, n_cycles, l
+        self.rank_rounds = 0
+
+    indptr = property(lambda self: self._v.pindptr)
+    indices = property(lambda self: self._v.pidx)
+    data = property(lambda self: self._v.pdata)
+    weights = property(lambda self: self._v.pw)
+    skeleton_id = property(lambda self: self._v.skel)
+    component_rank = property(lambda self: self._v.comp_rank)
+
+
+class _RunView:
+    def __init__(self, v, g, p, spacing_is_int, counts):
+        self._v, self.graph, self.paths, self.spacing_is_int, self.counts = v, g, p, spacing_is_int, counts
+
+    dist = property(lambda self: self._v.dist)
+    mean = property(lambda self: self._v.mean)
+    stdev = property(lambda self: self._v.stdev)
+    table = property(lambda self: (self._v.t32, self._v.t64, self._v.tf))

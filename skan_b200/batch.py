@@ -26,31 +26,15 @@ def stack_device(images, *, spacing=1, device=None, pack_variant=None):
     if len(shape) != 3:
         raise ValueError('expected a stack of 2-D images with shape (B, H, W)')
     B, H, W = shape
-    g = _pipeline.graph_nodes(images, spacing=spacing, device=device, pack_variant=pack_variant, image_stack=True,
-                              rank_positions=[i * H * W for i in range(B + 1)])
-    ctx = g.ctx
-    if g.position_ranks is not None:
-        node_off = g.position_ranks
-    else:  # image size is not a multiple of the mask tile: one rank query per image boundary
-        pos = torch.tensor([i * H * W for i in range(B)], dtype=torch.int64, device=ctx.device)
-        out = ctx.empty(B, torch.int32)
-        if g.n_nodes:
-            ctx.call('skb_rank_query', g.bits, g.pre256, pos, B, out)
-            node_off = out.tolist() + [g.n_nodes]
-        else:
-            node_off = [0] * (B + 1)
-    ea, eb, ek, ew = _pipeline.junction_edges(g)
-    g.n_junction_edges = int(ea.numel())
-    tree, g.mst_rounds = _pipeline.junction_mst(ctx, ea, eb, ew, g.n_nodes)
-    _pipeline.graph_csr(g, ea, eb, ek, tree)
-    p = _pipeline.trace_paths(ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges, state=g.path_state)
-    dist, mean, stdev = _pipeline.path_stats(ctx, p)
-    sp = np.asarray(spacing)
-    sp3 = np.concatenate([[1 if sp.dtype.kind in 'iub' else 1.0], np.full(2, sp) if sp.ndim == 0 else sp])
-    o32, o64, of, sp_is_int = _pipeline.branch_table(ctx, p, g.indptr, g.coords, g.values, sp3, 3, False)
+    r = _pipeline.run_native(images, spacing=spacing, device=device, pack_variant=pack_variant, image_stack=True)
+    g, p = r.graph, r.paths
+    # id of the first node of every image: nodes are in raster order, so count the nodes before each image
+    lin = g.lin
+    bounds = torch.arange(B + 1, dtype=torch.int64, device=lin.device) * (H * W)
+    node_off = torch.searchsorted(lin, bounds).tolist()
     from types import SimpleNamespace
-    return SimpleNamespace(graph=g, paths=p, dist=dist, mean=mean, stdev=stdev, table=(o32, o64, of),
-                           spacing_is_int=sp_is_int, node_offsets=node_off, n_images=B)
+    return SimpleNamespace(graph=g, paths=p, dist=r.dist, mean=r.mean, stdev=r.stdev, table=r.table,
+                           spacing_is_int=r.spacing_is_int, node_offsets=node_off, n_images=B)
 
 
 def summarize_images(images, *, spacing=1, separator='_', device=None):

@@ -44,7 +44,8 @@ def skeleton_to_csgraph(skel, *, spacing=1, value_is_height=False):
     fp64 distances (int32 index arrays, sorted columns) and a tuple of ndim int64 coordinate
     arrays, node ids being 0-based raster ranks of the nonzero pixels.
     """
-    g = _pipeline.pixel_graph(skel, spacing=spacing, value_is_height=value_is_height, device=_device_of(skel))
+    g = _pipeline.run_native(skel, spacing=spacing, value_is_height=value_is_height, device=_device_of(skel),
+                             graph_only=True).graph
     n = g.n_nodes
     graph = sparse.csr_matrix((_to_host(g.data), _to_host(g.indices), _to_host(g.indptr)), shape=(n, n))
     coords = _to_host(g.coords)
@@ -73,16 +74,18 @@ class Skeleton:
 
     def __init__(self, skeleton_image, *, spacing=1, source_image=None, keep_images=True,
                  value_is_height=False):
-        g = _pipeline.pixel_graph(skeleton_image, spacing=spacing, value_is_height=value_is_height,
-                                  device=_device_of(skeleton_image))
+        # the whole path (graph, paths, statistics, branch table) in one native call
+        run = _pipeline.run_native(skeleton_image, spacing=spacing, value_is_height=value_is_height,
+                                   device=_device_of(skeleton_image))
+        g = run.graph
+        self._run = run
         self._g = g
         self._ctx = g.ctx
         self._values_dev = g.values
         self._coords_dev = g.coords
         self._graph_dev = (g.indptr, g.indices, g.data)
         self._n_nodes = g.n_nodes
-        self._p = _pipeline.trace_paths(g.ctx, g.indptr, g.indices, g.data, g.values, g.n_nodes, g.n_edges,
-                                        state=g.path_state)
+        self._p = run.paths
         self.n_paths = self._p.n_paths
         self._host = {}
         self._stats = None
@@ -161,7 +164,7 @@ class Skeleton:
 
     def _device_stats(self):
         if self._stats is None:
-            self._stats = _pipeline.path_stats(self._ctx, self._p)
+            self._stats = (self._run.dist, self._run.mean, self._run.stdev)
         return self._stats
 
     @property
@@ -326,9 +329,14 @@ def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=
     spacing = skel.spacing
     if value_is_height and skel._values_dev is None:
         raise TypeError("'NoneType' object is not subscriptable")  # csr.py:933 on a boolean skeleton
-    dist, mean, stdev = _pipeline.path_stats(ctx, p)
-    o32, o64, of, sp_is_int = _pipeline.branch_table(ctx, p, indptr, skel._coords_dev, skel._values_dev,
-                                                      spacing, ndim, value_is_height)
+    run = getattr(skel, '_run', None)
+    if run is not None and bool(value_is_height) == skel._value_is_height:
+        dist, mean, stdev = run.dist, run.mean, run.stdev      # computed by the native run already
+        (o32, o64, of), sp_is_int = run.table, run.spacing_is_int
+    else:
+        dist, mean, stdev = _pipeline.path_stats(ctx, p)
+        o32, o64, of, sp_is_int = _pipeline.branch_table(ctx, p, indptr, skel._coords_dev, skel._values_dev,
+                                                          spacing, ndim, value_is_height)
     o32, o64, of = _to_host(o32), _to_host(o64), _to_host(of)
     h = int(bool(value_is_height))
     dh = ndim + h

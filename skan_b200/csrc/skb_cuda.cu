@@ -72,6 +72,11 @@ static int skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t s) {
     return skb_cuda_check(cudaMemsetAsync(p, byte, nbytes, s), "cudaMemsetAsync");
 }
 
+static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_t s) {
+    if (!nbytes) return 0;
+    return skb_cuda_check(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
+}
+
 static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s) {
     static thread_local int32_t* pinned = nullptr;
     if (!pinned) SKB_CUDA(cudaMallocHost((void**)&pinned, 64));
@@ -775,3 +780,5 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
 }
 
 }  // extern "C"
+
+#include "skb_run.inl"

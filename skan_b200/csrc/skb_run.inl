@@ -1,0 +1,328 @@
+// skan_b200 -- native sequencing of the whole hot path for one image (or one stack of 2-D images):
+// mask sweep -> nodes -> raw stencil -> junction MST -> CSR (+ node records) -> paths -> statistics
+// -> branch table, in ONE call.  It is the C++ twin of skan_b200/_pipeline.py: the same entry points
+// in the same order, but allocation is a bump pointer into two caller-provided device arenas and the
+// handful of counts that size the next allocation are read back here, so a call costs ~8 stream
+// synchronisations and no interpreter time.  Included after skb_api.inl by skb_cuda.cu and by
+// tests/emul/skb_emul.cpp (the including file provides skb_copy_bytes and skb_fetch_i32).
+//
+// Arenas: `work` holds scratch (mask, rank structure, neighbourhood masks, junction edges, walk
+// starts ...), `out` holds everything the caller may read afterwards.  When an arena is too small
+// the call returns SKB_RUN_NEED_MORE with the sizes needed so far in result->work_need / out_need;
+// the caller grows the arena and calls again.
+
+#define SKB_RUN_NEED_MORE 1
+
+// indices into skb_run_result.off (byte offsets into the `out` arena; -1 = absent)
+enum {
+    SKB_O_LIN = 0, SKB_O_COORDS, SKB_O_VALUES, SKB_O_DEGREES, SKB_O_INDPTR, SKB_O_INDICES, SKB_O_DATA,
+    SKB_O_PINDPTR, SKB_O_PIDX, SKB_O_PDATA, SKB_O_PW, SKB_O_SKEL, SKB_O_DIST, SKB_O_MEAN, SKB_O_STDEV,
+    SKB_O_T32, SKB_O_T64, SKB_O_TF, SKB_O_COMP_RANK, SKB_O_COUNT
+};
+// indices into skb_run_result.counts
+enum {
+    SKB_C_NODES = 0, SKB_C_EDGES, SKB_C_PATHS, SKB_C_REGULAR, SKB_C_CYCLES, SKB_C_ENTRIES, SKB_C_JUNCTION_EDGES,
+    SKB_C_STARTS, SKB_C_SYNCS, SKB_C_COUNT
+};
+
+struct skb_run_params {
+    const void* image;
+    int32_t dtype, ndim;
+    int64_t shape[3];
+    int64_t z_origin;
+    int32_t image_stack;  // leading axis = independent 2-D images
+    int32_t height;       // value_is_height
+    int32_t pack_variant;
+    int32_t stop_after_graph;  // 1: skeleton_to_csgraph only
+    int32_t want_values;       // fp64 node values (non-boolean images)
+    int32_t reserved;
+    const double* wtab;        // device, 27 weights
+    double spacing_f[3];       // for the branch table (table_ndim entries)
+    int64_t spacing_i[3];
+    int32_t spacing_is_int, table_ndim;
+    void* work;
+    int64_t work_bytes;
+    void* out;
+    int64_t out_bytes;
+    void* stream;
+};
+
+struct skb_run_result {
+    int64_t counts[16];
+    int64_t off[32];
+    int64_t work_need, out_need;
+};
+
+struct SkbArena {
+    uint8_t* base;
+    int64_t cap, off, need;
+    bool ok;
+    void init(void* p, int64_t bytes) {
+        base = (uint8_t*)p;
+        cap = bytes;
+        off = 0;
+        need = 0;
+        ok = true;
+    }
+    template <typename T>
+    T* take(int64_t count) {
+        int64_t bytes = (count > 0 ? count : 1) * (int64_t)sizeof(T);
+        off = (off + 255) & ~(int64_t)255;
+        need = off + bytes;
+        if (need > cap || !base) {
+            ok = false;
+            off = need;  // keep counting so that the caller learns how much this stage wanted
+            return nullptr;
+        }
+        T* p = (T*)(base + off);
+        off = need;
+        return p;
+    }
+};
+
+#define SKB_NEED(arena_ok)                                                     \
+    do {                                                                       \
+        if (!(arena_ok)) {                                                     \
+            res->work_need = work.need + work.need / 2 + (1 << 20);            \
+            res->out_need = out.need + out.need / 2 + (1 << 20);               \
+            return SKB_RUN_NEED_MORE;                                          \
+        }                                                                      \
+    } while (0)
+
+#define SKB_FETCH(dst, ptr)                                   \
+    do {                                                      \
+        int32_t _v = 0;                                       \
+        SKB_TRY(skb_fetch_i32((const int32_t*)(ptr), &_v, s)); \
+        (dst) = _v;                                           \
+        ++nsync;                                              \
+    } while (0)
+
+extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
+    skb_stream_t s = (skb_stream_t)prm->stream;
+    const int ndim = prm->ndim;
+    SKB_TRY(skb_check_geom(ndim, prm->shape));
+    if (prm->image_stack && ndim != 3) return skb_fail("a stack of 2-D images is a 3-D array");
+    SkbGeom g = skb_make_geom(ndim, prm->shape);
+    const int64_t V = g.nvox;
+    const int64_t ntiles = (V + SKB_TILE_VOX - 1) / SKB_TILE_VOX;
+    int64_t nsync = 0;
+    for (int i = 0; i < 16; ++i) res->counts[i] = 0;
+    for (int i = 0; i < 32; ++i) res->off[i] = -1;
+    res->work_need = res->out_need = 0;
+    SkbArena work, out;
+    work.init(prm->work, prm->work_bytes);
+    out.init(prm->out, prm->out_bytes);
+    auto out_off = [&](const void* p) -> int64_t { return p ? (int64_t)((const uint8_t*)p - out.base) : -1; };
+
+    // ---- mask sweep, tile prefix ---------------------------------------------------------------
+    uint64_t* store = work.take<uint64_t>(ntiles * SKB_TILE_WORDS + 4);
+    uint32_t* tile_prefix = work.take<uint32_t>(ntiles + 1);
+    void* scratch = work.take<uint8_t>(skb_scan_scratch_bytes(ntiles + 1));
+    int32_t* flag = work.take<int32_t>(4);
+    SKB_NEED(work.ok);
+    uint64_t* bits = store + 2;
+    SKB_TRY(skb_fill_bytes(store, 0, 16, s));
+    SKB_TRY(skb_fill_bytes(store + 2 + ntiles * SKB_TILE_WORDS, 0, 16, s));
+    SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)skb_scan_scratch_bytes(ntiles + 1), s));
+    SKB_TRY(skb_pack_count(prm->image, prm->dtype, V, bits, tile_prefix, ntiles, prm->pack_variant, s));
+    SKB_TRY(skb_scan_u32_impl(tile_prefix, tile_prefix, ntiles, scratch, s));
+    int64_t N;
+    SKB_FETCH(N, tile_prefix + ntiles);
+    res->counts[SKB_C_NODES] = N;
+    {   // every later scan runs over at most 27 N items (nodes, half-edges, walk starts, paths)
+        const int64_t bytes = skb_scan_scratch_bytes(27 * N + ntiles + 1);
+        scratch = work.take<uint8_t>(bytes);
+        SKB_NEED(work.ok);
+        SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)bytes, s));
+    }
+    // ---- nodes, raw neighbourhood ------------------------------------------------------------------
+    const bool want_values = prm->want_values != 0;
+    int64_t* lin = out.take<int64_t>(N);
+    int64_t* coords = out.take<int64_t>(N * ndim);
+    double* values = want_values ? out.take<double>(N) : nullptr;
+    uint32_t* pre256 = work.take<uint32_t>(ntiles * 64);
+    uint32_t* nb = work.take<uint32_t>(N);
+    uint32_t* jcount = work.take<uint32_t>(N + 1);
+    SKB_NEED(work.ok && out.ok);
+    SKB_TRY(skb_emit_nodes(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype, prm->z_origin, lin,
+                           coords, values, pre256, s));
+    SKB_TRY(skb_raw_neighbors(bits, ndim, prm->shape, lin, N, prm->image_stack, nb, s));
+    res->off[SKB_O_LIN] = out_off(lin);
+    res->off[SKB_O_COORDS] = out_off(coords);
+    res->off[SKB_O_VALUES] = out_off(values);
+    // ---- junction MST ----------------------------------------------------------------------------------
+    const int height = prm->height == 1 ? 1 : 0;
+    SKB_TRY(skb_junction_edge_count(bits, pre256, ndim, prm->shape, lin, nb, N, 0, N, jcount, s));
+    SKB_TRY(skb_scan_u32_impl(jcount, jcount, N, scratch, s));
+    int64_t nej;
+    SKB_FETCH(nej, jcount + N);
+    res->counts[SKB_C_JUNCTION_EDGES] = nej;
+    uint32_t* keep = nb;
+    int32_t *ea = nullptr, *eb = nullptr;
+    uint8_t *ek = nullptr, *tree = nullptr;
+    if (nej) {
+        ea = work.take<int32_t>(nej);
+        eb = work.take<int32_t>(nej);
+        ek = work.take<uint8_t>(nej);
+        uint64_t* ew = work.take<uint64_t>(nej);
+        int32_t* mpar = work.take<int32_t>(N);
+        uint64_t* bestw = work.take<uint64_t>(N);
+        uint32_t* beste = work.take<uint32_t>(N);
+        int32_t* era = work.take<int32_t>(nej);
+        int32_t* erb = work.take<int32_t>(nej);
+        tree = work.take<uint8_t>(nej);
+        keep = work.take<uint32_t>(N);
+        SKB_NEED(work.ok);
+        SKB_TRY(skb_junction_edge_emit(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values, height,
+                                       prm->dtype, ea, eb, ek, ew, s));
+        int r = skb_mst_junctions(ea, eb, ew, nej, N, mpar, bestw, beste, era, erb, tree, flag, s);
+        if (r < 0) return r;
+        SKB_TRY(skb_copy_bytes(keep, nb, (size_t)N * 4, s));
+        SKB_TRY(skb_mst_apply(ea, eb, ek, tree, nej, 0, N, keep, s));
+    }
+    // ---- CSR + node records ------------------------------------------------------------------------------
+    int32_t* deg = out.take<int32_t>(N);
+    int32_t* indptr = out.take<int32_t>(N + 1);
+    SKB_NEED(out.ok);
+    SKB_TRY(skb_degrees_indptr(keep, N, deg, indptr, scratch, s));
+    int64_t E;
+    SKB_FETCH(E, indptr + N);
+    res->counts[SKB_C_EDGES] = E;
+    int32_t* indices = out.take<int32_t>(E);
+    double* data = out.take<double>(E);
+    const bool paths_wanted = !prm->stop_after_graph;
+    skb_i4* rec = paths_wanted ? work.take<skb_i4>(2 * N) : nullptr;
+    uint32_t* startoff = paths_wanted ? work.take<uint32_t>(N + 1) : nullptr;
+    int32_t* cc_par = paths_wanted ? work.take<int32_t>(N) : nullptr;
+    int32_t* cc_min = paths_wanted ? work.take<int32_t>(N) : nullptr;
+    uint32_t* is_min = paths_wanted ? out.take<uint32_t>(N + 1) : nullptr;
+    SKB_NEED(work.ok && out.ok);
+    SKB_TRY(skb_csr_emit(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height, prm->dtype,
+                         indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min, scratch, s));
+    res->off[SKB_O_DEGREES] = out_off(deg);
+    res->off[SKB_O_INDPTR] = out_off(indptr);
+    res->off[SKB_O_INDICES] = out_off(indices);
+    res->off[SKB_O_DATA] = out_off(data);
+    res->off[SKB_O_COMP_RANK] = out_off(is_min);
+    if (!paths_wanted || N == 0 || E == 0) {
+        res->counts[SKB_C_SYNCS] = nsync;
+        return 0;
+    }
+    // ---- paths: phase 0 (between terminals), phase 1 (junction-free cycles) ------------------------------------
+    struct Phase {
+        int64_t S;
+        int32_t *su, *se;
+        skb_i4 *ranked, *einfo;
+        uint32_t* sel;
+    };
+    auto run_phase = [&](int ph, const uint32_t* so, Phase& P, int64_t* n_heads) -> int {
+        SKB_FETCH(P.S, so + N);
+        *n_heads = 0;
+        if (P.S == 0) return 0;
+        P.su = work.take<int32_t>(P.S);
+        P.se = work.take<int32_t>(P.S);
+        P.ranked = work.take<skb_i4>(P.S);
+        skb_i4* buf1 = work.take<skb_i4>(P.S);
+        P.sel = work.take<uint32_t>(P.S + 1);
+        P.einfo = work.take<skb_i4>(P.S);
+        if (!work.ok) return SKB_RUN_NEED_MORE;
+        SKB_TRY(skb_path_walk(indptr, indices, data, values, nullptr, rec, so, nullptr, N, P.S, P.su, P.se, P.ranked,
+                              nullptr, nullptr, s));
+        int r = skb_path_rank(P.ranked, buf1, nullptr, nullptr, P.S, 0, P.S, flag, s);
+        if (r < 0) return r;
+        if (r & 1) P.ranked = buf1;
+        SKB_TRY(skb_path_select(P.su, rec, P.ranked, P.S, ph, 0, P.sel, scratch, s));
+        SKB_FETCH(*n_heads, P.sel + P.S);
+        return 0;
+    };
+    Phase A{}, B{};
+    int64_t n_regular = 0, n_cycles = 0;
+    {
+        int r = run_phase(0, startoff, A, &n_regular);
+        if (r == SKB_RUN_NEED_MORE) SKB_NEED(false);
+        if (r) return r;
+    }
+    res->counts[SKB_C_STARTS] = A.S;
+    const int64_t P_cap = n_regular + E / 6 + 1;
+    int32_t* start_node = work.take<int32_t>(P_cap);
+    uint32_t* plen = work.take<uint32_t>(P_cap + 1);
+    int32_t* pmin = work.take<int32_t>(P_cap);
+    int32_t* pindptr = out.take<int32_t>(P_cap + 1);
+    SKB_NEED(work.ok && out.ok);
+    int64_t L_reg = 0;
+    if (n_regular) {
+        SKB_TRY(skb_path_heads(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin, A.einfo,
+                               nullptr, nullptr, s));
+        SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, n_regular, scratch, s));
+        SKB_FETCH(L_reg, pindptr + n_regular);
+    }
+    int64_t n_uncovered = E / 2 - (L_reg - n_regular);
+    if (n_uncovered < 0) n_uncovered = 0;
+    const int64_t L_cap = L_reg + n_uncovered + n_uncovered / 3 + 1;
+    int32_t* pidx = out.take<int32_t>(L_cap);
+    double* pdata = out.take<double>(L_cap);
+    double* pw = out.take<double>(L_cap);
+    uint8_t* covered = n_uncovered > 0 ? work.take<uint8_t>(N) : nullptr;
+    SKB_NEED(work.ok && out.ok);
+    if (covered) SKB_TRY(skb_fill_bytes(covered, 0, (size_t)N, s));
+    if (n_regular)
+        SKB_TRY(skb_path_emit(indices, data, rec, A.su, A.se, A.ranked, A.einfo, pindptr, values, covered, 0, A.S, pidx,
+                              pdata, pw, s));
+    if (n_uncovered > 0) {
+        int32_t* cpar = work.take<int32_t>(N);
+        uint32_t* startoff_b = work.take<uint32_t>(N + 1);
+        SKB_NEED(work.ok);
+        SKB_TRY(skb_cycle_roots(rec, covered, N, cpar, is_min, s));
+        SKB_TRY(skb_path_start_count(rec, covered, nullptr, N, startoff_b, scratch, s));
+        int r = run_phase(1, startoff_b, B, &n_cycles);
+        if (r == SKB_RUN_NEED_MORE) SKB_NEED(false);
+        if (r) return r;
+        if (n_cycles) {
+            SKB_TRY(skb_path_heads(B.su, rec, B.ranked, nullptr, B.sel, B.S, 1, n_regular, 0, 0, start_node, plen, pmin,
+                                   B.einfo, nullptr, nullptr, s));
+            SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, n_regular + n_cycles, scratch, s));
+            SKB_TRY(skb_path_emit(indices, data, rec, B.su, B.se, B.ranked, B.einfo, pindptr, values, nullptr, 0, B.S,
+                                  pidx, pdata, pw, s));
+        }
+    }
+    const int64_t P = n_regular + n_cycles;
+    const int64_t L = L_reg + n_uncovered + n_cycles;
+    res->counts[SKB_C_PATHS] = P;
+    res->counts[SKB_C_REGULAR] = n_regular;
+    res->counts[SKB_C_CYCLES] = n_cycles;
+    res->counts[SKB_C_ENTRIES] = L;
+    res->off[SKB_O_PINDPTR] = out_off(pindptr);
+    res->off[SKB_O_PIDX] = out_off(pidx);
+    res->off[SKB_O_PDATA] = out_off(pdata);
+    res->off[SKB_O_PW] = out_off(pw);
+    if (P == 0) {
+        res->counts[SKB_C_SYNCS] = nsync;
+        return 0;
+    }
+    // ---- skeleton ids, statistics, branch table ----------------------------------------------------------------------
+    int32_t* skel = out.take<int32_t>(P);
+    double* dist = out.take<double>(P);
+    double* mean = out.take<double>(P);
+    double* stdev = out.take<double>(P);
+    const int td = prm->table_ndim;
+    const int dh = td + height;
+    int32_t* t32 = out.take<int32_t>(3 * P);
+    int64_t* t64 = out.take<int64_t>((1 + 2 * td) * P);
+    double* tf = out.take<double>((2 * dh + 1) * P);
+    SKB_NEED(out.ok);
+    SKB_TRY(skb_skeleton_ids(pindptr, pidx, pmin, N, n_regular, P, cc_par, cc_min, is_min, skel, scratch, s));
+    SKB_TRY(skb_path_stats(pindptr, pdata, pw, P, dist, mean, stdev, s));
+    SKB_TRY(skb_branch_table(P, td, height, prm->spacing_is_int, prm->spacing_f, prm->spacing_i, pindptr, pidx, indptr,
+                             skel, coords, values, nullptr, nullptr, 0, nullptr, t32, t64, tf, s));
+    res->off[SKB_O_SKEL] = out_off(skel);
+    res->off[SKB_O_DIST] = out_off(dist);
+    res->off[SKB_O_MEAN] = out_off(mean);
+    res->off[SKB_O_STDEV] = out_off(stdev);
+    res->off[SKB_O_T32] = out_off(t32);
+    res->off[SKB_O_T64] = out_off(t64);
+    res->off[SKB_O_TF] = out_off(tf);
+    res->counts[SKB_C_SYNCS] = nsync;
+    res->work_need = work.need;
+    res->out_need = out.need;
+    return 0;
+}

@@ -36,6 +36,11 @@ static int skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t) {
     return 0;
 }
 
+static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_t) {
+    memcpy(dst, src, nbytes);
+    return 0;
+}
+
 static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t) {
     *host_out = *p;
     return 0;
@@ -132,3 +137,5 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
 }
 
 }  // extern "C"
+
+#include "skb_run.inl"

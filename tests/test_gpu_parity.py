@@ -235,3 +235,23 @@ def test_more_than_2_pow_32_voxels():
     assert np.array_equal(a.coordinates + np.array(off), b.coordinates)
     assert np.array_equal(a.paths.indices, b.paths.indices)
     assert np.array_equal(a.path_lengths(), b.path_lengths())
+
+
+@pytest.mark.parametrize('shape,valued', [((700, 900), False), ((80, 96, 112), False), ((512, 512), True)])
+def test_native_runner_equals_stagewise_sequencing(shape, valued):
+    """skb_run_image (one native call) and the per-stage Python sequencing run the same kernels in the
+    same order: every output must be bit-identical."""
+    img = walks(shape, 96, 200, seed=17, isolated=9, rings=5)
+    if valued:
+        img = (img * (np.random.default_rng(1).random(shape) + 0.5)).astype(np.float32)
+    t = torch.from_numpy(img).cuda()
+    a = _pipeline.skeleton_and_summary_device(t, spacing=1.5, device=t.device)
+    b = _pipeline.run_native(t, spacing=1.5, device=t.device)
+    pairs = [(a.graph.indptr, b.graph.indptr), (a.graph.indices, b.graph.indices), (a.graph.data, b.graph.data),
+             (a.graph.coords, b.graph.coords), (a.paths.indptr, b.paths.indptr), (a.paths.indices, b.paths.indices),
+             (a.paths.data, b.paths.data), (a.paths.skeleton_id, b.paths.skeleton_id), (a.dist, b.dist),
+             (a.mean, b.mean), (a.stdev, b.stdev), (a.table[0], b.table[0]), (a.table[1], b.table[1]),
+             (a.table[2], b.table[2])]
+    for i, (x, y) in enumerate(pairs):
+        assert torch.equal(x.view(torch.uint8) if x.dtype.is_floating_point else x,
+                           y.view(torch.uint8) if y.dtype.is_floating_point else y), i
