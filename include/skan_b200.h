@@ -235,7 +235,7 @@ int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int6
  * result->counts[SKB_C_*] the sizes (see skan_b200/csrc/skb_run.inl for the two enums). */
 typedef struct skb_run_params {
     const void* image; int32_t dtype, ndim; int64_t shape[3]; int64_t z_origin;
-    int32_t image_stack, height, pack_variant, stop_after_graph, want_values, reserved;
+    int32_t image_stack, height, pack_variant, stop_after_graph, want_values, time_sweep;
     const double* wtab;                 /* device: 27 neighbour weights (nputil.py:278-279, host-computed) */
     double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, table_ndim;
     void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;

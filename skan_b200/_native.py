@@ -72,7 +72,7 @@ class RunParams(ctypes.Structure):
     _fields_ = [('image', _vp), ('dtype', ctypes.c_int32), ('ndim', ctypes.c_int32), ('shape', _i64 * 3),
                 ('z_origin', _i64), ('image_stack', ctypes.c_int32), ('height', ctypes.c_int32),
                 ('pack_variant', ctypes.c_int32), ('stop_after_graph', ctypes.c_int32),
-                ('want_values', ctypes.c_int32), ('reserved', ctypes.c_int32), ('wtab', _vp),
+                ('want_values', ctypes.c_int32), ('time_sweep', ctypes.c_int32), ('wtab', _vp),
                 ('spacing_f', ctypes.c_double * 3), ('spacing_i', _i64 * 3), ('spacing_is_int', ctypes.c_int32),
                 ('table_ndim', ctypes.c_int32), ('work', _vp), ('work_bytes', _i64), ('out', _vp),
                 ('out_bytes', _i64), ('stream', _vp)]
@@ -90,7 +90,7 @@ RUN_OFF = {n: i for i, n in enumerate(
     ['lin', 'coords', 'values', 'degrees', 'indptr', 'indices', 'data', 'pindptr', 'pidx', 'pdata', 'pw', 'skel',
      'dist', 'mean', 'stdev', 't32', 't64', 'tf', 'comp_rank'])}
 RUN_COUNT = {n: i for i, n in enumerate(
-    ['nodes', 'edges', 'paths', 'regular', 'cycles', 'entries', 'junction_edges', 'starts', 'syncs'])}
+    ['nodes', 'edges', 'paths', 'regular', 'cycles', 'entries', 'junction_edges', 'starts', 'syncs', 'sweep_ns'])}
 
 EXPORTS = tuple(sorted(_SIGNATURES))
 

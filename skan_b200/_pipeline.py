@@ -439,6 +439,7 @@ def algorithmic_bytes(nvox, esize, ndim, n, e, p, l, valued):
 
 
 # ---- the same path through the native runner (skb_run_image): one C call per image ---------------
+TIME_SWEEP = False  # bench.py: record CUDA events around the mask sweep kernel (counts['sweep_ns'])
 _arena_cache = {}   # (device, stream) -> dict(work=tensor, out_bytes=int)
 _wtab_cache = {}
 
@@ -499,6 +500,7 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
     prm.height = int(bool(value_is_height))
     prm.pack_variant = PACK_VARIANT[pack_variant or default_pack_variant]
     prm.stop_after_graph, prm.want_values = int(bool(graph_only)), int(not is_bool)
+    prm.time_sweep = int(TIME_SWEEP)
     prm.wtab = wtab.data_ptr()
     for i in range(tdim):
         prm.spacing_f[i] = float(sp[i])

@@ -77,6 +77,31 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
     return skb_cuda_check(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
 }
 
+// CUDA events around one kernel on its launching stream (bench.py's roofline figure)
+struct SkbTimer {
+    cudaEvent_t a, b;
+};
+static int skb_timer_start(void** handle, skb_stream_t s) {
+    static thread_local SkbTimer t = {nullptr, nullptr};
+    if (!t.a) {
+        SKB_CUDA(cudaEventCreate(&t.a));
+        SKB_CUDA(cudaEventCreate(&t.b));
+    }
+    *handle = &t;
+    return skb_cuda_check(cudaEventRecord(t.a, s), "cudaEventRecord");
+}
+static int skb_timer_stop(void* handle, skb_stream_t s) {
+    return skb_cuda_check(cudaEventRecord(((SkbTimer*)handle)->b, s), "cudaEventRecord");
+}
+static int skb_timer_read_ns(void* handle, int64_t* ns) {  // call after the stream has been synchronised
+    float ms = 0.f;
+    SkbTimer* t = (SkbTimer*)handle;
+    SKB_CUDA(cudaEventSynchronize(t->b));
+    SKB_CUDA(cudaEventElapsedTime(&ms, t->a, t->b));
+    *ns = (int64_t)((double)ms * 1e6);
+    return 0;
+}
+
 static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s) {
     static thread_local int32_t* pinned = nullptr;
     if (!pinned) SKB_CUDA(cudaMallocHost((void**)&pinned, 64));

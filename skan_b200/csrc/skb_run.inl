@@ -22,7 +22,7 @@ enum {
 // indices into skb_run_result.counts
 enum {
     SKB_C_NODES = 0, SKB_C_EDGES, SKB_C_PATHS, SKB_C_REGULAR, SKB_C_CYCLES, SKB_C_ENTRIES, SKB_C_JUNCTION_EDGES,
-    SKB_C_STARTS, SKB_C_SYNCS, SKB_C_COUNT
+    SKB_C_STARTS, SKB_C_SYNCS, SKB_C_SWEEP_NS, SKB_C_COUNT
 };
 
 struct skb_run_params {
@@ -35,7 +35,7 @@ struct skb_run_params {
     int32_t pack_variant;
     int32_t stop_after_graph;  // 1: skeleton_to_csgraph only
     int32_t want_values;       // fp64 node values (non-boolean images)
-    int32_t reserved;
+    int32_t time_sweep;        // 1: counts[SKB_C_SWEEP_NS] = device time of the mask sweep kernel (events)
     const double* wtab;        // device, 27 weights
     double spacing_f[3];       // for the branch table (table_ndim entries)
     int64_t spacing_i[3];
@@ -124,10 +124,14 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SKB_TRY(skb_fill_bytes(store, 0, 16, s));
     SKB_TRY(skb_fill_bytes(store + 2 + ntiles * SKB_TILE_WORDS, 0, 16, s));
     SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)skb_scan_scratch_bytes(ntiles + 1), s));
+    void* ev = nullptr;
+    if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
     SKB_TRY(skb_pack_count(prm->image, prm->dtype, V, bits, tile_prefix, ntiles, prm->pack_variant, s));
+    if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
     SKB_TRY(skb_scan_u32_impl(tile_prefix, tile_prefix, ntiles, scratch, s));
     int64_t N;
     SKB_FETCH(N, tile_prefix + ntiles);
+    if (prm->time_sweep) SKB_TRY(skb_timer_read_ns(ev, &res->counts[SKB_C_SWEEP_NS]));
     res->counts[SKB_C_NODES] = N;
     {   // every later scan runs over at most 27 N items (nodes, half-edges, walk starts, paths)
         const int64_t bytes = skb_scan_scratch_bytes(27 * N + ntiles + 1);

@@ -41,6 +41,10 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
     return 0;
 }
 
+static int skb_timer_start(void** handle, skb_stream_t) { *handle = nullptr; return 0; }
+static int skb_timer_stop(void*, skb_stream_t) { return 0; }
+static int skb_timer_read_ns(void*, int64_t* ns) { *ns = 0; return 0; }
+
 static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t) {
     *host_out = *p;
     return 0;
