@@ -353,10 +353,15 @@ def main():
     if args.stages:
         hook = {'*': True}
         _pipeline.EVENT_HOOK = hook
+        _pipeline.TIME_SWEEP = 2
         r = step()
         sync_all()
         _pipeline.EVENT_HOOK = None
+        _pipeline.TIME_SWEEP = False
         rows = [(k, sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in hook.items() if k != '*']
+        if getattr(r, 'counts', None) and 'stage_ns' in r.counts:   # native runner: its own stage clock
+            rows = [(k, v * 1e-6, 1) for k, v in r.counts['stage_ns'].items() if k != 'start']
+            rows.append(('syncs', float(r.counts['syncs']), 0))
         if rank == 0:
             for k, t, n in sorted(rows, key=lambda x: -x[1]):
                 print(f'  {k:28s} {t:9.3f} ms  ({n} calls)', file=sys.stderr)

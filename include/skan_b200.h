@@ -240,7 +240,7 @@ typedef struct skb_run_params {
     double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, table_ndim;
     void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;
 } skb_run_params;
-typedef struct skb_run_result { int64_t counts[16]; int64_t off[32]; int64_t work_need, out_need; } skb_run_result;
+typedef struct skb_run_result { int64_t counts[16]; int64_t off[32]; int64_t work_need, out_need; int64_t stage_ns[32]; } skb_run_result;
 int skb_run_image(const skb_run_params* params /*host*/, skb_run_result* result /*host*/);
 
 #ifdef __cplusplus

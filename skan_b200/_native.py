@@ -80,7 +80,8 @@ class RunParams(ctypes.Structure):
 
 class RunResult(ctypes.Structure):
     """struct skb_run_result (include/skan_b200.h)"""
-    _fields_ = [('counts', _i64 * 16), ('off', _i64 * 32), ('work_need', _i64), ('out_need', _i64)]
+    _fields_ = [('counts', _i64 * 16), ('off', _i64 * 32), ('work_need', _i64), ('out_need', _i64),
+                ('stage_ns', _i64 * 32)]
 
 
 _SIGNATURES['skb_run_image'] = (_int, [ctypes.POINTER(RunParams), ctypes.POINTER(RunResult)])
@@ -91,6 +92,9 @@ RUN_OFF = {n: i for i, n in enumerate(
      'dist', 'mean', 'stdev', 't32', 't64', 'tf', 'comp_rank'])}
 RUN_COUNT = {n: i for i, n in enumerate(
     ['nodes', 'edges', 'paths', 'regular', 'cycles', 'entries', 'junction_edges', 'starts', 'syncs', 'sweep_ns'])}
+
+RUN_STAGES = ['start', 'sweep', 'nodes', 'raw_stencil', 'junction_count', 'junction_mst', 'degrees', 'csr_records',
+              'walk', 'rank', 'select', 'heads', 'emit', 'cycles', 'skeleton_ids', 'stats', 'table']
 
 EXPORTS = tuple(sorted(_SIGNATURES))
 

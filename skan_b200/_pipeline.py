@@ -500,7 +500,7 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
     prm.height = int(bool(value_is_height))
     prm.pack_variant = PACK_VARIANT[pack_variant or default_pack_variant]
     prm.stop_after_graph, prm.want_values = int(bool(graph_only)), int(not is_bool)
-    prm.time_sweep = int(TIME_SWEEP)
+    prm.time_sweep = int(TIME_SWEEP)   # 0, 1 (sweep kernel) or 2 (every stage boundary)
     prm.wtab = wtab.data_ptr()
     for i in range(tdim):
         prm.spacing_f[i] = float(sp[i])
@@ -529,6 +529,8 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
         raise _native.NativeError('skb_run_image kept asking for larger arenas')
     cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
     C = {k: int(res.counts[i]) for k, i in _native.RUN_COUNT.items()}
+    if prm.time_sweep == 2:
+        C['stage_ns'] = {k: int(res.stage_ns[i]) for i, k in enumerate(_native.RUN_STAGES)}
     O = {k: int(res.off[i]) for k, i in _native.RUN_OFF.items()}
     N, E, P, L = C['nodes'], C['edges'], C['paths'], C['entries']
     h = int(bool(value_is_height))

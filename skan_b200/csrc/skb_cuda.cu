@@ -77,6 +77,17 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
     return skb_cuda_check(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
 }
 
+// several device ints in one synchronisation
+static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t s) {
+    static thread_local int32_t* pinned = nullptr;
+    if (!pinned) SKB_CUDA(cudaMallocHost((void**)&pinned, 64 * 4));
+    if (n > 64) return skb_fail("too many values to fetch");
+    for (int i = 0; i < n; ++i) SKB_CUDA(cudaMemcpyAsync(pinned + i, ptrs[i], 4, cudaMemcpyDeviceToHost, s));
+    SKB_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) out[i] = pinned[i];
+    return 0;
+}
+
 // CUDA events around one kernel on its launching stream (bench.py's roofline figure)
 struct SkbTimer {
     cudaEvent_t a, b;
@@ -99,6 +110,30 @@ static int skb_timer_read_ns(void* handle, int64_t* ns) {  // call after the str
     SKB_CUDA(cudaEventSynchronize(t->b));
     SKB_CUDA(cudaEventElapsedTime(&ms, t->a, t->b));
     *ns = (int64_t)((double)ms * 1e6);
+    return 0;
+}
+
+// stage clock of the native runner (skb_run_params.time_sweep == 2): one event per stage boundary
+#define SKB_MAX_MARKS 32
+static thread_local cudaEvent_t g_skb_marks[SKB_MAX_MARKS] = {};
+static int skb_stage_mark(int idx, skb_stream_t s) {
+    if (idx < 0 || idx >= SKB_MAX_MARKS) return skb_fail("stage mark out of range");
+    if (!g_skb_marks[idx]) SKB_CUDA(cudaEventCreate(&g_skb_marks[idx]));
+    return skb_cuda_check(cudaEventRecord(g_skb_marks[idx], s), "cudaEventRecord");
+}
+static int skb_stage_read(const uint8_t* marked, int n, int64_t* ns) {  // ns[i] = time from the previous recorded mark to mark i
+    int prev = -1;
+    for (int i = 0; i < n; ++i) {
+        ns[i] = 0;
+        if (!marked[i]) continue;
+        if (prev >= 0) {
+            float ms = 0.f;
+            SKB_CUDA(cudaEventSynchronize(g_skb_marks[i]));
+            SKB_CUDA(cudaEventElapsedTime(&ms, g_skb_marks[prev], g_skb_marks[i]));
+            ns[i] = (int64_t)((double)ms * 1e6);
+        }
+        prev = i;
+    }
     return 0;
 }
 

@@ -1277,6 +1277,35 @@ struct SkbKeySkelItem {  // contribution of this rank to the skeleton id of ever
     }
 };
 
+struct SkbAnyUnfinishedItem {  // over the ranked inter-slab table: a list that never ends crosses slabs in a cycle
+    const skb_i4* table;
+    int32_t* flag;
+    SKB_HD void operator()(int64_t i) const {
+        if (skb_ld_i4(table + i).x >= 0) skb_raise(flag);
+    }
+};
+
+struct SkbAddOffsetItem {  // p[i] = q[i] + delta
+    const int32_t* q;
+    int32_t* p;
+    int32_t delta;
+    SKB_HD void operator()(int64_t i) const { p[i] = q[i] + delta; }
+};
+
+struct SkbSlabSkelFinalItem {  // skeleton ids of the paths headed on this rank, from the reduced table / the local ranks
+    const int32_t* skel_all;  // summed over ranks; this rank's regular paths start at row0
+    int64_t row0;
+    int32_t n_regular;
+    const int32_t* start_node;  // global ids
+    int32_t id_shift, comp_off, own0;
+    const uint32_t* rank;  // local exclusive scan of is_min
+    int32_t* skel;
+    SKB_HD void operator()(int64_t p) const {
+        if (p < n_regular) skel[p] = skel_all[row0 + p];
+        else skel[p] = comp_off + (int32_t)(rank[start_node[p] - id_shift] - rank[own0]);
+    }
+};
+
 struct SkbSlabStatsItem {  // over the paths headed on this rank
     const uint32_t* plen;
     const SkbAux* head_aux;

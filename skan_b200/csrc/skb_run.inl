@@ -24,6 +24,13 @@ enum {
     SKB_C_NODES = 0, SKB_C_EDGES, SKB_C_PATHS, SKB_C_REGULAR, SKB_C_CYCLES, SKB_C_ENTRIES, SKB_C_JUNCTION_EDGES,
     SKB_C_STARTS, SKB_C_SYNCS, SKB_C_SWEEP_NS, SKB_C_COUNT
 };
+// stage boundaries of skb_run_result.stage_ns (time_sweep == 2): stage_ns[i] = device time between
+// the previous boundary and boundary i, host synchronisation bubbles included
+enum {
+    SKB_M_START = 0, SKB_M_SWEEP, SKB_M_NODES, SKB_M_RAW, SKB_M_JCOUNT, SKB_M_MST, SKB_M_DEGREES, SKB_M_CSR,
+    SKB_M_WALK, SKB_M_RANK, SKB_M_SELECT, SKB_M_HEADS, SKB_M_EMIT, SKB_M_CYCLES, SKB_M_SKEL, SKB_M_STATS,
+    SKB_M_TABLE, SKB_M_COUNT
+};
 
 struct skb_run_params {
     const void* image;
@@ -35,7 +42,8 @@ struct skb_run_params {
     int32_t pack_variant;
     int32_t stop_after_graph;  // 1: skeleton_to_csgraph only
     int32_t want_values;       // fp64 node values (non-boolean images)
-    int32_t time_sweep;        // 1: counts[SKB_C_SWEEP_NS] = device time of the mask sweep kernel (events)
+    int32_t time_sweep;        // 1: counts[SKB_C_SWEEP_NS] = device time of the mask sweep kernel (events);
+                               // 2: also stage_ns[] (one event per stage boundary)
     const double* wtab;        // device, 27 weights
     double spacing_f[3];       // for the branch table (table_ndim entries)
     int64_t spacing_i[3];
@@ -51,6 +59,7 @@ struct skb_run_result {
     int64_t counts[16];
     int64_t off[32];
     int64_t work_need, out_need;
+    int64_t stage_ns[32];
 };
 
 struct SkbArena {
@@ -109,6 +118,20 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     for (int i = 0; i < 16; ++i) res->counts[i] = 0;
     for (int i = 0; i < 32; ++i) res->off[i] = -1;
     res->work_need = res->out_need = 0;
+    for (int i = 0; i < 32; ++i) res->stage_ns[i] = 0;
+    const bool stages = prm->time_sweep == 2;
+    uint8_t marked[32] = {};
+#define SKB_MARK(i)                           \
+    do {                                      \
+        if (stages) {                         \
+            SKB_TRY(skb_stage_mark((i), s));  \
+            marked[(i)] = 1;                  \
+        }                                     \
+    } while (0)
+#define SKB_MARKS_DONE()                                                          \
+    do {                                                                          \
+        if (stages) SKB_TRY(skb_stage_read(marked, SKB_M_COUNT, res->stage_ns));  \
+    } while (0)
     SkbArena work, out;
     work.init(prm->work, prm->work_bytes);
     out.init(prm->out, prm->out_bytes);
@@ -125,10 +148,12 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SKB_TRY(skb_fill_bytes(store + 2 + ntiles * SKB_TILE_WORDS, 0, 16, s));
     SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)skb_scan_scratch_bytes(ntiles + 1), s));
     void* ev = nullptr;
+    SKB_MARK(SKB_M_START);
     if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
     SKB_TRY(skb_pack_count(prm->image, prm->dtype, V, bits, tile_prefix, ntiles, prm->pack_variant, s));
     if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
     SKB_TRY(skb_scan_u32_impl(tile_prefix, tile_prefix, ntiles, scratch, s));
+    SKB_MARK(SKB_M_SWEEP);
     int64_t N;
     SKB_FETCH(N, tile_prefix + ntiles);
     if (prm->time_sweep) SKB_TRY(skb_timer_read_ns(ev, &res->counts[SKB_C_SWEEP_NS]));
@@ -150,7 +175,9 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SKB_NEED(work.ok && out.ok);
     SKB_TRY(skb_emit_nodes(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype, prm->z_origin, lin,
                            coords, values, pre256, s));
+    SKB_MARK(SKB_M_NODES);
     SKB_TRY(skb_raw_neighbors(bits, ndim, prm->shape, lin, N, prm->image_stack, nb, s));
+    SKB_MARK(SKB_M_RAW);
     res->off[SKB_O_LIN] = out_off(lin);
     res->off[SKB_O_COORDS] = out_off(coords);
     res->off[SKB_O_VALUES] = out_off(values);
@@ -158,6 +185,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     const int height = prm->height == 1 ? 1 : 0;
     SKB_TRY(skb_junction_edge_count(bits, pre256, ndim, prm->shape, lin, nb, N, 0, N, jcount, s));
     SKB_TRY(skb_scan_u32_impl(jcount, jcount, N, scratch, s));
+    SKB_MARK(SKB_M_JCOUNT);
     int64_t nej;
     SKB_FETCH(nej, jcount + N);
     res->counts[SKB_C_JUNCTION_EDGES] = nej;
@@ -184,11 +212,13 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         SKB_TRY(skb_copy_bytes(keep, nb, (size_t)N * 4, s));
         SKB_TRY(skb_mst_apply(ea, eb, ek, tree, nej, 0, N, keep, s));
     }
+    SKB_MARK(SKB_M_MST);
     // ---- CSR + node records ------------------------------------------------------------------------------
     int32_t* deg = out.take<int32_t>(N);
     int32_t* indptr = out.take<int32_t>(N + 1);
     SKB_NEED(out.ok);
     SKB_TRY(skb_degrees_indptr(keep, N, deg, indptr, scratch, s));
+    SKB_MARK(SKB_M_DEGREES);
     int64_t E;
     SKB_FETCH(E, indptr + N);
     res->counts[SKB_C_EDGES] = E;
@@ -203,12 +233,14 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SKB_NEED(work.ok && out.ok);
     SKB_TRY(skb_csr_emit(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height, prm->dtype,
                          indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min, scratch, s));
+    SKB_MARK(SKB_M_CSR);
     res->off[SKB_O_DEGREES] = out_off(deg);
     res->off[SKB_O_INDPTR] = out_off(indptr);
     res->off[SKB_O_INDICES] = out_off(indices);
     res->off[SKB_O_DATA] = out_off(data);
     res->off[SKB_O_COMP_RANK] = out_off(is_min);
     if (!paths_wanted || N == 0 || E == 0) {
+        SKB_MARKS_DONE();
         res->counts[SKB_C_SYNCS] = nsync;
         return 0;
     }
@@ -232,10 +264,13 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         if (!work.ok) return SKB_RUN_NEED_MORE;
         SKB_TRY(skb_path_walk(indptr, indices, data, values, nullptr, rec, so, nullptr, N, P.S, P.su, P.se, P.ranked,
                               nullptr, nullptr, s));
+        if (ph == 0) SKB_MARK(SKB_M_WALK);
         int r = skb_path_rank(P.ranked, buf1, nullptr, nullptr, P.S, 0, P.S, flag, s);
         if (r < 0) return r;
         if (r & 1) P.ranked = buf1;
+        if (ph == 0) SKB_MARK(SKB_M_RANK);
         SKB_TRY(skb_path_select(P.su, rec, P.ranked, P.S, ph, 0, P.sel, scratch, s));
+        if (ph == 0) SKB_MARK(SKB_M_SELECT);
         SKB_FETCH(*n_heads, P.sel + P.S);
         return 0;
     };
@@ -258,6 +293,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         SKB_TRY(skb_path_heads(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin, A.einfo,
                                nullptr, nullptr, s));
         SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, n_regular, scratch, s));
+        SKB_MARK(SKB_M_HEADS);
         SKB_FETCH(L_reg, pindptr + n_regular);
     }
     int64_t n_uncovered = E / 2 - (L_reg - n_regular);
@@ -272,6 +308,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     if (n_regular)
         SKB_TRY(skb_path_emit(indices, data, rec, A.su, A.se, A.ranked, A.einfo, pindptr, values, covered, 0, A.S, pidx,
                               pdata, pw, s));
+    SKB_MARK(SKB_M_EMIT);
     if (n_uncovered > 0) {
         int32_t* cpar = work.take<int32_t>(N);
         uint32_t* startoff_b = work.take<uint32_t>(N + 1);
@@ -289,6 +326,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
                                   pidx, pdata, pw, s));
         }
     }
+    SKB_MARK(SKB_M_CYCLES);
     const int64_t P = n_regular + n_cycles;
     const int64_t L = L_reg + n_uncovered + n_cycles;
     res->counts[SKB_C_PATHS] = P;
@@ -300,6 +338,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     res->off[SKB_O_PDATA] = out_off(pdata);
     res->off[SKB_O_PW] = out_off(pw);
     if (P == 0) {
+        SKB_MARKS_DONE();
         res->counts[SKB_C_SYNCS] = nsync;
         return 0;
     }
@@ -315,9 +354,13 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     double* tf = out.take<double>((2 * dh + 1) * P);
     SKB_NEED(out.ok);
     SKB_TRY(skb_skeleton_ids(pindptr, pidx, pmin, N, n_regular, P, cc_par, cc_min, is_min, skel, scratch, s));
+    SKB_MARK(SKB_M_SKEL);
     SKB_TRY(skb_path_stats(pindptr, pdata, pw, P, dist, mean, stdev, s));
+    SKB_MARK(SKB_M_STATS);
     SKB_TRY(skb_branch_table(P, td, height, prm->spacing_is_int, prm->spacing_f, prm->spacing_i, pindptr, pidx, indptr,
                              skel, coords, values, nullptr, nullptr, 0, nullptr, t32, t64, tf, s));
+    SKB_MARK(SKB_M_TABLE);
+    SKB_MARKS_DONE();
     res->off[SKB_O_SKEL] = out_off(skel);
     res->off[SKB_O_DIST] = out_off(dist);
     res->off[SKB_O_MEAN] = out_off(mean);

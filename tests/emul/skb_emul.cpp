@@ -41,6 +41,15 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
     return 0;
 }
 
+static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t) {
+    for (int i = 0; i < n; ++i) out[i] = *ptrs[i];
+    return 0;
+}
+static int skb_stage_mark(int, skb_stream_t) { return 0; }
+static int skb_stage_read(const uint8_t*, int n, int64_t* ns) {
+    for (int i = 0; i < n; ++i) ns[i] = 0;
+    return 0;
+}
 static int skb_timer_start(void** handle, skb_stream_t) { *handle = nullptr; return 0; }
 static int skb_timer_stop(void*, skb_stream_t) { return 0; }
 static int skb_timer_read_ns(void*, int64_t* ns) { *ns = 0; return 0; }
