@@ -170,7 +170,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='skan_b200')
     ap.add_argument('--workload', default='volume_2048', choices=sorted(WORKLOADS))
-    ap.add_argument('--pack-variant', default=None, choices=['ldg', 'tma'])
+    ap.add_argument('--pack-variant', default=None, choices=['ldg', 'tma', 'fused'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--halo', type=int, default=2, help='halo planes of the Z-slab decomposition (N > 1)')

@@ -62,6 +62,21 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
                    const int64_t* shape /*host*/, const void* image, int dtype, int64_t z_origin, int64_t* lin,
                    int64_t* coords, double* values, uint32_t* pre256, void* stream);
 
+/* Mask sweep + scan + node emission in ONE pass over the image (csr.py:1070,122-123,131-132,1088,
+ * 554-562): writes what skb_pack_count + skb_scan_u32 + skb_emit_nodes write (bits, pre256, lin,
+ * coords, values) except the tile counts, without reading the mask back.  The node arrays have room
+ * for node_cap nodes; *n_nodes (device) receives the true count N.  When N > node_cap only the first
+ * node_cap nodes were written: bits and pre256 are complete, so allocate N and call skb_tile_prefix +
+ * skb_emit_nodes.  scratch: skb_sweep_scratch_bytes(nvox) bytes, zeroed by the call itself.
+ * n_nodes: device i32[2]: [0] = N, [1] = number of waits inside the kernel that timed out (always 0
+ * unless the chunk hand-off protocol failed; the result is invalid then and the runner raises). */
+int64_t skb_sweep_scratch_bytes(int64_t nvox);
+int skb_sweep_nodes(const void* image, int dtype, int ndim, const int64_t* shape /*host*/, int64_t z_origin,
+                    uint64_t* bits, int64_t ntiles, uint32_t* pre256, int64_t node_cap, int64_t* lin, int64_t* coords,
+                    double* values, void* scratch, int32_t* n_nodes, void* stream);
+int skb_tile_prefix(const uint32_t* pre256, const int32_t* n_nodes, int64_t ntiles, uint32_t* tile_prefix,
+                    void* stream);
+
 /* Raw 3^d neighbourhood of every node as a 27-bit mask -- replaces the N x (3^d-1) neighbour
  * table and membership test of pixel_graph (csr.py:122-144).  planes_independent != 0: the image
  * is a stack of independent 2-D images (pipe.py:140-148 processes them one by one), no neighbours
@@ -239,6 +254,7 @@ typedef struct skb_run_params {
     const double* wtab;                 /* device: 27 neighbour weights (nputil.py:278-279, host-computed) */
     double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, table_ndim;
     void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;
+    int64_t node_cap_hint;              /* pack_variant 2 (fused sweep): capacity of the node arrays, 0 = V/256 + 4096 */
 } skb_run_params;
 typedef struct skb_run_result { int64_t counts[16]; int64_t off[32]; int64_t work_need, out_need; int64_t stage_ns[32]; } skb_run_result;
 int skb_run_image(const skb_run_params* params /*host*/, skb_run_result* result /*host*/);

@@ -26,6 +26,9 @@ _SIGNATURES = {
     'skb_kernel_launches': (_i64, []),
     'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
     'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'skb_sweep_scratch_bytes': (_i64, [_i64]),
+    'skb_sweep_nodes': (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_tile_prefix': (_int, [_vp, _vp, _i64, _vp, _vp]),
     'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _int, _vp, _vp]),
     'skb_junction_edge_count': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'skb_junction_edge_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int,
@@ -75,7 +78,7 @@ class RunParams(ctypes.Structure):
                 ('want_values', ctypes.c_int32), ('time_sweep', ctypes.c_int32), ('wtab', _vp),
                 ('spacing_f', ctypes.c_double * 3), ('spacing_i', _i64 * 3), ('spacing_is_int', ctypes.c_int32),
                 ('table_ndim', ctypes.c_int32), ('work', _vp), ('work_bytes', _i64), ('out', _vp),
-                ('out_bytes', _i64), ('stream', _vp)]
+                ('out_bytes', _i64), ('stream', _vp), ('node_cap_hint', _i64)]
 
 
 class RunResult(ctypes.Structure):

@@ -57,6 +57,13 @@ extern "C" {
 
 int skb_abi_version(void) { return 1; }
 
+// tile prefix (ntiles + 1 entries) of a mask whose rank structure exists already (after skb_sweep_nodes)
+int skb_tile_prefix(const uint32_t* pre256, const int32_t* n_nodes, int64_t ntiles, uint32_t* tile_prefix,
+                    void* stream) {
+    SkbTilePrefixItem it{pre256, n_nodes, ntiles, tile_prefix};
+    return skb_foreach(ntiles + 1, (skb_stream_t)stream, it);
+}
+
 // raw 3^d neighbourhood masks of the N foreground voxels            (replaces csr.py:122-144)
 int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape, const int64_t* lin, int64_t n,
                       int planes_independent, uint32_t* nb, void* stream) {

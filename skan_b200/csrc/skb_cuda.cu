@@ -182,6 +182,14 @@ __device__ __forceinline__ T skb_block_exclusive(T v, T* total) {
     return base + inc - v;
 }
 
+// Polling load of a status word another CTA publishes: the "memory" clobber keeps the compiler from
+// hoisting it out of the spin loop (it does hoist __ldcg, whose asm has no clobber).
+__device__ __forceinline__ unsigned long long skb_poll_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Single-pass u32 scan (decoupled look-back): every value is read once and written once.
 // scratch (zeroed once by the caller, reused by later scans on the same stream): word 0 = dynamic
 // tile counter (self-resetting), word 1 = unused, then one 64-bit status per tile =
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
             int64_t idx = look - lane;
             unsigned long long st;
             do {
-                st = idx >= 0 ? __ldcg(status + idx) : (tag | (SKB_ST_INCLUSIVE << 32));
+                st = idx >= 0 ? skb_poll_u64(status + idx) : (tag | (SKB_ST_INCLUSIVE << 32));
             } while (__any_sync(0xffffffffu, (st >> 34) != epoch || ((st >> 32) & 3ull) == 0ull));
             unsigned incl = __ballot_sync(0xffffffffu, ((st >> 32) & 3ull) == SKB_ST_INCLUSIVE);
             int stop = incl ? (__ffs((int)incl) - 1) : 31;
@@ -657,6 +665,433 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------- fused sweep
+// Mask sweep + device-wide scan + node emission in ONE pass over the image (variant 2, the default of
+// the native runner).  The image is the only V-proportional array; the three-kernel path above reads
+// it once and then reads the V/8-byte mask again to emit the nodes.  Here a CTA is warp-specialised:
+//   * warps 2..9 (256 "converter" threads) stream 64 Ki-voxel chunks through the TMA ring exactly like
+//     skb_pack_tma_kernel and assemble each chunk's 1024 mask words in shared memory (double-buffered);
+//   * warps 0 and 1 ("scanners", one per buffer) take a finished chunk: write its words with coalesced
+//     64-bit stores, count them, publish the count, obtain the number of foreground voxels before the
+//     chunk by decoupled look-back over one 64-bit status word per chunk, then write the rank structure
+//     and emit the chunk's nodes.
+// The look-back polls L2 behind ~20 MB of bulk loads in flight (microseconds per round trip), which is
+// why it runs beside the stream instead of inside it, and why it inspects 512 predecessors per round.
+// Chunks are handed out by a ticket counter, so every predecessor a scanner may wait for belongs to a
+// CTA that is already running.  Node arrays have a capacity (the count is only known afterwards):
+// nodes with id >= node_cap are counted but not written, and the caller falls back to skb_emit_nodes.
+#define SKB_CHUNK_VOX 65536
+#define SKB_CHUNK_WORDS 1024
+#define SKB_FUSED_THREADS 320
+#define SKB_FUSED_ROWS 8   // look-back: rows of 32 chunk statuses per round
+#define SKB_FUSED_STAGE_CAP 1536  // nodes of one chunk compacted in shared memory before emission (2.3 % density)
+
+// Every wait of the fused sweep is bounded (~2 s): a protocol error must end the kernel with a report
+// (n_out[1] = number of timed-out waits, details behind the chunk statuses), not hang the GPU.
+#define SKB_WAIT_LIMIT_CYCLES 4000000000ll
+// A waiting warp must not compete for issue slots with the scanner warps of its SM: the wait suspends the
+// thread in hardware (it resumes when the phase completes, or after this many nanoseconds to look again).
+#ifndef SKB_SUSPEND_HINT_NS
+#define SKB_SUSPEND_HINT_NS 20000u
+#endif
+__device__ __forceinline__ bool skb_mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(skb_smem_u32(bar)), "r"(parity), "r"(SKB_SUSPEND_HINT_NS)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void skb_sweep_report(unsigned long long* dbg, int32_t* n_out, int site, long long a, long long b,
+                                              long long c) {
+    const unsigned long long k = atomicAdd(dbg, 1ull);
+    if (k < 15) {
+        dbg[1 + 4 * k] = ((unsigned long long)site << 32) | blockIdx.x;
+        dbg[2 + 4 * k] = (unsigned long long)a;
+        dbg[3 + 4 * k] = (unsigned long long)b;
+        dbg[4 + 4 * k] = (unsigned long long)c;
+    }
+    atomicAdd(n_out + 1, 1);
+}
+// false = timed out, or another wait of this launch has (n_out[1] != 0): give up quickly
+__device__ __forceinline__ bool skb_mbar_wait_bounded(uint64_t* bar, uint32_t parity, const int32_t* n_out) {
+    if (skb_mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    long long next_check = 1ll << 21;  // the abort flag is one global address: poll it once per millisecond at most
+    for (;;) {
+        for (int i = 0; i < 8; ++i)
+            if (skb_mbar_try(bar, parity)) return true;
+        const long long dt = clock64() - t0;
+        if (dt > next_check) {
+            if (dt > SKB_WAIT_LIMIT_CYCLES || *(volatile const int32_t*)(n_out + 1) != 0) return false;
+            next_check = dt + (1ll << 21);
+        }
+    }
+}
+// barrier 1 over the 256 converter threads, returning the OR of `flag`
+__device__ __forceinline__ bool skb_converters_sync_or(bool flag) {
+    uint32_t out;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "bar.red.or.pred q, 1, 256, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(out)
+        : "r"((uint32_t)flag)
+        : "memory");
+    return out != 0;
+}
+
+__device__ __forceinline__ void skb_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(skb_smem_u32(bar)) : "memory");
+}
+
+#ifdef SKB_SWEEP_PROFILE
+#define SKB_PROF_T(var) const long long var = clock64()
+#define SKB_PROF_ADD(slot, cycles) \
+    do { if (blockIdx.x == SKB_SWEEP_PROFILE) atomicAdd(dbg + 64 + (slot), (unsigned long long)(cycles)); } while (0)
+#else
+#define SKB_PROF_T(var)
+#define SKB_PROF_ADD(slot, cycles)
+#endif
+
+template <int ESIZE, int STAGES>
+__global__ void __launch_bounds__(SKB_FUSED_THREADS, 3) skb_sweep_nodes_kernel(
+    const uint8_t* __restrict__ img, int64_t nvox, bool is_float, uint64_t* __restrict__ bits, int64_t nwords,
+    int64_t nchunks, SkbGeom g, int dtype, int64_t z_origin, int64_t node_cap, int64_t* __restrict__ lin,
+    int64_t* __restrict__ coords, double* __restrict__ values, uint32_t* __restrict__ pre256,
+    unsigned long long* status /* [0] = ticket counter, [1 + c] = chunk c */, int32_t* n_out) {
+    constexpr int EPV = 16 / ESIZE;                        // voxels per 16-byte piece
+    constexpr int NBITS = 64 / ESIZE;                      // voxels per converter thread and stage
+    constexpr int SV = SKB_STAGE_BYTES / ESIZE;            // voxels per stage
+    constexpr int SPC = SKB_CHUNK_VOX / SV;                // stages per chunk
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t ready_bar[2];         // converters -> scanner: chunk buffer b is complete
+    __shared__ __align__(8) uint64_t free_bar[2];          // scanner -> converters: chunk buffer b may be overwritten
+    // word w of a chunk lives in slot w + (w >> 5): rows of 32 words and runs of 32 words are both conflict-free
+    __shared__ __align__(16) uint64_t chunk_bits[2][SKB_CHUNK_WORDS + 32];
+    __shared__ long long chunk_ring[4];
+    __shared__ int32_t s_org[2][4][3];
+    __shared__ uint16_t node_stage[2][SKB_FUSED_STAGE_CAP];  // per scanner: chunk-relative offsets of the set bits, in order
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nbytes = nvox * ESIZE;
+    unsigned long long* ticket = status;
+    unsigned long long* chunk_status = status + 1;
+    unsigned long long* dbg = status + 1 + nchunks;  // 64 words: timed-out waits (see skb_sweep_report)
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) skb_mbar_init(&full_bar[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            skb_mbar_init(&ready_bar[i], 256);
+            skb_mbar_init(&free_bar[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= 2) {
+        // ================================ converters (and the TMA producer, their thread 0) ================
+        const int ct = tid - 64;
+        bool producer_done = false;
+        auto issue = [&](int64_t q) {  // converter thread 0 only
+            if (producer_done) return;
+            const int64_t n = q / SPC;
+            const int k = (int)(q % SPC);
+            long long c;
+            if (k == 0) {
+                c = (long long)atomicAdd(ticket, 1ull);
+                chunk_ring[n & 3] = c;
+                if (c >= nchunks) {
+                    chunk_ring[(n + 1) & 3] = c;  // both scanners must see the end
+                    producer_done = true;
+                    return;
+                }
+            } else {
+                c = chunk_ring[n & 3];
+            }
+            const int s = (int)(q % STAGES);
+            const int64_t off = ((int64_t)c * SPC + k) * (int64_t)SKB_STAGE_BYTES;
+            const int64_t avail = nbytes - off;
+            const uint32_t bytes = avail >= SKB_STAGE_BYTES ? (uint32_t)SKB_STAGE_BYTES : (uint32_t)(avail > 0 ? (avail & ~15LL) : 0);
+            skb_mbar_expect_tx(&full_bar[s], bytes);
+            if (bytes) skb_tma_load_1d(smem + (size_t)s * SKB_STAGE_BYTES, img + off, bytes, &full_bar[s]);
+        };
+        if (ct == 0)
+            for (int64_t q = 0; q < STAGES - 1; ++q) issue(q);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int64_t c = 0;
+        bool failed = false;
+        for (int64_t q = 0;; ++q) {
+            const int64_t n = q / SPC;
+            const int k = (int)(q % SPC);
+            const int s = (int)(q % STAGES);
+            const uint32_t parity = (uint32_t)((q / STAGES) & 1);
+            // the stage refilled here was read in iteration q-1; every converter has passed that
+            // iteration's barrier before thread 0 gets here
+            if (ct == 0) {
+                SKB_PROF_T(pf3);
+                issue(q + STAGES - 1);
+                SKB_PROF_ADD(10, clock64() - pf3);
+            }
+            if (k == 0) {
+                c = chunk_ring[n & 3];
+                if (c >= nchunks) {  // no more chunks: release both scanners (local chunks n and n + 1)
+                    for (int64_t e = n; e < n + 2; ++e) {
+                        if (e >= 2 && !skb_mbar_wait_bounded(&free_bar[e & 1], (uint32_t)(((e >> 1) - 1) & 1), n_out) && ct == 0)
+                            skb_sweep_report(dbg, n_out, 2, e, c, q);
+                        skb_mbar_arrive(&ready_bar[e & 1]);
+                    }
+                    break;
+                }
+                SKB_PROF_T(pf0);
+                if (n >= 2 && !skb_mbar_wait_bounded(&free_bar[n & 1], (uint32_t)(((n >> 1) - 1) & 1), n_out)) {
+                    failed = true;
+                    if (ct == 0) skb_sweep_report(dbg, n_out, 1, n, c, q);
+                }
+                if (ct == 0) { SKB_PROF_ADD(1, clock64() - pf0); SKB_PROF_ADD(8, 1); }
+                if (ct < 4) {  // coordinates of the origins of the chunk's four 16384-voxel tiles
+                    const int64_t r0 = (c * 4 + ct) * (int64_t)SKB_TILE_VOX;
+                    int32_t z = 0, y = 0, x = 0;
+                    if (r0 < nvox) skb_coords(g, r0, z, y, x);
+                    s_org[n & 1][ct][0] = z;
+                    s_org[n & 1][ct][1] = y;
+                    s_org[n & 1][ct][2] = x;
+                }
+            }
+            SKB_PROF_T(pf1);
+            if (!failed && !skb_mbar_wait_bounded(&full_bar[s], parity, n_out)) {
+                failed = true;
+                if (ct == 0) skb_sweep_report(dbg, n_out, 3, n, c, q);
+            }
+            if (ct == 0) SKB_PROF_ADD(0, clock64() - pf1);
+            const uint8_t* st = smem + (size_t)s * SKB_STAGE_BYTES;
+            const int64_t off = ((int64_t)c * SPC + k) * (int64_t)SKB_STAGE_BYTES;
+            const int64_t copied = (nbytes - off >= SKB_STAGE_BYTES) ? SKB_STAGE_BYTES : ((nbytes - off) > 0 ? ((nbytes - off) & ~15LL) : 0);
+            uint64_t word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int jj = (j + (lane >> 1)) & 3;  // rotation: the 8 lanes of a quarter-warp hit 32 distinct banks
+                const int boff = ct * 64 + jj * 16;
+                uint4 v;
+                if (boff + 16 <= copied) v = *(const uint4*)(st + boff);
+                else if (off + boff < nbytes) v = skb_load_tail<ESIZE>(img, off + boff, nbytes);
+                else v = make_uint4(0, 0, 0, 0);
+                word |= (uint64_t)skb_nonzero_bits<ESIZE>(v, is_float) << (jj * EPV);
+            }
+            {   // this thread's NBITS mask bits of the chunk
+                const int bit0 = k * SV + ct * NBITS;
+                uint8_t* cb = (uint8_t*)chunk_bits[n & 1] + (bit0 >> 11) * 8 + (bit0 >> 3);
+                if (NBITS == 64) *(uint64_t*)cb = word;
+                else if (NBITS == 32) *(uint32_t*)cb = (uint32_t)word;
+                else if (NBITS == 16) *(uint16_t*)cb = (uint16_t)word;
+                else *cb = (uint8_t)word;
+            }
+            if (k == SPC - 1) skb_mbar_arrive(&ready_bar[n & 1]);  // release: the chunk's words are complete
+            SKB_PROF_T(pf2);
+            if (skb_converters_sync_or(failed)) break;              // stage s fully read (or a wait timed out: stop)
+            if (ct == 0) SKB_PROF_ADD(9, clock64() - pf2);
+        }
+        return;
+    }
+
+    // ==================================== scanner of chunk buffer `warp` ====================================
+    for (int64_t n = warp;; n += 2) {
+        const int b = warp;
+        SKB_PROF_T(ps0);
+        if (!__all_sync(0xffffffffu, skb_mbar_wait_bounded(&ready_bar[b], (uint32_t)((n >> 1) & 1), n_out))) {
+            if (lane == 0) skb_sweep_report(dbg, n_out, 4, n, chunk_ring[n & 3], b);
+            break;
+        }
+        const int64_t c = chunk_ring[n & 3];
+        if (c >= nchunks) break;
+        SKB_PROF_T(ps1);
+        if (lane == 0) SKB_PROF_ADD(2, ps1 - ps0);
+        const uint64_t* cb = chunk_bits[b];
+        // pass 1: the words go to the global mask (coalesced), the chunk's count is published
+        uint32_t cnt = 0;
+        const int64_t wbase = c * SKB_CHUNK_WORDS + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const uint64_t w = cb[r * 33 + lane];
+            if (wbase + r * 32 < nwords) bits[wbase + r * 32] = w;
+        }
+        // this lane owns words 32 lane .. 32 lane + 31 (slots 33 lane + i): their count, then one warp scan per chunk
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) cnt += (uint32_t)__popcll(cb[33 * lane + i]);
+        uint32_t lane_incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, lane_incl, d);
+            if (lane >= d) lane_incl += o;
+        }
+        const uint32_t chunk_total = __shfl_sync(0xffffffffu, lane_incl, 31);
+        uint32_t excl = 0;
+        SKB_PROF_T(ps2);
+        if (lane == 0) SKB_PROF_ADD(6, ps2 - ps1);
+        if (c == 0) {
+            if (lane == 0) __stcg(chunk_status, (SKB_ST_INCLUSIVE << 32) | (unsigned long long)chunk_total);
+        } else {
+            if (lane == 0) __stcg(chunk_status + c, (SKB_ST_AGGREGATE << 32) | (unsigned long long)chunk_total);
+            // SKB_FUSED_ROWS x 32 predecessors per round, nearest first: row r = chunks look - 32 r - lane, one
+            // coalesced load per row.  Only rows that still hold an unpublished status are loaded again,
+            // after a short sleep: ~900 warps poll the same few lines of L2.
+            int64_t look = c - 1;
+            const long long t0 = clock64();
+            long long next_check = 1ll << 21;
+            for (;;) {
+                unsigned long long stw[SKB_FUSED_ROWS];
+                unsigned reload = (1u << SKB_FUSED_ROWS) - 1u;
+                uint32_t val;
+                bool found;
+                for (;;) {
+                    if (lane == 0) SKB_PROF_ADD(4, 1);
+#pragma unroll
+                    for (int r = 0; r < SKB_FUSED_ROWS; ++r) {
+                        if ((reload >> r) & 1u) {
+                            const int64_t idx = look - (r * 32 + lane);
+                            stw[r] = idx >= 0 ? skb_poll_u64(chunk_status + idx) : (SKB_ST_INCLUSIVE << 32);
+                        }
+                    }
+                    found = false;
+                    bool blocked = false;
+                    val = 0;
+                    reload = 0;
+#pragma unroll
+                    for (int r = 0; r < SKB_FUSED_ROWS; ++r) {
+                        if (!found && !blocked) {  // warp-uniform
+                            const unsigned incl = __ballot_sync(0xffffffffu, (stw[r] >> 32) == SKB_ST_INCLUSIVE);
+                            const unsigned zero = __ballot_sync(0xffffffffu, (stw[r] >> 32) == 0ull);
+                            const int stop = incl ? (__ffs((int)incl) - 1) : 31;
+                            const unsigned need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+                            if (zero & need) {  // something nearer than the first inclusive status is unpublished
+                                blocked = true;
+                                reload = 1u << r;
+                            } else {
+                                if (lane <= stop) val += (uint32_t)(stw[r] & 0xffffffffull);
+                                found = incl != 0u;
+                            }
+                        }
+                    }
+                    if (!blocked) break;
+                    __nanosleep(200);
+                    const long long dt = clock64() - t0;
+                    bool give_up = false;
+                    if (dt > next_check) {  // once per millisecond at most
+                        give_up = dt > SKB_WAIT_LIMIT_CYCLES || *(volatile int32_t*)(n_out + 1) != 0;
+                        next_check = dt + (1ll << 21);
+                    }
+                    if (__any_sync(0xffffffffu, give_up)) {
+                        if (lane == 0) skb_sweep_report(dbg, n_out, 5, c, look, reload);
+                        val = 0;
+                        found = true;  // give up: the count is wrong and the report says so
+                        break;
+                    }
+                }
+                excl += __reduce_add_sync(0xffffffffu, val);
+                if (lane == 0) SKB_PROF_ADD(5, 1);
+                if (found) break;
+                look -= 32 * SKB_FUSED_ROWS;
+            }
+            if (lane == 0) __stcg(chunk_status + c, (SKB_ST_INCLUSIVE << 32) | (unsigned long long)(excl + chunk_total));
+        }
+        if (lane == 0 && c == nchunks - 1) *n_out = (int32_t)(excl + chunk_total);
+        SKB_PROF_T(ps3);
+        if (lane == 0) SKB_PROF_ADD(3, ps3 - ps2);
+        // pass 2: rank structure and nodes; every lane walks its own 32 words (8 blocks of 256 voxels)
+        if (chunk_total == 0) {
+            if (c * 256 + 256 <= nwords / 4) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) pre256[c * 256 + r * 32 + lane] = excl;
+            } else {
+                for (int r = 0; r < 8; ++r)
+                    if (c * 256 + r * 32 + lane < nwords / 4) pre256[c * 256 + r * 32 + lane] = excl;
+            }
+        } else {
+            uint32_t id = excl + lane_incl - cnt;
+            const int64_t blk0 = c * 256 + lane * 8;
+            const bool full = (blk0 + 8) * 4 <= nwords;
+            if (chunk_total <= SKB_FUSED_STAGE_CAP) {
+                // compact the set bits (this lane knows the rank of each of its own) so that the emission
+                // below runs one node per lane with coalesced stores and few divisions
+                uint16_t* stg = node_stage[b];
+                uint32_t k = lane_incl - cnt;
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    if ((i & 3) == 0 && (full || (blk0 + (i >> 2)) * 4 < nwords)) pre256[blk0 + (i >> 2)] = excl + k;
+                    uint64_t w = cb[33 * lane + i];
+                    const uint32_t woff = (uint32_t)((lane * 32 + i) * 64);
+                    while (w) {
+                        stg[k++] = (uint16_t)(woff + (uint32_t)(__ffsll((long long)w) - 1));
+                        w &= w - 1;
+                    }
+                }
+                __syncwarp();
+                for (uint32_t i = lane; i < chunk_total; i += 32) {
+                    if ((int64_t)(excl + i) >= node_cap) break;
+                    const uint32_t o = stg[i];
+                    const int j = (int)(o >> 14);  // tile of the chunk
+                    skb_emit_one(o & 16383u, (c * 4 + j) * (int64_t)SKB_TILE_VOX,
+                                 (g.ndim == 3 ? z_origin : 0) + s_org[b][j][0], s_org[b][j][1], s_org[b][j][2], excl + i, g,
+                                 img, dtype, lin, coords, values);
+                }
+            } else {  // dense chunk: every lane walks its own words
+                const int j = lane >> 3;  // tile of the chunk
+                const int64_t r0 = (c * 4 + j) * (int64_t)SKB_TILE_VOX;
+                const int64_t z0 = (g.ndim == 3 ? z_origin : 0) + s_org[b][j][0];
+                const int32_t y0 = s_org[b][j][1], x0 = s_org[b][j][2];
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    if ((i & 3) == 0 && (full || (blk0 + (i >> 2)) * 4 < nwords)) pre256[blk0 + (i >> 2)] = id;
+                    uint64_t w = cb[33 * lane + i];
+                    const uint32_t woff = (uint32_t)(((lane & 7) * 32 + i) * 64);
+                    while (w) {
+                        if ((int64_t)id < node_cap)
+                            skb_emit_one(woff + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id, g, img, dtype,
+                                         lin, coords, values);
+                        ++id;
+                        w &= w - 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { SKB_PROF_ADD(7, clock64() - ps3); SKB_PROF_ADD(11, 1); }
+        if (lane == 0) skb_mbar_arrive(&free_bar[b]);
+    }
+}
+
+template <int ESIZE>
+static int skb_sweep_nodes_launch(const void* img, int64_t nvox, bool is_float, uint64_t* bits, int64_t ntiles,
+                                  SkbGeom g, int dtype, int64_t z_origin, int64_t node_cap, int64_t* lin,
+                                  int64_t* coords, double* values, uint32_t* pre256, void* scratch, int32_t* n_out,
+                                  skb_stream_t s) {
+    constexpr int STAGES = 3;
+    const size_t smem = (size_t)STAGES * SKB_STAGE_BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKB_CUDA(cudaFuncSetAttribute(skb_sweep_nodes_kernel<ESIZE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+        attr_set = true;
+    }
+    const int64_t nchunks = (nvox + SKB_CHUNK_VOX - 1) / SKB_CHUNK_VOX;
+    int64_t grid = (int64_t)skb_sm_count() * 3;
+    if (grid > nchunks) grid = nchunks;
+    SKB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(nchunks + 1 + 128) * 8, s));
+    SKB_CUDA(cudaMemsetAsync(n_out, 0, 8, s));
+    skb_sweep_nodes_kernel<ESIZE, STAGES><<<(unsigned)grid, SKB_FUSED_THREADS, smem, s>>>(
+        (const uint8_t*)img, nvox, is_float, bits, ntiles * SKB_TILE_WORDS, nchunks, g, dtype, z_origin, node_cap, lin,
+        coords, values, pre256, (unsigned long long*)scratch, n_out);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "sweep_nodes launch");
+}
+
 // ------------------------------------------------------------------------------- fused round loops
 // The junction MST and the two list rankings are loops of small kernels whose trip count depends on
 // the data; launched one kernel per phase they cost a host synchronisation per round.  Here each
@@ -837,6 +1272,34 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
         bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
+}
+
+// Mask sweep, scan and node emission in one pass (csr.py:1070,122-123,131-132,1088,554-562): what
+// skb_pack_count + skb_scan_u32 + skb_emit_nodes produce, except the tile counts.  lin / coords /
+// values have room for node_cap nodes; *n_nodes (device) receives the true count, and when it
+// exceeds node_cap the arrays hold the first node_cap nodes only (bits and pre256 are complete:
+// call skb_tile_prefix + skb_emit_nodes with larger arrays).  scratch: skb_sweep_scratch_bytes(nvox).
+int64_t skb_sweep_scratch_bytes(int64_t nvox) { return ((nvox + SKB_CHUNK_VOX - 1) / SKB_CHUNK_VOX + 2 + 128) * 8; }
+
+int skb_sweep_nodes(const void* image, int dtype, int ndim, const int64_t* shape, int64_t z_origin, uint64_t* bits,
+                    int64_t ntiles, uint32_t* pre256, int64_t node_cap, int64_t* lin, int64_t* coords, double* values,
+                    void* scratch, int32_t* n_nodes, void* stream) {
+    SKB_TRY(skb_check_geom(ndim, shape));
+    SkbGeom g = skb_make_geom(ndim, shape);
+    const int64_t nvox = g.nvox;
+    if (dtype < 0 || dtype >= SKB_DT_COUNT) return skb_fail("unsupported image dtype");
+    if (((uintptr_t)image & 15) != 0) return skb_fail("image pointer must be 16-byte aligned");
+    if (((uintptr_t)bits & 7) != 0) return skb_fail("mask pointer must be 8-byte aligned");
+    if (ntiles != (nvox + SKB_TILE_VOX - 1) / SKB_TILE_VOX) return skb_fail("ntiles does not match the shape");
+    skb_stream_t s = (skb_stream_t)stream;
+    if (nvox <= 0) return skb_cuda_check(cudaMemsetAsync(n_nodes, 0, 8, s), "memset");
+    bool is_float = dtype == SKB_DT_F32 || dtype == SKB_DT_F64;
+    switch (skb_dtype_size(dtype)) {
+        case 1: return skb_sweep_nodes_launch<1>(image, nvox, is_float, bits, ntiles, g, dtype, z_origin, node_cap, lin, coords, values, pre256, scratch, n_nodes, s);
+        case 2: return skb_sweep_nodes_launch<2>(image, nvox, is_float, bits, ntiles, g, dtype, z_origin, node_cap, lin, coords, values, pre256, scratch, n_nodes, s);
+        case 4: return skb_sweep_nodes_launch<4>(image, nvox, is_float, bits, ntiles, g, dtype, z_origin, node_cap, lin, coords, values, pre256, scratch, n_nodes, s);
+        default: return skb_sweep_nodes_launch<8>(image, nvox, is_float, bits, ntiles, g, dtype, z_origin, node_cap, lin, coords, values, pre256, scratch, n_nodes, s);
+    }
 }
 
 }  // extern "C"

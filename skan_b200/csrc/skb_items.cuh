@@ -1016,6 +1016,14 @@ SKB_HD void skb_union_min(int32_t* par, int32_t a, int32_t b) {
     }
 }
 
+struct SkbTilePrefixItem {  // tile_prefix[t] = nodes before tile t, read back from the rank structure
+    const uint32_t* pre256;
+    const int32_t* n_nodes;
+    int64_t ntiles;
+    uint32_t* tile_prefix;
+    SKB_HD void operator()(int64_t t) const { tile_prefix[t] = t < ntiles ? pre256[t * 64] : (uint32_t)*n_nodes; }
+};
+
 struct SkbIotaItem {
     int32_t* par;
     SKB_HD void operator()(int64_t v) const { par[v] = (int32_t)v; }

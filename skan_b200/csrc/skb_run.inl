@@ -53,6 +53,7 @@ struct skb_run_params {
     void* out;
     int64_t out_bytes;
     void* stream;
+    int64_t node_cap_hint;  // pack_variant 2: capacity of the node arrays the fused sweep writes (0 = V/256 + 4096)
 };
 
 struct skb_run_result {
@@ -137,45 +138,86 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     out.init(prm->out, prm->out_bytes);
     auto out_off = [&](const void* p) -> int64_t { return p ? (int64_t)((const uint8_t*)p - out.base) : -1; };
 
-    // ---- mask sweep, tile prefix ---------------------------------------------------------------
+    // ---- mask sweep, scan, nodes (one fused pass, or sweep -> tile scan -> node emission) ---------------
+    const bool fused = prm->pack_variant == 2;
+    const bool want_values = prm->want_values != 0;
     uint64_t* store = work.take<uint64_t>(ntiles * SKB_TILE_WORDS + 4);
-    uint32_t* tile_prefix = work.take<uint32_t>(ntiles + 1);
-    void* scratch = work.take<uint8_t>(skb_scan_scratch_bytes(ntiles + 1));
+    uint32_t* tile_prefix = fused ? nullptr : work.take<uint32_t>(ntiles + 1);
+    void* scratch = fused ? work.take<uint8_t>(skb_sweep_scratch_bytes(V))
+                          : work.take<uint8_t>(skb_scan_scratch_bytes(ntiles + 1));
     int32_t* flag = work.take<int32_t>(4);
+    int32_t* n_dev = work.take<int32_t>(4);
+    uint32_t* pre256 = work.take<uint32_t>(ntiles * 64);
     SKB_NEED(work.ok);
     uint64_t* bits = store + 2;
     SKB_TRY(skb_fill_bytes(store, 0, 16, s));
     SKB_TRY(skb_fill_bytes(store + 2 + ntiles * SKB_TILE_WORDS, 0, 16, s));
-    SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)skb_scan_scratch_bytes(ntiles + 1), s));
     void* ev = nullptr;
-    SKB_MARK(SKB_M_START);
-    if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
-    SKB_TRY(skb_pack_count(prm->image, prm->dtype, V, bits, tile_prefix, ntiles, prm->pack_variant, s));
-    if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
-    SKB_TRY(skb_scan_u32_impl(tile_prefix, tile_prefix, ntiles, scratch, s));
-    SKB_MARK(SKB_M_SWEEP);
     int64_t N;
-    SKB_FETCH(N, tile_prefix + ntiles);
+    int64_t *lin = nullptr, *coords = nullptr;
+    double* values = nullptr;
+    if (fused) {
+        int64_t node_cap = prm->node_cap_hint > 0 ? prm->node_cap_hint : V / 256 + 4096;
+        if (node_cap > V) node_cap = V;
+        const int64_t out_mark = out.off;
+        lin = out.take<int64_t>(node_cap);
+        coords = out.take<int64_t>(node_cap * ndim);
+        values = want_values ? out.take<double>(node_cap) : nullptr;
+        SKB_NEED(out.ok);
+        SKB_MARK(SKB_M_START);
+        if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
+        SKB_TRY(skb_sweep_nodes(prm->image, prm->dtype, ndim, prm->shape, prm->z_origin, bits, ntiles, pre256, node_cap,
+                                lin, coords, values, scratch, n_dev, s));
+        if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
+        SKB_MARK(SKB_M_SWEEP);
+        {
+            const int32_t* ptrs[2] = {n_dev, n_dev + 1};
+            int64_t got[2];
+            SKB_TRY(skb_fetch_i32s(ptrs, 2, got, s));
+            ++nsync;
+            N = got[0];
+            if (got[1] != 0) return skb_fail("fused sweep: a wait inside the kernel timed out (chunk hand-off protocol)");
+        }
+        if (N > node_cap) {  // the capacity guess was too small: emit again from the finished mask
+            out.off = out_mark;
+            lin = out.take<int64_t>(N);
+            coords = out.take<int64_t>(N * ndim);
+            values = want_values ? out.take<double>(N) : nullptr;
+            tile_prefix = work.take<uint32_t>(ntiles + 1);
+            SKB_NEED(work.ok && out.ok);
+            SKB_TRY(skb_tile_prefix(pre256, n_dev, ntiles, tile_prefix, s));
+            SKB_TRY(skb_emit_nodes(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype, prm->z_origin,
+                                   lin, coords, values, pre256, s));
+        }
+    } else {
+        SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)skb_scan_scratch_bytes(ntiles + 1), s));
+        SKB_MARK(SKB_M_START);
+        if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
+        SKB_TRY(skb_pack_count(prm->image, prm->dtype, V, bits, tile_prefix, ntiles, prm->pack_variant, s));
+        if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
+        SKB_TRY(skb_scan_u32_impl(tile_prefix, tile_prefix, ntiles, scratch, s));
+        SKB_MARK(SKB_M_SWEEP);
+        SKB_FETCH(N, tile_prefix + ntiles);
+        lin = out.take<int64_t>(N);
+        coords = out.take<int64_t>(N * ndim);
+        values = want_values ? out.take<double>(N) : nullptr;
+        SKB_NEED(out.ok);
+        SKB_TRY(skb_emit_nodes(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype, prm->z_origin, lin,
+                               coords, values, pre256, s));
+    }
     if (prm->time_sweep) SKB_TRY(skb_timer_read_ns(ev, &res->counts[SKB_C_SWEEP_NS]));
     res->counts[SKB_C_NODES] = N;
+    SKB_MARK(SKB_M_NODES);
     {   // every later scan runs over at most 27 N items (nodes, half-edges, walk starts, paths)
         const int64_t bytes = skb_scan_scratch_bytes(27 * N + ntiles + 1);
         scratch = work.take<uint8_t>(bytes);
         SKB_NEED(work.ok);
         SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)bytes, s));
     }
-    // ---- nodes, raw neighbourhood ------------------------------------------------------------------
-    const bool want_values = prm->want_values != 0;
-    int64_t* lin = out.take<int64_t>(N);
-    int64_t* coords = out.take<int64_t>(N * ndim);
-    double* values = want_values ? out.take<double>(N) : nullptr;
-    uint32_t* pre256 = work.take<uint32_t>(ntiles * 64);
+    // ---- raw neighbourhood -----------------------------------------------------------------------------
     uint32_t* nb = work.take<uint32_t>(N);
     uint32_t* jcount = work.take<uint32_t>(N + 1);
-    SKB_NEED(work.ok && out.ok);
-    SKB_TRY(skb_emit_nodes(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype, prm->z_origin, lin,
-                           coords, values, pre256, s));
-    SKB_MARK(SKB_M_NODES);
+    SKB_NEED(work.ok);
     SKB_TRY(skb_raw_neighbors(bits, ndim, prm->shape, lin, N, prm->image_stack, nb, s));
     SKB_MARK(SKB_M_RAW);
     res->off[SKB_O_LIN] = out_off(lin);

@@ -149,6 +149,46 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
     return 0;
 }
 
+int64_t skb_sweep_scratch_bytes(int64_t nvox) { return ((nvox + 65535) / 65536 + 2 + 64) * 8; }
+
+int skb_sweep_nodes(const void* image, int dtype, int ndim, const int64_t* shape, int64_t z_origin, uint64_t* bits,
+                    int64_t ntiles, uint32_t* pre256, int64_t node_cap, int64_t* lin, int64_t* coords, double* values,
+                    void*, int32_t* n_nodes, void*) {
+    SKB_TRY(skb_check_geom(ndim, shape));
+    SkbGeom g = skb_make_geom(ndim, shape);
+    if (dtype < 0 || dtype >= SKB_DT_COUNT) return skb_fail("unsupported image dtype");
+    if (ntiles != (g.nvox + SKB_TILE_VOX - 1) / SKB_TILE_VOX) return skb_fail("ntiles does not match the shape");
+    int64_t id = 0;
+    for (int64_t wi = 0; wi < ntiles * SKB_TILE_WORDS; ++wi) {
+        uint64_t word = 0;
+        for (int b = 0; b < 64; ++b) {
+            int64_t r = wi * 64 + b;
+            if (r < g.nvox && skb_host_nonzero(image, dtype, r)) word |= 1ull << b;
+        }
+        bits[wi] = word;
+        if ((wi & 3) == 0) pre256[wi >> 2] = (uint32_t)id;
+        while (word) {
+            int b = __builtin_ctzll(word);
+            word &= word - 1;
+            if (id < node_cap) {
+                int64_t r = wi * 64 + b;
+                lin[id] = r;
+                int32_t z, y, x;
+                skb_coords(g, r, z, y, x);
+                int64_t* c = coords + id * ndim;
+                if (ndim == 3) { c[0] = z + z_origin; c[1] = y; c[2] = x; }
+                else if (ndim == 2) { c[0] = y; c[1] = x; }
+                else c[0] = x;
+                if (values) values[id] = skb_load_value(image, dtype, r);
+            }
+            ++id;
+        }
+    }
+    n_nodes[0] = (int32_t)id;
+    n_nodes[1] = 0;
+    return 0;
+}
+
 }  // extern "C"
 
 #include "skb_run.inl"

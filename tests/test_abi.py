@@ -50,6 +50,10 @@ def test_library_is_sm100a_and_uses_tma(built_library):
     sass = subprocess.run([cuobjdump, '-sass', '-fun', '_Z19skb_pack_tma_kernelILi1ELi4EEvPKhlbPhPjl', built_library],
                           capture_output=True, text=True).stdout
     assert 'UBLKCP' in sass, 'TMA bulk copy (cp.async.bulk) not found in the sweep kernel'
+    sass = subprocess.run([cuobjdump, '-sass', '-fun',
+                           '_Z22skb_sweep_nodes_kernelILi1ELi3EEvPKhlbPmll7SkbGeomillPlS4_PdPjPyPi', built_library],
+                          capture_output=True, text=True).stdout
+    assert 'UBLKCP' in sass, 'TMA bulk copy (cp.async.bulk) not found in the fused sweep kernel'
 
 
 def test_package_has_no_cpu_fallback():

@@ -17,7 +17,7 @@ from skan_b200 import _pipeline
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['ldg', 'tma'])
+@pytest.fixture(params=['ldg', 'tma', 'fused'])
 def pack_variant(request):
     old = _pipeline.default_pack_variant
     _pipeline.default_pack_variant = request.param
