@@ -290,7 +290,12 @@ def main():
     else:
         counts = dict(nodes=r.n_nodes_total, edges=r.n_edges_total, paths=r.n_paths_total,
                       path_entries=r.n_entries_total, halo=args.halo, rank_rounds=r.rank_rounds,
-                      table_records=r.n_table, table_rounds=r.table_rounds, collectives_per_step=8)
+                      table_records=r.n_table, table_rounds=r.table_rounds)
+        if getattr(r, 'counts', None):   # native runner: exchanges through peer-mapped arenas, no collective library
+            counts.update(runner='native (skb_run_slab)', host_syncs_per_step=r.counts['syncs'],
+                          exchanges_per_step=r.counts['exchanges'], nccl_collectives_per_step=0)
+        else:
+            counts.update(runner='python (slab.py)', nccl_collectives_per_step=8)
     alg = _pipeline.algorithmic_bytes(V, esize, len(shape), counts['nodes'], counts['edges'], counts['paths'],
                                       counts['path_entries'], valued)
     del r
@@ -299,6 +304,7 @@ def main():
     hook = {'skb_pack_count': []}
     _pipeline.EVENT_HOOK = hook
     _pipeline.TIME_SWEEP = True      # the native runner times the sweep kernel with its own CUDA events
+    slab.TIME_SWEEP = True
     sweep_ns = []
     launches0 = lib.kernel_launches()
     start = torch.cuda.Event(enable_timing=True)
@@ -315,6 +321,7 @@ def main():
     clocks.__exit__()
     _pipeline.EVENT_HOOK = None
     _pipeline.TIME_SWEEP = False
+    slab.TIME_SWEEP = False
     total_ms = max_over_ranks(start.elapsed_time(stop))
     launches = int(sum_over_ranks(lib.kernel_launches() - launches0))
     ms = total_ms / args.steps

@@ -259,6 +259,31 @@ typedef struct skb_run_params {
 typedef struct skb_run_result { int64_t counts[16]; int64_t off[32]; int64_t work_need, out_need; int64_t stage_ns[32]; } skb_run_result;
 int skb_run_image(const skb_run_params* params /*host*/, skb_run_result* result /*host*/);
 
+/* ---- One volume over the GPUs of a node: Z-slab decomposition in one call per rank ------------------
+ * (the reference has no distributed layer.)  A communicator is created
+ * collectively by the ranks of ONE node: it maps a control block in POSIX shared memory (host
+ * integers: counts and barriers) and every rank's exchange arena, device memory exported with CUDA
+ * IPC, so that the kernels of a rank load the rows a peer produced in place over NVLink -- no
+ * collective library on the data path.  skb_run_slab is the native twin of skan_b200/slab.py: same
+ * kernels, same order; returns 0, 1 (an arena is too small: work_need / out_need), 2 (the exchange
+ * arena is too small: exchange_need; destroy and recreate the communicator on every rank), 3 (another
+ * rank returned 1 or failed: call skb_comm_reset on every rank between two barriers of the host's own
+ * process group and run again) or < 0. */
+int skb_comm_create(int rank, int world, const char* name /* same unique string on every rank */,
+                    int64_t exchange_bytes, void** comm_out);
+int skb_comm_destroy(void* comm);
+int skb_comm_reset(void* comm);
+int skb_comm_allgather_i64(void* comm, const int64_t* vals /*host*/, int n, int64_t* out /*host, world x n*/);
+typedef struct skb_slab_params {
+    const void* image;                  /* planes [ze0, ze0 + nz_ext) of the volume */
+    int32_t dtype, pack_variant; int64_t global_shape[3]; int64_t z0, z1, ze0, nz_ext;
+    int32_t want_values, time_sweep; const double* wtab;
+    double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, reserved;
+    void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;
+} skb_slab_params;
+typedef struct skb_slab_result { int64_t counts[32]; int64_t off[32]; int64_t work_need, out_need, exchange_need; } skb_slab_result;
+int skb_run_slab(const skb_slab_params* params /*host*/, void* comm, skb_slab_result* result /*host*/);
+
 #ifdef __cplusplus
 }
 #endif

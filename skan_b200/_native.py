@@ -89,6 +89,37 @@ class RunResult(ctypes.Structure):
 
 _SIGNATURES['skb_run_image'] = (_int, [ctypes.POINTER(RunParams), ctypes.POINTER(RunResult)])
 
+
+class SlabParams(ctypes.Structure):
+    """struct skb_slab_params (include/skan_b200.h)"""
+    _fields_ = [('image', _vp), ('dtype', ctypes.c_int32), ('pack_variant', ctypes.c_int32), ('global_shape', _i64 * 3),
+                ('z0', _i64), ('z1', _i64), ('ze0', _i64), ('nz_ext', _i64), ('want_values', ctypes.c_int32),
+                ('time_sweep', ctypes.c_int32), ('wtab', _vp), ('spacing_f', ctypes.c_double * 3),
+                ('spacing_i', _i64 * 3), ('spacing_is_int', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('work', _vp), ('work_bytes', _i64), ('out', _vp), ('out_bytes', _i64), ('stream', _vp)]
+
+
+class SlabResult(ctypes.Structure):
+    """struct skb_slab_result (include/skan_b200.h)"""
+    _fields_ = [('counts', _i64 * 32), ('off', _i64 * 32), ('work_need', _i64), ('out_need', _i64),
+                ('exchange_need', _i64)]
+
+
+_SIGNATURES['skb_comm_create'] = (_int, [_int, _int, ctypes.c_char_p, _i64, ctypes.POINTER(_vp)])
+_SIGNATURES['skb_comm_destroy'] = (_int, [_vp])
+_SIGNATURES['skb_comm_reset'] = (_int, [_vp])
+_SIGNATURES['skb_comm_allgather_i64'] = (_int, [_vp, _vp, _int, _vp])
+_SIGNATURES['skb_run_slab'] = (_int, [ctypes.POINTER(SlabParams), _vp, ctypes.POINTER(SlabResult)])
+# indices into SlabResult.off / .counts (the enums of skan_b200/csrc/skb_slab.inl)
+SLAB_OFF = {n: i for i, n in enumerate(
+    ['lin', 'coords', 'values', 'degrees', 'indptr', 'indices', 'data', 'plen', 'pidx', 'pdata', 'pw', 'dist', 'mean',
+     'stdev', 't32', 't64', 'tf', 'start_node'])}
+SLAB_COUNT = {n: i for i, n in enumerate(
+    ['nodes_ext', 'own0', 'own1', 'id_shift', 'node_offset', 'edge_offset', 'edges_owned', 'nodes_total', 'edges_total',
+     'regular', 'cycles', 'paths_total', 'entries_total', 'regular_total', 'regular_offset', 'cycle_offset',
+     'entry_off_regular', 'entry_off_cycles', 'starts', 'table_records', 'syncs', 'exchanges', 'edges_ext',
+     'sweep_ns'])}
+
 # indices into RunResult.off / .counts (the enums of skan_b200/csrc/skb_run.inl)
 RUN_OFF = {n: i for i, n in enumerate(
     ['lin', 'coords', 'values', 'degrees', 'indptr', 'indices', 'data', 'pindptr', 'pidx', 'pdata', 'pw', 'skel',

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "skb_items.cuh"
 
@@ -77,16 +78,48 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
     return skb_cuda_check(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
 }
 
-// several device ints in one synchronisation
+// several device ints in one synchronisation: a one-block kernel makes them contiguous, one copy brings them
 static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t s) {
     static thread_local int32_t* pinned = nullptr;
-    if (!pinned) SKB_CUDA(cudaMallocHost((void**)&pinned, 64 * 4));
-    if (n > 64) return skb_fail("too many values to fetch");
-    for (int i = 0; i < n; ++i) SKB_CUDA(cudaMemcpyAsync(pinned + i, ptrs[i], 4, cudaMemcpyDeviceToHost, s));
+    static thread_local int32_t* staged = nullptr;
+    if (!pinned) {
+        SKB_CUDA(cudaMallocHost((void**)&pinned, SKB_MAX_FETCH * 4));
+        SKB_CUDA(cudaMalloc((void**)&staged, SKB_MAX_FETCH * 4));
+    }
+    if (n > SKB_MAX_FETCH) return skb_fail("too many values to fetch");
+    SkbGatherI32Item it;
+    for (int i = 0; i < SKB_MAX_FETCH; ++i) it.ptr[i] = ptrs[i < n ? i : 0];
+    it.out = staged;
+    skb_foreach_kernel<SkbGatherI32Item><<<1, 32, 0, s>>>(it, n);
+    SKB_COUNT_LAUNCH(1);
+    SKB_CUDA(cudaMemcpyAsync(pinned, staged, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     SKB_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < n; ++i) out[i] = pinned[i];
     return 0;
 }
+
+static int skb_stream_sync(skb_stream_t s) { return skb_cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+
+// exchange arena of the Z-slab mode: device memory every rank of the node can read (CUDA IPC; the
+// peers map it once, kernels then load from it directly over NVLink)
+static int skb_xalloc(const char*, int, int64_t bytes, void** ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle does not fit the control block");
+    SKB_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    SKB_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    SKB_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+    memset(handle, 0, 64);
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+static int skb_xopen(const uint8_t handle[64], int64_t, void** ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    return skb_cuda_check(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+static int skb_xclose(void* ptr, int64_t) { return skb_cuda_check(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle"); }
+static int skb_xfree(void* ptr, int64_t, const char*, int) { return skb_cuda_check(cudaFree(ptr), "cudaFree"); }
+static int skb_xunlink(const char*, int) { return 0; }
 
 // CUDA events around one kernel on its launching stream (bench.py's roofline figure)
 struct SkbTimer {
@@ -1305,3 +1338,4 @@ int skb_sweep_nodes(const void* image, int dtype, int ndim, const int64_t* shape
 }  // extern "C"
 
 #include "skb_run.inl"
+#include "skb_slab.inl"

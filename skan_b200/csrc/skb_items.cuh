@@ -1314,6 +1314,41 @@ struct SkbSlabSkelFinalItem {  // skeleton ids of the paths headed on this rank,
     }
 };
 
+struct SkbSetI64Item {  // out[i] = v[i]: a few host integers as a kernel argument
+    int64_t v[8];
+    int64_t* out;
+    SKB_HD void operator()(int64_t i) const { out[i] = v[i]; }
+};
+
+#define SKB_MAX_FETCH 16
+struct SkbGatherI32Item {  // out[i] = *ptr[i]: the scalars of one host read-back, made contiguous
+    const int32_t* ptr[SKB_MAX_FETCH];
+    int32_t* out;
+    SKB_HD void operator()(int64_t i) const { out[i] = *ptr[i]; }
+};
+
+struct SkbSumSlotsItem {  // one item: out = sum of n spread counters
+    const uint32_t* in;
+    int32_t n;
+    int32_t* out;
+    SKB_HD void operator()(int64_t) const {
+        uint32_t t = 0;
+        for (int i = 0; i < n; ++i) t += in[i];
+        *out = (int32_t)t;
+    }
+};
+
+struct SkbPeerSumItem {  // dst[i] = sum over ranks of src[k][i] (every rank's contribution, read in place over NVLink)
+    const int32_t* src[SKB_MAX_RANKS];
+    int32_t n_src;
+    int32_t* dst;
+    SKB_HD void operator()(int64_t i) const {
+        int32_t t = 0;
+        for (int k = 0; k < n_src; ++k) t += src[k][i];
+        dst[i] = t;
+    }
+};
+
 struct SkbSlabStatsItem {  // over the paths headed on this rank
     const uint32_t* plen;
     const SkbAux* head_aux;

@@ -194,6 +194,147 @@ class _Exchange:
         return outs
 
 
+# ---- native runner (skb_run_slab): one C call per rank and volume -------------------------------------
+NATIVE = os.environ.get('SKAN_B200_SLAB_NATIVE', '1') != '0'   # 0: the per-stage python sequencing below
+TIME_SWEEP = False                                             # bench.py: counts['sweep_ns'] of the mask sweep
+_comms = {}     # group key -> dict(handle, bytes, lib)
+_arenas = {}    # (device, stream) -> dict(work, out_bytes)
+_wtabs = {}
+_INITIAL_ARENAS = (1 << 22, 1 << 22)   # work, out bytes of the first call (tests shrink them to exercise the retries)
+_INITIAL_EXCHANGE = None             # bytes of the exchange arena (None: SKAN_B200_EXCHANGE_MB, default 64)
+
+
+def _get_comm(ctx, group, min_bytes=0):
+    """This group's communicator (control block in shared memory + peer-mapped exchange arenas),
+    created collectively on first use and again when a volume needs a larger exchange arena."""
+    import ctypes
+    key = id(group) if group is not None else 0
+    cur = _comms.get(key)
+    if cur is not None and cur['lib'] is ctx.lib and cur['bytes'] >= min_bytes:
+        return cur
+    if cur is not None:
+        cur['lib'].call('skb_comm_destroy', cur['handle'])
+        del _comms[key]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nbytes = max(int(min_bytes), _INITIAL_EXCHANGE or (int(os.environ.get('SKAN_B200_EXCHANGE_MB', '64')) << 20))
+    name = [None]
+    if rank == 0:
+        import uuid
+        name[0] = 'g' + uuid.uuid4().hex[:20]
+    dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    handle = ctypes.c_void_p()
+    ctx.lib.call('skb_comm_create', rank, world, name[0].encode(), nbytes, ctypes.byref(handle))
+    cur = dict(handle=handle, bytes=nbytes, lib=ctx.lib)
+    _comms[key] = cur
+    import atexit
+    atexit.register(_close_comm, key)
+    return cur
+
+
+def _close_comm(key):
+    cur = _comms.pop(key, None)
+    if cur is not None:
+        try:
+            cur['lib'].call('skb_comm_destroy', cur['handle'])
+        except Exception:
+            pass
+
+
+def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, group, pack_variant):
+    """skeleton_and_summary_slab through skb_run_slab: the whole per-rank sequence in one native call."""
+    import ctypes
+    from . import _native
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ctx = _pipeline._Ctx(device)
+    img, code, shape, np_dtype = _pipeline._as_device_image(slab_image, ctx.device)
+    if len(shape) != 3:
+        raise ValueError('slab mode is for 3-D volumes')
+    is_bool = np_dtype == np.dtype(bool)
+    sp_arr = np.asarray(spacing)
+    wkey = (str(ctx.device), id(ctx.lib), sp_arr.dtype.str, tuple(np.atleast_1d(sp_arr).tolist()))
+    if wkey not in _wtabs:
+        _wtabs[wkey] = torch.from_numpy(_pipeline.neighbour_weights(3, spacing)).to(ctx.device)
+    sp = sp_arr if sp_arr.ndim else np.full(3, sp_arr)
+    sp_is_int = sp.dtype.kind in 'iub'
+    prm = _native.SlabParams()
+    prm.image, prm.dtype = img.data_ptr(), code
+    prm.pack_variant = min(1, _pipeline.PACK_VARIANT[pack_variant or _pipeline.default_pack_variant])
+    for i in range(3):
+        prm.global_shape[i] = int(global_shape[i])
+        prm.spacing_f[i] = float(sp[i])
+        prm.spacing_i[i] = int(sp[i]) if sp_is_int else 1
+    prm.z0, prm.z1, prm.ze0, prm.nz_ext = int(z0), int(z1), int(ze0), int(shape[0])
+    prm.want_values, prm.time_sweep = int(not is_bool), int(bool(TIME_SWEEP))
+    prm.wtab, prm.spacing_is_int, prm.stream = _wtabs[wkey].data_ptr(), int(sp_is_int), ctx.stream
+    V = int(np.prod(shape, dtype=np.int64))
+    akey = (str(ctx.device), ctx.stream, id(ctx.lib))
+    cache = _arenas.setdefault(akey, dict(work=None, out_bytes=_INITIAL_ARENAS[1]))
+    if cache['work'] is None:
+        cache['work'] = ctx.empty(max(_INITIAL_ARENAS[0], V // 4 + _INITIAL_ARENAS[0]), torch.uint8)
+    comm = _get_comm(ctx, group)
+    res = _native.SlabResult()
+    for _ in range(12):
+        work = cache['work']
+        out = ctx.empty(cache['out_bytes'], torch.uint8)
+        prm.work, prm.work_bytes = work.data_ptr(), work.numel()
+        prm.out, prm.out_bytes = out.data_ptr(), out.numel()
+        rc = ctx.lib.call('skb_run_slab', ctypes.byref(prm), comm['handle'], ctypes.byref(res))
+        if rc == 0:
+            break
+        # rare: some rank needs larger arenas.  The ranks agree on what happened through the process group
+        # (they no longer agree on the exchange sequence), then run again.
+        rcs = [None] * world
+        dist.all_gather_object(rcs, (int(rc), int(res.exchange_need)), group=group)
+        if rc == 1:
+            if res.work_need > work.numel():
+                cache['work'] = ctx.empty(int(res.work_need), torch.uint8)
+            if res.out_need > out.numel():
+                cache['out_bytes'] = int(res.out_need)
+        if any(r[0] == 2 for r in rcs):
+            comm = _get_comm(ctx, group, min_bytes=max(max(r[1] for r in rcs), 2 * comm['bytes']))
+        else:
+            dist.barrier(group=group)
+            ctx.lib.call('skb_comm_reset', comm['handle'])
+            dist.barrier(group=group)
+    else:
+        raise _native.NativeError('skb_run_slab kept asking for larger arenas')
+    cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
+    C = {k: int(res.counts[i]) for k, i in _native.SLAB_COUNT.items()}
+    O = {k: int(res.off[i]) for k, i in _native.SLAB_OFF.items()}
+    if C['paths_total'] == 0:
+        raise ValueError('index pointer size 0 should be 1')
+    Ne, E, Pk, L = C['nodes_ext'], C['edges_ext'], C['regular'] + C['cycles'], C['entries_total']
+    Pk1 = max(Pk, 1)
+    i32, i64, f64 = torch.int32, torch.int64, torch.float64
+
+    def view(name, count, dtype, shp=None):
+        off = O[name]
+        if off < 0:
+            return None
+        t = out[off: off + count * torch.empty(0, dtype=dtype).element_size()].view(dtype)
+        return t if shp is None else t.view(shp)
+
+    g = SimpleNamespace(ctx=ctx, shape=tuple(shape), ndim=3, np_dtype=np_dtype, n_nodes=Ne, n_edges=E,
+                        lin=view('lin', Ne, i64), coords=view('coords', Ne * 3, i64, (Ne, 3)),
+                        values=view('values', Ne, f64), degrees=view('degrees', Ne, i32),
+                        indptr=view('indptr', Ne + 1, i32), indices=view('indices', E, i32), data=view('data', E, f64),
+                        _keepalive=(img, out))
+    t32 = view('t32', 3 * Pk1, i32)[:3 * Pk].view(3, Pk)
+    t64 = view('t64', 7 * Pk1, i64)[:7 * Pk].view(7, Pk)
+    tf = view('tf', 7 * Pk1, f64)[:7 * Pk].view(7, Pk)
+    return SimpleNamespace(
+        rank=rank, world=world, graph=g, own=(C['own0'], C['own1']), id_shift=C['id_shift'],
+        n_nodes=C['own1'] - C['own0'], n_edges=C['edges_owned'], node_offset=C['node_offset'],
+        edge_offset=C['edge_offset'], n_nodes_total=C['nodes_total'], n_edges_total=C['edges_total'],
+        n_regular=C['regular'], n_cycles=C['cycles'], n_paths_total=C['paths_total'], n_entries_total=L,
+        n_regular_total=C['regular_total'], regular_offset=C['regular_offset'], cycle_offset=C['cycle_offset'],
+        path_len=view('plen', Pk + 1, i32)[:Pk], paths_indices=view('pidx', L, i32), paths_data=view('pdata', L, f64),
+        paths_weights=view('pw', L, f64), entry_offset_regular=C['entry_off_regular'],
+        entry_offset_cycles=C['entry_off_cycles'], dist=view('dist', Pk1, f64)[:Pk], mean=view('mean', Pk1, f64)[:Pk],
+        stdev=view('stdev', Pk1, f64)[:Pk], table=(t32, t64, tf), spacing_is_int=sp_is_int, rank_rounds=0,
+        table_rounds=0, n_starts=C['starts'], n_table=C['table_records'], counts=C)
+
+
 def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=1, device=None, group=None,
                               pack_variant=None):
     """Skeleton + summarize of one Z-slab of a 3-D volume, collectively over the process group.
@@ -220,6 +361,9 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     if device is None:
         from .csr import _default_device
         device = _default_device()
+    if NATIVE and _single_node(group) and world <= 16:
+        return _slab_native(slab_image, global_shape=global_shape, z0=z0, z1=z1, ze0=ze0, spacing=spacing,
+                            device=device, group=group, pack_variant=pack_variant)
     # ---- voxel and node stages on the extended slab ---------------------------------------------
     Vloc = (ze1 - ze0) * sz
     p_own0, p_own1 = (z0 - ze0) * sz, (z1 - ze0) * sz

@@ -45,6 +45,38 @@ static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_s
     for (int i = 0; i < n; ++i) out[i] = *ptrs[i];
     return 0;
 }
+static int skb_stream_sync(skb_stream_t) { return 0; }
+
+// exchange arena of the Z-slab mode: POSIX shared memory stands in for CUDA IPC device memory
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+static void skb_xname(char* out, size_t n, const char* name, int rank) { snprintf(out, n, "/skbx_%s_%d", name, rank); }
+static int skb_xmap(const char* shm, int64_t bytes, bool create, void** ptr) {
+    int fd = shm_open(shm, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return skb_fail("shm_open of an exchange arena failed");
+    if (create && ftruncate(fd, bytes) != 0) { close(fd); return skb_fail("ftruncate of an exchange arena failed"); }
+    void* p = mmap(nullptr, (size_t)bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return skb_fail("mmap of an exchange arena failed");
+    *ptr = p;
+    return 0;
+}
+static int skb_xalloc(const char* name, int rank, int64_t bytes, void** ptr, uint8_t handle[64]) {
+    memset(handle, 0, 64);
+    skb_xname((char*)handle, 64, name, rank);
+    return skb_xmap((const char*)handle, bytes, true, ptr);
+}
+static int skb_xopen(const uint8_t handle[64], int64_t bytes, void** ptr) { return skb_xmap((const char*)handle, bytes, false, ptr); }
+static int skb_xclose(void* ptr, int64_t bytes) { munmap(ptr, (size_t)bytes); return 0; }
+static int skb_xfree(void* ptr, int64_t bytes, const char*, int) { munmap(ptr, (size_t)bytes); return 0; }
+static int skb_xunlink(const char* name, int rank) {
+    char shm[64];
+    skb_xname(shm, sizeof(shm), name, rank);
+    shm_unlink(shm);
+    return 0;
+}
+
 static int skb_stage_mark(int, skb_stream_t) { return 0; }
 static int skb_stage_read(const uint8_t*, int n, int64_t* ns) {
     for (int i = 0; i < n; ++i) ns[i] = 0;
@@ -192,3 +224,4 @@ int skb_sweep_nodes(const void* image, int dtype, int ndim, const int64_t* shape
 }  // extern "C"
 
 #include "skb_run.inl"
+#include "skb_slab.inl"

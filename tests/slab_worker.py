@@ -86,12 +86,15 @@ def compare_with_oracle(img, spacing, glob):
     return ref
 
 
-def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate):
+def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate, native=1, small=0):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group(backend, rank=rank, world_size=world)
     try:
         import skan_b200
         from skan_b200 import slab
+        slab.NATIVE = bool(native)   # 1: skb_run_slab (one native call per rank), 0: the per-stage python sequencing
+        if small:   # tiny first arenas: every rank has to retry, at different points (restart protocol)
+            slab._INITIAL_ARENAS, slab._INITIAL_EXCHANGE = (4096, 4096), 4096
         img = make_volume(kind, shape, seed)
         if valued:
             rng = np.random.default_rng(seed + 1)
@@ -118,7 +121,7 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             share = {k: v.cpu().numpy() for k, v in share.items()}
             share['n_regular'] = res.n_regular
             share['meta'] = dict(rank_rounds=res.rank_rounds, table_rounds=res.table_rounds, n_table=res.n_table,
-                                 n_cycles=res.n_cycles)
+                                 n_cycles=res.n_cycles, native=hasattr(res, 'counts'))
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(share, gathered, dst=0)
         if rank == 0:
@@ -126,7 +129,7 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             ref = compare_with_oracle(img, spacing, glob)
             print(f'SLAB-OK world={world} kind={kind} shape={shape} nodes={ref.graph.shape[0]} paths={ref.n_paths} '
                   f'cycles={sum(g["meta"]["n_cycles"] for g in gathered)} table={gathered[0]["meta"]["n_table"]} '
-                  f'table_rounds={gathered[0]["meta"]["table_rounds"]}', flush=True)
+                  f'table_rounds={gathered[0]["meta"]["table_rounds"]} native={int(gathered[0]["meta"]["native"])}', flush=True)
     finally:
         dist.destroy_process_group()
 
@@ -142,8 +145,10 @@ if __name__ == '__main__':
     ap.add_argument('--backend', default='gloo')
     ap.add_argument('--emulate', type=int, default=1)
     ap.add_argument('--spacing', default='0.5,0.1,0.1')
+    ap.add_argument('--native', type=int, default=1)
+    ap.add_argument('--small-arenas', type=int, default=0)
     a = ap.parse_args()
     shape = tuple(int(x) for x in a.shape.split(','))
     spacing = tuple(float(x) for x in a.spacing.split(','))
     run(int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['MASTER_PORT']), a.kind, shape, a.seed,
-        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate))
+        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate), a.native, a.small_arenas)

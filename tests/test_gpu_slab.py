@@ -21,6 +21,14 @@ def test_slab_mode_nccl(args):
     assert 'SLAB-OK' in outs[0]
 
 
+def test_slab_mode_python_sequencing_nccl():
+    world = max(1, min(torch.cuda.device_count(), 8))
+    codes, outs = launch(world, '--kind', 'walks', '--shape', '96,64,64', '--halo', '2', '--seed', '11', '--native', '0',
+                         backend='nccl', emulate=0)
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'native=0' in outs[0]
+
+
 def test_slab_mode_two_ranks_on_one_gpu_is_rejected_or_passes():
     """With a single GPU the 2-rank run shares the device; NCCL refuses duplicate devices, so only
     run the multi-rank case when at least two GPUs are visible."""

@@ -8,6 +8,8 @@ import sys
 
 import pytest
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 WORKER = os.path.join(HERE, 'slab_worker.py')
 
@@ -41,6 +43,59 @@ def test_slab_mode_matches_oracle(world, args):
     codes, outs = launch(world, *args)
     assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
     assert 'SLAB-OK' in outs[0]
+
+
+@pytest.mark.parametrize('world,args', [
+    (2, ['--kind', 'walks', '--shape', '24,20,28', '--halo', '2']),
+    (3, ['--kind', 'dense', '--shape', '60,20,20', '--halo', '2', '--seed', '6']),
+])
+def test_slab_mode_python_sequencing_matches_oracle(world, args):
+    """The per-stage python sequencing (collectives through torch.distributed) stays covered: it is what
+    runs when the ranks are not all on one node."""
+    codes, outs = launch(world, *args, '--native', '0')
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'native=0' in outs[0]
+
+
+def test_native_runner_is_the_default():
+    codes, outs = launch(2, '--kind', 'walks', '--shape', '24,20,28', '--halo', '2', '--seed', '3')
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'native=1' in outs[0]
+
+
+def test_native_runner_restarts_when_arenas_are_too_small():
+    """Tiny work / out / exchange arenas on the first call: ranks give up at different points, the others
+    are released from their exchange (abort word), everybody grows and runs again."""
+    codes, outs = launch(3, '--kind', 'walks', '--shape', '48,32,32', '--halo', '5', '--seed', '7', '--small-arenas', '1')
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'native=1' in outs[0]
+
+
+def test_comm_allgather_between_processes():
+    """The shared-memory count channel of the native runner (skb_comm_*), three processes."""
+    code = (
+        "import os, sys, ctypes, numpy as np\n"
+        f"sys.path.insert(0, {os.path.dirname(HERE)!r}); sys.path.insert(0, {HERE!r})\n"
+        "from emul_util import build_emulation_library\n"
+        "from skan_b200 import _native\n"
+        "lib = _native.Library(build_emulation_library(), device_type='cpu')\n"
+        "r, w = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])\n"
+        "h = ctypes.c_void_p()\n"
+        "lib.call('skb_comm_create', r, w, os.environ['COMM_NAME'].encode(), 1 << 16, ctypes.byref(h))\n"
+        "for it in range(200):\n"
+        "    v = np.array([r * 1000 + it, it, -r], dtype=np.int64)\n"
+        "    out = np.zeros((w, 3), dtype=np.int64)\n"
+        "    lib.call('skb_comm_allgather_i64', h, v.ctypes.data, 3, out.ctypes.data)\n"
+        "    assert (out[:, 0] == np.arange(w) * 1000 + it).all() and (out[:, 1] == it).all() and (out[:, 2] == -np.arange(w)).all()\n"
+        "lib.call('skb_comm_destroy', h)\n"
+        "print('COMM-OK')\n")
+    from emul_util import build_emulation_library
+    build_emulation_library()
+    name = 't%08x' % random.getrandbits(32)
+    procs = [subprocess.Popen([sys.executable, '-c', code], env=dict(os.environ, RANK=str(r), WORLD_SIZE='3', COMM_NAME=name),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(3)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all('COMM-OK' in o for o in outs), '\n'.join(outs)
 
 
 def test_junction_clusters_across_slab_boundaries():
