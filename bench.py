@@ -193,7 +193,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        os.environ['NCCL_DEBUG'] = 'WARN'  # keep stdout to the one JSON line
+        os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
         dist.barrier()
     import skan_b200
@@ -340,7 +341,16 @@ def main():
                 'job': {'algorithmic_bytes': alg, 'achieved': alg / (ms * 1e-3) / 1e9,
                         'frac_of_n_gpus': alg / (ms * 1e-3) / 1e9 / (peak * world)}}
 
-    if args.timeline and world > 1:
+    if args.timeline and world > 1 and slab.NATIVE:
+        sync_all()
+        r = step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            for k, v in r.counts['host_us'].items():
+                print(f'  [host timeline, rank 0] {k:24s} +{v / 1e3:7.3f} ms', file=sys.stderr)
+            print(f'  [host timeline, rank 0] syncs {r.counts["syncs"]} exchanges {r.counts["exchanges"]}', file=sys.stderr)
+        del r
+    elif args.timeline and world > 1:
         sync_all()
         slab.TIMELINE = []
         t0 = time.perf_counter()

@@ -102,7 +102,7 @@ class SlabParams(ctypes.Structure):
 class SlabResult(ctypes.Structure):
     """struct skb_slab_result (include/skan_b200.h)"""
     _fields_ = [('counts', _i64 * 32), ('off', _i64 * 32), ('work_need', _i64), ('out_need', _i64),
-                ('exchange_need', _i64)]
+                ('exchange_need', _i64), ('host_ns', _i64 * 16)]
 
 
 _SIGNATURES['skb_comm_create'] = (_int, [_int, _int, ctypes.c_char_p, _i64, ctypes.POINTER(_vp)])
@@ -110,6 +110,8 @@ _SIGNATURES['skb_comm_destroy'] = (_int, [_vp])
 _SIGNATURES['skb_comm_reset'] = (_int, [_vp])
 _SIGNATURES['skb_comm_allgather_i64'] = (_int, [_vp, _vp, _int, _vp])
 _SIGNATURES['skb_run_slab'] = (_int, [ctypes.POINTER(SlabParams), _vp, ctypes.POINTER(SlabResult)])
+SLAB_SECTIONS = ['voxels_nodes', 'junction_mst', 'csr_records', 'walk_rank', 'table', 'covered_select', 'cycles_heads',
+                 'records', 'emit', 'skeleton_ids', 'stats_table(launch)']
 # indices into SlabResult.off / .counts (the enums of skan_b200/csrc/skb_slab.inl)
 SLAB_OFF = {n: i for i, n in enumerate(
     ['lin', 'coords', 'values', 'degrees', 'indptr', 'indices', 'data', 'plen', 'pidx', 'pdata', 'pw', 'dist', 'mean',

@@ -189,6 +189,7 @@ struct skb_slab_result {
     int64_t counts[32];
     int64_t off[32];
     int64_t work_need, out_need, exchange_need;
+    int64_t host_ns[16];  // host clock at the section boundaries (the sections end in a synchronisation), from the call's start
 };
 
 #define SKB_SNEED(cond)                                                        \
@@ -264,6 +265,13 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     const int64_t sz = NY * NX, V = g.nvox;
     const int64_t ntiles = (V + SKB_TILE_VOX - 1) / SKB_TILE_VOX;
     int64_t nsync = 0, nexch = 0;
+    const double t_call = skb_now_s();
+    int n_mark = 0;
+    for (int i = 0; i < 16; ++i) res->host_ns[i] = 0;
+#define SKB_HOST_MARK()                                                                   \
+    do {                                                                                  \
+        if (n_mark < 16) res->host_ns[n_mark++] = (int64_t)((skb_now_s() - t_call) * 1e9);  \
+    } while (0)
     for (int i = 0; i < 32; ++i) res->counts[i] = 0;
     for (int i = 0; i < 32; ++i) res->off[i] = -1;
     res->work_need = res->out_need = res->exchange_need = 0;
@@ -344,6 +352,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     }
     const int64_t own0 = pr[0], own1 = pr[1], f1 = pr[2], l0 = pr[3], hl0 = pr[4], hu1 = pr[5];
     const int64_t N_k = own1 - own0;
+    SKB_HOST_MARK();
     // ---- junction MST on the junction edges of the whole volume ----------------------------------------------
     SKB_TRY(skb_junction_edge_count(bits, pre256, 3, shape, lin, nb, Ne, own0, own1, jcount, s));
     SKB_TRY(skb_scan_u32_impl(jcount, jcount, Ne, scratch, s));
@@ -426,6 +435,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         int r = skb_mst_junctions(gea, geb, gew, nej_rows, N_total, mpar, bestw, beste, era, erb, tree, flag, s);
         if (r < 0) return r;
     }
+    SKB_HOST_MARK();
     // ---- CSR + node records + start numbering (one pass) ------------------------------------------------------
     int64_t slab[13] = {own0, own1, hl0, hu1, has_lo ? hl0 : 0, has_lo ? f1 : 0, has_hi ? l0 : 0, has_hi ? hu1 : 0,
                         0, 0, 0, 0, ze0 * sz};
@@ -489,6 +499,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     slab[9] = start_lo - so[0];
     slab[10] = start_lo;
     slab[11] = start_hi;
+    SKB_HOST_MARK();
     // ---- phase 0: lists between terminals, first inside the slab ---------------------------------------------
     const int64_t S1 = S > 0 ? S : 1, Ne1 = Ne > 0 ? Ne : 1;
     int32_t* su = work.take<int32_t>(S1);
@@ -511,6 +522,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
             raux = aux1;
         }
     }
+    SKB_HOST_MARK();
     // ---- inter-slab table ------------------------------------------------------------------------------------------
     int32_t* cross = small + 8;  // != 0: a list of the inter-slab table never ends (a cycle crossing slabs)
     SKB_TRY(skb_fill_bytes(cross, 0, 4, s));
@@ -572,6 +584,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         SKB_TRY(skb_slab_apply(ranked, raux, Tf, TAf, S, td, start_lo, start_hi, s));
         SKB_TRY(skb_foreach(n_table, s, SkbAnyUnfinishedItem{Tf, cross}));
     }
+    SKB_HOST_MARK();
     // ---- covered chain voxels, heads of the regular paths -----------------------------------------------------------
     uint8_t* covered = work.take<uint8_t>(Ne1);
     uint32_t* n_unc = work.take<uint32_t>(64);
@@ -588,6 +601,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         n_uncovered = vals[1];
         cc = vals[2] != 0;
     }
+    SKB_HOST_MARK();
     // ---- phase 1: junction-free cycles inside the slab -----------------------------------------------------------------
     int64_t Pc = 0, Sb = 0;
     int32_t *sub = nullptr, *seb = nullptr;
@@ -705,6 +719,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         res->counts[SKB_SC_EXCHANGES] = nexch;
         return 0;
     }
+    SKB_HOST_MARK();
     // ---- path records to every rank --------------------------------------------------------------------------------------
     SkbExchange exr;
     {
@@ -756,6 +771,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         SKB_TRY(skb_copy_segments(desc, s));
     }
     SKB_TRY(skb_slab_einfo(heads_all, nrec, S_total, einfo, s));
+    SKB_HOST_MARK();
     // ---- path entries: every rank writes the entries of its own voxels at their global positions ----------------------------
     SKB_TRY(skb_fill_bytes(pidx, 0, (size_t)L_total * 4, s));
     SKB_TRY(skb_fill_bytes(pdata, 0, (size_t)L_total * 8, s));
@@ -768,6 +784,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         SKB_TRY(skb_path_emit(indices, data, rec, sub, seb, rankedb, einfo_b, gptr, values, nullptr, id_shift, Sb, pidx, pdata,
                               pw, s));
     }
+    SKB_HOST_MARK();
     // ---- skeleton ids ------------------------------------------------------------------------------------------------------------
     const int64_t node_lo = Noff[rank], node_hi = Noff[rank + 1];
     SKB_TRY(skb_slab_components(links_all, nrec, S_total, kpar, kmin, node_lo, node_hi, id_shift, is_min, Ne, scratch, s));
@@ -814,6 +831,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     SKB_TRY(skb_foreach(Pk, s, SkbSlabSkelFinalItem{skel_reg, 0, (int32_t)P0, start_node, (int32_t)id_shift,
                                                    (int32_t)Coff[rank], (int32_t)own0, is_min, skel}));
     (void)cr0;
+    SKB_HOST_MARK();
     // ---- statistics and branch table of the paths headed here -----------------------------------------------------------------------
     SKB_TRY(skb_slab_path_stats(plen, head_aux, Pk, dist, mean, stdev, s));
     if (Pk)
@@ -830,6 +848,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     res->off[SKB_SO_T64] = out_off(t64);
     res->off[SKB_SO_TF] = out_off(tf);
     res->off[SKB_SO_START_NODE] = out_off(start_node);
+    SKB_HOST_MARK();
     res->counts[SKB_SC_SYNCS] = nsync;
     res->counts[SKB_SC_EXCHANGES] = nexch;
     res->work_need = work.need;

@@ -300,6 +300,11 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         raise _native.NativeError('skb_run_slab kept asking for larger arenas')
     cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
     C = {k: int(res.counts[i]) for k, i in _native.SLAB_COUNT.items()}
+    prev = 0
+    C['host_us'] = {}
+    for i, k in enumerate(_native.SLAB_SECTIONS):
+        C['host_us'][k] = (int(res.host_ns[i]) - prev) / 1e3
+        prev = int(res.host_ns[i])
     O = {k: int(res.off[i]) for k, i in _native.SLAB_OFF.items()}
     if C['paths_total'] == 0:
         raise ValueError('index pointer size 0 should be 1')
