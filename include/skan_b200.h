@@ -181,7 +181,8 @@ int skb_skeleton_ids(const int32_t* pindptr, const int32_t* pidx, const int32_t*
                      int32_t* skel_id, void* scratch, void* stream);
 
 /* Per-path statistics -- replaces _compute_distances (csr.py:962-977, left-to-right sum of pw),
- * path_means and path_stdev (csr.py:792-816; NumPy reduceat summation order).  NULL outputs are skipped. */
+ * path_means and path_stdev (csr.py:792-816; NumPy reduceat summation order).  NULL outputs are skipped.
+ * pdata NULL = boolean image: all of paths.data is 1.0, so mean = 1 and stdev = 0 exactly, nothing is read. */
 int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
                    double* mean, double* stdev, void* stream);
 

@@ -292,6 +292,7 @@ int skb_skeleton_ids(const int32_t* pindptr, const int32_t* pidx, const int32_t*
 }
 
 // branch_distance / mean / stdev per path (csr.py:962-977, 792-816); null outputs are skipped
+// pdata NULL: the image is boolean and every entry of paths.data is 1.0 (mean 1, stdev 0 without reading them)
 int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
                    double* mean, double* stdev, void* stream) {
     return skb_foreach(n_paths, (skb_stream_t)stream, SkbPathStatsItem{pindptr, pdata, pw, dist, mean, stdev});

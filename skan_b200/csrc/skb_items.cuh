@@ -1469,7 +1469,10 @@ struct SkbPathStatsItem {  // over paths
             for (int32_t j = s + 1; j < e; ++j) acc += pw[j];
             dist[p] = acc;
         }
-        if (mean || stdev) {
+        if (!pdata) {  // boolean image: every entry of paths.data is 1.0, so the mean is 1 and the variance 0, exactly
+            if (mean) mean[p] = 1.0;
+            if (stdev) stdev[p] = 0.0;
+        } else if (mean || stdev) {
             double n = (double)(e - s);
             double m = skb_np_reduceat(SkbIdLoad{pdata}, s, e - s) / n;
             if (mean) mean[p] = m;

@@ -397,7 +397,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SKB_NEED(out.ok);
     SKB_TRY(skb_skeleton_ids(pindptr, pidx, pmin, N, n_regular, P, cc_par, cc_min, is_min, skel, scratch, s));
     SKB_MARK(SKB_M_SKEL);
-    SKB_TRY(skb_path_stats(pindptr, pdata, pw, P, dist, mean, stdev, s));
+    SKB_TRY(skb_path_stats(pindptr, values ? pdata : nullptr, pw, P, dist, mean, stdev, s));
     SKB_MARK(SKB_M_STATS);
     SKB_TRY(skb_branch_table(P, td, height, prm->spacing_is_int, prm->spacing_f, prm->spacing_i, pindptr, pidx, indptr,
                              skel, coords, values, nullptr, nullptr, 0, nullptr, t32, t64, tf, s));

@@ -47,13 +47,12 @@ def test_library_is_sm100a_and_uses_tma(built_library):
         pytest.skip('cuobjdump not available')
     out = subprocess.run([cuobjdump, '-lelf', built_library], capture_output=True, text=True).stdout
     assert 'sm_100a' in out
-    sass = subprocess.run([cuobjdump, '-sass', '-fun', '_Z19skb_pack_tma_kernelILi1ELi4EEvPKhlbPhPjl', built_library],
-                          capture_output=True, text=True).stdout
-    assert 'UBLKCP' in sass, 'TMA bulk copy (cp.async.bulk) not found in the sweep kernel'
-    sass = subprocess.run([cuobjdump, '-sass', '-fun',
-                           '_Z22skb_sweep_nodes_kernelILi1ELi3EEvPKhlbPmll7SkbGeomillPlS4_PdPjPyPi', built_library],
-                          capture_output=True, text=True).stdout
-    assert 'UBLKCP' in sass, 'TMA bulk copy (cp.async.bulk) not found in the fused sweep kernel'
+    sass = subprocess.run([cuobjdump, '-sass', built_library], capture_output=True, text=True).stdout
+    functions = {part.split()[0]: part for part in sass.split('Function : ')[1:]}
+    for prefix in ('_Z19skb_pack_tma_kernelILi1E', '_Z22skb_sweep_nodes_kernelILi1E'):
+        names = [n for n in functions if n.startswith(prefix)]
+        assert names, f'{prefix}* not found in the library'
+        assert all('UBLKCP' in functions[n] for n in names), f'TMA bulk copy (cp.async.bulk) not found in {names}'
 
 
 def test_package_has_no_cpu_fallback():
