@@ -182,8 +182,8 @@ static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s) {
 // ------------------------------------------------------------------------------- scans
 // Exclusive scan with n+1 outputs (out[n] = total).  `in == out` is allowed: every block holds
 // its whole tile in registers before it writes.
-#define SKB_SCAN_THREADS 256
-#define SKB_SCAN_ITEMS 8
+#define SKB_SCAN_THREADS 512
+#define SKB_SCAN_ITEMS 16  // 8192 items per tile: the look-back chain advances ~32 tiles per L2 round trip, so fewer, larger tiles
 #define SKB_SCAN_TILE (SKB_SCAN_THREADS * SKB_SCAN_ITEMS)
 
 template <typename T>
@@ -249,11 +249,23 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
     const int64_t base = tile * SKB_SCAN_TILE + (int64_t)threadIdx.x * SKB_SCAN_ITEMS;
     uint32_t v[SKB_SCAN_ITEMS];
     uint32_t acc = 0;
+    // a thread's 16 values are 64 contiguous bytes: four 128-bit accesses when the arrays allow it
+    const bool vec = base + SKB_SCAN_ITEMS <= n && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0;
+    if (vec) {
 #pragma unroll
-    for (int j = 0; j < SKB_SCAN_ITEMS; ++j) {
-        v[j] = (base + j < n) ? in[base + j] : 0u;
-        acc += v[j];
+        for (int j = 0; j < SKB_SCAN_ITEMS / 4; ++j) {
+            const uint4 q = *(const uint4*)(in + base + 4 * j);
+            v[4 * j] = q.x;
+            v[4 * j + 1] = q.y;
+            v[4 * j + 2] = q.z;
+            v[4 * j + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SKB_SCAN_ITEMS; ++j) v[j] = (base + j < n) ? in[base + j] : 0u;
     }
+#pragma unroll
+    for (int j = 0; j < SKB_SCAN_ITEMS; ++j) acc += v[j];
     uint32_t total;
     uint32_t ex = skb_block_exclusive<uint32_t>(acc, &total);
     const unsigned long long tag = epoch << 34;
@@ -289,10 +301,23 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
     }
     __syncthreads();
     ex += s_excl;
+    if (vec) {
 #pragma unroll
-    for (int j = 0; j < SKB_SCAN_ITEMS; ++j) {
-        if (base + j < n) out[base + j] = ex;
-        ex += v[j];
+        for (int j = 0; j < SKB_SCAN_ITEMS / 4; ++j) {
+            uint4 q;
+            q.x = ex;
+            q.y = q.x + v[4 * j];
+            q.z = q.y + v[4 * j + 1];
+            q.w = q.z + v[4 * j + 2];
+            ex = q.w + v[4 * j + 3];
+            *(uint4*)(out + base + 4 * j) = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SKB_SCAN_ITEMS; ++j) {
+            if (base + j < n) out[base + j] = ex;
+            ex += v[j];
+        }
     }
     if (tile == nb - 1 && threadIdx.x == SKB_SCAN_THREADS - 1) out[n] = ex;
 }

@@ -611,11 +611,10 @@ struct SkbStartCountItem {  // over nodes
     SkbSlab sl;
     uint32_t* count;
     SKB_HD void operator()(int64_t v) const {
-        skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
         uint32_t c = 0;
-        if ((int32_t)v >= sl.own0 && (int32_t)v < sl.own1) {
-            if (r.w & SKB_REC_CYCLE_ROOT) c = 2;
-            else if ((r.w & SKB_REC_SPLITTER) && !covered[v]) c = 2;
+        if ((int32_t)v >= sl.own0 && (int32_t)v < sl.own1 && !covered[v]) {  // cycle roots are uncovered nodes too
+            skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
+            if (r.w & (SKB_REC_CYCLE_ROOT | SKB_REC_SPLITTER)) c = 2;
         }
         count[v] = c;
     }
@@ -952,7 +951,7 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
     const skb_i4* einfo;     // indexed by the id of the reversed last start: (path id, half-edges, base, -)
     const int32_t* pindptr;  // null: the entry offset of the path is einfo.z
     const double* values;    // null -> 1.0 (csr.py:207-215)
-    uint8_t* covered;        // may be null; chain nodes written are marked
+    uint8_t* covered;        // may be null; every node written is marked (what stays 0 is on no path headed at a terminal)
     int32_t id_shift;
     int32_t* pidx;
     double* pdata;
@@ -970,6 +969,7 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
             pidx[base] = u + id_shift;
             pdata[base] = values ? values[u] : 1.0;
             pw[base] = 0.0;
+            if (covered) covered[u] = 1;
         }
         int32_t prev = u, cur = indices[arc];
         double w_in = gdata[arc];  // weight of the edge arriving at `cur`; later ones come with the records
@@ -981,7 +981,7 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
             pdata[base + pos] = values ? values[cur] : 1.0;
             pw[base + pos] = w_in;
             if (r.w != 2) {
-                if (covered && (r.w & SKB_REC_DEG_MASK) == 2) covered[cur] = 1;
+                if (covered) covered[cur] = 1;
                 break;
             }
             if (covered) covered[cur] = 1;
@@ -1034,8 +1034,9 @@ struct SkbCycleHookItem {  // over nodes: uncovered degree-2 nodes join their sm
     const uint8_t* covered;
     int32_t* par;
     SKB_HD void operator()(int64_t v) const {
+        if (covered[v]) return;  // one byte decides for all but the few uncovered nodes: the 32-byte record stays unread
         skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
-        if ((r.w & SKB_REC_DEG_MASK) != 2 || covered[v]) return;
+        if ((r.w & SKB_REC_DEG_MASK) != 2) return;
         if (r.x < (int32_t)v) skb_union_min(par, (int32_t)v, r.x);
         if (r.y < (int32_t)v) skb_union_min(par, (int32_t)v, r.y);
     }
@@ -1047,8 +1048,9 @@ struct SkbCycleRootItem {  // over nodes: the minimum of every cycle becomes its
     int32_t* par;
     uint32_t* is_min;  // a junction-free cycle is a component of its own (csr.py:909)
     SKB_HD void operator()(int64_t v) const {
+        if (covered[v]) return;
         skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)v);
-        if ((r.w & SKB_REC_DEG_MASK) != 2 || covered[v]) return;
+        if ((r.w & SKB_REC_DEG_MASK) != 2) return;
         if (skb_find(par, (int32_t)v) == (int32_t)v) {
             rec[2 * (int64_t)v].w |= SKB_REC_CYCLE_ROOT;
             is_min[v] = 1u;
