@@ -16,6 +16,10 @@
         if (_e != 0) return _e;  \
     } while (0)
 
+#ifndef SKB_RANK_WALK_CAP
+#define SKB_RANK_WALK_CAP 48  // hops of the list-following pass before the synchronous pointer-jumping rounds take over
+#endif
+
 static SkbGeom skb_make_geom(int ndim, const int64_t* shape) {
     SkbGeom g;
     int64_t s[3] = {1, 1, 1};
@@ -206,12 +210,25 @@ int skb_path_rank(skb_i4* buf0, skb_i4* buf1, void* aux0, void* aux1, int64_t n_
                   int32_t* flag, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     if (n_starts <= 0) return 0;
+    // one pass in which every start follows its (short) list: buf0 -> buf1; flag[3] != 0 afterwards means
+    // that some list is longer than the hop limit and the synchronous rounds have to finish the job
+    SKB_TRY(skb_fill_bytes(flag, 0, 16, s));
+    SKB_TRY(skb_foreach(n_starts, s,
+                        SkbRankWalkItem{buf0, buf1, (const SkbAux*)aux0, (SkbAux*)aux1, (int32_t)lo, (int32_t)hi,
+                                        SKB_RANK_WALK_CAP, flag + 3}));
 #ifdef SKB_HAVE_FUSED_LOOPS
-    return skb_rank_run(buf0, buf1, (SkbAux*)aux0, (SkbAux*)aux1, n_starts, (int32_t)lo, (int32_t)hi, flag, s);
+    // the cooperative kernel returns at once when flag[3] is 0, else it runs the rounds with buf1 as its buffer 0
+    SKB_TRY(skb_rank_run(buf1, buf0, (SkbAux*)aux1, (SkbAux*)aux0, n_starts, (int32_t)lo, (int32_t)hi, flag, s));
+    return 1;
 #else
+    {
+        int32_t unfinished = 0;
+        SKB_TRY(skb_fetch_i32(flag + 3, &unfinished, s));
+        if (!unfinished) return 1;
+    }
     skb_i4* b[2] = {buf0, buf1};
     SkbAux* a[2] = {(SkbAux*)aux0, (SkbAux*)aux1};
-    int cur = 0, rounds = 0;
+    int cur = 1, rounds = 0;
     const int blind = 3;  // rounds run before the first host check (lists of up to 8 starts)
     for (;; ++rounds) {
         if (rounds > 40) return skb_fail("list ranking did not converge");

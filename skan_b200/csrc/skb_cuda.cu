@@ -1231,6 +1231,9 @@ __device__ __forceinline__ void skb_rank_rounds(cg::grid_group& grid, Jump jump,
 __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_rank_coop_kernel(skb_i4* b0, skb_i4* b1, SkbAux* a0,
                                                                          SkbAux* a1, int64_t n, int32_t lo,
                                                                          int32_t hi, int32_t* flags) {
+    // flags[3] == 0: the list-following pass (SkbRankWalkItem) finished every list, nothing to do.  Every
+    // thread reads the same value: nobody writes flags[3] before the last grid barrier below.
+    if (*(volatile int32_t*)(flags + 3) == 0) return;
     cg::grid_group grid = cg::this_grid();
     SkbJumpItem jump{b0, b1, a0, a1, lo, hi, flags};
     skb_rank_rounds(grid, jump, b0, b1, a0, a1, n, flags);

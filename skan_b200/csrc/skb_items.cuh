@@ -776,6 +776,46 @@ struct SkbJumpItem {
     }
 };
 
+// The lists are short (a few starts each: one per terminal half-edge plus one per sampled chain voxel), so
+// before any synchronous round every start simply follows its list, up to `cap` hops, reading the
+// unmodified records of src: most lists are finished by this one pass.  A start whose list closes on
+// itself lies on a junction-free cycle and stays as it is (phase 1 handles it); a start that is still
+// inside [lo, hi) after cap hops raises *unfinished and the synchronous rounds take over from dst.
+struct SkbRankWalkItem {
+    const skb_i4* src;
+    skb_i4* dst;
+    const SkbAux* aux_src;  // may be null
+    SkbAux* aux_dst;
+    int32_t lo, hi, cap;
+    int32_t* unfinished;
+    SKB_HD void operator()(int64_t s) const {
+        skb_i4 a = skb_ld_i4(src + s);
+        SkbAux A;
+        if (aux_src) A = aux_src[s];
+        const int32_t self = (int32_t)s + lo;
+        int32_t hops = 0;
+        while (a.x >= lo && a.x < hi && a.x != self) {
+            if (hops == cap) {
+                skb_raise(unfinished);
+                break;
+            }
+            const int32_t i = a.x - lo;
+            skb_i4 b = skb_ld_i4(src + i);
+            a.y += b.y;
+            if (b.z < a.z) a.z = b.z;
+            a.x = b.x;
+            if (aux_src) skb_aux_append(A, aux_src[i]);
+            ++hops;
+        }
+        if (a.x == self) {  // a cycle: leave the start untouched (x >= 0 marks it as never-ending)
+            a = skb_ld_i4(src + s);
+            if (aux_src) A = aux_src[s];
+        }
+        skb_st_i4(dst + s, a);
+        if (aux_src) aux_dst[s] = A;
+    }
+};
+
 // ---- inter-slab level: the starts leaving slab-boundary planes, gathered from every rank -----
 // table T = for rank 0, 1, ...: [starts of its first owned plane | starts of its last owned plane]
 #define SKB_MAX_RANKS 16
