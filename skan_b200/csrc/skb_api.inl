@@ -272,7 +272,8 @@ int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, c
                                     (SkbAux*)head_aux});
 }
 
-// second local walk: paths.indices i32[L], paths.data f64[L] (csr.py:396,402; values NULL -> 1.0),
+// second local walk: paths.indices i32[L], paths.data f64[L] (csr.py:396,402; values NULL -> 1.0;
+// pdata NULL -> not written: the caller fills the ones of a boolean image in one coalesced pass),
 // pw f64[L] = weight of the edge arriving at each entry; chain nodes written are marked in
 // covered u8[n] when it is given.  einfo is indexed by the id of a list's reversed last start;
 // pindptr NULL means the entry offset of a path is einfo.z (slabs).

@@ -1007,7 +1007,7 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
         int32_t arc = se[s];
         if (pos == 0) {
             pidx[base] = u + id_shift;
-            pdata[base] = values ? values[u] : 1.0;
+            if (pdata) pdata[base] = values ? values[u] : 1.0;
             pw[base] = 0.0;
             if (covered) covered[u] = 1;
         }
@@ -1018,7 +1018,7 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
             const skb_i4* rp = rec + 2 * (int64_t)cur;
             skb_i4 r = skb_ld_i4(rp);
             pidx[base + pos] = cur + id_shift;
-            pdata[base + pos] = values ? values[cur] : 1.0;
+            if (pdata) pdata[base + pos] = values ? values[cur] : 1.0;
             pw[base + pos] = w_in;
             if (r.w != 2) {
                 if (covered) covered[cur] = 1;
@@ -1052,6 +1052,32 @@ SKB_HD void skb_union_min(int32_t* par, int32_t a, int32_t b) {
             b = t;
         }
         // larger root goes under the smaller one: the root stays the component minimum
+        if (skb_atomic_cas_i32(par + a, a, b) == a) return;
+    }
+}
+
+// Union by a pseudo-random priority instead of by id: linking roots in id order builds chains as deep as the
+// component is large (find then costs one dependent load per level); random linking keeps the trees shallow.
+// For callers that do not need the root to be the component minimum.
+SKB_HD uint32_t skb_mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+SKB_HD void skb_union_rand(int32_t* par, int32_t a, int32_t b) {
+    for (;;) {
+        a = skb_find(par, a);
+        b = skb_find(par, b);
+        if (a == b) return;
+        const uint32_t ha = skb_mix32((uint32_t)a), hb = skb_mix32((uint32_t)b);
+        if (ha < hb || (ha == hb && a < b)) {
+            int32_t t = a;
+            a = b;
+            b = t;
+        }
         if (skb_atomic_cas_i32(par + a, a, b) == a) return;
     }
 }
@@ -1107,7 +1133,7 @@ struct SkbCcPathUnionItem {  // over regular paths
     const int32_t* pidx;
     int32_t* par;
     SKB_HD void operator()(int64_t p) const {
-        skb_union_min(par, pidx[pindptr[p]], pidx[pindptr[p + 1] - 1]);
+        skb_union_rand(par, pidx[pindptr[p]], pidx[pindptr[p + 1] - 1]);  // cmin, not the root, carries the minimum
     }
 };
 
@@ -1119,7 +1145,10 @@ struct SkbCcPathMinItem {  // over regular paths, after all unions
     int32_t* cmin;
     SKB_HD void operator()(int64_t p) const {
         int32_t r = skb_find(par, pidx[pindptr[p]]);
-        skb_atomic_min_u32((uint32_t*)cmin + r, (uint32_t)pmin[p]);
+        // thousands of paths of one large component would queue on one address: the value only decreases, so a
+        // plain look first lets all but the few that still lower it skip the atomic
+        const uint32_t m = (uint32_t)pmin[p];
+        if ((uint32_t)skb_ld_cg(cmin + r) > m) skb_atomic_min_u32((uint32_t*)cmin + r, m);
     }
 };
 
@@ -1354,6 +1383,12 @@ struct SkbSlabSkelFinalItem {  // skeleton ids of the paths headed on this rank,
         if (p < n_regular) skel[p] = skel_all[row0 + p];
         else skel[p] = comp_off + (int32_t)(rank[start_node[p] - id_shift] - rank[own0]);
     }
+};
+
+struct SkbFillF64Item {  // out[i] = v (paths.data of a boolean image is all ones: one coalesced fill)
+    double* out;
+    double v;
+    SKB_HD void operator()(int64_t i) const { out[i] = v; }
 };
 
 struct SkbSetI64Item {  // out[i] = v[i]: a few host integers as a kernel argument

@@ -347,9 +347,13 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     uint8_t* covered = n_uncovered > 0 ? work.take<uint8_t>(N) : nullptr;
     SKB_NEED(work.ok && out.ok);
     if (covered) SKB_TRY(skb_fill_bytes(covered, 0, (size_t)N, s));
+    // boolean image: paths.data is all ones (csr.py:207-215) -- one coalesced fill instead of a scattered 8-byte
+    // store per path entry in the walks below
+    double* pdata_w = values ? pdata : nullptr;
+    if (!values) SKB_TRY(skb_foreach(L_cap, s, SkbFillF64Item{pdata, 1.0}));
     if (n_regular)
         SKB_TRY(skb_path_emit(indices, data, rec, A.su, A.se, A.ranked, A.einfo, pindptr, values, covered, 0, A.S, pidx,
-                              pdata, pw, s));
+                              pdata_w, pw, s));
     SKB_MARK(SKB_M_EMIT);
     if (n_uncovered > 0) {
         int32_t* cpar = work.take<int32_t>(N);
@@ -365,7 +369,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
                                    B.einfo, nullptr, nullptr, s));
             SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, n_regular + n_cycles, scratch, s));
             SKB_TRY(skb_path_emit(indices, data, rec, B.su, B.se, B.ranked, B.einfo, pindptr, values, nullptr, 0, B.S,
-                                  pidx, pdata, pw, s));
+                                  pidx, pdata_w, pw, s));
         }
     }
     SKB_MARK(SKB_M_CYCLES);
