@@ -44,6 +44,24 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(workload, kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of the same workload (profiles/r01_ncu_full_<workload>.csv), or None."""
+    import csv
+    path = os.path.join(ROOT, 'profiles', f'r01_ncu_full_{workload}.csv')
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ni, ri, wi = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+        scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+        for d in rows[2:]:
+            if kernel_prefix in d[ni]:
+                return int(float(d[ri]) * scale[units[ri]] + float(d[wi]) * scale[units[wi]])
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -335,7 +353,9 @@ def main():
     peak, peak_src = load_peaks()
     achieved = V_local * esize / (pack_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': f'skb_pack_{_pipeline.default_pack_variant}_kernel<{esize}>',
-                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': ncu_traffic(args.workload, f'skb_pack_{_pipeline.default_pack_variant}_kernel<{esize},')
+                if world == 1 else None,
                 'peak_source': peak_src, 'kernel_ms': pack_ms, 'kernel_share_of_step': pack_ms / ms,
                 'algorithmic_bytes_per_launch': V_local * esize,
                 'job': {'algorithmic_bytes': alg, 'achieved': alg / (ms * 1e-3) / 1e9,

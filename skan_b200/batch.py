@@ -34,7 +34,7 @@ def stack_device(images, *, spacing=1, device=None, pack_variant=None):
     node_off = torch.searchsorted(lin, bounds).tolist()
     from types import SimpleNamespace
     return SimpleNamespace(graph=g, paths=p, dist=r.dist, mean=r.mean, stdev=r.stdev, table=r.table,
-                           spacing_is_int=r.spacing_is_int, node_offsets=node_off, n_images=B)
+                           spacing_is_int=r.spacing_is_int, node_offsets=node_off, n_images=B, counts=r.counts)
 
 
 def summarize_images(images, *, spacing=1, separator='_', device=None):
