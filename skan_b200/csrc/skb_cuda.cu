@@ -78,27 +78,67 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
     return skb_cuda_check(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync");
 }
 
-// several device ints in one synchronisation: a one-block kernel makes them contiguous, one copy brings them
-static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t s) {
-    static thread_local int32_t* pinned = nullptr;
-    static thread_local int32_t* staged = nullptr;
-    if (!pinned) {
-        SKB_CUDA(cudaMallocHost((void**)&pinned, SKB_MAX_FETCH * 4));
-        SKB_CUDA(cudaMalloc((void**)&staged, SKB_MAX_FETCH * 4));
+// Host read-back of a few device ints -- the only places where the host waits for the device.  A one-warp
+// kernel writes the values straight into mapped pinned host memory and then a sequence number; the host
+// spins on that word.  Compared with cudaMemcpyAsync + cudaStreamSynchronize this saves the copy engine
+// round trip and the driver's wake-up on each of the 8-13 read-backs of a step.  The stream is checked
+// from time to time so that a failed kernel is reported instead of being waited for.
+struct SkbMailbox {
+    volatile int32_t* host;  // [0..SKB_MAX_FETCH) values, [SKB_MAX_FETCH] sequence number
+    int32_t* dev;            // the same memory as the device sees it
+    int32_t seq;
+};
+static int skb_mailbox(SkbMailbox** out) {
+    static thread_local SkbMailbox box = {nullptr, nullptr, 0};
+    if (!box.host) {
+        void* h = nullptr;
+        SKB_CUDA(cudaHostAlloc(&h, (SKB_MAX_FETCH + 1) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h, 0, (SKB_MAX_FETCH + 1) * 4);
+        void* d = nullptr;
+        SKB_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+        box.host = (volatile int32_t*)h;
+        box.dev = (int32_t*)d;
     }
-    if (n > SKB_MAX_FETCH) return skb_fail("too many values to fetch");
-    SkbGatherI32Item it;
-    for (int i = 0; i < SKB_MAX_FETCH; ++i) it.ptr[i] = ptrs[i < n ? i : 0];
-    it.out = staged;
-    skb_foreach_kernel<SkbGatherI32Item><<<1, 32, 0, s>>>(it, n);
-    SKB_COUNT_LAUNCH(1);
-    SKB_CUDA(cudaMemcpyAsync(pinned, staged, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    SKB_CUDA(cudaStreamSynchronize(s));
-    for (int i = 0; i < n; ++i) out[i] = pinned[i];
+    *out = &box;
     return 0;
 }
 
-static int skb_stream_sync(skb_stream_t s) { return skb_cuda_check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+__global__ void skb_mail_kernel(SkbGatherI32Item it, int n, int32_t seq) {
+    const int lane = threadIdx.x;
+    if (lane < n) it.out[lane] = *it.ptr[lane];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *(volatile int32_t*)(it.out + SKB_MAX_FETCH) = seq;
+}
+
+static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t s) {
+    if (n > SKB_MAX_FETCH) return skb_fail("too many values to fetch");
+    SkbMailbox* box;
+    {
+        int e = skb_mailbox(&box);
+        if (e) return e;
+    }
+    SkbGatherI32Item it;
+    for (int i = 0; i < SKB_MAX_FETCH; ++i) it.ptr[i] = n ? ptrs[i < n ? i : 0] : nullptr;
+    it.out = box->dev;
+    const int32_t seq = ++box->seq;
+    skb_mail_kernel<<<1, 32, 0, s>>>(it, n, seq);
+    SKB_COUNT_LAUNCH(1);
+    SKB_CUDA(cudaGetLastError());
+    for (unsigned spins = 1;; ++spins) {
+        if (box->host[SKB_MAX_FETCH] == seq) break;
+        if ((spins & 0xfffffu) == 0) {  // ~ every few milliseconds: is the stream still alive?
+            cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return skb_cuda_check(e, "read-back");
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    for (int i = 0; i < n; ++i) out[i] = box->host[i];
+    return 0;
+}
+
+// everything enqueued on the stream so far has completed (an empty read-back)
+static int skb_stream_sync(skb_stream_t s) { return skb_fetch_i32s(nullptr, 0, nullptr, s); }
 
 // exchange arena of the Z-slab mode: device memory every rank of the node can read (CUDA IPC; the
 // peers map it once, kernels then load from it directly over NVLink)
@@ -171,12 +211,10 @@ static int skb_stage_read(const uint8_t* marked, int n, int64_t* ns) {  // ns[i]
 }
 
 static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s) {
-    static thread_local int32_t* pinned = nullptr;
-    if (!pinned) SKB_CUDA(cudaMallocHost((void**)&pinned, 64));
-    SKB_CUDA(cudaMemcpyAsync(pinned, p, 4, cudaMemcpyDeviceToHost, s));
-    SKB_CUDA(cudaStreamSynchronize(s));
-    *host_out = *pinned;
-    return 0;
+    int64_t v = 0;
+    int r = skb_fetch_i32s(&p, 1, &v, s);
+    *host_out = (int32_t)v;
+    return r;
 }
 
 // ------------------------------------------------------------------------------- scans
