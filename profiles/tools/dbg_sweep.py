@@ -1,5 +1,5 @@
 import sys, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 import __graft_entry__ as g; g.build()
 from skan_b200 import _pipeline
 dev = torch.device('cuda', 0)

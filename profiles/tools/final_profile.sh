@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-1 final captures on one GPU: tests, bench lines, ncu launch list, ncu --set full of one pass
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 timeout 250 python -m pytest tests -m gpu -x -q > $O/r01c_tests.log 2>&1; tail -2 $O/r01c_tests.log
 timeout 200 python bench.py --stages > $O/r01c_bench_volume_2048_n1.json 2> $O/r01c_bench_volume_2048_n1.err; echo bench rc=$?

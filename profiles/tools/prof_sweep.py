@@ -1,6 +1,6 @@
 """In-kernel cycle counters of the fused sweep (library built with -DSKB_SWEEP_PROFILE=<cta>)."""
 import sys, time, numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from skan_b200 import _native, _pipeline
 lib = _native.Library(sys.argv[1], device_type='cuda')
 _native._install_library_for_tests(lib)

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from skan_b200 import _native, _pipeline
 dev = torch.device('cuda', 0)
 ctx = _pipeline._Ctx(dev)

@@ -1312,7 +1312,7 @@ struct SkbKeyUnionItem {  // over the gathered links
     SKB_HD void operator()(int64_t p) const {
         skb_i4 l = skb_ld_i4(link + p);
         if (l.x < 0) return;  // padding
-        skb_union_min(par, l.x, l.y);
+        skb_union_rand(par, l.x, l.y);  // cmin, not the root, carries the minimum
     }
 };
 struct SkbKeyMinItem {
@@ -1322,7 +1322,8 @@ struct SkbKeyMinItem {
     SKB_HD void operator()(int64_t p) const {
         skb_i4 l = skb_ld_i4(link + p);
         if (l.x < 0) return;
-        skb_atomic_min_u32((uint32_t*)cmin + skb_find(par, l.x), (uint32_t)l.z);
+        const int32_t r = skb_find(par, l.x);
+        if ((uint32_t)skb_ld_cg(cmin + r) > (uint32_t)l.z) skb_atomic_min_u32((uint32_t*)cmin + r, (uint32_t)l.z);
     }
 };
 struct SkbKeyMarkItem {  // component minima that are nodes of this rank
