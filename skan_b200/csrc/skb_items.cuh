@@ -1398,6 +1398,169 @@ struct SkbSetI64Item {  // out[i] = v[i]: a few host integers as a kernel argume
     SKB_HD void operator()(int64_t i) const { out[i] = v[i]; }
 };
 
+// ---- Z-slab mode: junction-free cycles that touch a slab boundary ------------------------------------
+// Rare, and not worth a second two-level ranking: every rank exports its uncovered owned chain voxels
+// (48 bytes each), all ranks gather them in rank order (= ascending global id) and solve the same small
+// problem: union-find over the records, one ring per root; the rank that owns a ring's minimum node
+// emits the whole ring by walking it once (csr.py:369-386: [s, smaller neighbour of s, ..., s]).
+struct alignas(16) SkbRingRec {
+    int32_t gid, gn0, gn1, pad;  // global ids of the voxel and of its two neighbours
+    double w0, w1, value;        // weights of the edges to gn0 / gn1, node value (1.0 for boolean images)
+};
+
+struct SkbRingFlagItem {  // over nodes: flag[v] = owned, degree 2, not covered by a terminal-started list
+    const skb_i4* rec;
+    const uint8_t* covered;
+    int32_t own0, own1;
+    uint32_t* flag;
+    SKB_HD void operator()(int64_t v) const {
+        uint32_t f = 0;
+        if ((int32_t)v >= own0 && (int32_t)v < own1 && !covered[v])
+            f = (skb_ld_i4(rec + 2 * v).w & SKB_REC_DEG_MASK) == 2 ? 1u : 0u;
+        flag[v] = f;
+    }
+};
+
+struct SkbRingExportItem {  // over nodes, after the scan of the flags (pos[v+1] > pos[v] <=> flagged)
+    const skb_i4* rec;
+    const uint32_t* pos;
+    const double* values;  // may be null
+    int32_t id_shift;
+    int64_t cap;           // rows of the send buffer; rows beyond the flagged count get gid = -1
+    SkbRingRec* out;
+    SKB_HD void operator()(int64_t v) const {
+        if (pos[v + 1] == pos[v] || (int64_t)pos[v] >= cap) return;
+        skb_i4 r = skb_ld_i4(rec + 2 * v);
+        skb_d2 w = skb_ld_d2(rec + 2 * v + 1);
+        SkbRingRec o;
+        o.gid = (int32_t)v + id_shift;
+        o.gn0 = r.x + id_shift;
+        o.gn1 = r.y + id_shift;
+        o.pad = 0;
+        o.w0 = w.x;
+        o.w1 = w.y;
+        o.value = values ? values[v] : 1.0;
+        out[pos[v]] = o;
+    }
+};
+
+SKB_HD int32_t skb_ring_find(const SkbRingRec* R, int32_t m, int32_t gid) {  // index of the record of gid, or -1
+    int32_t lo = 0, hi = m - 1;
+    while (lo <= hi) {
+        int32_t mid = (lo + hi) >> 1;
+        int32_t g = R[mid].gid;
+        if (g == gid) return mid;
+        if (g < gid) lo = mid + 1;
+        else hi = mid - 1;
+    }
+    return -1;
+}
+
+struct SkbRingHookItem {  // over records: join the smaller neighbours (par initialised to the identity)
+    const SkbRingRec* R;
+    int32_t m;
+    int32_t* par;
+    int32_t* bad;  // raised when a neighbour is missing: the exported set is not a union of rings
+    SKB_HD void operator()(int64_t i) const {
+        const int32_t n[2] = {R[i].gn0, R[i].gn1};
+        for (int k = 0; k < 2; ++k) {
+            int32_t j = skb_ring_find(R, m, n[k]);
+            if (j < 0) skb_raise(bad);
+            else if (j < (int32_t)i) skb_union_min(par, (int32_t)i, j);
+        }
+    }
+};
+
+struct SkbRingSizeItem {  // over records: size[root] += 1; owned[i] = record i is the root of a ring headed on this rank
+    const SkbRingRec* R;
+    int32_t* par;
+    int32_t node_lo, node_hi;
+    uint32_t* size;   // zeroed
+    uint32_t* owned;  // m + 1 entries, scanned afterwards
+    SKB_HD void operator()(int64_t i) const {
+        int32_t r = skb_find(par, (int32_t)i);
+#if defined(__CUDA_ARCH__)
+        atomicAdd(size + r, 1u);
+#else
+        size[r] += 1u;
+#endif
+        owned[i] = (r == (int32_t)i && R[i].gid >= node_lo && R[i].gid < node_hi) ? 1u : 0u;
+    }
+};
+
+struct SkbRingHeadItem {  // over records: the rings headed here become paths pid_base + rank
+    const SkbRingRec* R;
+    const uint32_t* size;
+    const uint32_t* oidx;  // scanned `owned`
+    int32_t pid_base, id_shift;
+    int32_t* start_node;
+    uint32_t* plen;
+    int32_t* pmin;
+    uint32_t* is_min;  // a junction-free cycle is a component of its own (csr.py:909)
+    SKB_HD void operator()(int64_t i) const {
+        if (oidx[i + 1] == oidx[i]) return;
+        const int32_t pid = pid_base + (int32_t)oidx[i];
+        start_node[pid] = R[i].gid;
+        plen[pid] = size[i] + 1u;
+        pmin[pid] = R[i].gid;
+        is_min[R[i].gid - id_shift] = 1u;
+    }
+};
+
+struct SkbRingWalkItem {  // over records: the owner of a ring writes all its entries and its sums
+    const SkbRingRec* R;
+    int32_t m;
+    const uint32_t* oidx;
+    int32_t pid_base, id_shift;
+    const int32_t* gptr;  // global entry offset of every path headed here
+    const int64_t* lin;   // local raveled indices
+    int64_t lin_offset;
+    int32_t* pidx;
+    double* pdata;
+    double* pw;
+    SkbAux* head_aux;
+    SKB_HD void operator()(int64_t i) const {
+        if (oidx[i + 1] == oidx[i]) return;
+        const int32_t pid = pid_base + (int32_t)oidx[i];
+        int64_t at = gptr[pid];
+        const SkbRingRec s = R[i];
+        SkbAux a;
+        a.sw = 0.0;
+        a.sx = s.value;
+        a.sxx = s.value * s.value;
+        pidx[at] = s.gid;
+        pdata[at] = s.value;
+        pw[at] = 0.0;
+        ++at;
+        // towards the smaller neighbour first
+        int32_t prev = s.gid;
+        int32_t cur = s.gn0 < s.gn1 ? s.gn0 : s.gn1;
+        double w_in = s.gn0 < s.gn1 ? s.w0 : s.w1;
+        for (int32_t steps = 0; steps <= m; ++steps) {
+            const int32_t j = cur == s.gid ? (int32_t)i : skb_ring_find(R, m, cur);
+            const SkbRingRec c = R[j];
+            pidx[at] = c.gid;
+            pdata[at] = c.value;
+            pw[at] = w_in;
+            ++at;
+            a.sw += w_in;
+            a.sx += c.value;
+            a.sxx += c.value * c.value;
+            if (c.gid == s.gid) break;
+            const bool via0 = c.gn0 != prev;
+            prev = c.gid;
+            cur = via0 ? c.gn0 : c.gn1;
+            w_in = via0 ? c.w0 : c.w1;
+        }
+        a.end_lin = lin[s.gid - id_shift] + lin_offset;
+        a.end_node = s.gid;
+        a.end_deg = 2;
+        a.end_key = 0;
+        a.pad = 0;
+        head_aux[pid] = a;
+    }
+};
+
 #define SKB_MAX_FETCH 16
 struct SkbGatherI32Item {  // out[i] = *ptr[i]: the scalars of one host read-back, made contiguous
     const int32_t* ptr[SKB_MAX_FETCH];

@@ -602,13 +602,83 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         cc = vals[2] != 0;
     }
     SKB_HOST_MARK();
-    // ---- phase 1: junction-free cycles inside the slab -----------------------------------------------------------------
+    // ---- phase 1: junction-free cycles -----------------------------------------------------------------------------------
+    // All ranks agree first whether some ring touches a slab boundary (a list of the inter-slab table that never
+    // ends).  If none does, every ring lies inside one slab and the parallel machinery of phase 0 runs again on
+    // the uncovered voxels.  Otherwise (rare) every rank exports its uncovered chain voxels, all ranks gather them
+    // and the rank that owns a ring's minimum node emits the whole ring (SkbRing*Item).
     int64_t Pc = 0, Sb = 0;
     int32_t *sub = nullptr, *seb = nullptr;
     skb_i4* rankedb = nullptr;
     SkbAux* rauxb = nullptr;
     uint32_t* selb = nullptr;
-    if (n_uncovered > 0) {
+    bool ring_mode = false;
+    int64_t ring_m = 0, unc_of[SKB_MAX_RANKS], max_unc = 0;
+    SkbRingRec* ring_rec = nullptr;
+    uint32_t *ring_size = nullptr, *ring_oidx = nullptr;
+    const int64_t node_lo = Noff[rank], node_hi = Noff[rank + 1];
+    {
+        const int64_t v[2] = {cc, n_uncovered};
+        SKB_TRY(skb_comm_allgather(comm, v, 2, all));
+        ++nexch;
+        for (int k = 0; k < world; ++k) {
+            if (all[2 * k]) ring_mode = true;
+            unc_of[k] = all[2 * k + 1];
+            ring_m += unc_of[k];
+            if (unc_of[k] > max_unc) max_unc = unc_of[k];
+        }
+    }
+    if (ring_mode && ring_m > 0) {
+        SkbExchange exq;
+        const int64_t rbq[1] = {(int64_t)sizeof(SkbRingRec)};
+        exq.init(comm, &xoff, max_unc, 1, rbq);
+        if (!exq.ok) {
+            res->exchange_need = 4 * xoff + (1 << 22);
+            return SKB_RUN_NEED_EXCHANGE;
+        }
+        uint32_t* rflag = work.take<uint32_t>(Ne + 1);
+        ring_rec = work.take<SkbRingRec>(ring_m);
+        int32_t* rpar = work.take<int32_t>(ring_m);
+        ring_size = work.take<uint32_t>(ring_m);
+        ring_oidx = work.take<uint32_t>(ring_m + 1);
+        SKB_SNEED(work.ok);
+        SKB_TRY(skb_foreach(Ne, s, SkbRingFlagItem{rec, covered, (int32_t)own0, (int32_t)own1, rflag}));
+        SKB_TRY(skb_scan_u32_impl(rflag, rflag, Ne, scratch, s));
+        SKB_TRY(skb_foreach(Ne, s, SkbRingExportItem{rec, rflag, values, (int32_t)id_shift, exq.cap, (SkbRingRec*)exq.mine(0)}));
+        SKB_TRY(skb_stream_sync(s));
+        ++nsync;
+        {
+            const int64_t one = 1;
+            SKB_TRY(skb_comm_allgather(comm, &one, 1, all));
+            ++nexch;
+        }
+        {   // exactly unc_of[k] records of rank k, in rank order = ascending global id
+            int64_t desc[1 + 3 * SKB_MAX_RANKS];
+            int n = 0;
+            int64_t at = 0;
+            for (int k = 0; k < world; ++k) {
+                if (!unc_of[k]) continue;
+                desc[1 + 3 * n] = (int64_t)(uintptr_t)exq.field(0, k);
+                desc[2 + 3 * n] = (int64_t)(uintptr_t)(ring_rec + at);
+                desc[3 + 3 * n] = unc_of[k] * (int64_t)sizeof(SkbRingRec);
+                at += unc_of[k];
+                ++n;
+            }
+            desc[0] = n;
+            SKB_TRY(skb_copy_segments(desc, s));
+        }
+        int32_t* bad = small + 10;
+        SKB_TRY(skb_fill_bytes(bad, 0, 4, s));
+        SKB_TRY(skb_fill_bytes(ring_size, 0, (size_t)ring_m * 4, s));
+        SKB_TRY(skb_foreach(ring_m, s, SkbIotaItem{rpar}));
+        SKB_TRY(skb_foreach(ring_m, s, SkbRingHookItem{ring_rec, (int32_t)ring_m, rpar, bad}));
+        SKB_TRY(skb_foreach(ring_m, s, SkbRingSizeItem{ring_rec, rpar, (int32_t)node_lo, (int32_t)node_hi, ring_size, ring_oidx}));
+        SKB_TRY(skb_scan_u32_impl(ring_oidx, ring_oidx, ring_m, scratch, s));
+        const int32_t* ptrs[2] = {(const int32_t*)ring_oidx + ring_m, bad};
+        SKB_SFETCH(2, ptrs, vals);
+        Pc = vals[0];
+        if (vals[1]) return skb_fail("slab mode: the uncovered chain voxels do not form closed rings");
+    } else if (!ring_mode && n_uncovered > 0) {
         int32_t* cpar = work.take<int32_t>(Ne1);
         uint32_t* startoff_b = work.take<uint32_t>(Ne + 1);
         SKB_SNEED(work.ok);
@@ -651,11 +721,14 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     int32_t* head_end = work.take<int32_t>(Pk1);
     SkbAux* head_aux = work.take<SkbAux>(Pk1);
     int32_t* pindptr = work.take<int32_t>(Pk + 1);
-    skb_i4* einfo_b = Pc ? work.take<skb_i4>(Sb) : nullptr;
+    skb_i4* einfo_b = (Pc && !ring_mode) ? work.take<skb_i4>(Sb) : nullptr;
     SKB_SNEED(work.ok && out.ok);
     SKB_TRY(skb_path_heads(su, rec, ranked, raux, sel, S, 0, 0, start_lo, id_shift, start_node, plen, pmin, nullptr,
                            head_end, head_aux, s));
-    if (Pc)
+    if (Pc && ring_mode)
+        SKB_TRY(skb_foreach(ring_m, s, SkbRingHeadItem{ring_rec, ring_size, ring_oidx, (int32_t)P0, (int32_t)id_shift,
+                                                      start_node, plen, pmin, is_min}));
+    else if (Pc)
         SKB_TRY(skb_path_heads(sub, rec, rankedb, rauxb, selb, Sb, 1, P0, 0, id_shift, start_node, plen, pmin, einfo_b,
                                head_end, head_aux, s));
     SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, Pk, scratch, s));
@@ -670,7 +743,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     int64_t maxP = 0;
     bool any_cc = false;
     {
-        const int64_t v[5] = {P0, L0, Pc, Lc, cc};
+        const int64_t v[5] = {P0, L0, Pc, Lc, ring_mode ? 0 : cc};
         SKB_TRY(skb_comm_allgather(comm, v, 5, all));
         ++nexch;
         P0off[0] = L0off[0] = Pcoff[0] = Lcoff[0] = 0;
@@ -781,12 +854,15 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         int32_t* gptr = work.take<int32_t>(Pk + 1);
         SKB_SNEED(work.ok);
         SKB_TRY(skb_foreach(Pk + 1, s, SkbAddOffsetItem{pindptr, gptr, (int32_t)((L0_total + Lcoff[rank]) - L0)}));
-        SKB_TRY(skb_path_emit(indices, data, rec, sub, seb, rankedb, einfo_b, gptr, values, nullptr, id_shift, Sb, pidx, pdata,
-                              pw, s));
+        if (ring_mode)
+            SKB_TRY(skb_foreach(ring_m, s, SkbRingWalkItem{ring_rec, (int32_t)ring_m, ring_oidx, (int32_t)P0, (int32_t)id_shift,
+                                                          gptr, lin, ze0 * sz, pidx, pdata, pw, head_aux}));
+        else
+            SKB_TRY(skb_path_emit(indices, data, rec, sub, seb, rankedb, einfo_b, gptr, values, nullptr, id_shift, Sb, pidx,
+                                  pdata, pw, s));
     }
     SKB_HOST_MARK();
     // ---- skeleton ids ------------------------------------------------------------------------------------------------------------
-    const int64_t node_lo = Noff[rank], node_hi = Noff[rank + 1];
     SKB_TRY(skb_slab_components(links_all, nrec, S_total, kpar, kmin, node_lo, node_hi, id_shift, is_min, Ne, scratch, s));
     int64_t cr0, C_k;
     {

@@ -28,6 +28,22 @@ def make_volume(kind, shape, seed):
         img[:, ::5, ::7] = True
         img[1:-1, 2, 3] = False
         return img
+    if kind == 'rings':     # junction-free cycles that cross slab boundaries, touch them, or lie inside a slab
+        Z, Y, X = shape
+        img = np.zeros(shape, bool)
+        zA, zB, xA, xB = 2, Z - 3, 2, X - 3                 # one ring through every slab (x-z plane, corners cut)
+        img[zA, 3, xA + 1:xB] = True
+        img[zB, 3, xA + 1:xB] = True
+        img[zA + 1:zB, 3, xA] = True
+        img[zA + 1:zB, 3, xB] = True
+        for zc in range(4, Z - 4, 5):                       # 4-voxel rings, some of them astride a boundary
+            img[zc - 1, 8, 6] = img[zc, 8, 5] = img[zc, 8, 7] = img[zc + 1, 8, 6] = True
+        for zc in range(3, Z - 3, 7):                       # rings lying in one plane (some in a boundary plane)
+            img[zc, 12, 11:14] = img[zc, 16, 11:14] = True
+            img[zc, 13:16, 10] = img[zc, 13:16, 14] = True
+        img[1:-1, 19, 3] = img[2:-2, 19, 9] = True          # and ordinary paths through every slab
+        img[Z // 2, 19, 3:10] = True
+        return img
     raise ValueError(kind)
 
 

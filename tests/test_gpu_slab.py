@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
     ['--kind', 'dense12', '--shape', '64,32,32', '--halo', '2', '--seed', '5'],
     ['--kind', 'lines_z', '--shape', '64,33,40', '--halo', '2'],
     ['--kind', 'walks', '--shape', '128,96,80', '--halo', '8', '--seed', '12', '--valued', '1'],
+    ['--kind', 'rings', '--shape', '64,22,30', '--halo', '2'],
 ])
 def test_slab_mode_nccl(args):
     world = max(1, min(torch.cuda.device_count(), 8))

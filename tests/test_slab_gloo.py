@@ -71,6 +71,18 @@ def test_native_runner_restarts_when_arenas_are_too_small():
     assert 'SLAB-OK' in outs[0] and 'native=1' in outs[0]
 
 
+@pytest.mark.parametrize('world,args', [
+    (2, ['--kind', 'rings', '--shape', '40,22,30', '--halo', '2']),
+    (3, ['--kind', 'rings', '--shape', '48,22,30', '--halo', '3', '--valued', '1']),
+])
+def test_cycles_across_slab_boundaries(world, args):
+    """Junction-free cycles that cross one or several slab boundaries, lie astride one, or lie in a boundary
+    plane: the ranks gather the uncovered chain voxels and the owner of a ring's minimum node emits it."""
+    codes, outs = launch(world, *args)
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'native=1' in outs[0]
+
+
 def test_comm_allgather_between_processes():
     """The shared-memory count channel of the native runner (skb_comm_*), three processes."""
     code = (
