@@ -321,8 +321,6 @@ def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=
             stacklevel=2,
         )
         separator = '-'
-    if find_main_branch:
-        raise NotImplementedError('find_main_branch (summary_utils.py:7-62) is outside the B200 hot path')
     ctx, p = skel._ctx, skel._p
     indptr, indices, data = skel._graph_dev
     ndim = int(skel._coords_dev.shape[1])
@@ -367,5 +365,9 @@ def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=
         summary[f'coord_dst_{ndim}'] = of[dh + ndim].astype(vdtype, copy=False)
     summary['euclidean_distance'] = of[2 * dh]
     df = pd.DataFrame(summary)
+    if find_main_branch:
+        # host-side post-processing of the P-row table, like the reference (csr.py:955-957)
+        from .summary_utils import find_main_branches
+        df['main'] = find_main_branches(df)
     df.rename(columns=lambda s: s.replace('_', separator), inplace=True)
     return df
