@@ -182,7 +182,9 @@ int skb_path_start_count(const skb_i4* rec, const uint8_t* covered, const int64_
                          uint32_t* startoff, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     if (!covered) return skb_fail("phase 1 needs the covered marks");
-    SKB_TRY(skb_foreach(n, s, SkbStartCountItem{rec, covered, skb_make_slab(slab, n), startoff}));
+    // covered nodes start nothing: zero the counts in one fill, visit only the uncovered nodes
+    SKB_TRY(skb_fill_bytes(startoff, 0, (size_t)n * 4, s));
+    SKB_TRY(skb_foreach_unmarked(n, covered, s, SkbStartCountItem{rec, covered, skb_make_slab(slab, n), startoff}));
     return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }
 
@@ -196,9 +198,12 @@ int skb_path_walk(const int32_t* indptr, const int32_t* indices, const double* g
     skb_stream_t s = (skb_stream_t)stream;
     SkbSlab sl = skb_make_slab(slab, n);
     SKB_TRY(skb_foreach((int64_t)sl.own1 - sl.own0, s, SkbStartFillItem{indptr, startoff, sl.own0, su, se}));
-    return skb_foreach(
-        n_starts, s,
-        SkbWalkItem{indices, gdata, values, lin, rec, startoff, su, se, sl, ranked, (SkbAux*)aux, stamp});
+    if (aux)
+        return skb_foreach_steps(n_starts, s,
+                                 SkbWalkItemT<true>{indices, gdata, values, lin, rec, startoff, su, se, sl, ranked,
+                                                    (SkbAux*)aux, stamp});
+    return skb_foreach_steps(
+        n_starts, s, SkbWalkItemT<false>{indices, gdata, values, lin, rec, startoff, su, se, sl, ranked, nullptr, stamp});
 }
 
 // pointer jumping over the starts of this rank (synchronous rounds, ping-pong between buf0/aux0
@@ -281,7 +286,7 @@ int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec
                   const int32_t* se, const skb_i4* ranked, const skb_i4* einfo, const int32_t* pindptr,
                   const double* values, uint8_t* covered, int64_t id_shift, int64_t n_starts, int32_t* pidx,
                   double* pdata, double* pw, void* stream) {
-    return skb_foreach(n_starts, (skb_stream_t)stream,
+    return skb_foreach_steps(n_starts, (skb_stream_t)stream,
                        SkbEmitItem{indices, gdata, rec, su, se, ranked, einfo, pindptr, values, covered,
                                    (int32_t)id_shift, pidx, pdata, pw});
 }
@@ -290,9 +295,11 @@ int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec
 // degree-2 nodes is flagged in rec as a cycle root and in is_min.  Scratch: par i32[n].
 int skb_cycle_roots(skb_i4* rec, const uint8_t* covered, int64_t n, int32_t* par, uint32_t* is_min, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
+    // only uncovered nodes act: covered ones are skipped 16 marks at a time.  Every parent is initialised, though:
+    // in a Z-slab an uncovered halo node may have covered neighbours
     SKB_TRY(skb_foreach(n, s, SkbIotaItem{par}));
-    SKB_TRY(skb_foreach(n, s, SkbCycleHookItem{rec, covered, par}));
-    return skb_foreach(n, s, SkbCycleRootItem{rec, covered, par, is_min});
+    SKB_TRY(skb_foreach_unmarked(n, covered, s, SkbCycleHookItem{rec, covered, par}));
+    return skb_foreach_unmarked(n, covered, s, SkbCycleRootItem{rec, covered, par, is_min});
 }
 
 // skeleton ids (csr.py:909): connected components of the contracted graph, labelled by the rank

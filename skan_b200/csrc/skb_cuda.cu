@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "skb_items.cuh"
@@ -66,6 +67,154 @@ static int skb_foreach(int64_t n, skb_stream_t s, F f) {
     skb_foreach_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "skb_foreach launch");
+}
+
+// ------------------------------------------------------------------------------- foreach, stepwise items
+// Items whose work is a loop of dependent loads of very uneven length (the chain walks): one item per thread
+// leaves a warp waiting for its longest walk with a handful of lanes active (ncu: 5-9 of 32).  Here a warp is
+// persistent and its lanes are refilled from a queue: F::begin(i, st) starts item i (false = nothing to
+// iterate), F::step(st) advances it by one hop (false = finished, after which F::finish(i, st) stores the
+// result).  The queue is one 64-bit ticket counter per launch; a warp draws SKB_DYN_CHUNK consecutive items at a
+// time and hands them to its idle lanes in item order, whenever at least SKB_DYN_REFILL lanes are idle.
+#define SKB_DYN_CHUNK 64
+#define SKB_DYN_REFILL 8
+#define SKB_DYN_SLOTS 64
+
+template <typename F>
+__global__ void __launch_bounds__(256) skb_foreach_steps_kernel(F f, int64_t n, unsigned long long* ticket) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    typename F::State st;
+    int64_t item = 0;
+    bool active = false;
+    int64_t pos = 0, end = 0;  // warp-uniform: the part of the drawn chunk not handed out yet
+    bool exhausted = false;    // warp-uniform: a draw came back past the end of the queue
+    for (;;) {
+        unsigned idle = __ballot_sync(full, !active);
+        if (idle == full && exhausted) break;
+        if (!exhausted && __popc(idle) >= SKB_DYN_REFILL) {
+            do {
+                if (pos >= end) {
+                    unsigned long long b = 0;
+                    if (lane == 0) b = atomicAdd(ticket, (unsigned long long)SKB_DYN_CHUNK);
+                    b = __shfl_sync(full, b, 0);
+                    if ((int64_t)b >= n) {
+                        exhausted = true;
+                        break;
+                    }
+                    pos = (int64_t)b;
+                    end = pos + SKB_DYN_CHUNK < n ? pos + SKB_DYN_CHUNK : n;
+                }
+                if (!active) {
+                    const int64_t i = pos + __popc(idle & below);
+                    if (i < end) {
+                        item = i;
+                        active = f.begin(i, st);
+                    }
+                }
+                pos += __popc(idle);
+                idle = __ballot_sync(full, !active);
+            } while (__popc(idle) >= SKB_DYN_REFILL);
+        }
+        if (active) {
+            active = f.step(st);
+            if (!active) f.finish(item, st);
+        }
+    }
+    // every warp of the grid draws exactly once past the end; the last one to leave resets the ticket for the
+    // next launch that uses this slot (ticket[1] counts the warps that have left)
+    if (lane == 0) {
+        const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+        if (atomicAdd(ticket + 1, 1ull) == warps - 1) {
+            ticket[0] = 0;
+            ticket[1] = 0;
+        }
+    }
+}
+
+// ticket slots: a small ring per host thread and device, zeroed once; a launch leaves its slot zeroed again
+static int skb_ticket_slot(unsigned long long** out) {
+    enum { MAX_DEV = 64 };
+    static thread_local unsigned long long* ring[MAX_DEV] = {};
+    static thread_local unsigned next[MAX_DEV] = {};
+    int dev = 0;
+    SKB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) return skb_fail("device ordinal out of range");
+    if (!ring[dev]) {
+        void* p = nullptr;
+        SKB_CUDA(cudaMalloc(&p, SKB_DYN_SLOTS * 16));
+        SKB_CUDA(cudaMemset(p, 0, SKB_DYN_SLOTS * 16));
+        SKB_CUDA(cudaDeviceSynchronize());  // once: the zeroes are in place before any stream uses a slot
+        ring[dev] = (unsigned long long*)p;
+    }
+    *out = ring[dev] + 2 * (next[dev]++ % SKB_DYN_SLOTS);
+    return 0;
+}
+
+static int g_skb_steps_dynamic = -1;  // SKAN_B200_DYNAMIC_WALKS=0 falls back to one item per thread
+static bool skb_steps_dynamic() {
+    if (g_skb_steps_dynamic < 0) {
+        const char* e = getenv("SKAN_B200_DYNAMIC_WALKS");
+        g_skb_steps_dynamic = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_skb_steps_dynamic != 0;
+}
+
+template <typename F>
+static int skb_foreach_steps(int64_t n, skb_stream_t s, F f) {
+    if (n <= 0) return 0;
+    if (!skb_steps_dynamic()) return skb_foreach(n, s, f);  // F::operator() runs begin / step / finish in place
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = (int64_t)skb_sm_count() * 8;  // persistent: 2048 threads per SM
+    if (blocks > cap) blocks = cap;
+    unsigned long long* ticket = nullptr;
+    {
+        int e = skb_ticket_slot(&ticket);
+        if (e) return e;
+    }
+    skb_foreach_steps_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n, ticket);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "skb_foreach_steps launch");
+}
+
+// ------------------------------------------------------------------------------- foreach over unmarked items
+// f(i) for every i < n with marks[i] == 0, when almost every item is marked (the nodes no terminal-headed path
+// covers are a handful out of millions): a thread tests 16 marks with one 128-bit load.
+template <typename F>
+__global__ void __launch_bounds__(256) skb_foreach_unmarked_kernel(F f, const uint8_t* __restrict__ marks, int64_t n) {
+    const int64_t groups = (n + 15) >> 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {
+        const int64_t v0 = gi << 4;
+        if (v0 + 16 <= n) {
+            const uint4 c = *(const uint4*)(marks + v0);
+            const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+            uint32_t any_zero = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) any_zero |= (w[k] - 0x01010101u) & ~w[k] & 0x80808080u;
+            if (!any_zero) continue;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (((w[j >> 2] >> (8 * (j & 3))) & 0xffu) == 0) f(v0 + j);
+        } else {
+            for (int64_t v = v0; v < n; ++v)
+                if (!marks[v]) f(v);
+        }
+    }
+}
+
+template <typename F>
+static int skb_foreach_unmarked(int64_t n, const uint8_t* marks, skb_stream_t s, F f) {
+    if (n <= 0) return 0;
+    if (((uintptr_t)marks & 15) != 0)  // unaligned marks: every item tests its own byte (the items do)
+        return skb_foreach(n, s, f);
+    int64_t blocks = ((n + 15) / 16 + 255) / 256;
+    int64_t cap = (int64_t)skb_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    skb_foreach_unmarked_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, marks, n);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "skb_foreach_unmarked launch");
 }
 
 static int skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t s) {
@@ -671,6 +820,18 @@ __device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int64_t z
     if (values) values[id] = skb_load_value(img, dtype, r);
 }
 
+// (z, y, x) += (dz, dy, dx) in mixed radix (ny, nx); all inputs are valid digits, so one carry per digit suffices
+__device__ __forceinline__ void skb_advance_coords(const SkbGeom& g, int32_t& z, int32_t& y, int32_t& x, int32_t dz,
+                                                   int32_t dy, int32_t dx) {
+    x += dx;
+    int32_t c = x >= g.nx ? 1 : 0;
+    x -= c ? g.nx : 0;
+    y += dy + c;
+    c = y >= g.ny ? 1 : 0;
+    y -= c ? g.ny : 0;
+    z += dz + c;
+}
+
 __device__ __forceinline__ uint32_t skb_stage_bits(uint64_t w, uint32_t off, uint16_t* __restrict__ st, uint32_t k) {
     while (w) {
         st[k++] = (uint16_t)(off + (uint32_t)(__ffsll((long long)w) - 1));
@@ -679,15 +840,23 @@ __device__ __forceinline__ uint32_t skb_stage_bits(uint64_t w, uint32_t off, uin
     return k;
 }
 
+template <bool VALUES>  // false: boolean image, no node values (csr.py:554-562) and no dtype dispatch in the kernel
 __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, int64_t ntiles, SkbGeom g,
     const void* img, int dtype, int64_t z_origin, int64_t* __restrict__ lin, int64_t* __restrict__ coords,
-    double* __restrict__ values, uint32_t* __restrict__ pre256) {
+    double* __restrict__ values_arg, uint32_t* __restrict__ pre256) {
+    double* __restrict__ values = VALUES ? values_arg : nullptr;
     __shared__ uint16_t stage[SKB_EMIT_THREADS / 32][SKB_EMIT_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warps = (int64_t)gridDim.x * (SKB_EMIT_THREADS / 32);
     uint16_t* st = stage[warp];
-    for (int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + warp; tile < ntiles; tile += warps) {
+    // Coordinates of the tile origin: divided out once per warp (64-bit divisions when the volume has more than
+    // 2^32 voxels), then advanced by the constant stride of the loop with two carries per tile.
+    int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + warp;
+    int32_t zt = 0, y0 = 0, x0 = 0, dzt, dy0, dx0;
+    if (tile < ntiles) skb_coords(g, tile * SKB_TILE_VOX, zt, y0, x0);
+    skb_coords(g, warps * SKB_TILE_VOX, dzt, dy0, dx0);  // may exceed the volume: only a displacement
+    for (; tile < ntiles; tile += warps, skb_advance_coords(g, zt, y0, x0, dzt, dy0, dx0)) {
         const uint32_t t0 = tile_prefix[tile], total = tile_prefix[tile + 1] - t0;
         if (total == 0) {  // empty tile: only the rank structure (64 blocks of 256 bits)
             ((uint2*)(pre256 + tile * 64))[lane] = make_uint2(t0, t0);
@@ -719,8 +888,6 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
         const unsigned long long ex = inc - packed;
         const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
         const int64_t r0 = tile * SKB_TILE_VOX;
-        int32_t zt, y0, x0;
-        skb_coords(g, r0, zt, y0, x0);  // warp-uniform; the only 64-bit division of the tile
         const int64_t z0 = (g.ndim == 3 ? z_origin : 0) + zt;
         uint32_t base = 0;              // nodes of the tile in groups before j
         uint32_t idj[4];
@@ -1367,8 +1534,12 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
     int64_t grid = (ntiles + SKB_EMIT_THREADS / 32 - 1) / (SKB_EMIT_THREADS / 32);
     int64_t cap = (int64_t)skb_sm_count() * 8;
     if (grid > cap) grid = cap;
-    skb_emit_nodes_kernel<<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
-        bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256);
+    if (values)
+        skb_emit_nodes_kernel<true><<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
+            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256);
+    else
+        skb_emit_nodes_kernel<false><<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
+            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, nullptr, pre256);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
 }

@@ -643,11 +643,14 @@ struct SkbStartFillItem {  // over owned nodes (item index is relative to own0)
 // finished, -1-x = id of the start that is the REVERSED last half-edge (B -> m) of the list;
 // y = half-edges from this start's node to (x >= 0: the next start's node | x < 0: the list end);
 // z = minimum (global) node id seen so far on the list from this start on.
-struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle root / splitter
+// Stepwise item (skb_foreach_steps): begin() reads the start, step() is one hop (one 32-byte record), finish()
+// stores the result.  AUX = false on a single GPU (no per-list sums: the second walk provides them).
+template <bool AUX>
+struct SkbWalkItemT {  // over starts: local walk to the next terminal / cycle root / splitter
     const int32_t* indices;
-    const double* gdata;   // only read when aux is given
+    const double* gdata;   // only read when AUX
     const double* values;  // null -> 1.0
-    const int64_t* lin;    // only read when aux is given; may be null
+    const int64_t* lin;    // only read when AUX; may be null
     const skb_i4* rec;
     const uint32_t* startoff;
     const int32_t* su;
@@ -656,82 +659,106 @@ struct SkbWalkItem {  // over starts: local walk to the next terminal / cycle ro
     skb_i4* ranked;
     SkbAux* aux;     // null on a single GPU
     int32_t* stamp;  // null, or: stamp[v] = a start whose list passes through chain node v
-    SKB_HD void operator()(int64_t s) const {
+    struct State {
+        int32_t prev, cur, cnt, mn, out_x, start;
+        double w_in, sw, sx, sxx;  // AUX only
+        int64_t end_lin;
+        int32_t end_node, end_deg, end_key;
+    };
+    SKB_HD bool begin(int64_t s, State& st) const {
         int32_t u = su[s];
         int32_t arc = se[s];
-        int32_t prev = u, cur = indices[arc];
-        double w_in = aux ? gdata[arc] : 0.0;  // weight of the edge arriving at `cur`
-        int32_t cnt = 1, mn = u;
-        double sw = 0.0, sx = 0.0, sxx = 0.0;
-        if (aux) {
+        st.start = (int32_t)s;
+        st.prev = u;
+        st.cur = indices[arc];
+        st.cnt = 1;
+        st.mn = u;
+        st.out_x = 0;
+        if (AUX) {
+            st.w_in = gdata[arc];  // weight of the edge arriving at `cur`
             double x = values ? values[u] : 1.0;
-            sx = x;
-            sxx = x * x;
+            st.sw = 0.0;
+            st.sx = x;
+            st.sxx = x * x;
+            st.end_lin = 0;
+            st.end_node = -1;
+            st.end_deg = 0;
+            st.end_key = -1;
         }
-        skb_i4 out;
-        SkbAux ax;
-        ax.end_lin = 0;
-        ax.end_node = -1;
-        ax.end_deg = 0;
-        ax.end_key = -1;
-        ax.pad = 0;
-        for (;;) {
-            const skb_i4* rp = rec + 2 * (int64_t)cur;
-            skb_i4 r = skb_ld_i4(rp);
-            if (cur < mn) mn = cur;
-            if (aux) sw += w_in;
-            if (r.w != 2) {
-                if ((r.w & SKB_REC_SPLITTER) && !(r.w & SKB_REC_CYCLE_ROOT)) {
-                    // the list continues with the splitter's other half-edge
-                    out.x = (int32_t)(startoff[cur] + (r.x == prev ? 1u : 0u)) + sl.start_shift;
-                    break;
-                }
-                // terminal or cycle root: find the reverse half-edge (cur -> prev)
-                int32_t d = r.w & SKB_REC_DEG_MASK;
-                int32_t j = 0;
-                if (d == SKB_REC_DEG_MASK) {  // saturated degree field: unbounded row, rely on symmetry
-                    while (indices[r.z + j] != prev) ++j;
-                } else {
-                    while (j + 1 < d && indices[r.z + j] != prev) ++j;
-                }
-                int32_t key = (int32_t)startoff[cur] + sl.start_shift;
-                out.x = -1 - (key + j);
-                if (aux) {
-                    double x = values ? values[cur] : 1.0;
-                    sx += x;
-                    sxx += x * x;
-                    ax.end_lin = lin ? lin[cur] + sl.lin_offset : (int64_t)cur;
-                    ax.end_node = cur + sl.id_shift;
-                    ax.end_deg = d;
-                    ax.end_key = key;
-                }
-                break;
+        return true;
+    }
+    SKB_HD bool step(State& st) const {
+        const int32_t cur = st.cur, prev = st.prev;
+        const skb_i4* rp = rec + 2 * (int64_t)cur;
+        skb_i4 r = skb_ld_i4(rp);
+        if (cur < st.mn) st.mn = cur;
+        if (AUX) st.sw += st.w_in;
+        if (r.w != 2) {
+            if ((r.w & SKB_REC_SPLITTER) && !(r.w & SKB_REC_CYCLE_ROOT)) {
+                // the list continues with the splitter's other half-edge
+                st.out_x = (int32_t)(startoff[cur] + (r.x == prev ? 1u : 0u)) + sl.start_shift;
+                return false;
             }
-            if (stamp) stamp[cur] = (int32_t)s;
-            if (aux) {
+            // terminal or cycle root: find the reverse half-edge (cur -> prev)
+            int32_t d = r.w & SKB_REC_DEG_MASK;
+            int32_t j = 0;
+            if (d == SKB_REC_DEG_MASK) {  // saturated degree field: unbounded row, rely on symmetry
+                while (indices[r.z + j] != prev) ++j;
+            } else {
+                while (j + 1 < d && indices[r.z + j] != prev) ++j;
+            }
+            int32_t key = (int32_t)startoff[cur] + sl.start_shift;
+            st.out_x = -1 - (key + j);
+            if (AUX) {
                 double x = values ? values[cur] : 1.0;
-                sx += x;
-                sxx += x * x;
+                st.sx += x;
+                st.sxx += x * x;
+                st.end_lin = lin ? lin[cur] + sl.lin_offset : (int64_t)cur;
+                st.end_node = cur + sl.id_shift;
+                st.end_deg = d;
+                st.end_key = key;
             }
-            int32_t nxt = (r.x == prev) ? r.y : r.x;
-            if (aux) {
-                skb_d2 wn = skb_ld_d2(rp + 1);
-                w_in = (r.x == prev) ? wn.y : wn.x;
-            }
-            prev = cur;
-            cur = nxt;
-            ++cnt;
+            return false;
         }
-        out.y = cnt;
-        out.z = mn + sl.id_shift;
+        if (stamp) stamp[cur] = st.start;
+        if (AUX) {
+            double x = values ? values[cur] : 1.0;
+            st.sx += x;
+            st.sxx += x * x;
+            skb_d2 wn = skb_ld_d2(rp + 1);
+            st.w_in = (r.x == prev) ? wn.y : wn.x;
+        }
+        st.cur = (r.x == prev) ? r.y : r.x;
+        st.prev = cur;
+        ++st.cnt;
+        return true;
+    }
+    SKB_HD void finish(int64_t s, const State& st) const {
+        skb_i4 out;
+        out.x = st.out_x;
+        out.y = st.cnt;
+        out.z = st.mn + sl.id_shift;
         out.w = 0;
         skb_st_i4(ranked + s, out);
-        if (aux) {
-            ax.sw = sw;
-            ax.sx = sx;
-            ax.sxx = sxx;
+        if (AUX) {
+            SkbAux ax;
+            ax.sw = st.sw;
+            ax.sx = st.sx;
+            ax.sxx = st.sxx;
+            ax.end_lin = st.end_lin;
+            ax.end_node = st.end_node;
+            ax.end_deg = st.end_deg;
+            ax.end_key = st.end_key;
+            ax.pad = 0;
             aux[s] = ax;
         }
+    }
+    SKB_HD void operator()(int64_t s) const {
+        State st;
+        begin(s, st);
+        while (step(st)) {
+        }
+        finish(s, st);
     }
 };
 
@@ -981,7 +1008,7 @@ struct SkbHeadsItem {  // over starts: path id, start node, length, minimum node
     }
 };
 
-struct SkbEmitItem {  // over starts: second local walk, writes path entries (csr.py:394-409)
+struct SkbEmitItem {  // over starts: second local walk, writes path entries (csr.py:394-409); stepwise item
     const int32_t* indices;
     const double* gdata;
     const skb_i4* rec;
@@ -996,11 +1023,16 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
     int32_t* pidx;
     double* pdata;
     double* pw;  // weight of the edge arriving at each entry (0 for the first)
-    SKB_HD void operator()(int64_t s) const {
+    struct State {
+        int64_t at;  // entry index of the node last written
+        int32_t prev, cur;
+        double w_in;  // weight of the edge arriving at `cur`: the first from the graph, later ones from the records
+    };
+    SKB_HD bool begin(int64_t s, State& st) const {
         skb_i4 a = skb_ld_i4(ranked + s);
-        if (a.x >= 0 || a.x == SKB_DEAD) return;  // never reaches a terminal: a cycle that phase 1 handles
+        if (a.x >= 0 || a.x == SKB_DEAD) return false;  // never reaches a terminal: a cycle that phase 1 handles
         skb_i4 info = skb_ld_i4(einfo + (-1 - a.x));
-        if (info.x < 0) return;  // the emitted direction is the other one
+        if (info.x < 0) return false;  // the emitted direction is the other one
         int64_t base = pindptr ? pindptr[info.x] : info.z;
         int32_t pos = info.y - a.y;  // position of this start's node on the path
         int32_t u = su[s];
@@ -1011,31 +1043,38 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
             pw[base] = 0.0;
             if (covered) covered[u] = 1;
         }
-        int32_t prev = u, cur = indices[arc];
-        double w_in = gdata[arc];  // weight of the edge arriving at `cur`; later ones come with the records
-        for (;;) {
-            ++pos;
-            const skb_i4* rp = rec + 2 * (int64_t)cur;
-            skb_i4 r = skb_ld_i4(rp);
-            pidx[base + pos] = cur + id_shift;
-            if (pdata) pdata[base + pos] = values ? values[cur] : 1.0;
-            pw[base + pos] = w_in;
-            if (r.w != 2) {
-                if (covered) covered[cur] = 1;
-                break;
-            }
-            if (covered) covered[cur] = 1;
-            skb_d2 w = skb_ld_d2(rp + 1);
-            int32_t nxt;
-            if (r.x == prev) {
-                nxt = r.y;
-                w_in = w.y;
-            } else {
-                nxt = r.x;
-                w_in = w.x;
-            }
-            prev = cur;
-            cur = nxt;
+        st.at = base + pos;
+        st.prev = u;
+        st.cur = indices[arc];
+        st.w_in = gdata[arc];
+        return true;
+    }
+    SKB_HD bool step(State& st) const {
+        const int32_t cur = st.cur;
+        const int64_t at = ++st.at;
+        const skb_i4* rp = rec + 2 * (int64_t)cur;
+        skb_i4 r = skb_ld_i4(rp);
+        pidx[at] = cur + id_shift;
+        if (pdata) pdata[at] = values ? values[cur] : 1.0;
+        pw[at] = st.w_in;
+        if (covered) covered[cur] = 1;
+        if (r.w != 2) return false;
+        skb_d2 w = skb_ld_d2(rp + 1);
+        if (r.x == st.prev) {
+            st.cur = r.y;
+            st.w_in = w.y;
+        } else {
+            st.cur = r.x;
+            st.w_in = w.x;
+        }
+        st.prev = cur;
+        return true;
+    }
+    SKB_HD void finish(int64_t, const State&) const {}
+    SKB_HD void operator()(int64_t s) const {
+        State st;
+        if (!begin(s, st)) return;
+        while (step(st)) {
         }
     }
 };

@@ -31,6 +31,27 @@ static int skb_foreach(int64_t n, skb_stream_t, F f) {
     return 0;
 }
 
+// stepwise items (the chain walks): the CUDA build refills idle lanes from a queue; here the same begin / step /
+// finish functions run one item after the other
+template <typename F>
+static int skb_foreach_steps(int64_t n, skb_stream_t, F f) {
+    for (int64_t i = 0; i < n; ++i) {
+        typename F::State st;
+        if (!f.begin(i, st)) continue;
+        while (f.step(st)) {
+        }
+        f.finish(i, st);
+    }
+    return 0;
+}
+
+template <typename F>
+static int skb_foreach_unmarked(int64_t n, const uint8_t* marks, skb_stream_t, F f) {
+    for (int64_t i = 0; i < n; ++i)
+        if (!marks[i]) f(i);
+    return 0;
+}
+
 static int skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t) {
     memset(p, byte, nbytes);
     return 0;
