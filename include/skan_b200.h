@@ -37,6 +37,10 @@ int skb_abi_version(void);
 const char* skb_last_error(void);
 int64_t skb_scan_scratch_bytes(int64_t n); /* scratch needed by any call taking `scratch` over n items */
 int64_t skb_tile_voxels(void);             /* voxels per mask tile (16384) */
+int skb_set_option(const char* name, int64_t value); /* scheduling tunables, no effect on results: "dynamic_walks"
+                                                        (1: chain walks refill idle lanes from a queue, default;
+                                                        0: one walk per thread), "walk_refill" (1..32, idle lanes
+                                                        at which a warp draws new walks, default 8) */
 int64_t skb_kernel_launches(void);         /* kernels launched by the library since it was loaded */
 
 /* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes

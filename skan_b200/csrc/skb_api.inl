@@ -29,6 +29,7 @@ static SkbGeom skb_make_geom(int ndim, const int64_t* shape) {
     g.nx = (int32_t)s[2];
     g.ndim = ndim;
     g.sz = s[1] * s[2];
+    g.inv_sz = 1.0 / (double)g.sz;
     g.nvox = s[0] * s[1] * s[2];
     return g;
 }

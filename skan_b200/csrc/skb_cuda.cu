@@ -81,7 +81,7 @@ static int skb_foreach(int64_t n, skb_stream_t s, F f) {
 #define SKB_DYN_SLOTS 64
 
 template <typename F>
-__global__ void __launch_bounds__(256) skb_foreach_steps_kernel(F f, int64_t n, unsigned long long* ticket) {
+__global__ void __launch_bounds__(256) skb_foreach_steps_kernel(F f, int64_t n, unsigned long long* ticket, int refill) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned below = (1u << lane) - 1u;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) skb_foreach_steps_kernel(F f, int64_t n, 
     for (;;) {
         unsigned idle = __ballot_sync(full, !active);
         if (idle == full && exhausted) break;
-        if (!exhausted && __popc(idle) >= SKB_DYN_REFILL) {
+        if (!exhausted && __popc(idle) >= refill) {
             do {
                 if (pos >= end) {
                     unsigned long long b = 0;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) skb_foreach_steps_kernel(F f, int64_t n, 
                 }
                 pos += __popc(idle);
                 idle = __ballot_sync(full, !active);
-            } while (__popc(idle) >= SKB_DYN_REFILL);
+            } while (__popc(idle) >= refill);
         }
         if (active) {
             active = f.step(st);
@@ -152,11 +152,16 @@ static int skb_ticket_slot(unsigned long long** out) {
     return 0;
 }
 
-static int g_skb_steps_dynamic = -1;  // SKAN_B200_DYNAMIC_WALKS=0 falls back to one item per thread
+// tunables (skb_set_option, or the environment at first use): "dynamic_walks" 0 = one item per thread;
+// "walk_refill" = idle lanes at which a warp draws new items (1..32)
+static int g_skb_steps_dynamic = -1;
+static int g_skb_steps_refill = SKB_DYN_REFILL;
 static bool skb_steps_dynamic() {
     if (g_skb_steps_dynamic < 0) {
         const char* e = getenv("SKAN_B200_DYNAMIC_WALKS");
         g_skb_steps_dynamic = (e && e[0] == '0') ? 0 : 1;
+        const char* r = getenv("SKAN_B200_WALK_REFILL");
+        if (r && atoi(r) >= 1 && atoi(r) <= 32) g_skb_steps_refill = atoi(r);
     }
     return g_skb_steps_dynamic != 0;
 }
@@ -173,7 +178,7 @@ static int skb_foreach_steps(int64_t n, skb_stream_t s, F f) {
         int e = skb_ticket_slot(&ticket);
         if (e) return e;
     }
-    skb_foreach_steps_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n, ticket);
+    skb_foreach_steps_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n, ticket, g_skb_steps_refill);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "skb_foreach_steps launch");
 }
@@ -1499,6 +1504,22 @@ int64_t skb_scan_scratch_bytes(int64_t n) {
 }
 
 int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
+
+int skb_set_option(const char* name, int64_t value) {
+    if (!name) return skb_fail("skb_set_option: null name");
+    if (!strcmp(name, "dynamic_walks")) {
+        skb_steps_dynamic();  // read the environment first so that it does not override this later
+        g_skb_steps_dynamic = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "walk_refill")) {
+        if (value < 1 || value > 32) return skb_fail("skb_set_option: walk_refill must be in 1..32");
+        skb_steps_dynamic();
+        g_skb_steps_refill = (int)value;
+        return 0;
+    }
+    return skb_fail("skb_set_option: unknown option");
+}
 
 int64_t skb_kernel_launches(void) { return (int64_t)__atomic_load_n(&g_skb_launches, __ATOMIC_RELAXED); }
 

@@ -104,6 +104,7 @@ struct SkbGeom {
     int64_t nvox;
     int64_t sz;  // ny * nx
     int32_t nz, ny, nx, ndim;
+    double inv_sz;  // 1.0 / sz
 };
 
 SKB_HD void skb_coords(const SkbGeom& g, int64_t r, int32_t& z, int32_t& y, int32_t& x) {
@@ -113,6 +114,24 @@ SKB_HD void skb_coords(const SkbGeom& g, int64_t r, int32_t& z, int32_t& y, int3
         x = (int32_t)(rr - q * (uint32_t)g.nx);
         uint32_t q2 = q / (uint32_t)g.ny;
         y = (int32_t)(q - q2 * (uint32_t)g.ny);
+        z = (int32_t)q2;
+    } else if (g.sz <= 0x7fffffffLL && r >= 0 && r < (1LL << 52)) {
+        // more than 2^32 voxels, planes below 2^31: the plane index from one fp64 product (off by at most one,
+        // corrected below: r < 2^52 and a quotient below 2^31 leave the error far under 1), the rest in 32 bits
+        // instead of two 64-bit integer divisions per voxel
+        int64_t q2 = (int64_t)((double)r * g.inv_sz);
+        int64_t rem = r - q2 * g.sz;
+        if (rem < 0) {
+            --q2;
+            rem += g.sz;
+        } else if (rem >= g.sz) {
+            ++q2;
+            rem -= g.sz;
+        }
+        uint32_t rr = (uint32_t)rem;
+        uint32_t q = rr / (uint32_t)g.nx;
+        x = (int32_t)(rr - q * (uint32_t)g.nx);
+        y = (int32_t)q;
         z = (int32_t)q2;
     } else {
         int64_t q = r / g.nx;

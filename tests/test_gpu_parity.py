@@ -255,3 +255,32 @@ def test_native_runner_equals_stagewise_sequencing(shape, valued):
     for i, (x, y) in enumerate(pairs):
         assert torch.equal(x.view(torch.uint8) if x.dtype.is_floating_point else x,
                            y.view(torch.uint8) if y.dtype.is_floating_point else y), i
+
+
+@pytest.mark.parametrize('dynamic,refill', [(0, 8), (1, 1), (1, 8), (1, 32)])
+def test_walk_scheduling_variants_vs_oracle(dynamic, refill):
+    # the chain walks run either one per thread or on persistent warps whose idle lanes draw new walks from a
+    # ticket queue (skb_foreach_steps); scheduling must not change a single bit of the result
+    from skan_b200 import _native
+    lib = _native.library()
+    try:
+        lib.call('skb_set_option', b'dynamic_walks', dynamic)
+        lib.call('skb_set_option', b'walk_refill', refill)
+        compare_with_oracle(walks((96, 128, 160), 96, 128, seed=11, isolated=20, rings=8), (0.5, 0.1, 0.1))
+        for kind in ('serpentine', 'nested_rings', 'comb'):
+            img = long_chain_image(kind, 385)
+            compare_with_oracle(img, 1)
+        rng = np.random.default_rng(5)
+        img = walks((700, 900), 200, 300, seed=9, isolated=10, rings=6)
+        compare_with_oracle((img * (rng.random(img.shape) + 0.5)).astype(np.float32), (2.0, 0.5))
+        # many more walks than one launch has lanes: every warp draws several chunks
+        big = walks_device((512, 512, 512), 4096, 400, 21, torch.device('cuda'), isolated=100, rings=32)
+        sk = skan_b200.Skeleton(big, spacing=1)
+        lib.call('skb_set_option', b'dynamic_walks', 0)
+        base = skan_b200.Skeleton(big, spacing=1)
+        assert np.array_equal(sk.paths.indptr, base.paths.indptr)
+        assert np.array_equal(sk.paths.indices, base.paths.indices)
+        assert np.array_equal(sk.path_lengths(), base.path_lengths())
+    finally:
+        lib.call('skb_set_option', b'dynamic_walks', 1)
+        lib.call('skb_set_option', b'walk_refill', 8)
