@@ -38,9 +38,10 @@ const char* skb_last_error(void);
 int64_t skb_scan_scratch_bytes(int64_t n); /* scratch needed by any call taking `scratch` over n items */
 int64_t skb_tile_voxels(void);             /* voxels per mask tile (16384) */
 int skb_set_option(const char* name, int64_t value); /* scheduling tunables, no effect on results: "dynamic_walks"
-                                                        (1: chain walks refill idle lanes from a queue, default;
-                                                        0: one walk per thread), "walk_refill" (1..32, idle lanes
-                                                        at which a warp draws new walks, default 8) */
+                                                        (0: one chain walk per thread, default; 1: persistent warps
+                                                        whose idle lanes draw new walks from a queue -- measured
+                                                        slower on B200), "walk_refill" (1..32, idle lanes at which
+                                                        a warp draws new walks, default 8) */
 int64_t skb_kernel_launches(void);         /* kernels launched by the library since it was loaded */
 
 /* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes
@@ -65,6 +66,11 @@ int skb_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, vo
 int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
                    const int64_t* shape /*host*/, const void* image, int dtype, int64_t z_origin, int64_t* lin,
                    int64_t* coords, double* values, uint32_t* pre256, void* stream);
+/* The same when lin / coords / values have room for node_cap nodes only: nodes with id >= node_cap are not
+ * written (pre256 is always complete). */
+int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                       const int64_t* shape /*host*/, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                       int64_t* coords, double* values, uint32_t* pre256, int64_t node_cap, void* stream);
 
 /* Mask sweep + scan + node emission in ONE pass over the image (csr.py:1070,122-123,131-132,1088,
  * 554-562): writes what skb_pack_count + skb_scan_u32 + skb_emit_nodes write (bits, pre256, lin,
@@ -259,7 +265,12 @@ typedef struct skb_run_params {
     const double* wtab;                 /* device: 27 neighbour weights (nputil.py:278-279, host-computed) */
     double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, table_ndim;
     void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;
-    int64_t node_cap_hint;              /* pack_variant 2 (fused sweep): capacity of the node arrays, 0 = V/256 + 4096 */
+    int64_t node_cap_hint;              /* capacity hint for the node arrays (fused sweep: 0 = V/256 + 4096; else 0 = none) */
+    int64_t hint[8];                    /* capacity hints: [0] junction edges, [1] edges, [2] walk starts, [3] regular
+                                           paths; 0 = none.  With a hint, the read-back of the count overlaps the first
+                                           kernel that fills the arrays it sizes (counts[10] such overlaps per call);
+                                           a hint that proves too small costs that kernel a second launch (counts[11]).
+                                           Results never depend on the hints. */
 } skb_run_params;
 typedef struct skb_run_result { int64_t counts[16]; int64_t off[32]; int64_t work_need, out_need; int64_t stage_ns[32]; } skb_run_result;
 int skb_run_image(const skb_run_params* params /*host*/, skb_run_result* result /*host*/);

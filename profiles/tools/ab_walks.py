@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the chain-walk scheduling on one GPU, one process, one resident volume:
+"""A/B of the chain-walk scheduling and of the capacity hints on one GPU, one process, one resident volume:
 
     python profiles/tools/ab_walks.py [workload] > gpurun_out/ab_walks.txt
 
@@ -27,11 +27,13 @@ def main():
     img = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
     lib = _native.library()
     V = int(np.prod(shape, dtype=np.int64))
-    variants = [('static', 0, 8), ('dynamic r8', 1, 8), ('dynamic r16', 1, 16), ('dynamic r2', 1, 2),
-                ('dynamic r24', 1, 24), ('static again', 0, 8), ('dynamic r8 again', 1, 8)]
-    for name, dyn, refill in variants:
+    # (name, dynamic walks, refill threshold, capacity hints)
+    variants = [('static, no hints', 0, 8, False), ('static, hints', 0, 8, True), ('dynamic r8, hints', 1, 8, True),
+                ('static, no hints (2)', 0, 8, False), ('static, hints (2)', 0, 8, True)]
+    for name, dyn, refill, hints in variants:
         lib.call('skb_set_option', b'dynamic_walks', dyn)
         lib.call('skb_set_option', b'walk_refill', refill)
+        _pipeline.USE_HINTS = hints
         for _ in range(3):
             _pipeline.run_native(img, spacing=spacing, device=dev)
         torch.cuda.synchronize()
@@ -49,9 +51,10 @@ def main():
         st = r.counts['stage_ns']
         keys = ('sweep', 'nodes', 'raw_stencil', 'junction_count', 'junction_mst', 'degrees', 'csr_records', 'walk',
                 'rank', 'select', 'heads', 'emit', 'cycles', 'skeleton_ids', 'stats', 'table')
-        print(f'{name:18s} {ms:7.3f} ms/step  {V / ms / 1e3:11.0f} Mvox/s | ' +
+        print(f'{name:22s} {ms:7.3f} ms/step  {V / ms / 1e3:11.0f} Mvox/s  syncs={r.counts["syncs"]} '
+              f'overlapped={r.counts["overlapped"]} retaken={r.counts["retaken"]} | ' +
               ' '.join(f'{k}={st.get(k, 0) * 1e-6:.3f}' for k in keys), flush=True)
-    lib.call('skb_set_option', b'dynamic_walks', 1)
+    lib.call('skb_set_option', b'dynamic_walks', 0)
     lib.call('skb_set_option', b'walk_refill', 8)
 
 

@@ -27,6 +27,7 @@ _SIGNATURES = {
     'skb_set_option': (_int, [ctypes.c_char_p, _i64]),
     'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
     'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    'skb_emit_nodes_cap': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     'skb_sweep_scratch_bytes': (_i64, [_i64]),
     'skb_sweep_nodes': (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_tile_prefix': (_int, [_vp, _vp, _i64, _vp, _vp]),
@@ -79,7 +80,7 @@ class RunParams(ctypes.Structure):
                 ('want_values', ctypes.c_int32), ('time_sweep', ctypes.c_int32), ('wtab', _vp),
                 ('spacing_f', ctypes.c_double * 3), ('spacing_i', _i64 * 3), ('spacing_is_int', ctypes.c_int32),
                 ('table_ndim', ctypes.c_int32), ('work', _vp), ('work_bytes', _i64), ('out', _vp),
-                ('out_bytes', _i64), ('stream', _vp), ('node_cap_hint', _i64)]
+                ('out_bytes', _i64), ('stream', _vp), ('node_cap_hint', _i64), ('hint', _i64 * 8)]
 
 
 class RunResult(ctypes.Structure):
@@ -128,7 +129,9 @@ RUN_OFF = {n: i for i, n in enumerate(
     ['lin', 'coords', 'values', 'degrees', 'indptr', 'indices', 'data', 'pindptr', 'pidx', 'pdata', 'pw', 'skel',
      'dist', 'mean', 'stdev', 't32', 't64', 'tf', 'comp_rank'])}
 RUN_COUNT = {n: i for i, n in enumerate(
-    ['nodes', 'edges', 'paths', 'regular', 'cycles', 'entries', 'junction_edges', 'starts', 'syncs', 'sweep_ns'])}
+    ['nodes', 'edges', 'paths', 'regular', 'cycles', 'entries', 'junction_edges', 'starts', 'syncs', 'sweep_ns',
+     'overlapped', 'retaken'])}
+RUN_HINTS = ['junction_edges', 'edges', 'starts', 'regular']   # skb_run_params.hint[i] sizes by the count named
 
 RUN_STAGES = ['start', 'sweep', 'nodes', 'raw_stencil', 'junction_count', 'junction_mst', 'degrees', 'csr_records',
               'walk', 'rank', 'select', 'heads', 'emit', 'cycles', 'skeleton_ids', 'stats', 'table']

@@ -443,6 +443,14 @@ def algorithmic_bytes(nvox, esize, ndim, n, e, p, l, valued):
 
 # ---- the same path through the native runner (skb_run_image): one C call per image ---------------
 TIME_SWEEP = False  # bench.py: record CUDA events around the mask sweep kernel (counts['sweep_ns'])
+USE_HINTS = True    # pass the previous image's counts (+ slack) as capacity hints to skb_run_image
+
+
+HINT_SLACK = 4096   # entries added to every hint on top of 1/16 of the previous count
+
+
+def _hint(count):
+    return int(count * 1.0625) + HINT_SLACK
 _arena_cache = {}   # (device, stream) -> dict(work=tensor, out_bytes=int)
 _wtab_cache = {}
 
@@ -511,9 +519,15 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
     prm.spacing_is_int, prm.table_ndim = int(sp_is_int), tdim
     prm.stream = ctx.stream
     key = (str(ctx.device), ctx.stream)
-    cache = _arena_cache.setdefault(key, dict(work=None, out_bytes=1 << 22, shape=None, nodes=0))
-    # capacity of the node arrays of the fused sweep: what the last image of this shape needed, plus slack
-    prm.node_cap_hint = int(cache['nodes'] * 1.05) + 4096 if cache['shape'] == tuple(shape) else 0
+    cache = _arena_cache.setdefault(key, dict(work=None, out_bytes=1 << 22, shape=None, nodes=0, counts=None))
+    # Capacity hints: what the last image of this shape and kind needed, plus slack.  They only let the runner
+    # launch the kernel that fills an array while the exact count is still on its way to the host; a hint that is
+    # too small costs a second launch of that kernel, never a wrong result.
+    kind = (tuple(shape), code, bool(image_stack), bool(graph_only))
+    last = cache['counts'] if (USE_HINTS and cache['shape'] == kind) else None
+    prm.node_cap_hint = _hint(last['nodes']) if last else 0
+    for i, name in enumerate(_native.RUN_HINTS):
+        prm.hint[i] = _hint(last[name]) if last else 0
     V = int(np.prod(shape, dtype=np.int64))
     if cache['work'] is None:
         cache['work'] = ctx.empty(max(1 << 22, V // 4 + (1 << 22)), torch.uint8)
@@ -534,7 +548,7 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
         raise _native.NativeError('skb_run_image kept asking for larger arenas')
     cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
     C = {k: int(res.counts[i]) for k, i in _native.RUN_COUNT.items()}
-    cache['shape'], cache['nodes'] = tuple(shape), C['nodes']
+    cache['shape'], cache['nodes'], cache['counts'] = kind, C['nodes'], C
     if prm.time_sweep == 2:
         C['stage_ns'] = {k: int(res.stage_ns[i]) for i, k in enumerate(_native.RUN_STAGES)}
     O = {k: int(res.off[i]) for k, i in _native.RUN_OFF.items()}

@@ -86,15 +86,25 @@ int skb_junction_edge_count(const uint64_t* bits, const uint32_t* pre256, int nd
     return skb_foreach(n, (skb_stream_t)stream, it);
 }
 
+// (the _cap variants take the capacity of the arrays they fill: the native runner sizes them by a hint while
+// the exact count is still on its way to the host; entries beyond the capacity are counted, not written)
+static int skb_junction_edge_emit_cap(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape,
+                                      const int64_t* lin, const uint32_t* nb, const uint32_t* offset, int64_t n,
+                                      const double* wtab, const double* values, int height, int dtype, int32_t* ea,
+                                      int32_t* eb, uint8_t* ek, uint64_t* ew, int64_t cap, void* stream) {
+    SKB_TRY(skb_check_geom(ndim, shape));
+    if (height && !values) return skb_fail("height mode needs node values");
+    SkbWeight wf{wtab, values, height, dtype};
+    SkbJuncEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, nb, offset, wf, ea, eb, ek, ew,
+                       cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap};
+    return skb_foreach(n, (skb_stream_t)stream, it);
+}
 int skb_junction_edge_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape,
                            const int64_t* lin, const uint32_t* nb, const uint32_t* offset, int64_t n,
                            const double* wtab, const double* values, int height, int dtype, int32_t* ea,
                            int32_t* eb, uint8_t* ek, uint64_t* ew, void* stream) {
-    SKB_TRY(skb_check_geom(ndim, shape));
-    if (height && !values) return skb_fail("height mode needs node values");
-    SkbWeight wf{wtab, values, height, dtype};
-    SkbJuncEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, nb, offset, wf, ea, eb, ek, ew};
-    return skb_foreach(n, (skb_stream_t)stream, it);
+    return skb_junction_edge_emit_cap(bits, pre256, ndim, shape, lin, nb, offset, n, wtab, values, height, dtype, ea,
+                                      eb, ek, ew, 0xffffffffLL, stream);
 }
 
 // junction MST (csr.py:980-1020).  Edge endpoints are node ids < n (global ids when the edges of
@@ -148,20 +158,30 @@ int skb_degrees_indptr(const uint32_t* keep, int64_t n, int32_t* deg, int32_t* i
 // graph.indices / graph.data in canonical CSR order (csr.py:153-157).  With rec != NULL the same
 // pass also writes what skb_path_records would: node records rec (32 B per node), scanned phase-0
 // start offsets startoff u32[n+1] and the initial state of the skeleton-id stage.
-int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
-                 const uint32_t* keep, const int32_t* indptr, int64_t n, const double* wtab, const double* values,
-                 int height, int dtype, int32_t* indices, double* data, skb_i4* rec, const int64_t* slab,
-                 int lin_splitters, uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
-                 void* stream) {
+static int skb_csr_emit_cap(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape,
+                            const int64_t* lin, const uint32_t* keep, const int32_t* indptr, int64_t n,
+                            const double* wtab, const double* values, int height, int dtype, int32_t* indices,
+                            double* data, skb_i4* rec, const int64_t* slab, int lin_splitters, uint32_t* startoff,
+                            int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch, int64_t edge_cap,
+                            void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     SKB_TRY(skb_check_geom(ndim, shape));
     if (height && !values) return skb_fail("height mode needs node values");
     SkbWeight wf{wtab, values, height, dtype};
     SkbRecOut out{lin_splitters ? lin : nullptr, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min};
-    SkbCsrEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, keep, indptr, wf, indices, data, rec ? 1 : 0, out};
+    SkbCsrEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, keep, indptr, wf, indices, data, rec ? 1 : 0, out,
+                      edge_cap > 0x7fffffffLL ? 0x7fffffff : (int32_t)edge_cap};
     SKB_TRY(skb_foreach(n, s, it));
     if (rec) return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
     return 0;
+}
+int skb_csr_emit(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
+                 const uint32_t* keep, const int32_t* indptr, int64_t n, const double* wtab, const double* values,
+                 int height, int dtype, int32_t* indices, double* data, skb_i4* rec, const int64_t* slab,
+                 int lin_splitters, uint32_t* startoff, int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch,
+                 void* stream) {
+    return skb_csr_emit_cap(bits, pre256, ndim, shape, lin, keep, indptr, n, wtab, values, height, dtype, indices, data,
+                            rec, slab, lin_splitters, startoff, par, cmin, is_min, scratch, 0x7fffffffLL, stream);
 }
 
 // ---- path tracing (csr.py:347-446): sampled list ranking, see skb_items.cuh ------------------
@@ -189,6 +209,13 @@ int skb_path_start_count(const skb_i4* rec, const uint8_t* covered, const int64_
     return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }
 
+// the first half of skb_path_walk on its own, with a capacity for su / se
+static int skb_path_start_fill_cap(const int32_t* indptr, const uint32_t* startoff, int64_t n, int32_t* su, int32_t* se,
+                                   int64_t cap, void* stream) {
+    return skb_foreach(n, (skb_stream_t)stream,
+                       SkbStartFillItem{indptr, startoff, 0, su, se, cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap});
+}
+
 // su/se i32[S] (node and half-edge of every start leaving an owned node) and the first local walk:
 // ranked i4[S]; aux (48 B per start; NULL on a single GPU) carries sums and the end node; stamp
 // i32[n] (may be NULL, pre-set to -1) remembers a start per chain node passed.
@@ -198,7 +225,8 @@ int skb_path_walk(const int32_t* indptr, const int32_t* indices, const double* g
                   void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     SkbSlab sl = skb_make_slab(slab, n);
-    SKB_TRY(skb_foreach((int64_t)sl.own1 - sl.own0, s, SkbStartFillItem{indptr, startoff, sl.own0, su, se}));
+    if (indptr)  // NULL: su / se were filled by skb_path_start_fill_cap already
+        SKB_TRY(skb_foreach((int64_t)sl.own1 - sl.own0, s, SkbStartFillItem{indptr, startoff, sl.own0, su, se}));
     if (aux)
         return skb_foreach_steps(n_starts, s,
                                  SkbWalkItemT<true>{indices, gdata, values, lin, rec, startoff, su, se, sl, ranked,
@@ -266,16 +294,23 @@ int skb_path_select(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, 
 // per path (ids pid_base + ...): start_node i32 (global id), plen u32 (entries), pmin i32.
 // Single GPU: einfo i4[S] is filled (and cleared first).  Slabs: einfo NULL; head_end i32 and
 // head_aux (48 B each) receive the reversed last start and the sums / end node of every path.
-int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const void* aux,
-                   const uint32_t* sel, int64_t n_starts, int phase, int64_t pid_base, int64_t start_lo,
-                   int64_t id_shift, int32_t* start_node, uint32_t* plen, int32_t* pmin, skb_i4* einfo,
-                   int32_t* head_end, void* head_aux, void* stream) {
+static int skb_path_heads_cap(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const void* aux,
+                              const uint32_t* sel, int64_t n_starts, int phase, int64_t pid_base, int64_t start_lo,
+                              int64_t id_shift, int32_t* start_node, uint32_t* plen, int32_t* pmin, skb_i4* einfo,
+                              int32_t* head_end, void* head_aux, int64_t pid_cap, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     if (einfo) SKB_TRY(skb_fill_bytes(einfo, 0xff, (size_t)n_starts * 16, s));
     return skb_foreach(n_starts, s,
                        SkbHeadsItem{su, rec, ranked, (const SkbAux*)aux, sel, phase, (int32_t)pid_base,
                                     (int32_t)start_lo, (int32_t)id_shift, start_node, plen, pmin, einfo, head_end,
-                                    (SkbAux*)head_aux});
+                                    (SkbAux*)head_aux, pid_cap > 0x7fffffffLL ? 0x7fffffff : (int32_t)pid_cap});
+}
+int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const void* aux,
+                   const uint32_t* sel, int64_t n_starts, int phase, int64_t pid_base, int64_t start_lo,
+                   int64_t id_shift, int32_t* start_node, uint32_t* plen, int32_t* pmin, skb_i4* einfo,
+                   int32_t* head_end, void* head_aux, void* stream) {
+    return skb_path_heads_cap(su, rec, ranked, aux, sel, n_starts, phase, pid_base, start_lo, id_shift, start_node, plen,
+                              pmin, einfo, head_end, head_aux, 0x7fffffffLL, stream);
 }
 
 // second local walk: paths.indices i32[L], paths.data f64[L] (csr.py:396,402; values NULL -> 1.0;

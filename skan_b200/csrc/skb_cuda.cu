@@ -152,14 +152,14 @@ static int skb_ticket_slot(unsigned long long** out) {
     return 0;
 }
 
-// tunables (skb_set_option, or the environment at first use): "dynamic_walks" 0 = one item per thread;
+// tunables (skb_set_option, or the environment at first use): "dynamic_walks" 0 = one item per thread (default);
 // "walk_refill" = idle lanes at which a warp draws new items (1..32)
 static int g_skb_steps_dynamic = -1;
 static int g_skb_steps_refill = SKB_DYN_REFILL;
 static bool skb_steps_dynamic() {
     if (g_skb_steps_dynamic < 0) {
         const char* e = getenv("SKAN_B200_DYNAMIC_WALKS");
-        g_skb_steps_dynamic = (e && e[0] == '0') ? 0 : 1;
+        g_skb_steps_dynamic = (e && e[0] == '1') ? 1 : 0;  // off by default: measured slower on B200
         const char* r = getenv("SKAN_B200_WALK_REFILL");
         if (r && atoi(r) >= 1 && atoi(r) <= 32) g_skb_steps_refill = atoi(r);
     }
@@ -265,7 +265,11 @@ __global__ void skb_mail_kernel(SkbGatherI32Item it, int n, int32_t seq) {
     if (lane == 0) *(volatile int32_t*)(it.out + SKB_MAX_FETCH) = seq;
 }
 
-static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t s) {
+// A read-back in two halves: skb_fetch_post enqueues the mail kernel (it runs when everything enqueued before it
+// has finished), skb_fetch_wait spins until its values have arrived.  Kernels enqueued between the two keep the
+// device busy while the values travel: the runner posts a count, launches the first consumer sized by a
+// capacity hint, and only then waits.  One read-back per host thread may be in flight.
+static int skb_fetch_post(const int32_t* const* ptrs, int n, skb_stream_t s) {
     if (n > SKB_MAX_FETCH) return skb_fail("too many values to fetch");
     SkbMailbox* box;
     {
@@ -278,7 +282,16 @@ static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_s
     const int32_t seq = ++box->seq;
     skb_mail_kernel<<<1, 32, 0, s>>>(it, n, seq);
     SKB_COUNT_LAUNCH(1);
-    SKB_CUDA(cudaGetLastError());
+    return skb_cuda_check(cudaGetLastError(), "read-back launch");
+}
+
+static int skb_fetch_wait(int n, int64_t* out, skb_stream_t s) {
+    SkbMailbox* box;
+    {
+        int e = skb_mailbox(&box);
+        if (e) return e;
+    }
+    const int32_t seq = box->seq;
     for (unsigned spins = 1;; ++spins) {
         if (box->host[SKB_MAX_FETCH] == seq) break;
         if ((spins & 0xfffffu) == 0) {  // ~ every few milliseconds: is the stream still alive?
@@ -289,6 +302,12 @@ static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_s
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
     for (int i = 0; i < n; ++i) out[i] = box->host[i];
     return 0;
+}
+
+static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t s) {
+    int e = skb_fetch_post(ptrs, n, s);
+    if (e) return e;
+    return skb_fetch_wait(n, out, s);
 }
 
 // everything enqueued on the stream so far has completed (an empty read-back)
@@ -849,7 +868,9 @@ template <bool VALUES>  // false: boolean image, no node values (csr.py:554-562)
 __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     const uint64_t* __restrict__ bits, const uint32_t* __restrict__ tile_prefix, int64_t ntiles, SkbGeom g,
     const void* img, int dtype, int64_t z_origin, int64_t* __restrict__ lin, int64_t* __restrict__ coords,
-    double* __restrict__ values_arg, uint32_t* __restrict__ pre256) {
+    double* __restrict__ values_arg, uint32_t* __restrict__ pre256, uint32_t node_cap) {
+    // node_cap: capacity of lin / coords / values (the runner may size them by a hint before the count has
+    // arrived); nodes with id >= node_cap are not written, the rank structure always is
     double* __restrict__ values = VALUES ? values_arg : nullptr;
     __shared__ uint16_t stage[SKB_EMIT_THREADS / 32][SKB_EMIT_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -915,7 +936,7 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
             }
             __syncwarp();
             for (uint32_t i = lane; i < total; i += 32)
-                skb_emit_one(st[i], r0, z0, y0, x0, t0 + i, g, img, dtype, lin, coords, values);
+                if (t0 + i < node_cap) skb_emit_one(st[i], r0, z0, y0, x0, t0 + i, g, img, dtype, lin, coords, values);
             __syncwarp();
         } else if (packed) {  // dense tile: every lane walks its own words
 #pragma unroll
@@ -924,8 +945,10 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
                 uint32_t id = t0 + idj[q >> 1] + ((q & 1) ? (uint32_t)__popcll(w[q - 1]) : 0u);
                 const uint32_t off = (uint32_t)(2 * ((q >> 1) * 32 + lane) + (q & 1)) * 64u;
                 while (x) {
-                    skb_emit_one(off + (uint32_t)(__ffsll((long long)x) - 1), r0, z0, y0, x0, id++, g, img, dtype, lin,
-                                 coords, values);
+                    if (id < node_cap)
+                        skb_emit_one(off + (uint32_t)(__ffsll((long long)x) - 1), r0, z0, y0, x0, id, g, img, dtype, lin,
+                                     coords, values);
+                    ++id;
                     x &= x - 1;
                 }
             }
@@ -1545,22 +1568,34 @@ int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, u
 // nodes in raster order (csr.py:131-132,1088,554-562).  tile_prefix: exclusive scan of the
 // tile counts (ntiles+1).  values may be null (bool images).  pre256: u32[ntiles*64].  z_origin is
 // added to the first coordinate of 3-D images (the volume may be one Z-slab of a larger one).
+int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                       const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                       int64_t* coords, double* values, uint32_t* pre256, int64_t node_cap, void* stream);
 int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
                    const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
                    int64_t* coords, double* values, uint32_t* pre256, void* stream) {
+    return skb_emit_nodes_cap(bits, tile_prefix, ntiles, ndim, shape, image, dtype, z_origin, lin, coords, values,
+                              pre256, 0xffffffffLL, stream);
+}
+
+// the same with a capacity for lin / coords / values: nodes with id >= node_cap are not written
+int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                       const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                       int64_t* coords, double* values, uint32_t* pre256, int64_t node_cap, void* stream) {
     SKB_TRY(skb_check_geom(ndim, shape));
     if (ntiles <= 0) return 0;
     if (values && !image) return skb_fail("values requested without an image");
     if (((uintptr_t)bits & 15) != 0) return skb_fail("mask pointer must be 16-byte aligned");
+    const uint32_t cap32 = node_cap < 0 ? 0u : node_cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)node_cap;
     int64_t grid = (ntiles + SKB_EMIT_THREADS / 32 - 1) / (SKB_EMIT_THREADS / 32);
     int64_t cap = (int64_t)skb_sm_count() * 8;
     if (grid > cap) grid = cap;
     if (values)
         skb_emit_nodes_kernel<true><<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
-            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256);
+            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256, cap32);
     else
         skb_emit_nodes_kernel<false><<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
-            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, nullptr, pre256);
+            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, nullptr, pre256, cap32);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
 }

@@ -262,12 +262,15 @@ struct SkbJuncEmitFn {
     int32_t* eb;
     uint8_t* ek;
     uint64_t* ew;
+    uint32_t cap;  // capacity of the edge arrays (they may be sized by a hint): nothing is written beyond it
     SKB_HD void operator()(int k, int32_t u) {
         if (k > 13 && skb_popc(nb[u]) >= 3) {
-            ea[o] = a;
-            eb[o] = u;
-            ek[o] = (uint8_t)k;
-            ew[o] = skb_f64_bits(wf(a, u, k));
+            if (o < cap) {
+                ea[o] = a;
+                eb[o] = u;
+                ek[o] = (uint8_t)k;
+                ew[o] = skb_f64_bits(wf(a, u, k));
+            }
             ++o;
         }
     }
@@ -285,10 +288,11 @@ struct SkbJuncEmitItem {
     int32_t* eb;
     uint8_t* ek;
     uint64_t* ew;
+    uint32_t cap = 0xffffffffu;
     SKB_HD void operator()(int64_t i) const {
         uint32_t m = nb[i];
         if (skb_popc(m) >= 3 && (m >> 14) && offset[i + 1] != offset[i]) {
-            SkbJuncEmitFn fn{nb, wf, (int32_t)i, offset[i], ea, eb, ek, ew};
+            SkbJuncEmitFn fn{nb, wf, (int32_t)i, offset[i], ea, eb, ek, ew, cap};
             skb_for_neighbors(g, bits, pre256, lin[i], (int32_t)i, m & ~((1u << 14) - 1u), fn);
         }
     }
@@ -586,10 +590,13 @@ struct SkbCsrEmitFn {
     int32_t first;      // position of the row's first entry
     int32_t n0, n1;     // the first two neighbours and their weights (the record of a degree-2 node)
     double w0, w1;
+    int32_t cap;        // capacity of indices / data (they may be sized by a hint): nothing is written beyond it
     SKB_HD void operator()(int k, int32_t u) {
         double w = wf(a, u, k);
-        indices[o] = u;
-        data[o] = w;
+        if (o < cap) {
+            indices[o] = u;
+            data[o] = w;
+        }
         if (o == first) {
             n0 = u;
             w0 = w;
@@ -613,10 +620,11 @@ struct SkbCsrEmitItem {
     double* data;
     int32_t with_records;  // also write the node record the path stage walks on
     SkbRecOut out;
+    int32_t cap = 0x7fffffff;
     SKB_HD void operator()(int64_t i) const {
         uint32_t m = keep[i];
         int32_t o = indptr[i];
-        SkbCsrEmitFn fn{wf, (int32_t)i, o, indices, data, o, -1, -1, 0.0, 0.0};
+        SkbCsrEmitFn fn{wf, (int32_t)i, o, indices, data, o, -1, -1, 0.0, 0.0, cap};
         if (m) skb_for_neighbors(g, bits, pre256, lin[i], (int32_t)i, m, fn);
         if (with_records) out.write(i, o, fn.o - o, fn.n0, fn.n1, fn.w0, fn.w1);
     }
@@ -646,12 +654,13 @@ struct SkbStartFillItem {  // over owned nodes (item index is relative to own0)
     int32_t own0;
     int32_t* su;
     int32_t* se;
+    uint32_t cap = 0xffffffffu;  // capacity of su / se (they may be sized by a hint)
     SKB_HD void operator()(int64_t i) const {
         int64_t v = i + own0;
         uint32_t base = startoff[own0];
         uint32_t s0 = startoff[v] - base, c = startoff[v + 1] - startoff[v];
         int32_t o = indptr[v];
-        for (uint32_t j = 0; j < c; ++j) {
+        for (uint32_t j = 0; j < c && s0 + j < cap; ++j) {
             su[s0 + j] = (int32_t)v;
             se[s0 + j] = o + (int32_t)j;
         }
@@ -1005,10 +1014,12 @@ struct SkbHeadsItem {  // over starts: path id, start node, length, minimum node
     skb_i4* einfo;      // single GPU: pre-set to -1; einfo[reversed last start] = (path id, half-edges, -, -)
     int32_t* head_end;  // slabs: id of the reversed last start of every path
     SkbAux* head_aux;   // slabs: sums and end node of every path
+    int32_t pid_cap = 0x7fffffff;  // capacity of the per-path arrays (they may be sized by a hint)
     SKB_HD void operator()(int64_t s) const {
         skb_i4 a = skb_ld_i4(ranked + s);
         if (!skb_start_is_head(skb_ld_i4(rec + 2 * (int64_t)su[s]), a, s + start_lo, phase)) return;
         int32_t pid = pid_base + (int32_t)sel[s];
+        if (pid >= pid_cap) return;
         start_node[pid] = su[s] + id_shift;
         plen[pid] = (uint32_t)a.y + 1u;
         pmin[pid] = a.z;

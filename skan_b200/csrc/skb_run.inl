@@ -22,8 +22,11 @@ enum {
 // indices into skb_run_result.counts
 enum {
     SKB_C_NODES = 0, SKB_C_EDGES, SKB_C_PATHS, SKB_C_REGULAR, SKB_C_CYCLES, SKB_C_ENTRIES, SKB_C_JUNCTION_EDGES,
-    SKB_C_STARTS, SKB_C_SYNCS, SKB_C_SWEEP_NS, SKB_C_COUNT
+    SKB_C_STARTS, SKB_C_SYNCS, SKB_C_SWEEP_NS, SKB_C_OVERLAPPED, SKB_C_RETAKEN, SKB_C_COUNT
 };
+// indices into skb_run_params.hint: capacities for the arrays sized by a count that is still on its way to the
+// host when their first consumer is launched (0 = no hint: wait for the count, then launch)
+enum { SKB_H_JUNCTION_EDGES = 0, SKB_H_EDGES, SKB_H_STARTS, SKB_H_REGULAR, SKB_H_COUNT };
 // stage boundaries of skb_run_result.stage_ns (time_sweep == 2): stage_ns[i] = device time between
 // the previous boundary and boundary i, host synchronisation bubbles included
 enum {
@@ -53,7 +56,10 @@ struct skb_run_params {
     void* out;
     int64_t out_bytes;
     void* stream;
-    int64_t node_cap_hint;  // pack_variant 2: capacity of the node arrays the fused sweep writes (0 = V/256 + 4096)
+    int64_t node_cap_hint;  // capacity hint for the node arrays (fused sweep: 0 = V/256 + 4096; else 0 = no hint)
+    int64_t hint[8];        // SKB_H_*: capacity hints, typically the counts of the previous image of this kind plus
+                            // slack.  With a hint the read-back of the count overlaps the first kernel that fills
+                            // the arrays it sizes; a hint that turns out too small costs that kernel a second launch.
 };
 
 struct skb_run_result {
@@ -107,6 +113,20 @@ struct SkbArena {
         ++nsync;                                              \
     } while (0)
 
+// posted read-back of one count (see skb_fetch_post): the kernels launched before SKB_WAIT overlap its round trip
+#define SKB_POST(ptr)                                       \
+    do {                                                    \
+        const int32_t* _p[1] = {(const int32_t*)(ptr)};     \
+        SKB_TRY(skb_fetch_post(_p, 1, s));                  \
+    } while (0)
+#define SKB_WAIT(dst)                         \
+    do {                                      \
+        int64_t _v[1] = {0};                  \
+        SKB_TRY(skb_fetch_wait(1, _v, s));    \
+        (dst) = _v[0];                        \
+        ++nsync;                              \
+    } while (0)
+
 extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     skb_stream_t s = (skb_stream_t)prm->stream;
     const int ndim = prm->ndim;
@@ -115,7 +135,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SkbGeom g = skb_make_geom(ndim, prm->shape);
     const int64_t V = g.nvox;
     const int64_t ntiles = (V + SKB_TILE_VOX - 1) / SKB_TILE_VOX;
-    int64_t nsync = 0;
+    int64_t nsync = 0, noverlap = 0, nretaken = 0;
     for (int i = 0; i < 16; ++i) res->counts[i] = 0;
     for (int i = 0; i < 32; ++i) res->off[i] = -1;
     res->work_need = res->out_need = 0;
@@ -197,13 +217,34 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
         SKB_TRY(skb_scan_u32_impl(tile_prefix, tile_prefix, ntiles, scratch, s));
         SKB_MARK(SKB_M_SWEEP);
-        SKB_FETCH(N, tile_prefix + ntiles);
-        lin = out.take<int64_t>(N);
-        coords = out.take<int64_t>(N * ndim);
-        values = want_values ? out.take<double>(N) : nullptr;
-        SKB_NEED(out.ok);
-        SKB_TRY(skb_emit_nodes(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype, prm->z_origin, lin,
-                               coords, values, pre256, s));
+        int64_t cap = prm->node_cap_hint > 0 ? prm->node_cap_hint : 0;
+        if (cap > V) cap = V;
+        const int64_t out_mark = out.off;
+        bool emitted = false;
+        SKB_POST(tile_prefix + ntiles);
+        if (cap > 0) {  // node emission sized by the hint runs while the count travels
+            lin = out.take<int64_t>(cap);
+            coords = out.take<int64_t>(cap * ndim);
+            values = want_values ? out.take<double>(cap) : nullptr;
+            if (out.ok) {
+                SKB_TRY(skb_emit_nodes_cap(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype,
+                                           prm->z_origin, lin, coords, values, pre256, cap, s));
+                emitted = true;
+                ++noverlap;
+            }
+        }
+        SKB_WAIT(N);
+        if (!emitted || N > cap) {
+            if (emitted) ++nretaken;
+            out.off = out_mark;
+            out.ok = true;
+            lin = out.take<int64_t>(N);
+            coords = out.take<int64_t>(N * ndim);
+            values = want_values ? out.take<double>(N) : nullptr;
+            SKB_NEED(out.ok);
+            SKB_TRY(skb_emit_nodes(bits, tile_prefix, ntiles, ndim, prm->shape, prm->image, prm->dtype, prm->z_origin,
+                                   lin, coords, values, pre256, s));
+        }
     }
     if (prm->time_sweep) SKB_TRY(skb_timer_read_ns(ev, &res->counts[SKB_C_SWEEP_NS]));
     res->counts[SKB_C_NODES] = N;
@@ -229,26 +270,57 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SKB_TRY(skb_scan_u32_impl(jcount, jcount, N, scratch, s));
     SKB_MARK(SKB_M_JCOUNT);
     int64_t nej;
-    SKB_FETCH(nej, jcount + N);
-    res->counts[SKB_C_JUNCTION_EDGES] = nej;
     uint32_t* keep = nb;
     int32_t *ea = nullptr, *eb = nullptr;
     uint8_t *ek = nullptr, *tree = nullptr;
-    if (nej) {
-        ea = work.take<int32_t>(nej);
-        eb = work.take<int32_t>(nej);
-        ek = work.take<uint8_t>(nej);
-        uint64_t* ew = work.take<uint64_t>(nej);
-        int32_t* mpar = work.take<int32_t>(N);
-        uint64_t* bestw = work.take<uint64_t>(N);
-        uint32_t* beste = work.take<uint32_t>(N);
-        int32_t* era = work.take<int32_t>(nej);
-        int32_t* erb = work.take<int32_t>(nej);
-        tree = work.take<uint8_t>(nej);
+    uint64_t* ew = nullptr;
+    int32_t *mpar = nullptr, *era = nullptr, *erb = nullptr;
+    uint64_t* bestw = nullptr;
+    uint32_t* beste = nullptr;
+    auto take_junction = [&](int64_t cap) {
+        ea = work.take<int32_t>(cap);
+        eb = work.take<int32_t>(cap);
+        ek = work.take<uint8_t>(cap);
+        ew = work.take<uint64_t>(cap);
+        mpar = work.take<int32_t>(N);
+        bestw = work.take<uint64_t>(N);
+        beste = work.take<uint32_t>(N);
+        era = work.take<int32_t>(cap);
+        erb = work.take<int32_t>(cap);
+        tree = work.take<uint8_t>(cap);
         keep = work.take<uint32_t>(N);
-        SKB_NEED(work.ok);
-        SKB_TRY(skb_junction_edge_emit(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values, height,
-                                       prm->dtype, ea, eb, ek, ew, s));
+    };
+    {
+        const int64_t cap = prm->hint[SKB_H_JUNCTION_EDGES] > 0 ? prm->hint[SKB_H_JUNCTION_EDGES] : 0;
+        const int64_t work_mark = work.off;
+        bool emitted = false;
+        SKB_POST(jcount + N);
+        if (cap > 0) {  // edge emission sized by the hint runs while the count travels
+            take_junction(cap);
+            if (work.ok) {
+                SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values,
+                                                   height, prm->dtype, ea, eb, ek, ew, cap, s));
+                emitted = true;
+                ++noverlap;
+            }
+        }
+        SKB_WAIT(nej);
+        if (nej && (!emitted || nej > cap)) {
+            if (emitted) ++nretaken;
+            work.off = work_mark;
+            work.ok = true;
+            take_junction(nej);
+            SKB_NEED(work.ok);
+            SKB_TRY(skb_junction_edge_emit(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values, height,
+                                           prm->dtype, ea, eb, ek, ew, s));
+        } else if (!nej) {
+            work.off = work_mark;
+            work.ok = true;
+            keep = nb;
+        }
+    }
+    res->counts[SKB_C_JUNCTION_EDGES] = nej;
+    if (nej) {
         int r = skb_mst_junctions(ea, eb, ew, nej, N, mpar, bestw, beste, era, erb, tree, flag, s);
         if (r < 0) return r;
         SKB_TRY(skb_copy_bytes(keep, nb, (size_t)N * 4, s));
@@ -262,19 +334,50 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SKB_TRY(skb_degrees_indptr(keep, N, deg, indptr, scratch, s));
     SKB_MARK(SKB_M_DEGREES);
     int64_t E;
-    SKB_FETCH(E, indptr + N);
-    res->counts[SKB_C_EDGES] = E;
-    int32_t* indices = out.take<int32_t>(E);
-    double* data = out.take<double>(E);
     const bool paths_wanted = !prm->stop_after_graph;
-    skb_i4* rec = paths_wanted ? work.take<skb_i4>(2 * N) : nullptr;
-    uint32_t* startoff = paths_wanted ? work.take<uint32_t>(N + 1) : nullptr;
-    int32_t* cc_par = paths_wanted ? work.take<int32_t>(N) : nullptr;
-    int32_t* cc_min = paths_wanted ? work.take<int32_t>(N) : nullptr;
-    uint32_t* is_min = paths_wanted ? out.take<uint32_t>(N + 1) : nullptr;
-    SKB_NEED(work.ok && out.ok);
-    SKB_TRY(skb_csr_emit(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height, prm->dtype,
-                         indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min, scratch, s));
+    int32_t* indices = nullptr;
+    double* data = nullptr;
+    skb_i4* rec = nullptr;
+    uint32_t* startoff = nullptr;
+    int32_t *cc_par = nullptr, *cc_min = nullptr;
+    uint32_t* is_min = nullptr;
+    auto take_csr = [&](int64_t cap) {
+        indices = out.take<int32_t>(cap);
+        data = out.take<double>(cap);
+        rec = paths_wanted ? work.take<skb_i4>(2 * N) : nullptr;
+        startoff = paths_wanted ? work.take<uint32_t>(N + 1) : nullptr;
+        cc_par = paths_wanted ? work.take<int32_t>(N) : nullptr;
+        cc_min = paths_wanted ? work.take<int32_t>(N) : nullptr;
+        is_min = paths_wanted ? out.take<uint32_t>(N + 1) : nullptr;
+    };
+    {
+        const int64_t cap = prm->hint[SKB_H_EDGES] > 0 ? prm->hint[SKB_H_EDGES] : 0;
+        const int64_t work_mark = work.off, out_mark = out.off;
+        bool emitted = false;
+        SKB_POST(indptr + N);
+        if (cap > 0) {  // CSR emission sized by the hint runs while the count travels
+            take_csr(cap);
+            if (work.ok && out.ok) {
+                SKB_TRY(skb_csr_emit_cap(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height,
+                                         prm->dtype, indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min,
+                                         scratch, cap, s));
+                emitted = true;
+                ++noverlap;
+            }
+        }
+        SKB_WAIT(E);
+        if (!emitted || E > cap) {
+            if (emitted) ++nretaken;
+            work.off = work_mark;
+            out.off = out_mark;
+            work.ok = out.ok = true;
+            take_csr(E);
+            SKB_NEED(work.ok && out.ok);
+            SKB_TRY(skb_csr_emit(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height,
+                                 prm->dtype, indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min, scratch, s));
+        }
+    }
+    res->counts[SKB_C_EDGES] = E;
     SKB_MARK(SKB_M_CSR);
     res->off[SKB_O_DEGREES] = out_off(deg);
     res->off[SKB_O_INDPTR] = out_off(indptr);
@@ -284,6 +387,8 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     if (!paths_wanted || N == 0 || E == 0) {
         SKB_MARKS_DONE();
         res->counts[SKB_C_SYNCS] = nsync;
+    res->counts[SKB_C_OVERLAPPED] = noverlap;
+    res->counts[SKB_C_RETAKEN] = nretaken;
         return 0;
     }
     // ---- paths: phase 0 (between terminals), phase 1 (junction-free cycles) ------------------------------------
@@ -294,18 +399,45 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         uint32_t* sel;
     };
     auto run_phase = [&](int ph, const uint32_t* so, Phase& P, int64_t* n_heads) -> int {
-        SKB_FETCH(P.S, so + N);
+        skb_i4* buf1 = nullptr;
+        auto take_starts = [&](int64_t cap) {
+            P.su = work.take<int32_t>(cap);
+            P.se = work.take<int32_t>(cap);
+            P.ranked = work.take<skb_i4>(cap);
+            buf1 = work.take<skb_i4>(cap);
+            P.sel = work.take<uint32_t>(cap + 1);
+            P.einfo = work.take<skb_i4>(cap);
+        };
+        const int64_t cap = (ph == 0 && prm->hint[SKB_H_STARTS] > 0) ? prm->hint[SKB_H_STARTS] : 0;
+        const int64_t work_mark = work.off;
+        bool filled = false;
+        SKB_POST(so + N);
+        if (cap > 0) {  // the start lists sized by the hint are filled while the count travels
+            take_starts(cap);
+            if (work.ok) {
+                SKB_TRY(skb_path_start_fill_cap(indptr, so, N, P.su, P.se, cap, s));
+                filled = true;
+                ++noverlap;
+            }
+        }
+        SKB_WAIT(P.S);
         *n_heads = 0;
-        if (P.S == 0) return 0;
-        P.su = work.take<int32_t>(P.S);
-        P.se = work.take<int32_t>(P.S);
-        P.ranked = work.take<skb_i4>(P.S);
-        skb_i4* buf1 = work.take<skb_i4>(P.S);
-        P.sel = work.take<uint32_t>(P.S + 1);
-        P.einfo = work.take<skb_i4>(P.S);
-        if (!work.ok) return SKB_RUN_NEED_MORE;
-        SKB_TRY(skb_path_walk(indptr, indices, data, values, nullptr, rec, so, nullptr, N, P.S, P.su, P.se, P.ranked,
-                              nullptr, nullptr, s));
+        if (P.S == 0) {
+            work.off = work_mark;
+            work.ok = true;
+            return 0;
+        }
+        if (!filled || P.S > cap) {
+            if (filled) ++nretaken;
+            work.off = work_mark;
+            work.ok = true;
+            take_starts(P.S);
+            if (!work.ok) return SKB_RUN_NEED_MORE;
+            filled = false;
+        }
+        // indptr NULL: su / se are filled already
+        SKB_TRY(skb_path_walk(filled ? nullptr : indptr, indices, data, values, nullptr, rec, so, nullptr, N, P.S, P.su,
+                              P.se, P.ranked, nullptr, nullptr, s));
         if (ph == 0) SKB_MARK(SKB_M_WALK);
         int r = skb_path_rank(P.ranked, buf1, nullptr, nullptr, P.S, 0, P.S, flag, s);
         if (r < 0) return r;
@@ -313,6 +445,11 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         if (ph == 0) SKB_MARK(SKB_M_RANK);
         SKB_TRY(skb_path_select(P.su, rec, P.ranked, P.S, ph, 0, P.sel, scratch, s));
         if (ph == 0) SKB_MARK(SKB_M_SELECT);
+        if (ph == 0 && prm->hint[SKB_H_REGULAR] > 0) {
+            SKB_POST(P.sel + P.S);  // the caller launches the heads pass sized by the hint, then waits
+            *n_heads = -1;
+            return 0;
+        }
         SKB_FETCH(*n_heads, P.sel + P.S);
         return 0;
     };
@@ -324,36 +461,70 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         if (r) return r;
     }
     res->counts[SKB_C_STARTS] = A.S;
-    const int64_t P_cap = n_regular + E / 6 + 1;
-    int32_t* start_node = work.take<int32_t>(P_cap);
-    uint32_t* plen = work.take<uint32_t>(P_cap + 1);
-    int32_t* pmin = work.take<int32_t>(P_cap);
-    int32_t* pindptr = out.take<int32_t>(P_cap + 1);
-    SKB_NEED(work.ok && out.ok);
-    int64_t L_reg = 0;
-    if (n_regular) {
-        SKB_TRY(skb_path_heads(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin, A.einfo,
-                               nullptr, nullptr, s));
-        SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, n_regular, scratch, s));
-        SKB_MARK(SKB_M_HEADS);
-        SKB_FETCH(L_reg, pindptr + n_regular);
+    int32_t *start_node = nullptr, *pmin = nullptr, *pindptr = nullptr;
+    uint32_t* plen = nullptr;
+    auto take_paths = [&](int64_t regular_cap) {
+        const int64_t P_cap = regular_cap + E / 6 + 1;  // a junction-free cycle has at least 3 edges
+        start_node = work.take<int32_t>(P_cap);
+        plen = work.take<uint32_t>(P_cap + 1);
+        pmin = work.take<int32_t>(P_cap);
+        pindptr = out.take<int32_t>(P_cap + 1);
+    };
+    bool heads_done = false;
+    if (n_regular < 0) {  // the count of regular paths is on its way: the heads pass sized by the hint runs meanwhile
+        const int64_t cap = prm->hint[SKB_H_REGULAR];
+        const int64_t work_mark = work.off, out_mark = out.off;
+        take_paths(cap);
+        if (work.ok && out.ok) {
+            SKB_TRY(skb_path_heads_cap(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin,
+                                       A.einfo, nullptr, nullptr, cap, s));
+            heads_done = true;
+            ++noverlap;
+        }
+        SKB_WAIT(n_regular);
+        if (!heads_done || n_regular > cap) {
+            if (heads_done) ++nretaken;
+            work.off = work_mark;
+            out.off = out_mark;
+            work.ok = out.ok = true;
+            heads_done = false;
+        }
     }
-    int64_t n_uncovered = E / 2 - (L_reg - n_regular);
-    if (n_uncovered < 0) n_uncovered = 0;
-    const int64_t L_cap = L_reg + n_uncovered + n_uncovered / 3 + 1;
+    if (!heads_done) {
+        take_paths(n_regular);
+        SKB_NEED(work.ok && out.ok);
+        if (n_regular)
+            SKB_TRY(skb_path_heads(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin, A.einfo,
+                                   nullptr, nullptr, s));
+    }
+    // Entries: every undirected edge is on exactly one path, so L = E/2 + P; with at most E/6 cycles the arrays can
+    // be sized, and the second walk launched, before the number of entries on regular paths (which tells how
+    // many chain voxels no regular path covers) has arrived.
+    const int64_t L_cap = E / 2 + n_regular + E / 6 + 1;
     int32_t* pidx = out.take<int32_t>(L_cap);
     double* pdata = out.take<double>(L_cap);
     double* pw = out.take<double>(L_cap);
-    uint8_t* covered = n_uncovered > 0 ? work.take<uint8_t>(N) : nullptr;
+    uint8_t* covered = work.take<uint8_t>(N);
     SKB_NEED(work.ok && out.ok);
-    if (covered) SKB_TRY(skb_fill_bytes(covered, 0, (size_t)N, s));
+    int64_t L_reg = 0;
+    if (n_regular) {
+        SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, n_regular, scratch, s));
+        SKB_MARK(SKB_M_HEADS);
+        SKB_POST(pindptr + n_regular);
+    }
+    SKB_TRY(skb_fill_bytes(covered, 0, (size_t)N, s));
     // boolean image: paths.data is all ones (csr.py:207-215) -- one coalesced fill instead of a scattered 8-byte
     // store per path entry in the walks below
     double* pdata_w = values ? pdata : nullptr;
     if (!values) SKB_TRY(skb_foreach(L_cap, s, SkbFillF64Item{pdata, 1.0}));
-    if (n_regular)
+    if (n_regular) {
         SKB_TRY(skb_path_emit(indices, data, rec, A.su, A.se, A.ranked, A.einfo, pindptr, values, covered, 0, A.S, pidx,
                               pdata_w, pw, s));
+        ++noverlap;
+        SKB_WAIT(L_reg);
+    }
+    int64_t n_uncovered = E / 2 - (L_reg - n_regular);
+    if (n_uncovered < 0) n_uncovered = 0;
     SKB_MARK(SKB_M_EMIT);
     if (n_uncovered > 0) {
         int32_t* cpar = work.take<int32_t>(N);
@@ -386,6 +557,8 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     if (P == 0) {
         SKB_MARKS_DONE();
         res->counts[SKB_C_SYNCS] = nsync;
+    res->counts[SKB_C_OVERLAPPED] = noverlap;
+    res->counts[SKB_C_RETAKEN] = nretaken;
         return 0;
     }
     // ---- skeleton ids, statistics, branch table ----------------------------------------------------------------------
@@ -415,6 +588,8 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     res->off[SKB_O_T64] = out_off(t64);
     res->off[SKB_O_TF] = out_off(tf);
     res->counts[SKB_C_SYNCS] = nsync;
+    res->counts[SKB_C_OVERLAPPED] = noverlap;
+    res->counts[SKB_C_RETAKEN] = nretaken;
     res->work_need = work.need;
     res->out_need = out.need;
     return 0;

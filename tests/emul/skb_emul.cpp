@@ -66,6 +66,17 @@ static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_s
     for (int i = 0; i < n; ++i) out[i] = *ptrs[i];
     return 0;
 }
+// two-part read-back: the values are taken when the request is posted (on the device the mail kernel runs in
+// stream order, i.e. before anything enqueued after the post), and handed over by the wait
+static thread_local int64_t g_skb_posted[16];
+static int skb_fetch_post(const int32_t* const* ptrs, int n, skb_stream_t) {
+    for (int i = 0; i < n; ++i) g_skb_posted[i] = *ptrs[i];
+    return 0;
+}
+static int skb_fetch_wait(int n, int64_t* out, skb_stream_t) {
+    for (int i = 0; i < n; ++i) out[i] = g_skb_posted[i];
+    return 0;
+}
 static int skb_stream_sync(skb_stream_t) { return 0; }
 
 // exchange arena of the Z-slab mode: POSIX shared memory stands in for CUDA IPC device memory
@@ -172,9 +183,18 @@ int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, u
     return 0;
 }
 
+int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                       const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                       int64_t* coords, double* values, uint32_t* pre256, int64_t node_cap, void*);
 int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
                    const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
-                   int64_t* coords, double* values, uint32_t* pre256, void*) {
+                   int64_t* coords, double* values, uint32_t* pre256, void* stream) {
+    return skb_emit_nodes_cap(bits, tile_prefix, ntiles, ndim, shape, image, dtype, z_origin, lin, coords, values,
+                              pre256, 0xffffffffLL, stream);
+}
+int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
+                       const int64_t* shape, const void* image, int dtype, int64_t z_origin, int64_t* lin,
+                       int64_t* coords, double* values, uint32_t* pre256, int64_t node_cap, void*) {
     SKB_TRY(skb_check_geom(ndim, shape));
     SkbGeom g = skb_make_geom(ndim, shape);
     for (int64_t t = 0; t < ntiles; ++t) {
@@ -187,6 +207,10 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
                 int b = __builtin_ctzll(word);
                 word &= word - 1;
                 int64_t r = wi * 64 + b;
+                if ((int64_t)id >= node_cap) {  // beyond the capacity of the node arrays: counted, not written
+                    ++id;
+                    continue;
+                }
                 lin[id] = r;
                 int32_t z, y, x;
                 skb_coords(g, r, z, y, x);
@@ -226,6 +250,10 @@ int skb_sweep_nodes(const void* image, int dtype, int ndim, const int64_t* shape
             word &= word - 1;
             if (id < node_cap) {
                 int64_t r = wi * 64 + b;
+                if ((int64_t)id >= node_cap) {  // beyond the capacity of the node arrays: counted, not written
+                    ++id;
+                    continue;
+                }
                 lin[id] = r;
                 int32_t z, y, x;
                 skb_coords(g, r, z, y, x);

@@ -282,5 +282,5 @@ def test_walk_scheduling_variants_vs_oracle(dynamic, refill):
         assert np.array_equal(sk.paths.indices, base.paths.indices)
         assert np.array_equal(sk.path_lengths(), base.path_lengths())
     finally:
-        lib.call('skb_set_option', b'dynamic_walks', 1)
+        lib.call('skb_set_option', b'dynamic_walks', 0)
         lib.call('skb_set_option', b'walk_refill', 8)
