@@ -252,6 +252,19 @@ int skb_slab_path_stats(const uint32_t* plen, const void* head_aux, int64_t n_pa
 int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int64_t* lin, int64_t n_paths,
                          int64_t* image, void* stream);
 
+/* Sholl analysis (csr.py:1332-1390).  skb_sholl_bins: per node, the distance of
+ * coordinates * spacing from `center` (fp64, the arithmetic of scipy.spatial.distance_matrix, csr.py:1376-1377)
+ * and its shell index np.digitize(d, radii) (csr.py:1378-1379).  center / spacing_f / spacing_i: host arrays of 3
+ * (ndim used); radii: device f64[n_radii], monotonic (decreasing != 0 when decreasing).  bins i32[n], dist f64[n],
+ * max_bits u64[1] (pre-zeroed; bit pattern of the largest distance, csr.py:1314-1316) may each be NULL.
+ * skb_sholl_count: hist u64[n_radii+1] (pre-zeroed) += 1 at min(shell of i, shell of j) for every directed edge
+ * (i, j) whose ends lie in different shells (csr.py:1380-1385; halve for the undirected count). */
+int skb_sholl_bins(const int64_t* coords, int64_t n, int ndim, int spacing_is_int, const double* spacing_f /*host*/,
+                   const int64_t* spacing_i /*host*/, const double* center /*host*/, const double* radii,
+                   int64_t n_radii, int decreasing, int32_t* bins, double* dist, uint64_t* max_bits, void* stream);
+int skb_sholl_count(const int32_t* indptr, const int32_t* indices, const int32_t* bins, int64_t n,
+                    unsigned long long* hist, void* stream);
+
 /* ---- The whole hot path for one image (or one stack of 2-D images) in one call ---------------------
  * Native twin of the per-stage sequencing: same kernels in the same order; allocation is a bump
  * pointer into two caller-provided device arenas (`work`: scratch, `out`: results), the counts that

@@ -68,6 +68,8 @@ _SIGNATURES = {
     'skb_slab_path_stats': (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'skb_path_label_image': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     'skb_scan_u32': (_int, [_vp, _vp, _i64, _vp, _vp]),
+    'skb_sholl_bins': (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
+    'skb_sholl_count': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
 }
 
 

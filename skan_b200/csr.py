@@ -371,3 +371,7 @@ def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=
         df['main'] = find_main_branches(df)
     df.rename(columns=lambda s: s.replace('_', separator), inplace=True)
     return df
+
+
+# Sholl analysis (csr.py:1211-1390): device kernels for the node / edge part, see _sholl.py
+from ._sholl import _fast_graph_center_idx, _simplify_graph, sholl_analysis  # noqa: E402,F401

@@ -567,6 +567,35 @@ int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int6
     return skb_foreach(n_paths, (skb_stream_t)stream, SkbLabelImageItem{pindptr, pidx, lin, image});
 }
 
+// ---- Sholl analysis (csr.py:1332-1390), see skb_sholl.cuh ------------------------------------------------
+// Per node: distance from `center` of coordinates * spacing and its shell index np.digitize(d, radii).
+// center / spacing_f / spacing_i: host, 3 entries (ndim used).  radii: device f64[n_radii], monotonic
+// (decreasing != 0: decreasing).  Any of bins i32[n], dist f64[n], max_bits u64[1] (pre-zeroed; receives the
+// bit pattern of the largest distance) may be NULL; bins needs radii.
+int skb_sholl_bins(const int64_t* coords, int64_t n, int ndim, int spacing_is_int, const double* spacing_f,
+                   const int64_t* spacing_i, const double* center, const double* radii, int64_t n_radii,
+                   int decreasing, int32_t* bins, double* dist, uint64_t* max_bits, void* stream) {
+    if (ndim < 1 || ndim > 3) return skb_fail("ndim must be 1, 2 or 3");
+    if (bins && (!radii || n_radii < 1 || n_radii > 0x7fffffffLL)) return skb_fail("shell indices need radii");
+    SkbShollGeom g;
+    for (int k = 0; k < 3; ++k) {
+        g.center[k] = k < ndim ? center[k] : 0.0;
+        g.spacing_f[k] = k < ndim ? spacing_f[k] : 1.0;
+        g.spacing_i[k] = k < ndim ? spacing_i[k] : 1;
+    }
+    g.ndim = ndim;
+    g.spacing_is_int = spacing_is_int ? 1 : 0;
+    return skb_foreach(n, (skb_stream_t)stream,
+                       SkbShollBinItem{g, coords, radii, (int32_t)n_radii, decreasing ? 1 : 0, bins, dist, max_bits});
+}
+
+// hist u64[n_radii + 1], zeroed by the caller: hist[s] += 1 for every DIRECTED edge whose endpoints lie in
+// different shells, s = the smaller shell index (np.bincount(np.minimum(bins0, bins1)[crossings]))
+int skb_sholl_count(const int32_t* indptr, const int32_t* indices, const int32_t* bins, int64_t n,
+                    unsigned long long* hist, void* stream) {
+    return skb_foreach(n, (skb_stream_t)stream, SkbShollCountItem{indptr, indices, bins, hist});
+}
+
 int skb_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, void* stream) {
     return skb_scan_u32_impl(in, out, n, scratch, (skb_stream_t)stream);
 }

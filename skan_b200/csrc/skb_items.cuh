@@ -1905,3 +1905,5 @@ struct SkbLabelImageItem {
         }
     }
 };
+
+#include "skb_sholl.cuh"

@@ -37,6 +37,11 @@ SKB_HD uint64_t skb_atomic_min_u64(uint64_t* p, uint64_t v) {
 SKB_HD uint32_t skb_atomic_min_u32(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 SKB_HD uint32_t skb_atomic_and_u32(uint32_t* p, uint32_t v) { return atomicAnd(p, v); }
 SKB_HD int32_t skb_atomic_cas_i32(int32_t* p, int32_t cmp, int32_t v) { return atomicCAS(p, cmp, v); }
+SKB_HD void skb_atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+// maximum of a value that few items raise: look before the atomic
+SKB_HD void skb_atomic_max_u64_lazy(uint64_t* p, uint64_t v) {
+    if (__ldcg((const unsigned long long*)p) < v) atomicMax((unsigned long long*)p, (unsigned long long)v);
+}
 SKB_HD int32_t skb_ld_cg(const int32_t* p) { return __ldcg(p); }
 SKB_HD uint32_t skb_ld_cg(const uint32_t* p) { return __ldcg(p); }
 SKB_HD uint64_t skb_ld_cg(const uint64_t* p) { return (uint64_t)__ldcg((const unsigned long long*)p); }
@@ -79,6 +84,10 @@ SKB_HD int32_t skb_atomic_cas_i32(int32_t* p, int32_t cmp, int32_t v) {
     int32_t o = *p;
     if (o == cmp) *p = v;
     return o;
+}
+SKB_HD void skb_atomic_add_u64(unsigned long long* p, unsigned long long v) { *p += v; }
+SKB_HD void skb_atomic_max_u64_lazy(uint64_t* p, uint64_t v) {
+    if (*p < v) *p = v;
 }
 SKB_HD int32_t skb_ld_cg(const int32_t* p) { return *p; }
 SKB_HD uint32_t skb_ld_cg(const uint32_t* p) { return *p; }
