@@ -28,7 +28,7 @@ def main():
     lib = _native.library()
     V = int(np.prod(shape, dtype=np.int64))
     # (name, dynamic walks, refill threshold, capacity hints)
-    variants = [('static, no hints', 0, 8, False), ('static, hints', 0, 8, True), ('dynamic r8, hints', 1, 8, True),
+    variants = [('static, no hints', 0, 8, False), ('static, hints', 0, 8, True),
                 ('static, no hints (2)', 0, 8, False), ('static, hints (2)', 0, 8, True)]
     for name, dyn, refill, hints in variants:
         lib.call('skb_set_option', b'dynamic_walks', dyn)

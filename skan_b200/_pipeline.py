@@ -156,10 +156,12 @@ def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant
     g = SimpleNamespace(ctx=ctx, shape=tuple(shape), ndim=ndim, np_dtype=np_dtype, dtype_code=code,
                         spacing=spacing, value_is_height=bool(value_is_height), nvox=V)
     # --- mask sweep: 1 bit / voxel + per-tile counts, then the tile prefix ------------------
-    store = ctx.empty(ntiles * 256 + 4, torch.int64)   # two zero pad words on either side (16-byte aligned mask)
-    store[:2] = 0
+    # zero pad words on either side; the mask starts one 128-byte line into the allocation, so every 256-bit
+    # block of the rank structure is one 32-byte sector
+    store = ctx.empty(ntiles * 256 + 18, torch.int64)
+    store[:16] = 0
     store[-2:] = 0
-    bits = store[2:-2]
+    bits = store[16:-2]
     tile_prefix = ctx.empty(ntiles + 1, torch.int32)
     if V > 0:
         ctx.call('skb_pack_count', img, code, V, bits, tile_prefix, ntiles, variant)

@@ -375,3 +375,30 @@ def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=
 
 # Sholl analysis (csr.py:1211-1390): device kernels for the node / edge part, see _sholl.py
 from ._sholl import _fast_graph_center_idx, _simplify_graph, sholl_analysis  # noqa: E402,F401
+
+
+def skeleton_to_nx(skeleton, summary=None):
+    """Convert a Skeleton to a networkx MultiGraph (csr.py:1393-1435): one node per junction / endpoint, one edge
+    per path carrying its pixel coordinates ('path'), node ids ('indices') and pixel values ('values').  A host
+    container built from the P-row branch table, like in the reference."""
+    import networkx as nx
+    if summary is None:
+        summary = summarize(skeleton, separator='_')
+    csum = summary.rename(columns=lambda s: s.replace('-', '_'))
+    g = nx.MultiGraph(shape=skeleton.skeleton_shape, dtype=skeleton.skeleton_dtype)
+    for row in csum.itertuples(name='Edge'):
+        index = row.Index
+        indices, values = skeleton.path_with_data(index)
+        g.add_edge(row.node_id_src, row.node_id_dst,
+                   **{'path': skeleton.path_coordinates(index), 'indices': indices, 'values': values})
+    return g
+
+
+def nx_to_skeleton(g):
+    """Convert a networkx graph with 'shape' / 'dtype' graph attributes and 'path' / 'values' edge attributes back
+    to a Skeleton (csr.py:1438-1480): the image is regenerated from the paths and skeletonized to a graph again."""
+    image = np.zeros(g.graph['shape'], dtype=g.graph['dtype'])
+    all_coords = np.concatenate([path for _, _, path in g.edges.data('path')], axis=0)
+    all_values = np.concatenate([values for _, _, values in g.edges.data('values')], axis=0)
+    image[tuple(all_coords.T)] = all_values
+    return Skeleton(image)

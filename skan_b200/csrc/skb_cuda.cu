@@ -883,14 +883,24 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     if (tile < ntiles) skb_coords(g, tile * SKB_TILE_VOX, zt, y0, x0);
     skb_coords(g, warps * SKB_TILE_VOX, dzt, dy0, dx0);  // may exceed the volume: only a displacement
     for (; tile < ntiles; tile += warps, skb_advance_coords(g, zt, y0, x0, dzt, dy0, dx0)) {
+        // The warp's iteration is a chain of dependent latencies (prefix -> mask -> scan -> stores), not of issue
+        // slots: the mask is requested before the tile's count is looked at (one DRAM round trip instead of two;
+        // empty tiles are rare enough that reading them does not matter), and the next tile of this warp is
+        // pulled into L2 meanwhile.
+        // coalesced 128-bit loads: lane holds words 2*(32 j + lane) and +1 for j = 0..3
+        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS) + lane;
+        const uint4 q0 = src[0], q1 = src[32], q2 = src[64], q3 = src[96];
         const uint32_t t0 = tile_prefix[tile], total = tile_prefix[tile + 1] - t0;
+        if (tile + warps < ntiles) {
+            if (lane < 16)  // 16 lines of 128 bytes
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(bits + (tile + warps) * SKB_TILE_WORDS) + lane * 128));
+            else if (lane == 16)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tile_prefix + tile + warps));
+        }
         if (total == 0) {  // empty tile: only the rank structure (64 blocks of 256 bits)
             ((uint2*)(pre256 + tile * 64))[lane] = make_uint2(t0, t0);
             continue;
         }
-        // coalesced 128-bit loads: lane holds words 2*(32 j + lane) and +1 for j = 0..3
-        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS) + lane;
-        const uint4 q0 = src[0], q1 = src[32], q2 = src[64], q3 = src[96];
         uint64_t w[8];
         w[0] = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
         w[1] = (uint64_t)q0.z | ((uint64_t)q0.w << 32);

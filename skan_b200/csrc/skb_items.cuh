@@ -164,21 +164,67 @@ SKB_HD int32_t skb_rank(const uint64_t* bits, const uint32_t* pre256, int64_t r)
 // calls fn(k27, neighbour_id) for every set bit of mask m of node i, ascending k27.
 // One iteration per set bit (typically two) keeps the lanes of a warp in step; a neighbour in
 // another row costs one rank query, neighbours in the node's own row are i-1 / i+1.
+// raveled index of the neighbour in direction k27 of voxel r
+SKB_HD int64_t skb_neighbor_lin(const SkbGeom& g, int64_t r, int k) {
+    int row = k / 3;
+    int dz = row / 3 - 1, dy = row % 3 - 1, dx = k - row * 3 - 1;
+    return r + dz * g.sz + dy * (int64_t)g.nx + dx;
+}
+
+// skb_rank without data-dependent control flow: the prefix and the four words of the 256-bit block are loaded
+// unconditionally, so that the loads of two queries can be in flight together
+struct SkbRankLoad {
+    uint32_t pre;
+    uint64_t w[4];
+};
+SKB_HD SkbRankLoad skb_rank_load(const uint64_t* bits, const uint32_t* pre256, int64_t r) {
+    SkbRankLoad q;
+    int64_t blk = r >> 8;
+    q.pre = pre256[blk];
+    const uint64_t* w = bits + blk * 4;
+    q.w[0] = w[0];
+    q.w[1] = w[1];
+    q.w[2] = w[2];
+    q.w[3] = w[3];
+    return q;
+}
+SKB_HD int32_t skb_rank_finish(const SkbRankLoad& q, int64_t r) {
+    const int wi = (int)((r >> 6) & 3);
+    const uint64_t low = (1ull << (r & 63)) - 1ull;
+    uint32_t acc = q.pre;
+    for (int j = 0; j < 4; ++j) {
+        uint64_t mask = j < wi ? ~0ull : (j == wi ? low : 0ull);
+        acc += (uint32_t)skb_popcll(q.w[j] & mask);
+    }
+    return (int32_t)acc;
+}
+
 template <typename Fn>
 SKB_HD void skb_for_neighbors(const SkbGeom& g, const uint64_t* bits, const uint32_t* pre256, int64_t r, int32_t i,
                               uint32_t m, Fn& fn) {
+    // two neighbours per iteration (a chain voxel has two): both rank queries are issued before either result is
+    // used, one memory round trip instead of two
     while (m) {
-        int k = skb_ffs(m) - 1;
+        const int k0 = skb_ffs(m) - 1;
         m &= m - 1u;
-        int32_t id;
-        if (k == 12) id = i - 1;
-        else if (k == 14) id = i + 1;
-        else {
-            int row = k / 3;
-            int dz = row / 3 - 1, dy = row % 3 - 1, dx = k - row * 3 - 1;
-            id = skb_rank(bits, pre256, r + dz * g.sz + dy * (int64_t)g.nx + dx);
+        const int k1 = m ? skb_ffs(m) - 1 : -1;
+        if (k1 >= 0) m &= m - 1u;
+        const bool q0 = k0 != 12 && k0 != 14, q1 = k1 >= 0 && k1 != 12 && k1 != 14;
+        int64_t r0 = 0, r1 = 0;
+        SkbRankLoad l0, l1;
+        if (q0) {
+            r0 = skb_neighbor_lin(g, r, k0);
+            l0 = skb_rank_load(bits, pre256, r0);
         }
-        fn(k, id);
+        if (q1) {
+            r1 = skb_neighbor_lin(g, r, k1);
+            l1 = skb_rank_load(bits, pre256, r1);
+        }
+        const int32_t id0 = q0 ? skb_rank_finish(l0, r0) : (k0 == 12 ? i - 1 : i + 1);
+        int32_t id1 = 0;
+        if (k1 >= 0) id1 = q1 ? skb_rank_finish(l1, r1) : (k1 == 12 ? i - 1 : i + 1);
+        fn(k0, id0);
+        if (k1 >= 0) fn(k1, id1);
     }
 }
 

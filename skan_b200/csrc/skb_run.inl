@@ -12,6 +12,7 @@
 // the caller grows the arena and calls again.
 
 #define SKB_RUN_NEED_MORE 1
+#define SKB_MASK_PAD 16  // zero words in front of the mask (one 128-byte line)
 
 // indices into skb_run_result.off (byte offsets into the `out` arena; -1 = absent)
 enum {
@@ -161,7 +162,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     // ---- mask sweep, scan, nodes (one fused pass, or sweep -> tile scan -> node emission) ---------------
     const bool fused = prm->pack_variant == 2;
     const bool want_values = prm->want_values != 0;
-    uint64_t* store = work.take<uint64_t>(ntiles * SKB_TILE_WORDS + 4);
+    uint64_t* store = work.take<uint64_t>(ntiles * SKB_TILE_WORDS + SKB_MASK_PAD + 2);
     uint32_t* tile_prefix = fused ? nullptr : work.take<uint32_t>(ntiles + 1);
     void* scratch = fused ? work.take<uint8_t>(skb_sweep_scratch_bytes(V))
                           : work.take<uint8_t>(skb_scan_scratch_bytes(ntiles + 1));
@@ -169,9 +170,11 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     int32_t* n_dev = work.take<int32_t>(4);
     uint32_t* pre256 = work.take<uint32_t>(ntiles * 64);
     SKB_NEED(work.ok);
-    uint64_t* bits = store + 2;
-    SKB_TRY(skb_fill_bytes(store, 0, 16, s));
-    SKB_TRY(skb_fill_bytes(store + 2 + ntiles * SKB_TILE_WORDS, 0, 16, s));
+    // the mask starts one 128-byte line into its (256-byte aligned) allocation: every 256-bit block of the rank
+    // structure is one 32-byte sector, every tile a whole number of lines; the words before and after it are zero
+    uint64_t* bits = store + SKB_MASK_PAD;
+    SKB_TRY(skb_fill_bytes(store, 0, SKB_MASK_PAD * 8, s));
+    SKB_TRY(skb_fill_bytes(store + SKB_MASK_PAD + ntiles * SKB_TILE_WORDS, 0, 16, s));
     void* ev = nullptr;
     int64_t N;
     int64_t *lin = nullptr, *coords = nullptr;

@@ -285,7 +285,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     const int variant = prm->pack_variant == 0 ? 0 : 1;
 
     // ---- voxel and node stages on the extended slab -------------------------------------------------------
-    uint64_t* store = work.take<uint64_t>(ntiles * SKB_TILE_WORDS + 4);
+    uint64_t* store = work.take<uint64_t>(ntiles * SKB_TILE_WORDS + SKB_MASK_PAD + 2);
     uint32_t* tile_prefix = work.take<uint32_t>(ntiles + 1);
     void* scratch = work.take<uint8_t>(skb_scan_scratch_bytes(ntiles + 1));
     int32_t* flag = work.take<int32_t>(4);
@@ -293,9 +293,11 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     int64_t* posd = work.take<int64_t>(8);
     uint32_t* pre256 = work.take<uint32_t>(ntiles * 64);
     SKB_SNEED(work.ok);
-    uint64_t* bits = store + 2;
-    SKB_TRY(skb_fill_bytes(store, 0, 16, s));
-    SKB_TRY(skb_fill_bytes(store + 2 + ntiles * SKB_TILE_WORDS, 0, 16, s));
+    // the mask starts one 128-byte line into its (256-byte aligned) allocation: every 256-bit block of the rank
+    // structure is one 32-byte sector, every tile a whole number of lines; the words before and after it are zero
+    uint64_t* bits = store + SKB_MASK_PAD;
+    SKB_TRY(skb_fill_bytes(store, 0, SKB_MASK_PAD * 8, s));
+    SKB_TRY(skb_fill_bytes(store + SKB_MASK_PAD + ntiles * SKB_TILE_WORDS, 0, 16, s));
     SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)skb_scan_scratch_bytes(ntiles + 1), s));
     void* ev = nullptr;
     if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
