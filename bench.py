@@ -325,6 +325,9 @@ def main():
     _pipeline.TIME_SWEEP = True      # the native runner times the sweep kernel with its own CUDA events
     slab.TIME_SWEEP = True
     sweep_ns = []
+    if world == 1 and not is_stack:
+        counts.update(runner='native (skb_run_image); capacity hints = counts of the previous step + 1/16, read-backs '
+                             'overlap the kernels they size, every count verified every step')
     launches0 = lib.kernel_launches()
     start = torch.cuda.Event(enable_timing=True)
     stop = torch.cuda.Event(enable_timing=True)
@@ -334,6 +337,9 @@ def main():
         r = step()
         if getattr(r, 'counts', None):
             sweep_ns.append(r.counts.get('sweep_ns', 0))
+            if world == 1 and 'overlapped' in r.counts:
+                counts.update(host_read_backs_per_step=r.counts['syncs'], overlapped_read_backs=r.counts['overlapped'],
+                              relaunched_for_small_hint=r.counts['retaken'])
         del r
     stop.record()
     sync_all()
