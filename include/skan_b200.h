@@ -265,6 +265,25 @@ int skb_sholl_bins(const int64_t* coords, int64_t n, int ndim, int spacing_is_in
 int skb_sholl_count(const int32_t* indptr, const int32_t* indices, const int32_t* bins, int64_t n,
                     unsigned long long* hist, void* stream);
 
+/* image_stats.mesh_sizes / image_summary (image_stats.py:8-90): the 4-connected background
+ * components of a 2-D mask (scipy.ndimage.label(~skeleton), image_stats.py:31-32) as unions of horizontal runs of zero
+ * bits.  skb_mesh_runs: rs u64[nwords], rsp u32[nwords+1] (nwords = ceil(ny*nx/64)); rsp[nwords] = number of runs R.
+ * skb_mesh_link: par i32[R], len u32[R], border u8[R], size u64[R] and root_border u32[R] (both pre-zeroed),
+ * keepoff u32[R+1]; keepoff[R] = number of components that do not touch the border (image_stats.py:33-44).
+ * skb_mesh_emit: their sizes i64[keepoff[R]] in label order.  skb_mesh_border_foreground: flag i32[1] (pre-zeroed) is
+ * raised when a foreground pixel lies on the border.  skb_cc_count: number of connected components of a symmetric CSR
+ * graph, isolated nodes included (ndi.label(skeleton, full structure)[1], image_stats.py:86-87); par i32[n] scratch,
+ * count u64[1] pre-zeroed.  scratch: skb_scan_scratch_bytes(nwords + 1) resp. (R + 1). */
+int skb_mesh_runs(const uint64_t* bits, int64_t ny, int64_t nx, uint64_t* rs, uint32_t* rsp, void* scratch, void* stream);
+int skb_mesh_link(const uint64_t* bits, int64_t ny, int64_t nx, const uint64_t* rs, const uint32_t* rsp, int64_t n_runs,
+                  int32_t* par, uint32_t* len, uint8_t* border, unsigned long long* size, uint32_t* root_border,
+                  uint32_t* keepoff, void* scratch, void* stream);
+int skb_mesh_emit(const int32_t* par, const uint32_t* root_border, const uint32_t* keepoff, const unsigned long long* size,
+                  int64_t n_runs, int64_t* out, void* stream);
+int skb_mesh_border_foreground(const uint64_t* bits, int64_t ny, int64_t nx, int32_t* flag, void* stream);
+int skb_cc_count(const int32_t* indptr, const int32_t* indices, int64_t n, int32_t* par, unsigned long long* count,
+                 void* stream);
+
 /* ---- The whole hot path for one image (or one stack of 2-D images) in one call ---------------------
  * Native twin of the per-stage sequencing: same kernels in the same order; allocation is a bump
  * pointer into two caller-provided device arenas (`work`: scratch, `out`: results), the counts that

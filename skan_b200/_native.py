@@ -70,6 +70,11 @@ _SIGNATURES = {
     'skb_scan_u32': (_int, [_vp, _vp, _i64, _vp, _vp]),
     'skb_sholl_bins': (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp]),
     'skb_sholl_count': (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_mesh_runs': (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    'skb_mesh_link': (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'skb_mesh_emit': (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'skb_mesh_border_foreground': (_int, [_vp, _i64, _i64, _vp, _vp]),
+    'skb_cc_count': (_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
 }
 
 

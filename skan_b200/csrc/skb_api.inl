@@ -596,6 +596,61 @@ int skb_sholl_count(const int32_t* indptr, const int32_t* indices, const int32_t
     return skb_foreach(n, (skb_stream_t)stream, SkbShollCountItem{indptr, indices, bins, hist});
 }
 
+// ---- image_stats.mesh_sizes (image_stats.py:8-46), see skb_mesh.cuh ---------------------------------------
+// Run starts of the background of a 2-D mask: rs u64[nwords] (nwords = ceil(ny*nx / 64)) and rsp u32[nwords+1],
+// the exclusive scan of the starts per word; rsp[nwords] = number of runs.
+int skb_mesh_runs(const uint64_t* bits, int64_t ny, int64_t nx, uint64_t* rs, uint32_t* rsp, void* scratch,
+                  void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    if (ny < 1 || nx < 1 || ny > 0x7fffffffLL || nx > 0x7fffffffLL) return skb_fail("bad extent");
+    SkbMeshGeom g{ny * nx, (int32_t)ny, (int32_t)nx};
+    const int64_t nwords = (g.nvox + 63) / 64;
+    SKB_TRY(skb_foreach(nwords, s, SkbRunStartItem{g, bits, rs, rsp}));
+    return skb_scan_u32_impl(rsp, rsp, nwords, scratch, s);
+}
+
+// Components of the runs: par i32[R], len u32[R], border u8[R], size u64[R], root_border u32[R] (size and
+// root_border zeroed by the caller), keepoff u32[R+1] = exclusive scan of "root of a component that does not touch
+// the border"; keepoff[R] = number of such components.
+int skb_mesh_link(const uint64_t* bits, int64_t ny, int64_t nx, const uint64_t* rs, const uint32_t* rsp,
+                  int64_t n_runs, int32_t* par, uint32_t* len, uint8_t* border, unsigned long long* size,
+                  uint32_t* root_border, uint32_t* keepoff, void* scratch, void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    if (ny < 1 || nx < 1 || ny > 0x7fffffffLL || nx > 0x7fffffffLL) return skb_fail("bad extent");
+    if (n_runs > 0x7fffffffLL) return skb_fail("too many background runs");
+    SkbMeshGeom g{ny * nx, (int32_t)ny, (int32_t)nx};
+    const int64_t nwords = (g.nvox + 63) / 64;
+    SKB_TRY(skb_foreach(n_runs, s, SkbIotaItem{par}));
+    SKB_TRY(skb_foreach(nwords, s, SkbRunLinkItem{g, bits, rs, rsp, par, len, border}));
+    SKB_TRY(skb_foreach(n_runs, s, SkbRunBorderItem{par, border, root_border}));
+    SKB_TRY(skb_foreach(n_runs, s, SkbRunSizeItem{par, len, root_border, size}));
+    SKB_TRY(skb_foreach(n_runs, s, SkbRunKeepItem{par, root_border, keepoff}));
+    return skb_scan_u32_impl(keepoff, keepoff, n_runs, scratch, s);
+}
+
+// sizes i64[keepoff[R]] of the kept components, in the order of their first pixel (scipy.ndimage.label's order)
+int skb_mesh_emit(const int32_t* par, const uint32_t* root_border, const uint32_t* keepoff,
+                  const unsigned long long* size, int64_t n_runs, int64_t* out, void* stream) {
+    return skb_foreach(n_runs, (skb_stream_t)stream, SkbRunEmitItem{par, root_border, keepoff, size, out});
+}
+
+// flag i32[1] (zeroed by the caller) is raised when a foreground pixel lies on the border of the 2-D image
+int skb_mesh_border_foreground(const uint64_t* bits, int64_t ny, int64_t nx, int32_t* flag, void* stream) {
+    if (ny < 1 || nx < 1 || ny > 0x7fffffffLL || nx > 0x7fffffffLL) return skb_fail("bad extent");
+    SkbMeshGeom g{ny * nx, (int32_t)ny, (int32_t)nx};
+    return skb_foreach(2 * (ny + nx), (skb_stream_t)stream, SkbBorderFgItem{g, bits, flag});
+}
+
+// number of connected components of a symmetric CSR graph, isolated nodes included (image_stats.py:86-87):
+// par i32[n] scratch, count u64[1] zeroed by the caller
+int skb_cc_count(const int32_t* indptr, const int32_t* indices, int64_t n, int32_t* par, unsigned long long* count,
+                 void* stream) {
+    skb_stream_t s = (skb_stream_t)stream;
+    SKB_TRY(skb_foreach(n, s, SkbIotaItem{par}));
+    SKB_TRY(skb_foreach(n, s, SkbCcEdgeUnionItem{indptr, indices, par}));
+    return skb_foreach(n, s, SkbCcRootCountItem{par, count});
+}
+
 int skb_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, void* stream) {
     return skb_scan_u32_impl(in, out, n, scratch, (skb_stream_t)stream);
 }

@@ -31,6 +31,7 @@ struct skb_i2 {
 SKB_HD int skb_popc(uint32_t v) { return __popc(v); }
 SKB_HD int skb_popcll(uint64_t v) { return __popcll(v); }
 SKB_HD int skb_ffs(uint32_t v) { return __ffs((int)v); }
+SKB_HD int skb_ffsll(uint64_t v) { return __ffsll((long long)v); }
 SKB_HD uint64_t skb_atomic_min_u64(uint64_t* p, uint64_t v) {
     return (uint64_t)atomicMin((unsigned long long*)p, (unsigned long long)v);
 }
@@ -65,6 +66,7 @@ SKB_HD double skb_sqrt(double v) { return sqrt(v); }
 SKB_HD int skb_popc(uint32_t v) { return __builtin_popcount(v); }
 SKB_HD int skb_popcll(uint64_t v) { return __builtin_popcountll(v); }
 SKB_HD int skb_ffs(uint32_t v) { return __builtin_ffs((int)v); }
+SKB_HD int skb_ffsll(uint64_t v) { return __builtin_ffsll((long long)v); }
 SKB_HD uint64_t skb_atomic_min_u64(uint64_t* p, uint64_t v) {
     uint64_t o = *p;
     if (v < o) *p = v;
