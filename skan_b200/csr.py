@@ -100,6 +100,34 @@ class Skeleton:
             self.skeleton_image = skeleton_image
             self.source_image = source_image
 
+    @classmethod
+    def from_path_graph(cls, pg):
+        """A Skeleton from a PathGraph (csr.py:670-688): same accessors and ``summarize`` on an arbitrary graph.
+        The reference builds a dummy 4^ndim image first and overwrites its attributes; here the object is
+        filled from the PathGraph directly (device handles included), with the same resulting attributes."""
+        d = pg._dev
+        obj = object.__new__(cls)
+        coords = np.asarray(pg.node_coordinates)
+        obj._run = None
+        obj._g = None
+        obj._ctx = d['ctx']
+        obj._values_dev = d['values']
+        obj._coords_dev = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.int64)).to(obj._ctx.device)
+        obj._graph_dev = (d['indptr'], d['indices'], d['data'])
+        obj._n_nodes = int(pg.adj.shape[0])
+        obj._p = d['p']
+        obj.n_paths = pg.n_paths
+        obj._host = {'graph': pg.adj, 'coordinates': coords, 'pixel_values': pg.node_values, 'paths': pg.paths,
+                     'degrees': pg.degrees, 'distances': pg.distances}
+        obj._stats = None
+        obj._value_is_height = False
+        obj.skeleton_image = None
+        obj.source_image = None
+        obj.skeleton_shape = np.max(coords, axis=0) + 1
+        obj.skeleton_dtype = bool if pg.node_values is None else np.asarray(pg.node_values).dtype
+        obj.spacing = pg.spacing
+        return obj
+
     # ---- lazily materialised host views of the device results ---------------------------
     def _cached(self, key, make):
         if key not in self._host:
@@ -164,7 +192,10 @@ class Skeleton:
 
     def _device_stats(self):
         if self._stats is None:
-            self._stats = (self._run.dist, self._run.mean, self._run.stdev)
+            if self._run is not None:
+                self._stats = (self._run.dist, self._run.mean, self._run.stdev)
+            else:   # built from a PathGraph: no native run behind it
+                self._stats = tuple(_pipeline.path_stats(self._ctx, self._p))
         return self._stats
 
     @property
@@ -205,10 +236,15 @@ class Skeleton:
     def path_label_image(self):
         """Image of the skeleton's shape holding path id + 1 at every path pixel (csr.py:776-790)."""
         ctx, p = self._ctx, self._p
-        v = int(np.prod(self.skeleton_shape, dtype=np.int64))
+        shape = tuple(int(x) for x in self.skeleton_shape)
+        v = int(np.prod(shape, dtype=np.int64))
         out = torch.zeros(v, dtype=torch.int64, device=ctx.device)
-        ctx.call('skb_path_label_image', p.indptr, p.indices, self._g.lin, p.n_paths, out)
-        return _to_host(out).reshape(self.skeleton_shape)
+        if self._g is not None:
+            lin = self._g.lin
+        else:   # built from a PathGraph: raveled indices from the node coordinates
+            lin = torch.from_numpy(np.ravel_multi_index(tuple(self.coordinates.T), shape).astype(np.int64)).to(ctx.device)
+        ctx.call('skb_path_label_image', p.indptr, p.indices, lin, p.n_paths, out)
+        return _to_host(out).reshape(shape)
 
     def prune_paths(self, indices):
         """csr.py:818-854 re-skeletonizes with scikit-image after wiping the paths; thinning is
@@ -280,27 +316,6 @@ class PathGraph:
         return np.diff(self.adj.indptr)
 
 
-class _PathGraphSkeleton:
-    """What Skeleton.from_path_graph builds (csr.py:670-688), without the dummy image."""
-
-    def __init__(self, pg):
-        d = pg._dev
-        self._ctx = d['ctx']
-        self._graph_dev = (d['indptr'], d['indices'], d['data'])
-        self._values_dev = d['values']
-        self._p = d['p']
-        self.graph = pg.adj
-        self.coordinates = np.asarray(pg.node_coordinates)
-        self._coords_dev = torch.from_numpy(np.ascontiguousarray(self.coordinates, dtype=np.int64)).to(self._ctx.device)
-        self.pixel_values = pg.node_values
-        self.paths = pg.paths
-        self.n_paths = pg.n_paths
-        self.degrees = pg.degrees
-        self.spacing = pg.spacing
-        self.skeleton_shape = np.max(self.coordinates, axis=0) + 1
-        self.skeleton_dtype = bool if pg.node_values is None else np.asarray(pg.node_values).dtype
-
-
 def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=None):
     """Compute statistics for every skeleton and branch in ``skel`` (csr.py:861-959).
 
@@ -310,7 +325,7 @@ def summarize(skel, *, value_is_height=False, find_main_branch=False, separator=
     """
     import pandas as pd
     if isinstance(skel, PathGraph):
-        skel = _PathGraphSkeleton(skel)
+        skel = Skeleton.from_path_graph(skel)
     if separator is None:
         warnings.warn(
             "separator in column name will change to _ in version 0.13; "
