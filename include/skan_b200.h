@@ -93,6 +93,11 @@ int skb_tile_prefix(const uint32_t* pre256, const int32_t* n_nodes, int64_t ntil
  * across the leading axis. */
 int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape /*host*/, const int64_t* lin, int64_t n,
                       int planes_independent, uint32_t* nb, void* stream);
+/* nb[i] &= allowed: keeps the neighbour directions k27 whose bit is set -- pixel_graph(connectivity=c) with c < ndim
+ * (csr.py:51-158; scipy.ndimage.generate_binary_structure: at most c non-zero offset components). */
+int skb_mask_neighbors(uint32_t* nb, int64_t n, uint32_t allowed, void* stream);
+/* make_degree_image (csr.py:1173-1208): image i64[V], zeroed by the caller, receives popcount(nb[i]) at lin[i]. */
+int skb_degree_image(const uint32_t* nb, const int64_t* lin, int64_t n, int64_t* image, void* stream);
 
 /* Junction-junction edges (both ends of raw degree >= 3; csr.py:1004-1016): per-node count of
  * forward edges (only nodes a in [a0, a1): the nodes a Z-slab owns), then (after an exclusive scan

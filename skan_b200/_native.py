@@ -32,6 +32,8 @@ _SIGNATURES = {
     'skb_sweep_nodes': (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'skb_tile_prefix': (_int, [_vp, _vp, _i64, _vp, _vp]),
     'skb_raw_neighbors': (_int, [_vp, _int, _vp, _vp, _i64, _int, _vp, _vp]),
+    'skb_mask_neighbors': (_int, [_vp, _i64, ctypes.c_uint32, _vp]),
+    'skb_degree_image': (_int, [_vp, _vp, _i64, _vp, _vp]),
     'skb_junction_edge_count': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'skb_junction_edge_emit': (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _int, _int,
                                       _vp, _vp, _vp, _vp, _vp]),

@@ -37,6 +37,78 @@ def _to_host(t):
     return t.cpu().numpy()
 
 
+def _weighted_abs_diff(values0, values1, distances):
+    """Default edge function of a complete image graph: abs(values0 - values1) * distances (csr.py:24-48)."""
+    return np.abs(values0 - values1) * distances
+
+
+def pixel_graph(image, *, mask=None, edge_function=None, connectivity=1, spacing=None):
+    """Adjacency graph of the pixels of an image (csr.py:51-158): the raw 3^d stencil graph of the mask, before
+    any junction clean-up.  Returns ``(graph, nodes)``: a csr_matrix whose entries are the distances between
+    neighbouring mask pixels (or ``edge_function(values, neighbour values, distances)``) and the raveled indices
+    of the mask pixels.
+
+    Mask sweep, node ids, neighbourhood stencil and count-scan-emit CSR run on the device (the stage entry points
+    of the hot path, with the neighbour directions restricted to ``connectivity``); a user-supplied
+    ``edge_function`` is a Python callable and is evaluated on the host on the per-edge value arrays, as in the
+    reference.
+    """
+    image = _to_host(image) if isinstance(image, torch.Tensor) else np.asarray(image)
+    if image.dtype == bool and mask is None:
+        mask = image
+    if mask is None and edge_function is None:
+        mask = np.ones_like(image, dtype=bool)
+        edge_function = _weighted_abs_diff
+    if mask is None:
+        raise TypeError('pixel_graph needs a mask when an edge_function is given for a non-boolean image '
+                        '(the reference fails in np.pad(None), csr.py:122)')
+    mask = np.ascontiguousarray(mask, dtype=bool)
+    ndim = mask.ndim
+    if ndim < 1 or ndim > 3:
+        raise NotImplementedError('skan_b200 supports 1-D, 2-D and 3-D images')
+    g = _pipeline.graph_nodes(mask, spacing=1 if spacing is None else spacing, device=_default_device())
+    if connectivity < ndim:
+        # scipy.ndimage.generate_binary_structure(ndim, connectivity): at most `connectivity` non-zero offsets
+        offs = np.stack([a.ravel() for a in np.meshgrid(*([np.arange(-1, 2)] * 3), indexing='ij')], axis=-1)
+        allowed = int(sum(1 << k for k in range(27) if 0 < np.count_nonzero(offs[k]) <= max(int(connectivity), 0)))
+        g.ctx.call('skb_mask_neighbors', g.raw_nb, g.n_nodes, allowed)
+    empty32 = g.ctx.empty(0, torch.int32)
+    _pipeline.graph_csr(g, empty32, empty32, g.ctx.empty(0, torch.uint8), g.ctx.empty(0, torch.uint8), records=False)
+    n = g.n_nodes
+    nodes = _to_host(g.lin)
+    indptr, indices, data = _to_host(g.indptr), _to_host(g.indices), _to_host(g.data)
+    if edge_function is not None:
+        image_r = image.reshape(-1)
+        rows = np.repeat(nodes, np.diff(indptr))
+        data = edge_function(image_r[rows], image_r[nodes[indices]], data)
+    return sparse.csr_matrix((data, indices, indptr), shape=(n, n)), nodes
+
+
+def make_degree_image(skeleton_image):
+    """Image of the degree of connectivity of every skeleton pixel under the full 3^d neighbourhood
+    (csr.py:1173-1208): mask sweep + neighbourhood stencil on the device, scattered back into an int64 image."""
+    g = _pipeline.graph_nodes(skeleton_image, device=_device_of(skeleton_image))
+    out = torch.zeros(max(g.nvox, 1), dtype=torch.int64, device=g.ctx.device)
+    g.ctx.call('skb_degree_image', g.raw_nb, g.lin, g.n_nodes, out)
+    return _to_host(out[:g.nvox]).reshape(g.shape)
+
+
+def submatrix(M, idxs):
+    """The outer-index product submatrix ``M[idxs, :][:, idxs]`` (csr.py:1145-1170)."""
+    return M[idxs, :][:, idxs]
+
+
+def distance_with_height(source_values, neighbor_values, distances):
+    """Edge function of value_is_height: hypot(height difference, distance) (csr.py:1023-1025)."""
+    return np.hypot(source_values - neighbor_values, distances)
+
+
+def csr_to_nbgraph(csr, node_props=None):
+    """Host view of a CSR matrix with the reference's NBGraph fields (csr.py:206-216)."""
+    from ._nbgraph import csr_to_nbgraph as _impl
+    return _impl(csr, node_props)
+
+
 def skeleton_to_csgraph(skel, *, spacing=1, value_is_height=False):
     """Convert a skeleton image of thin lines to a graph of neighbor pixels (csr.py:1028-1089).
 

@@ -77,6 +77,16 @@ int skb_raw_neighbors(const uint64_t* bits, int ndim, const int64_t* shape, cons
     return skb_foreach(n, (skb_stream_t)stream, it);
 }
 
+// restrict raw neighbourhood masks to the directions in `allowed` (bit k27), for pixel_graph(connectivity < ndim)
+int skb_mask_neighbors(uint32_t* nb, int64_t n, uint32_t allowed, void* stream) {
+    return skb_foreach(n, (skb_stream_t)stream, SkbAndMaskItem{nb, allowed});
+}
+
+// make_degree_image (csr.py:1173-1208): image i64[V] (zeroed by the caller) receives the raw degree at every node
+int skb_degree_image(const uint32_t* nb, const int64_t* lin, int64_t n, int64_t* image, void* stream) {
+    return skb_foreach(n, (skb_stream_t)stream, SkbDegreeImageItem{nb, lin, image});
+}
+
 // junction-junction edges: per-node forward counts, then emission       (csr.py:1004-1016)
 int skb_junction_edge_count(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape,
                             const int64_t* lin, const uint32_t* nb, int64_t n, int64_t a0, int64_t a1,

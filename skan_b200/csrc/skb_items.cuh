@@ -272,6 +272,22 @@ struct SkbRawNbItem {
     }
 };
 
+// pixel_graph(connectivity=c) with c < ndim (csr.py:51-158): keep the neighbour directions with at most c
+// non-zero offset components (scipy.ndimage.generate_binary_structure); `allowed` has one bit per k27
+struct SkbAndMaskItem {  // over nodes
+    uint32_t* nb;
+    uint32_t allowed;
+    SKB_HD void operator()(int64_t i) const { nb[i] &= allowed; }
+};
+
+// make_degree_image (csr.py:1173-1208): the raw 3^d-neighbourhood degree of every skeleton pixel, as an image
+struct SkbDegreeImageItem {  // over nodes
+    const uint32_t* nb;
+    const int64_t* lin;
+    int64_t* image;  // V entries, zeroed by the caller
+    SKB_HD void operator()(int64_t i) const { image[lin[i]] = (int64_t)skb_popc(nb[i]); }
+};
+
 // ---- stage: junction-junction edges (csr.py:1004-1016) -------------------------------------
 // Edge weight of neighbour offset k27: table distance (nputil.py:278-279, host-computed) or, in
 // height mode, hypot(height difference, distance) (csr.py:148-151, 1023-1025).

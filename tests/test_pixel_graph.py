@@ -1,0 +1,89 @@
+"""The public pixel_graph (reference csr.py:51-158) against golden vectors of the unmodified reference
+(tests/golden/make_pixel_graph.py): masks at every connectivity, complete image graphs with the default edge
+function, a custom edge function.  Structure bit-exact; distances are the same table entries, so the data are
+compared exactly as well."""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, 'golden', 'pixel_graph.npz'))
+NAMES = sorted({k.split('/')[0] for k in GOLD.files})
+
+
+def edge_fn(v0, v1, d):
+    return (v0 + 2.0 * v1) / d
+
+
+def check(name):
+    from skan_b200 import csr
+    g = lambda k: GOLD[name + '/' + k]
+    has = lambda k: (name + '/' + k) in GOLD.files
+    spacing = tuple(float(x) for x in g('spacing')) if has('spacing') else None
+    graph, nodes = csr.pixel_graph(g('image'), mask=g('mask') if has('mask') else None,
+                                   edge_function=edge_fn if bool(g('custom')) else None,
+                                   connectivity=int(g('connectivity')), spacing=spacing)
+    assert graph.indptr.dtype == g('indptr').dtype and np.array_equal(graph.indptr, g('indptr'))
+    assert graph.indices.dtype == g('indices').dtype and np.array_equal(graph.indices, g('indices'))
+    assert graph.data.dtype == g('data').dtype and np.array_equal(graph.data, g('data'))
+    assert nodes.dtype == g('nodes').dtype and np.array_equal(nodes, g('nodes'))
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_pixel_graph_emulated(name):
+    from emul_util import emulated_device
+    with emulated_device():
+        check(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', NAMES)
+def test_pixel_graph_gpu(name):
+    check(name)
+
+
+def _degree_cases():
+    from skan_b200.synth import walks
+    rng = np.random.default_rng(8)
+    yield walks((50, 60), 10, 40, seed=1, isolated=3, rings=2)
+    yield rng.random((9, 8, 7)) < 0.4
+    yield (rng.random((21, 19)) < 0.5) * rng.random((21, 19))        # valued image: nonzero pixels are the skeleton
+    yield rng.random(30) < 0.5
+
+
+def _check_degree_image(to_device):
+    # the reference's formula (csr.py:1197-1205) with SciPy, on the host copy
+    from scipy import ndimage as ndi
+    from skan_b200 import csr
+    for img in _degree_cases():
+        b = img.astype(bool)
+        kernel = np.ones((3,) * b.ndim)
+        kernel[(1,) * b.ndim] = 0
+        want = ndi.convolve(b.astype(int), kernel, mode='constant') * b
+        got = csr.make_degree_image(to_device(img))
+        assert got.dtype == want.dtype and got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_make_degree_image_emulated():
+    from emul_util import emulated_device
+    with emulated_device():
+        _check_degree_image(lambda a: a)
+
+
+@pytest.mark.gpu
+def test_make_degree_image_gpu():
+    import torch
+    _check_degree_image(lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda())
+
+
+def test_small_utilities():
+    from scipy import sparse
+    from skan_b200 import csr
+    M = sparse.csr_matrix(np.arange(16).reshape((4, 4)))
+    assert csr.submatrix(M, [0, 2]).toarray().tolist() == [[0, 2], [8, 10]]        # csr.py:1163-1167
+    assert np.array_equal(csr.distance_with_height(np.array([3.0]), np.array([0.0]), np.array([4.0])), [5.0])
+    nbg = csr.csr_to_nbgraph(M.astype(float))
+    assert nbg.edge(1, 2) == 6.0 and nbg.neighbors(0).tolist() == [1, 2, 3]
+    with pytest.raises(AttributeError):                                              # test_csr.py:590-600
+        csr.csr_to_nbgraph(np.zeros((3, 3)))
