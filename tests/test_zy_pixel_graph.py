@@ -87,3 +87,31 @@ def test_small_utilities():
     assert nbg.edge(1, 2) == 6.0 and nbg.neighbors(0).tolist() == [1, 2, 3]
     with pytest.raises(AttributeError):                                              # test_csr.py:590-600
         csr.csr_to_nbgraph(np.zeros((3, 3)))
+
+
+@pytest.mark.gpu
+def test_skeleton_from_path_graph_gpu():
+    import warnings
+    import skan_b200
+    from skan_b200.synth import walks
+    # csr.py:670-688: a Skeleton built from a PathGraph has the same paths, statistics and label image
+    rng = np.random.default_rng(2)
+    img = walks((64, 72), 16, 50, seed=4, isolated=2, rings=2)
+    valued = (img * (rng.random(img.shape) + 0.5)).astype(np.float64)
+    sk = skan_b200.Skeleton(valued, spacing=(1.5, 0.5))
+    pg = skan_b200.PathGraph.from_graph(adj=sk.graph, node_coordinates=sk.coordinates, node_values=sk.pixel_values,
+                                        spacing=(1.5, 0.5))
+    sk2 = skan_b200.Skeleton.from_path_graph(pg)
+    assert sk2.n_paths == sk.n_paths and sk2.paths_list() == sk.paths_list()
+    assert np.array_equal(sk2.path_lengths(), sk.path_lengths())
+    assert np.array_equal(sk2.path_means(), sk.path_means())
+    assert np.array_equal(sk2.path_stdev(), sk.path_stdev())
+    assert np.array_equal(sk2.degrees, sk.degrees) and np.array_equal(sk2.coordinates, sk.coordinates)
+    assert tuple(sk2.skeleton_shape) == tuple(np.max(sk.coordinates, axis=0) + 1)
+    lab, lab2 = sk.path_label_image(), sk2.path_label_image()
+    assert np.array_equal(lab[:lab2.shape[0], :lab2.shape[1]], lab2)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        a, b = skan_b200.summarize(sk, separator='_'), skan_b200.summarize(sk2, separator='_')
+    for col in a.columns:
+        assert np.array_equal(a[col].to_numpy(), b[col].to_numpy()), col
