@@ -41,7 +41,10 @@ int skb_set_option(const char* name, int64_t value); /* scheduling tunables, no 
                                                         (0: one chain walk per thread, default; 1: persistent warps
                                                         whose idle lanes draw new walks from a queue -- measured
                                                         slower on B200), "walk_refill" (1..32, idle lanes at which
-                                                        a warp draws new walks, default 8) */
+                                                        a warp draws new walks, default 8), "emit_both_ways" (1:
+                                                        skb_run_image's second walk writes every chain from both of its
+                                                        ends, which halves its longest dependent-load chain; 0, default
+                                                        until timed on a B200: from one end) */
 int64_t skb_kernel_launches(void);         /* kernels launched by the library since it was loaded */
 
 /* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes

@@ -307,20 +307,21 @@ int skb_path_select(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, 
 static int skb_path_heads_cap(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const void* aux,
                               const uint32_t* sel, int64_t n_starts, int phase, int64_t pid_base, int64_t start_lo,
                               int64_t id_shift, int32_t* start_node, uint32_t* plen, int32_t* pmin, skb_i4* einfo,
-                              int32_t* head_end, void* head_aux, int64_t pid_cap, void* stream) {
+                              int32_t* head_end, void* head_aux, int64_t pid_cap, int both_ways, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
     if (einfo) SKB_TRY(skb_fill_bytes(einfo, 0xff, (size_t)n_starts * 16, s));
     return skb_foreach(n_starts, s,
                        SkbHeadsItem{su, rec, ranked, (const SkbAux*)aux, sel, phase, (int32_t)pid_base,
                                     (int32_t)start_lo, (int32_t)id_shift, start_node, plen, pmin, einfo, head_end,
-                                    (SkbAux*)head_aux, pid_cap > 0x7fffffffLL ? 0x7fffffff : (int32_t)pid_cap});
+                                    (SkbAux*)head_aux, pid_cap > 0x7fffffffLL ? 0x7fffffff : (int32_t)pid_cap,
+                                    both_ways ? 1 : 0});
 }
 int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, const void* aux,
                    const uint32_t* sel, int64_t n_starts, int phase, int64_t pid_base, int64_t start_lo,
                    int64_t id_shift, int32_t* start_node, uint32_t* plen, int32_t* pmin, skb_i4* einfo,
                    int32_t* head_end, void* head_aux, void* stream) {
     return skb_path_heads_cap(su, rec, ranked, aux, sel, n_starts, phase, pid_base, start_lo, id_shift, start_node, plen,
-                              pmin, einfo, head_end, head_aux, 0x7fffffffLL, stream);
+                              pmin, einfo, head_end, head_aux, 0x7fffffffLL, 0, stream);
 }
 
 // second local walk: paths.indices i32[L], paths.data f64[L] (csr.py:396,402; values NULL -> 1.0;
@@ -328,13 +329,22 @@ int skb_path_heads(const int32_t* su, const skb_i4* rec, const skb_i4* ranked, c
 // pw f64[L] = weight of the edge arriving at each entry; chain nodes written are marked in
 // covered u8[n] when it is given.  einfo is indexed by the id of a list's reversed last start;
 // pindptr NULL means the entry offset of a path is einfo.z (slabs).
+// both_ways: the chain between two stops is written from both ends (needs einfo from skb_path_heads_cap with
+// both_ways and ranked from skb_path_walk + skb_path_rank of this library: the local hop count rides in ranked.w)
+static int skb_path_emit_ways(const int32_t* indices, const double* gdata, const skb_i4* rec, const int32_t* su,
+                              const int32_t* se, const skb_i4* ranked, const skb_i4* einfo, const int32_t* pindptr,
+                              const double* values, uint8_t* covered, int64_t id_shift, int64_t n_starts, int32_t* pidx,
+                              double* pdata, double* pw, int both_ways, void* stream) {
+    return skb_foreach_steps(n_starts, (skb_stream_t)stream,
+                             SkbEmitItem{indices, gdata, rec, su, se, ranked, einfo, pindptr, values, covered,
+                                         (int32_t)id_shift, pidx, pdata, pw, both_ways ? 1 : 0});
+}
 int skb_path_emit(const int32_t* indices, const double* gdata, const skb_i4* rec, const int32_t* su,
                   const int32_t* se, const skb_i4* ranked, const skb_i4* einfo, const int32_t* pindptr,
                   const double* values, uint8_t* covered, int64_t id_shift, int64_t n_starts, int32_t* pidx,
                   double* pdata, double* pw, void* stream) {
-    return skb_foreach_steps(n_starts, (skb_stream_t)stream,
-                       SkbEmitItem{indices, gdata, rec, su, se, ranked, einfo, pindptr, values, covered,
-                                   (int32_t)id_shift, pidx, pdata, pw});
+    return skb_path_emit_ways(indices, gdata, rec, su, se, ranked, einfo, pindptr, values, covered, id_shift, n_starts,
+                              pidx, pdata, pw, 0, stream);
 }
 
 // junction-free cycles (csr.py:369-386): the minimum node of every component of uncovered

@@ -154,6 +154,16 @@ static int skb_ticket_slot(unsigned long long** out) {
 
 // tunables (skb_set_option, or the environment at first use): "dynamic_walks" 0 = one item per thread (default);
 // "walk_refill" = idle lanes at which a warp draws new items (1..32)
+// "emit_both_ways": 1 = the second walk writes every chain from both ends.  Off by default until it has been timed on
+// a B200 (it was written after the round's GPU budget was spent; bit-identical results in the emulation harness)
+static int g_skb_both_ways = -1;
+static int skb_option_both_ways() {
+    if (g_skb_both_ways < 0) {
+        const char* e = getenv("SKAN_B200_EMIT_BOTH_WAYS");
+        g_skb_both_ways = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_skb_both_ways;
+}
 static int g_skb_steps_dynamic = -1;
 static int g_skb_steps_refill = SKB_DYN_REFILL;
 static bool skb_steps_dynamic() {
@@ -1543,6 +1553,10 @@ int skb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "dynamic_walks")) {
         skb_steps_dynamic();  // read the environment first so that it does not override this later
         g_skb_steps_dynamic = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "emit_both_ways")) {
+        g_skb_both_ways = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "walk_refill")) {

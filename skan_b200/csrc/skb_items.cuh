@@ -844,7 +844,7 @@ struct SkbWalkItemT {  // over starts: local walk to the next terminal / cycle r
         out.x = st.out_x;
         out.y = st.cnt;
         out.z = st.mn + sl.id_shift;
-        out.w = 0;
+        out.w = st.cnt;  // local: half-edges to the next stop; the ranking leaves it alone (SkbEmitItem, both_ways)
         skb_st_i4(ranked + s, out);
         if (AUX) {
             SkbAux ax;
@@ -1093,6 +1093,7 @@ struct SkbHeadsItem {  // over starts: path id, start node, length, minimum node
     int32_t* head_end;  // slabs: id of the reversed last start of every path
     SkbAux* head_aux;   // slabs: sums and end node of every path
     int32_t pid_cap = 0x7fffffff;  // capacity of the per-path arrays (they may be sized by a hint)
+    int32_t both_ways = 0;         // single GPU: also tag the head itself, for the starts that look back at it
     SKB_HD void operator()(int64_t s) const {
         skb_i4 a = skb_ld_i4(ranked + s);
         if (!skb_start_is_head(skb_ld_i4(rec + 2 * (int64_t)su[s]), a, s + start_lo, phase)) return;
@@ -1108,6 +1109,12 @@ struct SkbHeadsItem {  // over starts: path id, start node, length, minimum node
             info.z = 0;
             info.w = 0;
             skb_st_i4(einfo + (-1 - a.x), info);
+            if (both_ways) {
+                // the lists of the starts that point back along this path end at the head: its slot is free
+                // (the head is the reversed last start of the reversed path only, which is never emitted)
+                info.w = 1;
+                skb_st_i4(einfo + s, info);
+            }
         }
         if (head_end) {
             head_end[pid] = -1 - a.x;
@@ -1123,7 +1130,7 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
     const int32_t* su;
     const int32_t* se;
     const skb_i4* ranked;
-    const skb_i4* einfo;     // indexed by the id of the reversed last start: (path id, half-edges, base, -)
+    const skb_i4* einfo;     // indexed by the id of the reversed last start: (path id, half-edges, base, looks back)
     const int32_t* pindptr;  // null: the entry offset of the path is einfo.z
     const double* values;    // null -> 1.0 (csr.py:207-215)
     uint8_t* covered;        // may be null; every node written is marked (what stays 0 is on no path headed at a terminal)
@@ -1131,42 +1138,72 @@ struct SkbEmitItem {  // over starts: second local walk, writes path entries (cs
     int32_t* pidx;
     double* pdata;
     double* pw;  // weight of the edge arriving at each entry (0 for the first)
+    // both_ways (single GPU; needs SkbHeadsItem.both_ways and the local hop count in ranked.w): the chain between two
+    // stops is written from both of its ends.  The start that looks along the path writes the first half of the
+    // interior voxels, the start at the far stop that looks back writes its own voxel and the second half.  The kernel
+    // lasts as long as its longest walk (dependent loads): this halves it.  0: the start that looks along the
+    // path writes the whole chain and the stop.
+    int32_t both_ways = 0;
     struct State {
-        int64_t at;  // entry index of the node last written
+        int64_t at;    // entry index of the node last written
         int32_t prev, cur;
-        double w_in;  // weight of the edge arriving at `cur`: the first from the graph, later ones from the records
+        int32_t left;  // both_ways: voxels still to write; else unused (the walk ends at the stop)
+        int32_t back;  // 1: walking against the path, entry indices decrease
+        double w_in;   // forward: weight of the edge arriving at `cur` (the first from the graph, later ones from the records)
     };
+    SKB_HD void put(int64_t at, int32_t node, double w) const {
+        pidx[at] = node + id_shift;
+        if (pdata) pdata[at] = values ? values[node] : 1.0;
+        pw[at] = w;
+        if (covered) covered[node] = 1;
+    }
     SKB_HD bool begin(int64_t s, State& st) const {
         skb_i4 a = skb_ld_i4(ranked + s);
         if (a.x >= 0 || a.x == SKB_DEAD) return false;  // never reaches a terminal: a cycle that phase 1 handles
         skb_i4 info = skb_ld_i4(einfo + (-1 - a.x));
-        if (info.x < 0) return false;  // the emitted direction is the other one
+        if (info.x < 0) return false;  // on no emitted path in this direction
+        const bool back = both_ways && info.w == 1;
+        if (!both_ways && info.w != 0) return false;
         int64_t base = pindptr ? pindptr[info.x] : info.z;
-        int32_t pos = info.y - a.y;  // position of this start's node on the path
         int32_t u = su[s];
         int32_t arc = se[s];
-        if (pos == 0) {
-            pidx[base] = u + id_shift;
-            if (pdata) pdata[base] = values ? values[u] : 1.0;
-            pw[base] = 0.0;
-            if (covered) covered[u] = 1;
-        }
-        st.at = base + pos;
         st.prev = u;
         st.cur = indices[arc];
+        st.back = back ? 1 : 0;
+        const int32_t interior = a.w - 1;           // chain voxels strictly between this start's node and the next stop
+        const int32_t ahead = (interior + 1) / 2;   // the share of the start that looks along the path
+        if (back) {
+            // a.y = half-edges from this node back to the path's first node = its position on the path
+            st.at = base + a.y;
+            put(st.at, u, gdata[arc]);  // the edge arriving here along the path is this start's own half-edge, reversed
+            st.left = interior - ahead;
+            st.w_in = 0.0;
+            return st.left > 0;
+        }
+        int32_t pos = info.y - a.y;  // position of this start's node on the path
+        if (pos == 0) put(base, u, 0.0);
+        st.at = base + pos;
         st.w_in = gdata[arc];
-        return true;
+        st.left = both_ways ? ahead : 0x7fffffff;
+        return st.left > 0;
     }
     SKB_HD bool step(State& st) const {
         const int32_t cur = st.cur;
-        const int64_t at = ++st.at;
         const skb_i4* rp = rec + 2 * (int64_t)cur;
         skb_i4 r = skb_ld_i4(rp);
-        pidx[at] = cur + id_shift;
-        if (pdata) pdata[at] = values ? values[cur] : 1.0;
-        pw[at] = st.w_in;
-        if (covered) covered[cur] = 1;
-        if (r.w != 2) return false;
+        if (st.back) {  // cur is an interior chain voxel: its entry carries the weight of the edge to the NEXT voxel back
+            const int64_t at = --st.at;
+            skb_d2 w = skb_ld_d2(rp + 1);
+            const bool first = r.x == st.prev;
+            put(at, cur, first ? w.y : w.x);
+            st.cur = first ? r.y : r.x;
+            st.prev = cur;
+            return --st.left > 0;
+        }
+        const int64_t at = ++st.at;
+        put(at, cur, st.w_in);
+        if (r.w != 2) return false;     // the stop itself (only reached when the whole chain is this start's)
+        if (--st.left == 0) return false;
         skb_d2 w = skb_ld_d2(rp + 1);
         if (r.x == st.prev) {
             st.cur = r.y;

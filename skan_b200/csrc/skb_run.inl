@@ -137,6 +137,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     const int64_t V = g.nvox;
     const int64_t ntiles = (V + SKB_TILE_VOX - 1) / SKB_TILE_VOX;
     int64_t nsync = 0, noverlap = 0, nretaken = 0;
+    const int both_ways = skb_option_both_ways();  // option: second walk written from both ends of every chain
     for (int i = 0; i < 16; ++i) res->counts[i] = 0;
     for (int i = 0; i < 32; ++i) res->off[i] = -1;
     res->work_need = res->out_need = 0;
@@ -480,7 +481,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         take_paths(cap);
         if (work.ok && out.ok) {
             SKB_TRY(skb_path_heads_cap(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin,
-                                       A.einfo, nullptr, nullptr, cap, s));
+                                       A.einfo, nullptr, nullptr, cap, both_ways, s));
             heads_done = true;
             ++noverlap;
         }
@@ -497,8 +498,8 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         take_paths(n_regular);
         SKB_NEED(work.ok && out.ok);
         if (n_regular)
-            SKB_TRY(skb_path_heads(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin, A.einfo,
-                                   nullptr, nullptr, s));
+            SKB_TRY(skb_path_heads_cap(A.su, rec, A.ranked, nullptr, A.sel, A.S, 0, 0, 0, 0, start_node, plen, pmin,
+                                       A.einfo, nullptr, nullptr, 0x7fffffffLL, both_ways, s));
     }
     // Entries: every undirected edge is on exactly one path, so L = E/2 + P; with at most E/6 cycles the arrays can
     // be sized, and the second walk launched, before the number of entries on regular paths (which tells how
@@ -521,8 +522,8 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     double* pdata_w = values ? pdata : nullptr;
     if (!values) SKB_TRY(skb_foreach(L_cap, s, SkbFillF64Item{pdata, 1.0}));
     if (n_regular) {
-        SKB_TRY(skb_path_emit(indices, data, rec, A.su, A.se, A.ranked, A.einfo, pindptr, values, covered, 0, A.S, pidx,
-                              pdata_w, pw, s));
+        SKB_TRY(skb_path_emit_ways(indices, data, rec, A.su, A.se, A.ranked, A.einfo, pindptr, values, covered, 0, A.S,
+                                   pidx, pdata_w, pw, both_ways, s));
         ++noverlap;
         SKB_WAIT(L_reg);
     }
@@ -539,11 +540,11 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         if (r == SKB_RUN_NEED_MORE) SKB_NEED(false);
         if (r) return r;
         if (n_cycles) {
-            SKB_TRY(skb_path_heads(B.su, rec, B.ranked, nullptr, B.sel, B.S, 1, n_regular, 0, 0, start_node, plen, pmin,
-                                   B.einfo, nullptr, nullptr, s));
+            SKB_TRY(skb_path_heads_cap(B.su, rec, B.ranked, nullptr, B.sel, B.S, 1, n_regular, 0, 0, start_node, plen,
+                                       pmin, B.einfo, nullptr, nullptr, 0x7fffffffLL, both_ways, s));
             SKB_TRY(skb_scan_u32_impl(plen, (uint32_t*)pindptr, n_regular + n_cycles, scratch, s));
-            SKB_TRY(skb_path_emit(indices, data, rec, B.su, B.se, B.ranked, B.einfo, pindptr, values, nullptr, 0, B.S,
-                                  pidx, pdata_w, pw, s));
+            SKB_TRY(skb_path_emit_ways(indices, data, rec, B.su, B.se, B.ranked, B.einfo, pindptr, values, nullptr, 0,
+                                       B.S, pidx, pdata_w, pw, both_ways, s));
         }
     }
     SKB_MARK(SKB_M_CYCLES);

@@ -160,7 +160,12 @@ const char* skb_last_error(void) { return g_skb_err; }
 int64_t skb_scan_scratch_bytes(int64_t n) { return ((n + 2047) / 2048 + 2) * 8; }
 int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
 int64_t skb_kernel_launches(void) { return 0; }
-int skb_set_option(const char*, int64_t) { return 0; }  // scheduling tunables of the CUDA build: nothing to tune here
+static int g_skb_both_ways = 0;
+static int skb_option_both_ways() { return g_skb_both_ways; }
+int skb_set_option(const char* name, int64_t value) {  // the scheduling tunables of the CUDA build do nothing here
+    if (name && !strcmp(name, "emit_both_ways")) g_skb_both_ways = value ? 1 : 0;
+    return 0;
+}
 
 int skb_pack_count(const void* image, int dtype, int64_t nvox, uint64_t* bits, uint32_t* tile_counts,
                    int64_t ntiles, int variant, void*) {

@@ -115,3 +115,37 @@ def test_skeleton_from_path_graph_gpu():
         a, b = skan_b200.summarize(sk, separator='_'), skan_b200.summarize(sk2, separator='_')
     for col in a.columns:
         assert np.array_equal(a[col].to_numpy(), b[col].to_numpy()), col
+
+
+def _both_ways_body(to_device):
+    """skb_run_image can write every chain from both ends ("emit_both_ways"); the result must be the same bit for bit
+    as with the one-ended walk, for regular paths, self-loops, junction-free cycles and valued images."""
+    import numpy as np
+    from parity_util import LONG_CHAIN_KINDS, compare_with_oracle, long_chain_image
+    from skan_b200 import _native
+    from skan_b200.synth import walks
+    lib = _native.library()
+    rng = np.random.default_rng(12)
+    images = [(long_chain_image(k, 193), 1) for k in LONG_CHAIN_KINDS]
+    images.append((walks((120, 150), 40, 120, seed=5, isolated=6, rings=5), (2.0, 0.5)))
+    images.append((walks((30, 36, 40), 24, 80, seed=6, isolated=4, rings=3), (0.5, 0.1, 0.1)))
+    images.append(((walks((90, 90), 30, 90, seed=7, rings=3) * (rng.random((90, 90)) + 0.5)).astype(np.float32), 1))
+    try:
+        for mode in (0, 1):
+            lib.call('skb_set_option', b'emit_both_ways', mode)
+            for img, spacing in images:
+                compare_with_oracle(img, spacing, image_for_device=to_device(img))
+    finally:
+        lib.call('skb_set_option', b'emit_both_ways', 0)
+
+
+def test_emit_both_ways_emulated():
+    from emul_util import emulated_device
+    with emulated_device():
+        _both_ways_body(lambda a: a)
+
+
+@pytest.mark.gpu
+def test_emit_both_ways_gpu():
+    import torch
+    _both_ways_body(lambda a: torch.from_numpy(a).cuda())
