@@ -44,7 +44,9 @@ int skb_set_option(const char* name, int64_t value); /* scheduling tunables, no 
                                                         a warp draws new walks, default 8), "emit_both_ways" (1:
                                                         skb_run_image's second walk writes every chain from both of its
                                                         ends, which halves its longest dependent-load chain; 0, default
-                                                        until timed on a B200: from one end) */
+                                                        until timed on a B200: from one end), "splitter_bits" (1..12,
+                                                        default 5: one chain voxel in 2^bits splits the chains into
+                                                        walks; every rank of a Z-slab run must use the same value) */
 int64_t skb_kernel_launches(void);         /* kernels launched by the library since it was loaded */
 
 /* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""A/B of the chain-walk scheduling and of the capacity hints on one GPU, one process, one resident volume:
+"""A/B of the walk options (both-ways emit, splitter density, dynamic scheduling) and of the capacity hints on one GPU,
+one process, one resident volume:
 
     python profiles/tools/ab_walks.py [workload] > gpurun_out/ab_walks.txt
 
@@ -27,12 +28,19 @@ def main():
     img = walks_device(shape, nw, steps, seed, dev, isolated=iso, rings=rings)
     lib = _native.library()
     V = int(np.prod(shape, dtype=np.int64))
-    # (name, dynamic walks, refill threshold, capacity hints)
-    variants = [('static, no hints', 0, 8, False), ('static, hints', 0, 8, True),
-                ('static, no hints (2)', 0, 8, False), ('static, hints (2)', 0, 8, True)]
-    for name, dyn, refill, hints in variants:
-        lib.call('skb_set_option', b'dynamic_walks', dyn)
-        lib.call('skb_set_option', b'walk_refill', refill)
+    # (name, options of skb_set_option, capacity hints)
+    base = dict(dynamic_walks=0, walk_refill=8, emit_both_ways=0, splitter_bits=5)
+    variants = [('default', {}, True),
+                ('emit both ways', dict(emit_both_ways=1), True),
+                ('splitters 1/16', dict(splitter_bits=4), True),
+                ('splitters 1/16, both ways', dict(splitter_bits=4, emit_both_ways=1), True),
+                ('splitters 1/8, both ways', dict(splitter_bits=3, emit_both_ways=1), True),
+                ('no hints', {}, False),
+                ('dynamic walks r8', dict(dynamic_walks=1), True),
+                ('default (again)', {}, True)]
+    for name, opts, hints in variants:
+        for k, v in {**base, **opts}.items():
+            lib.call('skb_set_option', k.encode(), v)
         _pipeline.USE_HINTS = hints
         for _ in range(3):
             _pipeline.run_native(img, spacing=spacing, device=dev)
@@ -51,11 +59,12 @@ def main():
         st = r.counts['stage_ns']
         keys = ('sweep', 'nodes', 'raw_stencil', 'junction_count', 'junction_mst', 'degrees', 'csr_records', 'walk',
                 'rank', 'select', 'heads', 'emit', 'cycles', 'skeleton_ids', 'stats', 'table')
-        print(f'{name:22s} {ms:7.3f} ms/step  {V / ms / 1e3:11.0f} Mvox/s  syncs={r.counts["syncs"]} '
+        print(f'{name:28s} {ms:7.3f} ms/step  {V / ms / 1e3:11.0f} Mvox/s  syncs={r.counts["syncs"]} '
               f'overlapped={r.counts["overlapped"]} retaken={r.counts["retaken"]} | ' +
               ' '.join(f'{k}={st.get(k, 0) * 1e-6:.3f}' for k in keys), flush=True)
-    lib.call('skb_set_option', b'dynamic_walks', 0)
-    lib.call('skb_set_option', b'walk_refill', 8)
+    for k, v in base.items():
+        lib.call('skb_set_option', k.encode(), v)
+    _pipeline.USE_HINTS = True
 
 
 if __name__ == '__main__':

@@ -178,7 +178,8 @@ static int skb_csr_emit_cap(const uint64_t* bits, const uint32_t* pre256, int nd
     SKB_TRY(skb_check_geom(ndim, shape));
     if (height && !values) return skb_fail("height mode needs node values");
     SkbWeight wf{wtab, values, height, dtype};
-    SkbRecOut out{lin_splitters ? lin : nullptr, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min};
+    SkbRecOut out{lin_splitters ? lin : nullptr, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min,
+                  skb_option_split_shift()};
     SkbCsrEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, keep, indptr, wf, indices, data, rec ? 1 : 0, out,
                       edge_cap > 0x7fffffffLL ? 0x7fffffff : (int32_t)edge_cap};
     SKB_TRY(skb_foreach(n, s, it));
@@ -203,7 +204,7 @@ int skb_path_records(const int32_t* indptr, const int32_t* indices, const double
                      const int64_t* slab, int64_t n, skb_i4* rec, uint32_t* startoff, int32_t* par, int32_t* cmin,
                      uint32_t* is_min, void* scratch, void* stream) {
     skb_stream_t s = (skb_stream_t)stream;
-    SkbRecOut out{lin, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min};
+    SkbRecOut out{lin, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min, skb_option_split_shift()};
     SKB_TRY(skb_foreach(n, s, SkbPathRecItem{indptr, indices, gdata, out}));
     return skb_scan_u32_impl(startoff, startoff, n, scratch, s);
 }

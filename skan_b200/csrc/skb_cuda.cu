@@ -164,6 +164,17 @@ static int skb_option_both_ways() {
     }
     return g_skb_both_ways;
 }
+// "splitter_bits": the chain voxels whose hash has this many leading zero bits split the chains into walks
+// (5 = one in 32, the measured default; more splitters = shorter walks, more starts to rank)
+static int g_skb_split_bits = -1;
+static uint32_t skb_option_split_shift() {
+    if (g_skb_split_bits < 0) {
+        const char* e = getenv("SKAN_B200_SPLITTER_BITS");
+        const int v = e ? atoi(e) : 0;
+        g_skb_split_bits = (v >= 1 && v <= 12) ? v : 5;
+    }
+    return 32u - (uint32_t)g_skb_split_bits;
+}
 static int g_skb_steps_dynamic = -1;
 static int g_skb_steps_refill = SKB_DYN_REFILL;
 static bool skb_steps_dynamic() {
@@ -1553,6 +1564,11 @@ int skb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "dynamic_walks")) {
         skb_steps_dynamic();  // read the environment first so that it does not override this later
         g_skb_steps_dynamic = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "splitter_bits")) {
+        if (value < 1 || value > 12) return skb_fail("skb_set_option: splitter_bits must be in 1..12");
+        g_skb_split_bits = (int)value;
         return 0;
     }
     if (!strcmp(name, "emit_both_ways")) {

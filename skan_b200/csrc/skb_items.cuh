@@ -573,9 +573,10 @@ SKB_HD void skb_st_i4(skb_i4* p, skb_i4 v) {
 
 // 1/32 hash sample; the key is the node id, or the global raveled voxel index when a volume is
 // split into Z-slabs (every rank must take the same decision for the same voxel)
-SKB_HD bool skb_hash_splitter(int64_t key) {
+// (shift = 32 - number of hash bits that must be zero: 27 = the default 1/32 sample)
+SKB_HD bool skb_hash_splitter(int64_t key, uint32_t shift = 27u) {
     uint32_t h = (uint32_t)key ^ (uint32_t)(key >> 32);
-    return ((h * 2654435761u) >> 27) == 0u;
+    return ((h * 2654435761u) >> shift) == 0u;
 }
 
 // Z-slab decomposition of one volume over several GPUs (all-zero / full range on a single GPU).
@@ -612,6 +613,7 @@ struct SkbRecOut {
     int32_t* par;      // union-find parent / component minimum of the skeleton-id stage (may be null)
     int32_t* cmin;
     uint32_t* is_min;  // "is the minimum node of a component": isolated pixels are flagged here (csr.py:909)
+    uint32_t split_shift = 27u;  // splitter sample = 2^-(32 - split_shift) of the chain voxels (skb_set_option "splitter_bits")
     SKB_HD void write(int64_t v, int32_t o, int32_t d, int32_t n0, int32_t n1, double w0, double w1) const {
         int32_t iv = (int32_t)v;
         skb_i4 r;
@@ -624,7 +626,7 @@ struct SkbRecOut {
             r.x = n0;
             r.y = n1;
             split = (iv >= sl.ga0 && iv < sl.ga1) || (iv >= sl.gb0 && iv < sl.gb1) ||
-                    skb_hash_splitter(lin ? lin[v] + sl.lin_offset : (int64_t)v);
+                    skb_hash_splitter(lin ? lin[v] + sl.lin_offset : (int64_t)v, split_shift);
             if (split) r.w |= SKB_REC_SPLITTER;
         }
         skb_st_i4(rec + 2 * v, r);

@@ -141,6 +141,11 @@ static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*
 #define SKB_TILE_VOX 16384
 #define SKB_TILE_WORDS 256
 
+// options of skb_set_option that reach shared code
+static int g_skb_split_bits = 5;
+static uint32_t skb_option_split_shift() { return 32u - (uint32_t)g_skb_split_bits; }
+static int g_skb_both_ways = 0;
+static int skb_option_both_ways() { return g_skb_both_ways; }
 #include "skb_api.inl"
 
 static bool skb_host_nonzero(const void* img, int dt, int64_t r) {
@@ -160,10 +165,9 @@ const char* skb_last_error(void) { return g_skb_err; }
 int64_t skb_scan_scratch_bytes(int64_t n) { return ((n + 2047) / 2048 + 2) * 8; }
 int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
 int64_t skb_kernel_launches(void) { return 0; }
-static int g_skb_both_ways = 0;
-static int skb_option_both_ways() { return g_skb_both_ways; }
 int skb_set_option(const char* name, int64_t value) {  // the scheduling tunables of the CUDA build do nothing here
     if (name && !strcmp(name, "emit_both_ways")) g_skb_both_ways = value ? 1 : 0;
+    if (name && !strcmp(name, "splitter_bits") && value >= 1 && value <= 12) g_skb_split_bits = (int)value;
     return 0;
 }
 

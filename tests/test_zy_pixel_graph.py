@@ -149,3 +149,35 @@ def test_emit_both_ways_emulated():
 def test_emit_both_ways_gpu():
     import torch
     _both_ways_body(lambda a: torch.from_numpy(a).cuda())
+
+
+def _splitter_bits_body(to_device):
+    """One chain voxel in 2^bits splits the chains into walks ("splitter_bits"); any value gives the same result."""
+    from parity_util import compare_with_oracle, long_chain_image
+    from skan_b200 import _native
+    from skan_b200.synth import walks
+    lib = _native.library()
+    images = [(long_chain_image(k, 161), 1) for k in ('serpentine', 'nested_rings', 'ring_with_tail')]
+    images.append((walks((40, 44, 48), 30, 90, seed=3, isolated=4, rings=3), (0.5, 0.1, 0.1)))
+    try:
+        for bits in (1, 3, 8, 12):
+            lib.call('skb_set_option', b'splitter_bits', bits)
+            for both in (0, 1):
+                lib.call('skb_set_option', b'emit_both_ways', both)
+                for img, spacing in images:
+                    compare_with_oracle(img, spacing, image_for_device=to_device(img))
+    finally:
+        lib.call('skb_set_option', b'splitter_bits', 5)
+        lib.call('skb_set_option', b'emit_both_ways', 0)
+
+
+def test_splitter_bits_emulated():
+    from emul_util import emulated_device
+    with emulated_device():
+        _splitter_bits_body(lambda a: a)
+
+
+@pytest.mark.gpu
+def test_splitter_bits_gpu():
+    import torch
+    _splitter_bits_body(lambda a: torch.from_numpy(a).cuda())
