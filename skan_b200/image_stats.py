@@ -25,7 +25,11 @@ def _packed_mask(skeleton, device):
     store = torch.zeros(ntiles * (tile // 64) + 18, dtype=torch.int64, device=ctx.device)
     bits = store[16:-2]
     counts = torch.empty(ntiles + 1, dtype=torch.int32, device=ctx.device)
-    ctx.call('skb_pack_count', img, code, nvox, bits, counts, ntiles, _pipeline.PACK_VARIANT[_pipeline.default_pack_variant])
+    variant = min(1, _pipeline.PACK_VARIANT[_pipeline.default_pack_variant])   # LDG or TMA sweep (the fused one emits nodes too)
+    if nvox:
+        ctx.call('skb_pack_count', img, code, nvox, bits, counts, ntiles, variant)
+    else:
+        counts.zero_()
     return ctx, store, bits, nvox, shape, counts[:ntiles]
 
 
