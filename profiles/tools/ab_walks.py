@@ -4,9 +4,9 @@ one process, one resident volume:
 
     python profiles/tools/ab_walks.py [workload] > gpurun_out/ab_walks.txt
 
-For every variant (one walk per thread; lanes refilled from the ticket queue at several refill thresholds) it
-prints the step time (CUDA events around 10 steps after 3 warm-ups) and the runner's stage clock.  Results do
-not depend on the variant (tests/test_gpu_parity.py runs both)."""
+For every variant it prints the step time (CUDA events around 10 steps after 3 warm-ups), the read-back counters and
+the runner's stage clock.  Results do not depend on the variant (tests/test_gpu_parity.py and
+tests/test_zy_pixel_graph.py compare every option with the oracle)."""
 import os
 import sys
 
