@@ -107,3 +107,35 @@ def test_sholl_large_gpu_vs_numpy():
     cross = b0 != b1
     want = np.bincount(np.minimum(b0[cross], b1[cross]), minlength=len(r)) // 2
     assert np.array_equal(counts, want)
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_sholl_random_vs_numpy_emulated(seed):
+    # random skeletons, centres on and off the lattice, integer / float / anisotropic spacing: the device histogram
+    # against the reference's formula (csr.py:1372-1388) evaluated with SciPy / NumPy on the host copies
+    from scipy.spatial import distance_matrix
+    import skan_b200
+    from emul_util import emulated_device
+    from skan_b200.csr import sholl_analysis
+    from skan_b200.synth import walks
+    rng = np.random.default_rng(50 + seed)
+    shape = [(60, 70), (20, 24, 28)][seed % 2]
+    spacing = [1, (2, 3), (0.5, 1.25), (0.5, 0.1, 0.1), 2, (1.5, 1.0, 0.25)][seed % 6]
+    if np.ndim(spacing) and len(spacing) != len(shape):
+        spacing = tuple(spacing)[:len(shape)] if len(spacing) > len(shape) else tuple(spacing) + (1.0,)
+    img = walks(shape, 12, 50, seed=seed, isolated=2, rings=2)
+    with emulated_device():
+        sk = skan_b200.Skeleton(img, spacing=spacing)
+        scaled = sk.coordinates * sk.spacing
+        center = scaled[rng.integers(0, len(scaled))] + (rng.random(len(shape)) if seed % 2 else 0)
+        shells = [None, 7, np.linspace(0.0, 40.0, 9)][seed % 3]
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            c, r, counts = sholl_analysis(sk, center=center, shells=shells)
+            edges = sk.graph.tocoo()
+            d0 = distance_matrix(scaled[edges.row], [c]).ravel()
+            d1 = distance_matrix(scaled[edges.col], [c]).ravel()
+    b0, b1 = np.digitize(d0, r), np.digitize(d1, r)
+    cross = b0 != b1
+    want = np.bincount(np.minimum(b0[cross], b1[cross]), minlength=len(r)) // 2
+    assert np.array_equal(counts, want)

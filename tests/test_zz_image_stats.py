@@ -74,3 +74,26 @@ def test_mesh_sizes_large_gpu_vs_scipy():
     want[touching] = 0
     want = want[want != 0]
     assert np.array_equal(sizes, want)
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_mesh_sizes_random_vs_scipy_emulated(seed):
+    # random masks of every density and ragged widths (rows that straddle 64-bit words in every phase) against
+    # scipy.ndimage.label, with the reference's border / label-0 handling (image_stats.py:31-45)
+    from scipy import ndimage as ndi
+    from emul_util import emulated_device
+    from skan_b200 import image_stats
+    rng = np.random.default_rng(100 + seed)
+    ny, nx = int(rng.integers(1, 90)), int(rng.integers(1, 200))
+    img = rng.random((ny, nx)) < rng.choice([0.05, 0.2, 0.4, 0.6, 0.9])
+    if seed % 3 == 0:
+        img[1:-1, 1:-1] |= False
+        img[0, :] = img[-1, :] = False      # skeleton clear of the top and bottom rows
+    with emulated_device():
+        got = image_stats.mesh_sizes(img)
+    labeled = ndi.label(~img)[0]
+    touching = np.unique(np.concatenate((labeled[0], labeled[-1], labeled[:, 0], labeled[:, -1])))
+    want = np.bincount(labeled.flat)
+    want[touching] = 0
+    want = want[want != 0]
+    assert np.array_equal(got, want), (ny, nx)
