@@ -95,21 +95,26 @@ def _count_skeletons(skeleton, graph):
 
 
 def image_summary(skeleton, *, spacing=1):
-    """Summary statistics of a skeleton image as a one-row pandas.DataFrame (image_stats.py:49-90)."""
+    """Summary statistics of a skeleton image as a one-row pandas.DataFrame (image_stats.py:49-90): scale, number of
+    junctions (degree > 2 after the junction clean-up), image area in real units, junction density, mean / median /
+    standard deviation of the mesh areas and the number of disjoint skeletons -- same column names, order and dtypes."""
     import pandas as pd
+    graph, _ = skeleton_to_csgraph(skeleton, spacing=spacing)
+    shape = tuple(skeleton.shape)
+    n_junctions = np.sum(np.diff(graph.indptr) > 2)
+    area = np.prod(shape) * (spacing**len(shape) if np.isscalar(spacing) else np.prod(spacing))
+    meshes = mesh_sizes(skeleton)
+    columns = [
+        ('number of junctions', n_junctions),
+        ('area', area),
+        ('junctions per unit area', None),          # derived below from the two columns, like the reference
+        ('average mesh area', np.mean(meshes)),
+        ('median mesh area', np.median(meshes)),
+        ('mesh area standard deviation', np.std(meshes)),
+        ('number of disjoint skeletons', _count_skeletons(skeleton, graph)),
+    ]
     stats = pd.DataFrame()
     stats['scale'] = [spacing]
-    g, coords = skeleton_to_csgraph(skeleton, spacing=spacing)
-    degrees = np.diff(g.indptr)
-    num_junctions = np.sum(degrees > 2)
-    stats['number of junctions'] = num_junctions
-    ndim = len(skeleton.shape)
-    pixel_area = spacing**ndim if np.isscalar(spacing) else np.prod(spacing)
-    stats['area'] = np.prod(skeleton.shape) * pixel_area
-    stats['junctions per unit area'] = stats['number of junctions'] / stats['area']
-    sizes = mesh_sizes(skeleton)
-    stats['average mesh area'] = np.mean(sizes)
-    stats['median mesh area'] = np.median(sizes)
-    stats['mesh area standard deviation'] = np.std(sizes)
-    stats['number of disjoint skeletons'] = _count_skeletons(skeleton, g)
+    for name, value in columns:
+        stats[name] = stats['number of junctions'] / stats['area'] if value is None else value
     return stats
