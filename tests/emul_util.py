@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, 'emul', 'skb_emul.cpp')
 OUT = os.path.join(HERE, 'emul', '_build', 'libskb_emul.so')
-DEPS = [SRC] + [os.path.join(ROOT, 'skan_b200', 'csrc', f) for f in ('skb_items.cuh', 'skb_api.inl', 'skb_platform.h', 'skb_run.inl', 'skb_slab.inl')]
+DEPS = [SRC] + [os.path.join(ROOT, 'skan_b200', 'csrc', f) for f in ('skb_items.cuh', 'skb_sholl.cuh', 'skb_mesh.cuh', 'skb_api.inl', 'skb_platform.h', 'skb_run.inl', 'skb_slab.inl')]
 
 
 def build_emulation_library():
