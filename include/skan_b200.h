@@ -37,16 +37,13 @@ int skb_abi_version(void);
 const char* skb_last_error(void);
 int64_t skb_scan_scratch_bytes(int64_t n); /* scratch needed by any call taking `scratch` over n items */
 int64_t skb_tile_voxels(void);             /* voxels per mask tile (16384) */
-int skb_set_option(const char* name, int64_t value); /* scheduling tunables, no effect on results: "dynamic_walks"
-                                                        (0: one chain walk per thread, default; 1: persistent warps
-                                                        whose idle lanes draw new walks from a queue -- measured
-                                                        slower on B200), "walk_refill" (1..32, idle lanes at which
-                                                        a warp draws new walks, default 8), "emit_both_ways" (1:
-                                                        skb_run_image's second walk writes every chain from both of its
-                                                        ends, which halves its longest dependent-load chain; 0, default
-                                                        until timed on a B200: from one end), "splitter_bits" (1..12,
-                                                        default 5: one chain voxel in 2^bits splits the chains into
-                                                        walks; every rank of a Z-slab run must use the same value) */
+int skb_set_option(const char* name, int64_t value); /* tunables with no effect on results: "emit_both_ways" (1,
+                                                        default: skb_run_image's second walk writes every chain from
+                                                        both of its ends, which halves its longest dependent-load
+                                                        chain; 0: from its head only), "splitter_bits" (1..12, default
+                                                        4: one chain voxel in 2^bits splits the chains into walks;
+                                                        every rank of a Z-slab run must use the same value).  Both
+                                                        defaults were measured on B200 (profiles/r02_summary.md) */
 int64_t skb_kernel_launches(void);         /* kernels launched by the library since it was loaded */
 
 /* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of the walk options (both-ways emit, splitter density, dynamic scheduling) and of the capacity hints on one GPU,
+"""A/B of the walk options (both-ways emit, splitter density) and of the capacity hints on one GPU,
 one process, one resident volume:
 
     python profiles/tools/ab_walks.py [workload] > gpurun_out/ab_walks.txt
@@ -29,14 +29,13 @@ def main():
     lib = _native.library()
     V = int(np.prod(shape, dtype=np.int64))
     # (name, options of skb_set_option, capacity hints)
-    base = dict(dynamic_walks=0, walk_refill=8, emit_both_ways=0, splitter_bits=5)
-    variants = [('default', {}, True),
-                ('emit both ways', dict(emit_both_ways=1), True),
-                ('splitters 1/16', dict(splitter_bits=4), True),
-                ('splitters 1/16, both ways', dict(splitter_bits=4, emit_both_ways=1), True),
-                ('splitters 1/8, both ways', dict(splitter_bits=3, emit_both_ways=1), True),
+    base = dict(emit_both_ways=1, splitter_bits=4)
+    variants = [('default (1/16, both ways)', {}, True),
+                ('splitters 1/32, one way (r01)', dict(splitter_bits=5, emit_both_ways=0), True),
+                ('splitters 1/32, both ways', dict(splitter_bits=5), True),
+                ('splitters 1/16, one way', dict(emit_both_ways=0), True),
+                ('splitters 1/8, both ways', dict(splitter_bits=3), True),
                 ('no hints', {}, False),
-                ('dynamic walks r8', dict(dynamic_walks=1), True),
                 ('default (again)', {}, True)]
     for name, opts, hints in variants:
         for k, v in {**base, **opts}.items():

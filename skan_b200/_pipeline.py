@@ -81,6 +81,14 @@ class _Ctx:
             self.stream = 0
         self._scratch = None
 
+    def guard(self):
+        """Make this context's device the current CUDA device for the duration of a native call: the library
+        launches on the current device, which need not be the image's (Skeleton(img_on_cuda1) under cuda:0)."""
+        if self.device.type == 'cuda':
+            return torch.cuda.device(self.device)
+        import contextlib
+        return contextlib.nullcontext()
+
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
@@ -98,12 +106,14 @@ class _Ctx:
             # CUDA events on the launching stream around this entry point (bench.py / profiling only)
             a = torch.cuda.Event(enable_timing=True)
             b = torch.cuda.Event(enable_timing=True)
-            a.record(torch.cuda.current_stream(self.device))
-            r = self.lib.call(name, *conv, self.stream)
-            b.record(torch.cuda.current_stream(self.device))
+            with self.guard():
+                a.record(torch.cuda.current_stream(self.device))
+                r = self.lib.call(name, *conv, self.stream)
+                b.record(torch.cuda.current_stream(self.device))
             hook.setdefault(name, []).append((a, b))
             return r
-        return self.lib.call(name, *conv, self.stream)
+        with self.guard():
+            return self.lib.call(name, *conv, self.stream)
 
 
 def _as_device_image(image, device):
@@ -539,7 +549,8 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
         out = ctx.empty(cache['out_bytes'], torch.uint8)
         prm.work, prm.work_bytes = work.data_ptr(), work.numel()
         prm.out, prm.out_bytes = out.data_ptr(), out.numel()
-        rc = ctx.lib.call('skb_run_image', ctypes_byref(prm), ctypes_byref(res))
+        with ctx.guard():
+            rc = ctx.lib.call('skb_run_image', ctypes_byref(prm), ctypes_byref(res))
         if rc == 0:
             break
         if res.work_need > work.numel():
@@ -548,7 +559,8 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
             cache['out_bytes'] = int(res.out_need)
     else:
         raise _native.NativeError('skb_run_image kept asking for larger arenas')
-    cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
+    if res.out_need > 0:   # what this image needed, plus slack, sizes the next image's output arena
+        cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
     C = {k: int(res.counts[i]) for k, i in _native.RUN_COUNT.items()}
     cache['shape'], cache['nodes'], cache['counts'] = kind, C['nodes'], C
     if prm.time_sweep == 2:

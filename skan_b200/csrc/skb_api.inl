@@ -10,11 +10,13 @@
 //   int  skb_fail(const char* what)                                               (records the message)
 // and the three block-cooperative stages (pack, node emit, scans) itself.
 
+#ifndef SKB_TRY
 #define SKB_TRY(expr)            \
     do {                         \
         int _e = (expr);         \
         if (_e != 0) return _e;  \
     } while (0)
+#endif
 
 #ifndef SKB_RANK_WALK_CAP
 #define SKB_RANK_WALK_CAP 48  // hops of the list-following pass before the synchronous pointer-jumping rounds take over

@@ -37,18 +37,42 @@ static int skb_cuda_check(cudaError_t e, const char* where) {
         if (_e) return _e; \
     } while (0)
 
+#define SKB_TRY(expr)            \
+    do {                         \
+        int _e = (expr);         \
+        if (_e != 0) return _e;  \
+    } while (0)
+
 // kernels launched by this library since load (bench.py reports it as gpu_launches)
 static unsigned long long g_skb_launches = 0;
 #define SKB_COUNT_LAUNCH(k) __atomic_fetch_add(&g_skb_launches, (unsigned long long)(k), __ATOMIC_RELAXED)
 
+// per-device facts, cached per device ordinal (a process may use several GPUs, from several threads)
+#define SKB_MAX_DEV 64
+static int skb_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SKB_MAX_DEV) return 0;
+    return dev;
+}
 static int skb_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static int sms[SKB_MAX_DEV] = {};
+    const int dev = skb_current_device();
+    int v = __atomic_load_n(&sms[dev], __ATOMIC_RELAXED);
+    if (!v) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        __atomic_store_n(&sms[dev], v, __ATOMIC_RELAXED);
     }
-    return sms;
+    return v;
+}
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: once per kernel AND device
+template <typename K>
+static int skb_optin_smem(K kernel, size_t bytes, uint8_t* done /* [SKB_MAX_DEV] */) {
+    const int dev = skb_current_device();
+    if (!__atomic_load_n(&done[dev], __ATOMIC_ACQUIRE)) {
+        SKB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        __atomic_store_n(&done[dev], (uint8_t)1, __ATOMIC_RELEASE);
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------- foreach
@@ -69,139 +93,35 @@ static int skb_foreach(int64_t n, skb_stream_t s, F f) {
     return skb_cuda_check(cudaGetLastError(), "skb_foreach launch");
 }
 
-// ------------------------------------------------------------------------------- foreach, stepwise items
-// Items whose work is a loop of dependent loads of very uneven length (the chain walks): one item per thread
-// leaves a warp waiting for its longest walk with a handful of lanes active (ncu: 5-9 of 32).  Here a warp is
-// persistent and its lanes are refilled from a queue: F::begin(i, st) starts item i (false = nothing to
-// iterate), F::step(st) advances it by one hop (false = finished, after which F::finish(i, st) stores the
-// result).  The queue is one 64-bit ticket counter per launch; a warp draws SKB_DYN_CHUNK consecutive items at a
-// time and hands them to its idle lanes in item order, whenever at least SKB_DYN_REFILL lanes are idle.
-#define SKB_DYN_CHUNK 64
-#define SKB_DYN_REFILL 8
-#define SKB_DYN_SLOTS 64
-
-template <typename F>
-__global__ void __launch_bounds__(256) skb_foreach_steps_kernel(F f, int64_t n, unsigned long long* ticket, int refill) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned below = (1u << lane) - 1u;
-    typename F::State st;
-    int64_t item = 0;
-    bool active = false;
-    int64_t pos = 0, end = 0;  // warp-uniform: the part of the drawn chunk not handed out yet
-    bool exhausted = false;    // warp-uniform: a draw came back past the end of the queue
-    for (;;) {
-        unsigned idle = __ballot_sync(full, !active);
-        if (idle == full && exhausted) break;
-        if (!exhausted && __popc(idle) >= refill) {
-            do {
-                if (pos >= end) {
-                    unsigned long long b = 0;
-                    if (lane == 0) b = atomicAdd(ticket, (unsigned long long)SKB_DYN_CHUNK);
-                    b = __shfl_sync(full, b, 0);
-                    if ((int64_t)b >= n) {
-                        exhausted = true;
-                        break;
-                    }
-                    pos = (int64_t)b;
-                    end = pos + SKB_DYN_CHUNK < n ? pos + SKB_DYN_CHUNK : n;
-                }
-                if (!active) {
-                    const int64_t i = pos + __popc(idle & below);
-                    if (i < end) {
-                        item = i;
-                        active = f.begin(i, st);
-                    }
-                }
-                pos += __popc(idle);
-                idle = __ballot_sync(full, !active);
-            } while (__popc(idle) >= refill);
-        }
-        if (active) {
-            active = f.step(st);
-            if (!active) f.finish(item, st);
-        }
-    }
-    // every warp of the grid draws exactly once past the end; the last one to leave resets the ticket for the
-    // next launch that uses this slot (ticket[1] counts the warps that have left)
-    if (lane == 0) {
-        const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
-        if (atomicAdd(ticket + 1, 1ull) == warps - 1) {
-            ticket[0] = 0;
-            ticket[1] = 0;
-        }
-    }
-}
-
-// ticket slots: a small ring per host thread and device, zeroed once; a launch leaves its slot zeroed again
-static int skb_ticket_slot(unsigned long long** out) {
-    enum { MAX_DEV = 64 };
-    static thread_local unsigned long long* ring[MAX_DEV] = {};
-    static thread_local unsigned next[MAX_DEV] = {};
-    int dev = 0;
-    SKB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= MAX_DEV) return skb_fail("device ordinal out of range");
-    if (!ring[dev]) {
-        void* p = nullptr;
-        SKB_CUDA(cudaMalloc(&p, SKB_DYN_SLOTS * 16));
-        SKB_CUDA(cudaMemset(p, 0, SKB_DYN_SLOTS * 16));
-        SKB_CUDA(cudaDeviceSynchronize());  // once: the zeroes are in place before any stream uses a slot
-        ring[dev] = (unsigned long long*)p;
-    }
-    *out = ring[dev] + 2 * (next[dev]++ % SKB_DYN_SLOTS);
-    return 0;
-}
-
-// tunables (skb_set_option, or the environment at first use): "dynamic_walks" 0 = one item per thread (default);
-// "walk_refill" = idle lanes at which a warp draws new items (1..32)
-// "emit_both_ways": 1 = the second walk writes every chain from both ends.  Off by default until it has been timed on
-// a B200 (it was written after the round's GPU budget was spent; bit-identical results in the emulation harness)
+// tunables (skb_set_option, or the environment at first use), measured on B200 in round 2 (profiles/r02_ab_walks_*.txt):
+// "emit_both_ways": 1 (default) = the second walk writes every chain from both of its ends; 0 = from its head only.
 static int g_skb_both_ways = -1;
 static int skb_option_both_ways() {
     if (g_skb_both_ways < 0) {
         const char* e = getenv("SKAN_B200_EMIT_BOTH_WAYS");
-        g_skb_both_ways = (e && e[0] == '1') ? 1 : 0;
+        g_skb_both_ways = (e && e[0] == '0') ? 0 : 1;
     }
     return g_skb_both_ways;
 }
 // "splitter_bits": the chain voxels whose hash has this many leading zero bits split the chains into walks
-// (5 = one in 32, the measured default; more splitters = shorter walks, more starts to rank)
+// (4 = one in 16, the measured default: a walk kernel lasts as long as its longest walk, ~16 ln(starts) hops;
+// more splitters = shorter walks, more starts to rank)
 static int g_skb_split_bits = -1;
 static uint32_t skb_option_split_shift() {
     if (g_skb_split_bits < 0) {
         const char* e = getenv("SKAN_B200_SPLITTER_BITS");
         const int v = e ? atoi(e) : 0;
-        g_skb_split_bits = (v >= 1 && v <= 12) ? v : 5;
+        g_skb_split_bits = (v >= 1 && v <= 12) ? v : 4;
     }
     return 32u - (uint32_t)g_skb_split_bits;
 }
-static int g_skb_steps_dynamic = -1;
-static int g_skb_steps_refill = SKB_DYN_REFILL;
-static bool skb_steps_dynamic() {
-    if (g_skb_steps_dynamic < 0) {
-        const char* e = getenv("SKAN_B200_DYNAMIC_WALKS");
-        g_skb_steps_dynamic = (e && e[0] == '1') ? 1 : 0;  // off by default: measured slower on B200
-        const char* r = getenv("SKAN_B200_WALK_REFILL");
-        if (r && atoi(r) >= 1 && atoi(r) <= 32) g_skb_steps_refill = atoi(r);
-    }
-    return g_skb_steps_dynamic != 0;
-}
 
+// stepwise items (the chain walks: begin / step / finish): one item per thread.  A variant with persistent warps
+// whose idle lanes drew new walks from a ticket queue was measured slower twice (r01: 3.73 -> 4.02 ms, r02: 3.68 ->
+// 3.97 ms at 2048^3) and has been removed: a walk kernel lasts as long as its longest walk, not as its lane count.
 template <typename F>
 static int skb_foreach_steps(int64_t n, skb_stream_t s, F f) {
-    if (n <= 0) return 0;
-    if (!skb_steps_dynamic()) return skb_foreach(n, s, f);  // F::operator() runs begin / step / finish in place
-    int64_t blocks = (n + 255) / 256;
-    int64_t cap = (int64_t)skb_sm_count() * 8;  // persistent: 2048 threads per SM
-    if (blocks > cap) blocks = cap;
-    unsigned long long* ticket = nullptr;
-    {
-        int e = skb_ticket_slot(&ticket);
-        if (e) return e;
-    }
-    skb_foreach_steps_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n, ticket, g_skb_steps_refill);
-    SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "skb_foreach_steps launch");
+    return skb_foreach(n, s, f);  // F::operator() runs begin / step / finish in place
 }
 
 // ------------------------------------------------------------------------------- foreach over unmarked items
@@ -360,7 +280,8 @@ struct SkbTimer {
     cudaEvent_t a, b;
 };
 static int skb_timer_start(void** handle, skb_stream_t s) {
-    static thread_local SkbTimer t = {nullptr, nullptr};
+    static thread_local SkbTimer per_dev[SKB_MAX_DEV] = {};  // an event belongs to the device it was created on
+    SkbTimer& t = per_dev[skb_current_device()];
     if (!t.a) {
         SKB_CUDA(cudaEventCreate(&t.a));
         SKB_CUDA(cudaEventCreate(&t.b));
@@ -382,13 +303,15 @@ static int skb_timer_read_ns(void* handle, int64_t* ns) {  // call after the str
 
 // stage clock of the native runner (skb_run_params.time_sweep == 2): one event per stage boundary
 #define SKB_MAX_MARKS 32
-static thread_local cudaEvent_t g_skb_marks[SKB_MAX_MARKS] = {};
+static thread_local cudaEvent_t g_skb_marks_dev[SKB_MAX_DEV][SKB_MAX_MARKS] = {};
 static int skb_stage_mark(int idx, skb_stream_t s) {
     if (idx < 0 || idx >= SKB_MAX_MARKS) return skb_fail("stage mark out of range");
+    cudaEvent_t* g_skb_marks = g_skb_marks_dev[skb_current_device()];
     if (!g_skb_marks[idx]) SKB_CUDA(cudaEventCreate(&g_skb_marks[idx]));
     return skb_cuda_check(cudaEventRecord(g_skb_marks[idx], s), "cudaEventRecord");
 }
 static int skb_stage_read(const uint8_t* marked, int n, int64_t* ns) {  // ns[i] = time from the previous recorded mark to mark i
+    cudaEvent_t* g_skb_marks = g_skb_marks_dev[skb_current_device()];
     int prev = -1;
     for (int i = 0; i < n; ++i) {
         ns[i] = 0;
@@ -809,12 +732,8 @@ static int skb_pack_launch(const void* img, int64_t nvox, bool is_float, uint64_
     if (variant == 1) {
         constexpr int STAGES = 4;
         size_t smem = (size_t)STAGES * SKB_STAGE_BYTES;
-        static bool attr_set = false;
-        if (!attr_set) {
-            SKB_CUDA(cudaFuncSetAttribute(skb_pack_tma_kernel<ESIZE, STAGES>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
+        static uint8_t attr_set[SKB_MAX_DEV] = {};
+        SKB_TRY(skb_optin_smem(skb_pack_tma_kernel<ESIZE, STAGES>, smem, attr_set));
         int64_t grid = (int64_t)sms * 3;
         if (grid > ntiles) grid = ntiles;
         skb_pack_tma_kernel<ESIZE, STAGES><<<(unsigned)grid, SKB_PACK_THREADS, smem, s>>>(
@@ -1396,12 +1315,8 @@ static int skb_sweep_nodes_launch(const void* img, int64_t nvox, bool is_float, 
                                   skb_stream_t s) {
     constexpr int STAGES = 3;
     const size_t smem = (size_t)STAGES * SKB_STAGE_BYTES;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SKB_CUDA(cudaFuncSetAttribute(skb_sweep_nodes_kernel<ESIZE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-        attr_set = true;
-    }
+    static uint8_t attr_set[SKB_MAX_DEV] = {};
+    SKB_TRY(skb_optin_smem(skb_sweep_nodes_kernel<ESIZE, STAGES>, smem, attr_set));
     const int64_t nchunks = (nvox + SKB_CHUNK_VOX - 1) / SKB_CHUNK_VOX;
     int64_t grid = (int64_t)skb_sm_count() * 3;
     if (grid > nchunks) grid = nchunks;
@@ -1561,11 +1476,6 @@ int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
 
 int skb_set_option(const char* name, int64_t value) {
     if (!name) return skb_fail("skb_set_option: null name");
-    if (!strcmp(name, "dynamic_walks")) {
-        skb_steps_dynamic();  // read the environment first so that it does not override this later
-        g_skb_steps_dynamic = value ? 1 : 0;
-        return 0;
-    }
     if (!strcmp(name, "splitter_bits")) {
         if (value < 1 || value > 12) return skb_fail("skb_set_option: splitter_bits must be in 1..12");
         g_skb_split_bits = (int)value;
@@ -1573,12 +1483,6 @@ int skb_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "emit_both_ways")) {
         g_skb_both_ways = value ? 1 : 0;
-        return 0;
-    }
-    if (!strcmp(name, "walk_refill")) {
-        if (value < 1 || value > 32) return skb_fail("skb_set_option: walk_refill must be in 1..32");
-        skb_steps_dynamic();
-        g_skb_steps_refill = (int)value;
         return 0;
     }
     return skb_fail("skb_set_option: unknown option");

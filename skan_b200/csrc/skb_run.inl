@@ -112,6 +112,7 @@ struct SkbArena {
         SKB_TRY(skb_fetch_i32((const int32_t*)(ptr), &_v, s)); \
         (dst) = _v;                                           \
         ++nsync;                                              \
+        if (_v < 0) return skb_fail("a count exceeds int32: the reference's int32 index arrays cannot hold this graph"); \
     } while (0)
 
 // posted read-back of one count (see skb_fetch_post): the kernels launched before SKB_WAIT overlap its round trip
@@ -126,6 +127,7 @@ struct SkbArena {
         SKB_TRY(skb_fetch_wait(1, _v, s));    \
         (dst) = _v[0];                        \
         ++nsync;                              \
+        if (_v[0] < 0) return skb_fail("a count exceeds int32: the reference's int32 index arrays cannot hold this graph"); \
     } while (0)
 
 extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
@@ -158,6 +160,15 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     SkbArena work, out;
     work.init(prm->work, prm->work_bytes);
     out.init(prm->out, prm->out_bytes);
+    // every successful return reports what the image needed: the caller sizes the next image's arenas by it
+#define SKB_RUN_DONE()                            \
+    do {                                          \
+        res->counts[SKB_C_SYNCS] = nsync;         \
+        res->counts[SKB_C_OVERLAPPED] = noverlap; \
+        res->counts[SKB_C_RETAKEN] = nretaken;    \
+        res->work_need = work.need;               \
+        res->out_need = out.need;                 \
+    } while (0)
     auto out_off = [&](const void* p) -> int64_t { return p ? (int64_t)((const uint8_t*)p - out.base) : -1; };
 
     // ---- mask sweep, scan, nodes (one fused pass, or sweep -> tile scan -> node emission) ---------------
@@ -390,9 +401,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     res->off[SKB_O_COMP_RANK] = out_off(is_min);
     if (!paths_wanted || N == 0 || E == 0) {
         SKB_MARKS_DONE();
-        res->counts[SKB_C_SYNCS] = nsync;
-    res->counts[SKB_C_OVERLAPPED] = noverlap;
-    res->counts[SKB_C_RETAKEN] = nretaken;
+        SKB_RUN_DONE();
         return 0;
     }
     // ---- paths: phase 0 (between terminals), phase 1 (junction-free cycles) ------------------------------------
@@ -560,9 +569,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     res->off[SKB_O_PW] = out_off(pw);
     if (P == 0) {
         SKB_MARKS_DONE();
-        res->counts[SKB_C_SYNCS] = nsync;
-    res->counts[SKB_C_OVERLAPPED] = noverlap;
-    res->counts[SKB_C_RETAKEN] = nretaken;
+        SKB_RUN_DONE();
         return 0;
     }
     // ---- skeleton ids, statistics, branch table ----------------------------------------------------------------------
@@ -591,10 +598,6 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     res->off[SKB_O_T32] = out_off(t32);
     res->off[SKB_O_T64] = out_off(t64);
     res->off[SKB_O_TF] = out_off(tf);
-    res->counts[SKB_C_SYNCS] = nsync;
-    res->counts[SKB_C_OVERLAPPED] = noverlap;
-    res->counts[SKB_C_RETAKEN] = nretaken;
-    res->work_need = work.need;
-    res->out_need = out.need;
+    SKB_RUN_DONE();
     return 0;
 }

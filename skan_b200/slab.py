@@ -278,13 +278,22 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         out = ctx.empty(cache['out_bytes'], torch.uint8)
         prm.work, prm.work_bytes = work.data_ptr(), work.numel()
         prm.out, prm.out_bytes = out.data_ptr(), out.numel()
-        rc = ctx.lib.call('skb_run_slab', ctypes.byref(prm), comm['handle'], ctypes.byref(res))
+        failure = None
+        try:
+            with ctx.guard():
+                rc = ctx.lib.call('skb_run_slab', ctypes.byref(prm), comm['handle'], ctypes.byref(res))
+        except _native.NativeError as e:   # the peers see the abort word and come here too: tell them, then raise
+            failure, rc = e, -1
         if rc == 0:
             break
         # rare: some rank needs larger arenas.  The ranks agree on what happened through the process group
         # (they no longer agree on the exchange sequence), then run again.
         rcs = [None] * world
         dist.all_gather_object(rcs, (int(rc), int(res.exchange_need)), group=group)
+        if failure is not None:
+            raise failure
+        if any(r[0] < 0 for r in rcs):
+            raise _native.NativeError('skb_run_slab failed on rank ' + str([k for k, r in enumerate(rcs) if r[0] < 0]))
         if rc == 1:
             if res.work_need > work.numel():
                 cache['work'] = ctx.empty(int(res.work_need), torch.uint8)

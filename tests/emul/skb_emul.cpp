@@ -142,9 +142,9 @@ static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*
 #define SKB_TILE_WORDS 256
 
 // options of skb_set_option that reach shared code
-static int g_skb_split_bits = 5;
+static int g_skb_split_bits = 4;
 static uint32_t skb_option_split_shift() { return 32u - (uint32_t)g_skb_split_bits; }
-static int g_skb_both_ways = 0;
+static int g_skb_both_ways = 1;
 static int skb_option_both_ways() { return g_skb_both_ways; }
 #include "skb_api.inl"
 

@@ -138,11 +138,16 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             share['n_regular'] = res.n_regular
             share['meta'] = dict(rank_rounds=res.rank_rounds, table_rounds=res.table_rounds, n_table=res.n_table,
                                  n_cycles=res.n_cycles, native=hasattr(res, 'counts'))
+            from skan_b200 import digest
+            dg = digest.digest_slab(res)     # collective: the same on every rank
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(share, gathered, dst=0)
         if rank == 0:
             glob = assemble(gathered, world)
             ref = compare_with_oracle(img, spacing, glob)
+            from oracle import skan_oracle as orc
+            want = digest.digest_oracle(ref, orc.summarize(ref))
+            assert digest.same(dg, want), f'digest of the slab run differs from the oracle\'s: {dg} != {want}'
             print(f'SLAB-OK world={world} kind={kind} shape={shape} nodes={ref.graph.shape[0]} paths={ref.n_paths} '
                   f'cycles={sum(g["meta"]["n_cycles"] for g in gathered)} table={gathered[0]["meta"]["n_table"]} '
                   f'table_rounds={gathered[0]["meta"]["table_rounds"]} native={int(gathered[0]["meta"]["native"])}', flush=True)

@@ -13,6 +13,7 @@ from skan_b200.synth import walks, walks_device
 
 import skan_b200
 from skan_b200 import _pipeline
+from oracle import skan_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
@@ -257,30 +258,20 @@ def test_native_runner_equals_stagewise_sequencing(shape, valued):
                            y.view(torch.uint8) if y.dtype.is_floating_point else y), i
 
 
-@pytest.mark.parametrize('dynamic,refill', [(0, 8), (1, 1), (1, 8), (1, 32)])
-def test_walk_scheduling_variants_vs_oracle(dynamic, refill):
-    # the chain walks run either one per thread or on persistent warps whose idle lanes draw new walks from a
-    # ticket queue (skb_foreach_steps); scheduling must not change a single bit of the result
-    from skan_b200 import _native
-    lib = _native.library()
+def test_image_on_a_device_that_is_not_current():
+    """Skeleton(image on cuda:k) while another device is current: the library must run on the image's device (per-device
+    SM count, shared-memory opt-in, events and mailbox)."""
+    n = torch.cuda.device_count()
+    img = walks((40, 48, 56), 24, 96, seed=7, isolated=5, rings=3)
+    ref = orc.OracleSkeleton(img, spacing=(0.5, 0.1, 0.1))
+    prev = torch.cuda.current_device()
     try:
-        lib.call('skb_set_option', b'dynamic_walks', dynamic)
-        lib.call('skb_set_option', b'walk_refill', refill)
-        compare_with_oracle(walks((96, 128, 160), 96, 128, seed=11, isolated=20, rings=8), (0.5, 0.1, 0.1))
-        for kind in ('serpentine', 'nested_rings', 'comb'):
-            img = long_chain_image(kind, 385)
-            compare_with_oracle(img, 1)
-        rng = np.random.default_rng(5)
-        img = walks((700, 900), 200, 300, seed=9, isolated=10, rings=6)
-        compare_with_oracle((img * (rng.random(img.shape) + 0.5)).astype(np.float32), (2.0, 0.5))
-        # many more walks than one launch has lanes: every warp draws several chunks
-        big = walks_device((512, 512, 512), 4096, 400, 21, torch.device('cuda'), isolated=100, rings=32)
-        sk = skan_b200.Skeleton(big, spacing=1)
-        lib.call('skb_set_option', b'dynamic_walks', 0)
-        base = skan_b200.Skeleton(big, spacing=1)
-        assert np.array_equal(sk.paths.indptr, base.paths.indptr)
-        assert np.array_equal(sk.paths.indices, base.paths.indices)
-        assert np.array_equal(sk.path_lengths(), base.path_lengths())
+        for k in range(min(n, 3) - 1, -1, -1):           # the highest device first, device 0 current
+            torch.cuda.set_device(0 if k else n - 1)
+            sk = skan_b200.Skeleton(torch.from_numpy(img).to(f'cuda:{k}'), spacing=(0.5, 0.1, 0.1))
+            assert np.array_equal(sk.graph.indices, ref.graph.indices)
+            assert np.array_equal(sk.paths.indices, ref.paths.indices)
+            df = skan_b200.summarize(sk, separator='_')
+            assert len(df) == ref.n_paths
     finally:
-        lib.call('skb_set_option', b'dynamic_walks', 0)
-        lib.call('skb_set_option', b'walk_refill', 8)
+        torch.cuda.set_device(prev)

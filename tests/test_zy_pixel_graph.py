@@ -136,7 +136,7 @@ def _both_ways_body(to_device):
             for img, spacing in images:
                 compare_with_oracle(img, spacing, image_for_device=to_device(img))
     finally:
-        lib.call('skb_set_option', b'emit_both_ways', 0)
+        lib.call('skb_set_option', b'emit_both_ways', 1)
 
 
 def test_emit_both_ways_emulated():
@@ -167,8 +167,8 @@ def _splitter_bits_body(to_device):
                 for img, spacing in images:
                     compare_with_oracle(img, spacing, image_for_device=to_device(img))
     finally:
-        lib.call('skb_set_option', b'splitter_bits', 5)
-        lib.call('skb_set_option', b'emit_both_ways', 0)
+        lib.call('skb_set_option', b'splitter_bits', 4)
+        lib.call('skb_set_option', b'emit_both_ways', 1)
 
 
 def test_splitter_bits_emulated():
