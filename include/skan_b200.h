@@ -73,7 +73,6 @@ int skb_emit_nodes(const uint64_t* bits, const uint32_t* tile_prefix, int64_t nt
 int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_t ntiles, int ndim,
                        const int64_t* shape /*host*/, const void* image, int dtype, int64_t z_origin, int64_t* lin,
                        int64_t* coords, double* values, uint32_t* pre256, int64_t node_cap, void* stream);
-
 /* Mask sweep + scan + node emission in ONE pass over the image (csr.py:1070,122-123,131-132,1088,
  * 554-562): writes what skb_pack_count + skb_scan_u32 + skb_emit_nodes write (bits, pre256, lin,
  * coords, values) except the tile counts, without reading the mask back.  The node arrays have room

@@ -37,6 +37,9 @@ def main():
                 ('splitters 1/8, both ways', dict(splitter_bits=3), True),
                 ('no hints', {}, False),
                 ('default (again)', {}, True)]
+    only = os.environ.get('AB_ONLY')
+    if only:
+        variants = [v for v in variants if any(k in v[0] for k in only.split(','))]
     for name, opts, hints in variants:
         for k, v in {**base, **opts}.items():
             lib.call('skb_set_option', k.encode(), v)

@@ -23,17 +23,9 @@
 #endif
 
 static SkbGeom skb_make_geom(int ndim, const int64_t* shape) {
-    SkbGeom g;
     int64_t s[3] = {1, 1, 1};
     for (int i = 0; i < ndim; ++i) s[3 - ndim + i] = shape[i];
-    g.nz = (int32_t)s[0];
-    g.ny = (int32_t)s[1];
-    g.nx = (int32_t)s[2];
-    g.ndim = ndim;
-    g.sz = s[1] * s[2];
-    g.inv_sz = 1.0 / (double)g.sz;
-    g.nvox = s[0] * s[1] * s[2];
-    return g;
+    return skb_geom_make(ndim, s[0], s[1], s[2]);
 }
 
 static int skb_check_geom(int ndim, const int64_t* shape) {

@@ -754,22 +754,25 @@ static int skb_pack_launch(const void* img, int64_t nvox, bool is_float, uint64_
 // (csr.py:1088) and fp64 values (csr.py:554-562) of every foreground voxel, in raster order
 // (csr.py:131-132).  Reads V/8 bytes of mask; no block-wide barrier anywhere.
 #define SKB_EMIT_THREADS 256
-#define SKB_EMIT_CAP 512  // set bits of one 4096-voxel group staged in shared memory per warp
 
-// coordinates of voxel (tile origin + off) from the tile origin's coordinates: 32-bit arithmetic only
-__device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int64_t z0, int32_t y0, int32_t x0,
+// coordinates of voxel (tile origin + off) from the tile origin's coordinates: 32-bit arithmetic only.
+// (Folding the stencil stage in here -- the coordinates are at hand, the rows are being streamed -- was measured in
+// round 2 and lost: 0.26 + 0.23 ms as two kernels, 0.52-0.80 ms as one; the emission is issue-bound and the stencil's
+// dependent loads sit badly in its per-tile chain.)
+__device__ __forceinline__ void skb_emit_one(uint32_t off, int64_t r0, int32_t zt, int64_t z_add, int32_t y0, int32_t x0,
                                              uint32_t id, const SkbGeom& g, const void* img, int dtype,
                                              int64_t* __restrict__ lin, int64_t* __restrict__ coords,
                                              double* __restrict__ values) {
     int64_t r = r0 + off;
     lin[id] = r;
     uint32_t t = (uint32_t)x0 + off;
-    uint32_t q = t / (uint32_t)g.nx;
+    uint32_t q = skb_udiv(t, g.dx);
     uint32_t x = t - q * (uint32_t)g.nx;
     uint32_t t2 = (uint32_t)y0 + q;
-    uint32_t q2 = t2 / (uint32_t)g.ny;
+    uint32_t q2 = skb_udiv(t2, g.dy);
     uint32_t y = t2 - q2 * (uint32_t)g.ny;
-    int64_t z = z0 + q2;
+    const int32_t zl = zt + (int32_t)q2;  // plane inside this volume / slab
+    int64_t z = z_add + zl;
     int64_t* c = coords + (int64_t)id * g.ndim;
     if (g.ndim == 3) {
         c[0] = z;
@@ -796,13 +799,51 @@ __device__ __forceinline__ void skb_advance_coords(const SkbGeom& g, int32_t& z,
     z += dz + c;
 }
 
-__device__ __forceinline__ uint32_t skb_stage_bits(uint64_t w, uint32_t off, uint16_t* __restrict__ st, uint32_t k) {
-    while (w) {
-        st[k++] = (uint16_t)(off + (uint32_t)(__ffsll((long long)w) - 1));
-        w &= w - 1;
+// One tile of the node emission: the rank structure (pre256), and the tile's 256 mask words plus the inclusive count of
+// set bits up to and including every word parked in shared memory for the emission loop.  Returns the tile's count.
+__device__ __forceinline__ uint32_t skb_rank_tile(const int64_t tile, const uint32_t t0, const uint32_t total, const int lane,
+                                                  const uint64_t* __restrict__ bits, uint4* __restrict__ s_words,
+                                                  uint32_t* __restrict__ s_incl, uint32_t* __restrict__ pre256) {
+    if (total == 0) {  // empty tile: only the rank structure (64 blocks of 256 bits)
+        ((uint2*)(pre256 + tile * 64))[lane] = make_uint2(t0, t0);
+        return 0u;
     }
-    return k;
+    // coalesced 128-bit loads: lane holds words 2*(32 j + lane) and +1 for j = 0..3
+    const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS) + lane;
+    uint4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = src[32 * j];
+    uint32_t c0[4], c1[4];
+    // one warp scan for the four groups: 16-bit fields (a group holds at most 4096 set bits)
+    unsigned long long packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s_words[32 * j + lane] = q[j];
+        c0[j] = (uint32_t)(__popc(q[j].x) + __popc(q[j].y));
+        c1[j] = (uint32_t)(__popc(q[j].z) + __popc(q[j].w));
+        packed |= (unsigned long long)(c0[j] + c1[j]) << (16 * j);
+    }
+    unsigned long long inc = packed;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xffffffffu, inc, s);
+        if (lane >= s) inc += o;
+    }
+    const unsigned long long ex = inc - packed;
+    const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;              // nodes of the tile in groups before j
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t before = base + (uint32_t)((ex >> (16 * j)) & 0xffffu);  // set bits of the tile before this lane's pair
+        base += (uint32_t)((tot >> (16 * j)) & 0xffffu);
+        // words 2*(32 j + lane), +1: the even lane of each pair starts a 256-bit block
+        if ((lane & 1) == 0) pre256[tile * 64 + j * 16 + (lane >> 1)] = t0 + before;
+        s_incl[32 * j + lane] = (before + c0[j]) | ((before + c0[j] + c1[j]) << 16);  // two 16-bit inclusive counts
+    }
+    return total;
 }
+
+#define SKB_EMIT_WARPS (SKB_EMIT_THREADS / 32)
 
 template <bool VALUES>  // false: boolean image, no node values (csr.py:554-562) and no dtype dispatch in the kernel
 __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
@@ -812,97 +853,65 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     // node_cap: capacity of lin / coords / values (the runner may size them by a hint before the count has
     // arrived); nodes with id >= node_cap are not written, the rank structure always is
     double* __restrict__ values = VALUES ? values_arg : nullptr;
-    __shared__ uint16_t stage[SKB_EMIT_THREADS / 32][SKB_EMIT_CAP];
+    __shared__ __align__(16) uint4 s_words[SKB_EMIT_WARPS][2][SKB_TILE_WORDS / 2];
+    __shared__ uint32_t s_incl[SKB_EMIT_WARPS][2][SKB_TILE_WORDS / 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warps = (int64_t)gridDim.x * (SKB_EMIT_THREADS / 32);
-    uint16_t* st = stage[warp];
+    const int64_t warps = (int64_t)gridDim.x * SKB_EMIT_WARPS;
+    const int64_t z_add = g.ndim == 3 ? z_origin : 0;
     // Coordinates of the tile origin: divided out once per warp (64-bit divisions when the volume has more than
     // 2^32 voxels), then advanced by the constant stride of the loop with two carries per tile.
-    int64_t tile = (int64_t)blockIdx.x * (SKB_EMIT_THREADS / 32) + warp;
-    int32_t zt = 0, y0 = 0, x0 = 0, dzt, dy0, dx0;
-    if (tile < ntiles) skb_coords(g, tile * SKB_TILE_VOX, zt, y0, x0);
+    int64_t tile = (int64_t)blockIdx.x * SKB_EMIT_WARPS + warp;
+    int32_t za = 0, ya = 0, xa = 0, dzt, dy0, dx0;
+    if (tile < ntiles) skb_coords(g, tile * SKB_TILE_VOX, za, ya, xa);
     skb_coords(g, warps * SKB_TILE_VOX, dzt, dy0, dx0);  // may exceed the volume: only a displacement
-    for (; tile < ntiles; tile += warps, skb_advance_coords(g, zt, y0, x0, dzt, dy0, dx0)) {
-        // The warp's iteration is a chain of dependent latencies (prefix -> mask -> scan -> stores), not of issue
-        // slots: the mask is requested before the tile's count is looked at (one DRAM round trip instead of two;
-        // empty tiles are rare enough that reading them does not matter), and the next tile of this warp is
-        // pulled into L2 meanwhile.
-        // coalesced 128-bit loads: lane holds words 2*(32 j + lane) and +1 for j = 0..3
-        const uint4* src = (const uint4*)(bits + tile * SKB_TILE_WORDS) + lane;
-        const uint4 q0 = src[0], q1 = src[32], q2 = src[64], q3 = src[96];
-        const uint32_t t0 = tile_prefix[tile], total = tile_prefix[tile + 1] - t0;
-        if (tile + warps < ntiles) {
-            if (lane < 16)  // 16 lines of 128 bytes
-                asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(bits + (tile + warps) * SKB_TILE_WORDS) + lane * 128));
-            else if (lane == 16)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(tile_prefix + tile + warps));
-        }
-        if (total == 0) {  // empty tile: only the rank structure (64 blocks of 256 bits)
-            ((uint2*)(pre256 + tile * 64))[lane] = make_uint2(t0, t0);
-            continue;
-        }
-        uint64_t w[8];
-        w[0] = (uint64_t)q0.x | ((uint64_t)q0.y << 32);
-        w[1] = (uint64_t)q0.z | ((uint64_t)q0.w << 32);
-        w[2] = (uint64_t)q1.x | ((uint64_t)q1.y << 32);
-        w[3] = (uint64_t)q1.z | ((uint64_t)q1.w << 32);
-        w[4] = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
-        w[5] = (uint64_t)q2.z | ((uint64_t)q2.w << 32);
-        w[6] = (uint64_t)q3.x | ((uint64_t)q3.y << 32);
-        w[7] = (uint64_t)q3.z | ((uint64_t)q3.w << 32);
-        // one warp scan for the four groups: 16-bit fields (a group holds at most 4096 set bits)
-        unsigned long long packed = 0;
+    // The kernel is bound by the instructions it issues (ncu, round 2: 71 % issue slots busy, 524 instructions per tile
+    // when every lane picked the set bits out of its own words in divergent loops, 18 % of them branches), and a sparse
+    // tile holds fewer nodes (~14 at 2048^3) than a warp has lanes.  So: the words and their running counts go to
+    // shared memory, TWO tiles per iteration (this one and the one a grid stride further), and then one loop over the
+    // nodes of both, one node per lane -- a lane finds its node's word by binary search in the running counts and the
+    // bit inside the word by clearing lower set bits.  The warp's next pair is pulled into L2 meanwhile.
+    for (; tile < ntiles; tile += 2 * warps) {
+        const int64_t tile_b = tile + warps;
+        const bool has_b = tile_b < ntiles;
+        const uint32_t ta = tile_prefix[tile], na_all = tile_prefix[tile + 1] - ta;
+        const uint32_t tb = has_b ? tile_prefix[tile_b] : 0u, nb_all = has_b ? tile_prefix[tile_b + 1] - tb : 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            packed |= (unsigned long long)(__popcll(w[2 * j]) + __popcll(w[2 * j + 1])) << (16 * j);
-        unsigned long long inc = packed;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            unsigned long long o = __shfl_up_sync(0xffffffffu, inc, s);
-            if (lane >= s) inc += o;
-        }
-        const unsigned long long ex = inc - packed;
-        const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
-        const int64_t r0 = tile * SKB_TILE_VOX;
-        const int64_t z0 = (g.ndim == 3 ? z_origin : 0) + zt;
-        uint32_t base = 0;              // nodes of the tile in groups before j
-        uint32_t idj[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            idj[j] = base + (uint32_t)((ex >> (16 * j)) & 0xffffu);
-            base += (uint32_t)((tot >> (16 * j)) & 0xffffu);
-            // words 2*(32 j + lane), +1: the even lane of each pair starts a 256-bit block
-            if ((lane & 1) == 0) pre256[tile * 64 + j * 16 + (lane >> 1)] = t0 + idj[j];
-        }
-        if (total <= SKB_EMIT_CAP) {
-            // compact the set bits of the tile into shared memory, then one node per lane
-            if (packed) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t off = (uint32_t)(2 * (j * 32 + lane)) * 64u;
-                    uint32_t k = skb_stage_bits(w[2 * j], off, st, idj[j]);
-                    skb_stage_bits(w[2 * j + 1], off + 64u, st, k);
-                }
-            }
-            __syncwarp();
-            for (uint32_t i = lane; i < total; i += 32)
-                if (t0 + i < node_cap) skb_emit_one(st[i], r0, z0, y0, x0, t0 + i, g, img, dtype, lin, coords, values);
-            __syncwarp();
-        } else if (packed) {  // dense tile: every lane walks its own words
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                uint64_t x = w[q];
-                uint32_t id = t0 + idj[q >> 1] + ((q & 1) ? (uint32_t)__popcll(w[q - 1]) : 0u);
-                const uint32_t off = (uint32_t)(2 * ((q >> 1) * 32 + lane) + (q & 1)) * 64u;
-                while (x) {
-                    if (id < node_cap)
-                        skb_emit_one(off + (uint32_t)(__ffsll((long long)x) - 1), r0, z0, y0, x0, id, g, img, dtype, lin,
-                                     coords, values);
-                    ++id;
-                    x &= x - 1;
-                }
+        for (int k = 2; k < 4; ++k) {
+            const int64_t tp = tile + k * warps;
+            if (tp < ntiles) {
+                if (lane < 16)  // 16 lines of 128 bytes
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(bits + tp * SKB_TILE_WORDS) + lane * 128));
+                else if (lane == 16)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(tile_prefix + tp));
             }
         }
+        int32_t zb = za, yb = ya, xb = xa;
+        skb_advance_coords(g, zb, yb, xb, dzt, dy0, dx0);
+        const uint32_t na = skb_rank_tile(tile, ta, na_all, lane, bits, s_words[warp][0], s_incl[warp][0], pre256);
+        const uint32_t nbs = has_b ? skb_rank_tile(tile_b, tb, nb_all, lane, bits, s_words[warp][1], s_incl[warp][1], pre256) : 0u;
+        __syncwarp();
+        for (uint32_t i = lane; i < na + nbs; i += 32) {
+            const int second = i >= na ? 1 : 0;
+            const uint32_t k = second ? i - na : i;  // the tile's k-th set bit
+            const uint16_t* incl = (const uint16_t*)s_incl[warp][second];
+            uint32_t pos = 0;  // first word whose inclusive count exceeds k
+#pragma unroll
+            for (uint32_t step = SKB_TILE_WORDS / 2; step; step >>= 1)
+                if ((uint32_t)incl[pos + step - 1] <= k) pos += step;
+            uint32_t skip = k - (pos ? (uint32_t)incl[pos - 1] : 0u);  // set bits of that word below ours
+            uint64_t word = ((const uint64_t*)s_words[warp][second])[pos];
+            for (; skip; --skip) word &= word - 1;
+            const uint32_t off = pos * 64u + (uint32_t)(__ffsll((long long)word) - 1);
+            const uint32_t id = (second ? tb : ta) + k;
+            if (id < node_cap)
+                skb_emit_one(off, (second ? tile_b : tile) * SKB_TILE_VOX, second ? zb : za, z_add, second ? yb : ya,
+                             second ? xb : xa, id, g, img, dtype, lin, coords, values);
+        }
+        __syncwarp();
+        za = zb;
+        ya = yb;
+        xa = xb;
+        skb_advance_coords(g, za, ya, xa, dzt, dy0, dx0);
     }
 }
 
@@ -1278,15 +1287,15 @@ __global__ void __launch_bounds__(SKB_FUSED_THREADS, 3) skb_sweep_nodes_kernel(
                     if ((int64_t)(excl + i) >= node_cap) break;
                     const uint32_t o = stg[i];
                     const int j = (int)(o >> 14);  // tile of the chunk
-                    skb_emit_one(o & 16383u, (c * 4 + j) * (int64_t)SKB_TILE_VOX,
-                                 (g.ndim == 3 ? z_origin : 0) + s_org[b][j][0], s_org[b][j][1], s_org[b][j][2], excl + i, g,
-                                 img, dtype, lin, coords, values);
+                    skb_emit_one(o & 16383u, (c * 4 + j) * (int64_t)SKB_TILE_VOX, s_org[b][j][0],
+                                 (g.ndim == 3 ? z_origin : 0), s_org[b][j][1], s_org[b][j][2], excl + i, g, img, dtype, lin,
+                                 coords, values);
                 }
             } else {  // dense chunk: every lane walks its own words
                 const int j = lane >> 3;  // tile of the chunk
                 const int64_t r0 = (c * 4 + j) * (int64_t)SKB_TILE_VOX;
-                const int64_t z0 = (g.ndim == 3 ? z_origin : 0) + s_org[b][j][0];
-                const int32_t y0 = s_org[b][j][1], x0 = s_org[b][j][2];
+                const int64_t z_add = (g.ndim == 3 ? z_origin : 0);
+                const int32_t zt = s_org[b][j][0], y0 = s_org[b][j][1], x0 = s_org[b][j][2];
 #pragma unroll 4
                 for (int i = 0; i < 32; ++i) {
                     if ((i & 3) == 0 && (full || (blk0 + (i >> 2)) * 4 < nwords)) pre256[blk0 + (i >> 2)] = id;
@@ -1294,7 +1303,7 @@ __global__ void __launch_bounds__(SKB_FUSED_THREADS, 3) skb_sweep_nodes_kernel(
                     const uint32_t woff = (uint32_t)(((lane & 7) * 32 + i) * 64);
                     while (w) {
                         if ((int64_t)id < node_cap)
-                            skb_emit_one(woff + (uint32_t)(__ffsll((long long)w) - 1), r0, z0, y0, x0, id, g, img, dtype,
+                            skb_emit_one(woff + (uint32_t)(__ffsll((long long)w) - 1), r0, zt, z_add, y0, x0, id, g, img, dtype,
                                          lin, coords, values);
                         ++id;
                         w &= w - 1;
@@ -1531,9 +1540,10 @@ int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_
     if (values && !image) return skb_fail("values requested without an image");
     if (((uintptr_t)bits & 15) != 0) return skb_fail("mask pointer must be 16-byte aligned");
     const uint32_t cap32 = node_cap < 0 ? 0u : node_cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)node_cap;
-    int64_t grid = (ntiles + SKB_EMIT_THREADS / 32 - 1) / (SKB_EMIT_THREADS / 32);
-    int64_t cap = (int64_t)skb_sm_count() * 8;
+    int64_t grid = (ntiles + 2 * SKB_EMIT_WARPS - 1) / (2 * SKB_EMIT_WARPS);  // a warp takes two tiles per iteration
+    int64_t cap = (int64_t)skb_sm_count() * 5;                                // what 41 KB of shared memory per CTA allows
     if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
     if (values)
         skb_emit_nodes_kernel<true><<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
             bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256, cap32);

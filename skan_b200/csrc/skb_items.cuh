@@ -100,19 +100,55 @@ SKB_HD double skb_hypot(double x, double y) {
 
 // ---- geometry ------------------------------------------------------------------------------
 // Every image is embedded as (nz, ny, nx) with leading extents 1 for ndim < 3.
+// exact unsigned 32-bit division by a divisor fixed per launch (Granlund & Montgomery 1994, figure 4.1): a multiply-high,
+// a subtraction and two shifts instead of the ~20 instructions of a hardware-assisted division -- the node emission and
+// the stencil turn a raveled index into coordinates once per foreground voxel
+struct SkbDiv {
+    uint32_t m, s1, s2, d;
+};
+SKB_HD SkbDiv skb_div_make(uint32_t d) {
+    SkbDiv v;
+    uint32_t l = 0;
+    while (l < 32 && ((uint64_t)1 << l) < (uint64_t)d) ++l;  // ceil(log2 d)
+    v.m = (uint32_t)(((((uint64_t)1 << l) - d) << 32) / d + 1);
+    v.s1 = l < 1 ? l : 1;
+    v.s2 = l < 1 ? 0 : l - 1;
+    v.d = d;
+    return v;
+}
+SKB_HD uint32_t skb_udiv(uint32_t n, const SkbDiv& v) {
+    const uint32_t t1 = skb_umulhi(v.m, n);
+    return (t1 + ((n - t1) >> v.s1)) >> v.s2;
+}
+
 struct SkbGeom {
     int64_t nvox;
     int64_t sz;  // ny * nx
     int32_t nz, ny, nx, ndim;
     double inv_sz;  // 1.0 / sz
+    SkbDiv dx, dy;  // division by nx, by ny
 };
+
+SKB_HD SkbGeom skb_geom_make(int ndim, int64_t nz, int64_t ny, int64_t nx) {
+    SkbGeom g;
+    g.nz = (int32_t)nz;
+    g.ny = (int32_t)ny;
+    g.nx = (int32_t)nx;
+    g.ndim = ndim;
+    g.sz = ny * nx;
+    g.inv_sz = 1.0 / (double)g.sz;
+    g.nvox = nz * ny * nx;
+    g.dx = skb_div_make((uint32_t)nx);
+    g.dy = skb_div_make((uint32_t)ny);
+    return g;
+}
 
 SKB_HD void skb_coords(const SkbGeom& g, int64_t r, int32_t& z, int32_t& y, int32_t& x) {
     if (g.nvox <= 0xffffffffLL) {
         uint32_t rr = (uint32_t)r;
-        uint32_t q = rr / (uint32_t)g.nx;
+        uint32_t q = skb_udiv(rr, g.dx);
         x = (int32_t)(rr - q * (uint32_t)g.nx);
-        uint32_t q2 = q / (uint32_t)g.ny;
+        uint32_t q2 = skb_udiv(q, g.dy);
         y = (int32_t)(q - q2 * (uint32_t)g.ny);
         z = (int32_t)q2;
     } else if (g.sz <= 0x7fffffffLL && r >= 0 && r < (1LL << 52)) {
@@ -129,7 +165,7 @@ SKB_HD void skb_coords(const SkbGeom& g, int64_t r, int32_t& z, int32_t& y, int3
             rem -= g.sz;
         }
         uint32_t rr = (uint32_t)rem;
-        uint32_t q = rr / (uint32_t)g.nx;
+        uint32_t q = skb_udiv(rr, g.dx);
         x = (int32_t)(rr - q * (uint32_t)g.nx);
         y = (int32_t)q;
         z = (int32_t)q2;
@@ -245,6 +281,25 @@ SKB_HD void skb_for_neighbors(const SkbGeom& g, const uint64_t* bits, const uint
 }
 
 // ---- stage: raw 3^d neighbourhood mask (csr.py:122-144, evaluated per foreground voxel) ----
+// 27-bit mask of the foreground neighbours of voxel r = (z, y, x) (local coordinates of this volume / slab)
+SKB_HD uint32_t skb_raw_nb_mask(const SkbGeom& g, const uint64_t* bits, int64_t r, int32_t z, int32_t y, int32_t x,
+                                int32_t planes_independent) {
+    uint32_t xm = 7u;
+    if (x == 0) xm &= ~1u;
+    if (x == g.nx - 1) xm &= ~4u;
+    uint32_t m = 0;
+    for (int dz = -1; dz <= 1; ++dz) {
+        if ((uint32_t)(z + dz) >= (uint32_t)g.nz || (planes_independent && dz != 0)) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            if ((uint32_t)(y + dy) >= (uint32_t)g.ny) continue;
+            int64_t rr = r + dz * g.sz + dy * (int64_t)g.nx;
+            uint32_t w = skb_win3(bits, rr - 1) & xm;
+            m |= w << (((dz + 1) * 3 + (dy + 1)) * 3);
+        }
+    }
+    return m & ~(1u << 13);
+}
+
 struct SkbRawNbItem {
     SkbGeom g;
     const uint64_t* bits;
@@ -255,20 +310,7 @@ struct SkbRawNbItem {
         int64_t r = lin[i];
         int32_t z, y, x;
         skb_coords(g, r, z, y, x);
-        uint32_t xm = 7u;
-        if (x == 0) xm &= ~1u;
-        if (x == g.nx - 1) xm &= ~4u;
-        uint32_t m = 0;
-        for (int dz = -1; dz <= 1; ++dz) {
-            if ((uint32_t)(z + dz) >= (uint32_t)g.nz || (planes_independent && dz != 0)) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                if ((uint32_t)(y + dy) >= (uint32_t)g.ny) continue;
-                int64_t rr = r + dz * g.sz + dy * (int64_t)g.nx;
-                uint32_t w = skb_win3(bits, rr - 1) & xm;
-                m |= w << (((dz + 1) * 3 + (dy + 1)) * 3);
-            }
-        }
-        nb[i] = m & ~(1u << 13);
+        nb[i] = skb_raw_nb_mask(g, bits, r, z, y, x, planes_independent);
     }
 };
 

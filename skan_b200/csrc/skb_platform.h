@@ -32,6 +32,7 @@ SKB_HD int skb_popc(uint32_t v) { return __popc(v); }
 SKB_HD int skb_popcll(uint64_t v) { return __popcll(v); }
 SKB_HD int skb_ffs(uint32_t v) { return __ffs((int)v); }
 SKB_HD int skb_ffsll(uint64_t v) { return __ffsll((long long)v); }
+SKB_HD uint32_t skb_umulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 SKB_HD uint64_t skb_atomic_min_u64(uint64_t* p, uint64_t v) {
     return (uint64_t)atomicMin((unsigned long long*)p, (unsigned long long)v);
 }
@@ -67,6 +68,7 @@ SKB_HD int skb_popc(uint32_t v) { return __builtin_popcount(v); }
 SKB_HD int skb_popcll(uint64_t v) { return __builtin_popcountll(v); }
 SKB_HD int skb_ffs(uint32_t v) { return __builtin_ffs((int)v); }
 SKB_HD int skb_ffsll(uint64_t v) { return __builtin_ffsll((long long)v); }
+SKB_HD uint32_t skb_umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 SKB_HD uint64_t skb_atomic_min_u64(uint64_t* p, uint64_t v) {
     uint64_t o = *p;
     if (v < o) *p = v;

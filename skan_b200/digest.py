@@ -39,7 +39,7 @@ def _weights(start, n, salt, device):
 
 def _as_i64(t):
     if not isinstance(t, torch.Tensor):
-        t = torch.from_numpy(np.ascontiguousarray(t))
+        t = torch.from_numpy(np.array(t))   # a copy: SciPy / pandas hand out read-only views
     if t.dtype == torch.float64:
         return t.contiguous().view(torch.int64)
     if t.dtype == torch.bool:
@@ -122,7 +122,7 @@ def _segments_oracle(sk, summary):
         segs.append(('t32', t, row * P))
     for row, t in enumerate(t64):
         segs.append(('t64', t, row * P))
-    fp = {k: torch.from_numpy(np.asarray(col[k], np.float64)) for k in
+    fp = {k: torch.from_numpy(np.array(col[k], dtype=np.float64)) for k in
           ('branch_distance', 'mean_pixel_value', 'stdev_pixel_value', 'euclidean_distance')}
     return segs, fp, dict(nodes=g.shape[0], edges=int(g.nnz), paths=P, entries=int(sk.paths.indices.size))
 

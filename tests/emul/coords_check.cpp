@@ -9,8 +9,7 @@ int main() {
     uint64_t rng = 88172645463325252ull;
     long bad = 0, n = 0;
     for (auto& sh : shapes) {
-        SkbGeom g;
-        g.nz = sh[0]; g.ny = sh[1]; g.nx = sh[2]; g.ndim = 3; g.sz = sh[1] * sh[2]; g.nvox = sh[0] * g.sz; g.inv_sz = 1.0 / (double)g.sz;
+        SkbGeom g = skb_geom_make(3, sh[0], sh[1], sh[2]);
         if (g.nvox <= 0xffffffffLL) { printf("shape too small\n"); continue; }
         for (int t = 0; t < 4000000; ++t) {
             rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
@@ -28,6 +27,28 @@ int main() {
             int64_t q = r / g.nx, ex = r - q * g.nx, q2 = q / g.ny, ey = q - q2 * g.ny;
             if (z != q2 || y != ey || x != ex) ++bad;
             ++n;
+        }
+    }
+    // the invariant division of skb_udiv against the hardware's, for awkward divisors and dividends
+    {
+        const uint32_t ds[] = {1, 2, 3, 5, 7, 10, 255, 256, 257, 1000, 1094, 1536, 2047, 2048, 2049, 46340, 46341, 65535,
+                               65536, 65537, 1000003, 0x7ffffffe, 0x7fffffff, 0x80000000u, 0x80000001u, 0xfffffffeu, 0xffffffffu};
+        for (uint32_t d : ds) {
+            const SkbDiv v = skb_div_make(d);
+            for (int t = 0; t < 400000; ++t) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                uint32_t x;
+                const int mode = t % 6;
+                if (mode == 0) x = (uint32_t)rng;
+                else if (mode == 1) x = (uint32_t)(rng % 70000);
+                else {  // around multiples of d and the top of the range
+                    const uint64_t k = (rng >> 8) % (0x100000000ull / d + 1);
+                    const int64_t c = (int64_t)(k * d) + (int64_t)(t % 5) - 2;
+                    x = (uint32_t)(c < 0 ? 0 : (c > 0xffffffffLL ? 0xffffffffLL - (t % 3) : c));
+                }
+                if (skb_udiv(x, v) != x / d) ++bad;
+                ++n;
+            }
         }
     }
     printf("%ld checked, %ld bad\n", n, bad);
