@@ -143,6 +143,28 @@ int skb_mst_junctions(const int32_t* ea, const int32_t* eb, const uint64_t* ew, 
 #endif
 }
 
+// Junction MST + removal of the dropped edges in one call, for the runners: keep u32[n_local] holds the raw masks of the
+// nodes with ids id_shift .. id_shift + n_local - 1 on entry and the final masks on return.  Table weights (height == 0):
+// packed-key rounds, one cooperative launch, see skb_mst_keys_coop_kernel; scratch best u64[2 * n_ids].  Height mode or
+// the emulation harness: skb_mst_junctions + skb_mst_apply with the same scratch (bestw = best, beste = best + n_ids).
+int skb_mst_apply(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const uint8_t* tree, int64_t nej,
+                  int64_t id_shift, int64_t n_local, uint32_t* keep, void* stream);
+static int skb_mst_junctions_apply(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const uint64_t* ew,
+                                   const double* wtab, int height, int64_t nej, int64_t n_ids, int32_t* par,
+                                   uint64_t* best, int32_t* era, int32_t* erb, uint8_t* tree, int32_t* flag,
+                                   uint32_t* keep, int64_t id_shift, int64_t n_local, void* stream) {
+    if (nej <= 0) return 0;
+#ifdef SKB_HAVE_FUSED_LOOPS
+    if (!height && g_skb_mst_keys)
+        return skb_mst_keys_run(ea, eb, ek, wtab, nej, par, (unsigned long long*)best, n_ids, era, erb, tree, flag, keep,
+                                (int32_t)id_shift, (int32_t)n_local, (skb_stream_t)stream);
+#endif
+    (void)wtab;
+    int r = skb_mst_junctions(ea, eb, ew, nej, n_ids, par, best, (uint32_t*)(best + n_ids), era, erb, tree, flag, stream);
+    if (r < 0) return r;
+    return skb_mst_apply(ea, eb, ek, tree, nej, id_shift, n_local, keep, stream);
+}
+
 // keep[] starts as a copy of nb[]; clear both directions of every non-tree junction edge.
 // keep has n_local entries for the nodes with (global) ids id_shift .. id_shift + n_local - 1.
 int skb_mst_apply(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const uint8_t* tree, int64_t nej,

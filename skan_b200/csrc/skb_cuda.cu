@@ -1385,6 +1385,94 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_coop_kernel(
     if (first) flags[2] = round;
 }
 
+// Junction MST, table weights (every weight is one of the 26 neighbour distances: anything but height mode).  The order
+// (weight, a, b) of an edge is then ONE 64-bit key, (rank of the weight among the table's values) << 32 | edge index
+// (edges are listed in (a, b) order), so a round needs one atomic minimum per end instead of two phases, and the
+// per-component minima are double-buffered by round parity (a round resets the entries the next round will use: the
+// roots of round r+1 are among the roots round r saw), so there is no reset phase either: 2 grid barriers per round
+// instead of 4.  After the last round the same launch clears the dropped junction-junction edges from `keep`
+// (csr.py:1018-1019; keep = the raw masks, updated in place).
+__global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_keys_coop_kernel(
+    const int32_t* ea, const int32_t* eb, const uint8_t* ek, const double* wtab, int64_t nej, int32_t* par,
+    unsigned long long* best /* [2][n_ids] */, int64_t n_ids, int32_t* era, int32_t* erb, uint8_t* tree,
+    int32_t* flags /* [3]: two flags + rounds */, uint32_t* keep, int32_t id_shift, int32_t n_local) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_rank[27];
+    if (threadIdx.x < 27) {  // rank of every table weight among the table's distinct values (positive doubles: bit order)
+        const unsigned long long me = (unsigned long long)__double_as_longlong(wtab[threadIdx.x]);
+        uint32_t r = 0;
+        for (int j = 0; j < 27; ++j) {
+            const unsigned long long o = (unsigned long long)__double_as_longlong(wtab[j]);
+            bool seen = false;
+            for (int i = 0; i < j; ++i) seen |= (unsigned long long)__double_as_longlong(wtab[i]) == o;
+            if (!seen && o < me) ++r;
+        }
+        s_rank[threadIdx.x] = r;
+    }
+    const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long* best0 = best;
+    unsigned long long* best1 = best + n_ids;
+    SKB_GRID_FOR(e, nej) {
+        const int32_t a = ea[e], b = eb[e];
+        tree[e] = 0;
+        if (a < 0) {  // padding row of a gathered edge list: dead from the start
+            era[e] = -2;
+            continue;
+        }
+        era[e] = 0;
+        par[a] = a;
+        par[b] = b;
+        best0[a] = best0[b] = best1[a] = best1[b] = ~0ull;
+    }
+    if (first) flags[0] = flags[1] = 0;
+    __syncthreads();
+    grid.sync();
+    int round = 0;
+    for (; round < 64; ++round) {
+        unsigned long long* cur = (round & 1) ? best1 : best0;
+        unsigned long long* nxt = (round & 1) ? best0 : best1;
+        int32_t* f = flags + (round & 1);
+        SKB_GRID_FOR(e, nej) {
+            if (era[e] == -2) continue;  // already inside one component
+            const int32_t ra = skb_find(par, ea[e]), rb = skb_find(par, eb[e]);
+            if (ra == rb) {
+                era[e] = -2;
+                continue;
+            }
+            era[e] = ra;
+            erb[e] = rb;
+            const unsigned long long key = ((unsigned long long)s_rank[ek[e]] << 32) | (unsigned long long)(uint32_t)e;
+            atomicMin(cur + ra, key);
+            atomicMin(cur + rb, key);
+            nxt[ra] = ~0ull;
+            nxt[rb] = ~0ull;
+            *f = 1;
+        }
+        grid.sync();
+        if (*(volatile int32_t*)f == 0) break;  // same value for every thread of the grid
+        if (first) flags[(round + 1) & 1] = 0;   // last read before the previous barrier, next written after the next one
+        SKB_GRID_FOR(e, nej) {
+            const int32_t ra = era[e];
+            if (ra == -2) continue;
+            const int32_t rb = erb[e];
+            const unsigned long long key = ((unsigned long long)s_rank[ek[e]] << 32) | (unsigned long long)(uint32_t)e;
+            const bool pa = __ldcg(cur + ra) == key, pb = __ldcg(cur + rb) == key;
+            if (!(pa || pb)) continue;
+            tree[e] = 1;
+            // a component's root is written by exactly one edge (its chosen one); a mutual choice keeps the smaller
+            // root so that the two hooks do not form a 2-cycle
+            if (pa && !(pb && ra < rb)) skb_st_cg(par + ra, rb);
+            if (pb && !(pa && rb < ra)) skb_st_cg(par + rb, ra);
+        }
+        grid.sync();
+    }
+    if (first) flags[2] = round;
+    if (keep) {  // every tree flag was written before the barrier that ended the loop
+        SkbMstApplyItem apply{ea, eb, ek, tree, id_shift, n_local, keep};
+        SKB_GRID_FOR(e, nej) apply(e);
+    }
+}
+
 template <typename Jump>
 __device__ __forceinline__ void skb_rank_rounds(cg::grid_group& grid, Jump jump, skb_i4* b0, skb_i4* b1, SkbAux* a0,
                                                 SkbAux* a1, int64_t n, int32_t* flags /* [4]: 3 flags + rounds */) {
@@ -1435,11 +1523,16 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_table_rank_coop_kernel(s
     skb_rank_rounds(grid, jump, b0, b1, a0, a1, n, flags);
 }
 
+// a grid barrier costs more the more CTAs take part: "mst_blocks_per_sm" caps the Boruvka launch (0 = what fits)
+static int g_skb_mst_blocks_per_sm = 0;  // measured: fewer CTAs lose (the rounds are bound by the finds, not the barriers)
+static int g_skb_emit_blocks_per_sm = 16;  // measured at 2048^3: 5 -> 0.314, 8 -> 0.258, 16 -> 0.254 ms (tail balance)
+static int g_skb_mst_keys = 1;  // "mst_keys": 0 = the two-phase rounds also for table weights (A/B)
 template <typename K>
-static int skb_coop_launch(K kernel, int64_t n_items, void** args, skb_stream_t s) {
+static int skb_coop_launch(K kernel, int64_t n_items, void** args, skb_stream_t s, int max_per_sm = 0) {
     int per_sm = 0;
     SKB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SKB_COOP_THREADS, 0));
     if (per_sm < 1) return skb_fail("cooperative kernel does not fit");
+    if (max_per_sm > 0 && per_sm > max_per_sm) per_sm = max_per_sm;
     int64_t cap = (int64_t)per_sm * skb_sm_count();
     int64_t blocks = (n_items + SKB_COOP_THREADS - 1) / SKB_COOP_THREADS;
     if (blocks > cap) blocks = cap;
@@ -1456,6 +1549,13 @@ static int skb_mst_run(const int32_t* ea, const int32_t* eb, const uint64_t* ew,
                        skb_stream_t s) {
     void* args[] = {&ea, &eb, &ew, &nej, &par, &bestw, &beste, &era, &erb, &tree, &flag};
     return skb_coop_launch(skb_mst_coop_kernel, nej, args, s);
+}
+
+static int skb_mst_keys_run(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const double* wtab, int64_t nej,
+                            int32_t* par, unsigned long long* best, int64_t n_ids, int32_t* era, int32_t* erb, uint8_t* tree,
+                            int32_t* flag, uint32_t* keep, int32_t id_shift, int32_t n_local, skb_stream_t s) {
+    void* args[] = {&ea, &eb, &ek, &wtab, &nej, &par, &best, &n_ids, &era, &erb, &tree, &flag, &keep, &id_shift, &n_local};
+    return skb_coop_launch(skb_mst_keys_coop_kernel, nej, args, s, g_skb_mst_blocks_per_sm);
 }
 
 static int skb_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, int32_t lo, int32_t hi,
@@ -1492,6 +1592,20 @@ int skb_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "emit_both_ways")) {
         g_skb_both_ways = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "mst_blocks_per_sm")) {
+        if (value < 0 || value > 32) return skb_fail("skb_set_option: mst_blocks_per_sm must be in 0..32");
+        g_skb_mst_blocks_per_sm = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "emit_blocks_per_sm")) {
+        if (value < 1 || value > 64) return skb_fail("skb_set_option: emit_blocks_per_sm must be in 1..64");
+        g_skb_emit_blocks_per_sm = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "mst_keys")) {
+        g_skb_mst_keys = value ? 1 : 0;
         return 0;
     }
     return skb_fail("skb_set_option: unknown option");
@@ -1541,7 +1655,7 @@ int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_
     if (((uintptr_t)bits & 15) != 0) return skb_fail("mask pointer must be 16-byte aligned");
     const uint32_t cap32 = node_cap < 0 ? 0u : node_cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)node_cap;
     int64_t grid = (ntiles + 2 * SKB_EMIT_WARPS - 1) / (2 * SKB_EMIT_WARPS);  // a warp takes two tiles per iteration
-    int64_t cap = (int64_t)skb_sm_count() * 5;                                // what 41 KB of shared memory per CTA allows
+    int64_t cap = (int64_t)skb_sm_count() * g_skb_emit_blocks_per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     if (values)

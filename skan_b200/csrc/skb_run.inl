@@ -291,19 +291,16 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     uint64_t* ew = nullptr;
     int32_t *mpar = nullptr, *era = nullptr, *erb = nullptr;
     uint64_t* bestw = nullptr;
-    uint32_t* beste = nullptr;
     auto take_junction = [&](int64_t cap) {
         ea = work.take<int32_t>(cap);
         eb = work.take<int32_t>(cap);
         ek = work.take<uint8_t>(cap);
         ew = work.take<uint64_t>(cap);
         mpar = work.take<int32_t>(N);
-        bestw = work.take<uint64_t>(N);
-        beste = work.take<uint32_t>(N);
+        bestw = work.take<uint64_t>(2 * N);
         era = work.take<int32_t>(cap);
         erb = work.take<int32_t>(cap);
         tree = work.take<uint8_t>(cap);
-        keep = work.take<uint32_t>(N);
     };
     {
         const int64_t cap = prm->hint[SKB_H_JUNCTION_EDGES] > 0 ? prm->hint[SKB_H_JUNCTION_EDGES] : 0;
@@ -331,16 +328,12 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         } else if (!nej) {
             work.off = work_mark;
             work.ok = true;
-            keep = nb;
         }
     }
     res->counts[SKB_C_JUNCTION_EDGES] = nej;
-    if (nej) {
-        int r = skb_mst_junctions(ea, eb, ew, nej, N, mpar, bestw, beste, era, erb, tree, flag, s);
-        if (r < 0) return r;
-        SKB_TRY(skb_copy_bytes(keep, nb, (size_t)N * 4, s));
-        SKB_TRY(skb_mst_apply(ea, eb, ek, tree, nej, 0, N, keep, s));
-    }
+    if (nej)  // the dropped junction-junction edges are cleared from the raw masks in place: keep == nb
+        SKB_TRY(skb_mst_junctions_apply(ea, eb, ek, ew, prm->wtab, height, nej, N, mpar, bestw, era, erb, tree, flag, keep, 0,
+                                        N, s));
     SKB_MARK(SKB_M_MST);
     // ---- CSR + node records ------------------------------------------------------------------------------
     int32_t* deg = out.take<int32_t>(N);

@@ -383,6 +383,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     int32_t *gea = nullptr, *geb = nullptr;
     uint64_t* gew = nullptr;
     uint8_t *gek = nullptr, *tree = nullptr;
+    int32_t *mpar = nullptr, *era = nullptr, *erb = nullptr;
+    uint64_t* bestw = nullptr;
     int64_t nej_rows = 0;
     if (max_e) {
         SkbExchange ex;
@@ -397,11 +399,10 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         geb = work.take<int32_t>(nej_rows);
         gew = work.take<uint64_t>(nej_rows);
         gek = work.take<uint8_t>(nej_rows);
-        int32_t* mpar = work.take<int32_t>(N_total);
-        uint64_t* bestw = work.take<uint64_t>(N_total);
-        uint32_t* beste = work.take<uint32_t>(N_total);
-        int32_t* era = work.take<int32_t>(nej_rows);
-        int32_t* erb = work.take<int32_t>(nej_rows);
+        mpar = work.take<int32_t>(N_total);
+        bestw = work.take<uint64_t>(2 * N_total);
+        era = work.take<int32_t>(nej_rows);
+        erb = work.take<int32_t>(nej_rows);
         tree = work.take<uint8_t>(nej_rows);
         SKB_SNEED(work.ok);
         SKB_TRY(skb_fill_bytes(ex.mine(0), 0xff, (size_t)ex.cap * 4, s));  // a < 0 marks the padding rows
@@ -434,20 +435,16 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         int64_t shifts[SKB_MAX_RANKS];
         for (int k = 0; k < world; ++k) shifts[k] = Noff[k] - own0_of[k];
         SKB_TRY(skb_slab_edge_shift(gea, geb, nej_rows, ex.cap, shifts, world, s));
-        int r = skb_mst_junctions(gea, geb, gew, nej_rows, N_total, mpar, bestw, beste, era, erb, tree, flag, s);
-        if (r < 0) return r;
+        // Boruvka on the gathered edges (the same on every rank) and, in the same launch, the dropped edges cleared from
+        // this rank's raw masks in place
+        SKB_TRY(skb_mst_junctions_apply(gea, geb, gek, gew, prm->wtab, 0, nej_rows, N_total, mpar, bestw, era, erb, tree, flag,
+                                        nb, id_shift, Ne, s));
     }
     SKB_HOST_MARK();
     // ---- CSR + node records + start numbering (one pass) ------------------------------------------------------
     int64_t slab[13] = {own0, own1, hl0, hu1, has_lo ? hl0 : 0, has_lo ? f1 : 0, has_hi ? l0 : 0, has_hi ? hu1 : 0,
                         0, 0, 0, 0, ze0 * sz};
     uint32_t* keep = nb;
-    if (nej_rows) {
-        keep = work.take<uint32_t>(Ne);
-        SKB_SNEED(work.ok);
-        SKB_TRY(skb_copy_bytes(keep, nb, (size_t)Ne * 4, s));
-        SKB_TRY(skb_mst_apply(gea, geb, gek, tree, nej_rows, id_shift, Ne, keep, s));
-    }
     int32_t* deg = out.take<int32_t>(Ne);
     int32_t* indptr = out.take<int32_t>(Ne + 1);
     SKB_SNEED(out.ok);
