@@ -1526,6 +1526,7 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_table_rank_coop_kernel(s
 // a grid barrier costs more the more CTAs take part: "mst_blocks_per_sm" caps the Boruvka launch (0 = what fits)
 static int g_skb_mst_blocks_per_sm = 0;  // measured: fewer CTAs lose (the rounds are bound by the finds, not the barriers)
 static int g_skb_emit_blocks_per_sm = 16;  // measured at 2048^3: 5 -> 0.314, 8 -> 0.258, 16 -> 0.254 ms (tail balance)
+static int g_skb_small_cycles = 1;  // "small_cycles": 0 = always the general machinery for junction-free cycles
 static int g_skb_mst_keys = 1;  // "mst_keys": 0 = the two-phase rounds also for table weights (A/B)
 template <typename K>
 static int skb_coop_launch(K kernel, int64_t n_items, void** args, skb_stream_t s, int max_per_sm = 0) {
@@ -1570,6 +1571,256 @@ static int skb_table_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, in
     return skb_coop_launch(skb_table_rank_coop_kernel, n, args, s);
 }
 
+// ------------------------------------------------------------------------------- junction-free cycles, small case
+// Junction-free cycles (csr.py:369-386) are rare and short in real skeletons: a few thousand voxels on rings of 4-20.
+// The general machinery (sampled list ranking all over again: ~17 launches, several of them passes over all N nodes,
+// 0.10-0.15 ms whatever the volume) is kept for large cases; up to SKB_SMALL_CYCLE_NODES uncovered chain voxels are
+// handled by ONE thread block in shared memory: sort the voxels, link neighbours, label rings by their minimum
+// (union by minimum), rank the ring minima (= path order), walk each ring once in shared memory for the positions,
+// then write all entries in parallel.  `list` holds the uncovered degree-2 nodes in any order (skb_foreach_unmarked +
+// an atomic counter).
+#define SKB_SMALL_CYCLE_NODES 4096
+#define SKB_SMALL_CYCLE_THREADS 1024
+
+struct SkbCollectUncoveredItem {  // over nodes that are not covered: chain voxels go to the list
+    const skb_i4* rec;
+    const uint8_t* covered;
+    int32_t* list;
+    int32_t* counter;
+    int32_t cap;
+    __device__ void operator()(int64_t v) const {
+        if (covered[v]) return;
+        if ((skb_ld_i4(rec + 2 * v).w & SKB_REC_DEG_MASK) != 2) return;
+        const int32_t k = atomicAdd(counter, 1);
+        if (k < cap) list[k] = (int32_t)v;
+    }
+};
+
+struct SkbSmallCycleSmem {
+    int32_t u[SKB_SMALL_CYCLE_NODES];     // node ids, ascending after the sort
+    int32_t par[SKB_SMALL_CYCLE_NODES];   // union by minimum, then the ring's minimum (local index) of every voxel
+    int32_t cnt[SKB_SMALL_CYCLE_NODES];   // per ring minimum: voxels on the ring
+    int32_t base[SKB_SMALL_CYCLE_NODES];  // per ring minimum: entry offset of the ring's path
+    uint16_t l0[SKB_SMALL_CYCLE_NODES], l1[SKB_SMALL_CYCLE_NODES];  // local indices of the two neighbours
+    uint16_t pos[SKB_SMALL_CYCLE_NODES];  // position on the path (the minimum is entry 0 and the closing entry)
+    uint8_t dir[SKB_SMALL_CYCLE_NODES];   // which neighbour precedes the voxel on the path (0: n0, 1: n1)
+    uint32_t warp_a[32], warp_b[32];
+    int32_t bad;
+};
+
+__device__ __forceinline__ int32_t skb_smem_find(int32_t* par, int32_t v) {
+    int32_t p = *(volatile int32_t*)(par + v);
+    while (p != v) {
+        int32_t gp = *(volatile int32_t*)(par + p);
+        if (gp != p) *(volatile int32_t*)(par + v) = gp;
+        v = p;
+        p = gp;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kernel(
+    const int32_t* __restrict__ list, const int32_t* __restrict__ counter, int32_t m, const skb_i4* __restrict__ rec,
+    const double* __restrict__ values, int32_t n_regular, int32_t* __restrict__ start_node, uint32_t* __restrict__ plen,
+    int32_t* __restrict__ pmin, int32_t* __restrict__ pindptr, int32_t* __restrict__ pidx, double* __restrict__ pdata,
+    double* __restrict__ pw, uint32_t* __restrict__ is_min, int32_t* __restrict__ out /* [0] cycles, [1] entries, [2] error */) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    SkbSmallCycleSmem& S = *(SkbSmallCycleSmem*)smem_raw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int n2 = 32;
+    while (n2 < m) n2 <<= 1;
+    if (tid == 0) S.bad = (*counter != m) ? 1 : 0;
+    for (int i = tid; i < n2; i += SKB_SMALL_CYCLE_THREADS) S.u[i] = i < m ? list[i] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < n2; t += SKB_SMALL_CYCLE_THREADS) {
+                const int x = t ^ j;
+                if (x > t) {
+                    const int32_t a = S.u[t], b = S.u[x];
+                    if ((a > b) == ((t & k) == 0)) {
+                        S.u[t] = b;
+                        S.u[x] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // neighbours as local indices
+    for (int i = tid; i < m; i += SKB_SMALL_CYCLE_THREADS) {
+        const skb_i4 r = skb_ld_i4(rec + 2 * (int64_t)S.u[i]);
+        int32_t loc[2];
+        const int32_t nbr[2] = {r.x, r.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int lo = 0, hi = m;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (S.u[mid] < nbr[h]) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo >= m || S.u[lo] != nbr[h]) {  // a neighbour that is not an uncovered chain voxel: not a ring
+                S.bad = 1;
+                lo = i;
+            }
+            loc[h] = lo;
+        }
+        S.l0[i] = (uint16_t)loc[0];
+        S.l1[i] = (uint16_t)loc[1];
+        S.par[i] = i;
+        S.cnt[i] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += SKB_SMALL_CYCLE_THREADS) {  // union by minimum: the root is the ring's minimum
+        const int32_t nbr[2] = {S.l0[i], S.l1[i]};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (nbr[h] >= i) continue;
+            int32_t a = i, b = nbr[h];
+            for (;;) {
+                a = skb_smem_find(S.par, a);
+                b = skb_smem_find(S.par, b);
+                if (a == b) break;
+                if (a < b) {
+                    const int32_t t = a;
+                    a = b;
+                    b = t;
+                }
+                if (atomicCAS(S.par + a, a, b) == a) break;
+            }
+        }
+    }
+    __syncthreads();
+    int32_t root_of[SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS];
+#pragma unroll
+    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
+        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+        root_of[q] = i < m ? skb_smem_find(S.par, i) : -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
+        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+        if (i < m) {
+            S.par[i] = root_of[q];
+            atomicAdd(S.cnt + root_of[q], 1);
+        }
+    }
+    __syncthreads();
+    // rank of every ring minimum among the minima (path order), and the entry offsets: one block scan of two sums
+    uint32_t na = 0, nb = 0;  // rings, entries in this thread's four voxels
+    uint32_t ra[SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS], rb[SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS];
+#pragma unroll
+    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
+        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+        ra[q] = na;
+        rb[q] = nb;
+        if (i < m && root_of[q] == i) {
+            na += 1u;
+            nb += (uint32_t)S.cnt[i] + 1u;
+        }
+    }
+    uint32_t ia = na, ib = nb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oa = __shfl_up_sync(0xffffffffu, ia, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= d) {
+            ia += oa;
+            ib += ob;
+        }
+    }
+    if (lane == 31) {
+        S.warp_a[warp] = ia;
+        S.warp_b[warp] = ib;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t wa = S.warp_a[lane], wb = S.warp_b[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t oa = __shfl_up_sync(0xffffffffu, wa, d), ob = __shfl_up_sync(0xffffffffu, wb, d);
+            if (lane >= d) {
+                wa += oa;
+                wb += ob;
+            }
+        }
+        S.warp_a[lane] = wa;
+        S.warp_b[lane] = wb;
+    }
+    __syncthreads();
+    const uint32_t ea = ia - na + (warp ? S.warp_a[warp - 1] : 0u), eb = ib - nb + (warp ? S.warp_b[warp - 1] : 0u);
+    const uint32_t n_cycles = S.warp_a[31], n_entries = S.warp_b[31];
+    const int32_t l_reg = pindptr[n_regular];  // entries of the regular paths (0 when there are none: the caller sets it)
+#pragma unroll
+    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
+        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+        if (i < m && root_of[q] == i) {
+            const int32_t pid = n_regular + (int32_t)(ea + ra[q]);
+            const int32_t off = l_reg + (int32_t)(eb + rb[q]);
+            start_node[pid] = S.u[i];
+            pmin[pid] = S.u[i];
+            plen[pid] = (uint32_t)S.cnt[i] + 1u;
+            pindptr[pid] = off;
+            is_min[S.u[i]] = 1u;  // a junction-free cycle is a component of its own (csr.py:909)
+            S.base[i] = off;
+            // the walk: from the minimum towards its smaller neighbour (csr.py:369-386), positions in shared memory only
+            int32_t prev = i, cur = S.l0[i] < S.l1[i] ? S.l0[i] : S.l1[i];
+            S.pos[i] = 0;
+            int32_t k = 1;
+            while (cur != i && k <= m) {
+                S.pos[cur] = (uint16_t)k;
+                const int32_t c0 = S.l0[cur], c1 = S.l1[cur];
+                const bool from0 = c0 == prev;
+                S.dir[cur] = from0 ? 0 : 1;
+                prev = cur;
+                cur = from0 ? c1 : c0;
+                ++k;
+            }
+            S.dir[i] = S.l0[i] == prev ? 0 : 1;  // the closing entry arrives from the last voxel
+            if (k != S.cnt[i]) S.bad = 1;
+        }
+    }
+    if (tid == 0) pindptr[n_regular + (int32_t)n_cycles] = l_reg + (int32_t)n_entries;
+    __syncthreads();
+    for (int i = tid; i < m; i += SKB_SMALL_CYCLE_THREADS) {
+        const int32_t r = S.par[i], node = S.u[i];
+        const skb_d2 w = skb_ld_d2(rec + 2 * (int64_t)node + 1);
+        const double w_in = S.dir[i] ? w.y : w.x;
+        const double val = values ? values[node] : 1.0;
+        const int64_t at = (int64_t)S.base[r] + S.pos[i];
+        pidx[at] = node;
+        if (pdata) pdata[at] = val;
+        pw[at] = r == i ? 0.0 : w_in;
+        if (r == i) {  // the ring closes on its minimum
+            const int64_t end = (int64_t)S.base[r] + S.cnt[r];
+            pidx[end] = node;
+            if (pdata) pdata[end] = val;
+            pw[end] = w_in;
+        }
+    }
+    if (tid == 0) {
+        out[0] = (int32_t)n_cycles;
+        out[1] = (int32_t)n_entries;
+        out[2] = S.bad;
+    }
+}
+
+// list i32[m], out i32[4] (device).  Returns 0, or 1 when the case is not a small one (the caller runs the general path).
+static int skb_cycles_small(const skb_i4* rec, const uint8_t* covered, int64_t n, int64_t m, const double* values,
+                            int64_t n_regular, int32_t* start_node, uint32_t* plen, int32_t* pmin, int32_t* pindptr,
+                            int32_t* pidx, double* pdata, double* pw, uint32_t* is_min, int32_t* list, int32_t* out,
+                            skb_stream_t s) {
+    if (m <= 0 || m > SKB_SMALL_CYCLE_NODES || !g_skb_small_cycles) return 1;
+    static uint8_t attr_set[SKB_MAX_DEV] = {};
+    SKB_TRY(skb_optin_smem(skb_small_cycles_kernel, sizeof(SkbSmallCycleSmem), attr_set));
+    SKB_TRY(skb_fill_bytes(out, 0, 16, s));
+    SKB_TRY(skb_foreach_unmarked(n, covered, s, SkbCollectUncoveredItem{rec, covered, list, out + 3, (int32_t)m}));
+    skb_small_cycles_kernel<<<1, SKB_SMALL_CYCLE_THREADS, sizeof(SkbSmallCycleSmem), s>>>(
+        list, out + 3, (int32_t)m, rec, values, (int32_t)n_regular, start_node, plen, pmin, pindptr, pidx, pdata, pw, is_min, out);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "small cycles launch");
+}
+
 #include "skb_api.inl"
 
 extern "C" {
@@ -1602,6 +1853,10 @@ int skb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "emit_blocks_per_sm")) {
         if (value < 1 || value > 64) return skb_fail("skb_set_option: emit_blocks_per_sm must be in 1..64");
         g_skb_emit_blocks_per_sm = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "small_cycles")) {
+        g_skb_small_cycles = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "mst_keys")) {

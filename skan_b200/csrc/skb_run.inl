@@ -532,7 +532,26 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     int64_t n_uncovered = E / 2 - (L_reg - n_regular);
     if (n_uncovered < 0) n_uncovered = 0;
     SKB_MARK(SKB_M_EMIT);
+    bool cycles_done = false;
     if (n_uncovered > 0) {
+        // few uncovered chain voxels (the usual case: short rings): one thread block does the whole phase
+        int32_t* list = work.take<int32_t>(n_uncovered);
+        SKB_NEED(work.ok);
+        if (!n_regular) SKB_TRY(skb_fill_bytes(pindptr, 0, 4, s));
+        int r = skb_cycles_small(rec, covered, N, n_uncovered, values, n_regular, start_node, plen, pmin, pindptr, pidx,
+                                 pdata_w, pw, is_min, list, flag, s);
+        if (r < 0) return r;
+        if (r == 0) {
+            const int32_t* ptrs[2] = {flag, flag + 2};
+            int64_t got[2];
+            SKB_TRY(skb_fetch_i32s(ptrs, 2, got, s));
+            ++nsync;
+            if (got[1] != 0) return skb_fail("junction-free cycles: the uncovered chain voxels do not form closed rings");
+            n_cycles = got[0];
+            cycles_done = true;
+        }
+    }
+    if (n_uncovered > 0 && !cycles_done) {
         int32_t* cpar = work.take<int32_t>(N);
         uint32_t* startoff_b = work.take<uint32_t>(N + 1);
         SKB_NEED(work.ok);

@@ -146,6 +146,11 @@ static int g_skb_split_bits = 4;
 static uint32_t skb_option_split_shift() { return 32u - (uint32_t)g_skb_split_bits; }
 static int g_skb_both_ways = 1;
 static int skb_option_both_ways() { return g_skb_both_ways; }
+// the single-block handling of small junction-free cycles is a CUDA kernel: the harness always runs the general path
+static int skb_cycles_small(const skb_i4*, const uint8_t*, int64_t, int64_t, const double*, int64_t, int32_t*, uint32_t*,
+                            int32_t*, int32_t*, int32_t*, double*, double*, uint32_t*, int32_t*, int32_t*, skb_stream_t) {
+    return 1;
+}
 #include "skb_api.inl"
 
 static bool skb_host_nonzero(const void* img, int dt, int64_t r) {

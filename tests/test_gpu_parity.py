@@ -275,3 +275,28 @@ def test_image_on_a_device_that_is_not_current():
             assert len(df) == ref.n_paths
     finally:
         torch.cuda.set_device(prev)
+
+
+@pytest.mark.parametrize('small', [0, 1])
+def test_junction_free_cycles_small_and_general_path(small):
+    """Up to 4096 uncovered chain voxels are handled by one thread block in shared memory (skb_small_cycles_kernel),
+    more by the general list-ranking machinery; both must reproduce the reference's rings, order and entries."""
+    from skan_b200 import _native
+    lib = _native.library()
+    rng = np.random.default_rng(3)
+    try:
+        lib.call('skb_set_option', b'small_cycles', small)
+        for kind, n in (('ring', 65), ('ring', 257), ('nested_rings', 97), ('nested_rings', 385), ('ring_with_tail', 129)):
+            compare_with_oracle(long_chain_image(kind, n), 1)
+        img = walks((300, 400), 60, 200, seed=4, isolated=10, rings=120)
+        compare_with_oracle(img, (2.0, 0.5))
+        compare_with_oracle((img * (rng.random(img.shape) + 0.5)).astype(np.float32), 1)
+        only_rings = np.zeros((64, 64), bool)          # no regular path at all: rings and isolated pixels
+        for c in range(6, 60, 12):
+            only_rings[c - 1, c] = only_rings[c, c - 1] = only_rings[c, c + 1] = only_rings[c + 1, c] = True
+        only_rings[2, 60] = True
+        compare_with_oracle(only_rings, 1)
+        vol = walks((48, 64, 80), 30, 100, seed=8, isolated=5, rings=40)
+        compare_with_oracle(vol, (0.5, 0.1, 0.1))
+    finally:
+        lib.call('skb_set_option', b'small_cycles', 1)
