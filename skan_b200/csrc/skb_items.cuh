@@ -1318,6 +1318,19 @@ struct SkbTilePrefixItem {  // tile_prefix[t] = nodes before tile t, read back f
     SKB_HD void operator()(int64_t t) const { tile_prefix[t] = t < ntiles ? pre256[t * 64] : (uint32_t)*n_nodes; }
 };
 
+struct SkbTileCountItem {  // over tiles tile0 .. : count[t] = set bits of the tile's 256 mask words (halo planes that arrived)
+    const uint64_t* bits;
+    uint32_t* count;
+    int64_t tile0;
+    SKB_HD void operator()(int64_t i) const {
+        const int64_t t = tile0 + i;
+        const uint64_t* w = bits + t * 256;
+        uint32_t c = 0;
+        for (int k = 0; k < 256; ++k) c += (uint32_t)skb_popcll(w[k]);
+        count[t] = c;
+    }
+};
+
 struct SkbIotaItem {
     int32_t* par;
     SKB_HD void operator()(int64_t v) const { par[v] = (int32_t)v; }

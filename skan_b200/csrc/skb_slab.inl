@@ -31,6 +31,8 @@ struct SkbComm {
     int64_t seq;
     void* xbase[SKB_MAX_RANKS];  // every rank's exchange arena as seen from this process
     int64_t xbytes;
+    int64_t epoch;   // calls of skb_run_slab so far: consecutive calls use alternate halves of the exchange arena, so a
+    int64_t xlimit;  // region is rewritten only after a whole intervening call (whose barriers every reader has passed)
 };
 
 static double skb_now_s() {
@@ -82,7 +84,9 @@ int skb_comm_create(int rank, int world, const char* name, int64_t exchange_byte
     c->world = world;
     snprintf(c->name, sizeof(c->name), "%s", name);
     c->seq = 0;
-    c->xbytes = (exchange_bytes + 4095) & ~(int64_t)4095;
+    c->epoch = 0;
+    c->xbytes = (exchange_bytes + 8191) & ~(int64_t)8191;
+    c->xlimit = c->xbytes;
     for (int k = 0; k < SKB_MAX_RANKS; ++k) c->xbase[k] = nullptr;
     char shm[64];
     snprintf(shm, sizeof(shm), "/skbc_%s", name);
@@ -137,6 +141,7 @@ int skb_comm_destroy(void* comm) {
 int skb_comm_reset(void* comm) {
     SkbComm* c = (SkbComm*)comm;
     c->seq = 0;
+    c->epoch = 0;
     for (int b = 0; b < 2; ++b) {
         int64_t* row = skb_comm_table(c, b) + (int64_t)c->rank * (1 + SKB_COMM_MAXV);
         for (int i = 0; i <= SKB_COMM_MAXV; ++i) row[i] = 0;
@@ -177,7 +182,7 @@ struct skb_slab_params {
     const double* wtab;     // device, 27 weights
     double spacing_f[3];
     int64_t spacing_i[3];
-    int32_t spacing_is_int, reserved;
+    int32_t spacing_is_int, halo_exchange;
     void* work;
     int64_t work_bytes;
     void* out;
@@ -232,7 +237,7 @@ struct SkbExchange {
         chunk = o;
         base = (*xoff + 255) & ~(int64_t)255;
         *xoff = base + chunk;
-        ok = *xoff <= comm->xbytes;
+        ok = *xoff <= comm->xlimit;
     }
     void* field(int f, int k) const { return (uint8_t*)c->xbase[k] + base + foff[f]; }
     void* mine(int f) const { return field(f, c->rank); }
@@ -259,6 +264,13 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         return skb_fail("bad slab bounds (each rank needs at least two owned planes)");
     const bool has_lo = z0 > 0, has_hi = z1 < NZ;
     if ((has_lo && z0 - ze0 < 2) || (has_hi && ze1 - z1 < 2)) return skb_fail("slab mode needs a halo of at least 2 planes");
+    const bool xhalo = prm->halo_exchange == 1;  // halo exchange: the image holds the owned planes [z0, z1) only
+    if (xhalo) {
+        if (ze0 != (has_lo ? z0 - 2 : z0) || ze1 != (has_hi ? z1 + 2 : z1))
+            return skb_fail("halo exchange: the extended slab is the owned planes plus two planes towards every neighbour");
+        if ((NY * NX) % SKB_TILE_VOX) return skb_fail("halo exchange needs planes of a multiple of 16384 voxels (pass the halo planes with the slab otherwise)");
+        if (prm->want_values) return skb_fail("halo exchange is implemented for boolean volumes (pass the halo planes with the slab for valued images)");
+    }
     const int64_t shape[3] = {prm->nz_ext, NY, NX};
     SKB_TRY(skb_check_geom(3, shape));
     SkbGeom g = skb_make_geom(3, shape);
@@ -279,7 +291,12 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     work.init(prm->work, prm->work_bytes);
     out.init(prm->out, prm->out_bytes);
     auto out_off = [&](const void* p) -> int64_t { return p ? (int64_t)((const uint8_t*)p - out.base) : -1; };
-    int64_t xoff = 0;  // bump pointer into the exchange arena, the same on every rank
+    // bump pointer into the exchange arena, the same on every rank; this call's half of the arena
+    const int64_t xhalf = comm->xbytes / 2;
+    int64_t xoff = (comm->epoch & 1) ? xhalf : 0;
+    const int64_t xoff0 = xoff;
+    comm->xlimit = xoff + xhalf;
+    ++comm->epoch;
     int64_t vals[SKB_MAX_FETCH];
     int64_t all[SKB_MAX_RANKS * SKB_COMM_MAXV];
     const int variant = prm->pack_variant == 0 ? 0 : 1;
@@ -300,9 +317,57 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     SKB_TRY(skb_fill_bytes(store + SKB_MASK_PAD + ntiles * SKB_TILE_WORDS, 0, 16, s));
     SKB_TRY(skb_fill_bytes(scratch, 0, (size_t)skb_scan_scratch_bytes(ntiles + 1), s));
     void* ev = nullptr;
-    if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
-    SKB_TRY(skb_pack_count(prm->image, prm->dtype, V, bits, tile_prefix, ntiles, variant, s));
-    if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
+    if (!xhalo) {
+        if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
+        SKB_TRY(skb_pack_count(prm->image, prm->dtype, V, bits, tile_prefix, ntiles, variant, s));
+        if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
+    } else {
+        // Halo exchange: the image holds the owned planes only.  They are swept into
+        // their place in the extended mask; every rank parks the packed mask of its first and last two owned planes
+        // in its exchange arena, and after the barrier reads its neighbours' planes from theirs over NVLink (2 planes
+        // of 1 bit per voxel per face: 1 MB at 2048^2); the halo tiles are counted from the bits that arrived.
+        const int64_t lo_planes = z0 - ze0, hi_planes = ze1 - z1, own_planes = z1 - z0;
+        const int64_t face_bytes = 2 * sz / 8;  // two planes of mask
+        const int64_t tile_lo = lo_planes * sz / SKB_TILE_VOX, tile_own = own_planes * sz / SKB_TILE_VOX;
+        uint64_t* own_bits = bits + lo_planes * sz / 64;
+        if (prm->time_sweep) SKB_TRY(skb_timer_start(&ev, s));
+        SKB_TRY(skb_pack_count(prm->image, prm->dtype, own_planes * sz, own_bits, tile_prefix + tile_lo, tile_own, variant, s));
+        if (prm->time_sweep) SKB_TRY(skb_timer_stop(ev, s));
+        SkbExchange exh;
+        const int64_t rbh[2] = {1, 1};
+        exh.init(comm, &xoff, face_bytes, 2, rbh);
+        if (!exh.ok) {
+            res->exchange_need = 8 * (xoff - xoff0) + (1 << 23);
+            return SKB_RUN_NEED_EXCHANGE;
+        }
+        SKB_TRY(skb_copy_bytes(exh.mine(0), own_bits, (size_t)face_bytes, s));
+        SKB_TRY(skb_copy_bytes(exh.mine(1), own_bits + (own_planes - 2) * sz / 64, (size_t)face_bytes, s));
+        SKB_TRY(skb_stream_sync(s));
+        ++nsync;
+        {
+            const int64_t one = 1;
+            SKB_TRY(skb_comm_allgather(comm, &one, 1, all));
+            ++nexch;
+        }
+        int64_t desc[1 + 3 * 2];
+        int n = 0;
+        if (has_lo) {  // the last two planes of the rank below
+            desc[1 + 3 * n] = (int64_t)(uintptr_t)exh.field(1, rank - 1);
+            desc[2 + 3 * n] = (int64_t)(uintptr_t)bits;
+            desc[3 + 3 * n] = face_bytes;
+            ++n;
+        }
+        if (has_hi) {  // the first two planes of the rank above
+            desc[1 + 3 * n] = (int64_t)(uintptr_t)exh.field(0, rank + 1);
+            desc[2 + 3 * n] = (int64_t)(uintptr_t)(own_bits + own_planes * sz / 64);
+            desc[3 + 3 * n] = face_bytes;
+            ++n;
+        }
+        desc[0] = n;
+        if (n) SKB_TRY(skb_copy_segments(desc, s));
+        if (has_lo) SKB_TRY(skb_foreach(tile_lo, s, SkbTileCountItem{bits, tile_prefix, 0}));
+        if (has_hi) SKB_TRY(skb_foreach(hi_planes * sz / SKB_TILE_VOX, s, SkbTileCountItem{bits, tile_prefix, tile_lo + tile_own}));
+    }
     SKB_TRY(skb_scan_u32_impl(tile_prefix, tile_prefix, ntiles, scratch, s));
     // node ranks of the plane boundaries: owned range, first / last owned plane, the halo planes next to them
     const int64_t p_own0 = (z0 - ze0) * sz, p_own1 = (z1 - ze0) * sz;
@@ -391,7 +456,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         const int64_t rb[4] = {4, 4, 8, 1};
         ex.init(comm, &xoff, max_e, 4, rb);
         if (!ex.ok) {
-            res->exchange_need = 4 * xoff + (1 << 22);
+            res->exchange_need = 8 * (xoff - xoff0) + (1 << 23);
             return SKB_RUN_NEED_EXCHANGE;
         }
         nej_rows = world * ex.cap;
@@ -530,7 +595,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         const int64_t rb[2] = {16, (int64_t)sizeof(SkbAux)};
         ex.init(comm, &xoff, max_blk, 2, rb);
         if (!ex.ok) {
-            res->exchange_need = 4 * xoff + (1 << 22);
+            res->exchange_need = 8 * (xoff - xoff0) + (1 << 23);
             return SKB_RUN_NEED_EXCHANGE;
         }
         const int64_t n_table = world * ex.cap;
@@ -632,7 +697,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         const int64_t rbq[1] = {(int64_t)sizeof(SkbRingRec)};
         exq.init(comm, &xoff, max_unc, 1, rbq);
         if (!exq.ok) {
-            res->exchange_need = 4 * xoff + (1 << 22);
+            res->exchange_need = 8 * (xoff - xoff0) + (1 << 23);
             return SKB_RUN_NEED_EXCHANGE;
         }
         uint32_t* rflag = work.take<uint32_t>(Ne + 1);
@@ -804,7 +869,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         exs.init(comm, &xoff, world * exr.cap, 1, rb);
     }
     if (!exr.ok || !exs.ok) {
-        res->exchange_need = 4 * xoff + (1 << 22);
+        res->exchange_need = 8 * (xoff - xoff0) + (1 << 23);
         return SKB_RUN_NEED_EXCHANGE;
     }
     const int64_t nrec = world * exr.cap;

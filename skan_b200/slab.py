@@ -240,7 +240,7 @@ def _close_comm(key):
             pass
 
 
-def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, group, pack_variant):
+def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, group, pack_variant, halo_exchange=False):
     """skeleton_and_summary_slab through skb_run_slab: the whole per-rank sequence in one native call."""
     import ctypes
     from . import _native
@@ -264,9 +264,13 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         prm.spacing_f[i] = float(sp[i])
         prm.spacing_i[i] = int(sp[i]) if sp_is_int else 1
     prm.z0, prm.z1, prm.ze0, prm.nz_ext = int(z0), int(z1), int(ze0), int(shape[0])
+    if halo_exchange:   # the image holds the owned planes only: the extended slab adds two planes towards every neighbour
+        prm.halo_exchange = 1
+        prm.ze0 = int(z0) - (2 if z0 > 0 else 0)
+        prm.nz_ext = (int(z1) + (2 if z1 < int(global_shape[0]) else 0)) - prm.ze0
     prm.want_values, prm.time_sweep = int(not is_bool), int(bool(TIME_SWEEP))
     prm.wtab, prm.spacing_is_int, prm.stream = _wtabs[wkey].data_ptr(), int(sp_is_int), ctx.stream
-    V = int(np.prod(shape, dtype=np.int64))
+    V = int(prm.nz_ext) * int(shape[1]) * int(shape[2])
     akey = (str(ctx.device), ctx.stream, id(ctx.lib))
     cache = _arenas.setdefault(akey, dict(work=None, out_bytes=_INITIAL_ARENAS[1]))
     if cache['work'] is None:
@@ -349,12 +353,16 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         table_rounds=0, n_starts=C['starts'], n_table=C['table_records'], counts=C)
 
 
-def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=1, device=None, group=None,
-                              pack_variant=None):
+def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spacing=1, device=None, group=None,
+                              pack_variant=None, halo='input'):
     """Skeleton + summarize of one Z-slab of a 3-D volume, collectively over the process group.
 
-    slab_image: planes [ze0, ze0 + slab_image.shape[0]) of the volume (owned planes [z0, z1) plus
-    the halo).  Returns a namespace with this rank's share of the results (device tensors):
+    halo='input' (default): slab_image = planes [ze0, ze0 + slab_image.shape[0]) of the volume (owned planes
+    [z0, z1) plus at least two halo planes towards every neighbour): the caller partitions with overlap.
+    halo='exchange': slab_image = the owned planes [z0, z1) only, a disjoint partition of the volume; the ranks
+    exchange the packed mask of their two boundary planes through the peer-mapped exchange arenas (NVLink),
+    1 bit per voxel (boolean volumes whose planes are a multiple of 16384 voxels; native runner only).
+    Returns a namespace with this rank's share of the results (device tensors):
     graph rows of the owned nodes with global column ids, global path arrays holding the entries
     of this rank's voxels, and the branch table of the paths whose first node is owned here.
     """
@@ -363,6 +371,24 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0, spacing=
     NZ, NY, NX = (int(x) for x in global_shape)
     if len(slab_image.shape) != 3:
         raise ValueError('slab mode is for 3-D volumes')
+    if halo not in ('input', 'exchange'):
+        raise ValueError("halo must be 'input' or 'exchange'")
+    if halo == 'exchange':
+        if int(slab_image.shape[0]) != z1 - z0:
+            raise ValueError("halo='exchange' takes the owned planes [z0, z1) only")
+        if not (NATIVE and _single_node(group) and world <= 16):
+            raise NotImplementedError("halo='exchange' needs the native runner (all ranks on one node)")
+        if z1 - z0 < 2:
+            raise ValueError('bad slab bounds (each rank needs at least two owned planes)')
+        if device is None:
+            device = slab_image.device if isinstance(slab_image, torch.Tensor) and slab_image.device.type == 'cuda' else None
+        if device is None:
+            from .csr import _default_device
+            device = _default_device()
+        return _slab_native(slab_image, global_shape=global_shape, z0=z0, z1=z1, ze0=z0, spacing=spacing, device=device,
+                            group=group, pack_variant=pack_variant, halo_exchange=True)
+    if ze0 is None:
+        raise ValueError("halo='input' needs ze0, the first plane of slab_image")
     ze1 = ze0 + int(slab_image.shape[0])
     if not (0 <= ze0 <= z0 < z1 <= ze1 <= NZ) or z1 - z0 < 2:
         raise ValueError('bad slab bounds (each rank needs at least two owned planes)')

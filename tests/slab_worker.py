@@ -102,7 +102,7 @@ def compare_with_oracle(img, spacing, glob):
     return ref
 
 
-def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate, native=1, small=0):
+def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate, native=1, small=0, xhalo=0):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group(backend, rank=rank, world_size=world)
     try:
@@ -116,7 +116,7 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             rng = np.random.default_rng(seed + 1)
             img = (img * (rng.random(shape) + 0.5)).astype(np.float32)
         z0, z1, ze0, ze1 = slab.slab_bounds(shape[0], world, rank, halo)
-        part = np.ascontiguousarray(img[ze0:ze1])
+        part = np.ascontiguousarray(img[z0:z1] if xhalo else img[ze0:ze1])
         if emulate:
             from emul_util import emulated_device
             cm = emulated_device()
@@ -127,8 +127,12 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             torch.cuda.set_device(rank % torch.cuda.device_count())
             dev = torch.device('cuda', rank % torch.cuda.device_count())
         with cm:
-            res = slab.skeleton_and_summary_slab(torch.from_numpy(part).to(dev), global_shape=shape, z0=z0, z1=z1,
-                                                 ze0=ze0, spacing=spacing, device=dev)
+            if xhalo:   # disjoint partition: the ranks exchange the packed mask of their boundary planes
+                res = slab.skeleton_and_summary_slab(torch.from_numpy(part).to(dev), global_shape=shape, z0=z0, z1=z1,
+                                                     spacing=spacing, device=dev, halo='exchange')
+            else:
+                res = slab.skeleton_and_summary_slab(torch.from_numpy(part).to(dev), global_shape=shape, z0=z0, z1=z1,
+                                                     ze0=ze0, spacing=spacing, device=dev)
             indptr, indices, data, coords, degrees = slab.owned_graph(res)
             share = dict(indptr=indptr, indices=indices, data=data, coords=coords, degrees=degrees,
                          pidx=res.paths_indices, pdata=res.paths_data, pw=res.paths_weights, plen=res.path_len,
@@ -150,7 +154,7 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             assert digest.same(dg, want), f'digest of the slab run differs from the oracle\'s: {dg} != {want}'
             print(f'SLAB-OK world={world} kind={kind} shape={shape} nodes={ref.graph.shape[0]} paths={ref.n_paths} '
                   f'cycles={sum(g["meta"]["n_cycles"] for g in gathered)} table={gathered[0]["meta"]["n_table"]} '
-                  f'table_rounds={gathered[0]["meta"]["table_rounds"]} native={int(gathered[0]["meta"]["native"])}', flush=True)
+                  f'table_rounds={gathered[0]["meta"]["table_rounds"]} native={int(gathered[0]["meta"]["native"])} xhalo={int(xhalo)}', flush=True)
     finally:
         dist.destroy_process_group()
 
@@ -168,8 +172,9 @@ if __name__ == '__main__':
     ap.add_argument('--spacing', default='0.5,0.1,0.1')
     ap.add_argument('--native', type=int, default=1)
     ap.add_argument('--small-arenas', type=int, default=0)
+    ap.add_argument('--halo-exchange', type=int, default=0)
     a = ap.parse_args()
     shape = tuple(int(x) for x in a.shape.split(','))
     spacing = tuple(float(x) for x in a.spacing.split(','))
     run(int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['MASTER_PORT']), a.kind, shape, a.seed,
-        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate), a.native, a.small_arenas)
+        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate), a.native, a.small_arenas, a.halo_exchange)

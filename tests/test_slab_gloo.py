@@ -116,3 +116,18 @@ def test_junction_clusters_across_slab_boundaries():
     codes, outs = launch(2, '--kind', 'dense12', '--shape', '40,16,16', '--halo', '2', '--seed', '5')
     assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
     assert 'SLAB-OK' in outs[0]
+
+
+@pytest.mark.parametrize('world,args', [
+    (2, ['--kind', 'walks', '--shape', '24,128,128', '--seed', '2']),
+    (3, ['--kind', 'dense', '--shape', '30,64,256', '--seed', '6']),
+    (3, ['--kind', 'rings', '--shape', '48,128,128']),
+    (2, ['--kind', 'walks', '--shape', '16,128,128', '--seed', '9', '--small-arenas', '1']),
+])
+def test_halo_exchange_from_a_disjoint_partition(world, args):
+    """halo='exchange': every rank passes its owned planes only; the packed mask of the boundary planes travels through
+    the exchange arenas.  The assembled result must equal the oracle's on the whole volume (and so the overlapped-input
+    path's, which the tests above compare with the same oracle)."""
+    codes, outs = launch(world, *args, '--halo-exchange', '1')
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'xhalo=1' in outs[0]
