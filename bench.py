@@ -347,7 +347,10 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-others', action='store_true', help='N=1 default run: skip the other BASELINE workloads')
     ap.add_argument('--sample-frac', type=int, default=None, help='CPU sample = leading 1/frac of the workload')
-    ap.add_argument('--halo', type=int, default=2, help='halo planes of the Z-slab decomposition (N > 1)')
+    ap.add_argument('--halo', type=int, default=2, help='halo planes of the Z-slab decomposition (N > 1, --halo-mode input)')
+    ap.add_argument('--halo-mode', default='exchange', choices=['exchange', 'input'],
+                    help='N > 1: exchange = disjoint Z-partition, boundary planes of the packed mask exchanged over NVLink; '
+                         'input = every rank is handed its slab with the halo planes')
     ap.add_argument('--timeline', action='store_true', help='N > 1: print the host timeline of one step to stderr')
     ap.add_argument('--stages', action='store_true', help='also print a per-entry-point timing table to stderr')
     args = ap.parse_args()
@@ -378,6 +381,7 @@ def main():
         _pipeline.default_pack_variant = args.pack_variant
     lib = _native.library()
     peak, peak_src = load_peaks()
+    xhalo = args.halo_mode == "exchange"
 
     def sync_all():
         torch.cuda.synchronize()
@@ -435,7 +439,7 @@ def main():
         else:
             # this rank's Z-slab: owned planes [z0, z1) plus `halo` planes on either side; the same seeded point
             # set on every rank, scattered into the slab only
-            z0, z1, ze0, ze1 = slab.slab_bounds(shape[0], world, rank, args.halo)
+            z0, z1, ze0, ze1 = slab.slab_bounds(shape[0], world, rank, 0 if xhalo else args.halo)
             img = scatter_slab(walks_points(shape, nw, wsteps, seed, isolated=iso, rings=rings), shape, ze0, ze1)
         V_local = int(img.numel())
         torch.cuda.synchronize()
@@ -447,6 +451,9 @@ def main():
             if world == 1:
                 return _pipeline.run_native(image, spacing=spacing, device=dev)
             a0, a1, ae0 = bounds or (z0, z1, ze0)
+            if xhalo:
+                return slab.skeleton_and_summary_slab(image, global_shape=gshape or shape, z0=a0, z1=a1, spacing=spacing,
+                                                      device=dev, halo='exchange')
             return slab.skeleton_and_summary_slab(image, global_shape=gshape or shape, z0=a0, z1=a1, ze0=ae0,
                                                   spacing=spacing, device=dev)
 
@@ -481,7 +488,9 @@ def main():
             del g, p
         else:
             counts = dict(nodes=r.n_nodes_total, edges=r.n_edges_total, paths=r.n_paths_total,
-                          path_entries=r.n_entries_total, halo=args.halo, table_records=r.n_table)
+                          path_entries=r.n_entries_total, table_records=r.n_table,
+                          halo='2 planes of packed mask per face exchanged over NVLink (disjoint partition)' if xhalo
+                          else f'{args.halo} planes per face passed with the slab')
             if getattr(r, 'counts', None):   # native runner: exchanges through peer-mapped arenas, no collective library
                 counts.update(runner='native (skb_run_slab)', host_syncs_per_step=r.counts['syncs'],
                               exchanges_per_step=r.counts['exchanges'], nccl_collectives_per_step=0)
@@ -589,7 +598,7 @@ def main():
             return par, base
         # N > 1: the sample volume over the same Z-slab decomposition, compared through the digest
         pts, sub = sample_points(workload, frac)
-        a0, a1, ae0, ae1 = slab.slab_bounds(sub[0], world, rank, args.halo)
+        a0, a1, ae0, ae1 = slab.slab_bounds(sub[0], world, rank, 0 if xhalo else args.halo)
         simg = scatter_slab(pts, sub, ae0, ae1)
         r = m['step'](simg, (a0, a1, ae0), sub)
         got = digest.digest_slab(r)
@@ -708,7 +717,7 @@ def main():
             'vs_baseline': None, 'dtype': m['dtype'], 'data': 'synthetic',
             'config': {'workload': workload, 'shape': list(shape), 'spacing': [float(x) for x in np.atleast_1d(spacing)],
                        'parallelism': 'single GPU' if world == 1 else
-                       (f'{world} shares of the stack, no collective' if is_stack else f'{world} Z-slabs, halo {args.halo}'),
+                       (f'{world} shares of the stack, no collective' if is_stack else f'{world} Z-slabs, halo {args.halo_mode}'),
                        'l2': 'input larger than L2 (no flush needed)' if V_local * esize > 256e6 else 'input fits L2',
                        'pack_variant': _pipeline.default_pack_variant, **m['counts']},
             'roofline': m['roofline'], 'clocks': m['clocks'], 'gpu_launches': int(m['launches']),

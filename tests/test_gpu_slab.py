@@ -43,6 +43,20 @@ def test_slab_mode_native(world, args):
     assert 'SLAB-OK' in outs[0] and f'world={world}' in outs[0]
 
 
+@pytest.mark.parametrize('world', WORLDS)
+@pytest.mark.parametrize('args', [
+    ['--kind', 'walks', '--shape', '64,128,128', '--seed', '2'],
+    ['--kind', 'dense12', '--shape', '48,64,256', '--seed', '6'],
+    ['--kind', 'rings', '--shape', '64,128,128'],
+])
+def test_halo_exchange_from_a_disjoint_partition(world, args):
+    """halo='exchange': owned planes only per rank, boundary planes of the packed mask exchanged over NVLink."""
+    _need(world)
+    codes, outs = launch(world, *args, '--halo-exchange', '1', backend='nccl', emulate=0)
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'xhalo=1' in outs[0] and f'world={world}' in outs[0]
+
+
 @pytest.mark.parametrize('world', (1, 2))
 def test_slab_mode_python_sequencing_nccl(world):
     _need(world)
