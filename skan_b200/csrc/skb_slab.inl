@@ -31,6 +31,8 @@ struct SkbComm {
     int64_t seq;
     void* xbase[SKB_MAX_RANKS];  // every rank's exchange arena as seen from this process
     int64_t xbytes;
+    int64_t hint_max_e, hint_edges;  // capacities learnt from the previous call (0: none): the largest per-rank junction
+                                     // edge count (the same on every rank) and this rank's edge count
     int64_t epoch;   // calls of skb_run_slab so far: consecutive calls use alternate halves of the exchange arena, so a
     int64_t xlimit;  // region is rewritten only after a whole intervening call (whose barriers every reader has passed)
 };
@@ -85,6 +87,7 @@ int skb_comm_create(int rank, int world, const char* name, int64_t exchange_byte
     snprintf(c->name, sizeof(c->name), "%s", name);
     c->seq = 0;
     c->epoch = 0;
+    c->hint_max_e = c->hint_edges = 0;
     c->xbytes = (exchange_bytes + 8191) & ~(int64_t)8191;
     c->xlimit = c->xbytes;
     for (int k = 0; k < SKB_MAX_RANKS; ++k) c->xbase[k] = nullptr;
@@ -142,6 +145,7 @@ int skb_comm_reset(void* comm) {
     SkbComm* c = (SkbComm*)comm;
     c->seq = 0;
     c->epoch = 0;
+    c->hint_max_e = c->hint_edges = 0;
     for (int b = 0; b < 2; ++b) {
         int64_t* row = skb_comm_table(c, b) + (int64_t)c->rank * (1 + SKB_COMM_MAXV);
         for (int i = 0; i <= SKB_COMM_MAXV; ++i) row[i] = 0;
@@ -423,38 +427,52 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     // ---- junction MST on the junction edges of the whole volume ----------------------------------------------
     SKB_TRY(skb_junction_edge_count(bits, pre256, 3, shape, lin, nb, Ne, own0, own1, jcount, s));
     SKB_TRY(skb_scan_u32_impl(jcount, jcount, Ne, scratch, s));
-    int64_t nej_k;
-    {
-        const int32_t* ptrs[1] = {(const int32_t*)jcount + Ne};
-        SKB_SFETCH(1, ptrs, vals);
-        nej_k = vals[0];
-    }
+    // The junction edges of every rank go to every rank.  With a capacity learnt from the previous call (the largest
+    // per-rank count, plus slack: the same number on every rank) the edges are emitted straight away and ONE
+    // synchronisation + exchange carries the counts and doubles as the barrier of the data; without one (first call,
+    // or the capacity proved too small: every rank sees that in the exchanged counts) the counts are exchanged first.
+    int64_t nej_k = -1;
     int64_t Noff[SKB_MAX_RANKS + 1], own0_of[SKB_MAX_RANKS];
     int64_t max_e = 0;
-    {
+    auto exchange_counts = [&]() -> int {
         const int64_t v[3] = {N_k, nej_k, own0};
         SKB_TRY(skb_comm_allgather(comm, v, 3, all));
         ++nexch;
         Noff[0] = 0;
+        max_e = 0;
         for (int k = 0; k < world; ++k) {
             Noff[k + 1] = Noff[k] + all[k * 3];
             if (all[k * 3 + 1] > max_e) max_e = all[k * 3 + 1];
             own0_of[k] = all[k * 3 + 2];
         }
-    }
-    const int64_t N_total = Noff[world];
-    if (N_total >= 0x7fffffffLL) return skb_fail("more than 2^31 nodes: node ids no longer fit the reference's int32 index arrays");
-    const int64_t id_shift = Noff[rank] - own0;
+        return 0;
+    };
+    auto fetch_nej = [&]() -> int {
+        const int32_t* ptrs[1] = {(const int32_t*)jcount + Ne};
+        SKB_SFETCH(1, ptrs, vals);
+        nej_k = vals[0];
+        return 0;
+    };
     int32_t *gea = nullptr, *geb = nullptr;
     uint64_t* gew = nullptr;
     uint8_t *gek = nullptr, *tree = nullptr;
     int32_t *mpar = nullptr, *era = nullptr, *erb = nullptr;
     uint64_t* bestw = nullptr;
     int64_t nej_rows = 0;
-    if (max_e) {
-        SkbExchange ex;
-        const int64_t rb[4] = {4, 4, 8, 1};
-        ex.init(comm, &xoff, max_e, 4, rb);
+    SkbExchange ex;
+    const int64_t rb[4] = {4, 4, 8, 1};
+    bool speculative = comm->hint_max_e > 0;
+    const int64_t work_mark_j = work.off, xoff_mark_j = xoff;
+    if (!speculative) {
+        SKB_TRY(fetch_nej());
+        SKB_TRY(exchange_counts());
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int64_t rows = speculative ? comm->hint_max_e + comm->hint_max_e / 8 + 1024 : max_e;
+        if (!rows) break;
+        work.off = work_mark_j;
+        xoff = xoff_mark_j;
+        ex.init(comm, &xoff, rows, 4, rb);
         if (!ex.ok) {
             res->exchange_need = 8 * (xoff - xoff0) + (1 << 23);
             return SKB_RUN_NEED_EXCHANGE;
@@ -464,24 +482,41 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         geb = work.take<int32_t>(nej_rows);
         gew = work.take<uint64_t>(nej_rows);
         gek = work.take<uint8_t>(nej_rows);
-        mpar = work.take<int32_t>(N_total);
-        bestw = work.take<uint64_t>(2 * N_total);
         era = work.take<int32_t>(nej_rows);
         erb = work.take<int32_t>(nej_rows);
         tree = work.take<uint8_t>(nej_rows);
         SKB_SNEED(work.ok);
         SKB_TRY(skb_fill_bytes(ex.mine(0), 0xff, (size_t)ex.cap * 4, s));  // a < 0 marks the padding rows
-        if (nej_k)
-            SKB_TRY(skb_junction_edge_emit(bits, pre256, 3, shape, lin, nb, jcount, Ne, prm->wtab, values, 0, prm->dtype,
-                                           (int32_t*)ex.mine(0), (int32_t*)ex.mine(1), (uint8_t*)ex.mine(3),
-                                           (uint64_t*)ex.mine(2), s));
-        SKB_TRY(skb_stream_sync(s));
-        ++nsync;
-        {
+        if (nej_k != 0)
+            SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, 3, shape, lin, nb, jcount, Ne, prm->wtab, values, 0, prm->dtype,
+                                               (int32_t*)ex.mine(0), (int32_t*)ex.mine(1), (uint8_t*)ex.mine(3),
+                                               (uint64_t*)ex.mine(2), ex.cap, s));
+        if (speculative) {
+            SKB_TRY(fetch_nej());        // the edges are complete when their count has arrived (stream order)
+            SKB_TRY(exchange_counts());  // ... and every peer's are when its row of counts has
+            if (max_e > ex.cap) {        // some rank's edges did not fit: every rank sees it, every rank goes again
+                speculative = false;
+                continue;
+            }
+        } else {
+            SKB_TRY(skb_stream_sync(s));
+            ++nsync;
             const int64_t one = 1;
-            SKB_TRY(skb_comm_allgather(comm, &one, 1, all));
+            int64_t dummy[SKB_MAX_RANKS];
+            SKB_TRY(skb_comm_allgather(comm, &one, 1, dummy));
             ++nexch;
         }
+        break;
+    }
+    comm->hint_max_e = max_e;
+    if (!max_e) nej_rows = 0;
+    const int64_t N_total = Noff[world];
+    if (N_total >= 0x7fffffffLL) return skb_fail("more than 2^31 nodes: node ids no longer fit the reference's int32 index arrays");
+    const int64_t id_shift = Noff[rank] - own0;
+    if (nej_rows) {
+        mpar = work.take<int32_t>(N_total);
+        bestw = work.take<uint64_t>(2 * N_total);
+        SKB_SNEED(work.ok);
         {   // the peers' rows, in rank order (= the global (a, b) order the tie-break needs), read in place
             int64_t desc[1 + 3 * 4 * SKB_MAX_RANKS];
             void* dst[4] = {gea, geb, gew, gek};
@@ -514,30 +549,48 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     int32_t* indptr = out.take<int32_t>(Ne + 1);
     SKB_SNEED(out.ok);
     SKB_TRY(skb_degrees_indptr(keep, Ne, deg, indptr, scratch, s));
-    int64_t E;
-    {
+    // graph.indices / data sized by the previous call's edge count (plus slack) when there is one: the emission runs
+    // without waiting for the exact count, which then arrives with the six offsets below (one synchronisation less)
+    int64_t E = -1;
+    const int64_t e_cap = comm->hint_edges > 0 ? comm->hint_edges + comm->hint_edges / 16 + 4096 : 0;
+    if (!e_cap) {
         const int32_t* ptrs[1] = {indptr + Ne};
         SKB_SFETCH(1, ptrs, vals);
         E = vals[0];
     }
-    int32_t* indices = out.take<int32_t>(E);
-    double* data = out.take<double>(E);
+    const int64_t out_mark_e = out.off, work_mark_e = work.off;
+    int32_t* indices = out.take<int32_t>(e_cap ? e_cap : E);
+    double* data = out.take<double>(e_cap ? e_cap : E);
     skb_i4* rec = work.take<skb_i4>(2 * Ne);
     uint32_t* startoff = work.take<uint32_t>(Ne + 1);
     uint32_t* is_min = work.take<uint32_t>(Ne + 1);
     SKB_SNEED(work.ok && out.ok);
-    SKB_TRY(skb_csr_emit(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
-                         rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, s));
+    SKB_TRY(skb_csr_emit_cap(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
+                             rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, e_cap ? e_cap : 0x7fffffffLL, s));
     int64_t so[4], ei[2];
-    {
-        const int32_t* ptrs[6] = {(const int32_t*)startoff + own0, (const int32_t*)startoff + own1,
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int32_t* ptrs[7] = {(const int32_t*)startoff + own0, (const int32_t*)startoff + own1,
                                   (const int32_t*)startoff + f1,   (const int32_t*)startoff + l0,
-                                  indptr + own0,                   indptr + own1};
-        SKB_SFETCH(6, ptrs, vals);
+                                  indptr + own0,                   indptr + own1,
+                                  indptr + Ne};
+        SKB_SFETCH(7, ptrs, vals);
         for (int i = 0; i < 4; ++i) so[i] = vals[i];
         ei[0] = vals[4];
         ei[1] = vals[5];
+        E = vals[6];
+        if (!e_cap || E <= e_cap || attempt) break;
+        out.off = out_mark_e;  // the capacity was too small: emit again with the exact size
+        work.off = work_mark_e;
+        indices = out.take<int32_t>(E);
+        data = out.take<double>(E);
+        rec = work.take<skb_i4>(2 * Ne);
+        startoff = work.take<uint32_t>(Ne + 1);
+        is_min = work.take<uint32_t>(Ne + 1);
+        SKB_SNEED(work.ok && out.ok);
+        SKB_TRY(skb_csr_emit(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
+                             rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, s));
     }
+    comm->hint_edges = E;
     const int64_t S = so[1] - so[0], SF = so[2] - so[0], SL0 = so[3] - so[0];
     const int64_t E_k = ei[1] - ei[0];
     int64_t Eoff[SKB_MAX_RANKS + 1], Soff[SKB_MAX_RANKS + 1], cnt_sf[SKB_MAX_RANKS], cnt_sl0[SKB_MAX_RANKS];

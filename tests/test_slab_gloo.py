@@ -131,3 +131,18 @@ def test_halo_exchange_from_a_disjoint_partition(world, args):
     codes, outs = launch(world, *args, '--halo-exchange', '1')
     assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
     assert 'SLAB-OK' in outs[0] and 'xhalo=1' in outs[0]
+
+
+@pytest.mark.parametrize('world,args', [
+    (2, ['--kind', 'walks', '--shape', '24,20,28', '--halo', '2', '--prime', '1']),
+    (3, ['--kind', 'dense', '--shape', '60,20,20', '--halo', '2', '--seed', '6', '--prime', '2']),
+    (2, ['--kind', 'dense12', '--shape', '40,16,16', '--halo', '2', '--seed', '5', '--prime', '2']),
+    (2, ['--kind', 'walks', '--shape', '24,128,128', '--seed', '2', '--halo-exchange', '1', '--prime', '1']),
+])
+def test_capacity_hints_of_the_previous_call(world, args):
+    """The second call on a communicator sizes the junction-edge exchange and the edge arrays by the first call's counts and
+    saves two synchronisations; hints that fit (--prime 1) and hints that are too small (--prime 2: a much sparser
+    volume first) must both give the oracle's result."""
+    codes, outs = launch(world, *args)
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0]
