@@ -44,6 +44,11 @@ int skb_set_option(const char* name, int64_t value); /* tunables with no effect 
                                                         4: one chain voxel in 2^bits splits the chains into walks;
                                                         every rank of a Z-slab run must use the same value).  Both
                                                         defaults were measured on B200 (profiles/r02_summary.md) */
+/* Debugging aid: after skb_set_option("arena_guard", 1) the runners leave a 256-byte gap behind every allocation they make
+ * in the caller's arenas; this returns the number of gaps of the calling thread's last runner call and writes their byte
+ * offsets (which = 0: work arena, 1: out arena).  A caller that filled the arenas with a pattern finds out-of-bounds writes
+ * as damaged gaps (tests/test_gpu_guards.py). */
+int64_t skb_debug_guard_offsets(int which, int64_t* out /*host*/, int64_t cap);
 int64_t skb_kernel_launches(void);         /* kernels launched by the library since it was loaded */
 
 /* Mask sweep -- replaces image.astype(bool), np.pad and both np.flatnonzero passes

@@ -24,6 +24,7 @@ _SIGNATURES = {
     'skb_scan_scratch_bytes': (_i64, [_i64]),
     'skb_tile_voxels': (_i64, []),
     'skb_kernel_launches': (_i64, []),
+    'skb_debug_guard_offsets': (_i64, [_int, _vp, _i64]),
     'skb_set_option': (_int, [ctypes.c_char_p, _i64]),
     'skb_pack_count': (_int, [_vp, _int, _i64, _vp, _vp, _i64, _int, _vp]),
     'skb_emit_nodes': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp]),

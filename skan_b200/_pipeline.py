@@ -454,6 +454,8 @@ def algorithmic_bytes(nvox, esize, ndim, n, e, p, l, valued):
 
 
 # ---- the same path through the native runner (skb_run_image): one C call per image ---------------
+DEBUG_FILL = None   # tests: fill both arenas with this byte before every native call (see tests/test_gpu_guards.py)
+LAST_ARENAS = None  # tests: (work, out) tensors of the last native call when DEBUG_FILL is set
 TIME_SWEEP = False  # bench.py: record CUDA events around the mask sweep kernel (counts['sweep_ns'])
 USE_HINTS = True    # pass the previous image's counts (+ slack) as capacity hints to skb_run_image
 
@@ -549,6 +551,11 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
         out = ctx.empty(cache['out_bytes'], torch.uint8)
         prm.work, prm.work_bytes = work.data_ptr(), work.numel()
         prm.out, prm.out_bytes = out.data_ptr(), out.numel()
+        if DEBUG_FILL is not None:
+            global LAST_ARENAS
+            work.fill_(DEBUG_FILL)
+            out.fill_(DEBUG_FILL)
+            LAST_ARENAS = (work, out)
         with ctx.guard():
             rc = ctx.lib.call('skb_run_image', ctypes_byref(prm), ctypes_byref(res))
         if rc == 0:

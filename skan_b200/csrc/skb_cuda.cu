@@ -1526,6 +1526,7 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_table_rank_coop_kernel(s
 // a grid barrier costs more the more CTAs take part: "mst_blocks_per_sm" caps the Boruvka launch (0 = what fits)
 static int g_skb_mst_blocks_per_sm = 0;  // measured: fewer CTAs lose (the rounds are bound by the finds, not the barriers)
 static int g_skb_emit_blocks_per_sm = 16;  // measured at 2048^3: 5 -> 0.314, 8 -> 0.258, 16 -> 0.254 ms (tail balance)
+static int g_skb_arena_guard = 0;  // "arena_guard": guard gaps between the runners' allocations (skb_run.inl)
 static int g_skb_small_cycles = 1;  // "small_cycles": 0 = always the general machinery for junction-free cycles
 static int g_skb_mst_keys = 1;  // "mst_keys": 0 = the two-phase rounds also for table weights (A/B)
 template <typename K>
@@ -1853,6 +1854,10 @@ int skb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "emit_blocks_per_sm")) {
         if (value < 1 || value > 64) return skb_fail("skb_set_option: emit_blocks_per_sm must be in 1..64");
         g_skb_emit_blocks_per_sm = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "arena_guard")) {
+        g_skb_arena_guard = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "small_cycles")) {

@@ -70,29 +70,65 @@ struct skb_run_result {
     int64_t stage_ns[32];
 };
 
+// Debugging aid (compute-sanitizer is closed on the pool this was built on): with skb_set_option("arena_guard", 1)
+// every allocation of a runner is followed by a 256-byte guard gap whose offset is recorded; the caller fills the arenas
+// with a byte pattern before the call and checks afterwards that every gap still holds it (an out-of-bounds write of a
+// kernel lands in a gap), and runs twice with different patterns (a result that depends on the pattern was computed
+// from uninitialised memory).  tests/test_gpu_guards.py does both.
+#define SKB_GUARD_BYTES 256
+#define SKB_MAX_GUARDS 512
+// g_skb_arena_guard is defined by the including file (skb_set_option "arena_guard")
+struct SkbGuardLog {
+    int64_t off[2][SKB_MAX_GUARDS];
+    int n[2];
+};
+static thread_local SkbGuardLog g_skb_guards = {};
+
 struct SkbArena {
     uint8_t* base;
     int64_t cap, off, need;
+    int64_t high;  // high-water mark of `off`: a gap recorded below it lies in space an earlier (rewound) allocation used
     bool ok;
-    void init(void* p, int64_t bytes) {
+    int which;  // 0 = work, 1 = out (index into the guard log)
+    void init(void* p, int64_t bytes, int which_ = 0) {
         base = (uint8_t*)p;
         cap = bytes;
         off = 0;
         need = 0;
+        high = 0;
         ok = true;
+        which = which_;
+        g_skb_guards.n[which] = 0;
     }
     template <typename T>
     T* take(int64_t count) {
         int64_t bytes = (count > 0 ? count : 1) * (int64_t)sizeof(T);
         off = (off + 255) & ~(int64_t)255;
-        need = off + bytes;
+        const int64_t guard = g_skb_arena_guard ? SKB_GUARD_BYTES : 0;
+        need = off + bytes + guard;
         if (need > cap || !base) {
             ok = false;
             off = need;  // keep counting so that the caller learns how much this stage wanted
             return nullptr;
         }
         T* p = (T*)(base + off);
+        if (guard) {
+            // (a runner that rewinds the bump pointer allocates over earlier gaps: drop the records at or beyond `off`)
+            int& n = g_skb_guards.n[which];
+            while (n > 0 && (g_skb_guards.off[which][n - 1] >= off || -g_skb_guards.off[which][n - 1] - 1 >= off)) --n;
+            const int64_t gap = (off + bytes + 255) & ~(int64_t)255;
+            // a gap in space that was handed out before the runner rewound its bump pointer may have been written to
+            // legitimately: recorded as -(offset) - 1, which the checker skips
+            if (n < SKB_MAX_GUARDS) g_skb_guards.off[which][n++] = gap < high ? -gap - 1 : gap;
+            need = ((off + bytes + 255) & ~(int64_t)255) + guard;
+            if (need > cap) {
+                ok = false;
+                off = need;
+                return nullptr;
+            }
+        }
         off = need;
+        if (off > high) high = off;
         return p;
     }
 };
@@ -158,8 +194,8 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         if (stages) SKB_TRY(skb_stage_read(marked, SKB_M_COUNT, res->stage_ns));  \
     } while (0)
     SkbArena work, out;
-    work.init(prm->work, prm->work_bytes);
-    out.init(prm->out, prm->out_bytes);
+    work.init(prm->work, prm->work_bytes, 0);
+    out.init(prm->out, prm->out_bytes, 1);
     // every successful return reports what the image needed: the caller sizes the next image's arenas by it
 #define SKB_RUN_DONE()                            \
     do {                                          \

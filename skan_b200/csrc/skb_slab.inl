@@ -259,6 +259,14 @@ extern "C" int skb_run_slab(const skb_slab_params* prm, void* comm_, skb_slab_re
     return rc;
 }
 
+// offsets (into the work arena: which = 0, the out arena: which = 1) of the guard gaps of this thread's last runner call
+extern "C" int64_t skb_debug_guard_offsets(int which, int64_t* out, int64_t cap) {
+    if (which < 0 || which > 1) return 0;
+    const int n = g_skb_guards.n[which];
+    for (int i = 0; i < n && i < cap; ++i) out[i] = g_skb_guards.off[which][i];
+    return n;
+}
+
 static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab_result* res) {
     skb_stream_t s = (skb_stream_t)prm->stream;
     const int world = comm->world, rank = comm->rank;
@@ -292,8 +300,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     for (int i = 0; i < 32; ++i) res->off[i] = -1;
     res->work_need = res->out_need = res->exchange_need = 0;
     SkbArena work, out;
-    work.init(prm->work, prm->work_bytes);
-    out.init(prm->out, prm->out_bytes);
+    work.init(prm->work, prm->work_bytes, 0);
+    out.init(prm->out, prm->out_bytes, 1);
     auto out_off = [&](const void* p) -> int64_t { return p ? (int64_t)((const uint8_t*)p - out.base) : -1; };
     // bump pointer into the exchange arena, the same on every rank; this call's half of the arena
     const int64_t xhalf = comm->xbytes / 2;

@@ -282,6 +282,10 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         out = ctx.empty(cache['out_bytes'], torch.uint8)
         prm.work, prm.work_bytes = work.data_ptr(), work.numel()
         prm.out, prm.out_bytes = out.data_ptr(), out.numel()
+        if _pipeline.DEBUG_FILL is not None:
+            work.fill_(_pipeline.DEBUG_FILL)
+            out.fill_(_pipeline.DEBUG_FILL)
+            _pipeline.LAST_ARENAS = (work, out)
         failure = None
         try:
             with ctx.guard():

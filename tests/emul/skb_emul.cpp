@@ -145,6 +145,7 @@ static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*
 static int g_skb_split_bits = 4;
 static uint32_t skb_option_split_shift() { return 32u - (uint32_t)g_skb_split_bits; }
 static int g_skb_both_ways = 1;
+static int g_skb_arena_guard = 0;
 static int skb_option_both_ways() { return g_skb_both_ways; }
 // the single-block handling of small junction-free cycles is a CUDA kernel: the harness always runs the general path
 static int skb_cycles_small(const skb_i4*, const uint8_t*, int64_t, int64_t, const double*, int64_t, int32_t*, uint32_t*,
@@ -172,6 +173,7 @@ int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
 int64_t skb_kernel_launches(void) { return 0; }
 int skb_set_option(const char* name, int64_t value) {  // the scheduling tunables of the CUDA build do nothing here
     if (name && !strcmp(name, "emit_both_ways")) g_skb_both_ways = value ? 1 : 0;
+    if (name && !strcmp(name, "arena_guard")) g_skb_arena_guard = value ? 1 : 0;
     if (name && !strcmp(name, "splitter_bits") && value >= 1 && value <= 12) g_skb_split_bits = (int)value;
     return 0;
 }

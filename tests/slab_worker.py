@@ -102,7 +102,7 @@ def compare_with_oracle(img, spacing, glob):
     return ref
 
 
-def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate, native=1, small=0, xhalo=0, prime=0):
+def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate, native=1, small=0, xhalo=0, prime=0, guard=0):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group(backend, rank=rank, world_size=world)
     try:
@@ -127,6 +127,10 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             torch.cuda.set_device(rank % torch.cuda.device_count())
             dev = torch.device('cuda', rank % torch.cuda.device_count())
         with cm:
+            if guard:   # guard gaps behind every allocation of the runner, arenas pre-filled with a pattern (tests/guard_util.py)
+                from guard_util import guarded
+                gctx = guarded(0xA5)
+                gctx.__enter__()
             # prime: earlier calls on this communicator leave capacity hints behind (1: the same volume, so the hints fit;
             # 2: a much sparser volume first, so the hints are too small and the speculative stages must go again)
             for p in range(prime and 1):
@@ -148,6 +152,11 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
             else:
                 res = slab.skeleton_and_summary_slab(torch.from_numpy(part).to(dev), global_shape=shape, z0=z0, z1=z1,
                                                      ze0=ze0, spacing=spacing, device=dev)
+            if guard:
+                if dev.type == 'cuda':
+                    torch.cuda.synchronize()
+                assert gctx.check_gaps() > 10
+                gctx.__exit__(None, None, None)
             indptr, indices, data, coords, degrees = slab.owned_graph(res)
             share = dict(indptr=indptr, indices=indices, data=data, coords=coords, degrees=degrees,
                          pidx=res.paths_indices, pdata=res.paths_data, pw=res.paths_weights, plen=res.path_len,
@@ -189,8 +198,9 @@ if __name__ == '__main__':
     ap.add_argument('--small-arenas', type=int, default=0)
     ap.add_argument('--halo-exchange', type=int, default=0)
     ap.add_argument('--prime', type=int, default=0)
+    ap.add_argument('--guard', type=int, default=0)
     a = ap.parse_args()
     shape = tuple(int(x) for x in a.shape.split(','))
     spacing = tuple(float(x) for x in a.spacing.split(','))
     run(int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['MASTER_PORT']), a.kind, shape, a.seed,
-        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate), a.native, a.small_arenas, a.halo_exchange, a.prime)
+        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate), a.native, a.small_arenas, a.halo_exchange, a.prime, a.guard)

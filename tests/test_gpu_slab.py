@@ -21,6 +21,8 @@ CASES = [
     ['--kind', 'lines_z', '--shape', '64,33,40', '--halo', '2'],
     ['--kind', 'walks', '--shape', '128,96,80', '--halo', '8', '--seed', '12', '--valued', '1'],
     ['--kind', 'rings', '--shape', '64,22,30', '--halo', '2'],
+    ['--kind', 'walks', '--shape', '96,64,64', '--halo', '2', '--seed', '11', '--guard', '1', '--prime', '1'],
+    ['--kind', 'dense12', '--shape', '64,32,32', '--halo', '2', '--seed', '5', '--guard', '1', '--prime', '2'],
 ]
 
 

@@ -138,6 +138,7 @@ def test_halo_exchange_from_a_disjoint_partition(world, args):
     (3, ['--kind', 'dense', '--shape', '60,20,20', '--halo', '2', '--seed', '6', '--prime', '2']),
     (2, ['--kind', 'dense12', '--shape', '40,16,16', '--halo', '2', '--seed', '5', '--prime', '2']),
     (2, ['--kind', 'walks', '--shape', '24,128,128', '--seed', '2', '--halo-exchange', '1', '--prime', '1']),
+    (3, ['--kind', 'rings', '--shape', '48,22,30', '--halo', '3', '--valued', '1', '--guard', '1', '--prime', '1']),
 ])
 def test_capacity_hints_of_the_previous_call(world, args):
     """The second call on a communicator sizes the junction-edge exchange and the edge arrays by the first call's counts and
