@@ -156,8 +156,8 @@ static int skb_mst_junctions_apply(const int32_t* ea, const int32_t* eb, const u
     if (nej <= 0) return 0;
 #ifdef SKB_HAVE_FUSED_LOOPS
     if (!height && g_skb_mst_keys)
-        return skb_mst_keys_run(ea, eb, ek, wtab, nej, par, (unsigned long long*)best, n_ids, era, erb, tree, flag, keep,
-                                (int32_t)id_shift, (int32_t)n_local, (skb_stream_t)stream);
+        return skb_mst_keys_run(ea, eb, ek, wtab, nej, nullptr, par, (unsigned long long*)best, n_ids, era, erb, tree, flag,
+                                keep, (int32_t)id_shift, (int32_t)n_local, (skb_stream_t)stream);
 #endif
     (void)wtab;
     int r = skb_mst_junctions(ea, eb, ew, nej, n_ids, par, best, (uint32_t*)(best + n_ids), era, erb, tree, flag, stream);

@@ -1386,18 +1386,32 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_coop_kernel(
 }
 
 // Junction MST, table weights (every weight is one of the 26 neighbour distances: anything but height mode).  The order
-// (weight, a, b) of an edge is then ONE 64-bit key, (rank of the weight among the table's values) << 32 | edge index
-// (edges are listed in (a, b) order), so a round needs one atomic minimum per end instead of two phases, and the
+// (weight, a, b) of an edge is then ONE 64-bit key: (rank of the weight among the table's values, a, direction code k27
+// of b seen from a) -- for a fixed a ascending direction codes are ascending neighbour ids -- so the edges may be listed
+// in ANY order (skb_junction_append_kernel appends them with one atomic per thread block), a round needs one atomic
+// minimum per end instead of two phases, and the
 // per-component minima are double-buffered by round parity (a round resets the entries the next round will use: the
 // roots of round r+1 are among the roots round r saw), so there is no reset phase either: 2 grid barriers per round
 // instead of 4.  After the last round the same launch clears the dropped junction-junction edges from `keep`
 // (csr.py:1018-1019; keep = the raw masks, updated in place).
+__device__ __forceinline__ unsigned long long skb_mst_key(const uint32_t* s_rank, int32_t a, uint8_t k) {
+    return ((unsigned long long)s_rank[k] << 40) | ((unsigned long long)(uint32_t)a << 5) | (unsigned long long)k;
+}
+
 __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_keys_coop_kernel(
-    const int32_t* ea, const int32_t* eb, const uint8_t* ek, const double* wtab, int64_t nej, int32_t* par,
+    const int32_t* ea, const int32_t* eb, const uint8_t* ek, const double* wtab, int64_t nej_arg, const int32_t* nej_ptr,
+    int64_t nej_cap, int32_t* par,
     unsigned long long* best /* [2][n_ids] */, int64_t n_ids, int32_t* era, int32_t* erb, uint8_t* tree,
     int32_t* flags /* [3]: two flags + rounds */, uint32_t* keep, int32_t id_shift, int32_t n_local) {
     cg::grid_group grid = cg::this_grid();
     __shared__ uint32_t s_rank[27];
+    // the number of edges: a launch argument, or (edges appended with an atomic counter, count still on its way to the
+    // host) read from device memory and clamped to the capacity of the arrays
+    int64_t nej = nej_arg;
+    if (nej_ptr) {
+        nej = *nej_ptr;
+        if (nej > nej_cap) nej = nej_cap;
+    }
     if (threadIdx.x < 27) {  // rank of every table weight among the table's distinct values (positive doubles: bit order)
         const unsigned long long me = (unsigned long long)__double_as_longlong(wtab[threadIdx.x]);
         uint32_t r = 0;
@@ -1441,7 +1455,7 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_keys_coop_kernel(
             }
             era[e] = ra;
             erb[e] = rb;
-            const unsigned long long key = ((unsigned long long)s_rank[ek[e]] << 32) | (unsigned long long)(uint32_t)e;
+            const unsigned long long key = skb_mst_key(s_rank, ea[e], ek[e]);
             atomicMin(cur + ra, key);
             atomicMin(cur + rb, key);
             nxt[ra] = ~0ull;
@@ -1455,7 +1469,7 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_keys_coop_kernel(
             const int32_t ra = era[e];
             if (ra == -2) continue;
             const int32_t rb = erb[e];
-            const unsigned long long key = ((unsigned long long)s_rank[ek[e]] << 32) | (unsigned long long)(uint32_t)e;
+            const unsigned long long key = skb_mst_key(s_rank, ea[e], ek[e]);
             const bool pa = __ldcg(cur + ra) == key, pb = __ldcg(cur + rb) == key;
             if (!(pa || pb)) continue;
             tree[e] = 1;
@@ -1553,12 +1567,91 @@ static int skb_mst_run(const int32_t* ea, const int32_t* eb, const uint64_t* ew,
     return skb_coop_launch(skb_mst_coop_kernel, nej, args, s);
 }
 
+// nej_ptr != NULL: the edge count is read on the device (at most nej edges, the capacity of the arrays)
 static int skb_mst_keys_run(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const double* wtab, int64_t nej,
-                            int32_t* par, unsigned long long* best, int64_t n_ids, int32_t* era, int32_t* erb, uint8_t* tree,
-                            int32_t* flag, uint32_t* keep, int32_t id_shift, int32_t n_local, skb_stream_t s) {
-    void* args[] = {&ea, &eb, &ek, &wtab, &nej, &par, &best, &n_ids, &era, &erb, &tree, &flag, &keep, &id_shift, &n_local};
+                            const int32_t* nej_ptr, int32_t* par, unsigned long long* best, int64_t n_ids, int32_t* era,
+                            int32_t* erb, uint8_t* tree, int32_t* flag, uint32_t* keep, int32_t id_shift, int32_t n_local,
+                            skb_stream_t s) {
+    int64_t nej_cap = nej;
+    void* args[] = {&ea, &eb, &ek, &wtab, &nej, &nej_ptr, &nej_cap, &par, &best, &n_ids, &era, &erb, &tree, &flag, &keep,
+                    &id_shift, &n_local};
     return skb_coop_launch(skb_mst_keys_coop_kernel, nej, args, s, g_skb_mst_blocks_per_sm);
 }
+
+// Junction-junction edges (csr.py:1004-1016) in ONE pass and in no particular order: every node of raw degree >= 3 tests
+// its forward neighbours (one rank query each), a thread block sums its edge count, takes its share of the arrays with
+// one atomic and writes.  Replaces count + scan + emit (two passes of rank queries) when the arrays can be sized by a
+// capacity; *counter receives the number of edges (edges beyond `cap` are counted, not written).
+__global__ void __launch_bounds__(256) skb_junction_append_kernel(SkbGeom g, const uint64_t* __restrict__ bits,
+                                                                  const uint32_t* __restrict__ pre256,
+                                                                  const int64_t* __restrict__ lin,
+                                                                  const uint32_t* __restrict__ nb, int64_t n,
+                                                                  int32_t* __restrict__ ea, int32_t* __restrict__ eb,
+                                                                  uint8_t* __restrict__ ek, uint32_t cap, int32_t* counter) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const int64_t n_round = (n + 255) / 256 * 256;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n_round; base += stride) {
+        const int64_t i = base + tid;
+        int32_t us[13];
+        uint8_t ks[13];
+        uint32_t cnt = 0;
+        if (i < n) {
+            const uint32_t m = nb[i];
+            if (__popc(m) >= 3 && (m >> 14)) {
+                uint32_t fm = m & ~((1u << 14) - 1u);
+                const int64_t r = lin[i];
+                while (fm) {
+                    const int k = __ffs((int)fm) - 1;
+                    fm &= fm - 1u;
+                    const int32_t u = k == 14 ? (int32_t)i + 1 : skb_rank(bits, pre256, skb_neighbor_lin(g, r, k));
+                    if (__popc(nb[u]) >= 3) {
+                        us[cnt] = u;
+                        ks[cnt] = (uint8_t)k;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t c = warp_tot[w];
+                warp_tot[w] = t;
+                t += c;
+            }
+            s_base = t ? (uint32_t)atomicAdd(counter, (int32_t)t) : 0u;
+        }
+        __syncthreads();
+        uint32_t o = s_base + warp_tot[warp] + inc - cnt;
+        for (uint32_t j = 0; j < cnt; ++j, ++o) {
+            if (o < cap) {
+                ea[o] = (int32_t)i;
+                eb[o] = us[j];
+                ek[o] = ks[j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int g_skb_junction_append = 1;  // "junction_append": 0 = always count + scan + emit
+// returns 0, or 1 when the one-pass form does not apply (the caller counts, scans and emits)
+static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
+                               const uint32_t* nb, int64_t n, int32_t* ea, int32_t* eb, uint8_t* ek, int64_t cap,
+                               int32_t* counter, skb_stream_t s);
+
 
 static int skb_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, int32_t lo, int32_t hi,
                         int32_t* flag, skb_stream_t s) {
@@ -1824,6 +1917,21 @@ static int skb_cycles_small(const skb_i4* rec, const uint8_t* covered, int64_t n
 
 #include "skb_api.inl"
 
+static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
+                               const uint32_t* nb, int64_t n, int32_t* ea, int32_t* eb, uint8_t* ek, int64_t cap,
+                               int32_t* counter, skb_stream_t s) {
+    if (!g_skb_junction_append || n <= 0 || cap <= 0) return 1;
+    SKB_TRY(skb_check_geom(ndim, shape));
+    SKB_TRY(skb_fill_bytes(counter, 0, 4, s));
+    int64_t blocks = (n + 255) / 256;
+    const int64_t max_blocks = (int64_t)skb_sm_count() * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    skb_junction_append_kernel<<<(unsigned)blocks, 256, 0, s>>>(skb_make_geom(ndim, shape), bits, pre256, lin, nb, n, ea, eb, ek,
+                                                                cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap, counter);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "junction append launch");
+}
+
 extern "C" {
 
 const char* skb_last_error(void) { return g_skb_err; }
@@ -1854,6 +1962,10 @@ int skb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "emit_blocks_per_sm")) {
         if (value < 1 || value > 64) return skb_fail("skb_set_option: emit_blocks_per_sm must be in 1..64");
         g_skb_emit_blocks_per_sm = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "junction_append")) {
+        g_skb_junction_append = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "arena_guard")) {

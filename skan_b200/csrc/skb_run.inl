@@ -317,10 +317,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     res->off[SKB_O_VALUES] = out_off(values);
     // ---- junction MST ----------------------------------------------------------------------------------
     const int height = prm->height == 1 ? 1 : 0;
-    SKB_TRY(skb_junction_edge_count(bits, pre256, ndim, prm->shape, lin, nb, N, 0, N, jcount, s));
-    SKB_TRY(skb_scan_u32_impl(jcount, jcount, N, scratch, s));
-    SKB_MARK(SKB_M_JCOUNT);
-    int64_t nej;
+    int64_t nej = 0;
     uint32_t* keep = nb;
     int32_t *ea = nullptr, *eb = nullptr;
     uint8_t *ek = nullptr, *tree = nullptr;
@@ -341,35 +338,66 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     {
         const int64_t cap = prm->hint[SKB_H_JUNCTION_EDGES] > 0 ? prm->hint[SKB_H_JUNCTION_EDGES] : 0;
         const int64_t work_mark = work.off;
-        bool emitted = false;
-        SKB_POST(jcount + N);
-        if (cap > 0) {  // edge emission sized by the hint runs while the count travels
+        bool emitted = false, appended = false;
+        if (cap > 0 && !height) {
+            // one pass, no order (skb_junction_append_kernel): the edges are appended with an atomic counter, and the
+            // Boruvka launch reads their number from that counter while it travels to the host
             take_junction(cap);
             if (work.ok) {
-                SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values,
-                                                   height, prm->dtype, ea, eb, ek, ew, cap, s));
-                emitted = true;
+                int r = skb_junction_append(bits, pre256, ndim, prm->shape, lin, nb, N, ea, eb, ek, cap, flag + 3, s);
+                if (r < 0) return r;
+                appended = r == 0;
+            }
+            if (appended) {
+                SKB_POST(flag + 3);
+                SKB_TRY(skb_mst_keys_run(ea, eb, ek, prm->wtab, cap, flag + 3, mpar, (unsigned long long*)bestw, N, era, erb,
+                                         tree, flag, keep, 0, (int32_t)N, s));
                 ++noverlap;
+                SKB_WAIT(nej);
+                if (nej > cap) {  // the capacity was too small: the masks are half-edited, so the stencil runs again
+                    appended = false;
+                    ++nretaken;
+                    SKB_TRY(skb_raw_neighbors(bits, ndim, prm->shape, lin, N, prm->image_stack, nb, s));
+                }
+            }
+            if (!appended) {
+                work.off = work_mark;
+                work.ok = true;
             }
         }
-        SKB_WAIT(nej);
-        if (nej && (!emitted || nej > cap)) {
-            if (emitted) ++nretaken;
-            work.off = work_mark;
-            work.ok = true;
-            take_junction(nej);
-            SKB_NEED(work.ok);
-            SKB_TRY(skb_junction_edge_emit(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values, height,
-                                           prm->dtype, ea, eb, ek, ew, s));
-        } else if (!nej) {
-            work.off = work_mark;
-            work.ok = true;
+        if (!appended) {
+            SKB_TRY(skb_junction_edge_count(bits, pre256, ndim, prm->shape, lin, nb, N, 0, N, jcount, s));
+            SKB_TRY(skb_scan_u32_impl(jcount, jcount, N, scratch, s));
+            SKB_MARK(SKB_M_JCOUNT);
+            SKB_POST(jcount + N);
+            if (cap > 0) {  // edge emission sized by the hint runs while the count travels
+                take_junction(cap);
+                if (work.ok) {
+                    SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values,
+                                                       height, prm->dtype, ea, eb, ek, ew, cap, s));
+                    emitted = true;
+                    ++noverlap;
+                }
+            }
+            SKB_WAIT(nej);
+            if (nej && (!emitted || nej > cap)) {
+                if (emitted) ++nretaken;
+                work.off = work_mark;
+                work.ok = true;
+                take_junction(nej);
+                SKB_NEED(work.ok);
+                SKB_TRY(skb_junction_edge_emit(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values, height,
+                                               prm->dtype, ea, eb, ek, ew, s));
+            } else if (!nej) {
+                work.off = work_mark;
+                work.ok = true;
+            }
+            if (nej)  // the dropped junction-junction edges are cleared from the raw masks in place: keep == nb
+                SKB_TRY(skb_mst_junctions_apply(ea, eb, ek, ew, prm->wtab, height, nej, N, mpar, bestw, era, erb, tree, flag,
+                                                keep, 0, N, s));
         }
     }
     res->counts[SKB_C_JUNCTION_EDGES] = nej;
-    if (nej)  // the dropped junction-junction edges are cleared from the raw masks in place: keep == nb
-        SKB_TRY(skb_mst_junctions_apply(ea, eb, ek, ew, prm->wtab, height, nej, N, mpar, bestw, era, erb, tree, flag, keep, 0,
-                                        N, s));
     SKB_MARK(SKB_M_MST);
     // ---- CSR + node records ------------------------------------------------------------------------------
     int32_t* deg = out.take<int32_t>(N);

@@ -33,6 +33,7 @@ def test_no_out_of_bounds_write_and_no_read_of_garbage(variant):
             seen = {}
             for small_cycles in (1, 0):
                 lib.call('skb_set_option', b'small_cycles', small_cycles)
+                lib.call('skb_set_option', b'junction_append', small_cycles)   # both forms of the junction edge emission
                 for fill in (0x00, 0xA5, 0xFF):
                     with guarded(fill) as g:
                         for rep in range(2):          # the second call runs with capacity hints
@@ -46,6 +47,7 @@ def test_no_out_of_bounds_write_and_no_read_of_garbage(variant):
     finally:
         _pipeline.default_pack_variant = old
         lib.call('skb_set_option', b'small_cycles', 1)
+        lib.call('skb_set_option', b'junction_append', 1)
 
 
 def test_repeated_runs_are_bit_identical():
