@@ -627,11 +627,16 @@ def main():
 
     if args.timeline and world > 1 and slab.NATIVE and not is_stack:
         sync_all()
+        slab.TIME_SWEEP = 2
         r = step()
         torch.cuda.synchronize()
+        slab.TIME_SWEEP = False
+        tl = [None] * world
+        dist.all_gather_object(tl, (r.counts['host_us'], r.counts['dev_us']))
         if rank == 0:
             for k, v in r.counts['host_us'].items():
-                print(f'  [host timeline, rank 0] {k:24s} +{v / 1e3:7.3f} ms', file=sys.stderr)
+                print(f'  [host timeline, rank 0] {k:24s} +{v / 1e3:7.3f} ms   device {r.counts["dev_us"][k] / 1e3:7.3f} ms   '
+                      f'(host, all ranks: ' + ' '.join(f'{t[0][k] / 1e3:.3f}' for t in tl) + ')', file=sys.stderr)
             print(f'  [host timeline, rank 0] syncs {r.counts["syncs"]} exchanges {r.counts["exchanges"]}', file=sys.stderr)
         del r
 

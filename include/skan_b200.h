@@ -340,7 +340,7 @@ typedef struct skb_slab_params {
     double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, halo_exchange;
     void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;
 } skb_slab_params;
-typedef struct skb_slab_result { int64_t counts[32]; int64_t off[32]; int64_t work_need, out_need, exchange_need; int64_t host_ns[16]; } skb_slab_result;
+typedef struct skb_slab_result { int64_t counts[32]; int64_t off[32]; int64_t work_need, out_need, exchange_need; int64_t host_ns[16]; int64_t dev_ns[16]; } skb_slab_result;
 int skb_run_slab(const skb_slab_params* params /*host*/, void* comm, skb_slab_result* result /*host*/);
 
 #ifdef __cplusplus

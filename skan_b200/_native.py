@@ -114,7 +114,7 @@ class SlabParams(ctypes.Structure):
 class SlabResult(ctypes.Structure):
     """struct skb_slab_result (include/skan_b200.h)"""
     _fields_ = [('counts', _i64 * 32), ('off', _i64 * 32), ('work_need', _i64), ('out_need', _i64),
-                ('exchange_need', _i64), ('host_ns', _i64 * 16)]
+                ('exchange_need', _i64), ('host_ns', _i64 * 16), ('dev_ns', _i64 * 16)]
 
 
 _SIGNATURES['skb_comm_create'] = (_int, [_int, _int, ctypes.c_char_p, _i64, ctypes.POINTER(_vp)])

@@ -1586,8 +1586,9 @@ __global__ void __launch_bounds__(256) skb_junction_append_kernel(SkbGeom g, con
                                                                   const uint32_t* __restrict__ pre256,
                                                                   const int64_t* __restrict__ lin,
                                                                   const uint32_t* __restrict__ nb, int64_t n,
-                                                                  int32_t* __restrict__ ea, int32_t* __restrict__ eb,
-                                                                  uint8_t* __restrict__ ek, uint32_t cap, int32_t* counter) {
+                                                                  int64_t a0, int64_t a1, int32_t* __restrict__ ea,
+                                                                  int32_t* __restrict__ eb, uint8_t* __restrict__ ek,
+                                                                  uint32_t cap, int32_t* counter) {
     __shared__ uint32_t warp_tot[8];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1598,7 +1599,7 @@ __global__ void __launch_bounds__(256) skb_junction_append_kernel(SkbGeom g, con
         int32_t us[13];
         uint8_t ks[13];
         uint32_t cnt = 0;
-        if (i < n) {
+        if (i < n && i >= a0 && i < a1) {  // [a0, a1): the nodes whose forward edges this call emits (a Z-slab's own nodes)
             const uint32_t m = nb[i];
             if (__popc(m) >= 3 && (m >> 14)) {
                 uint32_t fm = m & ~((1u << 14) - 1u);
@@ -1649,8 +1650,8 @@ __global__ void __launch_bounds__(256) skb_junction_append_kernel(SkbGeom g, con
 static int g_skb_junction_append = 1;  // "junction_append": 0 = always count + scan + emit
 // returns 0, or 1 when the one-pass form does not apply (the caller counts, scans and emits)
 static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
-                               const uint32_t* nb, int64_t n, int32_t* ea, int32_t* eb, uint8_t* ek, int64_t cap,
-                               int32_t* counter, skb_stream_t s);
+                               const uint32_t* nb, int64_t n, int64_t a0, int64_t a1, int32_t* ea, int32_t* eb, uint8_t* ek,
+                               int64_t cap, int32_t* counter, skb_stream_t s);
 
 
 static int skb_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, int32_t lo, int32_t hi,
@@ -1676,14 +1677,14 @@ static int skb_table_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, in
 #define SKB_SMALL_CYCLE_NODES 4096
 #define SKB_SMALL_CYCLE_THREADS 1024
 
-struct SkbCollectUncoveredItem {  // over nodes that are not covered: chain voxels go to the list
+struct SkbCollectUncoveredItem {  // over nodes that are not covered: the chain voxels this rank owns go to the list
     const skb_i4* rec;
     const uint8_t* covered;
     int32_t* list;
     int32_t* counter;
-    int32_t cap;
+    int32_t cap, own0, own1;
     __device__ void operator()(int64_t v) const {
-        if (covered[v]) return;
+        if (covered[v] || (int32_t)v < own0 || (int32_t)v >= own1) return;
         if ((skb_ld_i4(rec + 2 * v).w & SKB_REC_DEG_MASK) != 2) return;
         const int32_t k = atomicAdd(counter, 1);
         if (k < cap) list[k] = (int32_t)v;
@@ -1695,8 +1696,12 @@ struct SkbSmallCycleSmem {
     int32_t par[SKB_SMALL_CYCLE_NODES];   // union by minimum, then the ring's minimum (local index) of every voxel
     int32_t cnt[SKB_SMALL_CYCLE_NODES];   // per ring minimum: voxels on the ring
     int32_t base[SKB_SMALL_CYCLE_NODES];  // per ring minimum: entry offset of the ring's path
+    int32_t first[SKB_SMALL_CYCLE_NODES]; // per ring minimum: voxels on the rings before it (offset into `order`)
+    double wv[SKB_SMALL_CYCLE_NODES];     // weight of the edge arriving at the voxel along the path
+    double vv[SKB_SMALL_CYCLE_NODES];     // the voxel's value (1.0 for boolean images)
     uint16_t l0[SKB_SMALL_CYCLE_NODES], l1[SKB_SMALL_CYCLE_NODES];  // local indices of the two neighbours
     uint16_t pos[SKB_SMALL_CYCLE_NODES];  // position on the path (the minimum is entry 0 and the closing entry)
+    uint16_t order[SKB_SMALL_CYCLE_NODES];  // voxels in path order, ring after ring
     uint8_t dir[SKB_SMALL_CYCLE_NODES];   // which neighbour precedes the voxel on the path (0: n0, 1: n1)
     uint32_t warp_a[32], warp_b[32];
     int32_t bad;
@@ -1713,18 +1718,43 @@ __device__ __forceinline__ int32_t skb_smem_find(int32_t* par, int32_t v) {
     return v;
 }
 
-__global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kernel(
-    const int32_t* __restrict__ list, const int32_t* __restrict__ counter, int32_t m, const skb_i4* __restrict__ rec,
-    const double* __restrict__ values, int32_t n_regular, int32_t* __restrict__ start_node, uint32_t* __restrict__ plen,
-    int32_t* __restrict__ pmin, int32_t* __restrict__ pindptr, int32_t* __restrict__ pidx, double* __restrict__ pdata,
-    double* __restrict__ pw, uint32_t* __restrict__ is_min, int32_t* __restrict__ out /* [0] cycles, [1] entries, [2] error */) {
+// what one launch writes: everything (one GPU), or -- in Z-slab mode, where the entry offsets of a rank's paths are only
+// known after an exchange -- the path heads first (into arrays of their own, ids from pid_base) and the entries later
+enum { SKB_CYC_ALL = 0, SKB_CYC_HEADS = 1, SKB_CYC_ENTRIES = 2 };
+
+struct SkbSmallCycleArgs {
+    const int32_t* list;      // uncovered chain voxels (local node ids), any order
+    const int32_t* counter;   // their number as counted on the device (must equal m)
+    int32_t m, mode;
+    const skb_i4* rec;
+    const double* values;     // node values or NULL
+    int32_t pid_base;         // id of the first ring's path: SKB_CYC_ALL: the number of regular paths
+    int32_t id_shift;         // global node id = local id + id_shift (0 on one GPU)
+    const int64_t* lin;       // Z-slabs: raveled index of every node (for the branch table), else NULL
+    int64_t lin_offset;
+    int32_t* start_node;
+    uint32_t* plen;
+    int32_t* pmin;
+    int32_t* pindptr;         // SKB_CYC_ALL: entry offsets, continued from pindptr[pid_base]; SKB_CYC_ENTRIES: the offsets to use
+    int32_t* pidx;
+    double* pdata;            // NULL: not written (boolean image whose paths.data was filled with ones)
+    double* pw;
+    uint32_t* is_min;
+    SkbAux* head_aux;         // Z-slabs: per path sums and end node, else NULL
+    int32_t* out;             // [0] rings, [1] entries, [2] error
+};
+
+__global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kernel(const SkbSmallCycleArgs A) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     SkbSmallCycleSmem& S = *(SkbSmallCycleSmem*)smem_raw;
+    constexpr int PER = SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = A.m;
+    const skb_i4* __restrict__ rec = A.rec;
     int n2 = 32;
     while (n2 < m) n2 <<= 1;
-    if (tid == 0) S.bad = (*counter != m) ? 1 : 0;
-    for (int i = tid; i < n2; i += SKB_SMALL_CYCLE_THREADS) S.u[i] = i < m ? list[i] : 0x7fffffff;
+    if (tid == 0) S.bad = (*A.counter != m) ? 1 : 0;
+    for (int i = tid; i < n2; i += SKB_SMALL_CYCLE_THREADS) S.u[i] = i < m ? A.list[i] : 0x7fffffff;
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -1785,16 +1815,16 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
         }
     }
     __syncthreads();
-    int32_t root_of[SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS];
+    int32_t root_of[PER];
 #pragma unroll
-    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
-        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid * PER + q;
         root_of[q] = i < m ? skb_smem_find(S.par, i) : -1;
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
-        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid * PER + q;
         if (i < m) {
             S.par[i] = root_of[q];
             atomicAdd(S.cnt + root_of[q], 1);
@@ -1802,11 +1832,11 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
     }
     __syncthreads();
     // rank of every ring minimum among the minima (path order), and the entry offsets: one block scan of two sums
-    uint32_t na = 0, nb = 0;  // rings, entries in this thread's four voxels
-    uint32_t ra[SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS], rb[SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS];
+    uint32_t na = 0, nb = 0;  // rings, entries in this thread's voxels
+    uint32_t ra[PER], rb[PER];
 #pragma unroll
-    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
-        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid * PER + q;
         ra[q] = na;
         rb[q] = nb;
         if (i < m && root_of[q] == i) {
@@ -1844,25 +1874,34 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
     __syncthreads();
     const uint32_t ea = ia - na + (warp ? S.warp_a[warp - 1] : 0u), eb = ib - nb + (warp ? S.warp_b[warp - 1] : 0u);
     const uint32_t n_cycles = S.warp_a[31], n_entries = S.warp_b[31];
-    const int32_t l_reg = pindptr[n_regular];  // entries of the regular paths (0 when there are none: the caller sets it)
+    const int32_t l_reg = A.mode == SKB_CYC_ALL ? A.pindptr[A.pid_base] : 0;  // entries of the regular paths
 #pragma unroll
-    for (int q = 0; q < SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS; ++q) {
-        const int i = tid * (SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS) + q;
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid * PER + q;
         if (i < m && root_of[q] == i) {
-            const int32_t pid = n_regular + (int32_t)(ea + ra[q]);
-            const int32_t off = l_reg + (int32_t)(eb + rb[q]);
-            start_node[pid] = S.u[i];
-            pmin[pid] = S.u[i];
-            plen[pid] = (uint32_t)S.cnt[i] + 1u;
-            pindptr[pid] = off;
-            is_min[S.u[i]] = 1u;  // a junction-free cycle is a component of its own (csr.py:909)
-            S.base[i] = off;
+            const int32_t pid = A.pid_base + (int32_t)(ea + ra[q]);
+            const int32_t gid = S.u[i] + A.id_shift;
+            if (A.mode != SKB_CYC_ENTRIES) {
+                A.start_node[pid] = gid;
+                A.pmin[pid] = gid;
+                A.plen[pid] = (uint32_t)S.cnt[i] + 1u;
+                A.is_min[S.u[i]] = 1u;  // a junction-free cycle is a component of its own (csr.py:909)
+            }
+            if (A.mode == SKB_CYC_ALL) {
+                A.pindptr[pid] = l_reg + (int32_t)(eb + rb[q]);
+                S.base[i] = l_reg + (int32_t)(eb + rb[q]);
+            } else if (A.mode == SKB_CYC_ENTRIES) {
+                S.base[i] = A.pindptr[pid];
+            }
+            S.first[i] = (int32_t)((eb + rb[q]) - (ea + ra[q]));
             // the walk: from the minimum towards its smaller neighbour (csr.py:369-386), positions in shared memory only
             int32_t prev = i, cur = S.l0[i] < S.l1[i] ? S.l0[i] : S.l1[i];
             S.pos[i] = 0;
+            S.order[S.first[i]] = (uint16_t)i;
             int32_t k = 1;
             while (cur != i && k <= m) {
                 S.pos[cur] = (uint16_t)k;
+                if (k < S.cnt[i]) S.order[S.first[i] + k] = (uint16_t)cur;
                 const int32_t c0 = S.l0[cur], c1 = S.l1[cur];
                 const bool from0 = c0 == prev;
                 S.dir[cur] = from0 ? 0 : 1;
@@ -1874,60 +1913,121 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
             if (k != S.cnt[i]) S.bad = 1;
         }
     }
-    if (tid == 0) pindptr[n_regular + (int32_t)n_cycles] = l_reg + (int32_t)n_entries;
+    if (tid == 0 && A.mode == SKB_CYC_ALL) A.pindptr[A.pid_base + (int32_t)n_cycles] = l_reg + (int32_t)n_entries;
     __syncthreads();
     for (int i = tid; i < m; i += SKB_SMALL_CYCLE_THREADS) {
         const int32_t r = S.par[i], node = S.u[i];
         const skb_d2 w = skb_ld_d2(rec + 2 * (int64_t)node + 1);
         const double w_in = S.dir[i] ? w.y : w.x;
-        const double val = values ? values[node] : 1.0;
-        const int64_t at = (int64_t)S.base[r] + S.pos[i];
-        pidx[at] = node;
-        if (pdata) pdata[at] = val;
-        pw[at] = r == i ? 0.0 : w_in;
-        if (r == i) {  // the ring closes on its minimum
-            const int64_t end = (int64_t)S.base[r] + S.cnt[r];
-            pidx[end] = node;
-            if (pdata) pdata[end] = val;
-            pw[end] = w_in;
+        const double val = A.values ? A.values[node] : 1.0;
+        S.wv[i] = w_in;
+        S.vv[i] = val;
+        if (A.mode != SKB_CYC_HEADS) {
+            const int64_t at = (int64_t)S.base[r] + S.pos[i];
+            A.pidx[at] = node + A.id_shift;
+            if (A.pdata) A.pdata[at] = val;
+            A.pw[at] = r == i ? 0.0 : w_in;
+            if (r == i) {  // the ring closes on its minimum
+                const int64_t end = (int64_t)S.base[r] + S.cnt[r];
+                A.pidx[end] = node + A.id_shift;
+                if (A.pdata) A.pdata[end] = val;
+                A.pw[end] = w_in;
+            }
+        }
+    }
+    if (A.head_aux && A.mode != SKB_CYC_ENTRIES) {  // Z-slabs: the sums the statistics are made of, in path order
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = tid * PER + q;
+            if (i < m && root_of[q] == i) {
+                SkbAux a;
+                a.sw = 0.0;
+                a.sx = S.vv[i];
+                a.sxx = S.vv[i] * S.vv[i];
+                for (int32_t k = 1; k < S.cnt[i]; ++k) {
+                    const int j = S.order[S.first[i] + k];
+                    a.sw += S.wv[j];
+                    a.sx += S.vv[j];
+                    a.sxx += S.vv[j] * S.vv[j];
+                }
+                a.sw += S.wv[i];
+                a.sx += S.vv[i];
+                a.sxx += S.vv[i] * S.vv[i];
+                a.end_lin = (A.lin ? A.lin[S.u[i]] : (int64_t)S.u[i]) + A.lin_offset;
+                a.end_node = S.u[i] + A.id_shift;
+                a.end_deg = 2;
+                a.end_key = 0;
+                a.pad = 0;
+                A.head_aux[A.pid_base + (int32_t)(ea + ra[q])] = a;
+            }
         }
     }
     if (tid == 0) {
-        out[0] = (int32_t)n_cycles;
-        out[1] = (int32_t)n_entries;
-        out[2] = S.bad;
+        A.out[0] = (int32_t)n_cycles;
+        A.out[1] = (int32_t)n_entries;
+        A.out[2] = S.bad;
     }
 }
 
-// list i32[m], out i32[4] (device).  Returns 0, or 1 when the case is not a small one (the caller runs the general path).
+static int skb_small_cycles_launch(const SkbSmallCycleArgs& a, skb_stream_t s) {
+    static uint8_t attr_set[SKB_MAX_DEV] = {};
+    SKB_TRY(skb_optin_smem(skb_small_cycles_kernel, sizeof(SkbSmallCycleSmem), attr_set));
+    skb_small_cycles_kernel<<<1, SKB_SMALL_CYCLE_THREADS, sizeof(SkbSmallCycleSmem), s>>>(a);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "small cycles launch");
+}
+
+// One GPU: list i32[m], out i32[4] (device).  Returns 0, or 1 when the case is not a small one (the caller runs the
+// general path).
 static int skb_cycles_small(const skb_i4* rec, const uint8_t* covered, int64_t n, int64_t m, const double* values,
                             int64_t n_regular, int32_t* start_node, uint32_t* plen, int32_t* pmin, int32_t* pindptr,
                             int32_t* pidx, double* pdata, double* pw, uint32_t* is_min, int32_t* list, int32_t* out,
                             skb_stream_t s) {
     if (m <= 0 || m > SKB_SMALL_CYCLE_NODES || !g_skb_small_cycles) return 1;
-    static uint8_t attr_set[SKB_MAX_DEV] = {};
-    SKB_TRY(skb_optin_smem(skb_small_cycles_kernel, sizeof(SkbSmallCycleSmem), attr_set));
     SKB_TRY(skb_fill_bytes(out, 0, 16, s));
-    SKB_TRY(skb_foreach_unmarked(n, covered, s, SkbCollectUncoveredItem{rec, covered, list, out + 3, (int32_t)m}));
-    skb_small_cycles_kernel<<<1, SKB_SMALL_CYCLE_THREADS, sizeof(SkbSmallCycleSmem), s>>>(
-        list, out + 3, (int32_t)m, rec, values, (int32_t)n_regular, start_node, plen, pmin, pindptr, pidx, pdata, pw, is_min, out);
-    SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "small cycles launch");
+    SKB_TRY(skb_foreach_unmarked(n, covered, s, SkbCollectUncoveredItem{rec, covered, list, out + 3, (int32_t)m, 0, 0x7fffffff}));
+    SkbSmallCycleArgs a{list, out + 3, (int32_t)m, SKB_CYC_ALL, rec, values, (int32_t)n_regular, 0, nullptr, 0, start_node, plen,
+                        pmin, pindptr, pidx, pdata, pw, is_min, nullptr, out};
+    return skb_small_cycles_launch(a, s);
+}
+
+// Z-slabs, rings inside this rank's slab.  Heads: the owned uncovered chain voxels are collected (list i32[m]) and the rings'
+// heads written to start_node / plen / pmin / head_aux[0 ...]; out i32[4] = rings, entries, error, voxels collected.
+static int skb_cycles_small_heads(const skb_i4* rec, const uint8_t* covered, int64_t n, int64_t m, int64_t own0, int64_t own1,
+                                  const double* values, const int64_t* lin, int64_t lin_offset, int64_t id_shift,
+                                  int32_t* start_node, uint32_t* plen, int32_t* pmin, uint32_t* is_min, void* head_aux,
+                                  int32_t* list, int32_t* out, skb_stream_t s) {
+    if (m <= 0 || m > SKB_SMALL_CYCLE_NODES || !g_skb_small_cycles) return 1;
+    SKB_TRY(skb_fill_bytes(out, 0, 16, s));
+    SKB_TRY(skb_foreach_unmarked(n, covered, s,
+                                 SkbCollectUncoveredItem{rec, covered, list, out + 3, (int32_t)m, (int32_t)own0, (int32_t)own1}));
+    SkbSmallCycleArgs a{list, out + 3, (int32_t)m, SKB_CYC_HEADS, rec, values, 0, (int32_t)id_shift, lin, lin_offset, start_node,
+                        plen, pmin, nullptr, nullptr, nullptr, nullptr, is_min, (SkbAux*)head_aux, out};
+    return skb_small_cycles_launch(a, s);
+}
+// ... and, once the entry offsets are known (gptr[pid_base + j] for the j-th ring), the entries
+static int skb_cycles_small_entries(const skb_i4* rec, int64_t m, const double* values, int64_t id_shift, int64_t pid_base,
+                                    int32_t* gptr, int32_t* pidx, double* pdata, double* pw, const int32_t* list,
+                                    int32_t* out, skb_stream_t s) {
+    SkbSmallCycleArgs a{list, out + 3, (int32_t)m, SKB_CYC_ENTRIES, rec, values, (int32_t)pid_base, (int32_t)id_shift, nullptr, 0,
+                        nullptr, nullptr, nullptr, gptr, pidx, pdata, pw, nullptr, nullptr, out};
+    return skb_small_cycles_launch(a, s);
 }
 
 #include "skb_api.inl"
 
 static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
-                               const uint32_t* nb, int64_t n, int32_t* ea, int32_t* eb, uint8_t* ek, int64_t cap,
-                               int32_t* counter, skb_stream_t s) {
-    if (!g_skb_junction_append || n <= 0 || cap <= 0) return 1;
+                               const uint32_t* nb, int64_t n, int64_t a0, int64_t a1, int32_t* ea, int32_t* eb, uint8_t* ek,
+                               int64_t cap, int32_t* counter, skb_stream_t s) {
+    if (!g_skb_junction_append || !g_skb_mst_keys || n <= 0 || cap <= 0) return 1;  // the keyed Boruvka needs no edge order
     SKB_TRY(skb_check_geom(ndim, shape));
     SKB_TRY(skb_fill_bytes(counter, 0, 4, s));
     int64_t blocks = (n + 255) / 256;
     const int64_t max_blocks = (int64_t)skb_sm_count() * 16;
     if (blocks > max_blocks) blocks = max_blocks;
-    skb_junction_append_kernel<<<(unsigned)blocks, 256, 0, s>>>(skb_make_geom(ndim, shape), bits, pre256, lin, nb, n, ea, eb, ek,
-                                                                cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap, counter);
+    skb_junction_append_kernel<<<(unsigned)blocks, 256, 0, s>>>(skb_make_geom(ndim, shape), bits, pre256, lin, nb, n, a0, a1, ea, eb,
+                                                                ek, cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap, counter);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "junction append launch");
 }

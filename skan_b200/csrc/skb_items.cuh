@@ -1631,6 +1631,25 @@ struct SkbSlabSkelFinalItem {  // skeleton ids of the paths headed on this rank,
     }
 };
 
+struct SkbCopyCycleHeadsItem {  // over the rings a rank heads: their heads move behind the regular paths' (ids pid_base + j)
+    const int32_t* t_start;
+    const uint32_t* t_plen;
+    const int32_t* t_pmin;
+    const SkbAux* t_aux;
+    int32_t pid_base;
+    int32_t* start_node;
+    uint32_t* plen;
+    int32_t* pmin;
+    SkbAux* head_aux;
+    SKB_HD void operator()(int64_t j) const {
+        const int64_t p = pid_base + j;
+        start_node[p] = t_start[j];
+        plen[p] = t_plen[j];
+        pmin[p] = t_pmin[j];
+        head_aux[p] = t_aux[j];
+    }
+};
+
 struct SkbFillF64Item {  // out[i] = v (paths.data of a boolean image is all ones: one coalesced fill)
     double* out;
     double v;

@@ -13,6 +13,7 @@
 
 #define SKB_RUN_NEED_MORE 1
 #define SKB_MASK_PAD 16  // zero words in front of the mask (one 128-byte line)
+#define SKB_SMALL_CYCLE_LIMIT 4096  // uncovered chain voxels one thread block handles (skb_small_cycles_kernel)
 
 // indices into skb_run_result.off (byte offsets into the `out` arena; -1 = absent)
 enum {
@@ -344,7 +345,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
             // Boruvka launch reads their number from that counter while it travels to the host
             take_junction(cap);
             if (work.ok) {
-                int r = skb_junction_append(bits, pre256, ndim, prm->shape, lin, nb, N, ea, eb, ek, cap, flag + 3, s);
+                int r = skb_junction_append(bits, pre256, ndim, prm->shape, lin, nb, N, 0, N, ea, eb, ek, cap, flag + 3, s);
                 if (r < 0) return r;
                 appended = r == 0;
             }

@@ -199,6 +199,7 @@ struct skb_slab_result {
     int64_t off[32];
     int64_t work_need, out_need, exchange_need;
     int64_t host_ns[16];  // host clock at the section boundaries (the sections end in a synchronisation), from the call's start
+    int64_t dev_ns[16];   // time_sweep == 2: device time of every section (events on the stream at the same boundaries)
 };
 
 #define SKB_SNEED(cond)                                                        \
@@ -291,10 +292,22 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     int64_t nsync = 0, nexch = 0;
     const double t_call = skb_now_s();
     int n_mark = 0;
-    for (int i = 0; i < 16; ++i) res->host_ns[i] = 0;
-#define SKB_HOST_MARK()                                                                   \
-    do {                                                                                  \
-        if (n_mark < 16) res->host_ns[n_mark++] = (int64_t)((skb_now_s() - t_call) * 1e9);  \
+    for (int i = 0; i < 16; ++i) res->host_ns[i] = res->dev_ns[i] = 0;
+    const bool dev_clock = prm->time_sweep == 2;
+    uint8_t dev_marked[16] = {};
+    if (dev_clock) {
+        SKB_TRY(skb_stage_mark(0, s));
+        dev_marked[0] = 1;
+    }
+#define SKB_HOST_MARK()                                                                         \
+    do {                                                                                        \
+        if (n_mark < 15) {                                                                      \
+            res->host_ns[n_mark++] = (int64_t)((skb_now_s() - t_call) * 1e9);                     \
+            if (dev_clock) {                                                                    \
+                SKB_TRY(skb_stage_mark(n_mark, s));                                             \
+                dev_marked[n_mark] = 1;                                                         \
+            }                                                                                   \
+        }                                                                                       \
     } while (0)
     for (int i = 0; i < 32; ++i) res->counts[i] = 0;
     for (int i = 0; i < 32; ++i) res->off[i] = -1;
@@ -433,8 +446,14 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     const int64_t N_k = own1 - own0;
     SKB_HOST_MARK();
     // ---- junction MST on the junction edges of the whole volume ----------------------------------------------
-    SKB_TRY(skb_junction_edge_count(bits, pre256, 3, shape, lin, nb, Ne, own0, own1, jcount, s));
-    SKB_TRY(skb_scan_u32_impl(jcount, jcount, Ne, scratch, s));
+    bool counted = false;  // jcount holds the scanned per-node edge counts (count + scan + emit form)
+    auto count_edges = [&]() -> int {
+        if (counted) return 0;
+        SKB_TRY(skb_junction_edge_count(bits, pre256, 3, shape, lin, nb, Ne, own0, own1, jcount, s));
+        SKB_TRY(skb_scan_u32_impl(jcount, jcount, Ne, scratch, s));
+        counted = true;
+        return 0;
+    };
     // The junction edges of every rank go to every rank.  With a capacity learnt from the previous call (the largest
     // per-rank count, plus slack: the same number on every rank) the edges are emitted straight away and ONE
     // synchronisation + exchange carries the counts and doubles as the barrier of the data; without one (first call,
@@ -455,8 +474,9 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         }
         return 0;
     };
+    const int32_t* nej_src = nullptr;  // where the number of this rank's edges is: the scan's total, or the append counter
     auto fetch_nej = [&]() -> int {
-        const int32_t* ptrs[1] = {(const int32_t*)jcount + Ne};
+        const int32_t* ptrs[1] = {nej_src};
         SKB_SFETCH(1, ptrs, vals);
         nej_k = vals[0];
         return 0;
@@ -472,6 +492,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     bool speculative = comm->hint_max_e > 0;
     const int64_t work_mark_j = work.off, xoff_mark_j = xoff;
     if (!speculative) {
+        SKB_TRY(count_edges());
+        nej_src = (const int32_t*)jcount + Ne;
         SKB_TRY(fetch_nej());
         SKB_TRY(exchange_counts());
     }
@@ -495,10 +517,22 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         tree = work.take<uint8_t>(nej_rows);
         SKB_SNEED(work.ok);
         SKB_TRY(skb_fill_bytes(ex.mine(0), 0xff, (size_t)ex.cap * 4, s));  // a < 0 marks the padding rows
-        if (nej_k != 0)
-            SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, 3, shape, lin, nb, jcount, Ne, prm->wtab, values, 0, prm->dtype,
-                                               (int32_t*)ex.mine(0), (int32_t*)ex.mine(1), (uint8_t*)ex.mine(3),
-                                               (uint64_t*)ex.mine(2), ex.cap, s));
+        bool appended = false;
+        if (speculative) {  // one unordered pass (the keyed Boruvka needs no edge order), the count from its atomic counter
+            int r = skb_junction_append(bits, pre256, 3, shape, lin, nb, Ne, own0, own1, (int32_t*)ex.mine(0),
+                                        (int32_t*)ex.mine(1), (uint8_t*)ex.mine(3), ex.cap, small + 11, s);
+            if (r < 0) return r;
+            appended = r == 0;
+            if (appended) nej_src = small + 11;
+        }
+        if (!appended) {
+            SKB_TRY(count_edges());
+            nej_src = (const int32_t*)jcount + Ne;
+            if (nej_k != 0)
+                SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, 3, shape, lin, nb, jcount, Ne, prm->wtab, values, 0,
+                                                   prm->dtype, (int32_t*)ex.mine(0), (int32_t*)ex.mine(1),
+                                                   (uint8_t*)ex.mine(3), (uint64_t*)ex.mine(2), ex.cap, s));
+        }
         if (speculative) {
             SKB_TRY(fetch_nej());        // the edges are complete when their count has arrived (stream order)
             SKB_TRY(exchange_counts());  // ... and every peer's are when its row of counts has
@@ -803,7 +837,33 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         SKB_SFETCH(2, ptrs, vals);
         Pc = vals[0];
         if (vals[1]) return skb_fail("slab mode: the uncovered chain voxels do not form closed rings");
-    } else if (!ring_mode && n_uncovered > 0) {
+    }
+    // rings inside this rank's slab: few uncovered chain voxels (the usual case) are one thread block's work -- heads now,
+    // entries once the exchange below has told where this rank's paths start
+    bool small_cycles = false;
+    int32_t *clist = nullptr, *t_start = nullptr, *t_pmin = nullptr;
+    uint32_t* t_plen = nullptr;
+    SkbAux* t_aux = nullptr;
+    if (!ring_mode && n_uncovered > 0 && n_uncovered <= SKB_SMALL_CYCLE_LIMIT) {
+        const int64_t pc_cap = n_uncovered / 3 + 1;  // a ring has at least three voxels
+        clist = work.take<int32_t>(n_uncovered);
+        t_start = work.take<int32_t>(pc_cap);
+        t_plen = work.take<uint32_t>(pc_cap);
+        t_pmin = work.take<int32_t>(pc_cap);
+        t_aux = work.take<SkbAux>(pc_cap);
+        SKB_SNEED(work.ok);
+        int r = skb_cycles_small_heads(rec, covered, Ne, n_uncovered, own0, own1, values, lin, ze0 * sz, id_shift, t_start,
+                                       t_plen, t_pmin, is_min, t_aux, clist, small + 12, s);
+        if (r < 0) return r;
+        if (r == 0) {
+            const int32_t* ptrs[2] = {small + 12, small + 14};
+            SKB_SFETCH(2, ptrs, vals);
+            if (vals[1]) return skb_fail("slab mode: the uncovered chain voxels do not form closed rings");
+            Pc = vals[0];
+            small_cycles = true;
+        }
+    }
+    if (!ring_mode && n_uncovered > 0 && !small_cycles) {
         int32_t* cpar = work.take<int32_t>(Ne1);
         uint32_t* startoff_b = work.take<uint32_t>(Ne + 1);
         SKB_SNEED(work.ok);
@@ -846,13 +906,16 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     int32_t* head_end = work.take<int32_t>(Pk1);
     SkbAux* head_aux = work.take<SkbAux>(Pk1);
     int32_t* pindptr = work.take<int32_t>(Pk + 1);
-    skb_i4* einfo_b = (Pc && !ring_mode) ? work.take<skb_i4>(Sb) : nullptr;
+    skb_i4* einfo_b = (Pc && !ring_mode && !small_cycles) ? work.take<skb_i4>(Sb) : nullptr;
     SKB_SNEED(work.ok && out.ok);
     SKB_TRY(skb_path_heads(su, rec, ranked, raux, sel, S, 0, 0, start_lo, id_shift, start_node, plen, pmin, nullptr,
                            head_end, head_aux, s));
     if (Pc && ring_mode)
         SKB_TRY(skb_foreach(ring_m, s, SkbRingHeadItem{ring_rec, ring_size, ring_oidx, (int32_t)P0, (int32_t)id_shift,
                                                       start_node, plen, pmin, is_min}));
+    else if (Pc && small_cycles)
+        SKB_TRY(skb_foreach(Pc, s, SkbCopyCycleHeadsItem{t_start, t_plen, t_pmin, t_aux, (int32_t)P0, start_node, plen, pmin,
+                                                        head_aux}));
     else if (Pc)
         SKB_TRY(skb_path_heads(sub, rec, rankedb, rauxb, selb, Sb, 1, P0, 0, id_shift, start_node, plen, pmin, einfo_b,
                                head_end, head_aux, s));
@@ -982,6 +1045,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         if (ring_mode)
             SKB_TRY(skb_foreach(ring_m, s, SkbRingWalkItem{ring_rec, (int32_t)ring_m, ring_oidx, (int32_t)P0, (int32_t)id_shift,
                                                           gptr, lin, ze0 * sz, pidx, pdata, pw, head_aux}));
+        else if (small_cycles)
+            SKB_TRY(skb_cycles_small_entries(rec, n_uncovered, values, id_shift, P0, gptr, pidx, pdata, pw, clist, small + 12, s));
         else
             SKB_TRY(skb_path_emit(indices, data, rec, sub, seb, rankedb, einfo_b, gptr, values, nullptr, id_shift, Sb, pidx,
                                   pdata, pw, s));
@@ -1050,6 +1115,11 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     res->off[SKB_SO_TF] = out_off(tf);
     res->off[SKB_SO_START_NODE] = out_off(start_node);
     SKB_HOST_MARK();
+    if (dev_clock) {  // dev_ns[i] = device time between boundary i and boundary i + 1
+        int64_t ns[16];
+        SKB_TRY(skb_stage_read(dev_marked, 16, ns));
+        for (int i = 0; i + 1 < 16; ++i) res->dev_ns[i] = ns[i + 1];
+    }
     res->counts[SKB_SC_SYNCS] = nsync;
     res->counts[SKB_SC_EXCHANGES] = nexch;
     res->work_need = work.need;

@@ -268,7 +268,7 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         prm.halo_exchange = 1
         prm.ze0 = int(z0) - (2 if z0 > 0 else 0)
         prm.nz_ext = (int(z1) + (2 if z1 < int(global_shape[0]) else 0)) - prm.ze0
-    prm.want_values, prm.time_sweep = int(not is_bool), int(bool(TIME_SWEEP))
+    prm.want_values, prm.time_sweep = int(not is_bool), int(TIME_SWEEP)   # 0, 1 (sweep kernel) or 2 (device section clock)
     prm.wtab, prm.spacing_is_int, prm.stream = _wtabs[wkey].data_ptr(), int(sp_is_int), ctx.stream
     V = int(prm.nz_ext) * int(shape[1]) * int(shape[2])
     akey = (str(ctx.device), ctx.stream, id(ctx.lib))
@@ -322,6 +322,7 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
     for i, k in enumerate(_native.SLAB_SECTIONS):
         C['host_us'][k] = (int(res.host_ns[i]) - prev) / 1e3
         prev = int(res.host_ns[i])
+    C['dev_us'] = {k: int(res.dev_ns[i]) / 1e3 for i, k in enumerate(_native.SLAB_SECTIONS)}
     O = {k: int(res.off[i]) for k, i in _native.SLAB_OFF.items()}
     if C['paths_total'] == 0:
         raise ValueError('index pointer size 0 should be 1')

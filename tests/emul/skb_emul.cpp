@@ -152,9 +152,18 @@ static int skb_cycles_small(const skb_i4*, const uint8_t*, int64_t, int64_t, con
                             int32_t*, int32_t*, int32_t*, double*, double*, uint32_t*, int32_t*, int32_t*, skb_stream_t) {
     return 1;
 }
+static int skb_cycles_small_heads(const skb_i4*, const uint8_t*, int64_t, int64_t, int64_t, int64_t, const double*, const int64_t*,
+                                  int64_t, int64_t, int32_t*, uint32_t*, int32_t*, uint32_t*, void*, int32_t*, int32_t*,
+                                  skb_stream_t) {
+    return 1;
+}
+static int skb_cycles_small_entries(const skb_i4*, int64_t, const double*, int64_t, int64_t, int32_t*, int32_t*, double*, double*,
+                                    const int32_t*, int32_t*, skb_stream_t) {
+    return -2;
+}
 // one-pass junction edge emission and the packed-key Boruvka launch are CUDA kernels: the harness counts, scans, emits
 static int skb_junction_append(const uint64_t*, const uint32_t*, int, const int64_t*, const int64_t*, const uint32_t*, int64_t,
-                               int32_t*, int32_t*, uint8_t*, int64_t, int32_t*, skb_stream_t) {
+                               int64_t, int64_t, int32_t*, int32_t*, uint8_t*, int64_t, int32_t*, skb_stream_t) {
     return 1;
 }
 static int skb_mst_keys_run(const int32_t*, const int32_t*, const uint8_t*, const double*, int64_t, const int32_t*, int32_t*,
