@@ -40,9 +40,13 @@ int64_t skb_tile_voxels(void);             /* voxels per mask tile (16384) */
 int skb_set_option(const char* name, int64_t value); /* tunables with no effect on results: "emit_both_ways" (1,
                                                         default: skb_run_image's second walk writes every chain from
                                                         both of its ends, which halves its longest dependent-load
-                                                        chain; 0: from its head only), "splitter_bits" (1..12, default
-                                                        4: one chain voxel in 2^bits splits the chains into walks;
-                                                        every rank of a Z-slab run must use the same value).  Both
+                                                        chain; 0: from its head only), "splitter_bits" (0..12: one chain
+                                                        voxel in 2^bits splits the chains into walks; 0, the default:
+                                                        3 below 2.5 M nodes per GPU, else 4; every rank of a Z-slab
+                                                        run must use the same value), "small_cycles", "junction_append",
+                                                        "mst_keys", "mst_blocks_per_sm", "emit_blocks_per_sm" (A/B
+                                                        switches of round 2), "arena_guard" (debugging
+                                                        aid, see skb_debug_guard_offsets).  The
                                                         defaults were measured on B200 (profiles/r02_summary.md) */
 /* Debugging aid: after skb_set_option("arena_guard", 1) the runners leave a 256-byte gap behind every allocation they make
  * in the caller's arenas; this returns the number of gaps of the calling thread's last runner call and writes their byte

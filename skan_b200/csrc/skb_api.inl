@@ -189,13 +189,15 @@ static int skb_csr_emit_cap(const uint64_t* bits, const uint32_t* pre256, int nd
                             const double* wtab, const double* values, int height, int dtype, int32_t* indices,
                             double* data, skb_i4* rec, const int64_t* slab, int lin_splitters, uint32_t* startoff,
                             int32_t* par, int32_t* cmin, uint32_t* is_min, void* scratch, int64_t edge_cap,
-                            void* stream) {
+                            void* stream, int64_t split_population = 0) {
     skb_stream_t s = (skb_stream_t)stream;
     SKB_TRY(skb_check_geom(ndim, shape));
     if (height && !values) return skb_fail("height mode needs node values");
     SkbWeight wf{wtab, values, height, dtype};
+    // split_population: the node count the splitter density is chosen by (the runners pass it; every rank of a Z-slab run
+    // passes the same number); 0 = the fixed default
     SkbRecOut out{lin_splitters ? lin : nullptr, skb_make_slab(slab, n), rec, startoff, par, cmin, is_min,
-                  skb_option_split_shift()};
+                  skb_option_split_shift(split_population)};
     SkbCsrEmitItem it{skb_make_geom(ndim, shape), bits, pre256, lin, keep, indptr, wf, indices, data, rec ? 1 : 0, out,
                       edge_cap > 0x7fffffffLL ? 0x7fffffff : (int32_t)edge_cap};
     SKB_TRY(skb_foreach(n, s, it));

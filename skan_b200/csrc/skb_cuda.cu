@@ -106,14 +106,19 @@ static int skb_option_both_ways() {
 // "splitter_bits": the chain voxels whose hash has this many leading zero bits split the chains into walks
 // (4 = one in 16, the measured default: a walk kernel lasts as long as its longest walk, ~16 ln(starts) hops;
 // more splitters = shorter walks, more starts to rank)
-static int g_skb_split_bits = -1;
-static uint32_t skb_option_split_shift() {
+static int g_skb_split_bits = -1;  // -1: not set -> by the environment, else adaptive; >= 1: fixed by skb_set_option
+// population = nodes (per GPU) the walks will run over, 0 = unknown.  A walk kernel lasts as long as its longest walk
+// (~2^bits * ln(starts) dependent loads), whatever the volume: measured (profiles/r02_ab_walks_*.txt) 1/16 wins at
+// 7.5 M nodes (2048^3), 1/8 at 0.8 M (1024^3, a Z-slab of an eighth of 2048^3), where ranking the extra starts is cheap.
+static uint32_t skb_option_split_shift(int64_t population = 0) {
     if (g_skb_split_bits < 0) {
         const char* e = getenv("SKAN_B200_SPLITTER_BITS");
         const int v = e ? atoi(e) : 0;
-        g_skb_split_bits = (v >= 1 && v <= 12) ? v : 4;
+        g_skb_split_bits = (v >= 1 && v <= 12) ? v : 0;  // 0 = adaptive
     }
-    return 32u - (uint32_t)g_skb_split_bits;
+    int bits = g_skb_split_bits;
+    if (bits == 0) bits = (population > 0 && population < 2500000) ? 3 : 4;
+    return 32u - (uint32_t)bits;
 }
 
 // stepwise items (the chain walks: begin / step / finish): one item per thread.  A variant with persistent warps
@@ -2046,7 +2051,7 @@ int64_t skb_tile_voxels(void) { return SKB_TILE_VOX; }
 int skb_set_option(const char* name, int64_t value) {
     if (!name) return skb_fail("skb_set_option: null name");
     if (!strcmp(name, "splitter_bits")) {
-        if (value < 1 || value > 12) return skb_fail("skb_set_option: splitter_bits must be in 1..12");
+        if (value < 0 || value > 12) return skb_fail("skb_set_option: splitter_bits must be in 0..12 (0 = chosen by the node count)");
         g_skb_split_bits = (int)value;
         return 0;
     }

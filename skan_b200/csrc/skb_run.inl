@@ -433,7 +433,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
             if (work.ok && out.ok) {
                 SKB_TRY(skb_csr_emit_cap(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height,
                                          prm->dtype, indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min,
-                                         scratch, cap, s));
+                                         scratch, cap, s, N));
                 emitted = true;
                 ++noverlap;
             }
@@ -446,8 +446,9 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
             work.ok = out.ok = true;
             take_csr(E);
             SKB_NEED(work.ok && out.ok);
-            SKB_TRY(skb_csr_emit(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height,
-                                 prm->dtype, indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min, scratch, s));
+            SKB_TRY(skb_csr_emit_cap(bits, pre256, ndim, prm->shape, lin, keep, indptr, N, prm->wtab, values, height,
+                                     prm->dtype, indices, data, rec, nullptr, 0, startoff, cc_par, cc_min, is_min, scratch,
+                                     0x7fffffffLL, s, N));
         }
     }
     res->counts[SKB_C_EDGES] = E;

@@ -608,7 +608,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     uint32_t* is_min = work.take<uint32_t>(Ne + 1);
     SKB_SNEED(work.ok && out.ok);
     SKB_TRY(skb_csr_emit_cap(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
-                             rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, e_cap ? e_cap : 0x7fffffffLL, s));
+                             rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, e_cap ? e_cap : 0x7fffffffLL, s,
+                             N_total / world + 1));
     int64_t so[4], ei[2];
     for (int attempt = 0; attempt < 2; ++attempt) {
         const int32_t* ptrs[7] = {(const int32_t*)startoff + own0, (const int32_t*)startoff + own1,
@@ -629,8 +630,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         startoff = work.take<uint32_t>(Ne + 1);
         is_min = work.take<uint32_t>(Ne + 1);
         SKB_SNEED(work.ok && out.ok);
-        SKB_TRY(skb_csr_emit(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
-                             rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, s));
+        SKB_TRY(skb_csr_emit_cap(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
+                                 rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, 0x7fffffffLL, s, N_total / world + 1));
     }
     comm->hint_edges = E;
     const int64_t S = so[1] - so[0], SF = so[2] - so[0], SL0 = so[3] - so[0];

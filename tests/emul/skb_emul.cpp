@@ -142,8 +142,12 @@ static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*
 #define SKB_TILE_WORDS 256
 
 // options of skb_set_option that reach shared code
-static int g_skb_split_bits = 4;
-static uint32_t skb_option_split_shift() { return 32u - (uint32_t)g_skb_split_bits; }
+static int g_skb_split_bits = 0;  // adaptive, like the CUDA build
+static uint32_t skb_option_split_shift(int64_t population = 0) {
+    int bits = g_skb_split_bits;
+    if (bits == 0) bits = (population > 0 && population < 2500000) ? 3 : 4;
+    return 32u - (uint32_t)bits;
+}
 static int g_skb_both_ways = 1;
 static int g_skb_arena_guard = 0;
 static int skb_option_both_ways() { return g_skb_both_ways; }
@@ -193,7 +197,7 @@ int64_t skb_kernel_launches(void) { return 0; }
 int skb_set_option(const char* name, int64_t value) {  // the scheduling tunables of the CUDA build do nothing here
     if (name && !strcmp(name, "emit_both_ways")) g_skb_both_ways = value ? 1 : 0;
     if (name && !strcmp(name, "arena_guard")) g_skb_arena_guard = value ? 1 : 0;
-    if (name && !strcmp(name, "splitter_bits") && value >= 1 && value <= 12) g_skb_split_bits = (int)value;
+    if (name && !strcmp(name, "splitter_bits") && value >= 0 && value <= 12) g_skb_split_bits = (int)value;
     return 0;
 }
 
