@@ -395,7 +395,12 @@ int skb_skeleton_ids(const int32_t* pindptr, const int32_t* pidx, const int32_t*
 // pdata NULL: the image is boolean and every entry of paths.data is 1.0 (mean 1, stdev 0 without reading them)
 int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
                    double* mean, double* stdev, void* stream) {
+#ifdef SKB_HAVE_FUSED_LOOPS
+    SKB_TRY(skb_foreach(n_paths, (skb_stream_t)stream, SkbPathStatsItem{pindptr, pdata, pw, dist, mean, stdev, SKB_LONG_PATH}));
+    return skb_long_path_stats(pindptr, pdata, pw, n_paths, dist, mean, stdev, (skb_stream_t)stream);
+#else
     return skb_foreach(n_paths, (skb_stream_t)stream, SkbPathStatsItem{pindptr, pdata, pw, dist, mean, stdev});
+#endif
 }
 
 // the remaining columns of summarize() (csr.py:909-952)
@@ -603,7 +608,7 @@ int skb_slab_path_stats(const uint32_t* plen, const void* head_aux, int64_t n_pa
 // Skeleton.path_label_image (csr.py:776-790): image i64[V] must be zeroed by the caller
 int skb_path_label_image(const int32_t* pindptr, const int32_t* pidx, const int64_t* lin, int64_t n_paths,
                          int64_t* image, void* stream) {
-    return skb_foreach(n_paths, (skb_stream_t)stream, SkbLabelImageItem{pindptr, pidx, lin, image});
+    return skb_foreach(n_paths * 32, (skb_stream_t)stream, SkbLabelImageItem{pindptr, pidx, lin, image});
 }
 
 // ---- Sholl analysis (csr.py:1332-1390), see skb_sholl.cuh ------------------------------------------------

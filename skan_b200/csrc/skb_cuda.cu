@@ -2020,6 +2020,70 @@ static int skb_cycles_small_entries(const skb_i4* rec, int64_t m, const double* 
     return skb_small_cycles_launch(a, s);
 }
 
+// ------------------------------------------------------------------------------- statistics of very long paths
+// One thread block per path of more than SKB_LONG_PATH entries (the thread-per-path item skips those): every thread sums
+// the entries j = t, t + 256, ... in order, the 256 partial sums are combined in a fixed tree, so the result does not
+// depend on timing.  The order differs from the reference's left-to-right (distance) and pairwise (mean, stdev) sums:
+// agreement is to the rounding error of those sums themselves (~n eps), see DESIGN.md.
+__global__ void __launch_bounds__(256) skb_long_path_stats_kernel(const int32_t* __restrict__ pindptr,
+                                                                  const double* __restrict__ pdata,
+                                                                  const double* __restrict__ pw, int64_t n_paths,
+                                                                  double* dist, double* mean, double* stdev) {
+    __shared__ double red[3][256];
+    const int tid = threadIdx.x;
+    for (int64_t p = blockIdx.x; p < n_paths; p += gridDim.x) {
+        const int32_t s = pindptr[p], e = pindptr[p + 1];
+        if (e - s <= SKB_LONG_PATH) continue;  // the same decision in every thread of the block
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int32_t j = s + tid; j < e; j += 256) {
+            if (j > s) a += pw[j];
+            if (pdata) {
+                const double x = pdata[j];
+                b += x;
+                c += x * x;
+            }
+        }
+        red[0][tid] = a;
+        red[1][tid] = b;
+        red[2][tid] = c;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if (tid < d) {
+                red[0][tid] += red[0][tid + d];
+                red[1][tid] += red[1][tid + d];
+                red[2][tid] += red[2][tid + d];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const double n = (double)(e - s);
+            if (dist) dist[p] = red[0][0];
+            if (!pdata) {
+                if (mean) mean[p] = 1.0;
+                if (stdev) stdev[p] = 0.0;
+            } else {
+                const double m = red[1][0] / n;
+                if (mean) mean[p] = m;
+                if (stdev) {
+                    double var = red[2][0] / n - m * m;
+                    if (!(var > 0.0)) var = (var == var) ? 0.0 : var;
+                    stdev[p] = sqrt(var);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int skb_long_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
+                               double* mean, double* stdev, skb_stream_t s) {
+    if (n_paths <= 0) return 0;
+    int64_t blocks = n_paths < 4 * (int64_t)skb_sm_count() ? n_paths : 4 * (int64_t)skb_sm_count();
+    skb_long_path_stats_kernel<<<(unsigned)blocks, 256, 0, s>>>(pindptr, pdata, pw, n_paths, dist, mean, stdev);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "long path stats launch");
+}
+
 #include "skb_api.inl"
 
 static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,

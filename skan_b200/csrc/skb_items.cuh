@@ -1960,6 +1960,9 @@ SKB_HD double skb_np_reduceat(const Load& ld, int64_t s, int64_t n) {
     return first + skb_np_pairwise(ld, s + 1, n - 1);
 }
 
+// Paths of more than SKB_LONG_PATH entries are left to skb_long_path_stats_kernel (one thread block per path, sums in a
+// fixed tree order) in the CUDA build, so that a single 10^7-voxel spiral is not one thread's serial loop.
+#define SKB_LONG_PATH 32768
 struct SkbPathStatsItem {  // over paths
     const int32_t* pindptr;
     const double* pdata;
@@ -1967,8 +1970,10 @@ struct SkbPathStatsItem {  // over paths
     double* dist;   // may be null
     double* mean;   // may be null
     double* stdev;  // may be null
+    int32_t max_len = 0x7fffffff;  // longer paths are skipped here
     SKB_HD void operator()(int64_t p) const {
         int32_t s = pindptr[p], e = pindptr[p + 1];
+        if (e - s > max_len) return;
         if (dist) {
             double acc = 0.0;  // left to right over the path's edges, csr.py:971-977
             for (int32_t j = s + 1; j < e; ++j) acc += pw[j];
@@ -2084,13 +2089,14 @@ struct SkbBranchItem {
 
 // path_label_image (csr.py:776-790): every path writes id+1 at its voxels; the reference loops
 // over paths in order, so where paths share a voxel (junctions) the highest path id wins.
-struct SkbLabelImageItem {
+struct SkbLabelImageItem {  // over (path, lane): 32 items share a path, so that one very long path is not one thread's loop
     const int32_t* pindptr;
     const int32_t* pidx;
     const int64_t* lin;
     int64_t* image;  // pre-zeroed, V entries
-    SKB_HD void operator()(int64_t p) const {
-        for (int32_t j = pindptr[p]; j < pindptr[p + 1]; ++j) {
+    SKB_HD void operator()(int64_t i) const {
+        const int64_t p = i >> 5;
+        for (int32_t j = pindptr[p] + (int32_t)(i & 31); j < pindptr[p + 1]; j += 32) {
             int64_t* dst = image + lin[pidx[j]];
 #if defined(__CUDA_ARCH__)
             atomicMax((long long*)dst, (long long)(p + 1));

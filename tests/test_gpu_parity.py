@@ -300,3 +300,30 @@ def test_junction_free_cycles_small_and_general_path(small):
         compare_with_oracle(vol, (0.5, 0.1, 0.1))
     finally:
         lib.call('skb_set_option', b'small_cycles', 1)
+
+
+def test_one_very_long_path():
+    """A single chain of ~10^6 voxels (a serpentine): statistics of a path longer than 32768 entries are summed by one thread
+    block in a fixed tree order, the label image by 32 lanes per path; integer results stay bit-exact, the fp64 sums agree
+    with the reference's left-to-right / pairwise sums to the rounding error of those sums (1e-11 here)."""
+    import time
+    n = 1449
+    img = long_chain_image('serpentine', n)
+    rng = np.random.default_rng(8)
+    valued = (img * (rng.random(img.shape) + 0.5)).astype(np.float64)
+    ref = orc.OracleSkeleton(valued, spacing=(1.0, 0.7))
+    rs = orc.summarize(ref)
+    assert ref.n_paths == 1 and ref.paths.indices.size > 1_000_000
+    dev = torch.from_numpy(valued).cuda()
+    skan_b200.Skeleton(dev, spacing=(1.0, 0.7))                      # warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sk = skan_b200.Skeleton(dev, spacing=(1.0, 0.7))
+    df = skan_b200.summarize(sk, separator='_')
+    dt = time.perf_counter() - t0
+    assert np.array_equal(sk.paths.indices, ref.paths.indices)
+    for k in ('branch_distance', 'mean_pixel_value', 'euclidean_distance'):
+        np.testing.assert_allclose(df[k].to_numpy(), rs[k], rtol=1e-11, err_msg=k)
+    np.testing.assert_allclose(df['stdev_pixel_value'].to_numpy() ** 2, rs['stdev_pixel_value'] ** 2, rtol=1e-9)
+    assert np.array_equal(sk.path_label_image(), ref.path_label_image())
+    assert dt < 0.5, f'{dt:.3f} s for one long path'
