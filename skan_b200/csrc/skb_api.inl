@@ -52,6 +52,12 @@ static SkbSlab skb_make_slab(const int64_t* v, int64_t n) {
     return sl;
 }
 
+// one logical thread per item i < *n_ptr (a count in device memory), launched over `cap` items
+template <typename F>
+static int skb_foreach_n(int64_t cap, const int32_t* n_ptr, skb_stream_t s, F f) {
+    return skb_foreach(cap, s, SkbBounded<F>{f, n_ptr});
+}
+
 extern "C" {
 
 int skb_abi_version(void) { return 1; }

@@ -394,18 +394,32 @@ static unsigned int g_skb_scan_epoch = 0;
 __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(const uint32_t* in, int64_t n,
                                                                              uint32_t* out,
                                                                              unsigned long long* scratch,
-                                                                             unsigned long long epoch, int64_t nb) {
+                                                                             unsigned long long epoch, int64_t nb,
+                                                                             const int32_t* n_ptr, uint32_t* total_out) {
+    // n_ptr != NULL: the length is read on the device (at most n, the capacity the grid was sized by); total_out != NULL
+    // receives the total as well (a fixed address, where out[n] is not one)
     __shared__ int64_t s_tile;
     __shared__ uint32_t s_excl;
     unsigned int* counter = (unsigned int*)scratch;
     unsigned long long* status = scratch + 1;
     if (threadIdx.x == 0) {
         unsigned int t = atomicAdd(counter, 1u);
-        if (t == (unsigned int)(nb - 1)) *counter = 0u;  // every tile has been handed out: reset for the next scan
+        if (t == gridDim.x - 1) *counter = 0u;  // every tile has been handed out: reset for the next scan
         s_tile = t;
     }
     __syncthreads();
     const int64_t tile = s_tile;
+    if (n_ptr) {
+        int64_t m = *n_ptr;
+        if (m < 0) m = 0;
+        if (m < n) n = m;
+        nb = (n + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
+        if (n == 0 && tile == 0 && threadIdx.x == 0) {
+            out[0] = 0u;
+            if (total_out) *total_out = 0u;
+        }
+        if (tile >= nb) return;  // the same decision in every thread of the block
+    }
     const int64_t base = tile * SKB_SCAN_TILE + (int64_t)threadIdx.x * SKB_SCAN_ITEMS;
     uint32_t v[SKB_SCAN_ITEMS];
     uint32_t acc = 0;
@@ -479,18 +493,31 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
             ex += v[j];
         }
     }
-    if (tile == nb - 1 && threadIdx.x == SKB_SCAN_THREADS - 1) out[n] = ex;
+    if (tile == nb - 1 && threadIdx.x == SKB_SCAN_THREADS - 1) {
+        out[n] = ex;
+        if (total_out) *total_out = ex;
+    }
 }
 
-static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, skb_stream_t s) {
+// n_ptr (may be NULL): the length is *n_ptr, read on the device, at most n; total_out (may be NULL): also gets the total
+static int skb_scan_u32_dev(const uint32_t* in, uint32_t* out, int64_t n, const int32_t* n_ptr, uint32_t* total_out,
+                            void* scratch, skb_stream_t s) {
     if (n < 0) return skb_fail("scan: negative length");
-    if (n == 0) return skb_cuda_check(cudaMemsetAsync(out, 0, sizeof(uint32_t), s), "scan memset");
+    if (n == 0) {
+        SKB_CUDA(cudaMemsetAsync(out, 0, sizeof(uint32_t), s));
+        if (total_out) SKB_CUDA(cudaMemsetAsync(total_out, 0, sizeof(uint32_t), s));
+        return 0;
+    }
     int64_t nb = (n + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
     unsigned long long epoch = (unsigned long long)(__atomic_add_fetch(&g_skb_scan_epoch, 1u, __ATOMIC_RELAXED) & 0x3fffffffu);
     if (epoch == 0) epoch = (unsigned long long)(__atomic_add_fetch(&g_skb_scan_epoch, 1u, __ATOMIC_RELAXED) & 0x3fffffffu);
-    skb_scan_lookback_kernel<<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, out, (unsigned long long*)scratch, epoch, nb);
+    skb_scan_lookback_kernel<<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, out, (unsigned long long*)scratch, epoch, nb,
+                                                                      n_ptr, total_out);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "scan launch");
+}
+static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, skb_stream_t s) {
+    return skb_scan_u32_dev(in, out, n, nullptr, nullptr, scratch, s);
 }
 // ------------------------------------------------------------------------------- mask sweep
 // The only V-proportional pass (replaces image.astype(bool), np.pad and both np.flatnonzero
@@ -1525,7 +1552,8 @@ __device__ __forceinline__ void skb_rank_rounds(cg::grid_group& grid, Jump jump,
 
 __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_rank_coop_kernel(skb_i4* b0, skb_i4* b1, SkbAux* a0,
                                                                          SkbAux* a1, int64_t n, int32_t lo,
-                                                                         int32_t hi, int32_t* flags) {
+                                                                         int32_t hi, int32_t* flags, const int32_t* n_ptr) {
+    if (n_ptr && *n_ptr < n) n = *n_ptr;  // the number of starts in device memory
     // flags[3] == 0: the list-following pass (SkbRankWalkItem) finished every list, nothing to do.  Every
     // thread reads the same value: nobody writes flags[3] before the last grid barrier below.
     if (*(volatile int32_t*)(flags + 3) == 0) return;
@@ -1593,7 +1621,12 @@ __global__ void __launch_bounds__(256) skb_junction_append_kernel(SkbGeom g, con
                                                                   const uint32_t* __restrict__ nb, int64_t n,
                                                                   int64_t a0, int64_t a1, int32_t* __restrict__ ea,
                                                                   int32_t* __restrict__ eb, uint8_t* __restrict__ ek,
-                                                                  uint32_t cap, int32_t* counter) {
+                                                                  uint32_t cap, int32_t* counter, const int32_t* n_ptr) {
+    if (n_ptr) {  // the node count in device memory (at most n, the capacity of the node arrays)
+        const int64_t nd = *n_ptr;
+        if (nd < n) n = nd;
+        if (a1 > n) a1 = n;
+    }
     __shared__ uint32_t warp_tot[8];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1656,12 +1689,12 @@ static int g_skb_junction_append = 1;  // "junction_append": 0 = always count + 
 // returns 0, or 1 when the one-pass form does not apply (the caller counts, scans and emits)
 static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
                                const uint32_t* nb, int64_t n, int64_t a0, int64_t a1, int32_t* ea, int32_t* eb, uint8_t* ek,
-                               int64_t cap, int32_t* counter, skb_stream_t s);
+                               int64_t cap, int32_t* counter, skb_stream_t s, const int32_t* n_ptr = nullptr);
 
 
 static int skb_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, int32_t lo, int32_t hi,
-                        int32_t* flag, skb_stream_t s) {
-    void* args[] = {&b0, &b1, &a0, &a1, &n, &lo, &hi, &flag};
+                        int32_t* flag, skb_stream_t s, const int32_t* n_ptr = nullptr) {
+    void* args[] = {&b0, &b1, &a0, &a1, &n, &lo, &hi, &flag, &n_ptr};
     return skb_coop_launch(skb_rank_coop_kernel, n, args, s);
 }
 
@@ -1688,8 +1721,10 @@ struct SkbCollectUncoveredItem {  // over nodes that are not covered: the chain 
     int32_t* list;
     int32_t* counter;
     int32_t cap, own0, own1;
+    const int32_t* n_ptr = nullptr;  // the node count in device memory: nodes beyond it do not exist
     __device__ void operator()(int64_t v) const {
         if (covered[v] || (int32_t)v < own0 || (int32_t)v >= own1) return;
+        if (n_ptr && v >= (int64_t)*n_ptr) return;
         if ((skb_ld_i4(rec + 2 * v).w & SKB_REC_DEG_MASK) != 2) return;
         const int32_t k = atomicAdd(counter, 1);
         if (k < cap) list[k] = (int32_t)v;
@@ -1747,6 +1782,9 @@ struct SkbSmallCycleArgs {
     uint32_t* is_min;
     SkbAux* head_aux;         // Z-slabs: per path sums and end node, else NULL
     int32_t* out;             // [0] rings, [1] entries, [2] error
+    const int32_t* m_ptr = nullptr;         // the number of voxels in device memory (overrides m; more than the list holds:
+                                            // error 2, nothing written)
+    const int32_t* pid_base_ptr = nullptr;  // the number of regular paths in device memory (overrides pid_base)
 };
 
 __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kernel(const SkbSmallCycleArgs A) {
@@ -1754,11 +1792,32 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
     SkbSmallCycleSmem& S = *(SkbSmallCycleSmem*)smem_raw;
     constexpr int PER = SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m = A.m;
+    int m = A.m;
+    if (A.m_ptr) {
+        const int32_t md = *A.m_ptr;
+        if (md > SKB_SMALL_CYCLE_NODES || md < 0) {  // not a small case: the caller goes the general way
+            if (tid == 0) {
+                A.out[0] = 0;
+                A.out[1] = 0;
+                A.out[2] = 2;
+            }
+            return;
+        }
+        m = md;
+    }
+    const int32_t pid_base = A.pid_base_ptr ? *A.pid_base_ptr : A.pid_base;
     const skb_i4* __restrict__ rec = A.rec;
     int n2 = 32;
     while (n2 < m) n2 <<= 1;
     if (tid == 0) S.bad = (*A.counter != m) ? 1 : 0;
+    if (m == 0) {  // (device-resident count) nothing to do
+        if (tid == 0) {
+            A.out[0] = 0;
+            A.out[1] = 0;
+            A.out[2] = S.bad;
+        }
+        return;
+    }
     for (int i = tid; i < n2; i += SKB_SMALL_CYCLE_THREADS) S.u[i] = i < m ? A.list[i] : 0x7fffffff;
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1)
@@ -1879,12 +1938,12 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
     __syncthreads();
     const uint32_t ea = ia - na + (warp ? S.warp_a[warp - 1] : 0u), eb = ib - nb + (warp ? S.warp_b[warp - 1] : 0u);
     const uint32_t n_cycles = S.warp_a[31], n_entries = S.warp_b[31];
-    const int32_t l_reg = A.mode == SKB_CYC_ALL ? A.pindptr[A.pid_base] : 0;  // entries of the regular paths
+    const int32_t l_reg = A.mode == SKB_CYC_ALL ? A.pindptr[pid_base] : 0;  // entries of the regular paths
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
         const int i = tid * PER + q;
         if (i < m && root_of[q] == i) {
-            const int32_t pid = A.pid_base + (int32_t)(ea + ra[q]);
+            const int32_t pid = pid_base + (int32_t)(ea + ra[q]);
             const int32_t gid = S.u[i] + A.id_shift;
             if (A.mode != SKB_CYC_ENTRIES) {
                 A.start_node[pid] = gid;
@@ -1918,7 +1977,7 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
             if (k != S.cnt[i]) S.bad = 1;
         }
     }
-    if (tid == 0 && A.mode == SKB_CYC_ALL) A.pindptr[A.pid_base + (int32_t)n_cycles] = l_reg + (int32_t)n_entries;
+    if (tid == 0 && A.mode == SKB_CYC_ALL) A.pindptr[pid_base + (int32_t)n_cycles] = l_reg + (int32_t)n_entries;
     __syncthreads();
     for (int i = tid; i < m; i += SKB_SMALL_CYCLE_THREADS) {
         const int32_t r = S.par[i], node = S.u[i];
@@ -1964,7 +2023,7 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
                 a.end_deg = 2;
                 a.end_key = 0;
                 a.pad = 0;
-                A.head_aux[A.pid_base + (int32_t)(ea + ra[q])] = a;
+                A.head_aux[pid_base + (int32_t)(ea + ra[q])] = a;
             }
         }
     }
@@ -2028,7 +2087,9 @@ static int skb_cycles_small_entries(const skb_i4* rec, int64_t m, const double* 
 __global__ void __launch_bounds__(256) skb_long_path_stats_kernel(const int32_t* __restrict__ pindptr,
                                                                   const double* __restrict__ pdata,
                                                                   const double* __restrict__ pw, int64_t n_paths,
-                                                                  double* dist, double* mean, double* stdev) {
+                                                                  double* dist, double* mean, double* stdev,
+                                                                  const int32_t* n_ptr) {
+    if (n_ptr && *n_ptr < n_paths) n_paths = *n_ptr;  // the number of paths in device memory
     __shared__ double red[3][256];
     const int tid = threadIdx.x;
     for (int64_t p = blockIdx.x; p < n_paths; p += gridDim.x) {
@@ -2076,10 +2137,10 @@ __global__ void __launch_bounds__(256) skb_long_path_stats_kernel(const int32_t*
 }
 
 static int skb_long_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
-                               double* mean, double* stdev, skb_stream_t s) {
+                               double* mean, double* stdev, skb_stream_t s, const int32_t* n_ptr = nullptr) {
     if (n_paths <= 0) return 0;
     int64_t blocks = n_paths < 4 * (int64_t)skb_sm_count() ? n_paths : 4 * (int64_t)skb_sm_count();
-    skb_long_path_stats_kernel<<<(unsigned)blocks, 256, 0, s>>>(pindptr, pdata, pw, n_paths, dist, mean, stdev);
+    skb_long_path_stats_kernel<<<(unsigned)blocks, 256, 0, s>>>(pindptr, pdata, pw, n_paths, dist, mean, stdev, n_ptr);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "long path stats launch");
 }
@@ -2088,7 +2149,7 @@ static int skb_long_path_stats(const int32_t* pindptr, const double* pdata, cons
 
 static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
                                const uint32_t* nb, int64_t n, int64_t a0, int64_t a1, int32_t* ea, int32_t* eb, uint8_t* ek,
-                               int64_t cap, int32_t* counter, skb_stream_t s) {
+                               int64_t cap, int32_t* counter, skb_stream_t s, const int32_t* n_ptr) {
     if (!g_skb_junction_append || !g_skb_mst_keys || n <= 0 || cap <= 0) return 1;  // the keyed Boruvka needs no edge order
     SKB_TRY(skb_check_geom(ndim, shape));
     SKB_TRY(skb_fill_bytes(counter, 0, 4, s));
@@ -2096,7 +2157,7 @@ static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int
     const int64_t max_blocks = (int64_t)skb_sm_count() * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     skb_junction_append_kernel<<<(unsigned)blocks, 256, 0, s>>>(skb_make_geom(ndim, shape), bits, pre256, lin, nb, n, a0, a1, ea, eb,
-                                                                ek, cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap, counter);
+                                                                ek, cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap, counter, n_ptr);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "junction append launch");
 }

@@ -284,6 +284,16 @@ SKB_HD void skb_for_neighbors(const SkbGeom& g, const uint64_t* bits, const uint
     }
 }
 
+// an item whose range ends at a count that lives in device memory: launched over a capacity, does nothing beyond *n
+template <typename F>
+struct SkbBounded {
+    F f;
+    const int32_t* n;
+    SKB_HD void operator()(int64_t i) const {
+        if (i < (int64_t)*n) f(i);
+    }
+};
+
 // ---- stage: raw 3^d neighbourhood mask (csr.py:122-144, evaluated per foreground voxel) ----
 // 27-bit mask of the foreground neighbours of voxel r = (z, y, x) (local coordinates of this volume / slab)
 SKB_HD uint32_t skb_raw_nb_mask(const SkbGeom& g, const uint64_t* bits, int64_t r, int32_t z, int32_t y, int32_t x,
@@ -1414,9 +1424,11 @@ struct SkbCcPathIdItem {  // over all paths
     const int32_t* cmin;
     const uint32_t* rank;  // exclusive scan of is_min
     int32_t* skel_id;
+    const int32_t* n_regular_ptr = nullptr;  // the number of regular paths in device memory (overrides n_regular)
     SKB_HD void operator()(int64_t p) const {
         int32_t src = pidx[pindptr[p]];
-        int32_t m = p < n_regular ? cmin[skb_find(par, src)] : src;
+        const int32_t nreg = n_regular_ptr ? *n_regular_ptr : n_regular;
+        int32_t m = p < nreg ? cmin[skb_find(par, src)] : src;
         skel_id[p] = (int32_t)rank[m];
     }
 };
@@ -2021,7 +2033,9 @@ struct SkbBranchItem {
     int32_t* out_i32;
     int64_t* out_i64;
     double* out_f64;
+    const int32_t* P_ptr = nullptr;  // the number of paths (= the stride of the column arrays) in device memory (overrides P)
     SKB_HD void operator()(int64_t p) const {
+        const int64_t P = P_ptr ? (int64_t)*P_ptr : this->P;
         int32_t src, dst, ds, dd;
         int64_t cdst[3] = {0, 0, 0};
         double vdst = 0.0;

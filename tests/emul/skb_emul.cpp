@@ -137,6 +137,13 @@ static int skb_scan_host(const T* in, T* out, int64_t n) {
 static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*, skb_stream_t) {
     return skb_scan_host<uint32_t>(in, out, n);
 }
+static int skb_scan_u32_dev(const uint32_t* in, uint32_t* out, int64_t n, const int32_t* n_ptr, uint32_t* total_out, void*,
+                            skb_stream_t) {
+    if (n_ptr && *n_ptr < n) n = *n_ptr < 0 ? 0 : *n_ptr;
+    skb_scan_host<uint32_t>(in, out, n);
+    if (total_out) *total_out = out[n];
+    return 0;
+}
 
 #define SKB_TILE_VOX 16384
 #define SKB_TILE_WORDS 256

@@ -308,7 +308,11 @@ def test_one_very_long_path():
     with the reference's left-to-right / pairwise sums to the rounding error of those sums (1e-11 here)."""
     import time
     n = 1449
-    img = long_chain_image('serpentine', n)
+    img = np.zeros((n, n), bool)      # a serpentine whose turns go through one diagonal pixel: no junctions, ONE chain
+    for k, r in enumerate(range(1, n - 1, 2)):
+        img[r, 2:n - 2] = True
+        if r + 2 < n - 1:
+            img[r + 1, n - 2 if k % 2 == 0 else 1] = True
     rng = np.random.default_rng(8)
     valued = (img * (rng.random(img.shape) + 0.5)).astype(np.float64)
     ref = orc.OracleSkeleton(valued, spacing=(1.0, 0.7))
