@@ -493,7 +493,8 @@ def main():
                           else f'{args.halo} planes per face passed with the slab')
             if getattr(r, 'counts', None):   # native runner: exchanges through peer-mapped arenas, no collective library
                 counts.update(runner='native (skb_run_slab)', host_syncs_per_step=r.counts['syncs'],
-                              exchanges_per_step=r.counts['exchanges'], nccl_collectives_per_step=0)
+                              exchanges_per_step=r.counts['exchanges'],
+                              device_barriers_per_step=r.counts.get('device_barriers', 0), nccl_collectives_per_step=0)
             else:
                 counts.update(runner='python (slab.py)', nccl_collectives_per_step=8)
         alg = _pipeline.algorithmic_bytes(V, esize, len(shape), counts['nodes'], counts['edges'], counts['paths'],
@@ -637,7 +638,8 @@ def main():
             for k, v in r.counts['host_us'].items():
                 print(f'  [host timeline, rank 0] {k:24s} +{v / 1e3:7.3f} ms   device {r.counts["dev_us"][k] / 1e3:7.3f} ms   '
                       f'(host, all ranks: ' + ' '.join(f'{t[0][k] / 1e3:.3f}' for t in tl) + ')', file=sys.stderr)
-            print(f'  [host timeline, rank 0] syncs {r.counts["syncs"]} exchanges {r.counts["exchanges"]}', file=sys.stderr)
+            print(f'  [host timeline, rank 0] syncs {r.counts["syncs"]} exchanges {r.counts["exchanges"]} '
+                  f'device barriers {r.counts.get("device_barriers", 0)}', file=sys.stderr)
         del r
 
     # ---- optional stage clock of the native runner (one extra step, not part of any reported number) -----

@@ -29,7 +29,8 @@ def main():
     lib = _native.library()
     V = int(np.prod(shape, dtype=np.int64))
     # (name, options of skb_set_option, capacity hints)
-    base = dict(emit_both_ways=1, splitter_bits=0, mst_keys=1, mst_blocks_per_sm=0, emit_blocks_per_sm=16, junction_append=1)
+    base = dict(emit_both_ways=1, splitter_bits=0, mst_keys=1, mst_blocks_per_sm=0, emit_blocks_per_sm=16, junction_append=1,
+                pdl=1)
     variants = [('default (1/16, both ways)', {}, True),
                 ('splitters 1/32, one way (r01)', dict(splitter_bits=5, emit_both_ways=0), True),
                 ('splitters 1/32, both ways', dict(splitter_bits=5), True),
@@ -37,6 +38,7 @@ def main():
                 ('splitters 1/8, both ways', dict(splitter_bits=3), True),
                 ('splitters 1/16, both ways', dict(splitter_bits=4), True),
                 ('no hints', {}, False),
+                ('plain launches (no pdl)', dict(pdl=0), True),
                 ('mst two-phase rounds (r01)', dict(mst_keys=0), True),
                 ('junction edges: count + scan + emit', dict(junction_append=0), True),
                 ('default (again)', {}, True)]

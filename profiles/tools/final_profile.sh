@@ -5,7 +5,7 @@ cd "$(dirname "$0")/../.."
 O=gpurun_out
 T=${1:-r01g}
 timeout 200 python bench.py --stages > $O/${T}_bench_volume_2048_n1.json 2> $O/${T}_bench_volume_2048_n1.err; echo bench rc=$?
-B="python bench.py --workload volume_2048 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"
+B="python bench.py --workload volume_2048 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-others"
 timeout 100 $B > $O/${T}_plain.log 2>&1; echo plain rc=$?
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/${T}_launches_volume_2048.csv $B > $O/${T}_ncu_list.log 2>&1; echo list rc=$?
 SKIP=$(T=$T python - <<'PY'

@@ -132,7 +132,7 @@ SLAB_COUNT = {n: i for i, n in enumerate(
     ['nodes_ext', 'own0', 'own1', 'id_shift', 'node_offset', 'edge_offset', 'edges_owned', 'nodes_total', 'edges_total',
      'regular', 'cycles', 'paths_total', 'entries_total', 'regular_total', 'regular_offset', 'cycle_offset',
      'entry_off_regular', 'entry_off_cycles', 'starts', 'table_records', 'syncs', 'exchanges', 'edges_ext',
-     'sweep_ns'])}
+     'sweep_ns', 'device_barriers'])}
 
 # indices into RunResult.off / .counts (the enums of skan_b200/csrc/skb_run.inl)
 RUN_OFF = {n: i for i, n in enumerate(

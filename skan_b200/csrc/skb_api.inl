@@ -402,7 +402,7 @@ int skb_skeleton_ids(const int32_t* pindptr, const int32_t* pidx, const int32_t*
 int skb_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
                    double* mean, double* stdev, void* stream) {
 #ifdef SKB_HAVE_FUSED_LOOPS
-    SKB_TRY(skb_foreach(n_paths, (skb_stream_t)stream, SkbPathStatsItem{pindptr, pdata, pw, dist, mean, stdev, SKB_LONG_PATH}));
+    SKB_TRY(skb_foreach(n_paths, (skb_stream_t)stream, SkbPathStatsItem{pindptr, pdata, pw, dist, mean, stdev, g_skb_long_path}));
     return skb_long_path_stats(pindptr, pdata, pw, n_paths, dist, mean, stdev, (skb_stream_t)stream);
 #else
     return skb_foreach(n_paths, (skb_stream_t)stream, SkbPathStatsItem{pindptr, pdata, pw, dist, mean, stdev});

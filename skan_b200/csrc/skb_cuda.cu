@@ -75,9 +75,49 @@ static int skb_optin_smem(K kernel, size_t bytes, uint8_t* done /* [SKB_MAX_DEV]
     return 0;
 }
 
+// ------------------------------------------------------------------------------- abort word
+// Z-slab mode synchronises the ranks of a node on the device (skb_xbar_kernel below): a rank's kernels wait for
+// flags its peers write into its exchange arena.  A rank that gives up half-way (an arena too small, an error)
+// or a wait that times out sets this word instead; kernels launched as "guarded" (between such a barrier and the
+// host's next read-back, which reports the word) then return at once rather than interpret rows that never arrived.
+__device__ int g_skb_poison = 0;
+static thread_local int g_skb_guard = 0;  // host: launch the following kernels guarded
+
+// ------------------------------------------------------------------------------- programmatic dependent launch
+// The node/edge/path proportional part of a step is a chain of 40-60 short kernels, each consuming what the previous
+// one wrote.  Launched plainly, a kernel's blocks are scheduled only after its predecessor has drained and flushed;
+// with programmatic stream serialisation (sm_90+) they are made resident while the predecessor's last wave is still
+// running and park at griddepcontrol.wait until it has completed, which hides the launch latency of every link of
+// the chain.  Every kernel launched this way executes SKB_PDL_ENTRY() before it touches global memory.  Option
+// "pdl" (skb_set_option; default 1) switches the attribute off for A/B measurements.
+#include <utility>
+static int g_skb_pdl = 1;
+#define SKB_PDL_ENTRY()                                                   \
+    do {                                                                  \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
+    } while (0)
+template <typename... KArgs, typename... Args>
+static cudaError_t skb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, skb_stream_t s,
+                                  Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_skb_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ------------------------------------------------------------------------------- foreach
 template <typename F>
-__global__ void __launch_bounds__(256) skb_foreach_kernel(F f, int64_t n) {
+__global__ void __launch_bounds__(256) skb_foreach_kernel(F f, int64_t n, int guard) {
+    SKB_PDL_ENTRY();
+    if (guard && g_skb_poison) return;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
@@ -88,9 +128,9 @@ static int skb_foreach(int64_t n, skb_stream_t s, F f) {
     int64_t blocks = (n + 255) / 256;
     int64_t cap = (int64_t)skb_sm_count() * 32;  // grid-stride beyond 32 CTAs per SM
     if (blocks > cap) blocks = cap;
-    skb_foreach_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, n);
     SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "skb_foreach launch");
+    return skb_cuda_check(skb_launch_pdl(skb_foreach_kernel<F>, dim3((unsigned)blocks), dim3(256), 0, s, f, n, g_skb_guard),
+                          "skb_foreach launch");
 }
 
 // tunables (skb_set_option, or the environment at first use), measured on B200 in round 2 (profiles/r02_ab_walks_*.txt):
@@ -133,7 +173,10 @@ static int skb_foreach_steps(int64_t n, skb_stream_t s, F f) {
 // f(i) for every i < n with marks[i] == 0, when almost every item is marked (the nodes no terminal-headed path
 // covers are a handful out of millions): a thread tests 16 marks with one 128-bit load.
 template <typename F>
-__global__ void __launch_bounds__(256) skb_foreach_unmarked_kernel(F f, const uint8_t* __restrict__ marks, int64_t n) {
+__global__ void __launch_bounds__(256) skb_foreach_unmarked_kernel(F f, const uint8_t* __restrict__ marks, int64_t n,
+                                                                   int guard) {
+    SKB_PDL_ENTRY();
+    if (guard && g_skb_poison) return;
     const int64_t groups = (n + 15) >> 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += stride) {
@@ -163,9 +206,10 @@ static int skb_foreach_unmarked(int64_t n, const uint8_t* marks, skb_stream_t s,
     int64_t blocks = ((n + 15) / 16 + 255) / 256;
     int64_t cap = (int64_t)skb_sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    skb_foreach_unmarked_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, marks, n);
     SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "skb_foreach_unmarked launch");
+    return skb_cuda_check(skb_launch_pdl(skb_foreach_unmarked_kernel<F>, dim3((unsigned)blocks), dim3(256), 0, s, f, marks, n,
+                                         g_skb_guard),
+                          "skb_foreach_unmarked launch");
 }
 
 static int skb_fill_bytes(void* p, int byte, size_t nbytes, skb_stream_t s) {
@@ -184,7 +228,7 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
 // round trip and the driver's wake-up on each of the 8-13 read-backs of a step.  The stream is checked
 // from time to time so that a failed kernel is reported instead of being waited for.
 struct SkbMailbox {
-    volatile int32_t* host;  // [0..SKB_MAX_FETCH) values, [SKB_MAX_FETCH] sequence number
+    volatile int32_t* host;  // [0..SKB_MAX_FETCH) values, [SKB_MAX_FETCH] sequence number, [SKB_MAX_FETCH + 1] abort word
     int32_t* dev;            // the same memory as the device sees it
     int32_t seq;
 };
@@ -192,8 +236,8 @@ static int skb_mailbox(SkbMailbox** out) {
     static thread_local SkbMailbox box = {nullptr, nullptr, 0};
     if (!box.host) {
         void* h = nullptr;
-        SKB_CUDA(cudaHostAlloc(&h, (SKB_MAX_FETCH + 1) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
-        memset(h, 0, (SKB_MAX_FETCH + 1) * 4);
+        SKB_CUDA(cudaHostAlloc(&h, (SKB_MAX_FETCH + 2) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h, 0, (SKB_MAX_FETCH + 2) * 4);
         void* d = nullptr;
         SKB_CUDA(cudaHostGetDevicePointer(&d, h, 0));
         box.host = (volatile int32_t*)h;
@@ -203,9 +247,14 @@ static int skb_mailbox(SkbMailbox** out) {
     return 0;
 }
 
+#define SKB_POISONED 3  // = SKB_RUN_RESTART of skb_slab.inl: the call is to be repeated after skb_comm_reset
+__global__ void skb_poison_clear_kernel() { g_skb_poison = 0; }
+
 __global__ void skb_mail_kernel(SkbGatherI32Item it, int n, int32_t seq) {
+    SKB_PDL_ENTRY();
     const int lane = threadIdx.x;
     if (lane < n) it.out[lane] = *it.ptr[lane];
+    if (lane == 31) it.out[SKB_MAX_FETCH + 1] = g_skb_poison;  // every read-back also reports the abort word
     __threadfence_system();
     __syncwarp();
     if (lane == 0) *(volatile int32_t*)(it.out + SKB_MAX_FETCH) = seq;
@@ -226,9 +275,8 @@ static int skb_fetch_post(const int32_t* const* ptrs, int n, skb_stream_t s) {
     for (int i = 0; i < SKB_MAX_FETCH; ++i) it.ptr[i] = n ? ptrs[i < n ? i : 0] : nullptr;
     it.out = box->dev;
     const int32_t seq = ++box->seq;
-    skb_mail_kernel<<<1, 32, 0, s>>>(it, n, seq);
     SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "read-back launch");
+    return skb_cuda_check(skb_launch_pdl(skb_mail_kernel, dim3(1), dim3(32), 0, s, it, n, seq), "read-back launch");
 }
 
 static int skb_fetch_wait(int n, int64_t* out, skb_stream_t s) {
@@ -247,6 +295,12 @@ static int skb_fetch_wait(int n, int64_t* out, skb_stream_t s) {
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
     for (int i = 0; i < n; ++i) out[i] = box->host[i];
+    if (box->host[SKB_MAX_FETCH + 1] != 0) {  // a device-side barrier of the Z-slab mode was given up (a peer left, or a
+        skb_poison_clear_kernel<<<1, 1, 0, s>>>();  // wait timed out): guarded kernels have been skipped since
+        SKB_COUNT_LAUNCH(1);
+        snprintf(g_skb_err, sizeof(g_skb_err), "a device-side barrier between the ranks was abandoned");
+        return SKB_POISONED;
+    }
     return 0;
 }
 
@@ -258,6 +312,72 @@ static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_s
 
 // everything enqueued on the stream so far has completed (an empty read-back)
 static int skb_stream_sync(skb_stream_t s) { return skb_fetch_i32s(nullptr, 0, nullptr, s); }
+
+// Barrier between the ranks of a node on the device, in stream order (Z-slab mode): every rank owns a block of one
+// 64-bit flag per peer at the end of its exchange arena.  The kernel stores this barrier's sequence number into its
+// slot of EVERY rank's block (st.release.sys after a system fence: what earlier kernels of this stream wrote into this
+// rank's arena is complete, and the peers read it there, through this GPU's L2), then one lane per peer polls the own
+// block (ld.acquire.sys) until every flag has reached the number.  Sequence numbers only grow: (generation << 32) |
+// count, the generation advanced by skb_comm_reset.  A rank that leaves a call half-way stores the generation's
+// largest number (low word all ones) instead: every wait of the generation ends at once and sets g_skb_poison, as
+// does a wait that lasts longer than SKB_XBAR_TIMEOUT_NS (a peer died).  No host thread takes part.
+#define SKB_XBAR_TIMEOUT_NS 20000000000ull
+struct SkbXbarArgs {
+    unsigned long long* peer_slot[SKB_MAX_RANKS];  // this rank's slot in every rank's flag block
+    const unsigned long long* mine;                // this rank's flag block
+    unsigned long long seq;
+    int world, poison;
+};
+__device__ __forceinline__ unsigned long long skb_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void skb_xbar_kernel(const SkbXbarArgs a) {
+    const int lane = threadIdx.x;
+    const bool on = lane < a.world;
+    const bool dead = a.poison || g_skb_poison != 0;  // an abandoned call abandons the barriers that follow as well
+    if (on) {
+        const unsigned long long v = dead ? (a.seq | 0xffffffffull) : a.seq;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_slot[lane]), "l"(v) : "memory");
+    }
+    if (dead) return;
+    const unsigned long long t0 = skb_globaltimer();
+    bool ok = !on, bad = false;
+    for (unsigned spins = 1;; ++spins) {
+        if (!ok) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.mine + lane) : "memory");
+            if (v >= a.seq) {
+                ok = true;
+                bad = (uint32_t)v == 0xffffffffu;
+            }
+        }
+        if ((spins & 255u) == 0 && skb_globaltimer() - t0 > SKB_XBAR_TIMEOUT_NS) bad = true;
+        if (__any_sync(0xffffffffu, bad) || __all_sync(0xffffffffu, ok)) break;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) g_skb_poison = 1;
+}
+static int skb_xbar_launch(void* const* xbase, int rank, int world, int64_t flag_off, uint64_t seq, int poison,
+                           skb_stream_t s) {
+    SkbXbarArgs a{};
+    for (int k = 0; k < world; ++k) a.peer_slot[k] = (unsigned long long*)((uint8_t*)xbase[k] + flag_off) + rank;
+    a.mine = (const unsigned long long*)((uint8_t*)xbase[rank] + flag_off);
+    a.seq = seq;
+    a.world = world;
+    a.poison = poison;
+    skb_xbar_kernel<<<1, 32, 0, s>>>(a);
+    SKB_COUNT_LAUNCH(1);
+    return skb_cuda_check(cudaGetLastError(), "rank barrier launch");
+}
+// skb_comm_reset: the abort word is cleared once everything enqueued has run
+static int skb_poison_reset() {
+    SKB_CUDA(cudaDeviceSynchronize());
+    const int zero = 0;
+    SKB_CUDA(cudaMemcpyToSymbol(g_skb_poison, &zero, sizeof(int)));
+    return 0;
+}
 
 // exchange arena of the Z-slab mode: device memory every rank of the node can read (CUDA IPC; the
 // peers map it once, kernels then load from it directly over NVLink)
@@ -395,9 +515,11 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
                                                                              uint32_t* out,
                                                                              unsigned long long* scratch,
                                                                              unsigned long long epoch, int64_t nb,
-                                                                             const int32_t* n_ptr, uint32_t* total_out) {
+                                                                             const int32_t* n_ptr, uint32_t* total_out,
+                                                                             int guard) {
     // n_ptr != NULL: the length is read on the device (at most n, the capacity the grid was sized by); total_out != NULL
     // receives the total as well (a fixed address, where out[n] is not one)
+    SKB_PDL_ENTRY();
     __shared__ int64_t s_tile;
     __shared__ uint32_t s_excl;
     unsigned int* counter = (unsigned int*)scratch;
@@ -408,6 +530,7 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
         s_tile = t;
     }
     __syncthreads();
+    if (guard && g_skb_poison) return;  // (after the ticket: the counter still resets itself for the next scan)
     const int64_t tile = s_tile;
     if (n_ptr) {
         int64_t m = *n_ptr;
@@ -511,10 +634,10 @@ static int skb_scan_u32_dev(const uint32_t* in, uint32_t* out, int64_t n, const 
     int64_t nb = (n + SKB_SCAN_TILE - 1) / SKB_SCAN_TILE;
     unsigned long long epoch = (unsigned long long)(__atomic_add_fetch(&g_skb_scan_epoch, 1u, __ATOMIC_RELAXED) & 0x3fffffffu);
     if (epoch == 0) epoch = (unsigned long long)(__atomic_add_fetch(&g_skb_scan_epoch, 1u, __ATOMIC_RELAXED) & 0x3fffffffu);
-    skb_scan_lookback_kernel<<<(unsigned)nb, SKB_SCAN_THREADS, 0, s>>>(in, n, out, (unsigned long long*)scratch, epoch, nb,
-                                                                      n_ptr, total_out);
     SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "scan launch");
+    return skb_cuda_check(skb_launch_pdl(skb_scan_lookback_kernel, dim3((unsigned)nb), dim3(SKB_SCAN_THREADS), 0, s, in, n, out,
+                                         (unsigned long long*)scratch, epoch, nb, n_ptr, total_out, g_skb_guard),
+                          "scan launch");
 }
 static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void* scratch, skb_stream_t s) {
     return skb_scan_u32_dev(in, out, n, nullptr, nullptr, scratch, s);
@@ -884,6 +1007,7 @@ __global__ void __launch_bounds__(SKB_EMIT_THREADS) skb_emit_nodes_kernel(
     double* __restrict__ values_arg, uint32_t* __restrict__ pre256, uint32_t node_cap) {
     // node_cap: capacity of lin / coords / values (the runner may size them by a hint before the count has
     // arrived); nodes with id >= node_cap are not written, the rank structure always is
+    SKB_PDL_ENTRY();
     double* __restrict__ values = VALUES ? values_arg : nullptr;
     __shared__ __align__(16) uint4 s_words[SKB_EMIT_WARPS][2][SKB_TILE_WORDS / 2];
     __shared__ uint32_t s_incl[SKB_EMIT_WARPS][2][SKB_TILE_WORDS / 2];
@@ -1552,7 +1676,9 @@ __device__ __forceinline__ void skb_rank_rounds(cg::grid_group& grid, Jump jump,
 
 __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_rank_coop_kernel(skb_i4* b0, skb_i4* b1, SkbAux* a0,
                                                                          SkbAux* a1, int64_t n, int32_t lo,
-                                                                         int32_t hi, int32_t* flags, const int32_t* n_ptr) {
+                                                                         int32_t hi, int32_t* flags, const int32_t* n_ptr,
+                                                                         int guard) {
+    if (guard && g_skb_poison) return;  // every thread of the grid reads the same value
     if (n_ptr && *n_ptr < n) n = *n_ptr;  // the number of starts in device memory
     // flags[3] == 0: the list-following pass (SkbRankWalkItem) finished every list, nothing to do.  Every
     // thread reads the same value: nobody writes flags[3] before the last grid barrier below.
@@ -1564,7 +1690,8 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_rank_coop_kernel(skb_i4*
 
 __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_table_rank_coop_kernel(skb_i4* b0, skb_i4* b1, SkbAux* a0,
                                                                                SkbAux* a1, int64_t n,
-                                                                               SkbSlabTable t, int32_t* flags) {
+                                                                               SkbSlabTable t, int32_t* flags, int guard) {
+    if (guard && g_skb_poison) return;  // every thread of the grid reads the same value
     cg::grid_group grid = cg::this_grid();
     SkbTableJumpItem jump{b0, b1, a0, a1, t, flags};
     skb_rank_rounds(grid, jump, b0, b1, a0, a1, n, flags);
@@ -1576,6 +1703,9 @@ static int g_skb_emit_blocks_per_sm = 16;  // measured at 2048^3: 5 -> 0.314, 8 
 static int g_skb_arena_guard = 0;  // "arena_guard": guard gaps between the runners' allocations (skb_run.inl)
 static int g_skb_small_cycles = 1;  // "small_cycles": 0 = always the general machinery for junction-free cycles
 static int g_skb_mst_keys = 1;  // "mst_keys": 0 = the two-phase rounds also for table weights (A/B)
+// "long_path_exact": 1 = paths of any length are summed by one thread in the reference's order (bit-exact, O(longest
+// path) time); 0 (default) = paths of more than SKB_LONG_PATH entries by one thread block in a fixed tree order
+static int32_t g_skb_long_path = SKB_LONG_PATH;
 template <typename K>
 static int skb_coop_launch(K kernel, int64_t n_items, void** args, skb_stream_t s, int max_per_sm = 0) {
     int per_sm = 0;
@@ -1694,13 +1824,15 @@ static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int
 
 static int skb_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, int32_t lo, int32_t hi,
                         int32_t* flag, skb_stream_t s, const int32_t* n_ptr = nullptr) {
-    void* args[] = {&b0, &b1, &a0, &a1, &n, &lo, &hi, &flag, &n_ptr};
+    int guard = g_skb_guard;
+    void* args[] = {&b0, &b1, &a0, &a1, &n, &lo, &hi, &flag, &n_ptr, &guard};
     return skb_coop_launch(skb_rank_coop_kernel, n, args, s);
 }
 
 static int skb_table_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, SkbSlabTable t,
                               int32_t* flag, skb_stream_t s) {
-    void* args[] = {&b0, &b1, &a0, &a1, &n, &t, &flag};
+    int guard = g_skb_guard;
+    void* args[] = {&b0, &b1, &a0, &a1, &n, &t, &flag, &guard};
     return skb_coop_launch(skb_table_rank_coop_kernel, n, args, s);
 }
 
@@ -1785,9 +1917,12 @@ struct SkbSmallCycleArgs {
     const int32_t* m_ptr = nullptr;         // the number of voxels in device memory (overrides m; more than the list holds:
                                             // error 2, nothing written)
     const int32_t* pid_base_ptr = nullptr;  // the number of regular paths in device memory (overrides pid_base)
+    int guard = 0;                          // launched guarded (g_skb_poison)
 };
 
 __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kernel(const SkbSmallCycleArgs A) {
+    SKB_PDL_ENTRY();
+    if (A.guard && g_skb_poison) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     SkbSmallCycleSmem& S = *(SkbSmallCycleSmem*)smem_raw;
     constexpr int PER = SKB_SMALL_CYCLE_NODES / SKB_SMALL_CYCLE_THREADS;
@@ -2034,12 +2169,15 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
     }
 }
 
-static int skb_small_cycles_launch(const SkbSmallCycleArgs& a, skb_stream_t s) {
+static int skb_small_cycles_launch(const SkbSmallCycleArgs& a_in, skb_stream_t s) {
     static uint8_t attr_set[SKB_MAX_DEV] = {};
     SKB_TRY(skb_optin_smem(skb_small_cycles_kernel, sizeof(SkbSmallCycleSmem), attr_set));
-    skb_small_cycles_kernel<<<1, SKB_SMALL_CYCLE_THREADS, sizeof(SkbSmallCycleSmem), s>>>(a);
+    SkbSmallCycleArgs a = a_in;
+    a.guard = g_skb_guard;
     SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "small cycles launch");
+    return skb_cuda_check(skb_launch_pdl(skb_small_cycles_kernel, dim3(1), dim3(SKB_SMALL_CYCLE_THREADS),
+                                         sizeof(SkbSmallCycleSmem), s, a),
+                          "small cycles launch");
 }
 
 // One GPU: list i32[m], out i32[4] (device).  Returns 0, or 1 when the case is not a small one (the caller runs the
@@ -2088,61 +2226,79 @@ __global__ void __launch_bounds__(256) skb_long_path_stats_kernel(const int32_t*
                                                                   const double* __restrict__ pdata,
                                                                   const double* __restrict__ pw, int64_t n_paths,
                                                                   double* dist, double* mean, double* stdev,
-                                                                  const int32_t* n_ptr) {
+                                                                  const int32_t* n_ptr, int32_t long_path) {
+    SKB_PDL_ENTRY();
     if (n_ptr && *n_ptr < n_paths) n_paths = *n_ptr;  // the number of paths in device memory
     __shared__ double red[3][256];
+    __shared__ int s_list[256];
+    __shared__ int s_n;
     const int tid = threadIdx.x;
-    for (int64_t p = blockIdx.x; p < n_paths; p += gridDim.x) {
-        const int32_t s = pindptr[p], e = pindptr[p + 1];
-        if (e - s <= SKB_LONG_PATH) continue;  // the same decision in every thread of the block
-        double a = 0.0, b = 0.0, c = 0.0;
-        for (int32_t j = s + tid; j < e; j += 256) {
-            if (j > s) a += pw[j];
-            if (pdata) {
-                const double x = pdata[j];
-                b += x;
-                c += x * x;
-            }
-        }
-        red[0][tid] = a;
-        red[1][tid] = b;
-        red[2][tid] = c;
+    // a block looks at 256 paths at a time (coalesced loads of their bounds): long paths are rare, so the usual pass over
+    // a group ends at the vote
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n_paths; base += (int64_t)gridDim.x * 256) {
+        const int64_t q = base + tid;
+        const bool is_long = q < n_paths && pindptr[q + 1] - pindptr[q] > long_path;
+        if (!__syncthreads_or(is_long)) continue;
+        if (tid == 0) s_n = 0;
         __syncthreads();
-        for (int d = 128; d > 0; d >>= 1) {
-            if (tid < d) {
-                red[0][tid] += red[0][tid + d];
-                red[1][tid] += red[1][tid + d];
-                red[2][tid] += red[2][tid + d];
+        if (is_long) s_list[atomicAdd(&s_n, 1)] = tid;  // (the order of the list does not enter any result)
+        __syncthreads();
+        const int n_long = s_n;
+        for (int i = 0; i < n_long; ++i) {
+            const int64_t p = base + s_list[i];
+            const int32_t s = pindptr[p], e = pindptr[p + 1];
+            double a = 0.0, b = 0.0, c = 0.0;
+            for (int32_t j = s + tid; j < e; j += 256) {
+                if (j > s) a += pw[j];
+                if (pdata) {
+                    const double x = pdata[j];
+                    b += x;
+                    c += x * x;
+                }
+            }
+            red[0][tid] = a;
+            red[1][tid] = b;
+            red[2][tid] = c;
+            __syncthreads();
+            for (int d = 128; d > 0; d >>= 1) {
+                if (tid < d) {
+                    red[0][tid] += red[0][tid + d];
+                    red[1][tid] += red[1][tid + d];
+                    red[2][tid] += red[2][tid + d];
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                const double n = (double)(e - s);
+                if (dist) dist[p] = red[0][0];
+                if (!pdata) {
+                    if (mean) mean[p] = 1.0;
+                    if (stdev) stdev[p] = 0.0;
+                } else {
+                    const double m = red[1][0] / n;
+                    if (mean) mean[p] = m;
+                    if (stdev) {
+                        double var = red[2][0] / n - m * m;
+                        if (!(var > 0.0)) var = (var == var) ? 0.0 : var;
+                        stdev[p] = sqrt(var);
+                    }
+                }
             }
             __syncthreads();
         }
-        if (tid == 0) {
-            const double n = (double)(e - s);
-            if (dist) dist[p] = red[0][0];
-            if (!pdata) {
-                if (mean) mean[p] = 1.0;
-                if (stdev) stdev[p] = 0.0;
-            } else {
-                const double m = red[1][0] / n;
-                if (mean) mean[p] = m;
-                if (stdev) {
-                    double var = red[2][0] / n - m * m;
-                    if (!(var > 0.0)) var = (var == var) ? 0.0 : var;
-                    stdev[p] = sqrt(var);
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
 static int skb_long_path_stats(const int32_t* pindptr, const double* pdata, const double* pw, int64_t n_paths, double* dist,
                                double* mean, double* stdev, skb_stream_t s, const int32_t* n_ptr = nullptr) {
     if (n_paths <= 0) return 0;
-    int64_t blocks = n_paths < 4 * (int64_t)skb_sm_count() ? n_paths : 4 * (int64_t)skb_sm_count();
-    skb_long_path_stats_kernel<<<(unsigned)blocks, 256, 0, s>>>(pindptr, pdata, pw, n_paths, dist, mean, stdev, n_ptr);
+    int64_t blocks = (n_paths + 255) / 256;
+    if (blocks > 4 * (int64_t)skb_sm_count()) blocks = 4 * (int64_t)skb_sm_count();
+    if (g_skb_long_path == 0x7fffffff) return 0;  // "long_path_exact": every path was summed in the reference's order
     SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "long path stats launch");
+    return skb_cuda_check(skb_launch_pdl(skb_long_path_stats_kernel, dim3((unsigned)blocks), dim3(256), 0, s, pindptr, pdata, pw,
+                                         n_paths, dist, mean, stdev, n_ptr, g_skb_long_path),
+                          "long path stats launch");
 }
 
 #include "skb_api.inl"
@@ -2210,6 +2366,14 @@ int skb_set_option(const char* name, int64_t value) {
         g_skb_mst_keys = value ? 1 : 0;
         return 0;
     }
+    if (!strcmp(name, "pdl")) {
+        g_skb_pdl = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "long_path_exact")) {
+        g_skb_long_path = value ? 0x7fffffff : SKB_LONG_PATH;
+        return 0;
+    }
     return skb_fail("skb_set_option: unknown option");
 }
 
@@ -2260,14 +2424,16 @@ int skb_emit_nodes_cap(const uint64_t* bits, const uint32_t* tile_prefix, int64_
     int64_t cap = (int64_t)skb_sm_count() * g_skb_emit_blocks_per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    if (values)
-        skb_emit_nodes_kernel<true><<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
-            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, values, pre256, cap32);
-    else
-        skb_emit_nodes_kernel<false><<<(unsigned)grid, SKB_EMIT_THREADS, 0, (skb_stream_t)stream>>>(
-            bits, tile_prefix, ntiles, skb_make_geom(ndim, shape), image, dtype, z_origin, lin, coords, nullptr, pre256, cap32);
     SKB_COUNT_LAUNCH(1);
-    return skb_cuda_check(cudaGetLastError(), "emit_nodes launch");
+    const SkbGeom g = skb_make_geom(ndim, shape);
+    double* no_values = nullptr;
+    return skb_cuda_check(
+        values ? skb_launch_pdl(skb_emit_nodes_kernel<true>, dim3((unsigned)grid), dim3(SKB_EMIT_THREADS), 0, (skb_stream_t)stream,
+                                bits, tile_prefix, ntiles, g, image, dtype, z_origin, lin, coords, values, pre256, cap32)
+               : skb_launch_pdl(skb_emit_nodes_kernel<false>, dim3((unsigned)grid), dim3(SKB_EMIT_THREADS), 0,
+                                (skb_stream_t)stream, bits, tile_prefix, ntiles, g, image, dtype, z_origin, lin, coords,
+                                no_values, pre256, cap32),
+        "emit_nodes launch");
 }
 
 // Mask sweep, scan and node emission in one pass (csr.py:1070,122-123,131-132,1088,554-562): what

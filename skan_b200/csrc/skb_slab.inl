@@ -22,6 +22,7 @@
 #define SKB_COMM_MAXV 15
 #define SKB_RUN_NEED_EXCHANGE 2  // skb_run_slab: the exchange arena is too small (result->exchange_need)
 #define SKB_RUN_RESTART 3        // skb_run_slab: another rank gave up (its arenas were too small, or it failed)
+#define SKB_XFLAG_BYTES 8192     // tail of every exchange arena: the flags of the device-side barriers
 
 struct SkbComm {
     int rank, world;
@@ -35,7 +36,23 @@ struct SkbComm {
                                      // edge count (the same on every rank) and this rank's edge count
     int64_t epoch;   // calls of skb_run_slab so far: consecutive calls use alternate halves of the exchange arena, so a
     int64_t xlimit;  // region is rewritten only after a whole intervening call (whose barriers every reader has passed)
+    int64_t xgen, xcount;  // device-side barriers (skb_xbar_launch): generation (advanced by skb_comm_reset) and count
 };
+
+// The last SKB_XFLAG_BYTES of every exchange arena hold the flags of the device-side barriers.
+static int64_t skb_comm_xdata(const SkbComm* c) { return c->xbytes - SKB_XFLAG_BYTES; }
+
+// Barrier between the ranks in stream order, no host thread involved: what this rank's earlier kernels wrote into its
+// exchange arena can be read by the peers' kernels that follow THEIR barrier, and vice versa.  The kernels launched
+// until the next read-back are "guarded": should a peer have given the call up, they return at once (g_skb_poison)
+// and the read-back reports it.
+static int skb_comm_xbar(SkbComm* c, skb_stream_t s) {
+    if (c->world == 1) return 0;
+    const uint64_t seq = ((uint64_t)c->xgen << 32) | (uint64_t)(++c->xcount);
+    SKB_TRY(skb_xbar_launch(c->xbase, c->rank, c->world, skb_comm_xdata(c), seq, 0, s));
+    g_skb_guard = 1;
+    return 0;
+}
 
 static double skb_now_s() {
     timespec ts;
@@ -87,8 +104,9 @@ int skb_comm_create(int rank, int world, const char* name, int64_t exchange_byte
     snprintf(c->name, sizeof(c->name), "%s", name);
     c->seq = 0;
     c->epoch = 0;
+    c->xgen = c->xcount = 0;
     c->hint_max_e = c->hint_edges = 0;
-    c->xbytes = (exchange_bytes + 8191) & ~(int64_t)8191;
+    c->xbytes = ((exchange_bytes + 8191) & ~(int64_t)8191) + SKB_XFLAG_BYTES;
     c->xlimit = c->xbytes;
     for (int k = 0; k < SKB_MAX_RANKS; ++k) c->xbase[k] = nullptr;
     char shm[64];
@@ -145,6 +163,10 @@ int skb_comm_reset(void* comm) {
     SkbComm* c = (SkbComm*)comm;
     c->seq = 0;
     c->epoch = 0;
+    ++c->xgen;  // the flags of the abandoned call (and its abort marks) are smaller than anything this generation waits for
+    c->xcount = 0;
+    g_skb_guard = 0;
+    SKB_TRY(skb_poison_reset());
     c->hint_max_e = c->hint_edges = 0;
     for (int b = 0; b < 2; ++b) {
         int64_t* row = skb_comm_table(c, b) + (int64_t)c->rank * (1 + SKB_COMM_MAXV);
@@ -174,7 +196,7 @@ enum {
     SKB_SC_EDGES_OWNED, SKB_SC_NODES_TOTAL, SKB_SC_EDGES_TOTAL, SKB_SC_REGULAR, SKB_SC_CYCLES, SKB_SC_PATHS_TOTAL,
     SKB_SC_ENTRIES_TOTAL, SKB_SC_REGULAR_TOTAL, SKB_SC_REGULAR_OFFSET, SKB_SC_CYCLE_OFFSET, SKB_SC_ENTRY_OFF_REGULAR,
     SKB_SC_ENTRY_OFF_CYCLES, SKB_SC_STARTS, SKB_SC_TABLE_RECORDS, SKB_SC_SYNCS, SKB_SC_EXCHANGES, SKB_SC_EDGES_EXT,
-    SKB_SC_SWEEP_NS, SKB_SC_COUNT
+    SKB_SC_SWEEP_NS, SKB_SC_DEVICE_BARRIERS, SKB_SC_COUNT
 };
 
 struct skb_slab_params {
@@ -216,6 +238,7 @@ struct skb_slab_result {
     do {                                                       \
         SKB_TRY(skb_fetch_i32s((ptrs_), (n_), (vals_), s));    \
         ++nsync;                                               \
+        g_skb_guard = 0; /* the read-back reported no abandoned barrier */ \
     } while (0)
 
 static int64_t skb_round16(int64_t x) { return x < 16 ? 16 : (x + 15) / 16 * 16; }
@@ -255,8 +278,15 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
 extern "C" int skb_run_slab(const skb_slab_params* prm, void* comm_, skb_slab_result* res) {
     SkbComm* comm = (SkbComm*)comm_;
     if (!comm) return skb_fail("skb_run_slab needs a communicator");
+    g_skb_guard = 0;
     int rc = skb_run_slab_impl(prm, comm, res);
+    g_skb_guard = 0;
     if (rc < 0 || rc == SKB_RUN_NEED_MORE) __atomic_store_n(skb_comm_abort(comm), (int64_t)1, __ATOMIC_RELEASE);
+    if ((rc < 0 || rc == SKB_RUN_NEED_MORE || rc == SKB_RUN_RESTART) && comm->world > 1) {
+        // peers may be waiting on the device for this rank's next barrier: end every wait of this generation
+        const uint64_t seq = ((uint64_t)comm->xgen << 32) | 0xffffffffull;
+        skb_xbar_launch(comm->xbase, comm->rank, comm->world, skb_comm_xdata(comm), seq, 1, (skb_stream_t)prm->stream);
+    }
     return rc;
 }
 
@@ -289,7 +319,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     SkbGeom g = skb_make_geom(3, shape);
     const int64_t sz = NY * NX, V = g.nvox;
     const int64_t ntiles = (V + SKB_TILE_VOX - 1) / SKB_TILE_VOX;
-    int64_t nsync = 0, nexch = 0;
+    int64_t nsync = 0, nexch = 0, nxbar = 0;
     const double t_call = skb_now_s();
     int n_mark = 0;
     for (int i = 0; i < 16; ++i) res->host_ns[i] = res->dev_ns[i] = 0;
@@ -317,7 +347,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     out.init(prm->out, prm->out_bytes, 1);
     auto out_off = [&](const void* p) -> int64_t { return p ? (int64_t)((const uint8_t*)p - out.base) : -1; };
     // bump pointer into the exchange arena, the same on every rank; this call's half of the arena
-    const int64_t xhalf = comm->xbytes / 2;
+    const int64_t xhalf = (skb_comm_xdata(comm) / 2) & ~(int64_t)255;
     int64_t xoff = (comm->epoch & 1) ? xhalf : 0;
     const int64_t xoff0 = xoff;
     comm->xlimit = xoff + xhalf;
@@ -367,13 +397,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         }
         SKB_TRY(skb_copy_bytes(exh.mine(0), own_bits, (size_t)face_bytes, s));
         SKB_TRY(skb_copy_bytes(exh.mine(1), own_bits + (own_planes - 2) * sz / 64, (size_t)face_bytes, s));
-        SKB_TRY(skb_stream_sync(s));
-        ++nsync;
-        {
-            const int64_t one = 1;
-            SKB_TRY(skb_comm_allgather(comm, &one, 1, all));
-            ++nexch;
-        }
+        SKB_TRY(skb_comm_xbar(comm, s));
+        ++nxbar;
         int64_t desc[1 + 3 * 2];
         int n = 0;
         if (has_lo) {  // the last two planes of the rank below
@@ -702,13 +727,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         SKB_SNEED(work.ok);
         SKB_TRY(skb_slab_export(ranked, raux, SF, SL0, nblk[rank], ex.cap, start_lo, start_hi, (skb_i4*)ex.mine(0),
                                 ex.mine(1), s));
-        SKB_TRY(skb_stream_sync(s));
-        ++nsync;
-        {
-            const int64_t one = 1;
-            SKB_TRY(skb_comm_allgather(comm, &one, 1, all));
-            ++nexch;
-        }
+        SKB_TRY(skb_comm_xbar(comm, s));
+        ++nxbar;
         {
             int64_t desc[1 + 3 * 2 * SKB_MAX_RANKS];
             void* dst[2] = {T, TA};
@@ -1010,13 +1030,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     SKB_SNEED(work.ok && out.ok);
     SKB_TRY(skb_slab_head_records(head_end, plen, pindptr, pmin, start_node, startoff, head_aux, slab, Ne, P0, exr.cap,
                                   P0off[rank], L0off[rank], (skb_i4*)exr.mine(0), (skb_i4*)exr.mine(1), s));
-    SKB_TRY(skb_stream_sync(s));
-    ++nsync;
-    {
-        const int64_t one = 1;
-        SKB_TRY(skb_comm_allgather(comm, &one, 1, all));
-        ++nexch;
-    }
+    SKB_TRY(skb_comm_xbar(comm, s));
+    ++nxbar;
     {
         int64_t desc[1 + 3 * 2 * SKB_MAX_RANKS];
         void* dst[2] = {heads_all, links_all};
@@ -1055,11 +1070,21 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     SKB_HOST_MARK();
     // ---- skeleton ids ------------------------------------------------------------------------------------------------------------
     SKB_TRY(skb_slab_components(links_all, nrec, S_total, kpar, kmin, node_lo, node_hi, id_shift, is_min, Ne, scratch, s));
-    int64_t cr0, C_k;
+    // the last allocations come before the last exchange through the host: a rank that gets past it knows that no
+    // rank will give the call up (the barrier that follows is on the device and has nobody to report to)
+    int32_t* skel = work.take<int32_t>(Pk1);
+    int32_t* skel_reg = work.take<int32_t>(P0 > 0 ? P0 : 1);
+    double* dist = out.take<double>(Pk1);
+    double* mean = out.take<double>(Pk1);
+    double* stdev = out.take<double>(Pk1);
+    int32_t* t32 = out.take<int32_t>(3 * Pk1);
+    int64_t* t64 = out.take<int64_t>(7 * Pk1);
+    double* tf = out.take<double>(7 * Pk1);
+    SKB_SNEED(work.ok && out.ok);
+    int64_t C_k;
     {
         const int32_t* ptrs[2] = {(const int32_t*)is_min + own0, (const int32_t*)is_min + own1};
         SKB_SFETCH(2, ptrs, vals);
-        cr0 = vals[0];
         C_k = vals[1] - vals[0];
     }
     int64_t Coff[SKB_MAX_RANKS + 1];
@@ -1071,23 +1096,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     }
     SKB_TRY(skb_slab_skeleton_ids(links_all, nrec, kpar, kmin, is_min, node_lo, node_hi, id_shift, Coff[rank], own0,
                                   (int32_t*)exs.mine(0), s));
-    // the last allocations come before the last exchange: a rank that gets past it knows that no rank will restart
-    int32_t* skel = work.take<int32_t>(Pk1);
-    int32_t* skel_reg = work.take<int32_t>(P0 > 0 ? P0 : 1);
-    double* dist = out.take<double>(Pk1);
-    double* mean = out.take<double>(Pk1);
-    double* stdev = out.take<double>(Pk1);
-    int32_t* t32 = out.take<int32_t>(3 * Pk1);
-    int64_t* t64 = out.take<int64_t>(7 * Pk1);
-    double* tf = out.take<double>(7 * Pk1);
-    SKB_SNEED(work.ok && out.ok);
-    SKB_TRY(skb_stream_sync(s));
-    ++nsync;
-    {
-        const int64_t one = 1;
-        SKB_TRY(skb_comm_allgather(comm, &one, 1, all));
-        ++nexch;
-    }
+    SKB_TRY(skb_comm_xbar(comm, s));
+    ++nxbar;
     if (P0) {  // sum of every rank's contribution to the ids of the paths headed here, read in place
         SkbPeerSumItem ps{};
         for (int k = 0; k < world; ++k) ps.src[k] = (const int32_t*)exs.field(0, k) + rank * exr.cap;
@@ -1097,7 +1107,6 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     }
     SKB_TRY(skb_foreach(Pk, s, SkbSlabSkelFinalItem{skel_reg, 0, (int32_t)P0, start_node, (int32_t)id_shift,
                                                    (int32_t)Coff[rank], (int32_t)own0, is_min, skel}));
-    (void)cr0;
     SKB_HOST_MARK();
     // ---- statistics and branch table of the paths headed here -----------------------------------------------------------------------
     SKB_TRY(skb_slab_path_stats(plen, head_aux, Pk, dist, mean, stdev, s));
@@ -1123,6 +1132,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     }
     res->counts[SKB_SC_SYNCS] = nsync;
     res->counts[SKB_SC_EXCHANGES] = nexch;
+    res->counts[SKB_SC_DEVICE_BARRIERS] = nxbar;
     res->work_need = work.need;
     res->out_need = out.need;
     return 0;

@@ -25,8 +25,15 @@ static int skb_fail(const char* what) {
     return -2;
 }
 
+// abort word of the device-side barriers and the "guarded launch" flag, as in the CUDA build
+#define SKB_POISONED 3
+static int g_skb_poison = 0;
+static thread_local int g_skb_guard = 0;
+#define SKB_GUARDED_OUT() (g_skb_guard && g_skb_poison)
+
 template <typename F>
 static int skb_foreach(int64_t n, skb_stream_t, F f) {
+    if (SKB_GUARDED_OUT()) return 0;
     for (int64_t i = 0; i < n; ++i) f(i);
     return 0;
 }
@@ -35,6 +42,7 @@ static int skb_foreach(int64_t n, skb_stream_t, F f) {
 // finish functions run one item after the other
 template <typename F>
 static int skb_foreach_steps(int64_t n, skb_stream_t, F f) {
+    if (SKB_GUARDED_OUT()) return 0;
     for (int64_t i = 0; i < n; ++i) {
         typename F::State st;
         if (!f.begin(i, st)) continue;
@@ -47,6 +55,7 @@ static int skb_foreach_steps(int64_t n, skb_stream_t, F f) {
 
 template <typename F>
 static int skb_foreach_unmarked(int64_t n, const uint8_t* marks, skb_stream_t, F f) {
+    if (SKB_GUARDED_OUT()) return 0;
     for (int64_t i = 0; i < n; ++i)
         if (!marks[i]) f(i);
     return 0;
@@ -62,9 +71,10 @@ static int skb_copy_bytes(void* dst, const void* src, size_t nbytes, skb_stream_
     return 0;
 }
 
+static int skb_poisoned();
 static int skb_fetch_i32s(const int32_t* const* ptrs, int n, int64_t* out, skb_stream_t) {
     for (int i = 0; i < n; ++i) out[i] = *ptrs[i];
-    return 0;
+    return skb_poisoned();
 }
 // two-part read-back: the values are taken when the request is posted (on the device the mail kernel runs in
 // stream order, i.e. before anything enqueued after the post), and handed over by the wait
@@ -75,7 +85,7 @@ static int skb_fetch_post(const int32_t* const* ptrs, int n, skb_stream_t) {
 }
 static int skb_fetch_wait(int n, int64_t* out, skb_stream_t) {
     for (int i = 0; i < n; ++i) out[i] = g_skb_posted[i];
-    return 0;
+    return skb_poisoned();
 }
 static int skb_stream_sync(skb_stream_t) { return 0; }
 
@@ -109,6 +119,52 @@ static int skb_xunlink(const char* name, int rank) {
     return 0;
 }
 
+// device-side barrier between the ranks (skb_xbar_kernel of the CUDA build): the same flag protocol, run by the host
+// thread on the shared-memory arenas
+#include <sched.h>
+#include <time.h>
+static int skb_xbar_launch(void* const* xbase, int rank, int world, int64_t flag_off, uint64_t seq, int poison, skb_stream_t) {
+    const bool dead = poison || g_skb_poison;
+    for (int k = 0; k < world; ++k) {
+        uint64_t* slot = (uint64_t*)((uint8_t*)xbase[k] + flag_off) + rank;
+        __atomic_store_n(slot, dead ? (seq | 0xffffffffull) : seq, __ATOMIC_RELEASE);
+    }
+    if (dead) return 0;
+    const uint64_t* mine = (const uint64_t*)((uint8_t*)xbase[rank] + flag_off);
+    timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int k = 0; k < world; ++k) {
+        for (uint64_t spins = 1;; ++spins) {
+            const uint64_t v = __atomic_load_n(mine + k, __ATOMIC_ACQUIRE);
+            if (v >= seq) {
+                if ((uint32_t)v == 0xffffffffu) g_skb_poison = 1;
+                break;
+            }
+            if ((spins & 1023) == 0) {
+                timespec t1;
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if (t1.tv_sec - t0.tv_sec > 60) {
+                    g_skb_poison = 1;
+                    break;
+                }
+                sched_yield();
+            }
+        }
+        if (g_skb_poison) break;
+    }
+    return 0;
+}
+static int skb_poison_reset() {
+    g_skb_poison = 0;
+    return 0;
+}
+static int skb_poisoned() {  // every read-back reports (and clears) the abort word
+    if (!g_skb_poison) return 0;
+    g_skb_poison = 0;
+    snprintf(g_skb_err, sizeof(g_skb_err), "a device-side barrier between the ranks was abandoned");
+    return SKB_POISONED;
+}
+
 static int skb_stage_mark(int, skb_stream_t) { return 0; }
 static int skb_stage_read(const uint8_t*, int n, int64_t* ns) {
     for (int i = 0; i < n; ++i) ns[i] = 0;
@@ -135,6 +191,7 @@ static int skb_scan_host(const T* in, T* out, int64_t n) {
     return 0;
 }
 static int skb_scan_u32_impl(const uint32_t* in, uint32_t* out, int64_t n, void*, skb_stream_t) {
+    if (SKB_GUARDED_OUT()) return 0;
     return skb_scan_host<uint32_t>(in, out, n);
 }
 static int skb_scan_u32_dev(const uint32_t* in, uint32_t* out, int64_t n, const int32_t* n_ptr, uint32_t* total_out, void*,
