@@ -369,6 +369,9 @@ def main():
         entry.build()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # the host thread (launches, read-back mailbox, pinned buffers of the end-to-end leg) runs next to its GPU
+    from skan_b200._numa import bind_thread_to_gpu
+    placement = bind_thread_to_gpu(dev)
     if world > 1:
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
@@ -662,6 +665,7 @@ def main():
     # ---- end to end through the public API from a pinned host image ---------------------------
     e2e = None
     if not args.no_e2e:
+        # the pinned source buffer lives on the NUMA node of this rank's GPU (first touch by the thread bound there)
         host = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
         host.copy_(img)
         torch.cuda.synchronize()
@@ -695,7 +699,9 @@ def main():
                 times.append(dt)
         e2e_s = max_over_ranks(float(np.mean(times)))
         e2e = {'value': V / e2e_s / 1e6, 'unit': UNIT, 'h2d_bytes_per_step': int(sum_over_ranks(V_local * esize)),
-               'd2h_bytes_per_step': int(sum_over_ranks(d2h)), 'ms_per_step': e2e_s * 1e3, 'steps': n_e2e}
+               'd2h_bytes_per_step': int(sum_over_ranks(d2h)), 'ms_per_step': e2e_s * 1e3, 'steps': n_e2e,
+               'host_buffer': f"pinned, rank 0 on NUMA node {placement['numa_node']} ({placement['cpus']} CPUs)"
+               if placement['bound'] else 'pinned, no NUMA placement (' + placement.get('error', 'no node information') + ')'}
         del host
     m['img'] = m['step'] = None
     img = step = None
