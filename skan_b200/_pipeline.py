@@ -469,6 +469,9 @@ _arena_cache = {}   # (device, stream) -> dict(work=tensor, out_bytes=int)
 _wtab_cache = {}
 
 
+_ESIZE = {torch.int32: 4, torch.int64: 8, torch.float64: 8, torch.uint8: 1, torch.uint32: 4, torch.float32: 4}
+
+
 class _ArenaViews:
     """Typed views into the output arena, created on first access."""
 
@@ -483,7 +486,7 @@ class _ArenaViews:
         if off < 0:
             t = None
         else:
-            nbytes = count * torch.empty(0, dtype=dtype).element_size()
+            nbytes = count * _ESIZE[dtype]
             t = self._arena[off: off + nbytes].view(dtype)
             if shape is not None:
                 t = t.view(shape)

@@ -43,7 +43,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _pipeline
+from . import _native, _pipeline
 
 AUX_BYTES = 48
 
@@ -240,11 +240,23 @@ def _close_comm(key):
             pass
 
 
+_group_facts = {}
+
+
+def _world_rank(group):
+    """(world size, rank) of a process group; looked up once per group (each query costs microseconds of GPU idle time)"""
+    key = id(group) if group is not None else 0
+    got = _group_facts.get(key)
+    if got is None or got[2] is not (group if group is not None else dist.group.WORLD):
+        g = group if group is not None else dist.group.WORLD
+        got = _group_facts[key] = (dist.get_world_size(group), dist.get_rank(group), g)
+    return got[0], got[1]
+
+
 def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, group, pack_variant, halo_exchange=False):
     """skeleton_and_summary_slab through skb_run_slab: the whole per-rank sequence in one native call."""
     import ctypes
-    from . import _native
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world, rank = _world_rank(group)
     ctx = _pipeline._Ctx(device)
     img, code, shape, np_dtype = _pipeline._as_device_image(slab_image, ctx.device)
     if len(shape) != 3:
@@ -316,46 +328,79 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
     else:
         raise _native.NativeError('skb_run_slab kept asking for larger arenas')
     cache['out_bytes'] = max(1 << 20, int(res.out_need * 1.05) + (1 << 16))
-    C = {k: int(res.counts[i]) for k, i in _native.SLAB_COUNT.items()}
-    prev = 0
-    C['host_us'] = {}
-    for i, k in enumerate(_native.SLAB_SECTIONS):
-        C['host_us'][k] = (int(res.host_ns[i]) - prev) / 1e3
-        prev = int(res.host_ns[i])
-    C['dev_us'] = {k: int(res.dev_ns[i]) / 1e3 for i, k in enumerate(_native.SLAB_SECTIONS)}
-    O = {k: int(res.off[i]) for k, i in _native.SLAB_OFF.items()}
+    counts = res.counts
+    C = {k: int(counts[i]) for k, i in _native.SLAB_COUNT.items()}
+    if prm.time_sweep:   # host / device clocks of the sections (bench.py --timeline)
+        prev = 0
+        C['host_us'] = {}
+        for i, k in enumerate(_native.SLAB_SECTIONS):
+            C['host_us'][k] = (int(res.host_ns[i]) - prev) / 1e3
+            prev = int(res.host_ns[i])
+        C['dev_us'] = {k: int(res.dev_ns[i]) / 1e3 for i, k in enumerate(_native.SLAB_SECTIONS)}
     if C['paths_total'] == 0:
         raise ValueError('index pointer size 0 should be 1')
-    Ne, E, Pk, L = C['nodes_ext'], C['edges_ext'], C['regular'] + C['cycles'], C['entries_total']
-    Pk1 = max(Pk, 1)
-    i32, i64, f64 = torch.int32, torch.int64, torch.float64
+    return _SlabResult(ctx, out, res.off, C, rank, world, tuple(shape), np_dtype, img, sp_is_int)
 
-    def view(name, count, dtype, shp=None):
-        off = O[name]
-        if off < 0:
-            return None
-        t = out[off: off + count * torch.empty(0, dtype=dtype).element_size()].view(dtype)
-        return t if shp is None else t.view(shp)
 
-    g = SimpleNamespace(ctx=ctx, shape=tuple(shape), ndim=3, np_dtype=np_dtype, n_nodes=Ne, n_edges=E,
-                        lin=view('lin', Ne, i64), coords=view('coords', Ne * 3, i64, (Ne, 3)),
-                        values=view('values', Ne, f64), degrees=view('degrees', Ne, i32),
-                        indptr=view('indptr', Ne + 1, i32), indices=view('indices', E, i32), data=view('data', E, f64),
-                        _keepalive=(img, out))
-    t32 = view('t32', 3 * Pk1, i32)[:3 * Pk].view(3, Pk)
-    t64 = view('t64', 7 * Pk1, i64)[:7 * Pk].view(7, Pk)
-    tf = view('tf', 7 * Pk1, f64)[:7 * Pk].view(7, Pk)
-    return SimpleNamespace(
-        rank=rank, world=world, graph=g, own=(C['own0'], C['own1']), id_shift=C['id_shift'],
-        n_nodes=C['own1'] - C['own0'], n_edges=C['edges_owned'], node_offset=C['node_offset'],
-        edge_offset=C['edge_offset'], n_nodes_total=C['nodes_total'], n_edges_total=C['edges_total'],
-        n_regular=C['regular'], n_cycles=C['cycles'], n_paths_total=C['paths_total'], n_entries_total=L,
-        n_regular_total=C['regular_total'], regular_offset=C['regular_offset'], cycle_offset=C['cycle_offset'],
-        path_len=view('plen', Pk + 1, i32)[:Pk], paths_indices=view('pidx', L, i32), paths_data=view('pdata', L, f64),
-        paths_weights=view('pw', L, f64), entry_offset_regular=C['entry_off_regular'],
-        entry_offset_cycles=C['entry_off_cycles'], dist=view('dist', Pk1, f64)[:Pk], mean=view('mean', Pk1, f64)[:Pk],
-        stdev=view('stdev', Pk1, f64)[:Pk], table=(t32, t64, tf), spacing_is_int=sp_is_int, rank_rounds=0,
-        table_rounds=0, n_starts=C['starts'], n_table=C['table_records'], counts=C)
+class _SlabGraph:
+    """Graph part of a native slab run (rows of the extended slab, local ids): views created on first access."""
+
+    def __init__(self, v, ctx, shape, np_dtype, n, e, keepalive):
+        self._v, self.ctx, self.shape, self.ndim, self.np_dtype = v, ctx, shape, 3, np_dtype
+        self.n_nodes, self.n_edges, self._keepalive = n, e, keepalive
+
+    lin = property(lambda self: self._v.lin)
+    coords = property(lambda self: self._v.coords)
+    values = property(lambda self: self._v.values)
+    degrees = property(lambda self: self._v.degrees)
+    indptr = property(lambda self: self._v.indptr)
+    indices = property(lambda self: self._v.indices)
+    data = property(lambda self: self._v.data)
+
+
+class _SlabResult:
+    """This rank's share of a native slab run.  The arrays are typed views of the output arena, created when they are
+    first read: a caller that only looks at the branch table does not pay for the rest (the interpreter time between
+    two volumes is GPU idle time)."""
+
+    def __init__(self, ctx, out, off, C, rank, world, shape, np_dtype, img, sp_is_int):
+        Ne, E, Pk, L = C['nodes_ext'], C['edges_ext'], C['regular'] + C['cycles'], C['entries_total']
+        Pk1 = max(Pk, 1)
+        i32, i64, f64 = torch.int32, torch.int64, torch.float64
+        O = _native.SLAB_OFF
+        spec = {
+            'lin': (int(off[O['lin']]), Ne, i64, None), 'coords': (int(off[O['coords']]), Ne * 3, i64, (Ne, 3)),
+            'values': (int(off[O['values']]), Ne, f64, None), 'degrees': (int(off[O['degrees']]), Ne, i32, None),
+            'indptr': (int(off[O['indptr']]), Ne + 1, i32, None), 'indices': (int(off[O['indices']]), E, i32, None),
+            'data': (int(off[O['data']]), E, f64, None), 'plen': (int(off[O['plen']]), Pk, i32, None),
+            'pidx': (int(off[O['pidx']]), L, i32, None), 'pdata': (int(off[O['pdata']]), L, f64, None),
+            'pw': (int(off[O['pw']]), L, f64, None), 'dist': (int(off[O['dist']]), Pk, f64, None),
+            'mean': (int(off[O['mean']]), Pk, f64, None), 'stdev': (int(off[O['stdev']]), Pk, f64, None),
+            't32': (int(off[O['t32']]), 3 * Pk, i32, (3, Pk)), 't64': (int(off[O['t64']]), 7 * Pk, i64, (7, Pk)),
+            'tf': (int(off[O['tf']]), 7 * Pk, f64, (7, Pk)),
+        }
+        self._v = v = _pipeline._ArenaViews(out, spec)
+        self.graph = _SlabGraph(v, ctx, shape, np_dtype, Ne, E, (img, out))
+        self.rank, self.world, self.counts, self.spacing_is_int = rank, world, C, sp_is_int
+        self.own = (C['own0'], C['own1'])
+        self.id_shift = C['id_shift']
+        self.n_nodes = C['own1'] - C['own0']
+        self.n_edges, self.node_offset, self.edge_offset = C['edges_owned'], C['node_offset'], C['edge_offset']
+        self.n_nodes_total, self.n_edges_total = C['nodes_total'], C['edges_total']
+        self.n_regular, self.n_cycles, self.n_paths_total, self.n_entries_total = C['regular'], C['cycles'], C['paths_total'], L
+        self.n_regular_total, self.regular_offset, self.cycle_offset = C['regular_total'], C['regular_offset'], C['cycle_offset']
+        self.entry_offset_regular, self.entry_offset_cycles = C['entry_off_regular'], C['entry_off_cycles']
+        self.rank_rounds = self.table_rounds = 0
+        self.n_starts, self.n_table = C['starts'], C['table_records']
+
+    path_len = property(lambda self: self._v.plen)
+    paths_indices = property(lambda self: self._v.pidx)
+    paths_data = property(lambda self: self._v.pdata)
+    paths_weights = property(lambda self: self._v.pw)
+    dist = property(lambda self: self._v.dist)
+    mean = property(lambda self: self._v.mean)
+    stdev = property(lambda self: self._v.stdev)
+    table = property(lambda self: (self._v.t32, self._v.t64, self._v.tf))
 
 
 def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spacing=1, device=None, group=None,

@@ -23,6 +23,9 @@ CASES = [
     ['--kind', 'rings', '--shape', '64,22,30', '--halo', '2'],
     ['--kind', 'walks', '--shape', '96,64,64', '--halo', '2', '--seed', '11', '--guard', '1', '--prime', '1'],
     ['--kind', 'dense12', '--shape', '64,32,32', '--halo', '2', '--seed', '5', '--guard', '1', '--prime', '2'],
+    # tiny first arenas: every rank gives the call up at a different point, while its peers wait in a device-side barrier
+    # (the abort word ends the waits, the guarded kernels are skipped, the read-back reports it, everybody goes again)
+    ['--kind', 'walks', '--shape', '96,64,64', '--halo', '2', '--seed', '13', '--small-arenas', '1'],
 ]
 
 
@@ -50,6 +53,7 @@ def test_slab_mode_native(world, args):
     ['--kind', 'walks', '--shape', '64,128,128', '--seed', '2'],
     ['--kind', 'dense12', '--shape', '48,64,256', '--seed', '6'],
     ['--kind', 'rings', '--shape', '64,128,128'],
+    ['--kind', 'walks', '--shape', '64,128,128', '--seed', '4', '--small-arenas', '1'],
 ])
 def test_halo_exchange_from_a_disjoint_partition(world, args):
     """halo='exchange': owned planes only per rank, boundary planes of the packed mask exchanged over NVLink."""
