@@ -342,6 +342,7 @@ typedef struct skb_slab_params {
     int32_t dtype, pack_variant; int64_t global_shape[3]; int64_t z0, z1, ze0, nz_ext;
     int32_t want_values, time_sweep; const double* wtab;
     double spacing_f[3]; int64_t spacing_i[3]; int32_t spacing_is_int, halo_exchange;
+    int32_t height, reserved;           /* height: value_is_height (csr.py:148-151, 932-948); needs want_values */
     void* work; int64_t work_bytes; void* out; int64_t out_bytes; void* stream;
 } skb_slab_params;
 typedef struct skb_slab_result { int64_t counts[32]; int64_t off[32]; int64_t work_need, out_need, exchange_need; int64_t host_ns[16]; int64_t dev_ns[16]; } skb_slab_result;

@@ -18,6 +18,7 @@ PY
 )
 set -- $SKIP
 echo "skip $1 count $2"
-timeout 300 ncu --set full --clock-control none --import-source on --launch-skip $1 -c $2 -f -o $O/${T}_prof $B > $O/${T}_ncu_full.log 2>&1; echo full rc=$?
+# (ncu's kernel replay fails on launches with the programmatic-serialisation attribute: the capture runs with plain launches)
+SKAN_B200_PDL=0 timeout 300 ncu --set full --clock-control none --import-source on --launch-skip $1 -c $2 -f -o $O/${T}_prof $B > $O/${T}_ncu_full.log 2>&1; echo full rc=$?
 timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err; echo ref rc=$?
 for w in volume_1024 image_16384 batch_512; do timeout 100 python bench.py --workload $w --stages --no-cpu-baseline > $O/${T}_bench_${w}_n1.json 2> $O/${T}_bench_${w}_n1.err; echo $w rc=$?; done

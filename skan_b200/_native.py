@@ -108,6 +108,7 @@ class SlabParams(ctypes.Structure):
                 ('z0', _i64), ('z1', _i64), ('ze0', _i64), ('nz_ext', _i64), ('want_values', ctypes.c_int32),
                 ('time_sweep', ctypes.c_int32), ('wtab', _vp), ('spacing_f', ctypes.c_double * 3),
                 ('spacing_i', _i64 * 3), ('spacing_is_int', ctypes.c_int32), ('halo_exchange', ctypes.c_int32),
+                ('height', ctypes.c_int32), ('reserved', ctypes.c_int32),
                 ('work', _vp), ('work_bytes', _i64), ('out', _vp), ('out_bytes', _i64), ('stream', _vp)]
 
 

@@ -417,7 +417,7 @@ int skb_branch_table(int64_t n_paths, int ndim, int height, int spacing_is_int, 
                      int32_t* out_i32, int64_t* out_i64, double* out_f64, void* stream) {
     if (ndim < 1 || ndim > 3) return skb_fail("ndim must be 1, 2 or 3");
     if (height && !values) return skb_fail("height mode needs node values");
-    if (head_aux && (height || !start_node || !global_shape)) return skb_fail("bad slab-mode branch table call");
+    if (head_aux && (!start_node || !global_shape)) return skb_fail("bad slab-mode branch table call");
     SkbBranchItem it;
     it.P = n_paths;
     it.d = ndim;

@@ -91,7 +91,14 @@ static thread_local int g_skb_guard = 0;  // host: launch the following kernels 
 // the chain.  Every kernel launched this way executes SKB_PDL_ENTRY() before it touches global memory.  Option
 // "pdl" (skb_set_option; default 1) switches the attribute off for A/B measurements.
 #include <utility>
-static int g_skb_pdl = 1;
+static int g_skb_pdl = -1;  // -1: not set yet -> SKAN_B200_PDL in the environment ("0" switches it off), else on
+static int skb_option_pdl() {
+    if (g_skb_pdl < 0) {
+        const char* e = getenv("SKAN_B200_PDL");
+        g_skb_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_skb_pdl;
+}
 #define SKB_PDL_ENTRY()                                                   \
     do {                                                                  \
         asm volatile("griddepcontrol.wait;" ::: "memory");                \
@@ -107,7 +114,7 @@ static cudaError_t skb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_skb_pdl ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = skb_option_pdl() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
@@ -2158,6 +2165,8 @@ __global__ void __launch_bounds__(SKB_SMALL_CYCLE_THREADS) skb_small_cycles_kern
                 a.end_deg = 2;
                 a.end_key = 0;
                 a.pad = 0;
+                a.end_value = S.vv[i];
+                a.pad2 = 0.0;
                 A.head_aux[pid_base + (int32_t)(ea + ra[q])] = a;
             }
         }

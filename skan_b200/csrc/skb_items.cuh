@@ -656,6 +656,8 @@ struct alignas(16) SkbAux {
     int32_t end_deg;     // its degree
     int32_t end_key;     // global id of its first start (a dense key for the end node)
     int32_t pad;
+    double end_value;    // its pixel value (the extra coordinate of value_is_height, csr.py:932-948)
+    double pad2;         // (the records stay 16-byte aligned rows of the exchange arenas)
 };
 
 // Node record, 32 bytes = two 16-byte halves of rec[2v], rec[2v+1]:
@@ -828,6 +830,7 @@ struct SkbWalkItemT {  // over starts: local walk to the next terminal / cycle r
         double w_in, sw, sx, sxx;  // AUX only
         int64_t end_lin;
         int32_t end_node, end_deg, end_key;
+        double end_value;
     };
     SKB_HD bool begin(int64_t s, State& st) const {
         int32_t u = su[s];
@@ -848,6 +851,7 @@ struct SkbWalkItemT {  // over starts: local walk to the next terminal / cycle r
             st.end_node = -1;
             st.end_deg = 0;
             st.end_key = -1;
+            st.end_value = 0.0;
         }
         return true;
     }
@@ -881,6 +885,7 @@ struct SkbWalkItemT {  // over starts: local walk to the next terminal / cycle r
                 st.end_node = cur + sl.id_shift;
                 st.end_deg = d;
                 st.end_key = key;
+                st.end_value = x;
             }
             return false;
         }
@@ -914,6 +919,8 @@ struct SkbWalkItemT {  // over starts: local walk to the next terminal / cycle r
             ax.end_deg = st.end_deg;
             ax.end_key = st.end_key;
             ax.pad = 0;
+            ax.end_value = st.end_value;
+            ax.pad2 = 0.0;
             aux[s] = ax;
         }
     }
@@ -934,6 +941,7 @@ SKB_HD void skb_aux_append(SkbAux& a, const SkbAux& b) {  // list of a followed 
     a.end_node = b.end_node;
     a.end_deg = b.end_deg;
     a.end_key = b.end_key;
+    a.end_value = b.end_value;
 }
 
 // one synchronous pointer-jumping round, src -> dst, over the starts of this rank; pointers
@@ -1833,6 +1841,8 @@ struct SkbRingWalkItem {  // over records: the owner of a ring writes all its en
         a.end_deg = 2;
         a.end_key = 0;
         a.pad = 0;
+        a.end_value = s.value;
+        a.pad2 = 0.0;
         head_aux[pid] = a;
     }
 };
@@ -2044,6 +2054,7 @@ struct SkbBranchItem {
             src = start_node[p] - id_shift;
             dst = a.end_node;
             dd = a.end_deg;
+            vdst = a.end_value;
             int64_t q = a.end_lin / gnx;
             cdst[2] = a.end_lin - q * gnx;
             int64_t q2 = q / gny;

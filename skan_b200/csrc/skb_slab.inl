@@ -209,6 +209,8 @@ struct skb_slab_params {
     double spacing_f[3];
     int64_t spacing_i[3];
     int32_t spacing_is_int, halo_exchange;
+    int32_t height, reserved;  // height: value_is_height (edge weights hypot(height difference, distance), the pixel
+                               // value as an extra coordinate of the branch table); needs want_values
     void* work;
     int64_t work_bytes;
     void* out;
@@ -314,6 +316,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         if ((NY * NX) % SKB_TILE_VOX) return skb_fail("halo exchange needs planes of a multiple of 16384 voxels (pass the halo planes with the slab otherwise)");
         if (prm->want_values) return skb_fail("halo exchange is implemented for boolean volumes (pass the halo planes with the slab for valued images)");
     }
+    const int height = prm->height == 1 ? 1 : 0;
+    if (height && !prm->want_values) return skb_fail("value_is_height needs a numeric (non-boolean) image");
     const int64_t shape[3] = {prm->nz_ext, NY, NX};
     SKB_TRY(skb_check_geom(3, shape));
     SkbGeom g = skb_make_geom(3, shape);
@@ -543,7 +547,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         SKB_SNEED(work.ok);
         SKB_TRY(skb_fill_bytes(ex.mine(0), 0xff, (size_t)ex.cap * 4, s));  // a < 0 marks the padding rows
         bool appended = false;
-        if (speculative) {  // one unordered pass (the keyed Boruvka needs no edge order), the count from its atomic counter
+        if (speculative && !height) {  // one unordered pass (the keyed Boruvka needs no edge order; table weights only)
             int r = skb_junction_append(bits, pre256, 3, shape, lin, nb, Ne, own0, own1, (int32_t*)ex.mine(0),
                                         (int32_t*)ex.mine(1), (uint8_t*)ex.mine(3), ex.cap, small + 11, s);
             if (r < 0) return r;
@@ -554,7 +558,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
             SKB_TRY(count_edges());
             nej_src = (const int32_t*)jcount + Ne;
             if (nej_k != 0)
-                SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, 3, shape, lin, nb, jcount, Ne, prm->wtab, values, 0,
+                SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, 3, shape, lin, nb, jcount, Ne, prm->wtab, values, height,
                                                    prm->dtype, (int32_t*)ex.mine(0), (int32_t*)ex.mine(1),
                                                    (uint8_t*)ex.mine(3), (uint64_t*)ex.mine(2), ex.cap, s));
         }
@@ -604,8 +608,8 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         SKB_TRY(skb_slab_edge_shift(gea, geb, nej_rows, ex.cap, shifts, world, s));
         // Boruvka on the gathered edges (the same on every rank) and, in the same launch, the dropped edges cleared from
         // this rank's raw masks in place
-        SKB_TRY(skb_mst_junctions_apply(gea, geb, gek, gew, prm->wtab, 0, nej_rows, N_total, mpar, bestw, era, erb, tree, flag,
-                                        nb, id_shift, Ne, s));
+        SKB_TRY(skb_mst_junctions_apply(gea, geb, gek, gew, prm->wtab, height, nej_rows, N_total, mpar, bestw, era, erb, tree,
+                                        flag, nb, id_shift, Ne, s));
     }
     SKB_HOST_MARK();
     // ---- CSR + node records + start numbering (one pass) ------------------------------------------------------
@@ -632,7 +636,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     uint32_t* startoff = work.take<uint32_t>(Ne + 1);
     uint32_t* is_min = work.take<uint32_t>(Ne + 1);
     SKB_SNEED(work.ok && out.ok);
-    SKB_TRY(skb_csr_emit_cap(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
+    SKB_TRY(skb_csr_emit_cap(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, height, prm->dtype, indices, data,
                              rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, e_cap ? e_cap : 0x7fffffffLL, s,
                              N_total / world + 1));
     int64_t so[4], ei[2];
@@ -655,7 +659,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
         startoff = work.take<uint32_t>(Ne + 1);
         is_min = work.take<uint32_t>(Ne + 1);
         SKB_SNEED(work.ok && out.ok);
-        SKB_TRY(skb_csr_emit_cap(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, 0, prm->dtype, indices, data,
+        SKB_TRY(skb_csr_emit_cap(bits, pre256, 3, shape, lin, keep, indptr, Ne, prm->wtab, values, height, prm->dtype, indices, data,
                                  rec, slab, 1, startoff, nullptr, nullptr, is_min, scratch, 0x7fffffffLL, s, N_total / world + 1));
     }
     comm->hint_edges = E;
@@ -1079,7 +1083,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     double* stdev = out.take<double>(Pk1);
     int32_t* t32 = out.take<int32_t>(3 * Pk1);
     int64_t* t64 = out.take<int64_t>(7 * Pk1);
-    double* tf = out.take<double>(7 * Pk1);
+    double* tf = out.take<double>((2 * (3 + height) + 1) * Pk1);
     SKB_SNEED(work.ok && out.ok);
     int64_t C_k;
     {
@@ -1111,7 +1115,7 @@ static int skb_run_slab_impl(const skb_slab_params* prm, SkbComm* comm, skb_slab
     // ---- statistics and branch table of the paths headed here -----------------------------------------------------------------------
     SKB_TRY(skb_slab_path_stats(plen, head_aux, Pk, dist, mean, stdev, s));
     if (Pk)
-        SKB_TRY(skb_branch_table(Pk, 3, 0, prm->spacing_is_int, prm->spacing_f, prm->spacing_i, nullptr, nullptr, indptr, skel,
+        SKB_TRY(skb_branch_table(Pk, 3, height, prm->spacing_is_int, prm->spacing_f, prm->spacing_i, nullptr, nullptr, indptr, skel,
                                  coords, values, head_aux, start_node, id_shift, prm->global_shape, t32, t64, tf, s));
     res->off[SKB_SO_PLEN] = out_off(plen);
     res->off[SKB_SO_PIDX] = out_off(pidx);

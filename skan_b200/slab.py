@@ -45,7 +45,7 @@ import torch.distributed as dist
 
 from . import _native, _pipeline
 
-AUX_BYTES = 48
+AUX_BYTES = 64
 
 # optional host timeline (bench.py --timeline): list of (label, perf_counter) appended at the points
 # where the host has just waited for the device or for a collective
@@ -253,7 +253,8 @@ def _world_rank(group):
     return got[0], got[1]
 
 
-def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, group, pack_variant, halo_exchange=False):
+def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, group, pack_variant, halo_exchange=False,
+                 value_is_height=False):
     """skeleton_and_summary_slab through skb_run_slab: the whole per-rank sequence in one native call."""
     import ctypes
     world, rank = _world_rank(group)
@@ -262,6 +263,11 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
     if len(shape) != 3:
         raise ValueError('slab mode is for 3-D volumes')
     is_bool = np_dtype == np.dtype(bool)
+    if value_is_height and is_bool:
+        raise TypeError('value_is_height needs a numeric (non-boolean) skeleton image')
+    if value_is_height and np_dtype.kind == 'u':
+        raise ValueError('value_is_height with an unsigned integer image wraps the height differences '
+                         '(reference csr.py:1024); cast the image to a signed or floating dtype')
     sp_arr = np.asarray(spacing)
     wkey = (str(ctx.device), id(ctx.lib), sp_arr.dtype.str, tuple(np.atleast_1d(sp_arr).tolist()))
     if wkey not in _wtabs:
@@ -280,6 +286,7 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         prm.halo_exchange = 1
         prm.ze0 = int(z0) - (2 if z0 > 0 else 0)
         prm.nz_ext = (int(z1) + (2 if z1 < int(global_shape[0]) else 0)) - prm.ze0
+    prm.height = int(bool(value_is_height))
     prm.want_values, prm.time_sweep = int(not is_bool), int(TIME_SWEEP)   # 0, 1 (sweep kernel) or 2 (device section clock)
     prm.wtab, prm.spacing_is_int, prm.stream = _wtabs[wkey].data_ptr(), int(sp_is_int), ctx.stream
     V = int(prm.nz_ext) * int(shape[1]) * int(shape[2])
@@ -339,7 +346,7 @@ def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, grou
         C['dev_us'] = {k: int(res.dev_ns[i]) / 1e3 for i, k in enumerate(_native.SLAB_SECTIONS)}
     if C['paths_total'] == 0:
         raise ValueError('index pointer size 0 should be 1')
-    return _SlabResult(ctx, out, res.off, C, rank, world, tuple(shape), np_dtype, img, sp_is_int)
+    return _SlabResult(ctx, out, res.off, C, rank, world, tuple(shape), np_dtype, img, sp_is_int, int(prm.height))
 
 
 class _SlabGraph:
@@ -363,7 +370,7 @@ class _SlabResult:
     first read: a caller that only looks at the branch table does not pay for the rest (the interpreter time between
     two volumes is GPU idle time)."""
 
-    def __init__(self, ctx, out, off, C, rank, world, shape, np_dtype, img, sp_is_int):
+    def __init__(self, ctx, out, off, C, rank, world, shape, np_dtype, img, sp_is_int, height=0):
         Ne, E, Pk, L = C['nodes_ext'], C['edges_ext'], C['regular'] + C['cycles'], C['entries_total']
         Pk1 = max(Pk, 1)
         i32, i64, f64 = torch.int32, torch.int64, torch.float64
@@ -377,11 +384,11 @@ class _SlabResult:
             'pw': (int(off[O['pw']]), L, f64, None), 'dist': (int(off[O['dist']]), Pk, f64, None),
             'mean': (int(off[O['mean']]), Pk, f64, None), 'stdev': (int(off[O['stdev']]), Pk, f64, None),
             't32': (int(off[O['t32']]), 3 * Pk, i32, (3, Pk)), 't64': (int(off[O['t64']]), 7 * Pk, i64, (7, Pk)),
-            'tf': (int(off[O['tf']]), 7 * Pk, f64, (7, Pk)),
+            'tf': (int(off[O['tf']]), (7 + 2 * height) * Pk, f64, (7 + 2 * height, Pk)),
         }
         self._v = v = _pipeline._ArenaViews(out, spec)
         self.graph = _SlabGraph(v, ctx, shape, np_dtype, Ne, E, (img, out))
-        self.rank, self.world, self.counts, self.spacing_is_int = rank, world, C, sp_is_int
+        self.rank, self.world, self.counts, self.spacing_is_int, self.value_is_height = rank, world, C, sp_is_int, bool(height)
         self.own = (C['own0'], C['own1'])
         self.id_shift = C['id_shift']
         self.n_nodes = C['own1'] - C['own0']
@@ -404,7 +411,7 @@ class _SlabResult:
 
 
 def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spacing=1, device=None, group=None,
-                              pack_variant=None, halo='input'):
+                              pack_variant=None, halo='input', value_is_height=False):
     """Skeleton + summarize of one Z-slab of a 3-D volume, collectively over the process group.
 
     halo='input' (default): slab_image = planes [ze0, ze0 + slab_image.shape[0]) of the volume (owned planes
@@ -412,6 +419,9 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spa
     halo='exchange': slab_image = the owned planes [z0, z1) only, a disjoint partition of the volume; the ranks
     exchange the packed mask of their two boundary planes through the peer-mapped exchange arenas (NVLink),
     1 bit per voxel (boolean volumes whose planes are a multiple of 16384 voxels; native runner only).
+    value_is_height (Skeleton's argument, csr.py:148-151, 932-948; numeric images, halo='input', native runner): edge
+    weights are hypot(height difference, distance) and the pixel value is an extra coordinate of the branch table; the
+    value of a path's far end travels with the ranking records like its coordinates do.
     Returns a namespace with this rank's share of the results (device tensors):
     graph rows of the owned nodes with global column ids, global path arrays holding the entries
     of this rank's voxels, and the branch table of the paths whose first node is owned here.
@@ -424,6 +434,8 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spa
     if halo not in ('input', 'exchange'):
         raise ValueError("halo must be 'input' or 'exchange'")
     if halo == 'exchange':
+        if value_is_height:
+            raise NotImplementedError("value_is_height needs the pixel values of the halo planes: use halo='input'")
         if int(slab_image.shape[0]) != z1 - z0:
             raise ValueError("halo='exchange' takes the owned planes [z0, z1) only")
         if not (NATIVE and _single_node(group) and world <= 16):
@@ -453,7 +465,9 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spa
         device = _default_device()
     if NATIVE and _single_node(group) and world <= 16:
         return _slab_native(slab_image, global_shape=global_shape, z0=z0, z1=z1, ze0=ze0, spacing=spacing,
-                            device=device, group=group, pack_variant=pack_variant)
+                            device=device, group=group, pack_variant=pack_variant, value_is_height=value_is_height)
+    if value_is_height:
+        raise NotImplementedError('value_is_height in slab mode needs the native runner (all ranks on one node)')
     # ---- voxel and node stages on the extended slab ---------------------------------------------
     Vloc = (ze1 - ze0) * sz
     p_own0, p_own1 = (z0 - ze0) * sz, (z1 - ze0) * sz

@@ -66,10 +66,10 @@ def assemble(parts, world):
     return out
 
 
-def compare_with_oracle(img, spacing, glob):
+def compare_with_oracle(img, spacing, glob, height=False):
     from oracle import skan_oracle as orc
-    ref = orc.OracleSkeleton(img, spacing=spacing)
-    rs = orc.summarize(ref)
+    ref = orc.OracleSkeleton(img, spacing=spacing, value_is_height=height)
+    rs = orc.summarize(ref, value_is_height=bool(height))
     assert np.array_equal(glob['indptr'], ref.graph.indptr), 'graph.indptr'
     assert np.array_equal(glob['indices'], ref.graph.indices), 'graph.indices'
     assert np.array_equal(glob['data'], ref.graph.data), 'graph.data'
@@ -83,12 +83,14 @@ def compare_with_oracle(img, spacing, glob):
     cols = {'skeleton_id': glob['o32'][0], 'node_id_src': glob['o32'][1], 'node_id_dst': glob['o32'][2],
             'branch_distance': glob['dist'], 'branch_type': glob['o64'][0], 'mean_pixel_value': glob['mean'],
             'stdev_pixel_value': glob['stdev']}
+    dh = d + int(bool(height))   # value_is_height: the pixel value is one more coordinate (csr.py:932-948)
     for i in range(d):
         cols[f'image_coord_src_{i}'] = glob['o64'][1 + i]
         cols[f'image_coord_dst_{i}'] = glob['o64'][1 + d + i]
+    for i in range(dh):
         cols[f'coord_src_{i}'] = glob['of'][i]
-        cols[f'coord_dst_{i}'] = glob['of'][d + i]
-    cols['euclidean_distance'] = glob['of'][2 * d]
+        cols[f'coord_dst_{i}'] = glob['of'][dh + i]
+    cols['euclidean_distance'] = glob['of'][2 * dh]
     for k, want in rs.items():
         got = cols[k]
         want = np.asarray(want)
@@ -102,7 +104,8 @@ def compare_with_oracle(img, spacing, glob):
     return ref
 
 
-def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate, native=1, small=0, xhalo=0, prime=0, guard=0):
+def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, emulate, native=1, small=0, xhalo=0, prime=0, guard=0,
+        height=0):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group(backend, rank=rank, world_size=world)
     try:
@@ -151,7 +154,7 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
                                                      spacing=spacing, device=dev, halo='exchange')
             else:
                 res = slab.skeleton_and_summary_slab(torch.from_numpy(part).to(dev), global_shape=shape, z0=z0, z1=z1,
-                                                     ze0=ze0, spacing=spacing, device=dev)
+                                                     ze0=ze0, spacing=spacing, device=dev, value_is_height=bool(height))
             if guard:
                 if dev.type == 'cuda':
                     torch.cuda.synchronize()
@@ -172,9 +175,9 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
         dist.gather_object(share, gathered, dst=0)
         if rank == 0:
             glob = assemble(gathered, world)
-            ref = compare_with_oracle(img, spacing, glob)
+            ref = compare_with_oracle(img, spacing, glob, height=bool(height))
             from oracle import skan_oracle as orc
-            want = digest.digest_oracle(ref, orc.summarize(ref))
+            want = digest.digest_oracle(ref, orc.summarize(ref, value_is_height=bool(height)))
             assert digest.same(dg, want), f'digest of the slab run differs from the oracle\'s: {dg} != {want}'
             print(f'SLAB-OK world={world} kind={kind} shape={shape} nodes={ref.graph.shape[0]} paths={ref.n_paths} '
                   f'cycles={sum(g["meta"]["n_cycles"] for g in gathered)} table={gathered[0]["meta"]["n_table"]} '
@@ -199,8 +202,10 @@ if __name__ == '__main__':
     ap.add_argument('--halo-exchange', type=int, default=0)
     ap.add_argument('--prime', type=int, default=0)
     ap.add_argument('--guard', type=int, default=0)
+    ap.add_argument('--height', type=int, default=0, help='value_is_height (needs --valued 1)')
     a = ap.parse_args()
     shape = tuple(int(x) for x in a.shape.split(','))
     spacing = tuple(float(x) for x in a.spacing.split(','))
     run(int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['MASTER_PORT']), a.kind, shape, a.seed,
-        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate), a.native, a.small_arenas, a.halo_exchange, a.prime, a.guard)
+        spacing, a.halo, bool(a.valued), a.backend, bool(a.emulate), a.native, a.small_arenas, a.halo_exchange, a.prime, a.guard,
+        a.height)

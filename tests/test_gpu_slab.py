@@ -26,6 +26,9 @@ CASES = [
     # tiny first arenas: every rank gives the call up at a different point, while its peers wait in a device-side barrier
     # (the abort word ends the waits, the guarded kernels are skipped, the read-back reports it, everybody goes again)
     ['--kind', 'walks', '--shape', '96,64,64', '--halo', '2', '--seed', '13', '--small-arenas', '1'],
+    # value_is_height: hypot edge weights (graph, junction MST, paths), the far end's pixel value travels with the ranking
+    ['--kind', 'walks', '--shape', '96,64,64', '--halo', '2', '--seed', '14', '--valued', '1', '--height', '1'],
+    ['--kind', 'dense12', '--shape', '64,32,32', '--halo', '2', '--seed', '6', '--valued', '1', '--height', '1'],
 ]
 
 

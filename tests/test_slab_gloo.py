@@ -57,6 +57,21 @@ def test_slab_mode_python_sequencing_matches_oracle(world, args):
     assert 'SLAB-OK' in outs[0] and 'native=0' in outs[0]
 
 
+@pytest.mark.parametrize('world,args', [
+    (2, ['--kind', 'walks', '--shape', '24,20,28', '--halo', '2', '--valued', '1', '--height', '1']),
+    (3, ['--kind', 'walks', '--shape', '48,32,32', '--halo', '5', '--seed', '7', '--valued', '1', '--height', '1']),
+    (3, ['--kind', 'rings', '--shape', '48,22,30', '--halo', '3', '--valued', '1', '--height', '1']),
+    (2, ['--kind', 'dense12', '--shape', '32,16,16', '--halo', '2', '--seed', '4', '--valued', '1', '--height', '1']),
+])
+def test_value_is_height_in_slab_mode(world, args):
+    """Skeleton(value_is_height=True) (csr.py:148-151, 932-948): edge weights hypot(height difference, distance) in the
+    graph, in the junction MST (weights travel with the gathered edges) and along the paths; the pixel value of a
+    path's far end travels with the ranking records and enters euclidean_distance as an extra coordinate."""
+    codes, outs = launch(world, *args)
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'native=1' in outs[0]
+
+
 def test_native_runner_is_the_default():
     codes, outs = launch(2, '--kind', 'walks', '--shape', '24,20,28', '--halo', '2', '--seed', '3')
     assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
