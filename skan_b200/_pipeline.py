@@ -476,10 +476,14 @@ class _ArenaViews:
     """Typed views into the output arena, created on first access."""
 
     def __init__(self, arena, spec):
+        # spec: {name: (byte offset, count, dtype, shape or None)}, or a callable that builds it on first access (the
+        # interpreter time between two images is GPU idle time: a caller that reads two columns pays for two views)
         self._arena, self._spec = arena, spec
 
     def __getattr__(self, name):
         spec = self.__dict__['_spec']
+        if callable(spec):
+            spec = self.__dict__['_spec'] = spec()
         if name not in spec:
             raise AttributeError(name)
         off, count, dtype, shape = spec[name]
@@ -575,22 +579,26 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
     cache['shape'], cache['nodes'], cache['counts'] = kind, C['nodes'], C
     if prm.time_sweep == 2:
         C['stage_ns'] = {k: int(res.stage_ns[i]) for i, k in enumerate(_native.RUN_STAGES)}
-    O = {k: int(res.off[i]) for k, i in _native.RUN_OFF.items()}
     N, E, P, L = C['nodes'], C['edges'], C['paths'], C['entries']
     h = int(bool(value_is_height))
     dh = tdim + h
-    i32, i64, f64 = torch.int32, torch.int64, torch.float64
-    spec = {
-        'lin': (O['lin'], N, i64, None), 'coords': (O['coords'], N * ndim, i64, (N, ndim)),
-        'values': (O['values'], N, f64, None), 'degrees': (O['degrees'], N, i32, None),
-        'indptr': (O['indptr'], N + 1, i32, None), 'indices': (O['indices'], E, i32, None),
-        'data': (O['data'], E, f64, None), 'comp_rank': (O['comp_rank'], N + 1, i32, None),
-        'pindptr': (O['pindptr'], P + 1, i32, None), 'pidx': (O['pidx'], L, i32, None),
-        'pdata': (O['pdata'], L, f64, None), 'pw': (O['pw'], L, f64, None), 'skel': (O['skel'], P, i32, None),
-        'dist': (O['dist'], P, f64, None), 'mean': (O['mean'], P, f64, None), 'stdev': (O['stdev'], P, f64, None),
-        't32': (O['t32'], 3 * P, i32, (3, P)), 't64': (O['t64'], (1 + 2 * tdim) * P, i64, (1 + 2 * tdim, P)),
-        'tf': (O['tf'], (2 * dh + 1) * P, f64, (2 * dh + 1, P)),
-    }
+    off = res.off
+
+    def spec():
+        O = {k: int(off[i]) for k, i in _native.RUN_OFF.items()}
+        i32, i64, f64 = torch.int32, torch.int64, torch.float64
+        return {
+            'lin': (O['lin'], N, i64, None), 'coords': (O['coords'], N * ndim, i64, (N, ndim)),
+            'values': (O['values'], N, f64, None), 'degrees': (O['degrees'], N, i32, None),
+            'indptr': (O['indptr'], N + 1, i32, None), 'indices': (O['indices'], E, i32, None),
+            'data': (O['data'], E, f64, None), 'comp_rank': (O['comp_rank'], N + 1, i32, None),
+            'pindptr': (O['pindptr'], P + 1, i32, None), 'pidx': (O['pidx'], L, i32, None),
+            'pdata': (O['pdata'], L, f64, None), 'pw': (O['pw'], L, f64, None), 'skel': (O['skel'], P, i32, None),
+            'dist': (O['dist'], P, f64, None), 'mean': (O['mean'], P, f64, None), 'stdev': (O['stdev'], P, f64, None),
+            't32': (O['t32'], 3 * P, i32, (3, P)), 't64': (O['t64'], (1 + 2 * tdim) * P, i64, (1 + 2 * tdim, P)),
+            'tf': (O['tf'], (2 * dh + 1) * P, f64, (2 * dh + 1, P)),
+        }
+
     v = _ArenaViews(out, spec)
     g = _GraphView(v, ctx, tuple(shape), ndim, np_dtype, code, spacing, bool(value_is_height), V, N, E,
                    C['junction_edges'], img)
