@@ -45,9 +45,15 @@ int skb_set_option(const char* name, int64_t value); /* tunables with no effect 
                                                         3 below 2.5 M nodes per GPU, else 4; every rank of a Z-slab
                                                         run must use the same value), "small_cycles", "junction_append",
                                                         "mst_keys", "mst_blocks_per_sm", "emit_blocks_per_sm" (A/B
-                                                        switches of round 2), "arena_guard" (debugging
+                                                        switches of round 2), "pdl" (1, default: kernels
+                                                        are launched with programmatic stream serialisation; also
+                                                        SKAN_B200_PDL=0 in the environment), "arena_guard" (debugging
                                                         aid, see skb_debug_guard_offsets).  The
-                                                        defaults were measured on B200 (profiles/r02_summary.md) */
+                                                        defaults were measured on B200 (profiles/r02_summary.md).
+                                                        One option does change fp64 rounding: "long_path_exact" (0,
+                                                        default: the statistics of a path of more than 32768 entries
+                                                        are summed by a thread block in a fixed tree order; 1: by one
+                                                        thread in the reference's order, bit-exact, O(longest path)) */
 /* Debugging aid: after skb_set_option("arena_guard", 1) the runners leave a 256-byte gap behind every allocation they make
  * in the caller's arenas; this returns the number of gaps of the calling thread's last runner call and writes their byte
  * offsets (which = 0: work arena, 1: out arena).  A caller that filled the arenas with a pattern finds out-of-bounds writes
