@@ -141,8 +141,8 @@ RUN_OFF = {n: i for i, n in enumerate(
      'dist', 'mean', 'stdev', 't32', 't64', 'tf', 'comp_rank'])}
 RUN_COUNT = {n: i for i, n in enumerate(
     ['nodes', 'edges', 'paths', 'regular', 'cycles', 'entries', 'junction_edges', 'starts', 'syncs', 'sweep_ns',
-     'overlapped', 'retaken'])}
-RUN_HINTS = ['junction_edges', 'edges', 'starts', 'regular']   # skb_run_params.hint[i] sizes by the count named
+     'overlapped', 'retaken', 'junction_nodes'])}
+RUN_HINTS = ['junction_edges', 'edges', 'starts', 'regular', 'junction_nodes']   # skb_run_params.hint[i] sizes by the count named
 
 RUN_STAGES = ['start', 'sweep', 'nodes', 'raw_stencil', 'junction_count', 'junction_mst', 'degrees', 'csr_records',
               'walk', 'rank', 'select', 'heads', 'emit', 'cycles', 'skeleton_ids', 'stats', 'table']

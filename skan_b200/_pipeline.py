@@ -549,6 +549,8 @@ def run_native(image, *, spacing=1, value_is_height=False, device, pack_variant=
     prm.node_cap_hint = _hint(last['nodes']) if last else 0
     for i, name in enumerate(_native.RUN_HINTS):
         prm.hint[i] = _hint(last[name]) if last else 0
+        if name == 'junction_nodes' and last and last[name] == 0:
+            prm.hint[i] = 0   # not counted yet (the previous image went without hints): arrays indexed by node id
     V = int(np.prod(shape, dtype=np.int64))
     if cache['work'] is None:
         cache['work'] = ctx.empty(max(1 << 22, V // 4 + (1 << 22)), torch.uint8)

@@ -1565,7 +1565,15 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_keys_coop_kernel(
     const int32_t* ea, const int32_t* eb, const uint8_t* ek, const double* wtab, int64_t nej_arg, const int32_t* nej_ptr,
     int64_t nej_cap, int32_t* par,
     unsigned long long* best /* [2][n_ids] */, int64_t n_ids, int32_t* era, int32_t* erb, uint8_t* tree,
-    int32_t* flags /* [3]: two flags + rounds */, uint32_t* keep, int32_t id_shift, int32_t n_local) {
+    int32_t* flags /* [3]: two flags + rounds */, uint32_t* keep, int32_t id_shift, int32_t n_local,
+    const int32_t* jid, int32_t* eda, int32_t* edb, const int32_t* j_ptr) {
+    // jid != NULL: par / best are indexed by DENSE ids of the junction voxels (jid[node], assigned by
+    // skb_junction_append_kernel; *j_ptr of them, n_ids = the capacity of the arrays) instead of node ids.  On an image
+    // with many junction clusters (30 M nodes, 2.65 M junction edges: a stack of 2-D images) the node-indexed arrays span
+    // 600 MB and every find / atomic is a DRAM sector; the dense ones stay in L2.
+    // more junction voxels than the arrays hold: nothing is done (the host reads the same count and goes the other way);
+    // the same decision in every thread of the grid -- nobody writes the count during this launch -- before the first barrier
+    if (jid && (int64_t)*j_ptr > n_ids) return;
     cg::grid_group grid = cg::this_grid();
     __shared__ uint32_t s_rank[27];
     // the number of edges: a launch argument, or (edges appended with an atomic counter, count still on its way to the
@@ -1597,9 +1605,16 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_keys_coop_kernel(
             continue;
         }
         era[e] = 0;
-        par[a] = a;
-        par[b] = b;
-        best0[a] = best0[b] = best1[a] = best1[b] = ~0ull;
+        int32_t xa = a, xb = b;
+        if (jid) {
+            xa = jid[a];
+            xb = jid[b];
+            eda[e] = xa;
+            edb[e] = xb;
+        }
+        par[xa] = xa;
+        par[xb] = xb;
+        best0[xa] = best0[xb] = best1[xa] = best1[xb] = ~0ull;
     }
     if (first) flags[0] = flags[1] = 0;
     __syncthreads();
@@ -1611,7 +1626,7 @@ __global__ void __launch_bounds__(SKB_COOP_THREADS) skb_mst_keys_coop_kernel(
         int32_t* f = flags + (round & 1);
         SKB_GRID_FOR(e, nej) {
             if (era[e] == -2) continue;  // already inside one component
-            const int32_t ra = skb_find(par, ea[e]), rb = skb_find(par, eb[e]);
+            const int32_t ra = skb_find(par, jid ? eda[e] : ea[e]), rb = skb_find(par, jid ? edb[e] : eb[e]);
             if (ra == rb) {
                 era[e] = -2;
                 continue;
@@ -1710,6 +1725,8 @@ static int g_skb_emit_blocks_per_sm = 16;  // measured at 2048^3: 5 -> 0.314, 8 
 static int g_skb_arena_guard = 0;  // "arena_guard": guard gaps between the runners' allocations (skb_run.inl)
 static int g_skb_small_cycles = 1;  // "small_cycles": 0 = always the general machinery for junction-free cycles
 static int g_skb_mst_keys = 1;  // "mst_keys": 0 = the two-phase rounds also for table weights (A/B)
+static int64_t g_skb_dense_mst_min_nodes = 12000000;  // "dense_mst_min_nodes": dense junction ids for the Boruvka arrays above
+                                                       // this many nodes (skb_run.inl; tests set 0 to force them)
 // "long_path_exact": 1 = paths of any length are summed by one thread in the reference's order (bit-exact, O(longest
 // path) time); 0 (default) = paths of more than SKB_LONG_PATH entries by one thread block in a fixed tree order
 static int32_t g_skb_long_path = SKB_LONG_PATH;
@@ -1738,13 +1755,27 @@ static int skb_mst_run(const int32_t* ea, const int32_t* eb, const uint64_t* ew,
 }
 
 // nej_ptr != NULL: the edge count is read on the device (at most nej edges, the capacity of the arrays)
+// dense ids of the junction voxels (single-image runner): see skb_mst_keys_coop_kernel
+struct SkbDense {
+    int32_t* jid;       // [n nodes], written for every node of raw degree >= 3 by skb_junction_append_kernel
+    int32_t* jcounter;  // device: their number
+    int32_t* eda;       // [edge capacity] dense ids of every edge's two ends
+    int32_t* edb;
+    int64_t j_cap;      // capacity of par / best
+};
 static int skb_mst_keys_run(const int32_t* ea, const int32_t* eb, const uint8_t* ek, const double* wtab, int64_t nej,
                             const int32_t* nej_ptr, int32_t* par, unsigned long long* best, int64_t n_ids, int32_t* era,
                             int32_t* erb, uint8_t* tree, int32_t* flag, uint32_t* keep, int32_t id_shift, int32_t n_local,
-                            skb_stream_t s) {
+                            skb_stream_t s, const SkbDense* dense = nullptr) {
     int64_t nej_cap = nej;
+    if (dense && !dense->jid) dense = nullptr;  // (junction voxels counted only: arrays indexed by node id)
+    const int32_t* jid = dense ? dense->jid : nullptr;
+    int32_t* eda = dense ? dense->eda : nullptr;
+    int32_t* edb = dense ? dense->edb : nullptr;
+    const int32_t* j_ptr = dense ? dense->jcounter : nullptr;
+    if (dense) n_ids = dense->j_cap;
     void* args[] = {&ea, &eb, &ek, &wtab, &nej, &nej_ptr, &nej_cap, &par, &best, &n_ids, &era, &erb, &tree, &flag, &keep,
-                    &id_shift, &n_local};
+                    &id_shift, &n_local, &jid, &eda, &edb, &j_ptr};
     return skb_coop_launch(skb_mst_keys_coop_kernel, nej, args, s, g_skb_mst_blocks_per_sm);
 }
 
@@ -1758,40 +1789,83 @@ __global__ void __launch_bounds__(256) skb_junction_append_kernel(SkbGeom g, con
                                                                   const uint32_t* __restrict__ nb, int64_t n,
                                                                   int64_t a0, int64_t a1, int32_t* __restrict__ ea,
                                                                   int32_t* __restrict__ eb, uint8_t* __restrict__ ek,
-                                                                  uint32_t cap, int32_t* counter, const int32_t* n_ptr) {
+                                                                  uint32_t cap, int32_t* counter, const int32_t* n_ptr,
+                                                                  int32_t* __restrict__ jid, int32_t* jcounter) {
+    // jid != NULL: every node of raw degree >= 3 also receives a dense id (jid[node]; *jcounter of them, in no
+    // particular order: one atomic per thread block), by which the Boruvka launch indexes its arrays
     if (n_ptr) {  // the node count in device memory (at most n, the capacity of the node arrays)
         const int64_t nd = *n_ptr;
         if (nd < n) n = nd;
         if (a1 > n) a1 = n;
     }
+    // Only one node in ~12 has raw degree >= 3, and such a node tests 1-3 forward neighbours, each a chain of three
+    // dependent loads (block prefix, mask words, the neighbour's raw mask).  Done by the node's own lane, a warp waited for
+    // its busiest lane while 29 others idled (ncu, round 2: 14 of 32 lanes active, 0.117 ms at 2048^3, the neighbour lists
+    // in local memory).  Here the (node, direction) pairs of a warp are dealt out to its lanes, one pair per lane and round;
+    // accepted neighbours are parked in shared memory under their owner, who writes them out after the block's one atomic.
     __shared__ uint32_t warp_tot[8];
-    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_base, s_jbase;
+    __shared__ int32_t s_u[13][256];   // neighbour ids by (direction - 14, owner thread)
+    __shared__ uint32_t s_acc[256];    // accepted directions of every owner
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t stride = (int64_t)gridDim.x * 256;
     const int64_t n_round = (n + 255) / 256 * 256;
     for (int64_t base = (int64_t)blockIdx.x * 256; base < n_round; base += stride) {
         const int64_t i = base + tid;
-        int32_t us[13];
-        uint8_t ks[13];
-        uint32_t cnt = 0;
+        uint32_t fm = 0;   // forward directions (k27 >= 14) to test
+        int64_t r = 0;
+        uint32_t isj = 0;  // raw degree >= 3 (dense ids)
         if (i < n && i >= a0 && i < a1) {  // [a0, a1): the nodes whose forward edges this call emits (a Z-slab's own nodes)
             const uint32_t m = nb[i];
-            if (__popc(m) >= 3 && (m >> 14)) {
-                uint32_t fm = m & ~((1u << 14) - 1u);
-                const int64_t r = lin[i];
-                while (fm) {
-                    const int k = __ffs((int)fm) - 1;
-                    fm &= fm - 1u;
-                    const int32_t u = k == 14 ? (int32_t)i + 1 : skb_rank(bits, pre256, skb_neighbor_lin(g, r, k));
-                    if (__popc(nb[u]) >= 3) {
-                        us[cnt] = u;
-                        ks[cnt] = (uint8_t)k;
-                        ++cnt;
-                    }
+            if (__popc(m) >= 3) {
+                isj = 1u;
+                if (m >> 14) {
+                    fm = m & ~((1u << 14) - 1u);
+                    r = lin[i];
                 }
             }
         }
-        uint32_t inc = cnt;
+        s_acc[tid] = 0u;
+        const uint32_t nf = (uint32_t)__popc(fm);
+        uint32_t pinc = nf;  // inclusive prefix of the pair counts over the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, pinc, d);
+            if (lane >= d) pinc += o;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, pinc, 31);
+        __syncwarp();
+        for (uint32_t t0 = 0; t0 < total; t0 += 32) {   // the same trip count in every lane of the warp
+            const uint32_t t = t0 + lane;
+            // owner = first lane whose inclusive prefix exceeds t
+            int owner = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, pinc, owner + step - 1);
+                if (v <= t) owner += step;
+            }
+            owner &= 31;
+            const uint32_t o_inc = __shfl_sync(0xffffffffu, pinc, owner);
+            const uint32_t o_fm = __shfl_sync(0xffffffffu, fm, owner);
+            const long long o_r = __shfl_sync(0xffffffffu, (long long)r, owner);
+            if (t < total) {
+                uint32_t skip = t - (o_inc - (uint32_t)__popc(o_fm));  // the pair's place among the owner's directions
+                uint32_t w = o_fm;
+                for (; skip; --skip) w &= w - 1u;
+                const int k = __ffs((int)w) - 1;
+                const int64_t oi = base + (int64_t)(warp * 32 + owner);
+                const int32_t u = k == 14 ? (int32_t)oi + 1 : skb_rank(bits, pre256, skb_neighbor_lin(g, (int64_t)o_r, k));
+                if (__popc(nb[u]) >= 3) {
+                    s_u[k - 14][warp * 32 + owner] = u;
+                    atomicOr(&s_acc[warp * 32 + owner], 1u << k);
+                }
+            }
+        }
+        __syncwarp();
+        const uint32_t acc = s_acc[tid];
+        const uint32_t cnt = (uint32_t)__popc(acc);
+        // one scan for both counts: edges in the low 16 bits (a warp holds at most 416), junction voxels above
+        uint32_t inc = cnt | (isj << 16);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
@@ -1800,22 +1874,26 @@ __global__ void __launch_bounds__(256) skb_junction_append_kernel(SkbGeom g, con
         if (lane == 31) warp_tot[warp] = inc;
         __syncthreads();
         if (tid == 0) {
-            uint32_t t = 0;
+            uint32_t t = 0, tj = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const uint32_t c = warp_tot[w];
-                warp_tot[w] = t;
-                t += c;
+                warp_tot[w] = t | (tj << 16);
+                t += c & 0xffffu;
+                tj += c >> 16;
             }
             s_base = t ? (uint32_t)atomicAdd(counter, (int32_t)t) : 0u;
+            s_jbase = (jcounter && tj) ? (uint32_t)atomicAdd(jcounter, (int32_t)tj) : 0u;  // (jid NULL: counted only)
         }
         __syncthreads();
-        uint32_t o = s_base + warp_tot[warp] + inc - cnt;
-        for (uint32_t j = 0; j < cnt; ++j, ++o) {
+        if (jid && isj) jid[i] = (int32_t)(s_jbase + (warp_tot[warp] >> 16) + (inc >> 16) - 1u);
+        uint32_t o = s_base + (warp_tot[warp] & 0xffffu) + (inc & 0xffffu) - cnt;
+        for (uint32_t am = acc; am; am &= am - 1u, ++o) {   // ascending directions = ascending neighbour ids, as before
+            const int k = __ffs((int)am) - 1;
             if (o < cap) {
                 ea[o] = (int32_t)i;
-                eb[o] = us[j];
-                ek[o] = ks[j];
+                eb[o] = s_u[k - 14][tid];
+                ek[o] = (uint8_t)k;
             }
         }
         __syncthreads();
@@ -1826,7 +1904,8 @@ static int g_skb_junction_append = 1;  // "junction_append": 0 = always count + 
 // returns 0, or 1 when the one-pass form does not apply (the caller counts, scans and emits)
 static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
                                const uint32_t* nb, int64_t n, int64_t a0, int64_t a1, int32_t* ea, int32_t* eb, uint8_t* ek,
-                               int64_t cap, int32_t* counter, skb_stream_t s, const int32_t* n_ptr = nullptr);
+                               int64_t cap, int32_t* counter, skb_stream_t s, const int32_t* n_ptr = nullptr,
+                               const SkbDense* dense = nullptr);
 
 
 static int skb_rank_run(skb_i4* b0, skb_i4* b1, SkbAux* a0, SkbAux* a1, int64_t n, int32_t lo, int32_t hi,
@@ -2314,15 +2393,17 @@ static int skb_long_path_stats(const int32_t* pindptr, const double* pdata, cons
 
 static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int ndim, const int64_t* shape, const int64_t* lin,
                                const uint32_t* nb, int64_t n, int64_t a0, int64_t a1, int32_t* ea, int32_t* eb, uint8_t* ek,
-                               int64_t cap, int32_t* counter, skb_stream_t s, const int32_t* n_ptr) {
+                               int64_t cap, int32_t* counter, skb_stream_t s, const int32_t* n_ptr, const SkbDense* dense) {
     if (!g_skb_junction_append || !g_skb_mst_keys || n <= 0 || cap <= 0) return 1;  // the keyed Boruvka needs no edge order
     SKB_TRY(skb_check_geom(ndim, shape));
     SKB_TRY(skb_fill_bytes(counter, 0, 4, s));
+    if (dense) SKB_TRY(skb_fill_bytes(dense->jcounter, 0, 4, s));
     int64_t blocks = (n + 255) / 256;
     const int64_t max_blocks = (int64_t)skb_sm_count() * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     skb_junction_append_kernel<<<(unsigned)blocks, 256, 0, s>>>(skb_make_geom(ndim, shape), bits, pre256, lin, nb, n, a0, a1, ea, eb,
-                                                                ek, cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap, counter, n_ptr);
+                                                                ek, cap > 0xffffffffLL ? 0xffffffffu : (uint32_t)cap, counter, n_ptr,
+                                                                dense ? dense->jid : nullptr, dense ? dense->jcounter : nullptr);
     SKB_COUNT_LAUNCH(1);
     return skb_cuda_check(cudaGetLastError(), "junction append launch");
 }
@@ -2373,6 +2454,11 @@ int skb_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "mst_keys")) {
         g_skb_mst_keys = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "dense_mst_min_nodes")) {
+        if (value < 0) return skb_fail("skb_set_option: dense_mst_min_nodes must be >= 0");
+        g_skb_dense_mst_min_nodes = value;
         return 0;
     }
     if (!strcmp(name, "pdl")) {

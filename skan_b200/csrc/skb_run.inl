@@ -24,11 +24,11 @@ enum {
 // indices into skb_run_result.counts
 enum {
     SKB_C_NODES = 0, SKB_C_EDGES, SKB_C_PATHS, SKB_C_REGULAR, SKB_C_CYCLES, SKB_C_ENTRIES, SKB_C_JUNCTION_EDGES,
-    SKB_C_STARTS, SKB_C_SYNCS, SKB_C_SWEEP_NS, SKB_C_OVERLAPPED, SKB_C_RETAKEN, SKB_C_COUNT
+    SKB_C_STARTS, SKB_C_SYNCS, SKB_C_SWEEP_NS, SKB_C_OVERLAPPED, SKB_C_RETAKEN, SKB_C_JUNCTION_NODES, SKB_C_COUNT
 };
 // indices into skb_run_params.hint: capacities for the arrays sized by a count that is still on its way to the
 // host when their first consumer is launched (0 = no hint: wait for the count, then launch)
-enum { SKB_H_JUNCTION_EDGES = 0, SKB_H_EDGES, SKB_H_STARTS, SKB_H_REGULAR, SKB_H_COUNT };
+enum { SKB_H_JUNCTION_EDGES = 0, SKB_H_EDGES, SKB_H_STARTS, SKB_H_REGULAR, SKB_H_JUNCTION_NODES, SKB_H_COUNT };
 // stage boundaries of skb_run_result.stage_ns (time_sweep == 2): stage_ns[i] = device time between
 // the previous boundary and boundary i, host synchronisation bubbles included
 enum {
@@ -325,16 +325,30 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
     uint64_t* ew = nullptr;
     int32_t *mpar = nullptr, *era = nullptr, *erb = nullptr;
     uint64_t* bestw = nullptr;
-    auto take_junction = [&](int64_t cap) {
+    int64_t n_junction_nodes = 0;
+#ifdef SKB_HAVE_FUSED_LOOPS
+    SkbDense dense{};  // dense ids of the junction voxels for the Boruvka arrays (capacity hint: their number last time)
+#endif
+    auto take_junction = [&](int64_t cap, int64_t jcap) {
         ea = work.take<int32_t>(cap);
         eb = work.take<int32_t>(cap);
         ek = work.take<uint8_t>(cap);
         ew = work.take<uint64_t>(cap);
-        mpar = work.take<int32_t>(N);
-        bestw = work.take<uint64_t>(2 * N);
+        mpar = work.take<int32_t>(jcap > 0 ? jcap : N);
+        bestw = work.take<uint64_t>(2 * (jcap > 0 ? jcap : N));
         era = work.take<int32_t>(cap);
         erb = work.take<int32_t>(cap);
         tree = work.take<uint8_t>(cap);
+#ifdef SKB_HAVE_FUSED_LOOPS
+        dense = SkbDense{};
+        dense.jcounter = n_dev + 2;  // the junction voxels are counted in any case: the next image's capacity hint
+        if (jcap > 0) {
+            dense.jid = work.take<int32_t>(N);
+            dense.eda = work.take<int32_t>(cap);
+            dense.edb = work.take<int32_t>(cap);
+            dense.j_cap = jcap;
+        }
+#endif
     };
     {
         const int64_t cap = prm->hint[SKB_H_JUNCTION_EDGES] > 0 ? prm->hint[SKB_H_JUNCTION_EDGES] : 0;
@@ -343,24 +357,45 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         if (cap > 0 && !height) {
             // one pass, no order (skb_junction_append_kernel): the edges are appended with an atomic counter, and the
             // Boruvka launch reads their number from that counter while it travels to the host
-            take_junction(cap);
+#ifdef SKB_HAVE_FUSED_LOOPS
+            // dense ids for the Boruvka arrays pay when the node-indexed arrays (20 bytes per node) are far larger than L2:
+            // measured (round 2) -0.16 ms at 30 M nodes / 2.65 M junction edges, +-0.01 ms at 0.8-7.5 M nodes
+            const int64_t jcap = (prm->hint[SKB_H_JUNCTION_NODES] > 0 && N > g_skb_dense_mst_min_nodes) ? prm->hint[SKB_H_JUNCTION_NODES] : 0;
+            take_junction(cap, jcap);
             if (work.ok) {
-                int r = skb_junction_append(bits, pre256, ndim, prm->shape, lin, nb, N, 0, N, ea, eb, ek, cap, flag + 3, s);
+                int r = skb_junction_append(bits, pre256, ndim, prm->shape, lin, nb, N, 0, N, ea, eb, ek, cap, flag + 3, s, nullptr,
+                                            &dense);
                 if (r < 0) return r;
                 appended = r == 0;
             }
             if (appended) {
-                SKB_POST(flag + 3);
+                const int32_t* ptrs[2] = {flag + 3, n_dev + 2};
+                SKB_TRY(skb_fetch_post(ptrs, 2, s));
                 SKB_TRY(skb_mst_keys_run(ea, eb, ek, prm->wtab, cap, flag + 3, mpar, (unsigned long long*)bestw, N, era, erb,
-                                         tree, flag, keep, 0, (int32_t)N, s));
+                                         tree, flag, keep, 0, (int32_t)N, s, &dense));
                 ++noverlap;
-                SKB_WAIT(nej);
+                int64_t got[2] = {0, 0};
+                SKB_TRY(skb_fetch_wait(2, got, s));
+                ++nsync;
+                if (got[0] < 0 || got[1] < 0) return skb_fail("a count exceeds int32: the reference's int32 index arrays cannot hold this graph");
+                nej = got[0];
+                n_junction_nodes = got[1];
                 if (nej > cap) {  // the capacity was too small: the masks are half-edited, so the stencil runs again
                     appended = false;
                     ++nretaken;
                     SKB_TRY(skb_raw_neighbors(bits, ndim, prm->shape, lin, N, prm->image_stack, nb, s));
+                } else if (jcap > 0 && n_junction_nodes > jcap) {
+                    // more junction voxels than the dense arrays hold: the launch did nothing (masks and edges are intact);
+                    // once more with arrays indexed by node id
+                    ++nretaken;
+                    mpar = work.take<int32_t>(N);
+                    bestw = work.take<uint64_t>(2 * N);
+                    SKB_NEED(work.ok);
+                    SKB_TRY(skb_mst_keys_run(ea, eb, ek, prm->wtab, nej, nullptr, mpar, (unsigned long long*)bestw, N, era, erb,
+                                             tree, flag, keep, 0, (int32_t)N, s, nullptr));
                 }
             }
+#endif
             if (!appended) {
                 work.off = work_mark;
                 work.ok = true;
@@ -372,7 +407,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
             SKB_MARK(SKB_M_JCOUNT);
             SKB_POST(jcount + N);
             if (cap > 0) {  // edge emission sized by the hint runs while the count travels
-                take_junction(cap);
+                take_junction(cap, 0);
                 if (work.ok) {
                     SKB_TRY(skb_junction_edge_emit_cap(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values,
                                                        height, prm->dtype, ea, eb, ek, ew, cap, s));
@@ -385,7 +420,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
                 if (emitted) ++nretaken;
                 work.off = work_mark;
                 work.ok = true;
-                take_junction(nej);
+                take_junction(nej, 0);
                 SKB_NEED(work.ok);
                 SKB_TRY(skb_junction_edge_emit(bits, pre256, ndim, prm->shape, lin, nb, jcount, N, prm->wtab, values, height,
                                                prm->dtype, ea, eb, ek, ew, s));
@@ -399,6 +434,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         }
     }
     res->counts[SKB_C_JUNCTION_EDGES] = nej;
+    res->counts[SKB_C_JUNCTION_NODES] = n_junction_nodes;
     SKB_MARK(SKB_M_MST);
     // ---- CSR + node records ------------------------------------------------------------------------------
     int32_t* deg = out.take<int32_t>(N);

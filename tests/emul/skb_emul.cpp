@@ -214,6 +214,7 @@ static uint32_t skb_option_split_shift(int64_t population = 0) {
 }
 static int g_skb_both_ways = 1;
 static int g_skb_arena_guard = 0;
+static int64_t g_skb_dense_mst_min_nodes = 12000000;
 static int skb_option_both_ways() { return g_skb_both_ways; }
 // the single-block handling of small junction-free cycles is a CUDA kernel: the harness always runs the general path
 static int skb_cycles_small(const skb_i4*, const uint8_t*, int64_t, int64_t, const double*, int64_t, int32_t*, uint32_t*,
@@ -231,7 +232,8 @@ static int skb_cycles_small_entries(const skb_i4*, int64_t, const double*, int64
 }
 // one-pass junction edge emission and the packed-key Boruvka launch are CUDA kernels: the harness counts, scans, emits
 static int skb_junction_append(const uint64_t*, const uint32_t*, int, const int64_t*, const int64_t*, const uint32_t*, int64_t,
-                               int64_t, int64_t, int32_t*, int32_t*, uint8_t*, int64_t, int32_t*, skb_stream_t) {
+                               int64_t, int64_t, int32_t*, int32_t*, uint8_t*, int64_t, int32_t*, skb_stream_t,
+                               const int32_t* = nullptr) {
     return 1;
 }
 static int skb_mst_keys_run(const int32_t*, const int32_t*, const uint8_t*, const double*, int64_t, const int32_t*, int32_t*,

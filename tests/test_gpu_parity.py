@@ -86,6 +86,37 @@ def test_dense_blobs_vs_oracle(seed, pack_variant):
     compare_with_oracle(img, spacing)
 
 
+@pytest.mark.parametrize('seed', range(4))
+def test_dense_junction_ids_vs_oracle(seed):
+    """The Boruvka arrays indexed by dense ids of the junction voxels (the runner's choice above 12 M nodes; forced here):
+    the same image three times -- without hints, with hints but the junction voxels not counted yet, then with dense ids --
+    and once more after a much sparser image, whose count of junction voxels is too small a capacity (the launch does
+    nothing, the runner goes again with node-indexed arrays).  Every run is compared with the oracle."""
+    lib = skan_b200._native.library()
+    rng = np.random.default_rng(2100 + seed)
+    shape = [(200, 300), (40, 40, 40), (512, 64), (24, 48, 96)][seed]
+    spacing = [1, (0.5, 0.1, 0.1), (2.0, 1.0), 1][seed]
+    img = rng.random(shape) < [0.5, 0.3, 0.42, 0.2][seed]
+    sparse = img & (rng.random(shape) < 0.5)
+    from skan_b200 import _pipeline
+    slack, _pipeline.HINT_SLACK = _pipeline.HINT_SLACK, 1
+    lib.call('skb_set_option', b'dense_mst_min_nodes', 0)
+    try:
+        _pipeline._arena_cache.clear()
+        for k in range(3):
+            compare_with_oracle(img, spacing)
+        (cache,) = [c for c in _pipeline._arena_cache.values() if c.get('counts')][-1:]
+        assert cache['counts']['junction_nodes'] > 0 and cache['counts']['retaken'] == 0
+        for k in range(3):
+            compare_with_oracle(sparse, spacing)
+        compare_with_oracle(img, spacing)       # hints of the sparse image: too small, also for the junction voxels
+        (cache,) = [c for c in _pipeline._arena_cache.values() if c.get('counts')][-1:]
+        assert cache['counts']['retaken'] >= 1
+    finally:
+        lib.call('skb_set_option', b'dense_mst_min_nodes', 12000000)
+        _pipeline.HINT_SLACK = slack
+
+
 @pytest.mark.parametrize('dt', [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.uint64, np.int64,
                                 np.float32, np.float64])
 def test_valued_images_vs_oracle(dt, pack_variant):
