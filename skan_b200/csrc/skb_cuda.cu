@@ -2397,7 +2397,7 @@ static int skb_junction_append(const uint64_t* bits, const uint32_t* pre256, int
     if (!g_skb_junction_append || !g_skb_mst_keys || n <= 0 || cap <= 0) return 1;  // the keyed Boruvka needs no edge order
     SKB_TRY(skb_check_geom(ndim, shape));
     SKB_TRY(skb_fill_bytes(counter, 0, 4, s));
-    if (dense) SKB_TRY(skb_fill_bytes(dense->jcounter, 0, 4, s));
+    if (dense && dense->jcounter) SKB_TRY(skb_fill_bytes(dense->jcounter, 0, 4, s));
     int64_t blocks = (n + 255) / 256;
     const int64_t max_blocks = (int64_t)skb_sm_count() * 16;
     if (blocks > max_blocks) blocks = max_blocks;

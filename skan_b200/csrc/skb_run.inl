@@ -341,7 +341,9 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
         tree = work.take<uint8_t>(cap);
 #ifdef SKB_HAVE_FUSED_LOOPS
         dense = SkbDense{};
-        dense.jcounter = n_dev + 2;  // the junction voxels are counted in any case: the next image's capacity hint
+        // the junction voxels are counted (the next image's capacity hint) only where dense ids can be used: the count
+        // costs every thread block of the append pass an atomic it otherwise needs only when it has edges
+        dense.jcounter = N > g_skb_dense_mst_min_nodes ? n_dev + 2 : nullptr;
         if (jcap > 0) {
             dense.jid = work.take<int32_t>(N);
             dense.eda = work.take<int32_t>(cap);
@@ -369,7 +371,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
                 appended = r == 0;
             }
             if (appended) {
-                const int32_t* ptrs[2] = {flag + 3, n_dev + 2};
+                const int32_t* ptrs[2] = {flag + 3, dense.jcounter ? dense.jcounter : flag + 3};
                 SKB_TRY(skb_fetch_post(ptrs, 2, s));
                 SKB_TRY(skb_mst_keys_run(ea, eb, ek, prm->wtab, cap, flag + 3, mpar, (unsigned long long*)bestw, N, era, erb,
                                          tree, flag, keep, 0, (int32_t)N, s, &dense));
@@ -379,7 +381,7 @@ extern "C" int skb_run_image(const skb_run_params* prm, skb_run_result* res) {
                 ++nsync;
                 if (got[0] < 0 || got[1] < 0) return skb_fail("a count exceeds int32: the reference's int32 index arrays cannot hold this graph");
                 nej = got[0];
-                n_junction_nodes = got[1];
+                n_junction_nodes = dense.jcounter ? got[1] : 0;
                 if (nej > cap) {  // the capacity was too small: the masks are half-edited, so the stencil runs again
                     appended = false;
                     ++nretaken;
