@@ -470,7 +470,12 @@ static int skb_fetch_i32(const int32_t* p, int32_t* host_out, skb_stream_t s) {
 // Exclusive scan with n+1 outputs (out[n] = total).  `in == out` is allowed: every block holds
 // its whole tile in registers before it writes.
 #define SKB_SCAN_THREADS 512
-#define SKB_SCAN_ITEMS 16  // 8192 items per tile: the look-back chain advances ~32 tiles per L2 round trip, so fewer, larger tiles
+#ifndef SKB_SCAN_ITEMS
+#define SKB_SCAN_ITEMS 16  // 8192 items per tile: the look-back chain advances one window of tiles per L2 round trip, so fewer, larger tiles
+#endif
+#ifndef SKB_SCAN_WIDE
+#define SKB_SCAN_WIDE 0    // 1: the look-back inspects 128 predecessors per round (4 per lane) instead of 32
+#endif
 #define SKB_SCAN_TILE (SKB_SCAN_THREADS * SKB_SCAN_ITEMS)
 
 template <typename T>
@@ -578,6 +583,49 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
         __stcg(status + tile, st);
         if (tile == 0) s_excl = 0;
     }
+#if SKB_SCAN_WIDE
+    if (tile > 0 && threadIdx.x < 32) {
+        // warp 0 looks back over the 128 nearest predecessors at a time: lane l holds look - 4 l - j, j = 0..3 (j = 0 the
+        // nearest).  The chain of inclusive prefixes advances one window per L2 round trip, so a wider window shortens it.
+        const int lane = threadIdx.x;
+        uint32_t excl = 0;
+        int64_t look = tile - 1;
+        for (;;) {
+            unsigned long long st[4];
+            bool ready;
+            do {
+                ready = true;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t idx = look - 4 * lane - j;
+                    st[j] = idx >= 0 ? skb_poll_u64(status + idx) : (tag | (SKB_ST_INCLUSIVE << 32));
+                    ready = ready && (st[j] >> 34) == epoch && ((st[j] >> 32) & 3ull) != 0ull;
+                }
+            } while (__any_sync(0xffffffffu, !ready));
+            uint32_t lsum = 0;
+            bool linc = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!linc) {
+                    lsum += (uint32_t)(st[j] & 0xffffffffull);
+                    linc = ((st[j] >> 32) & 3ull) == SKB_ST_INCLUSIVE;
+                }
+            }
+            const unsigned incl = __ballot_sync(0xffffffffu, linc);
+            const int stop = incl ? (__ffs((int)incl) - 1) : 31;
+            uint32_t val = lane <= stop ? lsum : 0u;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+            excl += val;
+            if (incl) break;
+            look -= 128;
+        }
+        if (lane == 0) {
+            __stcg(status + tile, tag | (SKB_ST_INCLUSIVE << 32) | (unsigned long long)(excl + total));
+            s_excl = excl;
+        }
+    }
+#else
     if (tile > 0 && threadIdx.x < 32) {
         // warp 0 looks back over the 32 nearest predecessors at a time
         const int lane = threadIdx.x;
@@ -603,6 +651,7 @@ __global__ void __launch_bounds__(SKB_SCAN_THREADS) skb_scan_lookback_kernel(con
             s_excl = excl;
         }
     }
+#endif
     __syncthreads();
     ex += s_excl;
     if (vec) {

@@ -65,3 +65,16 @@ def test_package_has_no_cpu_fallback():
         pytest.skip('a CUDA device is present')
     with pytest.raises(_native.NativeError):
         skan_b200.Skeleton(np.eye(5, dtype=bool))
+
+
+def test_numa_placement_never_raises():
+    """skan_b200/_numa.py is an optimisation of the end-to-end leg: without NVML / a GPU it reports that nothing was bound."""
+    import os
+    from skan_b200._numa import bind_thread_to_gpu
+    before = os.sched_getaffinity(0)
+    info = bind_thread_to_gpu(0)
+    assert set(info) >= {'bound', 'cpus', 'numa_node'}
+    if not info['bound']:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
