@@ -186,7 +186,7 @@ def graph_nodes(image, *, spacing=1, value_is_height=False, device, pack_variant
         vals = tile_prefix.index_select(0, idx).tolist()
         N, g.position_ranks = vals[0], vals[1:]
     else:
-        N = int(tile_prefix[ntiles].item())
+        N = _count(tile_prefix[ntiles], 'nodes')
     g.n_nodes = N
     g.bits = bits
     g._bits_store = store
@@ -225,7 +225,7 @@ def junction_edge_counts(g, a0=0, a1=None):
     jcount = ctx.empty(N + 1, torch.int32)
     ctx.call('skb_junction_edge_count', g.bits, g.pre256, *g.geom, g.lin, g.raw_nb, N, a0, a1, jcount)
     ctx.call('skb_scan_u32', jcount, jcount, N, ctx.scratch(N))
-    return jcount, int(jcount[N].item())
+    return jcount, _count(jcount[N], 'junction edges')
 
 
 def junction_edge_emit(g, jcount, ea, eb, ek, ew):
@@ -277,7 +277,7 @@ def graph_csr(g, ea, eb, ek, tree, id_shift=0, records=True, slab=None, cc_init=
     deg = ctx.empty(N, torch.int32)
     indptr = ctx.empty(N + 1, torch.int32)
     ctx.call('skb_degrees_indptr', keep, N, deg, indptr, ctx.scratch(N))
-    E = int(indptr[N].item())
+    E = _count(indptr[N], 'half-edges')
     indices = ctx.empty(E, torch.int32)
     data = ctx.empty(E, torch.float64)
     rec = startoff = par = cmin = is_min = None
@@ -333,7 +333,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None,
         else:
             startoff = ctx.empty(N + 1, torch.int32)
             ctx.call('skb_path_start_count', rec, covered, None, N, startoff, ctx.scratch(N))
-        S = int(startoff[N].item())
+        S = _count(startoff[N], 'walk starts')
         if S == 0:
             return None
         su = ctx.empty(S, torch.int32)
@@ -373,7 +373,7 @@ def trace_paths(ctx, indptr, indices, gdata, values, n_nodes, n_edges, lin=None,
     if n_regular:
         heads(a, start_node, plen, pmin)
         ctx.call('skb_scan_u32', plen, pindptr, n_regular, ctx.scratch(n_regular))
-        L_reg = int(pindptr[n_regular].item())
+        L_reg = _count(pindptr[n_regular], 'path entries')
     n_uncovered = max(0, E // 2 - (L_reg - n_regular))
     L_cap = L_reg + n_uncovered + n_uncovered // 3 + 1
     pidx = ctx.empty(L_cap, torch.int32)
@@ -461,6 +461,16 @@ USE_HINTS = True    # pass the previous image's counts (+ slack) as capacity hin
 
 
 HINT_SLACK = 4096   # entries added to every hint on top of 1/16 of the previous count
+
+
+def _count(t, what):
+    """A count read back from the last element of a scanned int32 array.  The reference's index arrays are int32
+    (csr.py:206-216): a graph whose node, half-edge or entry count does not fit comes back negative here, and is refused
+    instead of being used as an allocation size."""
+    v = int(t.item())
+    if v < 0:
+        raise OverflowError(f'the number of {what} exceeds int32: the reference\'s int32 index arrays cannot hold this graph')
+    return v
 
 
 def _hint(count):
