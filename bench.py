@@ -629,15 +629,20 @@ def main():
     shape, spacing, is_stack, ms = m['shape'], m['spacing'], m['is_stack'], m['ms']
     img, step = m['img'], m['step']
 
-    if args.timeline and world > 1 and slab.NATIVE and not is_stack:
+    # ---- N > 1: section clock of the slab runner (one extra step, not part of any reported number): device time of
+    # every section of rank 0 goes into the JSON line (what limits the scaling is read from it), --timeline prints the
+    # host clock of every rank as well
+    sections = None
+    if world > 1 and slab.NATIVE and not is_stack:
         sync_all()
         slab.TIME_SWEEP = 2
         r = step()
         torch.cuda.synchronize()
         slab.TIME_SWEEP = False
         tl = [None] * world
-        dist.all_gather_object(tl, (r.counts['host_us'], r.counts['dev_us']))
-        if rank == 0:
+        dist.all_gather_object(tl, (r.counts.get('host_us', {}), r.counts.get('dev_us', {})))
+        sections = {k: round(max(t[1].get(k, 0.0) for t in tl) / 1e3, 4) for k in r.counts.get('dev_us', {})}
+        if rank == 0 and args.timeline:
             for k, v in r.counts['host_us'].items():
                 print(f'  [host timeline, rank 0] {k:24s} +{v / 1e3:7.3f} ms   device {r.counts["dev_us"][k] / 1e3:7.3f} ms   '
                       f'(host, all ranks: ' + ' '.join(f'{t[0][k] / 1e3:.3f}' for t in tl) + ')', file=sys.stderr)
@@ -735,6 +740,8 @@ def main():
                        'pack_variant': _pipeline.default_pack_variant, **m['counts']},
             'roofline': m['roofline'], 'clocks': m['clocks'], 'gpu_launches': int(m['launches']),
             'e2e': e2e}
+    if sections:   # device ms per section of the slab runner, max over ranks (one extra, untimed step)
+        line['slab_sections_ms'] = sections
     if m['cold_ms'] is not None:
         line['cold_image_ms'] = m['cold_ms']
     if parity is not None or m['full_digest'] is not None:
