@@ -319,15 +319,40 @@ class Skeleton:
         return _to_host(out).reshape(shape)
 
     def prune_paths(self, indices):
-        """csr.py:818-854 re-skeletonizes with scikit-image after wiping the paths; thinning is
-        outside this package's scope."""
+        """Prune paths from the skeleton (csr.py:818-854): the non-junction pixels of the given paths are wiped from a copy
+        of the skeleton image, the image is re-skeletonized and a new Skeleton is built from it.  The re-thinning is the
+        reference's own call of ``skimage.morphology.skeletonize`` on the host (pre-processing, outside the hot path:
+        SURVEY.md section 8 (f5)); where scikit-image is not installed this raises NotImplementedError after the
+        reference's index check."""
         if not np.all(np.array(indices) < self.n_paths):
             raise ValueError(
                 f'The path index {np.max(indices)} does not exist in this '
                 f'skeleton. (The highest path index is {self.n_paths}.)\n'
                 'If you obtained the index from a summary table, you '
                 'probably need to resummarize the skeleton.')
-        raise NotImplementedError('prune_paths needs skimage.morphology.skeletonize (out of scope)')
+        try:
+            from skimage import morphology
+        except ImportError:
+            raise NotImplementedError('prune_paths needs skimage.morphology.skeletonize (scikit-image is not installed; '
+                                      'the thinning is out of this package\'s scope)') from None
+        if self.skeleton_image is None:
+            raise ValueError('prune_paths needs the skeleton image (Skeleton(..., keep_images=True))')
+        image = self.skeleton_image
+        if isinstance(image, torch.Tensor):   # the reference's images are NumPy arrays; ours may live on a device
+            image = image.detach().cpu().numpy()
+        image_cp = np.copy(image)
+        degrees = self.degrees
+        coordinates = self.coordinates
+        for i in indices:
+            pixel_ids_to_wipe = self.path(i)
+            junctions = degrees[pixel_ids_to_wipe] > 2
+            pixel_ids_to_wipe = pixel_ids_to_wipe[~junctions]
+            coords_to_wipe = coordinates[pixel_ids_to_wipe]
+            coords_idxs = tuple(np.round(coords_to_wipe).astype(int).T)
+            image_cp[coords_idxs] = 0
+        new_skeleton = morphology.skeletonize(image_cp.astype(bool)) * image_cp
+        return Skeleton(new_skeleton, spacing=self.spacing, source_image=self.source_image,
+                        keep_images=self.keep_images)
 
     def __array__(self, dtype=None):
         """Array representation of the skeleton path labels (csr.py:856-858)."""

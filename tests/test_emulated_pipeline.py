@@ -155,3 +155,38 @@ def test_skeleton_to_csgraph_contract():
     assert g.indices.tolist() == [1, 2, 0, 3, 0, 3, 1, 2]
     assert np.all(g.data == np.sqrt(2))
     assert np.ravel_multi_index(coords, (3, 3)).tolist() == [1, 3, 5, 7]
+
+
+def test_prune_paths_like_the_reference(monkeypatch):
+    """Skeleton.prune_paths (csr.py:818-854): wipe the non-junction pixels of the paths, re-skeletonize on the host with
+    scikit-image, build a new Skeleton.  scikit-image is not in this image: without it the call raises
+    NotImplementedError after the reference's index check; with a stand-in whose skeletonize is the identity (true for
+    an image that is still one pixel wide after the wipe) the result is the skeleton of the wiped image."""
+    import sys
+    import types
+    img = case('tinycycle')['image'].copy().astype(bool)
+    img = np.pad(img, 3)
+    img[3, 6:9] = True                                    # a spur hanging off the ring
+    with emulated_device():
+        sk = skan_b200.Skeleton(img)
+        with pytest.raises(ValueError):
+            sk.prune_paths([sk.n_paths])
+        monkeypatch.setitem(sys.modules, 'skimage', None)  # import skimage -> ImportError
+        with pytest.raises(NotImplementedError):
+            sk.prune_paths([0])
+        fake = types.ModuleType('skimage')
+        fake.morphology = types.ModuleType('skimage.morphology')
+        fake.morphology.skeletonize = lambda a: np.asarray(a, bool)
+        monkeypatch.setitem(sys.modules, 'skimage', fake)
+        monkeypatch.setitem(sys.modules, 'skimage.morphology', fake.morphology)
+        spur = [i for i in range(sk.n_paths) if np.any(sk.degrees[sk.path(i)] == 1)]
+        assert len(spur) == 1
+        pruned = sk.prune_paths(spur)
+        wiped = img.copy()
+        ids = sk.path(spur[0])
+        keep = sk.degrees[ids] > 2
+        wiped[tuple(sk.coordinates[ids[~keep]].T)] = False
+        ref = orc.OracleSkeleton(wiped)
+        assert np.array_equal(pruned.graph.indices, ref.graph.indices)
+        assert np.array_equal(pruned.paths.indices, ref.paths.indices)
+        assert pruned.n_paths == ref.n_paths
