@@ -240,17 +240,12 @@ def _close_comm(key):
             pass
 
 
-_group_facts = {}
-
-
 def _world_rank(group):
-    """(world size, rank) of a process group; looked up once per group (each query costs microseconds of GPU idle time)"""
-    key = id(group) if group is not None else 0
-    got = _group_facts.get(key)
-    if got is None or got[2] is not (group if group is not None else dist.group.WORLD):
-        g = group if group is not None else dist.group.WORLD
-        got = _group_facts[key] = (dist.get_world_size(group), dist.get_rank(group), g)
-    return got[0], got[1]
+    """(world size, rank) of a process group.  Asked every time (a few microseconds): remembering the group object in a
+    module global keeps it alive into interpreter shutdown, where its destructor races the backend's threads
+    ("terminate called without an active exception" in one rank of a finished run), and remembering only its identity
+    goes stale when a group is destroyed and another one created."""
+    return dist.get_world_size(group), dist.get_rank(group)
 
 
 def _slab_native(slab_image, *, global_shape, z0, z1, ze0, spacing, device, group, pack_variant, halo_exchange=False,
