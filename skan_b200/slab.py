@@ -405,16 +405,47 @@ class _SlabResult:
     table = property(lambda self: (self._v.t32, self._v.t64, self._v.tf))
 
 
+def _exchange_image_halo(slab_image, z0, z1, NZ, device, group):
+    """Owned planes [z0, z1) of rank k -> (extended slab with two planes of either neighbour, its first plane).
+    Ranks are ordered along Z (rank k-1 holds the planes below z0, rank k+1 those from z1 on), as everywhere in this
+    module; the planes travel as bytes through torch.distributed point-to-point operations (NCCL on GPUs, gloo on the
+    CPU), so every image dtype is served."""
+    world, rank = _world_rank(group)
+    t = slab_image if isinstance(slab_image, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(slab_image))
+    t = t.to(device).contiguous()
+    dt = t.dtype
+    nz, NY, NX = (int(x) for x in t.shape)
+    b = t.reshape(nz, -1).view(torch.uint8)
+    has_lo, has_hi = z0 > 0 and rank > 0, z1 < NZ and rank + 1 < world
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    lo = torch.empty((2, b.shape[1]), dtype=torch.uint8, device=b.device) if has_lo else None
+    hi = torch.empty((2, b.shape[1]), dtype=torch.uint8, device=b.device) if has_hi else None
+    ops = []
+    if has_lo:
+        ops += [dist.P2POp(dist.isend, b[:2].contiguous(), peer(rank - 1), group),
+                dist.P2POp(dist.irecv, lo, peer(rank - 1), group)]
+    if has_hi:
+        ops += [dist.P2POp(dist.isend, b[-2:].contiguous(), peer(rank + 1), group),
+                dist.P2POp(dist.irecv, hi, peer(rank + 1), group)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    ext = torch.cat([x for x in (lo, b, hi) if x is not None]).view(dt).reshape(-1, NY, NX)
+    return ext, z0 - (2 if has_lo else 0)
+
+
 def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spacing=1, device=None, group=None,
                               pack_variant=None, halo='input', value_is_height=False):
     """Skeleton + summarize of one Z-slab of a 3-D volume, collectively over the process group.
 
     halo='input' (default): slab_image = planes [ze0, ze0 + slab_image.shape[0]) of the volume (owned planes
     [z0, z1) plus at least two halo planes towards every neighbour): the caller partitions with overlap.
-    halo='exchange': slab_image = the owned planes [z0, z1) only, a disjoint partition of the volume; the ranks
-    exchange the packed mask of their two boundary planes through the peer-mapped exchange arenas (NVLink),
-    1 bit per voxel (boolean volumes whose planes are a multiple of 16384 voxels; native runner only).
-    value_is_height (Skeleton's argument, csr.py:148-151, 932-948; numeric images, halo='input', native runner): edge
+    halo='exchange': slab_image = the owned planes [z0, z1) only, a disjoint partition of the volume.  For boolean
+    volumes whose planes are a multiple of 16384 voxels (native runner) the ranks exchange the packed mask of their two
+    boundary planes through the peer-mapped exchange arenas (NVLink), 1 bit per voxel; otherwise (valued images,
+    value_is_height, other plane sizes, several nodes) the two boundary planes of the image travel through the process
+    group and the extended slab goes the halo='input' way.
+    value_is_height (Skeleton's argument, csr.py:148-151, 932-948; numeric images, native runner): edge
     weights are hypot(height difference, distance) and the pixel value is an extra coordinate of the branch table; the
     value of a path's far end travels with the ranking records like its coordinates do.
     Returns a namespace with this rank's share of the results (device tensors):
@@ -429,12 +460,8 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spa
     if halo not in ('input', 'exchange'):
         raise ValueError("halo must be 'input' or 'exchange'")
     if halo == 'exchange':
-        if value_is_height:
-            raise NotImplementedError("value_is_height needs the pixel values of the halo planes: use halo='input'")
         if int(slab_image.shape[0]) != z1 - z0:
             raise ValueError("halo='exchange' takes the owned planes [z0, z1) only")
-        if not (NATIVE and _single_node(group) and world <= 16):
-            raise NotImplementedError("halo='exchange' needs the native runner (all ranks on one node)")
         if z1 - z0 < 2:
             raise ValueError('bad slab bounds (each rank needs at least two owned planes)')
         if device is None:
@@ -442,8 +469,17 @@ def skeleton_and_summary_slab(slab_image, *, global_shape, z0, z1, ze0=None, spa
         if device is None:
             from .csr import _default_device
             device = _default_device()
-        return _slab_native(slab_image, global_shape=global_shape, z0=z0, z1=z1, ze0=z0, spacing=spacing, device=device,
-                            group=group, pack_variant=pack_variant, halo_exchange=True)
+        is_bool = (slab_image.dtype == torch.bool) if isinstance(slab_image, torch.Tensor) else (np.asarray(slab_image).dtype == bool)
+        if (NATIVE and _single_node(group) and world <= 16 and is_bool and not value_is_height
+                and (NY * NX) % 16384 == 0):   # 16384 = voxels per mask tile (skb_tile_voxels)
+            # the packed mask of the boundary planes travels through the peer-mapped arenas inside the native runner
+            return _slab_native(slab_image, global_shape=global_shape, z0=z0, z1=z1, ze0=z0, spacing=spacing, device=device,
+                                group=group, pack_variant=pack_variant, halo_exchange=True)
+        # everything else (valued images, value_is_height, planes that are not whole mask tiles, ranks on several nodes):
+        # the two boundary planes of the IMAGE are exchanged with the neighbours through the process group, then the
+        # extended slab goes the halo='input' way
+        slab_image, ze0 = _exchange_image_halo(slab_image, z0, z1, NZ, device, group)
+        halo = 'input'
     if ze0 is None:
         raise ValueError("halo='input' needs ze0, the first plane of slab_image")
     ze1 = ze0 + int(slab_image.shape[0])

@@ -151,7 +151,8 @@ def run(rank, world, port, kind, shape, seed, spacing, halo, valued, backend, em
                     pass   # a volume without any path: every rank raises alike
             if xhalo:   # disjoint partition: the ranks exchange the packed mask of their boundary planes
                 res = slab.skeleton_and_summary_slab(torch.from_numpy(part).to(dev), global_shape=shape, z0=z0, z1=z1,
-                                                     spacing=spacing, device=dev, halo='exchange')
+                                                     spacing=spacing, device=dev, halo='exchange',
+                                                     value_is_height=bool(height))
             else:
                 res = slab.skeleton_and_summary_slab(torch.from_numpy(part).to(dev), global_shape=shape, z0=z0, z1=z1,
                                                      ze0=ze0, spacing=spacing, device=dev, value_is_height=bool(height))

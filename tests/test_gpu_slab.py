@@ -57,6 +57,9 @@ def test_slab_mode_native(world, args):
     ['--kind', 'dense12', '--shape', '48,64,256', '--seed', '6'],
     ['--kind', 'rings', '--shape', '64,128,128'],
     ['--kind', 'walks', '--shape', '64,128,128', '--seed', '4', '--small-arenas', '1'],
+    # not served by the packed-mask exchange of the native runner: the image's boundary planes go through the process group
+    ['--kind', 'walks', '--shape', '64,96,80', '--seed', '8', '--valued', '1'],
+    ['--kind', 'walks', '--shape', '64,96,80', '--seed', '9', '--valued', '1', '--height', '1'],
 ])
 def test_halo_exchange_from_a_disjoint_partition(world, args):
     """halo='exchange': owned planes only per rank, boundary planes of the packed mask exchanged over NVLink."""

@@ -72,6 +72,21 @@ def test_value_is_height_in_slab_mode(world, args):
     assert 'SLAB-OK' in outs[0] and 'native=1' in outs[0]
 
 
+@pytest.mark.parametrize('world,args', [
+    (2, ['--kind', 'walks', '--shape', '24,20,28', '--seed', '5']),                                  # planes of 560 voxels
+    (3, ['--kind', 'walks', '--shape', '48,32,32', '--seed', '7', '--valued', '1']),                 # valued image
+    (3, ['--kind', 'rings', '--shape', '48,22,30', '--valued', '1', '--height', '1']),               # value_is_height
+    (2, ['--kind', 'dense12', '--shape', '32,16,16', '--seed', '4', '--native', '0']),               # python sequencing
+])
+def test_halo_exchange_of_image_planes_through_the_process_group(world, args):
+    """halo='exchange' where the packed-mask exchange of the native runner does not apply (valued images, value_is_height,
+    planes that are not whole mask tiles, python sequencing): the two boundary planes of the image travel through
+    torch.distributed point-to-point operations, then the extended slab goes the halo='input' way."""
+    codes, outs = launch(world, *args, '--halo-exchange', '1')
+    assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
+    assert 'SLAB-OK' in outs[0] and 'xhalo=1' in outs[0]
+
+
 def test_native_runner_is_the_default():
     codes, outs = launch(2, '--kind', 'walks', '--shape', '24,20,28', '--halo', '2', '--seed', '3')
     assert all(c == 0 for c in codes), '\n'.join(o[-2000:] for o in outs)
